@@ -1,0 +1,323 @@
+"""boda_b200 -- Python (ctypes) face of libboda_b200.so, the B200-native back-end for Boda's rtc_fwd conv/SGEMM path.
+
+The product is the C-ABI shared library (include/boda_b200.h) and the C++ classes behind it (boda_b200/csrc):
+`b200_compute_t` mirrors Boda's `rtc_compute_t` (src/rtc_compute.H:35-97) and `b200_conv_fwd_t` mirrors
+`has_conv_fwd_t` (src/has_conv_fwd.H:16-25). This module only marshals numpy buffers and strings onto that ABI with
+the reference's method names, so tests read like the reference's own flows (ops-prof, test_compute).
+
+There is no CPU fallback: if the library is missing or no sm_100 device is present, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libboda_b200.so")
+_lib = None
+
+
+class RtException(RuntimeError):
+    """rt_exception (reference: rt_err, src/boda_base.H:98-105)."""
+
+
+class UnsupException(RtException):
+    """unsup_exception (reference: unsup_err): a shape / feature the back-end does not handle."""
+
+
+_c = ctypes
+_strp = _c.POINTER(_c.c_char_p)
+
+_SIGS = {
+    "b200_last_error": (_c.c_char_p, []),
+    "b200_version": (_c.c_char_p, []),
+    "b200_device_count": (_c.c_int, []),
+    "b200_rtc_create": (_c.c_void_p, []),
+    "b200_rtc_destroy": (None, [_c.c_void_p]),
+    "b200_rtc_set_option": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_char_p]),
+    "b200_rtc_init": (_c.c_int, [_c.c_void_p]),
+    "b200_rtc_get_plat_tag": (_c.c_char_p, [_c.c_void_p]),
+    "b200_rtc_create_var": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_char_p, _c.c_int, _strp, _c.POINTER(_c.c_uint32)]),
+    "b200_rtc_create_view": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_char_p, _c.c_int, _strp, _c.POINTER(_c.c_uint32), _c.c_char_p]),
+    "b200_rtc_release_var": (_c.c_int, [_c.c_void_p, _c.c_char_p]),
+    "b200_rtc_get_var_dims": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_int, _c.POINTER(_c.c_uint32), _c.c_char_p, _c.c_int]),
+    "b200_rtc_set_var_to_zero": (_c.c_int, [_c.c_void_p, _c.c_char_p]),
+    "b200_rtc_compile": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_char_p]),
+    "b200_rtc_release_func": (_c.c_int, [_c.c_void_p, _c.c_char_p]),
+    "b200_rtc_run": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_int, _strp, _strp]),
+    "b200_rtc_finish_and_sync": (_c.c_int, [_c.c_void_p]),
+    "b200_rtc_release_per_call_id_data": (_c.c_int, [_c.c_void_p]),
+    "b200_rtc_release_all_funcs": (_c.c_int, [_c.c_void_p]),
+    "b200_rtc_get_dur": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_uint32, _c.POINTER(_c.c_float)]),
+    "b200_rtc_copy_to_var": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_void_p, _c.c_uint64]),
+    "b200_rtc_copy_from_var": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_char_p, _c.c_uint64]),
+    "b200_rtc_get_var_raw_native_pointer": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.POINTER(_c.c_void_p)]),
+    "b200_rtc_launches": (_c.c_uint64, [_c.c_void_p]),
+    "b200_fwd_create": (_c.c_void_p, [_c.c_char_p, _c.c_char_p]),
+    "b200_fwd_destroy": (None, [_c.c_void_p]),
+    "b200_fwd_set_param": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_void_p, _c.c_uint64]),
+    "b200_fwd_run": (_c.c_int, [_c.c_void_p, _c.c_int, _strp, _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_uint64), _c.c_int, _strp,
+                                _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_uint64)]),
+    "b200_fwd_run_device_only": (_c.c_int, [_c.c_void_p, _c.c_int, _c.POINTER(_c.c_float)]),
+    "b200_fwd_set_det_drop_seed": (_c.c_int, [_c.c_void_p, _c.c_uint32]),
+    "b200_fwd_get_info_log": (_c.c_char_p, [_c.c_void_p]),
+    "b200_fwd_get_node_dims": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.POINTER(_c.c_uint32)]),
+    "b200_fwd_num_calls": (_c.c_int, [_c.c_void_p]),
+    "b200_fwd_launches": (_c.c_uint64, [_c.c_void_p]),
+    "b200_fwd_profile": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_char_p, _c.c_int, _c.POINTER(_c.c_float), _c.POINTER(_c.c_float), _c.POINTER(_c.c_double), _c.c_int]),
+    "b200_fwd_run_timed": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_uint64, _c.POINTER(_c.c_float)]),
+    "b200_fwd_get_node_raw_native_pointer": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.POINTER(_c.c_void_p)]),
+    "b200_rtc_get_kernel_dur": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.POINTER(_c.c_float)]),
+}
+ABI_SYMBOLS = tuple(_SIGS)
+
+
+def lib():
+    """Load libboda_b200.so (built in-tree by boda_b200/build.py or __graft_entry__.build()). Raises if absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RtException("libboda_b200.so is not built (%s); run `python -m boda_b200.build` -- there is no fallback path" % LIB_PATH)
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def _chk(rc: int) -> int:
+    if rc < 0:
+        msg = lib().b200_last_error().decode()
+        raise (UnsupException if rc == -2 else RtException)(msg)
+    return rc
+
+
+def _b(s: str) -> bytes:
+    return s.encode()
+
+
+def _str_array(items: Sequence[str]):
+    arr = (_c.c_char_p * len(items))(*[_b(i) for i in items])
+    return arr
+
+
+def device_count() -> int:
+    return int(lib().b200_device_count())
+
+
+Dims = Sequence[Tuple[str, int]]
+
+
+class B200Compute:
+    """`be=b200`: same methods as rtc_compute_t (src/rtc_compute.H:35-97); ndas are numpy arrays + named dims."""
+
+    def __init__(self, prec: str = "fp32", acc_chunk_kblks: Optional[int] = None, device: int = 0):
+        self._h = lib().b200_rtc_create()
+        if not self._h:
+            raise RtException(lib().b200_last_error().decode())
+        _chk(lib().b200_rtc_set_option(self._h, b"prec", _b(prec)))
+        _chk(lib().b200_rtc_set_option(self._h, b"device", _b(str(device))))
+        if acc_chunk_kblks is not None:
+            _chk(lib().b200_rtc_set_option(self._h, b"acc_chunk_kblks", _b(str(acc_chunk_kblks))))
+        self._dims: Dict[str, Dims] = {}
+
+    def close(self):
+        if self._h:
+            lib().b200_rtc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def init(self):
+        _chk(lib().b200_rtc_init(self._h))
+
+    def get_plat_tag(self) -> str:
+        return lib().b200_rtc_get_plat_tag(self._h).decode()
+
+    def create_var_with_dims(self, vn: str, dims: Dims, tn: str = "float"):
+        names = _str_array([d[0] for d in dims])
+        sizes = (_c.c_uint32 * len(dims))(*[int(d[1]) for d in dims])
+        _chk(lib().b200_rtc_create_var(self._h, _b(vn), _b(tn), len(dims), names, sizes))
+        self._dims[vn] = tuple(dims)
+
+    def create_var_with_dims_as_reshaped_view_of_var(self, vn: str, dims: Dims, src_vn: str, tn: str = "float"):
+        names = _str_array([d[0] for d in dims])
+        sizes = (_c.c_uint32 * len(dims))(*[int(d[1]) for d in dims])
+        _chk(lib().b200_rtc_create_view(self._h, _b(vn), _b(tn), len(dims), names, sizes, _b(src_vn)))
+        self._dims[vn] = tuple(dims)
+
+    def release_var(self, vn: str):
+        _chk(lib().b200_rtc_release_var(self._h, _b(vn)))
+        self._dims.pop(vn, None)
+
+    def get_var_dims(self, vn: str) -> List[Tuple[str, int]]:
+        sizes = (_c.c_uint32 * 8)()
+        buf = ctypes.create_string_buffer(256)
+        n = _chk(lib().b200_rtc_get_var_dims(self._h, _b(vn), 8, sizes, buf, 256))
+        names = buf.value.decode().split(":") if n else []
+        return [(names[i], int(sizes[i])) for i in range(n)]
+
+    def set_var_to_zero(self, vn: str):
+        _chk(lib().b200_rtc_set_var_to_zero(self._h, _b(vn)))
+
+    def compile(self, func_name: str, op_text: str):
+        """rtc_compute_t::compile for one rtc_func_info_t{func_name, op}."""
+        _chk(lib().b200_rtc_compile(self._h, _b(func_name), _b(op_text)))
+
+    def release_func(self, func_name: str):
+        _chk(lib().b200_rtc_release_func(self._h, _b(func_name)))
+
+    def release_all_funcs(self):
+        _chk(lib().b200_rtc_release_all_funcs(self._h))
+
+    def run(self, func_name: str, arg_map: Dict[str, object]) -> int:
+        """rtc_compute_t::run(rtc_func_call_t{func_name, arg_map}) -> call_id. Values: var name (str) or a scalar
+        (int -> uint32_t nda, float -> float nda) passed by value."""
+        names, vals = [], []
+        for k, v in arg_map.items():
+            names.append(k)
+            if isinstance(v, str):
+                vals.append(v)
+            elif isinstance(v, (int, np.integer)):
+                vals.append("(tn=uint32_t,v=%d)" % int(v))
+            else:
+                vals.append("(tn=float,v=%r)" % float(v))
+        return _chk(lib().b200_rtc_run(self._h, _b(func_name), len(names), _str_array(names), _str_array(vals)))
+
+    def finish_and_sync(self):
+        _chk(lib().b200_rtc_finish_and_sync(self._h))
+
+    def release_per_call_id_data(self):
+        _chk(lib().b200_rtc_release_per_call_id_data(self._h))
+
+    def get_kernel_dur(self, call_id: int) -> float:
+        ms = _c.c_float()
+        _chk(lib().b200_rtc_get_kernel_dur(self._h, call_id, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def get_dur(self, b: int, e: int) -> float:
+        ms = _c.c_float()
+        _chk(lib().b200_rtc_get_dur(self._h, b, e, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def copy_nda_to_var(self, vn: str, nda: np.ndarray):
+        a = np.ascontiguousarray(nda)
+        _chk(lib().b200_rtc_copy_to_var(self._h, _b(vn), a.ctypes.data_as(_c.c_void_p), a.nbytes))
+
+    def copy_var_to_nda(self, vn: str, dtype=np.float32) -> np.ndarray:
+        dims = self.get_var_dims(vn)
+        out = np.empty([d[1] for d in dims], dtype)
+        _chk(lib().b200_rtc_copy_from_var(self._h, out.ctypes.data_as(_c.c_void_p), _b(vn), out.nbytes))
+        return out
+
+    def create_var_from_nda(self, vn: str, nda: np.ndarray, dim_names: Sequence[str]):
+        self.create_var_with_dims(vn, list(zip(dim_names, nda.shape)))
+        self.copy_nda_to_var(vn, nda)
+
+    def get_var_raw_native_pointer(self, vn: str) -> int:
+        p = _c.c_void_p()
+        _chk(lib().b200_rtc_get_var_raw_native_pointer(self._h, _b(vn), ctypes.byref(p)))
+        return int(p.value or 0)
+
+    def launches(self) -> int:
+        return int(lib().b200_rtc_launches(self._h))
+
+
+class B200ConvFwd:
+    """`mode=b200`: has_conv_fwd_t (src/has_conv_fwd.H:16-25). `pipe_text` is the conv_pipe in op-line text form."""
+
+    def __init__(self, pipe_text: str, opts: str = ""):
+        self._h = lib().b200_fwd_create(_b(pipe_text), _b(opts))
+        if not self._h:
+            msg = lib().b200_last_error().decode()
+            raise (UnsupException if msg.startswith("unsupported") else RtException)(msg)
+
+    def close(self):
+        if self._h:
+            lib().b200_fwd_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def node_dims(self, name: str) -> Tuple[int, ...]:
+        d = (_c.c_uint32 * 4)()
+        n = _chk(lib().b200_fwd_get_node_dims(self._h, _b(name), d))
+        return tuple(int(d[i]) for i in range(n))
+
+    def set_param(self, name: str, arr: np.ndarray):
+        a = np.ascontiguousarray(arr, np.float32)
+        _chk(lib().b200_fwd_set_param(self._h, _b(name), a.ctypes.data_as(_c.c_void_p), a.size))
+
+    def run_fwd(self, to_set: Dict[str, np.ndarray], to_get: Sequence[str], out_bufs: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
+        """has_conv_fwd_t::run_fwd(to_set_vns, fwd, to_get_vns): host fp32 NCHW in, host out, synchronous."""
+        sn = list(to_set)
+        sa = [np.ascontiguousarray(to_set[k], np.float32) for k in sn]
+        outs = {}
+        for k in to_get:
+            outs[k] = out_bufs[k] if out_bufs and k in out_bufs else np.empty(self.node_dims(k), np.float32)
+        gn = list(to_get)
+        sp = (_c.c_void_p * len(sn))(*[a.ctypes.data for a in sa])
+        se = (_c.c_uint64 * len(sn))(*[a.size for a in sa])
+        gp = (_c.c_void_p * len(gn))(*[outs[k].ctypes.data for k in gn])
+        ge = (_c.c_uint64 * len(gn))(*[outs[k].size for k in gn])
+        _chk(lib().b200_fwd_run(self._h, len(sn), _str_array(sn), sp, se, len(gn), _str_array(gn), gp, ge))
+        return outs
+
+    def run_fwd_ptrs(self, set_names, set_ptrs, set_elems, get_names, get_ptrs, get_elems):
+        """Same call with raw host pointers (e.g. pinned torch tensors' data_ptr()) -- used by bench.py's e2e leg."""
+        sp = (_c.c_void_p * len(set_names))(*set_ptrs)
+        se = (_c.c_uint64 * len(set_names))(*set_elems)
+        gp = (_c.c_void_p * len(get_names))(*get_ptrs)
+        ge = (_c.c_uint64 * len(get_names))(*get_elems)
+        _chk(lib().b200_fwd_run(self._h, len(set_names), _str_array(set_names), sp, se, len(get_names), _str_array(get_names), gp, ge))
+
+    def run_device_only(self, iters: int) -> float:
+        ms = _c.c_float()
+        _chk(lib().b200_fwd_run_device_only(self._h, iters, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def set_det_drop_seed(self, seed: int):
+        _chk(lib().b200_fwd_set_det_drop_seed(self._h, seed))
+
+    def get_info_log(self) -> str:
+        return lib().b200_fwd_get_info_log(self._h).decode()
+
+    def num_calls(self) -> int:
+        return int(lib().b200_fwd_num_calls(self._h))
+
+    def launches(self) -> int:
+        return int(lib().b200_fwd_launches(self._h))
+
+    def profile(self, iters: int = 5) -> List[Tuple[str, float, float, float]]:
+        """[(func_name, call_ms, contraction_kernel_ms, algorithmic_flops)] per forward call, averaged over `iters` eager runs."""
+        n = self.num_calls()
+        buf = ctypes.create_string_buffer(1 << 16)
+        ms = (_c.c_float * max(n, 1))()
+        kms = (_c.c_float * max(n, 1))()
+        fl = (_c.c_double * max(n, 1))()
+        got = _chk(lib().b200_fwd_profile(self._h, iters, buf, len(buf), ms, kms, fl, n))
+        tags = buf.value.decode().split("\n") if got else []
+        return [(tags[i], float(ms[i]), float(kms[i]), float(fl[i])) for i in range(got)]
+
+    def run_timed(self, iters: int, l2_flush_bytes: int = 0) -> List[float]:
+        ms = (_c.c_float * max(iters, 1))()
+        _chk(lib().b200_fwd_run_timed(self._h, iters, l2_flush_bytes, ms))
+        return [float(ms[i]) for i in range(iters)]
+
+    def node_device_ptr(self, name: str) -> int:
+        p = _c.c_void_p()
+        _chk(lib().b200_fwd_get_node_raw_native_pointer(self._h, _b(name), ctypes.byref(p)))
+        return int(p.value or 0)

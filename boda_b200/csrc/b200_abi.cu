@@ -1,0 +1,171 @@
+// b200_abi.cu -- extern "C" surface declared in include/boda_b200.h. No exceptions cross this boundary.
+#include "../../include/boda_b200.h"
+#include "b200_conv_fwd.h"
+#include <cstdio>
+
+using namespace boda;
+
+struct b200_rtc { p_b200_compute_t rtc; string tmp; };
+struct b200_fwd { shared_ptr<b200_conv_fwd_t> fwd; string tmp; };
+
+namespace {
+thread_local string g_last_error;
+
+template <typename F> int guarded(F &&f) {
+  try { return f(); }
+  catch (unsup_exception const &e) { g_last_error = e.what(); return -2; }
+  catch (std::exception const &e) { g_last_error = e.what(); return -1; }
+  catch (...) { g_last_error = "unknown exception"; return -1; }
+}
+
+dims_t make_dims(char const *tn, int ndims, char const *const *dim_names, uint32_t const *dim_sizes) {
+  dims_t d;
+  d.tn = tn ? tn : "float";
+  for (int i = 0; i < ndims; ++i) { d.add_dim(dim_names[i], dim_sizes[i]); }
+  d.calc_strides();
+  return d;
+}
+}  // namespace
+
+extern "C" {
+
+#define B200_API __attribute__((visibility("default")))
+
+B200_API const char *b200_last_error(void) { return g_last_error.c_str(); }
+B200_API const char *b200_version(void) { return "boda_b200 0.1 (sm_100a; tcgen05+TMA igemm, fp16x2-split fp32 parity mode)"; }
+B200_API int b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+B200_API b200_rtc *b200_rtc_create(void) {
+  b200_rtc *r = nullptr;
+  guarded([&] { r = new b200_rtc; r->rtc = std::make_shared<b200_compute_t>(); return 0; });
+  return r;
+}
+B200_API void b200_rtc_destroy(b200_rtc *r) { guarded([&] { delete r; return 0; }); }
+B200_API int b200_rtc_set_option(b200_rtc *r, const char *key, const char *val) {
+  return guarded([&] {
+    string const k = key, v = val;
+    if (k == "prec") { r->rtc->prec = (v == "fp32") ? B200_PREC_FP32_SPLIT : (v == "fp16") ? B200_PREC_FP16 : (v == "bf16") ? B200_PREC_BF16 : (rt_err("unknown prec '" + v + "'"), B200_PREC_FP32_SPLIT); }
+    else if (k == "acc_chunk_kblks") { r->rtc->acc_chunk_kblks = std::stoi(v); }
+    else if (k == "device") { r->rtc->device = std::stoi(v); }
+    else { rt_err("be=b200: unused option '" + k + "'"); }
+    return 0;
+  });
+}
+B200_API int b200_rtc_init(b200_rtc *r) { return guarded([&] { r->rtc->init(); return 0; }); }
+B200_API const char *b200_rtc_get_plat_tag(b200_rtc *r) { r->tmp = r->rtc->get_plat_tag(); return r->tmp.c_str(); }
+B200_API int b200_rtc_create_var(b200_rtc *r, const char *vn, const char *tn, int ndims, const char *const *dim_names, const uint32_t *dim_sizes) {
+  return guarded([&] { r->rtc->create_var_with_dims(vn, make_dims(tn, ndims, dim_names, dim_sizes)); return 0; });
+}
+B200_API int b200_rtc_create_view(b200_rtc *r, const char *vn, const char *tn, int ndims, const char *const *dim_names, const uint32_t *dim_sizes, const char *src_vn) {
+  return guarded([&] { r->rtc->create_var_with_dims_as_reshaped_view_of_var(vn, make_dims(tn, ndims, dim_names, dim_sizes), src_vn); return 0; });
+}
+B200_API int b200_rtc_release_var(b200_rtc *r, const char *vn) { return guarded([&] { r->rtc->release_var(vn); return 0; }); }
+B200_API int b200_rtc_get_var_dims(b200_rtc *r, const char *vn, int max_dims, uint32_t *dim_sizes, char *names_buf, int names_buf_len) {
+  return guarded([&] {
+    dims_t const d = r->rtc->get_var_dims(vn);
+    string names;
+    for (size_t i = 0; i < d.size(); ++i) { if ((int)i < max_dims) { dim_sizes[i] = d[i].sz; } names += (i ? ":" : "") + d[i].name; }
+    if (names_buf && names_buf_len > 0) { snprintf(names_buf, names_buf_len, "%s", names.c_str()); }
+    return (int)d.size();
+  });
+}
+B200_API int b200_rtc_set_var_to_zero(b200_rtc *r, const char *vn) { return guarded([&] { r->rtc->set_var_to_zero(vn); return 0; }); }
+B200_API int b200_rtc_compile(b200_rtc *r, const char *func_name, const char *op_text) {
+  return guarded([&] {
+    rtc_func_info_t fi;
+    fi.func_name = func_name;
+    fi.op = *make_p_op_base_t_from_str(op_text);
+    r->rtc->compile({fi}, rtc_compile_opts_t());
+    return 0;
+  });
+}
+B200_API int b200_rtc_release_func(b200_rtc *r, const char *func_name) { return guarded([&] { r->rtc->release_func(func_name); return 0; }); }
+B200_API int b200_rtc_run(b200_rtc *r, const char *func_name, int nargs, const char *const *arg_names, const char *const *arg_vals) {
+  return guarded([&] {
+    rtc_func_call_t rfc;
+    rfc.rtc_func_name = func_name;
+    for (int i = 0; i < nargs; ++i) {
+      string const v = arg_vals[i];
+      if (!v.empty() && v[0] == '(') { rfc.arg_map[arg_names[i]] = rtc_arg_t(nda_from_lexp(*parse_lexp(v))); }
+      else { rfc.arg_map[arg_names[i]] = rtc_arg_t(v); }
+    }
+    return (int)r->rtc->run(rfc);
+  });
+}
+B200_API int b200_rtc_finish_and_sync(b200_rtc *r) { return guarded([&] { r->rtc->finish_and_sync(); return 0; }); }
+B200_API int b200_rtc_release_per_call_id_data(b200_rtc *r) { return guarded([&] { r->rtc->release_per_call_id_data(); return 0; }); }
+B200_API int b200_rtc_release_all_funcs(b200_rtc *r) { return guarded([&] { r->rtc->release_all_funcs(); return 0; }); }
+B200_API int b200_rtc_get_dur(b200_rtc *r, uint32_t b, uint32_t e, float *ms_out) { return guarded([&] { *ms_out = r->rtc->get_dur(b, e); return 0; }); }
+B200_API int b200_rtc_copy_to_var(b200_rtc *r, const char *vn, const void *host_src, uint64_t bytes) { return guarded([&] { r->rtc->copy_raw_to_var(vn, host_src, bytes); return 0; }); }
+B200_API int b200_rtc_copy_from_var(b200_rtc *r, void *host_dst, const char *vn, uint64_t bytes) { return guarded([&] { r->rtc->copy_var_to_raw(host_dst, vn, bytes); return 0; }); }
+B200_API int b200_rtc_get_var_raw_native_pointer(b200_rtc *r, const char *vn, void **dev_ptr_out) {
+  return guarded([&] { *dev_ptr_out = r->rtc->get_var_raw_native_pointer(vn)->rp_elems(); return 0; });
+}
+B200_API uint64_t b200_rtc_launches(b200_rtc *r) { return r->rtc->launches(); }
+
+// ---- tier B ----
+B200_API b200_fwd *b200_fwd_create(const char *pipe_text, const char *opts) {
+  b200_fwd *f = nullptr;
+  int const rc = guarded([&] {
+    f = new b200_fwd;
+    f->fwd = std::make_shared<b200_conv_fwd_t>();
+    f->fwd->init(make_conv_pipe_from_text(pipe_text), opts ? opts : "");
+    return 0;
+  });
+  if (rc != 0) { delete f; return nullptr; }
+  return f;
+}
+B200_API void b200_fwd_destroy(b200_fwd *f) { guarded([&] { delete f; return 0; }); }
+B200_API int b200_fwd_set_param(b200_fwd *f, const char *node_name, const float *host_src, uint64_t n_elems) {
+  return guarded([&] { f->fwd->set_param(node_name, host_src, n_elems); return 0; });
+}
+B200_API int b200_fwd_run(b200_fwd *f, int n_set, const char *const *set_names, const float *const *set_bufs, const uint64_t *set_elems, int n_get,
+                          const char *const *get_names, float *const *get_bufs, const uint64_t *get_elems) {
+  return guarded([&] { f->fwd->run_fwd_raw(n_set, set_names, set_bufs, set_elems, n_get, get_names, get_bufs, get_elems); return 0; });
+}
+B200_API int b200_fwd_run_device_only(b200_fwd *f, int iters, float *ms_per_iter_out) {
+  return guarded([&] { *ms_per_iter_out = f->fwd->run_device_only(iters); return 0; });
+}
+B200_API int b200_fwd_set_det_drop_seed(b200_fwd *f, uint32_t seed) { return guarded([&] { f->fwd->set_det_drop_seed(seed); return 0; }); }
+B200_API const char *b200_fwd_get_info_log(b200_fwd *f) { f->tmp = f->fwd->get_info_log(); return f->tmp.c_str(); }
+B200_API int b200_fwd_get_node_dims(b200_fwd *f, const char *node_name, uint32_t *dims4) {
+  return guarded([&] {
+    dims_t const &d = f->fwd->cp->must_get_node(node_name)->dims;
+    for (size_t i = 0; i < d.size() && i < 4; ++i) { dims4[i] = d[i].sz; }
+    return (int)d.size();
+  });
+}
+B200_API int b200_fwd_num_calls(b200_fwd *f) { return (int)f->fwd->fwd_calls.size(); }
+B200_API uint64_t b200_fwd_launches(b200_fwd *f) { return f->fwd->launches(); }
+B200_API int b200_fwd_profile(b200_fwd *f, int iters, char *tags_buf, int tags_buf_len, float *call_ms_out, float *kernel_ms_out, double *flops_out, int max_calls) {
+  return guarded([&] {
+    auto res = f->fwd->profile(iters);
+    string tags;
+    int n = 0;
+    for (auto const &r : res) {
+      if (n >= max_calls) { break; }
+      tags += (n ? "\n" : "") + r.func_name;
+      call_ms_out[n] = r.call_ms; kernel_ms_out[n] = r.kernel_ms; flops_out[n] = r.flops;
+      ++n;
+    }
+    if (tags_buf && tags_buf_len > 0) { snprintf(tags_buf, tags_buf_len, "%s", tags.c_str()); }
+    return n;
+  });
+}
+B200_API int b200_fwd_run_timed(b200_fwd *f, int iters, uint64_t l2_flush_bytes, float *ms_each_out) {
+  return guarded([&] {
+    vector<float> ms = f->fwd->run_timed(iters, l2_flush_bytes);
+    for (int i = 0; i < iters; ++i) { ms_each_out[i] = ms[i]; }
+    return 0;
+  });
+}
+B200_API int b200_fwd_get_node_raw_native_pointer(b200_fwd *f, const char *node_name, void **dev_ptr_out) {
+  return guarded([&] { *dev_ptr_out = f->fwd->rtc->get_var_raw_native_pointer(node_name)->rp_elems(); return 0; });
+}
+B200_API int b200_rtc_get_kernel_dur(b200_rtc *r, uint32_t id, float *ms_out) { return guarded([&] { *ms_out = r->rtc->get_kernel_dur(id); return 0; }); }
+
+}  // extern "C"

@@ -1,0 +1,698 @@
+// b200_compute.cu -- implementation of `be=b200` (see b200_compute.h) over the CUDA runtime + driver tensor-map API.
+// Replaces nvrtc_compute_t (src/nvrtc_util.cc:174-395) and the culibs escape hatch (src/culibs-wrap.cc) for the
+// rtc_fwd path. There is deliberately NO CPU fallback: every function either launches sm_100a kernels or throws.
+#include "b200_compute.h"
+#include "igemm.cuh"
+#include "pointwise.cuh"
+#include <cudaTypedefs.h>
+#include <algorithm>
+#include <cmath>
+
+namespace boda {
+
+#define CU_CHK(x) do { cudaError_t const e_ = (x); if (e_ != cudaSuccess) { rt_err(string("CUDA error: ") + cudaGetErrorString(e_) + " in " #x " at " + __FILE__ + ":" + std::to_string(__LINE__)); } } while (0)
+
+void rtc_reshape_check(dims_t const &dims, dims_t const &src_dims) {
+  if (dims.bytes_sz() != src_dims.bytes_sz()) { rt_err("reshape: view dims " + dims.pretty() + " and source dims " + src_dims.pretty() + " differ in size"); }
+}
+
+namespace {
+
+struct dev_buf_t {
+  void *p = nullptr;
+  uint64_t bytes = 0;
+  explicit dev_buf_t(uint64_t b) : bytes(b) { CU_CHK(cudaMalloc(&p, std::max<uint64_t>(b, 16))); }
+  ~dev_buf_t() { if (p) { cudaFree(p); } }
+  dev_buf_t(dev_buf_t const &) = delete;
+};
+typedef shared_ptr<dev_buf_t> p_dev_buf_t;
+
+struct var_info_t {
+  p_dev_buf_t buf;
+  dims_t dims;
+  shared_ptr<uint64_t> gen;  // bumped on every write; shared between reshaped views of the same storage
+};
+
+// a 16-bit K-major operand in hi (+lo) planes with its power-of-two scale
+struct packed_t {
+  p_dev_buf_t hi, lo, scale2, absmax_bits;
+  uint64_t src_gen = ~0ull;
+  void const *src_ptr = nullptr;
+  long long rows = 0, row_stride = 0;  // elements
+};
+
+enum func_kind_t { FK_CONV, FK_SGEMM, FK_POOL, FK_LRN, FK_RELU, FK_SOFTMAX, FK_COPY, FK_REDUCE, FK_GEN_DATA };
+
+struct conv_plan_t {
+  int N, C, H, W, OC, KH, KW, sy, sx, py, px, OH, OW;
+  int Cpad, cblks;
+  bool im2col, full_kernel, swapped;
+  int BN, splits, kblks_total, kblks_per_split;
+  long long a_rows, a_row_stride;  // activation matrix view (2-d modes)
+  long long w_tap_stride, w_row_stride;
+  int relu, has_bias;
+};
+
+struct func_t {
+  func_kind_t kind;
+  op_base_t op;
+  string gen_arg;  // gen_data: name of the output argument
+  conv_plan_t cp;
+  packed_t w_pack, a_pack;  // conv: filts / in ; sgemm: b / a
+  p_dev_buf_t splitk_ws;
+};
+
+struct call_ev_t { cudaEvent_t b = nullptr, e = nullptr, kb = nullptr, ke = nullptr; };  // whole call; its main (contraction) kernel
+
+PFN_cuTensorMapEncodeTiled_v12000 g_encode_tiled = nullptr;
+PFN_cuTensorMapEncodeIm2col_v12000 g_encode_im2col = nullptr;
+
+void load_driver_entry_points() {
+  if (g_encode_tiled) { return; }
+  cudaDriverEntryPointQueryResult qres;
+  void *fn = nullptr;
+  CU_CHK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) { rt_err("cuTensorMapEncodeTiled not available from the driver"); }
+  g_encode_tiled = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  fn = nullptr;
+  CU_CHK(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) { rt_err("cuTensorMapEncodeIm2col not available from the driver"); }
+  g_encode_im2col = reinterpret_cast<PFN_cuTensorMapEncodeIm2col_v12000>(fn);
+}
+
+// 2-d K-major matrix [rows][row_stride] of 16-bit elements; box = 64 (K) x box_rows, 128-byte swizzle, zero OOB fill.
+CUtensorMap make_tiled_map(void const *base, bool bf16, uint64_t k_extent, uint64_t rows, uint64_t row_stride_elems, uint32_t box_rows) {
+  CUtensorMap m;
+  cuuint64_t gdim[2] = {k_extent, rows};
+  cuuint64_t gstride[1] = {row_stride_elems * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult const r = g_encode_tiled(&m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), gdim,
+                                    gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { rt_err("cuTensorMapEncodeTiled failed with code " + str(int(r)) + " (k=" + str(k_extent) + " rows=" + str(rows) + " stride=" + str(row_stride_elems) + ")"); }
+  return m;
+}
+
+// NHWC activation tensor [N][H][W][Cpad] read in im2col mode: 128 output pixels x 64 channels per load.
+CUtensorMap make_im2col_map(void const *base, bool bf16, conv_plan_t const &cp) {
+  CUtensorMap m;
+  cuuint64_t gdim[4] = {(cuuint64_t)cp.Cpad, (cuuint64_t)cp.W, (cuuint64_t)cp.H, (cuuint64_t)cp.N};
+  cuuint64_t gstride[3] = {(cuuint64_t)cp.Cpad * 2, (cuuint64_t)cp.W * cp.Cpad * 2, (cuuint64_t)cp.H * cp.W * cp.Cpad * 2};
+  int lower[2] = {-cp.px, -cp.py};                                // {w, h}: footprint corner of the first output pixel
+  int upper[2] = {cp.px - (cp.KW - 1), cp.py - (cp.KH - 1)};      // ... of the last one, relative to the far image edge
+  cuuint32_t estr[4] = {1, (cuuint32_t)cp.sx, (cuuint32_t)cp.sy, 1};
+  CUresult const r = g_encode_im2col(&m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(base), gdim, gstride,
+                                     lower, upper, 64 /*channelsPerPixel*/, 128 /*pixelsPerColumn*/, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { rt_err("cuTensorMapEncodeIm2col failed with code " + str(int(r))); }
+  // driver <= 13.1 quirk for small tensors (same workaround CUTLASS applies when it builds im2col descriptors)
+  int drv = 0;
+  cudaDriverGetVersion(&drv);
+  if (drv <= 13010 && (uint64_t)cp.N * cp.H * cp.W * cp.Cpad * 2 < 131072) { reinterpret_cast<uint64_t *>(&m)[1] &= ~(1ull << 21); }
+  return m;
+}
+
+int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
+long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
+
+}  // namespace
+
+struct b200_impl_t {
+  map<string, var_info_t> vars;
+  map<string, func_t> funcs;
+  vector<call_ev_t> calls;
+  cudaStream_t stream = nullptr;
+  bool inited = false, timing = true;
+  uint64_t n_launches = 0;
+  int num_sms = 148;
+  string plat_tag;
+
+  var_info_t &must_var(string const &vn) {
+    auto i = vars.find(vn);
+    if (i == vars.end()) { rt_err("var '" + vn + "' not found"); }
+    return i->second;
+  }
+  void bump(var_info_t &v) { ++(*v.gen); }
+};
+
+b200_compute_t::b200_compute_t() : impl(new b200_impl_t) {}
+b200_compute_t::~b200_compute_t() {
+  if (impl) {
+    if (impl->inited) { cudaStreamSynchronize(impl->stream); }
+    release_per_call_id_data();
+    impl->funcs.clear();
+    impl->vars.clear();
+    if (impl->stream) { cudaStreamDestroy(impl->stream); }
+    delete impl;
+  }
+}
+
+void b200_compute_t::init() {
+  if (impl->inited) { return; }
+  int ndev = 0;
+  cudaError_t const e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) { rt_err(string("be=b200 needs a CUDA device and there is no CPU fallback: ") + cudaGetErrorString(e)); }
+  CU_CHK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU_CHK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) { unsup_err("be=b200 is built for sm_100a only; device is sm_" + str(prop.major) + str(prop.minor)); }
+  impl->num_sms = prop.multiProcessorCount;
+  impl->plat_tag = string("b200:") + prop.name;
+  CU_CHK(cudaStreamCreateWithFlags(&impl->stream, cudaStreamNonBlocking));
+  load_driver_entry_points();
+  impl->inited = true;
+}
+string b200_compute_t::get_plat_tag() { return impl->plat_tag.empty() ? string("b200:uninit") : impl->plat_tag; }
+cudaStream_t b200_compute_t::stream() const { return impl->stream; }
+uint64_t b200_compute_t::launches() const { return impl->n_launches; }
+void b200_compute_t::set_timing(bool on) { impl->timing = on; }
+bool b200_compute_t::has_var(string const &vn) const { return impl->vars.count(vn) != 0; }
+bool b200_compute_t::has_func(string const &fn) const { return impl->funcs.count(fn) != 0; }
+
+// ---- vars -----------------------------------------------------------------------------------------------------
+void b200_compute_t::create_var_with_dims(string const &vn, dims_t const &dims) {
+  assert_st(impl->inited);
+  if (impl->vars.count(vn)) { rt_err("var '" + vn + "' already exists"); }
+  if (dims.tn == "none") { rt_err("can't create var '" + vn + "' with no element type"); }
+  var_info_t v;
+  v.dims = dims;
+  v.dims.calc_strides();
+  v.buf = std::make_shared<dev_buf_t>(dims.bytes_sz());
+  v.gen = std::make_shared<uint64_t>(1);
+  CU_CHK(cudaMemsetAsync(v.buf->p, 0, std::max<uint64_t>(dims.bytes_sz(), 16), impl->stream));  // new vars are zero-filled
+  impl->vars[vn] = v;
+}
+void b200_compute_t::create_var_with_dims_as_reshaped_view_of_var(string const &vn, dims_t const &dims, string const &src_vn) {
+  if (impl->vars.count(vn)) { rt_err("var '" + vn + "' already exists"); }
+  var_info_t const &src = impl->must_var(src_vn);
+  rtc_reshape_check(dims, src.dims);
+  var_info_t v = src;  // shares buffer + generation counter
+  v.dims = dims;
+  v.dims.calc_strides();
+  impl->vars[vn] = v;
+}
+void b200_compute_t::release_var(string const &vn) { impl->must_var(vn); impl->vars.erase(vn); }
+dims_t b200_compute_t::get_var_dims(string const &vn) { return impl->must_var(vn).dims; }
+void b200_compute_t::set_var_to_zero(string const &vn) {
+  var_info_t &v = impl->must_var(vn);
+  CU_CHK(cudaMemsetAsync(v.buf->p, 0, v.dims.bytes_sz(), impl->stream));
+  impl->bump(v);
+}
+void b200_compute_t::copy_nda_to_var(string const &vn, p_nda_t const &nda) {
+  var_info_t &v = impl->must_var(vn);
+  if (!(nda->dims == v.dims)) { rt_err("copy_nda_to_var: dims mismatch for '" + vn + "': nda " + nda->dims.pretty() + " vs var " + v.dims.pretty()); }
+  copy_raw_to_var(vn, nda->rp_elems(), v.dims.bytes_sz());
+}
+void b200_compute_t::copy_var_to_nda(p_nda_t const &nda, string const &vn) {
+  var_info_t &v = impl->must_var(vn);
+  if (!(nda->dims == v.dims)) { rt_err("copy_var_to_nda: dims mismatch for '" + vn + "': nda " + nda->dims.pretty() + " vs var " + v.dims.pretty()); }
+  copy_var_to_raw(nda->rp_elems(), vn, v.dims.bytes_sz());
+}
+void b200_compute_t::copy_raw_to_var_async(string const &vn, void const *src, uint64_t bytes) {
+  var_info_t &v = impl->must_var(vn);
+  if (bytes != v.dims.bytes_sz()) { rt_err("copy to var '" + vn + "': got " + str(bytes) + " bytes, var holds " + str(v.dims.bytes_sz())); }
+  CU_CHK(cudaMemcpyAsync(v.buf->p, src, bytes, cudaMemcpyHostToDevice, impl->stream));
+  impl->bump(v);
+}
+void b200_compute_t::copy_var_to_raw_async(void *dst, string const &vn, uint64_t bytes) {
+  var_info_t &v = impl->must_var(vn);
+  if (bytes != v.dims.bytes_sz()) { rt_err("copy from var '" + vn + "': asked " + str(bytes) + " bytes, var holds " + str(v.dims.bytes_sz())); }
+  CU_CHK(cudaMemcpyAsync(dst, v.buf->p, bytes, cudaMemcpyDeviceToHost, impl->stream));
+}
+void b200_compute_t::copy_raw_to_var(string const &vn, void const *src, uint64_t bytes) {
+  copy_raw_to_var_async(vn, src, bytes);
+  CU_CHK(cudaStreamSynchronize(impl->stream));
+}
+void b200_compute_t::copy_var_to_raw(void *dst, string const &vn, uint64_t bytes) {
+  copy_var_to_raw_async(dst, vn, bytes);
+  CU_CHK(cudaStreamSynchronize(impl->stream));
+}
+p_nda_t b200_compute_t::get_var_raw_native_pointer(string const &vn) {
+  var_info_t &v = impl->must_var(vn);
+  impl->bump(v);  // the caller may write through the pointer: invalidate anything derived from this var
+  p_nda_t r = std::make_shared<nda_t>(v.dims, false);
+  r->rp = v.buf->p;
+  return r;
+}
+
+// ---- functions ------------------------------------------------------------------------------------------------
+namespace {
+
+bool starts_with(string const &s, string const &p) { return s.size() >= p.size() && s.compare(0, p.size(), p) == 0; }
+
+func_kind_t resolve_kind(op_base_t const &op, string &gen_arg) {
+  string fn = op.has_func_name() ? op.get_func_name() : string();
+  string const type = op.has_type() ? op.get_type() : string();
+  if (starts_with(fn, "gen_data_")) {
+    size_t const us = fn.rfind('_');
+    gen_arg = fn.substr(us + 1);
+    return FK_GEN_DATA;
+  }
+  if (fn.empty()) {
+    if (type == "Convolution") { fn = "conv"; } else if (type == "sgemm") { fn = "sgemm"; } else if (type == "Pooling") { fn = "pool"; }
+    else if (type == "LRN") { fn = "lrn"; } else if (type == "ReLU") { fn = "relu"; } else if (type == "Softmax") { fn = "softmax"; }
+    else if (type == "Concat") { fn = "copy"; } else if (type == "Reduce" || type == "Eltwise") { fn = "reduce"; }
+    else { unsup_err("be=b200: no function for op of type '" + type + "'"); }
+  }
+  // every reference conv variant computes the same function; ours takes the reference-layout (NCHW / OIHW) arguments,
+  // i.e. the same call contract as the `cudnn_conv` variant (src/cnn_op.cc:46-50, src/culibs-wrap.cc:94-212)
+  if (fn == "conv" || fn == "tconv" || fn == "k1conv" || fn == "ipconv" || fn == "conv_simd" || fn == "k1conv_simd" || fn == "cudnn_conv" || fn == "b200_conv") { return FK_CONV; }
+  if (fn == "sgemm" || fn == "sgemm_simd" || fn == "sgemm_no_local" || fn == "sgemm_simd_local" || fn == "cublas_sgemm" || fn == "b200_sgemm") { return FK_SGEMM; }
+  if (fn == "pool") { return FK_POOL; }
+  if (fn == "lrn") { return FK_LRN; }
+  if (fn == "relu") { return FK_RELU; }
+  if (fn == "softmax") { return FK_SOFTMAX; }
+  if (fn == "copy") { return FK_COPY; }
+  if (fn == "reduce") { return FK_REDUCE; }
+  unsup_err("be=b200: unknown function '" + fn + "'");
+}
+
+void check_nchw(dims_t const &d, char const *what) {
+  if (d.size() != 4 || d[0].name != "img" || d[1].name != "chan" || d[2].name != "y" || d[3].name != "x" || d.tn != "float") {
+    unsup_err(string("be=b200 conv expects reference-layout float img:chan:y:x for '") + what + "', got " + d.pretty());
+  }
+}
+
+void plan_conv(conv_plan_t &cp, op_base_t const &op, int num_sms) {
+  dims_t const &din = op.get_dims("in"), &df = op.get_dims("filts"), &dout = op.get_dims("out");
+  check_nchw(din, "in");
+  check_nchw(dout, "out");
+  if (df.size() != 4 || df[0].name != "out_chan" || df[1].name != "in_chan" || df[2].name != "y" || df[3].name != "x" || df.tn != "float") {
+    unsup_err("be=b200 conv expects reference-layout float out_chan:in_chan:y:x filts, got " + df.pretty());
+  }
+  cp.N = din.dsz("img"); cp.C = din.dsz("chan"); cp.H = din.dsz("y"); cp.W = din.dsz("x");
+  cp.OC = df.dsz("out_chan"); cp.KH = df.dsz("y"); cp.KW = df.dsz("x");
+  if ((int)df.dsz("in_chan") != cp.C) { unsup_err("conv: filts in_chan != in chan (groups are not supported by the reference either)"); }
+  cp.sy = op.yx("stride", "y", 1); cp.sx = op.yx("stride", "x", 1);
+  cp.py = op.yx("in_pad", "y", 0); cp.px = op.yx("in_pad", "x", 0);
+  if (op.has("kern_sz") && ((int)op.get_dims("kern_sz").dsz("y") != cp.KH || (int)op.get_dims("kern_sz").dsz("x") != cp.KW)) { rt_err("conv: kern_sz disagrees with filts dims"); }
+  if (cp.H + 2 * cp.py < cp.KH || cp.W + 2 * cp.px < cp.KW) { rt_err("conv: padded input smaller than kernel"); }
+  cp.OH = (cp.H + 2 * cp.py - cp.KH) / cp.sy + 1;  // src/conv_util.cc:167-173
+  cp.OW = (cp.W + 2 * cp.px - cp.KW) / cp.sx + 1;
+  if ((int)dout.dsz("img") != cp.N || (int)dout.dsz("chan") != cp.OC || (int)dout.dsz("y") != cp.OH || (int)dout.dsz("x") != cp.OW) {
+    rt_err("conv: out dims " + dout.pretty() + " do not match computed img=" + str(cp.N) + ",chan=" + str(cp.OC) + ",y=" + str(cp.OH) + ",x=" + str(cp.OW));
+  }
+  if (cp.KW > 255 || cp.KH > 255 || cp.px > 127 || cp.py > 127) { unsup_err("conv: kernel/padding too large for the im2col TMA path"); }
+  cp.relu = op.has("conv_has_relu") ? op.get_u32("conv_has_relu") : 0;
+  cp.has_bias = 1;
+  cp.Cpad = (int)round_up(cp.C, 8);
+  bool const k1 = (cp.KH == 1 && cp.KW == 1 && cp.sy == 1 && cp.sx == 1 && cp.py == 0 && cp.px == 0);
+  cp.full_kernel = (!k1 && cp.KH == cp.H && cp.KW == cp.W && cp.py == 0 && cp.px == 0);  // inner-product shaped (OH=OW=1)
+  cp.im2col = !(k1 || cp.full_kernel);
+  long long const pixels = (long long)cp.N * cp.OH * cp.OW;
+  if (cp.im2col) {
+    cp.cblks = ceil_div(cp.Cpad, 64);
+    cp.w_tap_stride = (long long)cp.cblks * 64;
+    cp.kblks_total = cp.KH * cp.KW * cp.cblks;
+    cp.a_rows = 0; cp.a_row_stride = 0;
+  } else if (k1) {
+    cp.cblks = ceil_div(cp.Cpad, 64);
+    cp.w_tap_stride = cp.Cpad;
+    cp.kblks_total = cp.cblks;
+    cp.a_rows = (long long)cp.N * cp.H * cp.W; cp.a_row_stride = cp.Cpad;
+  } else {
+    cp.cblks = 0;
+    cp.w_tap_stride = cp.Cpad;
+    cp.kblks_total = ceil_div((long long)cp.KH * cp.KW * cp.Cpad, 64);
+    cp.a_rows = cp.N; cp.a_row_stride = (long long)cp.H * cp.W * cp.Cpad;
+  }
+  cp.w_row_stride = round_up((long long)cp.KH * cp.KW * cp.w_tap_stride, 64);
+  cp.swapped = (!cp.im2col) && pixels <= 64 && cp.OC >= 128;
+  if (cp.swapped) { cp.BN = pixels <= 32 ? 32 : 64; }
+  else { cp.BN = cp.OC > 64 ? 128 : (cp.OC > 32 ? 64 : 32); }
+  long long const p_rows = cp.swapped ? cp.OC : pixels, q_rows = cp.swapped ? pixels : cp.OC;
+  long long const tiles = (long long)ceil_div(p_rows, b200::IGEMM_BM) * ceil_div(q_rows, cp.BN);
+  cp.splits = 1;
+  if (tiles * 2 <= num_sms && cp.kblks_total >= 16) {  // too few CTAs to fill the chip: split K (deterministic two-pass reduce)
+    int s = (int)std::min<long long>((long long)(num_sms / tiles), (long long)(cp.kblks_total / 8));
+    cp.splits = std::max(1, std::min(s, 16));
+  }
+  cp.kblks_per_split = ceil_div(cp.kblks_total, cp.splits);
+  cp.splits = ceil_div(cp.kblks_total, cp.kblks_per_split);
+}
+
+}  // namespace
+
+void b200_compute_t::compile(vect_rtc_func_info_t const &func_infos, rtc_compile_opts_t const &) {
+  assert_st(impl->inited);
+  for (auto const &fi : func_infos) {
+    if (impl->funcs.count(fi.func_name)) { rt_err("function '" + fi.func_name + "' already compiled"); }
+    func_t f;
+    f.op = fi.op;
+    f.kind = resolve_kind(fi.op, f.gen_arg);
+    if (f.kind == FK_CONV) { plan_conv(f.cp, fi.op, impl->num_sms); }
+    impl->funcs[fi.func_name] = f;
+  }
+}
+void b200_compute_t::release_func(string const &func_name) {
+  if (!impl->funcs.erase(func_name)) { rt_err("release_func: '" + func_name + "' not found"); }
+}
+void b200_compute_t::release_all_funcs() { impl->funcs.clear(); }
+void b200_compute_t::finish_and_sync() { CU_CHK(cudaStreamSynchronize(impl->stream)); }
+void b200_compute_t::release_per_call_id_data() {
+  for (auto &c : impl->calls) { for (cudaEvent_t ev : {c.b, c.e, c.kb, c.ke}) { if (ev) { cudaEventDestroy(ev); } } }
+  impl->calls.clear();
+}
+float b200_compute_t::get_dur(uint32_t const &b, uint32_t const &e) {
+  if (b >= impl->calls.size() || e >= impl->calls.size()) { rt_err("get_dur: invalid call id"); }
+  if (!impl->calls[b].b || !impl->calls[e].e) { rt_err("get_dur: call was not timed"); }
+  CU_CHK(cudaEventSynchronize(impl->calls[e].e));
+  float ms = 0;
+  CU_CHK(cudaEventElapsedTime(&ms, impl->calls[b].b, impl->calls[e].e));
+  return ms;
+}
+float b200_compute_t::get_kernel_dur(uint32_t const &id) {
+  if (id >= impl->calls.size()) { rt_err("get_kernel_dur: invalid call id"); }
+  call_ev_t const &c = impl->calls[id];
+  if (!c.kb || !c.ke) { return get_dur(id, id); }  // single-kernel functions: the call is the kernel
+  CU_CHK(cudaEventSynchronize(c.ke));
+  float ms = 0;
+  CU_CHK(cudaEventElapsedTime(&ms, c.kb, c.ke));
+  return ms;
+}
+void b200_compute_t::profile_start() {}
+void b200_compute_t::profile_stop() {}
+
+// ---- run ------------------------------------------------------------------------------------------------------
+namespace {
+
+struct run_ctx_t {
+  b200_compute_t &rtc;
+  b200_impl_t &im;
+  func_t &f;
+  rtc_func_call_t const &rfc;
+  cudaStream_t st;
+  call_ev_t *ev;
+  void mark_kernel_begin() { if (ev && im.timing) { CU_CHK(cudaEventCreate(&ev->kb)); CU_CHK(cudaEventRecord(ev->kb, st)); } }
+  void mark_kernel_end() { if (ev && im.timing) { CU_CHK(cudaEventCreate(&ev->ke)); CU_CHK(cudaEventRecord(ev->ke, st)); } }
+
+  var_info_t &var(string const &an) {
+    auto i = rfc.arg_map.find(an);
+    if (i == rfc.arg_map.end() || !i->second.is_var()) { rt_err("call to '" + rfc.rtc_func_name + "': missing var argument '" + an + "'"); }
+    return im.must_var(i->second.get_var());
+  }
+  bool has_arg(string const &an) { return rfc.arg_map.count(an) != 0; }
+  double scalar(string const &an, bool has_default = false, double dflt = 0) {
+    auto i = rfc.arg_map.find(an);
+    if (i != rfc.arg_map.end() && i->second.is_nda()) { return nda_scalar_as_double(*i->second.get_nda()); }
+    if (f.op.has(an) && f.op.get(an)->has_data()) { return nda_scalar_as_double(*f.op.get(an)); }
+    if (has_default) { return dflt; }
+    rt_err("call to '" + rfc.rtc_func_name + "': missing by-value argument '" + an + "'");
+  }
+  void launched(int n = 1) {
+    im.n_launches += n;
+    cudaError_t const e = cudaGetLastError();
+    if (e != cudaSuccess) { rt_err(string("kernel launch failed in '") + rfc.rtc_func_name + "': " + cudaGetErrorString(e)); }
+  }
+  float *fptr(var_info_t &v) { if (v.dims.tn != "float") { unsup_err("be=b200: only float vars are supported, got " + v.dims.pretty()); } return static_cast<float *>(v.buf->p); }
+
+  // src [B][R][Cc] fp32 -> planes [B][Cc][..R..] 16-bit, with abs-max scaling. Cached on (pointer, generation).
+  void pack(packed_t &pk, var_info_t &src, int B, int R, int Cc, int Rpad, long long dst_c_stride, long long dst_b_stride, long long total_elems, bool want_lo, bool bf16) {
+    if (pk.src_gen == *src.gen && pk.src_ptr == src.buf->p && pk.hi) { return; }
+    if (!pk.hi || pk.hi->bytes < (uint64_t)total_elems * 2) {
+      pk.hi = std::make_shared<dev_buf_t>(total_elems * 2);
+      CU_CHK(cudaMemsetAsync(pk.hi->p, 0, total_elems * 2, st));
+      if (want_lo) { pk.lo = std::make_shared<dev_buf_t>(total_elems * 2); CU_CHK(cudaMemsetAsync(pk.lo->p, 0, total_elems * 2, st)); }
+      pk.scale2 = std::make_shared<dev_buf_t>(8);
+      pk.absmax_bits = std::make_shared<dev_buf_t>(4);
+      CU_CHK(cudaMemsetAsync(pk.absmax_bits->p, 0, 4, st));
+    }
+    long long const n = (long long)B * R * Cc;
+    int const blocks = (int)std::min<long long>((n + 1023) / 1024, 148 * 8);
+    bool const use_scale = !bf16;  // bf16 has fp32's exponent range: no scaling needed
+    if (use_scale) { b200::absmax_kernel<<<std::max(blocks, 1), 256, 0, st>>>(fptr(src), n, static_cast<unsigned int *>(pk.absmax_bits->p)); launched(); }
+    b200::finalize_scale_kernel<<<1, 1, 0, st>>>(static_cast<unsigned int *>(pk.absmax_bits->p), static_cast<float *>(pk.scale2->p), use_scale ? 1 : 0);
+    launched();
+    dim3 grid(ceil_div(Rpad, 64), ceil_div(Cc, 32), B);
+    uint16_t *hi = static_cast<uint16_t *>(pk.hi->p), *lo = want_lo ? static_cast<uint16_t *>(pk.lo->p) : nullptr;
+    if (bf16) { b200::pack_xpose_split_kernel<true><<<grid, 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, Cc, Rpad, dst_c_stride, dst_b_stride); }
+    else { b200::pack_xpose_split_kernel<false><<<grid, 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, Cc, Rpad, dst_c_stride, dst_b_stride); }
+    launched();
+    pk.src_gen = *src.gen;
+    pk.src_ptr = src.buf->p;
+  }
+
+  template <int BN, int kPlanes>
+  void launch_igemm_t(dim3 grid, CUtensorMap const &ph, CUtensorMap const &pl, CUtensorMap const &qh, CUtensorMap const &ql, b200::IgemmParams const &prm) {
+    using Cfg = b200::IgemmCfg<BN, kPlanes>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      CU_CHK(cudaFuncSetAttribute(b200::igemm_umma_kernel<BN, kPlanes>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+      attr_set = true;
+    }
+    b200::igemm_umma_kernel<BN, kPlanes><<<grid, b200::IGEMM_THREADS, Cfg::kSmemBytes, st>>>(ph, pl, qh, ql, prm);
+    launched();
+  }
+  void launch_igemm(int BN, int planes, dim3 grid, CUtensorMap const &ph, CUtensorMap const &pl, CUtensorMap const &qh, CUtensorMap const &ql, b200::IgemmParams const &prm) {
+    if (planes == 2) {
+      if (BN == 128) { launch_igemm_t<128, 2>(grid, ph, pl, qh, ql, prm); } else if (BN == 64) { launch_igemm_t<64, 2>(grid, ph, pl, qh, ql, prm); } else { launch_igemm_t<32, 2>(grid, ph, pl, qh, ql, prm); }
+    } else {
+      if (BN == 128) { launch_igemm_t<128, 1>(grid, ph, pl, qh, ql, prm); } else if (BN == 64) { launch_igemm_t<64, 1>(grid, ph, pl, qh, ql, prm); } else { launch_igemm_t<32, 1>(grid, ph, pl, qh, ql, prm); }
+    }
+  }
+
+  void run_conv() {
+    conv_plan_t const &cp = f.cp;
+    var_info_t &vin = var("in"), &vf = var("filts"), &vout = var("out");
+    if (!(vin.dims == f.op.get_dims("in")) || !(vf.dims == f.op.get_dims("filts")) || !(vout.dims == f.op.get_dims("out"))) {
+      rt_err("conv call '" + rfc.rtc_func_name + "': var dims differ from the dims the function was compiled for");
+    }
+    float const *bias = nullptr;
+    if (has_arg("biases")) { var_info_t &vb = var("biases"); if ((int)vb.dims.dims_prod() != cp.OC) { rt_err("conv: biases size mismatch"); } bias = fptr(vb); }
+    bool const bf16 = (rtc.prec == B200_PREC_BF16);
+    int const planes = (rtc.prec == B200_PREC_FP32_SPLIT) ? 2 : 1;
+    // filters: OIHW -> [OC][tap][chan] K-major rows (once per weight version; the reference's xpose_filts, src/rtc_fwd.cc:310-313)
+    pack(f.w_pack, vf, cp.OC, cp.C, cp.KH * cp.KW, cp.Cpad, cp.w_tap_stride, cp.w_row_stride, (long long)cp.OC * cp.w_row_stride, planes == 2, bf16);
+    // activations: NCHW -> NHWC (chan padded to a multiple of 8)
+    long long const act_elems = (long long)cp.N * cp.H * cp.W * cp.Cpad;
+    pack(f.a_pack, vin, cp.N, cp.C, cp.H * cp.W, cp.Cpad, cp.Cpad, (long long)cp.H * cp.W * cp.Cpad, act_elems, planes == 2, bf16);
+
+    long long const pixels = (long long)cp.N * cp.OH * cp.OW;
+    CUtensorMap act_hi, act_lo, w_hi, w_lo;
+    uint32_t const act_box = cp.swapped ? cp.BN : IGEMM_BM_host(), w_box = cp.swapped ? IGEMM_BM_host() : cp.BN;
+    if (cp.im2col) {
+      act_hi = make_im2col_map(f.a_pack.hi->p, bf16, cp);
+      act_lo = planes == 2 ? make_im2col_map(f.a_pack.lo->p, bf16, cp) : act_hi;
+    } else {
+      uint64_t const kext = cp.full_kernel ? (uint64_t)cp.a_row_stride : (uint64_t)cp.Cpad;
+      act_hi = make_tiled_map(f.a_pack.hi->p, bf16, kext, cp.a_rows, cp.a_row_stride, act_box);
+      act_lo = planes == 2 ? make_tiled_map(f.a_pack.lo->p, bf16, kext, cp.a_rows, cp.a_row_stride, act_box) : act_hi;
+    }
+    w_hi = make_tiled_map(f.w_pack.hi->p, bf16, cp.w_row_stride, cp.OC, cp.w_row_stride, w_box);
+    w_lo = planes == 2 ? make_tiled_map(f.w_pack.lo->p, bf16, cp.w_row_stride, cp.OC, cp.w_row_stride, w_box) : w_hi;
+
+    b200::IgemmParams prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.p_rows = cp.swapped ? cp.OC : (int)pixels;
+    prm.q_rows = cp.swapped ? (int)pixels : cp.OC;
+    prm.kblks_total = cp.kblks_total;
+    prm.kblks_per_split = cp.kblks_per_split;
+    prm.chunk_kblks = std::max(1, rtc.acc_chunk_kblks);
+    prm.p_im2col = cp.im2col ? 1 : 0;
+    prm.cblks = std::max(cp.cblks, 1); prm.kw = cp.KW; prm.ow = cp.OW; prm.ohw = cp.OH * cp.OW;
+    prm.sx = cp.sx; prm.sy = cp.sy; prm.px = cp.px; prm.py = cp.py;
+    prm.swapped = cp.swapped ? 1 : 0;
+    prm.out_chans = cp.OC; prm.out_hw = cp.OH * cp.OW;
+    prm.relu = cp.relu; prm.has_bias = bias ? 1 : 0; prm.bias = bias;
+    prm.p_scale = static_cast<float *>((cp.swapped ? f.w_pack : f.a_pack).scale2->p);
+    prm.q_scale = static_cast<float *>((cp.swapped ? f.a_pack : f.w_pack).scale2->p);
+    prm.idesc = b200::make_idesc_f16(bf16 ? 1u : 0u, 128, cp.BN);
+    long long const out_elems = (long long)cp.N * cp.OC * cp.OH * cp.OW;
+    if (cp.splits > 1) {
+      uint64_t const need = (uint64_t)cp.splits * out_elems * 4;
+      if (!f.splitk_ws || f.splitk_ws->bytes < need) { f.splitk_ws = std::make_shared<dev_buf_t>(need); }
+      prm.out = static_cast<float *>(f.splitk_ws->p);
+      prm.split_stride = out_elems;
+    } else {
+      prm.out = fptr(vout);
+      prm.split_stride = 0;
+    }
+    dim3 grid(ceil_div(prm.p_rows, b200::IGEMM_BM), ceil_div(prm.q_rows, cp.BN), cp.splits);
+    mark_kernel_begin();
+    if (cp.swapped) { launch_igemm(cp.BN, planes, grid, w_hi, w_lo, act_hi, act_lo, prm); }
+    else { launch_igemm(cp.BN, planes, grid, act_hi, act_lo, w_hi, w_lo, prm); }
+    mark_kernel_end();
+    if (cp.splits > 1) {
+      b200::splitk_reduce_kernel<<<ceil_div(out_elems, 256), 256, 0, st>>>(static_cast<float *>(f.splitk_ws->p), fptr(vout), bias, out_elems, cp.splits, cp.OC, cp.OH * cp.OW, cp.relu);
+      launched();
+    }
+    im.bump(vout);
+  }
+  static constexpr uint32_t IGEMM_BM_host() { return b200::IGEMM_BM; }
+
+  // c[M,N] = a[K,M]^T b[K,N]  (test/rtc/sgemm.cucl:1-3). P = a^T rows (M), Q = b^T rows (N), both packed K-major.
+  void run_sgemm() {
+    var_info_t &va = var("a"), &vb = var("b"), &vc = var("c");
+    if (va.dims.size() != 2 || vb.dims.size() != 2 || vc.dims.size() != 2) { unsup_err("sgemm expects 2-d a (K:M), b (K:N), c (M:N)"); }
+    int const K = va.dims.dsz("K"), M = va.dims.dsz("M"), N = vb.dims.dsz("N");
+    if ((int)vb.dims.dsz("K") != K || (int)vc.dims.dsz("M") != M || (int)vc.dims.dsz("N") != N) { rt_err("sgemm: inconsistent dims"); }
+    bool const bf16 = (rtc.prec == B200_PREC_BF16);
+    int const planes = (rtc.prec == B200_PREC_FP32_SPLIT) ? 2 : 1;
+    long long const Kpad = round_up(K, 64);
+    pack(f.a_pack, va, 1, K, M, (int)Kpad, Kpad, 0, (long long)M * Kpad, planes == 2, bf16);
+    pack(f.w_pack, vb, 1, K, N, (int)Kpad, Kpad, 0, (long long)N * Kpad, planes == 2, bf16);
+    int const BN = N > 64 ? 128 : (N > 32 ? 64 : 32);
+    CUtensorMap a_hi = make_tiled_map(f.a_pack.hi->p, bf16, Kpad, M, Kpad, b200::IGEMM_BM);
+    CUtensorMap a_lo = planes == 2 ? make_tiled_map(f.a_pack.lo->p, bf16, Kpad, M, Kpad, b200::IGEMM_BM) : a_hi;
+    CUtensorMap b_hi = make_tiled_map(f.w_pack.hi->p, bf16, Kpad, N, Kpad, BN);
+    CUtensorMap b_lo = planes == 2 ? make_tiled_map(f.w_pack.lo->p, bf16, Kpad, N, Kpad, BN) : b_hi;
+    b200::IgemmParams prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.p_rows = M; prm.q_rows = N;
+    prm.kblks_total = prm.kblks_per_split = (int)(Kpad / 64);
+    prm.chunk_kblks = std::max(1, rtc.acc_chunk_kblks);
+    prm.cblks = 1; prm.kw = 1; prm.ow = 1; prm.ohw = 1; prm.sx = prm.sy = 1;
+    prm.out_chans = N; prm.out_hw = 1;
+    prm.out = fptr(vc);
+    prm.p_scale = static_cast<float *>(f.a_pack.scale2->p);
+    prm.q_scale = static_cast<float *>(f.w_pack.scale2->p);
+    prm.idesc = b200::make_idesc_f16(bf16 ? 1u : 0u, 128, BN);
+    dim3 grid(ceil_div(M, b200::IGEMM_BM), ceil_div(N, BN), 1);
+    mark_kernel_begin();
+    launch_igemm(BN, planes, grid, a_hi, a_lo, b_hi, b_lo, prm);
+    mark_kernel_end();
+    im.bump(vc);
+  }
+
+  void run_pool() {
+    var_info_t &vin = var("in"), &vout = var("out");
+    check_nchw(vin.dims, "in"); check_nchw(vout.dims, "out");
+    int const H = vin.dims.dsz("y"), W = vin.dims.dsz("x"), OH = vout.dims.dsz("y"), OW = vout.dims.dsz("x");
+    int KH, KW, sy = 1, sx = 1, py = 0, px = 0;
+    if (f.op.has("kern_sz")) {
+      KH = f.op.yx("kern_sz", "y", 1); KW = f.op.yx("kern_sz", "x", 1);
+      sy = f.op.yx("stride", "y", 1); sx = f.op.yx("stride", "x", 1); py = f.op.yx("in_pad", "y", 0); px = f.op.yx("in_pad", "x", 0);
+      int const eoh = (H + 2 * py < KH) ? 1 : ceil_div(H + 2 * py - KH, sy) + 1, eow = (W + 2 * px < KW) ? 1 : ceil_div(W + 2 * px - KW, sx) + 1;
+      if (eoh != OH || eow != OW) { rt_err("pool: out dims " + vout.dims.pretty() + " do not match the Caffe ceil rule (" + str(eoh) + "x" + str(eow) + ")"); }
+    } else {  // global pooling (src/cnn_op.cc:39-45)
+      KH = H; KW = W;
+      if (OH != 1 || OW != 1) { rt_err("global pooling must produce 1x1 output"); }
+    }
+    if (vin.dims.dsz("img") != vout.dims.dsz("img") || vin.dims.dsz("chan") != vout.dims.dsz("chan")) { rt_err("pool: img/chan mismatch"); }
+    if (scalar("emit_out_in_yx", true, 0) != 0) { unsup_err("pool: emit_out_in_yx (training only) is out of scope for be=b200"); }
+    long long const n_out = vout.dims.dims_prod();
+    b200::pool_kernel<<<ceil_div(n_out, 256), 256, 0, st>>>(fptr(vin), fptr(vout), n_out, H, W, OH, OW, KH, KW, sy, sx, py, px, (int)scalar("avg_pool", true, 0));
+    launched();
+    im.bump(vout);
+  }
+
+  void run_lrn() {
+    var_info_t &vin = var("in"), &vout = var("out");
+    check_nchw(vin.dims, "in");
+    if (!(vin.dims == vout.dims)) { rt_err("lrn: in/out dims differ"); }
+    if (scalar("emit_out_scale_base", true, 0) != 0) { unsup_err("lrn: emit_out_scale_base (training only) is out of scope for be=b200"); }
+    int const C = vin.dims.dsz("chan"), HW = vin.dims.dsz("y") * vin.dims.dsz("x");
+    long long const n_pels = (long long)vin.dims.dsz("img") * HW;
+    int const ls = (int)scalar("local_size", true, 5);
+    float const alpha = (float)scalar("alpha", true, 1.0), beta = (float)scalar("beta", true, 0.75), k = (float)scalar("k", true, 1.0);
+    int const blocks = ceil_div(n_pels, 128);
+    if (ls == 5) { b200::lrn_kernel<5><<<blocks, 128, 0, st>>>(fptr(vin), fptr(vout), n_pels, C, HW, alpha, beta, k); }
+    else if (ls == 3) { b200::lrn_kernel<3><<<blocks, 128, 0, st>>>(fptr(vin), fptr(vout), n_pels, C, HW, alpha, beta, k); }
+    else if (ls <= 32) { b200::lrn_kernel_generic<<<blocks, 128, 0, st>>>(fptr(vin), fptr(vout), n_pels, C, HW, ls, alpha, beta, k); }
+    else { unsup_err("lrn: local_size > 32"); }
+    launched();
+    im.bump(vout);
+  }
+
+  void run_relu() {
+    var_info_t &v = var("inout");
+    long long const n = v.dims.dims_prod();
+    b200::relu_kernel<<<ceil_div(ceil_div(n, 4), 256), 256, 0, st>>>(fptr(v), n);
+    launched();
+    im.bump(v);
+  }
+
+  void run_softmax() {
+    var_info_t &vin = var("in"), &vout = var("prob");
+    check_nchw(vin.dims, "in");
+    if (!(vin.dims == vout.dims)) { rt_err("softmax: in/prob dims differ"); }
+    int const C = vin.dims.dsz("chan"), HW = vin.dims.dsz("y") * vin.dims.dsz("x");
+    long long const n_pels = (long long)vin.dims.dsz("img") * HW;
+    b200::softmax_kernel<<<ceil_div(n_pels * 32, 256), 256, 0, st>>>(fptr(vin), fptr(vout), n_pels, C, HW);
+    launched();
+    im.bump(vout);
+  }
+
+  void run_copy() {  // Concat piece: out[:, ocix:ocix+C] = in  (src/rtc_fwd.cc:267-280)
+    var_info_t &vin = var("in"), &vout = var("out");
+    check_nchw(vin.dims, "in"); check_nchw(vout.dims, "out");
+    int const ocix = (int)scalar("ocix");
+    int const C = vin.dims.dsz("chan"), HW = vin.dims.dsz("y") * vin.dims.dsz("x"), OC = vout.dims.dsz("chan"), n_img = vin.dims.dsz("img");
+    if (vout.dims.dsz("y") != vin.dims.dsz("y") || vout.dims.dsz("x") != vin.dims.dsz("x") || (int)vout.dims.dsz("img") != n_img || ocix + C > OC) { rt_err("copy: in does not fit into out at ocix"); }
+    long long const per_img = (long long)C * HW, out_img_stride = (long long)OC * HW, out_off = (long long)ocix * HW;
+    int const vec4 = ((per_img % 4) == 0 && (out_img_stride % 4) == 0 && (out_off % 4) == 0) ? 1 : 0;
+    long long const work = vec4 ? per_img * n_img / 4 : per_img * n_img;
+    b200::concat_copy_kernel<<<ceil_div(work, 256), 256, 0, st>>>(fptr(vin), fptr(vout), per_img, out_img_stride, out_off, n_img, vec4);
+    launched();
+    im.bump(vout);
+  }
+
+  void run_reduce() {
+    var_info_t &vout = var("out");
+    int const ins_num = (int)scalar("ins_num");
+    if (ins_num < 1 || ins_num > 8) { unsup_err("reduce: 1..8 inputs supported"); }
+    b200::ReduceArgs a;
+    a.ins_num = ins_num;
+    for (int i = 0; i < ins_num; ++i) {
+      var_info_t &vi = var("ins_" + str(i));
+      if (!(vi.dims == vout.dims)) { rt_err("reduce: input dims differ from out"); }
+      a.ins[i] = fptr(vi);
+    }
+    long long const n = vout.dims.dims_prod();
+    b200::reduce_sum_kernel<<<ceil_div(n, 256), 256, 0, st>>>(a, fptr(vout), n);
+    launched();
+    im.bump(vout);
+  }
+
+  void run_gen_data() {  // test/rtc/gen_data_*.cucl; the generator's name carries the op type and the argument
+    var_info_t &v = var(f.gen_arg);
+    string const &fn = f.op.get_func_name();
+    uint32_t const mode = (uint32_t)scalar("mode");
+    float const vi = (float)scalar("vi", true, 0.0);
+    long long const n = v.dims.dims_prod();
+    if (n >= (1ll << 32)) { unsup_err("gen_data: tensors >= 2^32 elements (the reference's flat index is uint32_t, src/boda_base.H:608)"); }
+    int kind; uint32_t inner = 1, inner2 = 1, salt;
+    if (fn == "gen_data_Convolution_in" || fn == "gen_data_Convolution_filts") {
+      kind = 0; inner = v.dims.dsz("x"); inner2 = v.dims.dsz("y"); salt = (f.gen_arg == "in") ? 234234567u : 8753985u;
+    } else if (fn == "gen_data_Convolution_biases") { kind = 1; salt = 39475612u; }
+    else if (fn == "gen_data_sgemm_a") { kind = 2; inner = v.dims.dsz("M"); inner2 = v.dims.dsz("K"); salt = 12738732u; }
+    else if (fn == "gen_data_sgemm_b") { kind = 3; inner = v.dims.dsz("N"); inner2 = v.dims.dsz("K"); salt = 12738732u; }
+    else { unsup_err("be=b200: unknown generator '" + fn + "'"); }
+    b200::gen_data_kernel<<<ceil_div(n, 256), 256, 0, st>>>(fptr(v), (uint32_t)n, kind, inner, inner2, mode, vi, salt);
+    launched();
+    im.bump(v);
+  }
+};
+
+}  // namespace
+
+uint32_t b200_compute_t::run(rtc_func_call_t const &rfc) {
+  assert_st(impl->inited);
+  auto fi = impl->funcs.find(rfc.rtc_func_name);
+  if (fi == impl->funcs.end()) { rt_err("run: function '" + rfc.rtc_func_name + "' was not compiled"); }
+  for (auto const &kv : rfc.arg_map) { if (!kv.second.is_valid()) { rt_err("run: invalid argument '" + kv.first + "'"); } }
+  call_ev_t ev;
+  if (impl->timing) {
+    CU_CHK(cudaEventCreate(&ev.b));
+    CU_CHK(cudaEventCreate(&ev.e));
+    CU_CHK(cudaEventRecord(ev.b, impl->stream));
+  }
+  run_ctx_t ctx{*this, *impl, fi->second, rfc, impl->stream, &ev};
+  switch (fi->second.kind) {
+    case FK_CONV: ctx.run_conv(); break;
+    case FK_SGEMM: ctx.run_sgemm(); break;
+    case FK_POOL: ctx.run_pool(); break;
+    case FK_LRN: ctx.run_lrn(); break;
+    case FK_RELU: ctx.run_relu(); break;
+    case FK_SOFTMAX: ctx.run_softmax(); break;
+    case FK_COPY: ctx.run_copy(); break;
+    case FK_REDUCE: ctx.run_reduce(); break;
+    case FK_GEN_DATA: ctx.run_gen_data(); break;
+  }
+  if (impl->timing) { CU_CHK(cudaEventRecord(ev.e, impl->stream)); }
+  impl->calls.push_back(ev);
+  return static_cast<uint32_t>(impl->calls.size() - 1);
+}
+
+}  // namespace boda

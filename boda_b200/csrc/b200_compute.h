@@ -1,0 +1,115 @@
+// b200_compute.h -- `be=b200`: a B200-native implementation of Boda's run-time compute interface.
+//
+// Mirrors rtc_compute_t (src/rtc_compute.H:35-97) method-for-method, with the same argument meaning and error
+// behaviour as the NVRTC back-end it replaces (nvrtc_compute_t, src/nvrtc_util.cc:174-395):
+//   * vars are owned by the back-end, keyed by unique name, zero-filled on creation (nvrtc_util.cc:81-84);
+//     duplicate names and unknown names are errors; reshaped views share storage (:136-138)
+//   * copy_nda_to_var / copy_var_to_nda require exact dims_t equality incl. names (:302-303)
+//   * compile() registers functions, run() launches one and returns a call_id usable with get_dur() (ms)
+//   * unsupported shapes throw unsup_exception, everything else rt_exception
+// What differs by design: compile() does not JIT generated source. It binds rtc_func_info_t.op (function name or op
+// type + dims + params) to a table of precompiled hand-written sm_100a kernels, and run() ignores tpb/blks: the
+// B200 kernels pick their own geometry (as the culibs escape hatch does, src/nvrtc_util.cc:369-373).
+#pragma once
+#include "boda_base.h"
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace boda {
+
+struct rtc_compile_opts_t {  // src/rtc_compute.H:10-22
+  uint32_t show_compile_log = 0, enable_lineinfo = 0, show_func_attrs = 0, show_rtc_calls = 0;
+};
+
+struct rtc_func_info_t {  // src/rtc_compute.H:24-29
+  string func_name;       // unique (generated) name the call will use
+  string func_src;        // ignored by this back-end (no run-time compilation)
+  vect_string arg_names;  // ignored: the kernel table knows its arguments
+  op_base_t op;
+};
+typedef vector<rtc_func_info_t> vect_rtc_func_info_t;
+
+struct rtc_arg_t {  // src/rtc_compute.H:103-115: a var name, or a by-value nda
+  rtc_arg_t() {}
+  rtc_arg_t(string const &n_) : n(n_) {}
+  rtc_arg_t(char const *n_) : n(n_) {}
+  rtc_arg_t(p_nda_t const &v_) : v(v_) {}
+  string n;
+  p_nda_t v;
+  bool is_valid() const { return bool(v) != (!n.empty()); }
+  bool is_var() const { assert_st(is_valid()); return !n.empty(); }
+  bool is_nda() const { assert_st(is_valid()); return bool(v); }
+  string const &get_var() const { assert_st(is_var()); return n; }
+  p_nda_t const &get_nda() const { assert_st(is_nda()); return v; }
+};
+typedef map<string, rtc_arg_t> map_str_rtc_arg_t;
+
+struct rtc_func_call_t {  // src/rtc_compute.H:120-126
+  string rtc_func_name;
+  map_str_rtc_arg_t arg_map;
+  uint32_t tpb = 0, blks = 0;  // accepted for signature compatibility; unused
+};
+
+struct b200_impl_t;  // kernel launchers + per-function derived state (packed operands, tensor maps)
+
+// numeric mode of the contraction kernels
+enum b200_prec_t {
+  B200_PREC_FP32_SPLIT = 0,  // fp32 parity: fp16 hi/lo planes, 3 tcgen05.mma per k-step (default)
+  B200_PREC_FP16 = 1,        // operands rounded to fp16, fp32 accumulate (BASELINE config C3)
+  B200_PREC_BF16 = 2,        // operands rounded to bf16, fp32 accumulate (BASELINE config C4)
+};
+
+struct b200_compute_t {
+  string be = "b200";
+  int device = 0;
+  b200_prec_t prec = B200_PREC_FP32_SPLIT;
+  int acc_chunk_kblks = 4;  // drain TMEM accumulators into fp32 registers every this many 64-wide k-blocks
+
+  b200_compute_t();
+  ~b200_compute_t();
+
+  void init();
+  string get_plat_tag();
+
+  void create_var_with_dims(string const &vn, dims_t const &dims);
+  void create_var_with_dims_as_reshaped_view_of_var(string const &vn, dims_t const &dims, string const &src_vn);
+  void release_var(string const &vn);
+  dims_t get_var_dims(string const &vn);
+  void set_var_to_zero(string const &vn);
+
+  void compile(vect_rtc_func_info_t const &func_infos, rtc_compile_opts_t const &opts);
+  void release_func(string const &func_name);
+  uint32_t run(rtc_func_call_t const &rfc);
+  void finish_and_sync();
+  void release_per_call_id_data();
+  void release_all_funcs();
+  float get_dur(uint32_t const &b, uint32_t const &e);  // ms, start of call b to end of call e
+  float get_kernel_dur(uint32_t const &id);             // ms of the call's main (contraction) kernel alone, without operand packing
+  void profile_start();
+  void profile_stop();
+
+  void copy_var_to_nda(p_nda_t const &nda, string const &vn);
+  void copy_nda_to_var(string const &vn, p_nda_t const &nda);
+  p_nda_t get_var_raw_native_pointer(string const &vn);
+  // layered helpers (src/rtc_compute.cc:30-97)
+  void create_var_from_nda(p_nda_t const &nda, string const &vn) { create_var_with_dims(vn, nda->dims); copy_nda_to_var(vn, nda); }
+  p_nda_t create_nda_from_var(string const &vn) { p_nda_t r = std::make_shared<nda_t>(get_var_dims(vn)); copy_var_to_nda(r, vn); return r; }
+
+  // --- extensions used by the C ABI / whole-net driver ---
+  bool has_var(string const &vn) const;
+  bool has_func(string const &fn) const;
+  void copy_raw_to_var(string const &vn, void const *src, uint64_t bytes);   // host -> device (async on the stream, then sync)
+  void copy_var_to_raw(void *dst, string const &vn, uint64_t bytes);
+  void copy_raw_to_var_async(string const &vn, void const *src, uint64_t bytes);
+  void copy_var_to_raw_async(void *dst, string const &vn, uint64_t bytes);
+  cudaStream_t stream() const;
+  uint64_t launches() const;  // number of kernels this back-end has launched so far (claimed in bench.py's gpu_launches)
+  void set_timing(bool on);   // per-call event recording on/off (off inside CUDA-graph capture)
+
+  b200_impl_t *impl;
+};
+typedef shared_ptr<b200_compute_t> p_b200_compute_t;
+
+void rtc_reshape_check(dims_t const &dims, dims_t const &src_dims);  // src/rtc_compute.cc:24-27
+
+}  // namespace boda

@@ -1,0 +1,367 @@
+// b200_conv_fwd.cu -- see b200_conv_fwd.h. Graph walk follows conv_pipe_fwd_t::init / gen_ops_rec / gen_op
+// (src/rtc_fwd.cc:469-527, :436-465, :263-405); every node is an fp32 NCHW var as in the reference, so
+// test_compute-style per-node comparison works on any node (src/test_compute.cc:165-169).
+#include "b200_conv_fwd.h"
+#include <algorithm>
+
+namespace boda {
+
+#define CU_CHK(x) do { cudaError_t const e_ = (x); if (e_ != cudaSuccess) { rt_err(string("CUDA error: ") + cudaGetErrorString(e_) + " in " #x " at " + __FILE__ + ":" + std::to_string(__LINE__)); } } while (0)
+
+namespace {
+vect_string split_colon(string const &s) {
+  vect_string r;
+  std::stringstream ss(s);
+  string item;
+  while (std::getline(ss, item, ':')) { if (!item.empty()) { r.push_back(item); } }
+  return r;
+}
+uint32_t ceil_div_u32(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+}  // namespace
+
+p_conv_node_t conv_pipe_t::get_or_make_node(string const &n) {
+  auto i = nodes.find(n);
+  if (i != nodes.end()) { return i->second; }
+  p_conv_node_t node = std::make_shared<conv_node_t>();
+  node->name = n;
+  node->dims = dims_t();
+  nodes[n] = node;
+  return node;
+}
+
+void conv_pipe_t::add_op_from_lexp(lexp_t const &l) {
+  if (p_lexp_t nl = l.find("node")) {  // source node declaration
+    p_conv_node_t node = get_or_make_node(nl->leaf);
+    p_lexp_t dl = l.find("dims");
+    if (!dl) { rt_err("pipe: node line needs dims"); }
+    node->dims = dims_from_lexp(*dl, "float");
+    data_node_names.push_back(node->name);
+    return;
+  }
+  p_conv_op_t op = std::make_shared<conv_op_t>();
+  fill_op_base_from_lexp(*op, l, {"tag", "bots", "tops"});
+  p_lexp_t tl = l.find("tag"), bl = l.find("bots"), tpl = l.find("tops");
+  if (!tl || !bl || !tpl) { rt_err("pipe: op line needs tag, bots and tops"); }
+  op->tag = tl->leaf;
+  op->bots = split_colon(bl->leaf);
+  op->tops = split_colon(tpl->leaf);
+  if (!op->has_type()) { rt_err("Operation has no type field; can't determine type."); }
+  for (auto const &o : ops) { if (o->tag == op->tag) { rt_err("pipe: duplicate op tag '" + op->tag + "'"); } }
+  op->in_place = (op->bots.size() == 1 && op->tops.size() == 1 && op->bots[0] == op->tops[0]);
+  if (op->is("Convolution")) {  // filts / biases are implicit parameter nodes named <tag>_filts / <tag>_biases (src/conv_util.cc:270-293)
+    if (op->bots.size() == 1) { op->bots.push_back(op->tag + "_filts"); op->bots.push_back(op->tag + "_biases"); }
+    if (op->bots.size() != 3) { rt_err("Convolution '" + op->tag + "' needs bots in[:filts:biases]"); }
+  }
+  for (auto const &b : op->bots) { get_or_make_node(b)->bot_for.push_back(op->tag); }
+  for (auto const &t : op->tops) {
+    p_conv_node_t tn = get_or_make_node(t);
+    if (op->in_place) { tn->in_place_ops.push_back(op); }
+    else { if (!tn->top_for.empty()) { rt_err("pipe: node '" + t + "' has multiple writers"); } tn->top_for.push_back(op->tag); }
+  }
+  ops.push_back(op);
+}
+
+void conv_pipe_t::calc_dims() {
+  for (auto const &op : ops) {
+    if (op->in_place) { if (must_get_node(op->bots[0])->dims.empty()) { rt_err("pipe: in-place op '" + op->tag + "' on node without dims"); } continue; }
+    dims_t const &din = must_get_node(op->bots[0])->dims;
+    if (din.empty()) { rt_err("pipe: op '" + op->tag + "' reads node '" + op->bots[0] + "' before it has dims (ops must be in topological order)"); }
+    uint32_t const N = din.dsz("img"), C = din.dsz("chan"), H = din.dsz("y"), W = din.dsz("x");
+    dims_t dout;
+    if (op->is("Convolution")) {
+      uint32_t const KH = op->yx("kern_sz", "y", 0), KW = op->yx("kern_sz", "x", 0);
+      if (!KH || !KW) { rt_err("Convolution '" + op->tag + "' needs kern_sz"); }
+      uint32_t const sy = op->yx("stride", "y", 1), sx = op->yx("stride", "x", 1), py = op->yx("in_pad", "y", 0), px = op->yx("in_pad", "x", 0);
+      uint32_t const OC = op->get_u32("out_chans");
+      if (H + 2 * py < KH || W + 2 * px < KW) { rt_err("Convolution '" + op->tag + "': padded input smaller than kernel"); }
+      dout = dims_t({N, OC, (H + 2 * py - KH) / sy + 1, (W + 2 * px - KW) / sx + 1}, {"img", "chan", "y", "x"}, "float");
+      p_conv_node_t fn = must_get_node(op->bots[1]), bn = must_get_node(op->bots[2]);
+      fn->dims = dims_t({OC, C, KH, KW}, {"out_chan", "in_chan", "y", "x"}, "float");
+      bn->dims = dims_t({OC}, {"out_chan"}, "float");
+      if (!fn->is_param) { fn->is_param = true; param_names.push_back(fn->name); }
+      if (!bn->is_param) { bn->is_param = true; param_names.push_back(bn->name); }
+    } else if (op->is("Pooling")) {
+      if (op->has("kern_sz")) {  // Caffe: any partial window makes an output (src/conv_util.cc:198-204)
+        uint32_t const KH = op->yx("kern_sz", "y", 1), KW = op->yx("kern_sz", "x", 1), sy = op->yx("stride", "y", 1), sx = op->yx("stride", "x", 1);
+        uint32_t const py = op->yx("in_pad", "y", 0), px = op->yx("in_pad", "x", 0);
+        uint32_t const OH = (H + 2 * py < KH) ? 1 : ceil_div_u32(H + 2 * py - KH, sy) + 1, OW = (W + 2 * px < KW) ? 1 : ceil_div_u32(W + 2 * px - KW, sx) + 1;
+        dout = dims_t({N, C, OH, OW}, {"img", "chan", "y", "x"}, "float");
+      } else { dout = dims_t({N, C, 1, 1}, {"img", "chan", "y", "x"}, "float"); }
+    } else if (op->is("LRN") || op->is("ReLU") || op->is("Dropout") || op->is("Softmax")) {
+      dout = din;
+    } else if (op->is("Concat")) {
+      uint32_t oc = 0;
+      for (auto const &b : op->bots) {
+        dims_t const &d = must_get_node(b)->dims;
+        if (d.empty() || d.dsz("img") != N || d.dsz("y") != H || d.dsz("x") != W) { rt_err("Concat '" + op->tag + "': inputs disagree in img/y/x"); }
+        oc += d.dsz("chan");
+      }
+      dout = dims_t({N, oc, H, W}, {"img", "chan", "y", "x"}, "float");
+    } else if (op->is("Eltwise") || op->is("Reduce")) {
+      for (auto const &b : op->bots) { if (!(must_get_node(b)->dims == din)) { rt_err("Eltwise '" + op->tag + "': input dims differ"); } }
+      dout = din;
+    } else {
+      rt_err("calc_dims: unhandled op of type: " + op->get_type());
+    }
+    for (auto const &t : op->tops) { must_get_node(t)->dims = dout; }
+  }
+}
+
+uint64_t conv_pipe_t::total_conv_flops() const {  // 2*B*OC*OH*OW*IC*KH*KW (src/latex-util.H:116-120)
+  uint64_t fl = 0;
+  for (auto const &op : ops) {
+    if (!op->is("Convolution")) { continue; }
+    dims_t const &o = must_get_node(op->tops[0])->dims, &f = must_get_node(op->bots[1])->dims;
+    fl += 2ull * o.dims_prod() * f.dsz("in_chan") * f.dsz("y") * f.dsz("x");
+  }
+  return fl;
+}
+
+p_conv_pipe_t make_conv_pipe_from_text(string const &pipe_text) {
+  p_conv_pipe_t cp = std::make_shared<conv_pipe_t>();
+  std::stringstream ss(pipe_text);
+  string line;
+  while (std::getline(ss, line)) {
+    line = detail::strip(line);
+    if (line.empty() || line[0] == '#') { continue; }
+    cp->add_op_from_lexp(*parse_lexp(line));
+  }
+  if (cp->data_node_names.empty()) { rt_err("pipe: no source (node=...) lines"); }
+  cp->calc_dims();
+  return cp;
+}
+
+// ---- b200_conv_fwd_t ------------------------------------------------------------------------------------------
+b200_conv_fwd_t::b200_conv_fwd_t() {}
+b200_conv_fwd_t::~b200_conv_fwd_t() {
+  if (flush_buf) { cudaFree(flush_buf); }
+  if (graph_exec) { cudaGraphExecDestroy(graph_exec); }
+  if (graph) { cudaGraphDestroy(graph); }
+}
+
+void b200_conv_fwd_t::add_call(string const &fn_base, conv_op_t const &op, op_base_t const &fop, map_str_rtc_arg_t const &args) {
+  fwd_call_t c;
+  c.tag = op.tag;
+  c.func_name = fn_base + "__" + op.tag + "__" + str(fwd_calls.size());
+  rtc_func_info_t fi;
+  fi.func_name = c.func_name;
+  fi.op = fop;
+  fi.op.set_func_name(fn_base);
+  rtc->compile({fi}, rtc_compile_opts_t());
+  c.rfc.rtc_func_name = c.func_name;
+  c.rfc.arg_map = args;
+  fwd_calls.push_back(c);
+  double fl = 0.0;  // algorithmic FLOPs: 2*B*OC*OH*OW*IC*KH*KW for conv (src/latex-util.H:116-120); bandwidth ops count none
+  if (fn_base == "conv") { dims_t const &o = fop.get_dims("out"), &f = fop.get_dims("filts"); fl = 2.0 * o.dims_prod() * f.dsz("in_chan") * f.dsz("y") * f.dsz("x"); }
+  call_flops.push_back(fl);
+}
+
+void b200_conv_fwd_t::gen_op(p_conv_op_t const &op) {
+  if (op->fused) { return; }  // folded into its producer (src/rtc_fwd.cc:266)
+  op_base_t fop;              // function signature: op params + the dims of every argument (conv_op_t::set_arg_dims_and_map_from_pipe)
+  fop.str_vals = op->str_vals;
+  fop.nda_vals = op->nda_vals;
+  if (op->is("Convolution")) {
+    fop.set_dims("in", cp->must_get_node(op->bots[0])->dims);
+    fop.set_dims("filts", cp->must_get_node(op->bots[1])->dims);
+    fop.set_dims("biases", cp->must_get_node(op->bots[2])->dims);
+    fop.set_dims("out", cp->must_get_node(op->tops[0])->dims);
+    // conv+ReLU fusion: only if ReLU is the FIRST in-place op on the conv's output node (src/rtc_fwd.cc:486-494)
+    p_conv_node_t on = cp->must_get_node(op->tops[0]);
+    bool relu = false;
+    if (!on->in_place_ops.empty() && on->in_place_ops[0]->is("ReLU")) { relu = true; on->in_place_ops[0]->fused = true; }
+    fop.set_u32("conv_has_relu", relu ? 1 : 0);
+    add_call("conv", *op, fop, {{"in", op->bots[0]}, {"filts", op->bots[1]}, {"biases", op->bots[2]}, {"out", op->tops[0]}});
+  } else if (op->is("Pooling")) {
+    add_call("pool", *op, fop, {{"in", op->bots[0]}, {"out", op->tops[0]}});
+  } else if (op->is("LRN")) {
+    add_call("lrn", *op, fop, {{"in", op->bots[0]}, {"out", op->tops[0]}});
+  } else if (op->is("ReLU")) {
+    if (!op->in_place) { rt_err("ReLU '" + op->tag + "' must be in-place (src/rtc_fwd.cc:337)"); }
+    add_call("relu", *op, fop, {{"inout", op->bots[0]}});
+  } else if (op->is("Dropout")) {
+    if (!op->in_place) { rt_err("non-in-place Dropout becomes `clone`, which rtc_fwd cannot run (src/caffepb.cc:235-238)"); }
+    // test-phase forward: identity
+  } else if (op->is("Softmax")) {
+    add_call("softmax", *op, fop, {{"in", op->bots[0]}, {"prob", op->tops[0]}});
+  } else if (op->is("Concat")) {  // one copy per input at a running channel offset (src/rtc_fwd.cc:267-280)
+    uint32_t chans_out_done = 0;
+    for (auto const &b : op->bots) {
+      op_base_t cop = fop;
+      cop.set_u32("ocix", chans_out_done);
+      add_call("copy", *op, cop, {{"in", b}, {"out", op->tops[0]}});
+      chans_out_done += cp->must_get_node(b)->dims.dsz("chan");
+    }
+  } else if (op->is("Eltwise") || op->is("Reduce")) {
+    map_str_rtc_arg_t args{{"out", op->tops[0]}};
+    for (size_t i = 0; i < op->bots.size(); ++i) { args["ins_" + str(i)] = op->bots[i]; }
+    fop.set_u32("ins_num", (uint32_t)op->bots.size());
+    add_call("reduce", *op, fop, args);
+  } else {
+    rt_err("gen_op: unhandled op of type: " + op->get_type());  // src/rtc_fwd.cc:402-404
+  }
+}
+
+void b200_conv_fwd_t::init(p_conv_pipe_t const &cp_, string const &opts) {
+  cp = cp_;
+  rtc = std::make_shared<b200_compute_t>();
+  if (!opts.empty()) {
+    p_lexp_t l = parse_lexp(opts);
+    if (!l->is_leaf) {
+      for (auto const &kv : l->kids) {
+        string const &k = kv.first, &v = kv.second->leaf;
+        if (k == "prec") { rtc->prec = (v == "fp32") ? B200_PREC_FP32_SPLIT : (v == "fp16") ? B200_PREC_FP16 : (v == "bf16") ? B200_PREC_BF16 : (rt_err("unknown prec '" + v + "'"), B200_PREC_FP32_SPLIT); }
+        else if (k == "use_graph") { use_graph = (uint32_t)std::stoul(v); }
+        else if (k == "acc_chunk_kblks") { rtc->acc_chunk_kblks = std::stoi(v); }
+        else if (k == "device") { rtc->device = std::stoi(v); }
+        else if (k == "enable_prof") { enable_prof = (uint32_t)std::stoul(v); }
+        else { rt_err("mode=b200: unused option '" + k + "'"); }  // NESI rejects unused keys (src/nesi.cc:25-35)
+      }
+    }
+  }
+  rtc->init();
+  for (auto const &kv : cp->nodes) {  // one zero-filled fp32 var per pipe node
+    if (kv.second->dims.empty()) { rt_err("pipe: node '" + kv.first + "' has no dims (unused / unreachable?)"); }
+    rtc->create_var_with_dims(kv.first, kv.second->dims);
+  }
+  for (auto const &op : cp->ops) { gen_op(op); }
+  info_log = "mode=b200 plat=" + rtc->get_plat_tag() + " nodes=" + str(cp->nodes.size()) + " ops=" + str(cp->ops.size()) + " fwd_calls=" + str(fwd_calls.size()) +
+             " conv_flops=" + str(cp->total_conv_flops());
+}
+
+void b200_conv_fwd_t::set_param(string const &node_name, float const *src, uint64_t n_elems) {
+  p_conv_node_t n = cp->must_get_node(node_name);
+  if (n->dims.dims_prod() != n_elems) { rt_err("set_param '" + node_name + "': got " + str(n_elems) + " elements, node holds " + str(n->dims.dims_prod())); }
+  rtc->copy_raw_to_var(node_name, src, n_elems * 4);
+}
+
+void b200_conv_fwd_t::run_calls() {
+  for (auto const &c : fwd_calls) { rtc->run(c.rfc); }
+}
+
+void b200_conv_fwd_t::ensure_graph() {
+  if (!warmed) {  // first pass eager: allocates packed-operand buffers, packs weights, sets kernel attributes
+    uint64_t const l0 = rtc->launches();
+    rtc->set_timing(false);
+    run_calls();
+    rtc->finish_and_sync();
+    run_calls();  // second pass = steady state (weights cached): count kernels per forward
+    rtc->finish_and_sync();
+    uint64_t const l1 = rtc->launches();
+    run_calls();
+    rtc->finish_and_sync();
+    kernels_per_fwd = rtc->launches() - l1;
+    (void)l0;
+    warmed = true;
+  }
+  if (use_graph && !graph_exec) {
+    rtc->set_timing(false);
+    uint64_t const l0 = rtc->launches();
+    CU_CHK(cudaStreamBeginCapture(rtc->stream(), cudaStreamCaptureModeThreadLocal));
+    try { run_calls(); } catch (...) { cudaGraph_t g = nullptr; cudaStreamEndCapture(rtc->stream(), &g); if (g) { cudaGraphDestroy(g); } throw; }
+    CU_CHK(cudaStreamEndCapture(rtc->stream(), &graph));
+    CU_CHK(cudaGraphInstantiate(&graph_exec, graph, 0));
+    kernels_per_fwd = rtc->launches() - l0;
+  }
+}
+
+void b200_conv_fwd_t::run_fwd_raw(int n_set, char const *const *set_names, float const *const *set_bufs, uint64_t const *set_elems, int n_get,
+                                  char const *const *get_names, float *const *get_bufs, uint64_t const *get_elems) {
+  for (int i = 0; i < n_set; ++i) {
+    p_conv_node_t n = cp->must_get_node(set_names[i]);
+    if (n->dims.dims_prod() != set_elems[i]) { rt_err(string("run_fwd: input '") + set_names[i] + "' has " + str(set_elems[i]) + " elements, node holds " + str(n->dims.dims_prod())); }
+    rtc->copy_raw_to_var_async(set_names[i], set_bufs[i], set_elems[i] * 4);
+  }
+  for (int i = 0; i < n_get; ++i) {
+    p_conv_node_t n = cp->must_get_node(get_names[i]);
+    if (n->dims.dims_prod() != get_elems[i]) { rt_err(string("run_fwd: output '") + get_names[i] + "' has " + str(get_elems[i]) + " elements, node holds " + str(n->dims.dims_prod())); }
+  }
+  ensure_graph();
+  if (use_graph) { CU_CHK(cudaGraphLaunch(graph_exec, rtc->stream())); graph_launches += kernels_per_fwd; }
+  else { rtc->set_timing(false); run_calls(); }
+  for (int i = 0; i < n_get; ++i) { rtc->copy_var_to_raw_async(get_bufs[i], get_names[i], get_elems[i] * 4); }
+  rtc->finish_and_sync();
+}
+
+void b200_conv_fwd_t::run_fwd(vect_string const &to_set_vns, p_map_str_p_nda_float_t const &fwd, vect_string const &to_get_vns) {
+  vector<char const *> sn, gn;
+  vector<float const *> sb;
+  vector<float *> gb;
+  vector<uint64_t> se, ge;
+  for (auto const &vn : to_set_vns) {
+    auto i = fwd->find(vn);
+    if (i == fwd->end()) { rt_err("run_fwd: input '" + vn + "' not in fwd map"); }
+    if (!(i->second->dims == cp->must_get_node(vn)->dims)) { rt_err("run_fwd: dims mismatch for input '" + vn + "'"); }
+    sn.push_back(vn.c_str()); sb.push_back(static_cast<float *>(i->second->rp_elems())); se.push_back(i->second->elems_sz());
+  }
+  for (auto const &vn : to_get_vns) {  // created if absent; overwritten if dims match (src/rtc_compute.cc:92-97)
+    dims_t const &d = cp->must_get_node(vn)->dims;
+    auto i = fwd->find(vn);
+    if (i == fwd->end()) { (*fwd)[vn] = std::make_shared<nda_float_t>(d); i = fwd->find(vn); }
+    else if (!(i->second->dims == d)) { rt_err("run_fwd: dims mismatch for output '" + vn + "'"); }
+    gn.push_back(vn.c_str()); gb.push_back(static_cast<float *>(i->second->rp_elems())); ge.push_back(d.dims_prod());
+  }
+  run_fwd_raw((int)sn.size(), sn.data(), sb.data(), se.data(), (int)gn.size(), gn.data(), gb.data(), ge.data());
+}
+
+float b200_conv_fwd_t::run_device_only(int iters) {
+  ensure_graph();
+  cudaEvent_t b, e;
+  CU_CHK(cudaEventCreate(&b));
+  CU_CHK(cudaEventCreate(&e));
+  rtc->set_timing(false);
+  CU_CHK(cudaEventRecord(b, rtc->stream()));
+  for (int i = 0; i < iters; ++i) {
+    if (use_graph) { CU_CHK(cudaGraphLaunch(graph_exec, rtc->stream())); graph_launches += kernels_per_fwd; }
+    else { run_calls(); }
+  }
+  CU_CHK(cudaEventRecord(e, rtc->stream()));
+  CU_CHK(cudaEventSynchronize(e));
+  float ms = 0;
+  CU_CHK(cudaEventElapsedTime(&ms, b, e));
+  cudaEventDestroy(b);
+  cudaEventDestroy(e);
+  return ms / std::max(iters, 1);
+}
+
+vector<b200_conv_fwd_t::prof_row_t> b200_conv_fwd_t::profile(int iters) {
+  ensure_graph();
+  vector<prof_row_t> res;
+  for (size_t i = 0; i < fwd_calls.size(); ++i) { res.push_back(prof_row_t{fwd_calls[i].func_name, 0.0f, 0.0f, i < call_flops.size() ? call_flops[i] : 0.0}); }
+  rtc->set_timing(true);
+  for (int it = 0; it < iters; ++it) {
+    rtc->release_per_call_id_data();
+    vector<uint32_t> ids;
+    for (auto const &c : fwd_calls) { ids.push_back(rtc->run(c.rfc)); }
+    rtc->finish_and_sync();
+    for (size_t i = 0; i < ids.size(); ++i) { res[i].call_ms += rtc->get_dur(ids[i], ids[i]) / iters; res[i].kernel_ms += rtc->get_kernel_dur(ids[i]) / iters; }
+  }
+  rtc->release_per_call_id_data();
+  rtc->set_timing(false);
+  return res;
+}
+
+vector<float> b200_conv_fwd_t::run_timed(int iters, uint64_t l2_flush_bytes) {
+  ensure_graph();
+  if (l2_flush_bytes > flush_bytes) {
+    if (flush_buf) { cudaFree(flush_buf); flush_buf = nullptr; }
+    CU_CHK(cudaMalloc(&flush_buf, l2_flush_bytes));
+    flush_bytes = l2_flush_bytes;
+  }
+  rtc->set_timing(false);
+  vector<cudaEvent_t> evb(iters), eve(iters);
+  for (int i = 0; i < iters; ++i) { CU_CHK(cudaEventCreate(&evb[i])); CU_CHK(cudaEventCreate(&eve[i])); }
+  for (int i = 0; i < iters; ++i) {
+    if (l2_flush_bytes) { CU_CHK(cudaMemsetAsync(flush_buf, i & 0xff, l2_flush_bytes, rtc->stream())); }
+    CU_CHK(cudaEventRecord(evb[i], rtc->stream()));
+    if (use_graph) { CU_CHK(cudaGraphLaunch(graph_exec, rtc->stream())); graph_launches += kernels_per_fwd; }
+    else { run_calls(); }
+    CU_CHK(cudaEventRecord(eve[i], rtc->stream()));
+  }
+  rtc->finish_and_sync();
+  vector<float> ms(iters, 0.0f);
+  for (int i = 0; i < iters; ++i) { CU_CHK(cudaEventElapsedTime(&ms[i], evb[i], eve[i])); cudaEventDestroy(evb[i]); cudaEventDestroy(eve[i]); }
+  return ms;
+}
+
+}  // namespace boda

@@ -1,0 +1,85 @@
+// b200_conv_fwd.h -- `mode=b200`: whole-net forward over be=b200, mirroring has_conv_fwd_t (src/has_conv_fwd.H:16-25)
+// as implemented by conv_pipe_fwd_t (src/rtc_fwd.cc:43-577), plus the slice of the conv_pipe graph IR it needs
+// (conv_op_t / conv_node_t / conv_pipe_t, src/conv_util.H:75-243; dims rules src/conv_util.cc:167-226, :405-529).
+#pragma once
+#include "b200_compute.h"
+
+namespace boda {
+
+struct conv_op_t : public op_base_t {  // src/conv_util.H:112-141
+  string tag;
+  vect_string bots, tops;
+  bool in_place = false;  // single bot == single top (ReLU / Dropout written onto their input node)
+  bool fused = false;     // folded into the producer (conv+ReLU, src/rtc_fwd.cc:486-494)
+  bool is(string const &t) const { return has_type() && get_type() == t; }
+};
+typedef shared_ptr<conv_op_t> p_conv_op_t;
+
+struct conv_node_t {  // src/conv_util.H:152-170
+  string name;
+  dims_t dims;
+  vect_string top_for, bot_for;
+  vector<p_conv_op_t> in_place_ops;
+  bool is_param = false;  // filts / biases (conv_pipe_t::op_params)
+};
+typedef shared_ptr<conv_node_t> p_conv_node_t;
+
+struct conv_pipe_t {  // src/conv_util.H:172-243
+  map<string, p_conv_node_t> nodes;
+  vector<p_conv_op_t> ops;  // topological (file) order
+  vect_string data_node_names, param_names;
+  p_conv_node_t must_get_node(string const &n) const { auto i = nodes.find(n); if (i == nodes.end()) { rt_err("pipe: no node named '" + n + "'"); } return i->second; }
+  p_conv_node_t get_or_make_node(string const &n);
+  void add_op_from_lexp(lexp_t const &l);
+  void calc_dims();  // src/conv_util.cc:405-529
+  uint64_t total_conv_flops() const;
+};
+typedef shared_ptr<conv_pipe_t> p_conv_pipe_t;
+p_conv_pipe_t make_conv_pipe_from_text(string const &pipe_text);
+
+struct fwd_call_t { string func_name, tag; rtc_func_call_t rfc; };
+
+struct b200_conv_fwd_t {
+  string mode = "b200";
+  // options (conv_pipe_fwd_t fields, src/rtc_fwd.cc:48-66, reduced to what applies)
+  uint32_t use_graph = 1;      // replay the forward calls as one CUDA graph (launch-bound at B200 speeds)
+  uint32_t enable_prof = 0;
+  p_b200_compute_t rtc;
+  p_conv_pipe_t cp;
+  vector<fwd_call_t> fwd_calls;
+  string info_log;
+
+  b200_conv_fwd_t();
+  ~b200_conv_fwd_t();
+  void init(p_conv_pipe_t const &cp_, string const &opts);  // has_conv_fwd_t::init
+  void set_det_drop_seed(uint32_t const &) {}              // dropout is stripped from fwd graphs (src/caffepb.cc:235-238)
+  void run_fwd(vect_string const &to_set_vns, p_map_str_p_nda_float_t const &fwd, vect_string const &to_get_vns);
+  string get_info_log() { return info_log; }
+
+  // raw-buffer variants used by the C ABI
+  void set_param(string const &node_name, float const *src, uint64_t n_elems);
+  void run_fwd_raw(int n_set, char const *const *set_names, float const *const *set_bufs, uint64_t const *set_elems, int n_get,
+                   char const *const *get_names, float *const *get_bufs, uint64_t const *get_elems);
+  float run_device_only(int iters);  // ms per forward, CUDA-event timed on the back-end's stream
+  struct prof_row_t { string func_name; float call_ms, kernel_ms; double flops; };
+  vector<prof_row_t> profile(int iters);
+  // `iters` forwards, each bracketed by its own CUDA events on the back-end's stream; when l2_flush_bytes > 0 a scratch buffer of that size is
+  // overwritten before every forward (outside the events) so no iteration starts with a warm L2. Returns ms per forward.
+  vector<float> run_timed(int iters, uint64_t l2_flush_bytes);
+  uint64_t launches() const { return rtc->launches() + graph_launches; }
+
+ private:
+  void gen_op(p_conv_op_t const &op);
+  void add_call(string const &fn_base, conv_op_t const &op, op_base_t const &fop, map_str_rtc_arg_t const &args);
+  void run_calls();
+  void ensure_graph();
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  uint64_t graph_launches = 0, kernels_per_fwd = 0;
+  bool warmed = false;
+  void *flush_buf = nullptr;
+  uint64_t flush_bytes = 0;
+  vector<double> call_flops;
+};
+
+}  // namespace boda

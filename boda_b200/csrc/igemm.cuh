@@ -1,0 +1,276 @@
+// igemm.cuh -- the tensor-core contraction kernel behind Boda's conv / k1conv / tconv / ipconv / sgemm functions
+// (replaces test/rtc/{conv,tconv,k1conv,ipconv,sgemm}.cucl + src/cnn_codegen.cc's generated FMA loops).
+//
+//   D[P rows x Q rows] = sum_k  Pop[p, k] * Qop[q, k]            (both operands K-major, 16-bit, in "planes")
+//
+// * Pop is either a plain 2-d K-major matrix (sgemm, 1x1 convs, inner-product-shaped convs, swapped weights) read with
+//   tiled TMA, or an NHWC activation tensor read with *im2col* TMA: the hardware walks 128 consecutive output pixels
+//   (n,oy,ox) for one filter tap (ky,kx) and one 64-channel block, zero-filling padding taps.
+// * Qop is always a plain 2-d K-major matrix (packed filters, or the activation matrix in swapped mode).
+// * fp32-parity mode (kPlanes == 2): every fp32 operand x is carried as two fp16 planes, hi = fp16(s*x) and
+//   lo = fp16(s*x - hi) (s a per-tensor power of two), and each k-step issues three tcgen05.mma:
+//   hi*hi into the main TMEM accumulator, hi*lo + lo*hi into a separate cross-term accumulator (2^-11 the magnitude,
+//   so the tensor core's truncating fp32 accumulation costs it nothing). That recovers ~22 bits of each product -- the
+//   reference kernels are fp32 FFMA, and its compare tolerance (2e-4 .. 1e-3 mrd) cannot be met by one fp16/bf16/tf32 pass.
+//   kPlanes == 1 is the single-pass fp16 / bf16 storage mode (BASELINE configs C3 / C4).
+// * Tensor-core accumulation drift: TMEM accumulators are drained every `chunk_kblks` k-blocks into fp32 registers of
+//   the epilogue warps (round-to-nearest adds) while the MMA warp continues into the second TMEM buffer.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue
+// (TMEM lane quarter = warp_id % 4).
+#pragma once
+#include "umma.cuh"
+#include <cuda_fp16.h>
+
+namespace b200 {
+
+constexpr int IGEMM_BM = 128;      // rows of the P operand per CTA (UMMA M)
+constexpr int IGEMM_BK = 64;       // K elements per k-block: 64 x 2 B = one 128-byte swizzle row
+constexpr int IGEMM_UMMA_K = 16;   // K per tcgen05.mma for 16-bit operands
+constexpr int IGEMM_THREADS = 192;
+
+struct IgemmParams {
+  // problem extents
+  int p_rows;       // valid rows of P (output pixels; or out-chans when swapped)
+  int q_rows;       // valid rows of Q
+  int kblks_total;  // number of 64-wide k-blocks over the whole K
+  int kblks_per_split;
+  int chunk_kblks;  // drain TMEM into registers every this many k-blocks (>= kblks_per_split: single chunk)
+  // P-operand addressing
+  int p_im2col;     // 0: tiled 2-d {k, row}; 1: im2col
+  int cblks;        // im2col: 64-channel blocks per filter tap
+  int kw;           // im2col: filter width (taps are enumerated ky-major)
+  int ow, ohw;      // im2col: output width, output pixels per image
+  int sx, sy, px, py;
+  // epilogue
+  int swapped;      // 0: P rows = pixels, Q rows = channels; 1: P rows = channels, Q rows = pixels
+  int out_chans;    // channels of the NCHW output
+  int out_hw;       // pixels per image of the NCHW output
+  int relu;
+  int has_bias;
+  long long split_stride;  // elements between split-K partial buffers (0 when writing final output)
+  float *out;              // NCHW fp32 output, or split-K workspace
+  float const *bias;       // per out-chan
+  float const *p_scale;    // {scale, inv_scale} of the P tensor
+  float const *q_scale;
+  uint32_t idesc;
+};
+
+template <int BN, int kPlanes>
+struct IgemmCfg {
+  static constexpr int kStageBytes = kPlanes * (IGEMM_BM * 128 + BN * 128);
+  static constexpr int kMaxSmem = 220 * 1024;
+  static constexpr int kStagesRaw = (kMaxSmem - 2048) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 1024 /*barriers*/;
+  // TMEM columns: two ping-pong buffers for the main (hi*hi) accumulator + one for the cross-term (hi*lo + lo*hi)
+  // accumulator in split mode; allocation must be a power of two >= 32
+  static constexpr uint32_t kColsNeeded = (kPlanes == 2 ? 3 : 2) * BN;
+  static constexpr uint32_t kTmemCols = kColsNeeded <= 32 ? 32 : kColsNeeded <= 64 ? 64 : kColsNeeded <= 128 ? 128 : kColsNeeded <= 256 ? 256 : 512;
+};
+
+template <int BN, int kPlanes>
+__global__ void __launch_bounds__(IGEMM_THREADS, 1)
+igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_constant__ CUtensorMap p_lo_map,
+                  const __grid_constant__ CUtensorMap q_hi_map, const __grid_constant__ CUtensorMap q_lo_map,
+                  const IgemmParams prm) {
+  using Cfg = IgemmCfg<BN, kPlanes>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr uint32_t kPBytes = IGEMM_BM * 128, kQBytes = BN * 128;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *bar_mem = smem + kStages * Cfg::kStageBytes;
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(bar_mem);
+  uint64_t *empty_bar = full_bar + kStages;
+  uint64_t *tmem_full_bar = empty_bar + kStages;   // [2]
+  uint64_t *tmem_empty_bar = tmem_full_bar + 2;    // [2]
+  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
+
+  int const warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int const m0 = blockIdx.x * IGEMM_BM;
+  int const n0 = blockIdx.y * BN;
+  int const split = blockIdx.z;
+  int const kb_begin = split * prm.kblks_per_split;
+  int const kb_end = min(kb_begin + prm.kblks_per_split, prm.kblks_total);
+  int const nkb = kb_end - kb_begin;
+  int const chunk = prm.chunk_kblks;
+  int const nchunks = (nkb + chunk - 1) / chunk;
+
+  if (warp_id == 0 && lane == 0) {
+    tma_prefetch_desc(&p_hi_map);
+    tma_prefetch_desc(&q_hi_map);
+    if (kPlanes == 2) { tma_prefetch_desc(&p_lo_map); tma_prefetch_desc(&q_lo_map); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp_id == 1) { tmem_alloc<Cfg::kTmemCols>(tmem_ptr_smem); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t const tmem_base = *tmem_ptr_smem;
+
+  if (warp_id == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int img = 0, h_base = 0, w_base = 0;
+      if (prm.p_im2col) {
+        img = m0 / prm.ohw;
+        int const rem = m0 - img * prm.ohw;
+        int const oy = rem / prm.ow, ox = rem - oy * prm.ow;
+        h_base = oy * prm.sy - prm.py;
+        w_base = ox * prm.sx - prm.px;
+      }
+      for (int i = 0; i < nkb; ++i) {
+        int const kb = kb_begin + i;
+        int const s = i % kStages;
+        uint32_t const ph = (i / kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+        uint8_t *st = smem + s * Cfg::kStageBytes;
+        uint8_t *p_hi = st, *p_lo = st + kPBytes;
+        uint8_t *q_hi = st + kPlanes * kPBytes, *q_lo = q_hi + kQBytes;
+        if (prm.p_im2col) {
+          int const tap = kb / prm.cblks, cb = kb - tap * prm.cblks;
+          int const ky = tap / prm.kw, kx = tap - ky * prm.kw;
+          tma_load_im2col_4d(p_hi, &p_hi_map, &full_bar[s], cb * IGEMM_BK, w_base, h_base, img, (uint16_t)kx, (uint16_t)ky);
+          if (kPlanes == 2) {
+            tma_load_im2col_4d(p_lo, &p_lo_map, &full_bar[s], cb * IGEMM_BK, w_base, h_base, img, (uint16_t)kx, (uint16_t)ky);
+          }
+        } else {
+          tma_load_2d(p_hi, &p_hi_map, &full_bar[s], kb * IGEMM_BK, m0);
+          if (kPlanes == 2) { tma_load_2d(p_lo, &p_lo_map, &full_bar[s], kb * IGEMM_BK, m0); }
+        }
+        tma_load_2d(q_hi, &q_hi_map, &full_bar[s], kb * IGEMM_BK, n0);
+        if (kPlanes == 2) { tma_load_2d(q_lo, &q_lo_map, &full_bar[s], kb * IGEMM_BK, n0); }
+      }
+    }
+  } else if (warp_id == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t const idesc = prm.idesc;
+      int i = 0;
+      for (int c = 0; c < nchunks; ++c) {
+        int const buf = c & 1;
+        mbar_wait(&tmem_empty_bar[buf], ((c >> 1) & 1) ^ 1);
+        tc_fence_after();
+        uint32_t const tmem_d = tmem_base + buf * BN;
+        uint32_t const tmem_x = tmem_base + 2 * BN;  // cross-term accumulator: 2^-11 of the main one, drained once at the end
+        int const i_end = min(i + chunk, nkb);
+        bool first = true;
+        for (; i < i_end; ++i) {
+          int const s = i % kStages;
+          uint32_t const ph = (i / kStages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          uint32_t const st = smem_u32(smem + s * Cfg::kStageBytes);
+          uint64_t const p_hi = make_kmajor_sw128_desc(st), p_lo = make_kmajor_sw128_desc(st + kPBytes);
+          uint64_t const q_hi = make_kmajor_sw128_desc(st + kPlanes * kPBytes);
+          uint64_t const q_lo = make_kmajor_sw128_desc(st + kPlanes * kPBytes + kQBytes);
+#pragma unroll
+          for (int k = 0; k < IGEMM_BK / IGEMM_UMMA_K; ++k) {
+            uint64_t const adv = static_cast<uint64_t>((k * IGEMM_UMMA_K * 2) >> 4);  // +32 B per k-step inside the swizzle row
+            umma_f16(tmem_d, p_hi + adv, q_hi + adv, idesc, first ? 0u : 1u);
+            first = false;
+            if (kPlanes == 2) {
+              umma_f16(tmem_x, p_hi + adv, q_lo + adv, idesc, (i == 0 && k == 0) ? 0u : 1u);
+              umma_f16(tmem_x, p_lo + adv, q_hi + adv, idesc, 1u);
+            }
+          }
+          umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
+        }
+        umma_commit(&tmem_full_bar[buf]);  // accumulator chunk complete
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    int const q = warp_id & 3;  // TMEM lane quarter this warp may read
+    int const row = q * 32 + lane;
+    float acc[BN];
+#pragma unroll
+    for (int j = 0; j < BN; ++j) { acc[j] = 0.0f; }
+    for (int c = 0; c < nchunks; ++c) {
+      int const buf = c & 1;
+      mbar_wait(&tmem_full_bar[buf], (c >> 1) & 1);
+      tc_fence_after();
+      uint32_t const taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
+#pragma unroll
+      for (int j0 = 0; j0 < BN; j0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + j0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { acc[j0 + j] += __uint_as_float(r[j]); }
+      }
+      if (kPlanes == 2 && c == nchunks - 1) {  // the last commit also covers every cross-term MMA
+        uint32_t const xaddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 2 * BN;
+#pragma unroll
+        for (int j0 = 0; j0 < BN; j0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(xaddr + j0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { acc[j0 + j] += __uint_as_float(r[j]); }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&tmem_empty_bar[buf]); }
+    }
+    // ---- write out: NCHW fp32 (or split-K partial) ----
+    float const inv = prm.p_scale[1] * prm.q_scale[1];
+    int const prow = m0 + row;
+    if (prow < prm.p_rows) {
+      float *outp = prm.out + static_cast<long long>(split) * prm.split_stride;
+      bool const final_out = (prm.split_stride == 0);
+      if (!prm.swapped) {
+        int const img = prow / prm.out_hw, pix = prow - img * prm.out_hw;
+        float *o = outp + (static_cast<long long>(img) * prm.out_chans) * prm.out_hw + pix;
+#pragma unroll
+        for (int j = 0; j < BN; ++j) {
+          int const ch = n0 + j;
+          if (ch < prm.q_rows) {
+            float v = acc[j] * inv;
+            if (final_out) {
+              if (prm.has_bias) { v += __ldg(prm.bias + ch); }
+              if (prm.relu) { v = fmaxf(v, 0.0f); }
+            }
+            o[static_cast<long long>(ch) * prm.out_hw] = v;
+          }
+        }
+      } else {
+        int const ch = prow;
+        float const b = (final_out && prm.has_bias) ? __ldg(prm.bias + ch) : 0.0f;
+#pragma unroll
+        for (int j = 0; j < BN; ++j) {
+          int const pel = n0 + j;
+          if (pel < prm.q_rows) {
+            int const img = pel / prm.out_hw, pix = pel - img * prm.out_hw;
+            float v = acc[j] * inv + b;
+            if (final_out && prm.relu) { v = fmaxf(v, 0.0f); }
+            outp[(static_cast<long long>(img) * prm.out_chans + ch) * prm.out_hw + pix] = v;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_id == 1) { tmem_dealloc<Cfg::kTmemCols>(tmem_base); }
+}
+
+// split-K fix-up: out[i] = relu( sum_s ws[s][i] + bias[chan(i)] )   (deterministic order)
+__global__ void splitk_reduce_kernel(float const *__restrict__ ws, float *__restrict__ out, float const *__restrict__ bias,
+                                     long long n, int splits, int out_chans, int out_hw, int relu) {
+  long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) { return; }
+  float v = 0.0f;
+  for (int s = 0; s < splits; ++s) { v += ws[s * n + i]; }
+  if (bias) { v += __ldg(bias + (i / out_hw) % out_chans); }
+  if (relu) { v = fmaxf(v, 0.0f); }
+  out[i] = v;
+}
+
+}  // namespace b200

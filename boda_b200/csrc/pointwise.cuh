@@ -1,0 +1,284 @@
+// pointwise.cuh -- the bandwidth-bound functions of Boda's rtc_fwd path as hand-written sm_100a kernels:
+// gen_data_* (test inputs), pool, lrn, relu, softmax, copy (Concat), reduce (N-ary sum), plus the operand
+// "pack" kernels (abs-max -> power-of-two scale -> transpose + fp16 hi/lo split) that feed the tensor-core kernel.
+// All activations are fp32 NCHW (`img:chan:y:x`) exactly as in the reference (src/conv_util.cc:482-503).
+#pragma once
+#include <cstdint>
+#include <cfloat>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+
+namespace b200 {
+
+// ---- gen_data (test/rtc/gen-util.h:1-9 and test/rtc/gen_data_*.cucl) -----------------------------------------
+__device__ __forceinline__ float det_hash_rand(uint32_t rv) {
+  uint32_t h = rv;
+  h ^= h >> 16;
+  h *= 0x85ebca6bu;
+  h ^= h >> 13;
+  h *= 0xc2b2ae35u;
+  h ^= h >> 16;
+  return __fmaf_rn((float)(h), (10.0f / (float)(0xFFFFFFFFu)), -5.0f);  // one fused op, as NVRTC's fmad=true compiles the reference
+}
+
+// kind: 0 = Convolution_in / Convolution_filts style 4-d (x,y modes), 1 = biases, 2 = sgemm_a (K:M), 3 = sgemm_b (K:N)
+__global__ void gen_data_kernel(float *__restrict__ dst, uint32_t n, int kind, uint32_t inner /*x | M | N*/,
+                                uint32_t inner2 /*y | K*/, uint32_t mode, float vi, uint32_t salt) {
+  uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) { return; }
+  float val = vi;
+  if (kind == 0) {
+    uint32_t const x = i % inner, y = (i / inner) % inner2;
+    if (mode == 2) { val += (float)x; }
+    if (mode == 3) { val += (float)y; }
+    else if (mode == 4) { if ((x == inner / 2) && (y == inner2 / 2)) { val += 1.0f; } }
+    else if (mode == 5) { val += det_hash_rand(i + salt); }
+  } else if (kind == 1) {
+    if (mode == 5) { val += det_hash_rand(i + salt); }
+  } else if (kind == 2) {
+    uint32_t fin_mode = mode;
+    if (fin_mode >= 100) { fin_mode = fin_mode / 100; }
+    uint32_t const m = i % inner, k = i / inner;
+    if (fin_mode == 2) { val += (float)m; }
+    if (fin_mode == 3) { val += (float)k; }
+    else if (fin_mode == 4) { if ((m == inner / 2) && (k == inner2 / 2)) { val += 1.0f; } }
+    else if (fin_mode == 5) { val += det_hash_rand(i + salt); }
+    else if (fin_mode == 6) { val += (float)(m * 1000 + k); }
+  } else {
+    uint32_t const nn = i % inner, k = i / inner;
+    if (mode == 2) { val += (float)nn; }
+    if (mode == 3) { val += (float)k; }
+    else if (mode == 4) { if ((nn == inner / 2) && (k == inner2 / 2)) { val += 1.0f; } }
+    else if (mode == 5) { val += det_hash_rand(i + salt); }
+    else if (mode >= 100) { if (nn == k) { val += 1.0f; } }
+  }
+  dst[i] = val;
+}
+
+// ---- relu (test/rtc/relu.cucl) --------------------------------------------------------------------------------
+__global__ void relu_kernel(float *__restrict__ x, long long n) {
+  long long const i4 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4;
+  if (i4 + 3 < n && ((reinterpret_cast<uintptr_t>(x) & 15) == 0)) {
+    float4 v = *reinterpret_cast<float4 *>(x + i4);
+    v.x = (v.x <= 0) ? 0.0f : v.x; v.y = (v.y <= 0) ? 0.0f : v.y; v.z = (v.z <= 0) ? 0.0f : v.z; v.w = (v.w <= 0) ? 0.0f : v.w;
+    *reinterpret_cast<float4 *>(x + i4) = v;
+  } else {
+    for (long long i = i4; i < n && i < i4 + 4; ++i) { x[i] = (x[i] <= 0) ? 0.0f : x[i]; }
+  }
+}
+
+// ---- copy / Concat (test/rtc/copy.cucl) -----------------------------------------------------------------------
+// in: [N][C][HW] -> out[:, ocix:ocix+C]; per image the source block is contiguous, so move 128-bit words when aligned.
+__global__ void concat_copy_kernel(float const *__restrict__ in, float *__restrict__ out, long long per_img /*C*HW*/,
+                                   long long out_img_stride, long long out_off, int n_img, int vec4) {
+  long long const total = per_img * n_img;
+  if (vec4) {
+    long long const i4 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4;
+    if (i4 >= total) { return; }
+    long long const img = i4 / per_img, r = i4 - img * per_img;
+    float4 const v = __ldg(reinterpret_cast<float4 const *>(in + i4));
+    *reinterpret_cast<float4 *>(out + img * out_img_stride + out_off + r) = v;
+  } else {
+    long long const i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i >= total) { return; }
+    long long const img = i / per_img, r = i - img * per_img;
+    out[img * out_img_stride + out_off + r] = __ldg(in + i);
+  }
+}
+
+// ---- reduce: N-ary elementwise sum (test/rtc/reduce.cucl) ------------------------------------------------------
+struct ReduceArgs { float const *ins[8]; int ins_num; };
+__global__ void reduce_sum_kernel(ReduceArgs a, float *__restrict__ out, long long n) {
+  long long const i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) { return; }
+  float v = 0;
+  for (int j = 0; j < a.ins_num; ++j) { v += __ldg(a.ins[j] + i); }
+  out[i] = v;
+}
+
+// ---- pool (test/rtc/pool.cucl:13-40) --------------------------------------------------------------------------
+__global__ void pool_kernel(float const *__restrict__ in, float *__restrict__ out, long long n_out, int H, int W, int OH,
+                            int OW, int KH, int KW, int sy, int sx, int py, int px, int avg_pool) {
+  long long const i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n_out) { return; }
+  int const ox = static_cast<int>(i % OW), oy = static_cast<int>((i / OW) % OH);
+  long long const plane = i / (static_cast<long long>(OW) * OH);
+  float const *ip = in + plane * H * W;
+  float out_v = avg_pool ? 0.0f : -FLT_MAX;
+  float avg_pool_sz = 0;
+  for (int kx = 0; kx != KW; ++kx) {
+    for (int ky = 0; ky != KH; ++ky) {
+      int const in_y = oy * sy + ky - py, in_x = ox * sx + kx - px;
+      if (in_y >= 0 && in_x >= 0 && in_x < W && in_y < H) {
+        float const v = __ldg(ip + in_y * W + in_x);
+        if (avg_pool) { out_v += v; avg_pool_sz += 1; }
+        else if (v > out_v) { out_v = v; }
+      }
+    }
+  }
+  if (avg_pool) { out_v = __fdiv_rn(out_v, avg_pool_sz); }
+  out[i] = out_v;
+}
+
+// ---- lrn (test/rtc/lrn.cucl:35-50, LRN_MATCH_CAFFE branch) ----------------------------------------------------
+// One thread per (img,y,x) walking the channels with the running add-new / subtract-old sum of squares; consecutive
+// threads are consecutive x so every channel step is a coalesced 128-byte row. kLS = local_size (ring in registers).
+template <int kLS>
+__global__ void lrn_kernel(float const *__restrict__ in, float *__restrict__ out, long long n_pels, int C, int HW, float alpha,
+                           float beta, float k) {
+  long long const pel = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (pel >= n_pels) { return; }
+  long long const img = pel / HW;
+  long long const base = img * C * HW + (pel - img * HW);
+  constexpr int hls = kLS >> 1;
+  float const alpha_over_ls = alpha / (float)kLS;
+  float ls_buf[kLS];
+#pragma unroll
+  for (int i = 0; i < kLS; ++i) { ls_buf[i] = 0.0f; }
+  float ls_sum = 0.0f;
+  // the ring index is kept compile-time by unrolling kLS channel steps per trip
+  for (int c0 = 0; c0 < C + hls; c0 += kLS) {
+#pragma unroll
+    for (int u = 0; u < kLS; ++u) {
+      int const ic = c0 + u;
+      if (ic < C + hls) {
+        float const ls_old = ls_buf[u];
+        ls_buf[u] = (ic < C) ? __ldg(in + base + static_cast<long long>(ic) * HW) : 0.0f;
+        ls_sum = __fmaf_rn(ls_buf[u], ls_buf[u], ls_sum);
+        ls_sum = __fmaf_rn(-ls_old, ls_old, ls_sum);
+        if (ic >= hls) {
+          float const scale_base = __fmaf_rn(ls_sum, alpha_over_ls, k);
+          float const scale = powf(scale_base, -beta);
+          out[base + static_cast<long long>(ic - hls) * HW] = ls_buf[(u + kLS - hls) % kLS] * scale;
+        }
+      }
+    }
+  }
+}
+
+// generic local_size fallback (ring in local memory)
+__global__ void lrn_kernel_generic(float const *__restrict__ in, float *__restrict__ out, long long n_pels, int C, int HW,
+                                   int local_size, float alpha, float beta, float k) {
+  long long const pel = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (pel >= n_pels) { return; }
+  long long const img = pel / HW;
+  long long const base = img * C * HW + (pel - img * HW);
+  int const hls = local_size >> 1;
+  float const alpha_over_ls = alpha / (float)local_size;
+  float ls_buf[32];
+  for (int i = 0; i < local_size; ++i) { ls_buf[i] = 0.0f; }
+  float ls_sum = 0.0f;
+  for (int ic = 0; ic < C + hls; ++ic) {
+    int const lsb_ix = ic % local_size;
+    float const ls_old = ls_buf[lsb_ix];
+    ls_buf[lsb_ix] = (ic < C) ? __ldg(in + base + static_cast<long long>(ic) * HW) : 0.0f;
+    ls_sum = __fmaf_rn(ls_buf[lsb_ix], ls_buf[lsb_ix], ls_sum);
+    ls_sum = __fmaf_rn(-ls_old, ls_old, ls_sum);
+    if (ic >= hls) {
+      float const scale_base = __fmaf_rn(ls_sum, alpha_over_ls, k);
+      out[base + static_cast<long long>(ic - hls) * HW] = ls_buf[(lsb_ix + local_size - hls) % local_size] * powf(scale_base, -beta);
+    }
+  }
+}
+
+// ---- softmax over chan (test/rtc/softmax.cucl:6-21; running max starts at 0.0f) -------------------------------
+// One warp per (img,y,x): lanes stride the channel dim, shuffle-reduce max and sum.
+__global__ void softmax_kernel(float const *__restrict__ in, float *__restrict__ prob, long long n_pels, int C, int HW) {
+  long long const pel = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  int const lane = threadIdx.x & 31;
+  if (pel >= n_pels) { return; }
+  long long const img = pel / HW;
+  long long const base = img * C * HW + (pel - img * HW);
+  float pel_max = 0.0f;
+  for (int c = lane; c < C; c += 32) { pel_max = fmaxf(pel_max, __ldg(in + base + static_cast<long long>(c) * HW)); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { pel_max = fmaxf(pel_max, __shfl_xor_sync(0xffffffffu, pel_max, o)); }
+  float pel_sum = 0.0f;
+  for (int c = lane; c < C; c += 32) {
+    float const v = expf(__ldg(in + base + static_cast<long long>(c) * HW) - pel_max);
+    prob[base + static_cast<long long>(c) * HW] = v;
+    pel_sum += v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { pel_sum += __shfl_xor_sync(0xffffffffu, pel_sum, o); }
+  for (int c = lane; c < C; c += 32) { prob[base + static_cast<long long>(c) * HW] = __fdiv_rn(prob[base + static_cast<long long>(c) * HW], pel_sum); }
+}
+
+// ---- operand pack: abs-max -> power-of-two scale -> transpose + 16-bit split ----------------------------------
+// absmax over a tensor (non-negative floats order like their bit patterns, so atomicMax on uint works).
+__global__ void absmax_kernel(float const *__restrict__ x, long long n, unsigned int *__restrict__ out_bits) {
+  float m = 0.0f;
+  long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride) { m = fmaxf(m, fabsf(__ldg(x + i))); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o)); }
+  if ((threadIdx.x & 31) == 0 && m > 0.0f) { atomicMax(out_bits, __float_as_uint(m)); }
+}
+// scale = 2^(13 - floor(log2(absmax))) so that scaled values land in [2^13, 2^14) -- well inside fp16 range with the
+// lo-plane residuals (>= 2^-12 relative) still mostly normal. Writes {scale, 1/scale} and re-arms the abs-max cell.
+// mode 0: fixed scale 1 (bf16 storage / caller opts out).
+__global__ void finalize_scale_kernel(unsigned int *__restrict__ bits, float *__restrict__ scale2, int use_scale) {
+  float const m = __uint_as_float(*bits);
+  float s = 1.0f;
+  if (use_scale && m > 0.0f && isfinite(m)) {
+    int e;
+    frexpf(m, &e);  // m = f * 2^e, f in [0.5,1)  -> floor(log2 m) = e-1
+    int sh = 13 - (e - 1);
+    sh = max(-100, min(100, sh));
+    s = ldexpf(1.0f, sh);
+  }
+  scale2[0] = s;
+  scale2[1] = 1.0f / s;
+  *bits = 0u;
+}
+
+// src [B][R][C] fp32 (C contiguous)  ->  dst planes [B][C][Rpad] 16-bit (R contiguous, zero padded to Rpad):
+//   NCHW activations  (B=img, R=chan, C=y*x)        -> NHWC  [img][y*x][chan_pad]
+//   OIHW filters      (B=out_chan, R=in_chan, C=ky*kx) -> [out_chan][ky*kx][chan_pad]  (K-major rows for the Q operand)
+//   sgemm a  K:M      (B=1, R=K, C=M)               -> [M][Kpad]
+// hi = cvt(s*x), lo = cvt(s*x - hi) (lo plane optional). kBf16 selects bf16 instead of fp16 storage.
+// Tile: 64 (R) x 32 (C); loads are 128-byte rows along C, stores are 128-byte rows of half2 along R.
+template <bool kBf16>
+__global__ void __launch_bounds__(256)
+pack_xpose_split_kernel(float const *__restrict__ src, uint16_t *__restrict__ hi, uint16_t *__restrict__ lo, float const *__restrict__ scale2,
+                        int R, int C, int Rpad, long long dst_c_stride, long long dst_b_stride) {
+  __shared__ float tile[64][33];
+  int const tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  int const r0 = blockIdx.x * 64, c0 = blockIdx.y * 32;
+  long long const b = blockIdx.z;
+  float const s = scale2[0];
+  float const *sp = src + b * static_cast<long long>(R) * C;
+#pragma unroll
+  for (int rr = ty; rr < 64; rr += 8) {
+    int const r = r0 + rr, c = c0 + tx;
+    tile[rr][tx] = (r < R && c < C) ? __ldg(sp + static_cast<long long>(r) * C + c) * s : 0.0f;
+  }
+  __syncthreads();
+  int const r = r0 + 2 * tx;
+  if (r < Rpad) {
+#pragma unroll
+    for (int cc = ty; cc < 32; cc += 8) {
+      int const c = c0 + cc;
+      if (c < C) {
+        float const v0 = tile[2 * tx][cc], v1 = tile[2 * tx + 1][cc];
+        long long const o = b * dst_b_stride + static_cast<long long>(c) * dst_c_stride + r;
+        if (kBf16) {
+          __nv_bfloat16 const h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+          *reinterpret_cast<__nv_bfloat162 *>(hi + o) = __nv_bfloat162(h0, h1);
+          if (lo) {
+            *reinterpret_cast<__nv_bfloat162 *>(lo + o) =
+                __nv_bfloat162(__float2bfloat16_rn(v0 - __bfloat162float(h0)), __float2bfloat16_rn(v1 - __bfloat162float(h1)));
+          }
+        } else {
+          __half const h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+          *reinterpret_cast<__half2 *>(hi + o) = __half2(h0, h1);
+          if (lo) {
+            *reinterpret_cast<__half2 *>(lo + o) = __half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
+          }
+        }
+      }
+    }
+  }
+}
+
+}  // namespace b200

@@ -1,0 +1,205 @@
+"""Net descriptions in Boda's op-line text form (one conv_op_t per line) for has_conv_fwd_t::init, plus synthetic
+parameter generation.
+
+The reference builds its conv_pipe from Caffe prototxts (src/caffepb.cc:166-326); no prototxt or caffemodel travels
+with this repo, so the architectures of the BASELINE configs are restated here from nets/<name>/train_val.prototxt
+(TEST phase: Data/Accuracy/SoftmaxWithLoss layers dropped, src/caffepb.cc:250-261; Dropout kept as an in-place
+identity). Weights are synthetic: the reference's deterministic hash (test/rtc/gen-util.h) scaled He-style so
+activations stay O(input) through the net (no caffemodel ships with the reference either, INSTALL.md:199-209).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+
+class PipeBuilder:
+    def __init__(self):
+        self.lines: List[str] = []
+        self.convs: List[Tuple[str, int, int, int, int]] = []  # tag, OC, C, KH, KW (filled lazily by param_shapes)
+
+    def data(self, name: str, img: int, chan: int, y: int, x: int):
+        self.lines.append("(node=%s,dims=(img=%d,chan=%d,y=%d,x=%d))" % (name, img, chan, y, x))
+        return name
+
+    def conv(self, tag: str, bot: str, top: str, out_chans: int, k, stride=1, pad=0, relu: Optional[str] = None):
+        ky, kx = (k, k) if isinstance(k, int) else k
+        self.lines.append(
+            "(tag=%s,str_vals=(type=Convolution),nda_vals=(kern_sz=(tn=none,dims=(y=%d,x=%d)),stride=(tn=none,dims=(y=%d,x=%d)),"
+            "in_pad=(tn=none,dims=(y=%d,x=%d)),out_chans=(tn=uint32_t,v=%d)),bots=%s,tops=%s)" % (tag, ky, kx, stride, stride, pad, pad, out_chans, bot, top))
+        if relu:
+            self.relu(relu, top)
+        return top
+
+    def relu(self, tag: str, node: str):
+        self.lines.append("(tag=%s,str_vals=(type=ReLU),bots=%s,tops=%s)" % (tag, node, node))
+        return node
+
+    def dropout(self, tag: str, node: str, ratio: float = 0.5):
+        self.lines.append("(tag=%s,str_vals=(type=Dropout),nda_vals=(dropout_ratio=(tn=float,v=%g)),bots=%s,tops=%s)" % (tag, ratio, node, node))
+        return node
+
+    def lrn(self, tag: str, bot: str, top: str, local_size=5, alpha=1e-4, beta=0.75, k=1.0):
+        self.lines.append("(tag=%s,str_vals=(type=LRN),nda_vals=(local_size=(tn=uint32_t,v=%d),alpha=(tn=float,v=%r),beta=(tn=float,v=%r),k=(tn=float,v=%r)),bots=%s,tops=%s)"
+                          % (tag, local_size, float(alpha), float(beta), float(k), bot, top))
+        return top
+
+    def pool(self, tag: str, bot: str, top: str, k: Optional[int], stride=1, pad=0, avg=False):
+        if k is None:  # global pooling
+            nda = "avg_pool=(tn=uint32_t,v=%d)" % (1 if avg else 0)
+        else:
+            nda = ("avg_pool=(tn=uint32_t,v=%d),kern_sz=(tn=none,dims=(y=%d,x=%d)),stride=(tn=none,dims=(y=%d,x=%d)),in_pad=(tn=none,dims=(y=%d,x=%d))"
+                   % (1 if avg else 0, k, k, stride, stride, pad, pad))
+        self.lines.append("(tag=%s,str_vals=(type=Pooling),nda_vals=(%s),bots=%s,tops=%s)" % (tag, nda, bot, top))
+        return top
+
+    def concat(self, tag: str, bots: List[str], top: str):
+        self.lines.append("(tag=%s,str_vals=(type=Concat),bots=%s,tops=%s)" % (tag, ":".join(bots), top))
+        return top
+
+    def eltwise(self, tag: str, bots: List[str], top: str):
+        self.lines.append("(tag=%s,str_vals=(type=Eltwise),bots=%s,tops=%s)" % (tag, ":".join(bots), top))
+        return top
+
+    def softmax(self, tag: str, bot: str, top: str):
+        self.lines.append("(tag=%s,str_vals=(type=Softmax),bots=%s,tops=%s)" % (tag, bot, top))
+        return top
+
+    def text(self) -> str:
+        return "\n".join(self.lines) + "\n"
+
+
+def alexnet_ng_conv(batch: int = 32, in_sz: int = 227) -> Tuple[str, str, str]:
+    """nets/alexnet_ng_conv/train_val.prototxt (BASELINE config C2). Returns (pipe_text, input node, output node)."""
+    p = PipeBuilder()
+    p.data("data", batch, 3, in_sz, in_sz)
+    p.conv("conv1", "data", "conv1", 96, 11, 4, 0, relu="relu1")
+    p.lrn("norm1", "conv1", "norm1")
+    p.pool("pool1", "norm1", "pool1", 3, 2)
+    p.conv("conv2", "pool1", "conv2", 256, 5, 1, 2, relu="relu2")
+    p.lrn("norm2", "conv2", "norm2")
+    p.pool("pool2", "norm2", "pool2", 3, 2)
+    p.conv("conv3", "pool2", "conv3", 384, 3, 1, 1, relu="relu3")
+    p.conv("conv4", "conv3", "conv4", 384, 3, 1, 1, relu="relu4")
+    p.conv("conv5", "conv4", "conv5", 256, 3, 1, 1, relu="relu5")
+    p.pool("pool5", "conv5", "pool5", 3, 2)
+    p.conv("fc6-conv", "pool5", "fc6", 4096, 6, 1, 0, relu="relu6")
+    p.dropout("drop6", "fc6")
+    p.conv("fc7-conv", "fc6", "fc7", 4096, 1, 1, 0, relu="relu7")
+    p.dropout("drop7", "fc7")
+    p.conv("fc8-conv", "fc7", "fc8", 1000, 1, 1, 0)
+    return p.text(), "data", "fc8"
+
+
+def nin_imagenet(batch: int = 32, in_sz: int = 227) -> Tuple[str, str, str]:
+    """nets/nin_imagenet/train_val.prototxt: 4 x (kxk conv + two 1x1 cccp convs), max pools, 6x6 average pool."""
+    p = PipeBuilder()
+    p.data("data", batch, 3, in_sz, in_sz)
+    p.conv("conv1", "data", "conv1", 96, 11, 4, 0, relu="relu0")
+    p.conv("cccp1", "conv1", "cccp1", 96, 1, relu="relu1")
+    p.conv("cccp2", "cccp1", "cccp2", 96, 1, relu="relu2")
+    p.pool("pool0", "cccp2", "pool0", 3, 2)
+    p.conv("conv2", "pool0", "conv2", 256, 5, 1, 2, relu="relu3")
+    p.conv("cccp3", "conv2", "cccp3", 256, 1, relu="relu5")
+    p.conv("cccp4", "cccp3", "cccp4", 256, 1, relu="relu6")
+    p.pool("pool2", "cccp4", "pool2", 3, 2)
+    p.conv("conv3", "pool2", "conv3", 384, 3, 1, 1, relu="relu7")
+    p.conv("cccp5", "conv3", "cccp5", 384, 1, relu="relu8")
+    p.conv("cccp6", "cccp5", "cccp6", 384, 1, relu="relu9")
+    p.pool("pool3", "cccp6", "pool3", 3, 2)
+    p.dropout("drop", "pool3")
+    p.conv("conv4-1024", "pool3", "conv4", 1024, 3, 1, 1, relu="relu10")
+    p.conv("cccp7-1024", "conv4", "cccp7", 1024, 1, relu="relu11")
+    p.conv("cccp8-1024", "cccp7", "cccp8", 1000, 1, relu="relu12")
+    p.pool("pool4", "cccp8", "pool4", 6, 1, 0, avg=True)
+    return p.text(), "data", "pool4"
+
+
+def tiny_net(batch: int = 3) -> Tuple[str, str, str]:
+    """A small net touching every forward op kind (conv variants, LRN, max/avg/global pool, concat, eltwise, softmax)."""
+    p = PipeBuilder()
+    p.data("data", batch, 3, 31, 29)
+    p.conv("c1", "data", "c1", 24, 5, 2, 1, relu="r1")
+    p.lrn("n1", "c1", "n1", 5, 1e-2, 0.75, 1.0)
+    p.pool("p1", "n1", "p1", 3, 2)
+    p.conv("b1", "p1", "b1", 16, 1, relu="rb1")
+    p.conv("b2", "p1", "b2", 40, 3, 1, 1, relu="rb2")
+    p.pool("b3p", "p1", "b3p", 3, 1, 1)
+    p.conv("b3", "b3p", "b3", 8, 1, relu="rb3")
+    p.concat("cat", ["b1", "b2", "b3"], "cat")
+    p.conv("c2", "cat", "c2", 64, 3, 1, 1)
+    p.conv("c2b", "cat", "c2b", 64, 1, 1, 0)
+    p.eltwise("sum", ["c2", "c2b"], "sum")
+    p.relu("rsum", "sum")
+    p.pool("pa", "sum", "pa", 2, 2, 0, avg=True)
+    p.conv("fc", "pa", "fc", 10, (3, 3), 1, 0)
+    p.pool("gp", "fc", "gp", None, avg=True)
+    p.softmax("prob", "gp", "prob")
+    return p.text(), "data", "prob"
+
+
+# ---- synthetic parameters ----------------------------------------------------------------------------------------
+
+def _det_hash_rand(ix: np.ndarray) -> np.ndarray:
+    """The reference's input hash (test/rtc/gen-util.h:1-9), vectorised: uniform in [-5, 5]."""
+    h = ix.astype(np.uint32)
+    h ^= h >> np.uint32(16)
+    h = (h * np.uint32(0x85EBCA6B)).astype(np.uint32)
+    h ^= h >> np.uint32(13)
+    h = (h * np.uint32(0xC2B2AE35)).astype(np.uint32)
+    h ^= h >> np.uint32(16)
+    return (h.astype(np.float32).astype(np.float64) * (10.0 / 4294967296.0) - 5.0).astype(np.float32)
+
+
+def hash_fill(shape, salt: int, scale: float) -> np.ndarray:
+    n = int(np.prod(shape))
+    return (_det_hash_rand(np.arange(n, dtype=np.uint32) + np.uint32(salt & 0xFFFFFFFF)) * np.float32(scale)).reshape(shape).astype(np.float32)
+
+
+def conv_param_shapes(pipe_text: str) -> Dict[str, Tuple[int, ...]]:
+    """Walk the pipe text and return {<tag>_filts: (OC,C,KH,KW), <tag>_biases: (OC,)} with channel counts inferred."""
+    import re
+    chans: Dict[str, int] = {}
+    shapes: Dict[str, Tuple[int, ...]] = {}
+    for line in pipe_text.splitlines():
+        line = line.strip()
+        if not line:
+            continue
+        m = re.match(r"\(node=([^,]+),dims=\(img=(\d+),chan=(\d+),y=(\d+),x=(\d+)\)\)", line)
+        if m:
+            chans[m.group(1)] = int(m.group(3))
+            continue
+        tag = re.search(r"tag=([^,]+),", line).group(1)
+        typ = re.search(r"type=([A-Za-z]+)", line).group(1)
+        bots = re.search(r"bots=([^,)]+)", line).group(1).split(":")
+        tops = re.search(r"tops=([^,)]+)", line).group(1).split(":")
+        if typ == "Convolution":
+            oc = int(re.search(r"out_chans=\(tn=uint32_t,v=(\d+)\)", line).group(1))
+            ky, kx = map(int, re.search(r"kern_sz=\(tn=none,dims=\(y=(\d+),x=(\d+)\)\)", line).groups())
+            c = chans[bots[0]]
+            shapes[tag + "_filts"] = (oc, c, ky, kx)
+            shapes[tag + "_biases"] = (oc,)
+            chans[tops[0]] = oc
+        elif typ == "Concat":
+            chans[tops[0]] = sum(chans[b] for b in bots)
+        else:
+            chans[tops[0]] = chans[bots[0]]
+    return shapes
+
+
+def synth_params(pipe_text: str, seed: int = 0) -> Dict[str, np.ndarray]:
+    """filts ~ U(-a,a) with a = sqrt(6/K) (variance 2/K), biases ~ U(-0.5,0.5)/5: per-layer salts, no RNG state."""
+    out = {}
+    for i, (name, shape) in enumerate(sorted(conv_param_shapes(pipe_text).items())):
+        salt = 8753985 + 7919 * i + 104729 * seed
+        if name.endswith("_filts"):
+            k = shape[1] * shape[2] * shape[3]
+            out[name] = hash_fill(shape, salt, np.sqrt(6.0 / k) / 5.0)
+        else:
+            out[name] = hash_fill(shape, salt + 39475612, 0.1 / 5.0)
+    return out
+
+
+def synth_input(shape, seed: int = 0, scale: float = 25.0) -> np.ndarray:
+    return hash_fill(shape, 234234567 + 15485863 * seed, scale)

@@ -1,0 +1,97 @@
+/* boda_b200.h -- C ABI of libboda_b200.so: the drop-in boundary of the B200-native rtc_fwd back-end.
+ *
+ * Plain pointers, sizes and NUL-terminated strings only; no C++/torch types; no exceptions cross the boundary:
+ * every function returns 0 on success (or a non-negative id / handle where stated) and a negative code on
+ * failure, with the message available from b200_last_error(). Codes: -1 = rt_exception (reference: rt_err,
+ * src/boda_base.H:98-105), -2 = unsup_exception (unsup_err: shape/feature this back-end does not handle).
+ *
+ * Each entry point names the reference interface it replaces (paths relative to moskewcz/boda):
+ *   tier A = rtc_compute_t      src/rtc_compute.H:35-97   (implemented for `be=nvrtc` by src/nvrtc_util.cc:174-395)
+ *   tier B = has_conv_fwd_t     src/has_conv_fwd.H:16-25  (implemented for `mode=rtc` by src/rtc_fwd.cc:43-577)
+ * INTEGRATION.md shows the C++ adaptor classes a Boda maintainer adds to bind these (NESI type_id "b200").
+ */
+#ifndef BODA_B200_H_
+#define BODA_B200_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200_rtc b200_rtc;  /* one back-end instance == one rtc_compute_t object (one device, one stream) */
+typedef struct b200_fwd b200_fwd;  /* one has_conv_fwd_t object */
+
+/* ---- library ---- */
+const char *b200_last_error(void);                 /* message of the last failure on this thread */
+const char *b200_version(void);
+int b200_device_count(void);                       /* number of CUDA devices visible (0 on a CPU-only box) */
+
+/* ---- tier A: rtc_compute_t ---- */
+b200_rtc *b200_rtc_create(void);                   /* NESI construction of `(be=b200)`; never touches the GPU */
+void b200_rtc_destroy(b200_rtc *r);
+int b200_rtc_set_option(b200_rtc *r, const char *key, const char *val); /* "prec"=fp32|fp16|bf16, "acc_chunk_kblks"=N, "device"=N */
+int b200_rtc_init(b200_rtc *r);                    /* rtc_compute_t::init()            src/rtc_compute.H:45 */
+const char *b200_rtc_get_plat_tag(b200_rtc *r);    /* ::get_plat_tag()                 :46 */
+/* ::create_var_with_dims(vn, dims)  :48  -- dims as element type name + named sizes; new vars are zero-filled */
+int b200_rtc_create_var(b200_rtc *r, const char *vn, const char *tn, int ndims, const char *const *dim_names, const uint32_t *dim_sizes);
+/* ::create_var_with_dims_as_reshaped_view_of_var  :49 */
+int b200_rtc_create_view(b200_rtc *r, const char *vn, const char *tn, int ndims, const char *const *dim_names, const uint32_t *dim_sizes, const char *src_vn);
+int b200_rtc_release_var(b200_rtc *r, const char *vn);           /* ::release_var       :50 */
+/* ::get_var_dims  :51 -- returns ndims (<= max_dims filled), dim names are written as a ':'-joined string */
+int b200_rtc_get_var_dims(b200_rtc *r, const char *vn, int max_dims, uint32_t *dim_sizes, char *names_buf, int names_buf_len);
+int b200_rtc_set_var_to_zero(b200_rtc *r, const char *vn);       /* ::set_var_to_zero   :52 */
+/* ::compile(func_infos, opts)  :55 -- binds `func_name` to a precompiled sm_100a kernel chosen from the op text
+ * (current or stale op-line syntax). No source is compiled at run time. */
+int b200_rtc_compile(b200_rtc *r, const char *func_name, const char *op_text);
+int b200_rtc_release_func(b200_rtc *r, const char *func_name);   /* ::release_func      :56 */
+/* ::run(rtc_func_call_t)  :59 -- arg_vals[i] is a var name, or an nda literal "(tn=uint32_t,v=5)" passed by value.
+ * Returns the call id (>= 0). tpb/blks of the reference call struct are not needed. */
+int b200_rtc_run(b200_rtc *r, const char *func_name, int nargs, const char *const *arg_names, const char *const *arg_vals);
+int b200_rtc_finish_and_sync(b200_rtc *r);                       /* ::finish_and_sync   :60 */
+int b200_rtc_release_per_call_id_data(b200_rtc *r);              /* ::release_per_call_id_data :61 */
+int b200_rtc_release_all_funcs(b200_rtc *r);                     /* ::release_all_funcs :62 */
+int b200_rtc_get_dur(b200_rtc *r, uint32_t b, uint32_t e, float *ms_out); /* ::get_dur(b,e) in ms  :70 */
+int b200_rtc_get_kernel_dur(b200_rtc *r, uint32_t call_id, float *ms_out); /* the call's contraction kernel alone (no operand packing) */
+/* ::copy_nda_to_var / ::copy_var_to_nda  :79-81 -- host buffers; `bytes` must equal the var's size */
+int b200_rtc_copy_to_var(b200_rtc *r, const char *vn, const void *host_src, uint64_t bytes);
+int b200_rtc_copy_from_var(b200_rtc *r, void *host_dst, const char *vn, uint64_t bytes);
+/* ::get_var_raw_native_pointer  :80 -- device pointer (for external low-level libs) */
+int b200_rtc_get_var_raw_native_pointer(b200_rtc *r, const char *vn, void **dev_ptr_out);
+uint64_t b200_rtc_launches(b200_rtc *r);           /* kernels launched so far by this instance */
+
+/* ---- tier B: has_conv_fwd_t ---- */
+/* has_conv_fwd_t::init(conv_pipe, nia)  src/has_conv_fwd.H:21 (conv_pipe_fwd_t::init, src/rtc_fwd.cc:469-527).
+ * `pipe_text`: one conv_op_t per line in NESI text form,
+ *   (tag=conv1,str_vals=(type=Convolution),nda_vals=(kern_sz=..,stride=..,in_pad=..,out_chans=..),bots=(data,conv1_filts,conv1_biases),tops=(conv1))
+ * preceded by one line per source node: (node=data,dims=(img=32,chan=3,y=227,x=227)).
+ * `opts`: lexp list of conv_pipe_fwd_t-style options, e.g. "(prec=fp32,use_graph=1,acc_chunk_kblks=4,device=0)". */
+b200_fwd *b200_fwd_create(const char *pipe_text, const char *opts);
+void b200_fwd_destroy(b200_fwd *f);
+/* parameter (filts/biases) upload: conv_pipe_t::op_params -> copy_ndas_to_vars (src/rtc_fwd.cc:524) */
+int b200_fwd_set_param(b200_fwd *f, const char *node_name, const float *host_src, uint64_t n_elems);
+/* has_conv_fwd_t::run_fwd(to_set_vns, fwd, to_get_vns)  src/has_conv_fwd.H:23 (src/rtc_fwd.cc:529-577): host fp32 NCHW
+ * buffers in, host buffers out; synchronous. n_elems arrays are checked against the node dims. */
+int b200_fwd_run(b200_fwd *f, int n_set, const char *const *set_names, const float *const *set_bufs, const uint64_t *set_elems,
+                 int n_get, const char *const *get_names, float *const *get_bufs, const uint64_t *get_elems);
+/* device-resident variant for benchmarking the kernels alone: inputs must have been set by a previous b200_fwd_run /
+ * b200_fwd_set_param; runs the forward calls only and returns after a stream sync. */
+int b200_fwd_run_device_only(b200_fwd *f, int iters, float *ms_per_iter_out);
+int b200_fwd_set_det_drop_seed(b200_fwd *f, uint32_t seed);      /* ::set_det_drop_seed  :22 (no-op: dropout is stripped from fwd graphs) */
+const char *b200_fwd_get_info_log(b200_fwd *f);                  /* ::get_info_log       :24 */
+/* node dims: returns ndims (img,chan,y,x order) or <0 */
+int b200_fwd_get_node_dims(b200_fwd *f, const char *node_name, uint32_t *dims4);
+int b200_fwd_num_calls(b200_fwd *f);                             /* forward calls per run_fwd (size of fwd_calls) */
+uint64_t b200_fwd_launches(b200_fwd *f);                         /* kernels launched so far (graph replays counted per node) */
+/* per-call profile of `iters` eager runs (the per_call_fn dump of src/rtc_fwd.cc:560-572): function names ('\n'-joined), ms per
+ * call, ms of the call's contraction kernel alone (conv calls also pack their operands), algorithmic FLOPs. Returns #calls. */
+int b200_fwd_profile(b200_fwd *f, int iters, char *tags_buf, int tags_buf_len, float *call_ms_out, float *kernel_ms_out, double *flops_out, int max_calls);
+/* `iters` forwards on device-resident inputs, each bracketed by its own CUDA events on the back-end's stream; a scratch
+ * buffer of l2_flush_bytes (0 = off) is overwritten before each one, outside the events. ms_each_out[iters]. */
+int b200_fwd_run_timed(b200_fwd *f, int iters, uint64_t l2_flush_bytes, float *ms_each_out);
+/* device pointer of a node's fp32 NCHW var (e.g. to hand the logits to NCCL) */
+int b200_fwd_get_node_raw_native_pointer(b200_fwd *f, const char *node_name, void **dev_ptr_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BODA_B200_H_ */

@@ -35,7 +35,8 @@ static inline float det_hash_rand(uint32_t rv) {
   h ^= h >> 13;
   h *= 0xc2b2ae35u;
   h ^= h >> 16;
-  return (float)(h) * (10.0f / (float)(UINT32_MAX)) - 5.0f;
+  /* the reference builds with NVRTC's default fmad=true (src/nvrtc_util.cc:251), i.e. one fused multiply-add */
+  return fmaf((float)(h), (10.0f / (float)(UINT32_MAX)), -5.0f);
 }
 
 ORACLE_API float oracle_det_hash_rand(uint32_t rv) { return det_hash_rand(rv); }
@@ -173,6 +174,53 @@ ORACLE_API int oracle_conv_fwd(float const *in, float const *filts, float const 
   return 0;
 }
 
+/* Same algorithm and accumulation ORDER as oracle_conv_fwd, but the accumulator is double and the result is rounded to
+ * fp32 once: the reference's arithmetic with its fp32 accumulation rounding noise removed. Used to separate "differs
+ * from the reference's math" from "differs from the reference's rounding" (for K in the thousands and the +-5 hash
+ * inputs, fp32 sequential accumulation alone is ~2e-3 mrd away from this; see DESIGN.md "Numerics"). */
+ORACLE_API int oracle_conv_fwd_acc64(float const *in, float const *filts, float const *biases, float *out, uint32_t N,
+                                     uint32_t C, uint32_t H, uint32_t W, uint32_t OC, uint32_t KH, uint32_t KW, uint32_t sy,
+                                     uint32_t sx, uint32_t py, uint32_t px, int relu) {
+  if (H + 2 * py < KH || W + 2 * px < KW) { return -1; }
+  int32_t const OH = (int32_t)((H + 2 * py - KH) / sy + 1), OW = (int32_t)((W + 2 * px - KW) / sx + 1);
+  int64_t const jobs = (int64_t)N * OC;
+#pragma omp parallel
+  {
+    double *acc = (double *)malloc(sizeof(double) * (size_t)OH * OW);
+#pragma omp for schedule(dynamic, 4)
+    for (int64_t job = 0; job < jobs; ++job) {
+      uint32_t const n = (uint32_t)(job / OC), oc = (uint32_t)(job % OC);
+      memset(acc, 0, sizeof(double) * (size_t)OH * OW);
+      for (uint32_t ic = 0; ic < C; ++ic) {
+        float const *inp = in + ((size_t)n * C + ic) * H * W;
+        for (uint32_t ky = 0; ky < KH; ++ky) {
+          for (uint32_t kx = 0; kx < KW; ++kx) {
+            double const w = filts[(((size_t)oc * C + ic) * KH + ky) * KW + kx];
+            for (int32_t oy = 0; oy < OH; ++oy) {
+              int32_t const iy = oy * (int32_t)sy + (int32_t)ky - (int32_t)py;
+              if (iy < 0 || iy >= (int32_t)H) { continue; }
+              for (int32_t ox = 0; ox < OW; ++ox) {
+                int32_t const ix = ox * (int32_t)sx + (int32_t)kx - (int32_t)px;
+                if (ix < 0 || ix >= (int32_t)W) { continue; }
+                acc[(size_t)oy * OW + ox] += (double)inp[(size_t)iy * W + ix] * w;
+              }
+            }
+          }
+        }
+      }
+      double const b = biases ? biases[oc] : 0.0;
+      float *o = out + ((size_t)n * OC + oc) * OH * OW;
+      for (int32_t i = 0; i < OH * OW; ++i) {
+        float v = (float)(acc[i] + b);
+        if (relu) { v = (v > 0.0f) ? v : 0.0f; }
+        o[i] = v;
+      }
+    }
+    free(acc);
+  }
+  return 0;
+}
+
 /* ---- SGEMM ---------------------------------------------------------------------------------------- */
 
 /* c[m,n] = sum_k a[k,m] * b[k,n]; a is K:M (pre-transposed A), b is K:N, c is M:N; fp32 FMA, k ascending.
@@ -198,6 +246,32 @@ ORACLE_API void oracle_sgemm(float const *a, float const *b, float *c, uint32_t 
       }
       for (uint32_t mi = 0; mi < mlen; ++mi) {
         memcpy(c + (size_t)(m0 + mi) * N + n0, acc[mi], sizeof(float) * nlen);
+      }
+    }
+  }
+}
+
+/* oracle_sgemm with a double accumulator (same k order), rounded to fp32 once. */
+ORACLE_API void oracle_sgemm_acc64(float const *a, float const *b, float *c, uint32_t M, uint32_t N, uint32_t K) {
+  enum { MB = 8, NB = 256 };
+  int64_t const mblks = (M + MB - 1) / MB, nblks = (N + NB - 1) / NB;
+#pragma omp parallel for schedule(dynamic, 1) collapse(2)
+  for (int64_t mb = 0; mb < mblks; ++mb) {
+    for (int64_t nb = 0; nb < nblks; ++nb) {
+      double acc[MB][NB];
+      uint32_t const m0 = (uint32_t)mb * MB, n0 = (uint32_t)nb * NB;
+      uint32_t const mlen = (M - m0 < MB) ? (M - m0) : MB, nlen = (N - n0 < NB) ? (N - n0) : NB;
+      memset(acc, 0, sizeof(acc));
+      for (uint32_t k = 0; k < K; ++k) {
+        float const *brow = b + (size_t)k * N + n0;
+        float const *arow = a + (size_t)k * M + m0;
+        for (uint32_t mi = 0; mi < mlen; ++mi) {
+          double const av = arow[mi];
+          for (uint32_t ni = 0; ni < nlen; ++ni) { acc[mi][ni] += av * (double)brow[ni]; }
+        }
+      }
+      for (uint32_t mi = 0; mi < mlen; ++mi) {
+        for (uint32_t ni = 0; ni < nlen; ++ni) { c[(size_t)(m0 + mi) * N + n0 + ni] = (float)acc[mi][ni]; }
       }
     }
   }
@@ -259,11 +333,11 @@ ORACLE_API void oracle_lrn_fwd(float const *in, float *out, uint32_t N, uint32_t
       int32_t const lsb_ix = ic % (int32_t)local_size;
       float const ls_old = ls_buf[lsb_ix];
       ls_buf[lsb_ix] = (ic < (int32_t)C) ? in[base + (size_t)ic * cs] : 0.0f;
-      ls_sum += ls_buf[lsb_ix] * ls_buf[lsb_ix];
-      ls_sum -= ls_old * ls_old;
+      ls_sum = fmaf(ls_buf[lsb_ix], ls_buf[lsb_ix], ls_sum); /* fmad contraction, as NVRTC compiles lrn.cucl:43 */
+      ls_sum = fmaf(-ls_old, ls_old, ls_sum);
       if (ic >= hls) {
         int32_t const oc = ic - hls;
-        float const scale_base = k + ls_sum * alpha_over_ls;
+        float const scale_base = fmaf(ls_sum, alpha_over_ls, k);
         float const scale = powf(scale_base, -beta);
         out[base + (size_t)oc * cs] = ls_buf[(lsb_ix + (int32_t)local_size - hls) % (int32_t)local_size] * scale;
       }

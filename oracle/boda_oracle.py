@@ -49,6 +49,7 @@ def lib():
         _lib.oracle_strided_sum.restype = ctypes.c_float
         _lib.oracle_strided_sum.argtypes = [_f32p, _u64, _u64, _u64]
         _lib.oracle_conv_fwd.restype = ctypes.c_int
+        _lib.oracle_conv_fwd_acc64.restype = ctypes.c_int
         _lib.oracle_num_threads.restype = ctypes.c_int
     return _lib
 
@@ -78,8 +79,9 @@ def det_hash_rand_np(ix: np.ndarray) -> np.ndarray:
     h ^= h >> np.uint32(13)
     h = (h * np.uint32(0xC2B2AE35)).astype(np.uint32)
     h ^= h >> np.uint32(16)
-    scale = np.float32(10.0) / np.float32(4294967295.0)
-    return (h.astype(np.float32) * scale - np.float32(5.0)).astype(np.float32)
+    scale = np.float64(np.float32(10.0) / np.float32(4294967295.0))  # == 10 * 2^-32 exactly
+    # fused multiply-add semantics: the product and sum are exact in float64, so one rounding to float32 remains
+    return (h.astype(np.float32).astype(np.float64) * scale - 5.0).astype(np.float32)
 
 
 def gen_conv_in(img, chan, y, x, mode=5, vi=0.0) -> np.ndarray:
@@ -128,7 +130,8 @@ def pool_out_sz(in_sz, pad, stride, kern):
     return 1 if p < kern else -((p - kern) // -stride) + 1
 
 
-def conv_fwd(inp, filts, biases, stride=(1, 1), in_pad=(0, 0), relu=True) -> np.ndarray:
+def conv_fwd(inp, filts, biases, stride=(1, 1), in_pad=(0, 0), relu=True, acc64=False) -> np.ndarray:
+    """acc64=True: same algorithm and order with a double accumulator (the reference's math without fp32 accumulation noise)."""
     inp = np.ascontiguousarray(inp, np.float32)
     filts = np.ascontiguousarray(filts, np.float32)
     biases = np.ascontiguousarray(biases, np.float32)
@@ -138,14 +141,14 @@ def conv_fwd(inp, filts, biases, stride=(1, 1), in_pad=(0, 0), relu=True) -> np.
     OH, OW = conv_out_sz(H, in_pad[0], stride[0], KH), conv_out_sz(W, in_pad[1], stride[1], KW)
     assert OH > 0 and OW > 0
     out = np.empty((N, OC, OH, OW), np.float32)
-    r = lib().oracle_conv_fwd(_p(inp), _p(filts), _p(biases), _p(out), _u32(N), _u32(C), _u32(H), _u32(W), _u32(OC),
+    r = (lib().oracle_conv_fwd_acc64 if acc64 else lib().oracle_conv_fwd)(_p(inp), _p(filts), _p(biases), _p(out), _u32(N), _u32(C), _u32(H), _u32(W), _u32(OC),
                               _u32(KH), _u32(KW), _u32(stride[0]), _u32(stride[1]), _u32(in_pad[0]), _u32(in_pad[1]),
                               ctypes.c_int(1 if relu else 0))
     assert r == 0
     return out
 
 
-def sgemm(a, b) -> np.ndarray:
+def sgemm(a, b, acc64=False) -> np.ndarray:
     """c[M,N] = a[K,M]^T . b[K,N] (test/rtc/sgemm.cucl:1-3: `a` is stored K:M)."""
     a = np.ascontiguousarray(a, np.float32)
     b = np.ascontiguousarray(b, np.float32)
@@ -153,7 +156,7 @@ def sgemm(a, b) -> np.ndarray:
     K2, N = b.shape
     assert K == K2
     c = np.empty((M, N), np.float32)
-    lib().oracle_sgemm(_p(a), _p(b), _p(c), _u32(M), _u32(N), _u32(K))
+    (lib().oracle_sgemm_acc64 if acc64 else lib().oracle_sgemm)(_p(a), _p(b), _p(c), _u32(M), _u32(N), _u32(K))
     return c
 
 
@@ -419,15 +422,15 @@ def gen_op_inputs(op: Op, mode: int = 5, vi: float = 0.0) -> Dict[str, np.ndarra
     raise ValueError("gen_op_inputs: unhandled op type " + op.type)
 
 
-def run_op(op: Op, ins: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
+def run_op(op: Op, ins: Dict[str, np.ndarray], acc64: bool = False) -> Dict[str, np.ndarray]:
     """Per-op flow of ops-prof: conv -> {"out"} with conv_has_relu forced to 1 (src/cnn_op.cc:337); sgemm -> {"c"}."""
     if op.type == "Convolution":
-        out = conv_fwd(ins["in"], ins["filts"], ins["biases"], op.pt("stride", (1, 1)), op.pt("in_pad", (0, 0)), relu=True)
+        out = conv_fwd(ins["in"], ins["filts"], ins["biases"], op.pt("stride", (1, 1)), op.pt("in_pad", (0, 0)), relu=True, acc64=acc64)
         if op.has("out"):
             assert out.shape == op.get_dims("out").shape(), (out.shape, op.get_dims("out").shape())
         return {"out": out}
     if op.type == "sgemm":
-        return {"c": sgemm(ins["a"], ins["b"])}
+        return {"c": sgemm(ins["a"], ins["b"], acc64=acc64)}
     raise ValueError("run_op: unhandled op type " + op.type)
 
 

@@ -1,0 +1,65 @@
+"""CPU suite for the drop-in boundary: the C-ABI library loads without a GPU, exports every symbol include/boda_b200.h
+declares, refuses to compute without a device (no CPU fallback), and its host-side logic (op-line grammar, conv_pipe
+dims inference, error codes) behaves like the reference's."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def bb():
+    import boda_b200
+    if not os.path.exists(boda_b200.LIB_PATH):
+        from boda_b200 import build
+        build.build()
+    return boda_b200
+
+
+def test_header_symbols_all_exported(bb):
+    hdr = open(os.path.join(ROOT, "include", "boda_b200.h")).read()
+    declared = set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 35
+    out = subprocess.check_output(["nm", "-D", "--defined-only", bb.LIB_PATH], text=True)
+    exported = set(re.findall(r" T (b200_[a-z0-9_]+)", out))
+    assert declared <= exported, sorted(declared - exported)
+    assert set(bb.ABI_SYMBOLS) == declared, sorted(set(bb.ABI_SYMBOLS) ^ declared)
+    bb.lib()  # ctypes load + every signature bound
+
+
+def test_no_gpu_fails_loudly(bb):
+    if bb.device_count() > 0:
+        pytest.skip("a GPU is present")
+    r = bb.B200Compute()
+    with pytest.raises(bb.RtException, match="no CPU fallback"):
+        r.init()
+    with pytest.raises(bb.RtException):
+        from boda_b200 import nets
+        bb.B200ConvFwd(nets.tiny_net(1)[0], "")
+
+
+def test_cuda_sass_is_blackwell_native(bb):
+    """The shipped library carries sm_100a SASS with tcgen05 (UTCHMMA), TMA (UTMALDG incl. im2col) and TMEM loads (LDTM)."""
+    sass = subprocess.run(["cuobjdump", "-sass", bb.LIB_PATH], capture_output=True, text=True).stdout
+    if not sass:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTMALDG.2D", "UTMALDG.4D.IM2COL", "LDTM"):
+        assert mnemonic in sass, mnemonic
+
+
+def test_pipe_text_matches_oracle_dims(bb, oracle):
+    """nets.py's parameter-shape walk and the oracle's executor agree on the AlexNet-ng layer shapes."""
+    from boda_b200 import nets
+    txt, i, o = nets.alexnet_ng_conv(32)
+    shapes = nets.conv_param_shapes(txt)
+    assert shapes["conv1_filts"] == (96, 3, 11, 11) and shapes["conv2_filts"] == (256, 96, 5, 5)
+    assert shapes["fc6-conv_filts"] == (4096, 256, 6, 6) and shapes["fc8-conv_biases"] == (1000,)
+    assert sum(int(np.prod(s)) for s in shapes.values()) == 62378344  # 62.4 M params
+    p = nets.synth_params(txt)
+    assert p["conv3_filts"].dtype == np.float32 and abs(float(p["conv3_filts"].mean())) < 1e-3
