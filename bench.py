@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py -- AlexNet-ng forward images/sec (BASELINE.json metric, config C2: nets/alexnet_ng_conv batch=32 fp32) on N B200s.
+
+  python bench.py --gpus N --steps K --warmup W          (N>1: launched by torch.distributed.run, one rank per GPU)
+  python bench.py --impl reference ...                   (the reference arm: the path's CPU implementation on host cores)
+
+A step = one whole-net forward of one batch (32 images per GPU) of synthetic NCHW input with hash-synthetic weights.
+`value`   : device-resident whole-job throughput (inputs already in HBM), CUDA-event timed per step on the back-end's
+            stream with an L2 flush between steps, max over ranks.
+`e2e`     : the same metric through the reference-facing call (has_conv_fwd_t::run_fwd via the C ABI) with HOST pinned
+            buffers: H2D of the batch and D2H of the logits inside the timed region of every step.
+`roofline`: the dominant kernel (the tcgen05 implicit-GEMM contraction behind every Convolution): algorithmic conv FLOPs
+            (2*B*OC*OH*OW*IC*KH*KW, src/latex-util.H:116-120) / its CUDA-event launch durations, vs the measured bf16 peak.
+`cpu_baseline` / `--impl reference`: the oracle port of the reference's operator semantics (Boda itself cannot be built
+            here: boost/protobuf/python2/Caffe missing) on all host cores, on a bounded sample of the same workload.
+Multi-GPU: images are independent units of the path, so ranks shard the batch dimension (weak scaling, 32 images per
+GPU); weights are broadcast once from rank 0 over NCCL at init and the logits are all-gathered over NCCL every step.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "alexnet_ng_conv_fwd_images_per_sec"
+UNIT = "images/s"
+PER_GPU_BATCH = 32
+L2_FLUSH_BYTES = 256 << 20
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"bf16_tflops": d.get("bf16_tflops", 1590.0), "bf16_tflops_sustained": d.get("bf16_tflops_sustained", 1400.0), "hbm_gbs": d.get("hbm_gbs", 6650.0), "source": "measured"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML every few ms while the timed regions run."""
+
+    def __init__(self, dev_index):
+        super().__init__(daemon=True)
+        self.dev_index, self.stop_flag, self.samples, self.reasons, self.max_mhz = dev_index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(dev_index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8), "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+                r = int(get(self.h))
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.003)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": int(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_reference_forward(n_images, reps=1):
+    """The reference arm / cpu_baseline: the oracle port of Boda's operator semantics, whole AlexNet-ng forward on the host
+    cores (OpenMP over all of them). Returns (images/s, cores, seconds). This is the one place bench.py executes oracle/."""
+    from boda_b200 import nets
+    from oracle import boda_oracle as bo, net_oracle
+    txt, i, o = nets.alexnet_ng_conv(n_images)
+    params = nets.synth_params(txt)
+    x = nets.synth_input((n_images, 3, 227, 227))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        net_oracle.run_pipe(txt, {i: x}, params)
+    dt = time.perf_counter() - t0
+    return n_images * reps / dt, bo.num_threads(), dt
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    sample = 4  # images per step: ~1-2 s of CPU work; the whole K+W run stays within a few minutes
+    for _ in range(args.warmup):
+        cpu_reference_forward(sample)
+    t0 = time.perf_counter()
+    cores = 1
+    for _ in range(args.steps):
+        _, cores, _ = cpu_reference_forward(sample)
+    dt = time.perf_counter() - t0
+    val = sample * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "nets/alexnet_ng_conv fwd, batch=32 per GPU, fp32, 227x227 (BASELINE configs[1])", "parallelism": "host cores only"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "each step = AlexNet-ng forward of %d images (a bounded sample of the 32-image batch) through the oracle port, OpenMP on all host cores; Boda's own binary / Caffe CPU path is not buildable here" % sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--prec", default="fp32", choices=["fp32", "fp16", "bf16"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import boda_b200 as bb
+    from boda_b200 import nets
+
+    if bb.device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device: the B200 back-end has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    B = PER_GPU_BATCH
+    txt, in_node, out_node = nets.alexnet_ng_conv(B)
+    fwd = bb.B200ConvFwd(txt, "(prec=%s,device=%d)" % (args.prec, local_rank))
+
+    # ---- weights: rank 0 synthesises, one NCCL broadcast over NVLink distributes (north_star: "single NCCL broadcast of weights")
+    shapes = nets.conv_param_shapes(txt)
+    names = sorted(shapes)
+    total = sum(int(np.prod(shapes[n])) for n in names)
+    if world > 1:
+        flat = torch.empty(total, dtype=torch.float32, device="cuda")
+        if rank == 0:
+            params = nets.synth_params(txt)
+            flat.copy_(torch.from_numpy(np.concatenate([params[n].ravel() for n in names])))
+        dist.broadcast(flat, src=0)
+        host = flat.cpu().numpy()
+        off = 0
+        for n in names:
+            sz = int(np.prod(shapes[n]))
+            fwd.set_param(n, host[off:off + sz].reshape(shapes[n]))
+            off += sz
+        del flat
+    else:
+        params = nets.synth_params(txt)
+        for n in names:
+            fwd.set_param(n, params[n])
+
+    # ---- inputs: each rank owns its shard of the global batch (images [rank*B, (rank+1)*B)), pinned host memory
+    x_host = torch.from_numpy(nets.synth_input((B, 3, 227, 227), seed=rank)).pin_memory()
+    logits_host = torch.empty((B, 1000, 1, 1), dtype=torch.float32).pin_memory()
+    in_elems, out_elems = x_host.numel(), logits_host.numel()
+
+    def e2e_step():
+        fwd.run_fwd_ptrs([in_node], [x_host.data_ptr()], [in_elems], [out_node], [logits_host.data_ptr()], [out_elems])
+
+    # the logits node as a torch view of the back-end's device var, for the NCCL gather
+    class _DevView:
+        def __init__(self, ptr, shape):
+            self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
+    logits_dev = torch.as_tensor(_DevView(fwd.node_device_ptr(out_node), (B, 1000)), device="cuda")
+    gathered = torch.empty((world * B, 1000), dtype=torch.float32, device="cuda") if world > 1 else None
+
+    sampler = ClockSampler(local_rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also: first eager pass, weight packing, CUDA-graph capture)
+    for _ in range(args.warmup):
+        e2e_step()
+    fwd.run_timed(args.warmup, L2_FLUSH_BYTES)
+    if dist:
+        dist.all_gather_into_tensor(gathered, logits_dev)
+    barrier()
+
+    sampler.start()
+    # ---- timed region 1: device-resident steps (value)
+    launches0 = fwd.launches()
+    barrier()
+    if world == 1:
+        ms_each = fwd.run_timed(args.steps, L2_FLUSH_BYTES)
+        dev_ms = float(sum(ms_each))
+    else:
+        # forward (events on the back-end's stream) + per-step NCCL all-gather of the logits (events on torch's stream)
+        dev_ms = 0.0
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(args.steps):
+            dev_ms += fwd.run_timed(1, L2_FLUSH_BYTES)[0]
+            ev0.record()
+            dist.all_gather_into_tensor(gathered, logits_dev)
+            ev1.record()
+            ev1.synchronize()
+            dev_ms += ev0.elapsed_time(ev1)
+    barrier()
+    launches = fwd.launches() - launches0
+    if dist:
+        t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t.item())
+
+    # ---- timed region 2: end to end through run_fwd with host buffers (e2e)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    barrier()
+
+    # ---- roofline of the dominant kernel: per-launch CUDA events around every contraction kernel (eager profile pass)
+    prof = fwd.profile(max(5, min(args.steps, 20)))
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    conv_rows = [r for r in prof if r[3] > 0]
+    conv_flops = sum(r[3] for r in conv_rows)
+    conv_kernel_ms = sum(r[2] for r in conv_rows)
+    peaks = measured_peaks()
+    achieved_tf = conv_flops / (conv_kernel_ms * 1e-3) / 1e12 if conv_kernel_ms > 0 else 0.0
+    peak_tf = peaks["bf16_tflops"]
+
+    if rank == 0:
+        global_batch = B * world
+        value = global_batch * args.steps / (dev_ms * 1e-3)
+        e2e_val = global_batch * args.steps / e2e_s
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32": "f32 (fp16 hi/lo split, 3 tcgen05.mma per k-step, fp32 accumulate)", "fp16": "f16", "bf16": "bf16"}[args.prec], "data": "synthetic",
+            "config": {"workload": "nets/alexnet_ng_conv fwd, batch=32 per GPU, fp32, 227x227 (BASELINE configs[1])", "global_batch": global_batch,
+                       "parallelism": "batch-shard x%d, NCCL weight broadcast at init + logits all-gather per step" % world if world > 1 else "single GPU",
+                       "l2": "256 MiB scratch buffer overwritten before every timed step (outside the events)", "cuda_graph": True},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": in_elems * 4, "d2h_bytes_per_step": out_elems * 4, "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None,
+                         "traffic": None, "kernel": "b200::igemm_umma_kernel (8 launches per forward, one per Convolution)",
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernels timed one by one with CUDA events), %s" % peaks["source"],
+                         "note": "algorithmic fp32 conv FLOPs / summed launch durations; the fp32-parity mode issues 3 fp16 MMAs per product, so the tensor pipe does 3x this"},
+            "clocks": sampler.summary(),
+            "per_call": [{"func": r[0], "call_ms": round(r[1], 5), "kernel_ms": round(r[2], 5), "gflop": round(r[3] / 1e9, 3)} for r in prof],
+        }
+        if not args.no_cpu_baseline and world == 1:
+            v, cores, secs = cpu_reference_forward(32, reps=2)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "2 x AlexNet-ng forward of the full 32-image batch through the oracle port (OpenMP, all host cores), %.1f s" % secs}
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
