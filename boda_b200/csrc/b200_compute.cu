@@ -47,6 +47,8 @@ struct conv_plan_t {
   int N, C, H, W, OC, KH, KW, sy, sx, py, px, OH, OW;
   int Cpad, cblks;
   bool im2col, full_kernel, swapped;
+  bool rowmerge;  // small-chan convs (conv1): K = (ky) x [(kx,chan) run of 64 contiguous NHWC elements], see plan_conv
+  int Wp;         // rowmerge: pixel pitch of a packed image row (>= W + 2*px, and long enough for the last 64-element run)
   int BN, splits, kblks_total, kblks_per_split;
   long long a_rows, a_row_stride;  // activation matrix view (2-d modes)
   long long w_tap_stride, w_row_stride;
@@ -102,6 +104,14 @@ CUtensorMap make_im2col_map(void const *base, bool bf16, conv_plan_t const &cp) 
   int lower[2] = {-cp.px, -cp.py};                                // {w, h}: footprint corner of the first output pixel
   int upper[2] = {cp.px - (cp.KW - 1), cp.py - (cp.KH - 1)};      // ... of the last one, relative to the far image edge
   cuuint32_t estr[4] = {1, (cuuint32_t)cp.sx, (cuuint32_t)cp.sy, 1};
+  if (cp.rowmerge) {
+    // virtual tensor: "channel" = run of 64 contiguous elements of a packed image row, "w" = output column (runs overlap: stride sx*Cpad
+    // elements), x padding is materialised in the packed row, y padding is the im2col corner as usual; the filter is 1 wide, KH tall.
+    gdim[0] = 64; gdim[1] = (cuuint64_t)cp.OW;
+    gstride[0] = (cuuint64_t)cp.sx * cp.Cpad * 2; gstride[1] = (cuuint64_t)cp.Wp * cp.Cpad * 2; gstride[2] = (cuuint64_t)cp.H * cp.Wp * cp.Cpad * 2;
+    lower[0] = 0; upper[0] = 0;
+    estr[1] = 1;
+  }
   CUresult const r = g_encode_im2col(&m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(base), gdim, gstride,
                                      lower, upper, 64 /*channelsPerPixel*/, 128 /*pixelsPerColumn*/, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -109,7 +119,7 @@ CUtensorMap make_im2col_map(void const *base, bool bf16, conv_plan_t const &cp) 
   // driver <= 13.1 quirk for small tensors (same workaround CUTLASS applies when it builds im2col descriptors)
   int drv = 0;
   cudaDriverGetVersion(&drv);
-  if (drv <= 13010 && (uint64_t)cp.N * cp.H * cp.W * cp.Cpad * 2 < 131072) { reinterpret_cast<uint64_t *>(&m)[1] &= ~(1ull << 21); }
+  if (drv <= 13010 && (uint64_t)cp.N * cp.H * (cp.rowmerge ? cp.Wp : cp.W) * cp.Cpad * 2 < 131072) { reinterpret_cast<uint64_t *>(&m)[1] &= ~(1ull << 21); }
   return m;
 }
 
@@ -301,7 +311,25 @@ void plan_conv(conv_plan_t &cp, op_base_t const &op, int num_sms) {
   cp.full_kernel = (!k1 && cp.KH == cp.H && cp.KW == cp.W && cp.py == 0 && cp.px == 0);  // inner-product shaped (OH=OW=1)
   cp.im2col = !(k1 || cp.full_kernel);
   long long const pixels = (long long)cp.N * cp.OH * cp.OW;
+  // Row-merged path for few-channel inputs (AlexNet/NiN conv1 11x11 s4, GoogLeNet conv1 7x7 s2): with chan padded to only 4 (or 8) an NHWC
+  // image row is [x][chan] contiguous, so the (kx, chan) taps of one filter row are ONE contiguous run of <= 64 elements starting at pixel
+  // ox*sx. The K loop then has KH k-blocks of 64 instead of KH*KW k-blocks that are mostly zero padding (chan 3 of 64).
+  cp.rowmerge = false;
+  cp.Wp = 0;
   if (cp.im2col) {
+    int const cpx = (cp.C <= 4 && (cp.sx % 2) == 0) ? 4 : (cp.C <= 8 ? 8 : 0);  // x stride in bytes (sx*cpx*2) must be a multiple of 16 for TMA
+    if (cpx && cp.KW * cpx <= 64 && cp.KW > 1) {
+      cp.rowmerge = true;
+      cp.Cpad = cpx;
+      cp.Wp = (int)round_up(std::max(cp.W + 2 * cp.px, (cp.OW - 1) * cp.sx + 64 / cpx), 16 / cpx);
+    }
+  }
+  if (cp.rowmerge) {
+    cp.cblks = 1;
+    cp.w_tap_stride = cp.Cpad;  // (kx,chan) packed densely inside a 64-element filter row
+    cp.kblks_total = cp.KH;
+    cp.a_rows = 0; cp.a_row_stride = 0;
+  } else if (cp.im2col) {
     cp.cblks = ceil_div(cp.Cpad, 64);
     cp.w_tap_stride = (long long)cp.cblks * 64;
     cp.kblks_total = cp.KH * cp.KW * cp.cblks;
@@ -317,7 +345,7 @@ void plan_conv(conv_plan_t &cp, op_base_t const &op, int num_sms) {
     cp.kblks_total = ceil_div((long long)cp.KH * cp.KW * cp.Cpad, 64);
     cp.a_rows = cp.N; cp.a_row_stride = (long long)cp.H * cp.W * cp.Cpad;
   }
-  cp.w_row_stride = round_up((long long)cp.KH * cp.KW * cp.w_tap_stride, 64);
+  cp.w_row_stride = cp.rowmerge ? (long long)cp.KH * 64 : round_up((long long)cp.KH * cp.KW * cp.w_tap_stride, 64);
   cp.swapped = (!cp.im2col) && pixels <= 64 && cp.OC >= 128;
   if (cp.swapped) { cp.BN = pixels <= 32 ? 32 : 64; }
   else { cp.BN = cp.OC > 64 ? 128 : (cp.OC > 32 ? 64 : 32); }
@@ -405,10 +433,22 @@ struct run_ctx_t {
     cudaError_t const e = cudaGetLastError();
     if (e != cudaSuccess) { rt_err(string("kernel launch failed in '") + rfc.rtc_func_name + "': " + cudaGetErrorString(e)); }
   }
+  // optional abs-max side channel: args "<which>_absmax_cells" (uint32_t var) + by-value "<which>_absmax_ix"
+  unsigned int *absmax_cell(string const &which) {
+    string const an = which + "_absmax_cells";
+    if (!has_arg(an)) { return nullptr; }
+    var_info_t &v = var(an);
+    if (v.dims.tn != "uint32_t") { rt_err("call to '" + rfc.rtc_func_name + "': '" + an + "' must be a uint32_t var"); }
+    uint64_t const ix = (uint64_t)scalar(which + "_absmax_ix");
+    if (ix >= v.dims.dims_prod()) { rt_err("call to '" + rfc.rtc_func_name + "': '" + which + "_absmax_ix' out of range"); }
+    return static_cast<unsigned int *>(v.buf->p) + ix;
+  }
   float *fptr(var_info_t &v) { if (v.dims.tn != "float") { unsup_err("be=b200: only float vars are supported, got " + v.dims.pretty()); } return static_cast<float *>(v.buf->p); }
 
   // src [B][R][Cc] fp32 -> planes [B][Cc][..R..] 16-bit, with abs-max scaling. Cached on (pointer, generation).
-  void pack(packed_t &pk, var_info_t &src, int B, int R, int Cc, int Rpad, long long dst_c_stride, long long dst_b_stride, long long total_elems, bool want_lo, bool bf16) {
+  void pack(packed_t &pk, var_info_t &src, int B, int R, int Cc, int Rpad, long long dst_c_stride, long long dst_b_stride, long long total_elems, bool want_lo, bool bf16,
+            int c_inner = 0, long long dst_chi_stride = 0, long long dst_base = 0, unsigned int const *absmax_src = nullptr) {
+    if (c_inner <= 0) { c_inner = std::max(Cc, 1); }
     if (pk.src_gen == *src.gen && pk.src_ptr == src.buf->p && pk.hi) { return; }
     if (!pk.hi || pk.hi->bytes < (uint64_t)total_elems * 2) {
       pk.hi = std::make_shared<dev_buf_t>(total_elems * 2);
@@ -421,13 +461,16 @@ struct run_ctx_t {
     long long const n = (long long)B * R * Cc;
     int const blocks = (int)std::min<long long>((n + 1023) / 1024, 148 * 8);
     bool const use_scale = !bf16;  // bf16 has fp32's exponent range: no scaling needed
-    if (use_scale) { b200::absmax_kernel<<<std::max(blocks, 1), 256, 0, st>>>(fptr(src), n, static_cast<unsigned int *>(pk.absmax_bits->p)); launched(); }
-    b200::finalize_scale_kernel<<<1, 1, 0, st>>>(static_cast<unsigned int *>(pk.absmax_bits->p), static_cast<float *>(pk.scale2->p), use_scale ? 1 : 0);
-    launched();
+    if (!use_scale) { absmax_src = nullptr; }
+    if (!absmax_src) {  // nobody published max|x| for this tensor: reduce it here
+      if (use_scale) { b200::absmax_kernel<<<std::max(blocks, 1), 256, 0, st>>>(fptr(src), n, static_cast<unsigned int *>(pk.absmax_bits->p)); launched(); }
+      b200::finalize_scale_kernel<<<1, 1, 0, st>>>(static_cast<unsigned int *>(pk.absmax_bits->p), static_cast<float *>(pk.scale2->p), use_scale ? 1 : 0);
+      launched();
+    }
     dim3 grid(ceil_div(Rpad, 64), ceil_div(Cc, 32), B);
     uint16_t *hi = static_cast<uint16_t *>(pk.hi->p), *lo = want_lo ? static_cast<uint16_t *>(pk.lo->p) : nullptr;
-    if (bf16) { b200::pack_xpose_split_kernel<true><<<grid, 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, Cc, Rpad, dst_c_stride, dst_b_stride); }
-    else { b200::pack_xpose_split_kernel<false><<<grid, 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, Cc, Rpad, dst_c_stride, dst_b_stride); }
+    if (bf16) { b200::pack_xpose_split_kernel<true><<<grid, 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, Cc, Rpad, dst_c_stride, dst_b_stride, c_inner, dst_chi_stride, dst_base, absmax_src); }
+    else { b200::pack_xpose_split_kernel<false><<<grid, 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, Cc, Rpad, dst_c_stride, dst_b_stride, c_inner, dst_chi_stride, dst_base, absmax_src); }
     launched();
     pk.src_gen = *src.gen;
     pk.src_ptr = src.buf->p;
@@ -463,10 +506,16 @@ struct run_ctx_t {
     bool const bf16 = (rtc.prec == B200_PREC_BF16);
     int const planes = (rtc.prec == B200_PREC_FP32_SPLIT) ? 2 : 1;
     // filters: OIHW -> [OC][tap][chan] K-major rows (once per weight version; the reference's xpose_filts, src/rtc_fwd.cc:310-313)
-    pack(f.w_pack, vf, cp.OC, cp.C, cp.KH * cp.KW, cp.Cpad, cp.w_tap_stride, cp.w_row_stride, (long long)cp.OC * cp.w_row_stride, planes == 2, bf16);
-    // activations: NCHW -> NHWC (chan padded to a multiple of 8)
-    long long const act_elems = (long long)cp.N * cp.H * cp.W * cp.Cpad;
-    pack(f.a_pack, vin, cp.N, cp.C, cp.H * cp.W, cp.Cpad, cp.Cpad, (long long)cp.H * cp.W * cp.Cpad, act_elems, planes == 2, bf16);
+    // activations: NCHW -> NHWC (chan padded to a multiple of 8; row-merged path: chan padded to 4|8 and image rows at pitch Wp with x padding)
+    if (cp.rowmerge) {
+      pack(f.w_pack, vf, cp.OC, cp.C, cp.KH * cp.KW, cp.Cpad, cp.Cpad, cp.w_row_stride, (long long)cp.OC * cp.w_row_stride, planes == 2, bf16, cp.KW, 64, 0);
+      long long const img_elems = (long long)cp.H * cp.Wp * cp.Cpad;
+      pack(f.a_pack, vin, cp.N, cp.C, cp.H * cp.W, cp.Cpad, cp.Cpad, img_elems, (long long)cp.N * img_elems + 64, planes == 2, bf16, cp.W, (long long)cp.Wp * cp.Cpad, (long long)cp.px * cp.Cpad, absmax_cell("in"));
+    } else {
+      pack(f.w_pack, vf, cp.OC, cp.C, cp.KH * cp.KW, cp.Cpad, cp.w_tap_stride, cp.w_row_stride, (long long)cp.OC * cp.w_row_stride, planes == 2, bf16);
+      long long const act_elems = (long long)cp.N * cp.H * cp.W * cp.Cpad;
+      pack(f.a_pack, vin, cp.N, cp.C, cp.H * cp.W, cp.Cpad, cp.Cpad, (long long)cp.H * cp.W * cp.Cpad, act_elems, planes == 2, bf16, 0, 0, 0, absmax_cell("in"));
+    }
 
     long long const pixels = (long long)cp.N * cp.OH * cp.OW;
     CUtensorMap act_hi, act_lo, w_hi, w_lo;
@@ -492,12 +541,14 @@ struct run_ctx_t {
     prm.p_im2col = cp.im2col ? 1 : 0;
     prm.cblks = std::max(cp.cblks, 1); prm.kw = cp.KW; prm.ow = cp.OW; prm.ohw = cp.OH * cp.OW;
     prm.sx = cp.sx; prm.sy = cp.sy; prm.px = cp.px; prm.py = cp.py;
+    if (cp.rowmerge) { prm.kw = 1; prm.sx = 1; prm.px = 0; }  // taps = filter rows; the w coordinate is the output column itself
     prm.swapped = cp.swapped ? 1 : 0;
     prm.out_chans = cp.OC; prm.out_hw = cp.OH * cp.OW;
     prm.relu = cp.relu; prm.has_bias = bias ? 1 : 0; prm.bias = bias;
     prm.p_scale = static_cast<float *>((cp.swapped ? f.w_pack : f.a_pack).scale2->p);
     prm.q_scale = static_cast<float *>((cp.swapped ? f.a_pack : f.w_pack).scale2->p);
     prm.idesc = b200::make_idesc_f16(bf16 ? 1u : 0u, 128, cp.BN);
+    prm.out_absmax = absmax_cell("out");
     long long const out_elems = (long long)cp.N * cp.OC * cp.OH * cp.OW;
     if (cp.splits > 1) {
       uint64_t const need = (uint64_t)cp.splits * out_elems * 4;
@@ -514,7 +565,7 @@ struct run_ctx_t {
     else { launch_igemm(cp.BN, planes, grid, act_hi, act_lo, w_hi, w_lo, prm); }
     mark_kernel_end();
     if (cp.splits > 1) {
-      b200::splitk_reduce_kernel<<<ceil_div(out_elems, 256), 256, 0, st>>>(static_cast<float *>(f.splitk_ws->p), fptr(vout), bias, out_elems, cp.splits, cp.OC, cp.OH * cp.OW, cp.relu);
+      b200::splitk_reduce_kernel<<<ceil_div(out_elems, 256), 256, 0, st>>>(static_cast<float *>(f.splitk_ws->p), fptr(vout), bias, out_elems, cp.splits, cp.OC, cp.OH * cp.OW, cp.relu, prm.out_absmax);
       launched();
     }
     im.bump(vout);
@@ -572,7 +623,7 @@ struct run_ctx_t {
     if (vin.dims.dsz("img") != vout.dims.dsz("img") || vin.dims.dsz("chan") != vout.dims.dsz("chan")) { rt_err("pool: img/chan mismatch"); }
     if (scalar("emit_out_in_yx", true, 0) != 0) { unsup_err("pool: emit_out_in_yx (training only) is out of scope for be=b200"); }
     long long const n_out = vout.dims.dims_prod();
-    b200::pool_kernel<<<ceil_div(n_out, 256), 256, 0, st>>>(fptr(vin), fptr(vout), n_out, H, W, OH, OW, KH, KW, sy, sx, py, px, (int)scalar("avg_pool", true, 0));
+    b200::pool_kernel<<<ceil_div(n_out, 256), 256, 0, st>>>(fptr(vin), fptr(vout), n_out, H, W, OH, OW, KH, KW, sy, sx, py, px, (int)scalar("avg_pool", true, 0), absmax_cell("out"));
     launched();
     im.bump(vout);
   }
@@ -587,9 +638,11 @@ struct run_ctx_t {
     int const ls = (int)scalar("local_size", true, 5);
     float const alpha = (float)scalar("alpha", true, 1.0), beta = (float)scalar("beta", true, 0.75), k = (float)scalar("k", true, 1.0);
     int const blocks = ceil_div(n_pels, 128);
-    if (ls == 5) { b200::lrn_kernel<5><<<blocks, 128, 0, st>>>(fptr(vin), fptr(vout), n_pels, C, HW, alpha, beta, k); }
-    else if (ls == 3) { b200::lrn_kernel<3><<<blocks, 128, 0, st>>>(fptr(vin), fptr(vout), n_pels, C, HW, alpha, beta, k); }
-    else if (ls <= 32) { b200::lrn_kernel_generic<<<blocks, 128, 0, st>>>(fptr(vin), fptr(vout), n_pels, C, HW, ls, alpha, beta, k); }
+    constexpr int kChunk = 32;
+    dim3 const grid(blocks, ceil_div(C, kChunk));
+    if (ls == 5) { b200::lrn_kernel<5, kChunk><<<grid, 128, 0, st>>>(fptr(vin), fptr(vout), n_pels, C, HW, alpha, beta, k, absmax_cell("out")); }
+    else if (ls == 3) { b200::lrn_kernel<3, kChunk><<<grid, 128, 0, st>>>(fptr(vin), fptr(vout), n_pels, C, HW, alpha, beta, k, absmax_cell("out")); }
+    else if (ls <= 32) { b200::lrn_kernel_generic<<<blocks, 128, 0, st>>>(fptr(vin), fptr(vout), n_pels, C, HW, ls, alpha, beta, k, absmax_cell("out")); }
     else { unsup_err("lrn: local_size > 32"); }
     launched();
     im.bump(vout);
@@ -623,7 +676,7 @@ struct run_ctx_t {
     long long const per_img = (long long)C * HW, out_img_stride = (long long)OC * HW, out_off = (long long)ocix * HW;
     int const vec4 = ((per_img % 4) == 0 && (out_img_stride % 4) == 0 && (out_off % 4) == 0) ? 1 : 0;
     long long const work = vec4 ? per_img * n_img / 4 : per_img * n_img;
-    b200::concat_copy_kernel<<<ceil_div(work, 256), 256, 0, st>>>(fptr(vin), fptr(vout), per_img, out_img_stride, out_off, n_img, vec4);
+    b200::concat_copy_kernel<<<ceil_div(work, 256), 256, 0, st>>>(fptr(vin), fptr(vout), per_img, out_img_stride, out_off, n_img, vec4, absmax_cell("out"));
     launched();
     im.bump(vout);
   }

@@ -156,6 +156,14 @@ void b200_conv_fwd_t::add_call(string const &fn_base, conv_op_t const &op, op_ba
   call_flops.push_back(fl);
 }
 
+static char const *const absmax_cells_vn = "__absmax_cells";
+void b200_conv_fwd_t::add_absmax_args(map_str_rtc_arg_t &args, string const &which, string const &node) {
+  auto i = absmax_ix.find(node);
+  if (i == absmax_ix.end()) { return; }
+  args[which + "_absmax_cells"] = rtc_arg_t(string(absmax_cells_vn));
+  args[which + "_absmax_ix"] = rtc_arg_t(make_scalar_nda<uint32_t>(i->second, "uint32_t"));
+}
+
 void b200_conv_fwd_t::gen_op(p_conv_op_t const &op) {
   if (op->fused) { return; }  // folded into its producer (src/rtc_fwd.cc:266)
   op_base_t fop;              // function signature: op params + the dims of every argument (conv_op_t::set_arg_dims_and_map_from_pipe)
@@ -171,11 +179,18 @@ void b200_conv_fwd_t::gen_op(p_conv_op_t const &op) {
     bool relu = false;
     if (!on->in_place_ops.empty() && on->in_place_ops[0]->is("ReLU")) { relu = true; on->in_place_ops[0]->fused = true; }
     fop.set_u32("conv_has_relu", relu ? 1 : 0);
-    add_call("conv", *op, fop, {{"in", op->bots[0]}, {"filts", op->bots[1]}, {"biases", op->bots[2]}, {"out", op->tops[0]}});
+    map_str_rtc_arg_t args{{"in", op->bots[0]}, {"filts", op->bots[1]}, {"biases", op->bots[2]}, {"out", op->tops[0]}};
+    add_absmax_args(args, "in", op->bots[0]);
+    add_absmax_args(args, "out", op->tops[0]);
+    add_call("conv", *op, fop, args);
   } else if (op->is("Pooling")) {
-    add_call("pool", *op, fop, {{"in", op->bots[0]}, {"out", op->tops[0]}});
+    map_str_rtc_arg_t args{{"in", op->bots[0]}, {"out", op->tops[0]}};
+    add_absmax_args(args, "out", op->tops[0]);
+    add_call("pool", *op, fop, args);
   } else if (op->is("LRN")) {
-    add_call("lrn", *op, fop, {{"in", op->bots[0]}, {"out", op->tops[0]}});
+    map_str_rtc_arg_t args{{"in", op->bots[0]}, {"out", op->tops[0]}};
+    add_absmax_args(args, "out", op->tops[0]);
+    add_call("lrn", *op, fop, args);
   } else if (op->is("ReLU")) {
     if (!op->in_place) { rt_err("ReLU '" + op->tag + "' must be in-place (src/rtc_fwd.cc:337)"); }
     add_call("relu", *op, fop, {{"inout", op->bots[0]}});
@@ -189,7 +204,9 @@ void b200_conv_fwd_t::gen_op(p_conv_op_t const &op) {
     for (auto const &b : op->bots) {
       op_base_t cop = fop;
       cop.set_u32("ocix", chans_out_done);
-      add_call("copy", *op, cop, {{"in", b}, {"out", op->tops[0]}});
+      map_str_rtc_arg_t args{{"in", b}, {"out", op->tops[0]}};
+      add_absmax_args(args, "out", op->tops[0]);
+      add_call("copy", *op, cop, args);
       chans_out_done += cp->must_get_node(b)->dims.dsz("chan");
     }
   } else if (op->is("Eltwise") || op->is("Reduce")) {
@@ -224,6 +241,19 @@ void b200_conv_fwd_t::init(p_conv_pipe_t const &cp_, string const &opts) {
     if (kv.second->dims.empty()) { rt_err("pipe: node '" + kv.first + "' has no dims (unused / unreachable?)"); }
     rtc->create_var_with_dims(kv.first, kv.second->dims);
   }
+  // abs-max side channel: a node gets a cell when its (single) writer can publish max|x| and some Convolution reads it.
+  // In-place ReLU/Dropout on the node only shrink max|x|, so the published value stays a valid bound.
+  for (auto const &kv : cp->nodes) {
+    conv_node_t const &n = *kv.second;
+    if (n.top_for.size() != 1) { continue; }
+    p_conv_op_t writer;
+    for (auto const &o : cp->ops) { if (o->tag == n.top_for[0]) { writer = o; } }
+    if (!writer || !(writer->is("Convolution") || writer->is("Pooling") || writer->is("LRN") || writer->is("Concat"))) { continue; }
+    bool feeds_conv = false;
+    for (auto const &o : cp->ops) { if (o->is("Convolution") && !o->bots.empty() && o->bots[0] == n.name) { feeds_conv = true; } }
+    if (feeds_conv) { uint32_t const ix = (uint32_t)absmax_ix.size(); absmax_ix[n.name] = ix; }
+  }
+  rtc->create_var_with_dims(absmax_cells_vn, dims_t({(uint32_t)std::max<size_t>(absmax_ix.size(), 1)}, {"cell"}, "uint32_t"));
   for (auto const &op : cp->ops) { gen_op(op); }
   info_log = "mode=b200 plat=" + rtc->get_plat_tag() + " nodes=" + str(cp->nodes.size()) + " ops=" + str(cp->ops.size()) + " fwd_calls=" + str(fwd_calls.size()) +
              " conv_flops=" + str(cp->total_conv_flops());
@@ -236,6 +266,7 @@ void b200_conv_fwd_t::set_param(string const &node_name, float const *src, uint6
 }
 
 void b200_conv_fwd_t::run_calls() {
+  rtc->set_var_to_zero(absmax_cells_vn);  // one memset re-arms every abs-max cell for this forward
   for (auto const &c : fwd_calls) { rtc->run(c.rfc); }
 }
 
@@ -332,6 +363,7 @@ vector<b200_conv_fwd_t::prof_row_t> b200_conv_fwd_t::profile(int iters) {
   for (int it = 0; it < iters; ++it) {
     rtc->release_per_call_id_data();
     vector<uint32_t> ids;
+    rtc->set_var_to_zero(absmax_cells_vn);
     for (auto const &c : fwd_calls) { ids.push_back(rtc->run(c.rfc)); }
     rtc->finish_and_sync();
     for (size_t i = 0; i < ids.size(); ++i) { res[i].call_ms += rtc->get_dur(ids[i], ids[i]) / iters; res[i].kernel_ms += rtc->get_kernel_dur(ids[i]) / iters; }

@@ -80,6 +80,8 @@ struct b200_conv_fwd_t {
   void *flush_buf = nullptr;
   uint64_t flush_bytes = 0;
   vector<double> call_flops;
+  map<string, uint32_t> absmax_ix;  // nodes whose producer publishes max|x| for the consuming convolution's operand scaling
+  void add_absmax_args(map_str_rtc_arg_t &args, string const &which, string const &node);
 };
 
 }  // namespace boda

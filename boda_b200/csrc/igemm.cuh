@@ -53,6 +53,7 @@ struct IgemmParams {
   float const *bias;       // per out-chan
   float const *p_scale;    // {scale, inv_scale} of the P tensor
   float const *q_scale;
+  unsigned int *out_absmax;  // optional: publish max|out| (bit pattern) for the consumer's operand scaling
   uint32_t idesc;
 };
 
@@ -221,6 +222,7 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
     // ---- write out: NCHW fp32 (or split-K partial) ----
     float const inv = prm.p_scale[1] * prm.q_scale[1];
     int const prow = m0 + row;
+    float amax = 0.0f;
     if (prow < prm.p_rows) {
       float *outp = prm.out + static_cast<long long>(split) * prm.split_stride;
       bool const final_out = (prm.split_stride == 0);
@@ -236,6 +238,7 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
               if (prm.has_bias) { v += __ldg(prm.bias + ch); }
               if (prm.relu) { v = fmaxf(v, 0.0f); }
             }
+            amax = fmaxf(amax, fabsf(v));
             o[static_cast<long long>(ch) * prm.out_hw] = v;
           }
         }
@@ -249,10 +252,16 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
             int const img = pel / prm.out_hw, pix = pel - img * prm.out_hw;
             float v = acc[j] * inv + b;
             if (final_out && prm.relu) { v = fmaxf(v, 0.0f); }
+            amax = fmaxf(amax, fabsf(v));
             outp[(static_cast<long long>(img) * prm.out_chans + ch) * prm.out_hw + pix] = v;
           }
         }
       }
+    }
+    if (prm.out_absmax && prm.split_stride == 0) {  // warp-uniform branch; all 32 lanes take part in the shuffle reduce
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o)); }
+      if (lane == 0 && amax > 0.0f) { atomicMax(prm.out_absmax, __float_as_uint(amax)); }
     }
   }
 
@@ -263,14 +272,21 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
 
 // split-K fix-up: out[i] = relu( sum_s ws[s][i] + bias[chan(i)] )   (deterministic order)
 __global__ void splitk_reduce_kernel(float const *__restrict__ ws, float *__restrict__ out, float const *__restrict__ bias,
-                                     long long n, int splits, int out_chans, int out_hw, int relu) {
+                                     long long n, int splits, int out_chans, int out_hw, int relu, unsigned int *out_absmax) {
   long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (i >= n) { return; }
   float v = 0.0f;
-  for (int s = 0; s < splits; ++s) { v += ws[s * n + i]; }
-  if (bias) { v += __ldg(bias + (i / out_hw) % out_chans); }
-  if (relu) { v = fmaxf(v, 0.0f); }
-  out[i] = v;
+  if (i < n) {
+    for (int s = 0; s < splits; ++s) { v += ws[s * n + i]; }
+    if (bias) { v += __ldg(bias + (i / out_hw) % out_chans); }
+    if (relu) { v = fmaxf(v, 0.0f); }
+    out[i] = v;
+  }
+  if (out_absmax) {
+    float m = (i < n) ? fabsf(v) : 0.0f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o)); }
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) { atomicMax(out_absmax, __float_as_uint(m)); }
+  }
 }
 
 }  // namespace b200

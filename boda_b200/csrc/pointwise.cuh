@@ -10,6 +10,31 @@
 
 namespace b200 {
 
+// ---- abs-max side channel -------------------------------------------------------------------------------------
+// Producers of a tensor that a convolution will consume can publish max|x| into a uint32 cell (non-negative floats order like
+// their bit patterns), which saves the consumer a separate reduction pass before it picks its power-of-two operand scale.
+__device__ __forceinline__ void publish_absmax_warp(float m, unsigned int *cell) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o)); }
+  if ((threadIdx.x & 31) == 0 && m > 0.0f) {
+    unsigned int const bits = __float_as_uint(m);
+    if (bits > *reinterpret_cast<volatile unsigned int *>(cell)) { atomicMax(cell, bits); }
+  }
+}
+// scale = 2^(13 - floor(log2(absmax))): scaled values land in [2^13, 2^14), well inside fp16 range with most lo-plane residuals normal
+__device__ __forceinline__ float scale_from_absmax_bits(unsigned int bits) {
+  float const m = __uint_as_float(bits);
+  float s = 1.0f;
+  if (m > 0.0f && isfinite(m)) {
+    int e;
+    frexpf(m, &e);  // m = f * 2^e, f in [0.5,1)  -> floor(log2 m) = e-1
+    int sh = 13 - (e - 1);
+    sh = max(-100, min(100, sh));
+    s = ldexpf(1.0f, sh);
+  }
+  return s;
+}
+
 // ---- gen_data (test/rtc/gen-util.h:1-9 and test/rtc/gen_data_*.cucl) -----------------------------------------
 __device__ __forceinline__ float det_hash_rand(uint32_t rv) {
   uint32_t h = rv;
@@ -70,20 +95,27 @@ __global__ void relu_kernel(float *__restrict__ x, long long n) {
 // ---- copy / Concat (test/rtc/copy.cucl) -----------------------------------------------------------------------
 // in: [N][C][HW] -> out[:, ocix:ocix+C]; per image the source block is contiguous, so move 128-bit words when aligned.
 __global__ void concat_copy_kernel(float const *__restrict__ in, float *__restrict__ out, long long per_img /*C*HW*/,
-                                   long long out_img_stride, long long out_off, int n_img, int vec4) {
+                                   long long out_img_stride, long long out_off, int n_img, int vec4, unsigned int *out_absmax) {
   long long const total = per_img * n_img;
+  float m = 0.0f;
   if (vec4) {
     long long const i4 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4;
-    if (i4 >= total) { return; }
-    long long const img = i4 / per_img, r = i4 - img * per_img;
-    float4 const v = __ldg(reinterpret_cast<float4 const *>(in + i4));
-    *reinterpret_cast<float4 *>(out + img * out_img_stride + out_off + r) = v;
+    if (i4 < total) {
+      long long const img = i4 / per_img, r = i4 - img * per_img;
+      float4 const v = __ldg(reinterpret_cast<float4 const *>(in + i4));
+      *reinterpret_cast<float4 *>(out + img * out_img_stride + out_off + r) = v;
+      m = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
   } else {
     long long const i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-    if (i >= total) { return; }
-    long long const img = i / per_img, r = i - img * per_img;
-    out[img * out_img_stride + out_off + r] = __ldg(in + i);
+    if (i < total) {
+      long long const img = i / per_img, r = i - img * per_img;
+      float const v = __ldg(in + i);
+      out[img * out_img_stride + out_off + r] = v;
+      m = fabsf(v);
+    }
   }
+  if (out_absmax) { publish_absmax_warp(m, out_absmax); }
 }
 
 // ---- reduce: N-ary elementwise sum (test/rtc/reduce.cucl) ------------------------------------------------------
@@ -98,71 +130,86 @@ __global__ void reduce_sum_kernel(ReduceArgs a, float *__restrict__ out, long lo
 
 // ---- pool (test/rtc/pool.cucl:13-40) --------------------------------------------------------------------------
 __global__ void pool_kernel(float const *__restrict__ in, float *__restrict__ out, long long n_out, int H, int W, int OH,
-                            int OW, int KH, int KW, int sy, int sx, int py, int px, int avg_pool) {
+                            int OW, int KH, int KW, int sy, int sx, int py, int px, int avg_pool, unsigned int *out_absmax) {
   long long const i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (i >= n_out) { return; }
-  int const ox = static_cast<int>(i % OW), oy = static_cast<int>((i / OW) % OH);
-  long long const plane = i / (static_cast<long long>(OW) * OH);
-  float const *ip = in + plane * H * W;
-  float out_v = avg_pool ? 0.0f : -FLT_MAX;
-  float avg_pool_sz = 0;
-  for (int kx = 0; kx != KW; ++kx) {
-    for (int ky = 0; ky != KH; ++ky) {
-      int const in_y = oy * sy + ky - py, in_x = ox * sx + kx - px;
-      if (in_y >= 0 && in_x >= 0 && in_x < W && in_y < H) {
-        float const v = __ldg(ip + in_y * W + in_x);
-        if (avg_pool) { out_v += v; avg_pool_sz += 1; }
-        else if (v > out_v) { out_v = v; }
+  float out_v = 0.0f;
+  if (i < n_out) {
+    int const ox = static_cast<int>(i % OW), oy = static_cast<int>((i / OW) % OH);
+    long long const plane = i / (static_cast<long long>(OW) * OH);
+    float const *ip = in + plane * H * W;
+    out_v = avg_pool ? 0.0f : -FLT_MAX;
+    float avg_pool_sz = 0;
+    for (int kx = 0; kx != KW; ++kx) {
+      for (int ky = 0; ky != KH; ++ky) {
+        int const in_y = oy * sy + ky - py, in_x = ox * sx + kx - px;
+        if (in_y >= 0 && in_x >= 0 && in_x < W && in_y < H) {
+          float const v = __ldg(ip + in_y * W + in_x);
+          if (avg_pool) { out_v += v; avg_pool_sz += 1; }
+          else if (v > out_v) { out_v = v; }
+        }
       }
     }
+    if (avg_pool) { out_v = __fdiv_rn(out_v, avg_pool_sz); }
+    out[i] = out_v;
   }
-  if (avg_pool) { out_v = __fdiv_rn(out_v, avg_pool_sz); }
-  out[i] = out_v;
+  if (out_absmax) { publish_absmax_warp((i < n_out) ? fabsf(out_v) : 0.0f, out_absmax); }  // whole warp reaches this point together
 }
 
 // ---- lrn (test/rtc/lrn.cucl:35-50, LRN_MATCH_CAFFE branch) ----------------------------------------------------
-// One thread per (img,y,x) walking the channels with the running add-new / subtract-old sum of squares; consecutive
-// threads are consecutive x so every channel step is a coalesced 128-byte row. kLS = local_size (ring in registers).
-template <int kLS>
+// The reference runs one thread per (img,y,x) that walks ALL channels with a running add-new / subtract-old sum of squares.
+// At B200 widths that is latency-bound (a 27x27 map has too few pixels to fill 148 SMs), so a thread here owns one pixel and
+// one CHUNK of kChunk output channels: it rebuilds the window sum at the chunk start (ascending-order FMAs, exactly the
+// reference's sequence for chunk 0) and then runs the reference's running update inside the chunk. Consecutive threads are
+// consecutive x, so every channel step reads/writes coalesced 128-byte rows. kLS = local_size (ring buffer in registers).
+template <int kLS, int kChunk>
 __global__ void lrn_kernel(float const *__restrict__ in, float *__restrict__ out, long long n_pels, int C, int HW, float alpha,
-                           float beta, float k) {
+                           float beta, float k, unsigned int *out_absmax) {
   long long const pel = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (pel >= n_pels) { return; }
-  long long const img = pel / HW;
-  long long const base = img * C * HW + (pel - img * HW);
+  bool const valid = pel < n_pels;
+  long long const img = valid ? pel / HW : 0;
+  long long const base = img * C * HW + (valid ? (pel - img * HW) : 0);
   constexpr int hls = kLS >> 1;
+  float amax = 0.0f;
+  int const c_begin = blockIdx.y * kChunk;
+  int const c_end = min(C, c_begin + kChunk);
+  int const total = valid ? (c_end - c_begin) + 2 * hls : 0;  // input channels c_begin-hls .. c_end-1+hls
   float const alpha_over_ls = alpha / (float)kLS;
   float ls_buf[kLS];
 #pragma unroll
   for (int i = 0; i < kLS; ++i) { ls_buf[i] = 0.0f; }
   float ls_sum = 0.0f;
-  // the ring index is kept compile-time by unrolling kLS channel steps per trip
-  for (int c0 = 0; c0 < C + hls; c0 += kLS) {
+  for (int s0 = 0; s0 < total; s0 += kLS) {  // ring slot == s % kLS is compile-time inside the unrolled body
 #pragma unroll
     for (int u = 0; u < kLS; ++u) {
-      int const ic = c0 + u;
-      if (ic < C + hls) {
+      int const sidx = s0 + u;
+      if (sidx < total) {
+        int const ic = c_begin - hls + sidx;
         float const ls_old = ls_buf[u];
-        ls_buf[u] = (ic < C) ? __ldg(in + base + static_cast<long long>(ic) * HW) : 0.0f;
+        ls_buf[u] = (ic >= 0 && ic < C) ? __ldg(in + base + static_cast<long long>(ic) * HW) : 0.0f;
         ls_sum = __fmaf_rn(ls_buf[u], ls_buf[u], ls_sum);
         ls_sum = __fmaf_rn(-ls_old, ls_old, ls_sum);
-        if (ic >= hls) {
+        if (sidx >= 2 * hls) {
           float const scale_base = __fmaf_rn(ls_sum, alpha_over_ls, k);
           float const scale = powf(scale_base, -beta);
-          out[base + static_cast<long long>(ic - hls) * HW] = ls_buf[(u + kLS - hls) % kLS] * scale;
+          float const ov = ls_buf[(u + kLS - hls) % kLS] * scale;
+          out[base + static_cast<long long>(ic - hls) * HW] = ov;
+          amax = fmaxf(amax, fabsf(ov));
         }
       }
     }
   }
+  if (out_absmax) { publish_absmax_warp(amax, out_absmax); }
 }
 
 // generic local_size fallback (ring in local memory)
 __global__ void lrn_kernel_generic(float const *__restrict__ in, float *__restrict__ out, long long n_pels, int C, int HW,
-                                   int local_size, float alpha, float beta, float k) {
+                                   int local_size, float alpha, float beta, float k, unsigned int *out_absmax) {
   long long const pel = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (pel >= n_pels) { return; }
-  long long const img = pel / HW;
-  long long const base = img * C * HW + (pel - img * HW);
+  bool const valid = pel < n_pels;
+  long long const img = valid ? pel / HW : 0;
+  long long const base = img * C * HW + (valid ? (pel - img * HW) : 0);
+  float amax = 0.0f;
+  if (!valid) { C = -local_size; }  // no iterations
   int const hls = local_size >> 1;
   float const alpha_over_ls = alpha / (float)local_size;
   float ls_buf[32];
@@ -176,9 +223,12 @@ __global__ void lrn_kernel_generic(float const *__restrict__ in, float *__restri
     ls_sum = __fmaf_rn(-ls_old, ls_old, ls_sum);
     if (ic >= hls) {
       float const scale_base = __fmaf_rn(ls_sum, alpha_over_ls, k);
-      out[base + static_cast<long long>(ic - hls) * HW] = ls_buf[(lsb_ix + local_size - hls) % local_size] * powf(scale_base, -beta);
+      float const ov = ls_buf[(lsb_ix + local_size - hls) % local_size] * powf(scale_base, -beta);
+      out[base + static_cast<long long>(ic - hls) * HW] = ov;
+      amax = fmaxf(amax, fabsf(ov));
     }
   }
+  if (out_absmax) { publish_absmax_warp(amax, out_absmax); }
 }
 
 // ---- softmax over chan (test/rtc/softmax.cucl:6-21; running max starts at 0.0f) -------------------------------
@@ -218,15 +268,7 @@ __global__ void absmax_kernel(float const *__restrict__ x, long long n, unsigned
 // lo-plane residuals (>= 2^-12 relative) still mostly normal. Writes {scale, 1/scale} and re-arms the abs-max cell.
 // mode 0: fixed scale 1 (bf16 storage / caller opts out).
 __global__ void finalize_scale_kernel(unsigned int *__restrict__ bits, float *__restrict__ scale2, int use_scale) {
-  float const m = __uint_as_float(*bits);
-  float s = 1.0f;
-  if (use_scale && m > 0.0f && isfinite(m)) {
-    int e;
-    frexpf(m, &e);  // m = f * 2^e, f in [0.5,1)  -> floor(log2 m) = e-1
-    int sh = 13 - (e - 1);
-    sh = max(-100, min(100, sh));
-    s = ldexpf(1.0f, sh);
-  }
+  float const s = use_scale ? scale_from_absmax_bits(*bits) : 1.0f;
   scale2[0] = s;
   scale2[1] = 1.0f / s;
   *bits = 0u;
@@ -236,17 +278,22 @@ __global__ void finalize_scale_kernel(unsigned int *__restrict__ bits, float *__
 //   NCHW activations  (B=img, R=chan, C=y*x)        -> NHWC  [img][y*x][chan_pad]
 //   OIHW filters      (B=out_chan, R=in_chan, C=ky*kx) -> [out_chan][ky*kx][chan_pad]  (K-major rows for the Q operand)
 //   sgemm a  K:M      (B=1, R=K, C=M)               -> [M][Kpad]
+//   row-merged small-chan convs: NCHW -> [img][y][x_pitch][4|8], OIHW -> [out_chan][ky][(kx,chan) padded to 64]
 // hi = cvt(s*x), lo = cvt(s*x - hi) (lo plane optional). kBf16 selects bf16 instead of fp16 storage.
 // Tile: 64 (R) x 32 (C); loads are 128-byte rows along C, stores are 128-byte rows of half2 along R.
 template <bool kBf16>
 __global__ void __launch_bounds__(256)
 pack_xpose_split_kernel(float const *__restrict__ src, uint16_t *__restrict__ hi, uint16_t *__restrict__ lo, float const *__restrict__ scale2,
-                        int R, int C, int Rpad, long long dst_c_stride, long long dst_b_stride) {
+                        int R, int C, int Rpad, long long dst_c_stride, long long dst_b_stride, int c_inner, long long dst_chi_stride, long long dst_base,
+                        unsigned int const *__restrict__ absmax_bits) {
   __shared__ float tile[64][33];
   int const tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   int const r0 = blockIdx.x * 64, c0 = blockIdx.y * 32;
   long long const b = blockIdx.z;
-  float const s = scale2[0];
+  // scale: either finalised earlier into scale2, or derived here from the abs-max cell the tensor's producer published
+  // (then one thread also writes {scale, 1/scale} for the contraction kernel's epilogue)
+  float const s = absmax_bits ? scale_from_absmax_bits(*absmax_bits) : scale2[0];
+  if (absmax_bits && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) { const_cast<float *>(scale2)[0] = s; const_cast<float *>(scale2)[1] = 1.0f / s; }
   float const *sp = src + b * static_cast<long long>(R) * C;
 #pragma unroll
   for (int rr = ty; rr < 64; rr += 8) {
@@ -261,7 +308,9 @@ pack_xpose_split_kernel(float const *__restrict__ src, uint16_t *__restrict__ hi
       int const c = c0 + cc;
       if (c < C) {
         float const v0 = tile[2 * tx][cc], v1 = tile[2 * tx + 1][cc];
-        long long const o = b * dst_b_stride + static_cast<long long>(c) * dst_c_stride + r;
+        // destination of source column c: (c / c_inner) * dst_chi_stride + (c % c_inner) * dst_c_stride  (c_inner >= C: plain c * dst_c_stride);
+        // the two-level form lays image rows out with a padded pitch / filter rows as (ky)(kx,chan) for the row-merged conv path
+        long long const o = b * dst_b_stride + dst_base + static_cast<long long>(c / c_inner) * dst_chi_stride + static_cast<long long>(c % c_inner) * dst_c_stride + r;
         if (kBf16) {
           __nv_bfloat16 const h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
           *reinterpret_cast<__nv_bfloat162 *>(hi + o) = __nv_bfloat162(h0, h1);
