@@ -469,6 +469,15 @@ struct run_ctx_t {
     }
     dim3 grid(ceil_div(Rpad, 64), ceil_div(Cc, 32), B);
     uint16_t *hi = static_cast<uint16_t *>(pk.hi->p), *lo = want_lo ? static_cast<uint16_t *>(pk.lo->p) : nullptr;
+    if (Cc == 1 && dst_base == 0) {  // rows are already K-major: elementwise scale + split
+      long long const nn = (long long)B * R;
+      if (bf16) { b200::pack_rows_split_kernel<true><<<ceil_div(nn, 256), 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, dst_b_stride, nn, absmax_src); }
+      else { b200::pack_rows_split_kernel<false><<<ceil_div(nn, 256), 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, dst_b_stride, nn, absmax_src); }
+      launched();
+      pk.src_gen = *src.gen;
+      pk.src_ptr = src.buf->p;
+      return;
+    }
     if (bf16) { b200::pack_xpose_split_kernel<true><<<grid, 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, Cc, Rpad, dst_c_stride, dst_b_stride, c_inner, dst_chi_stride, dst_base, absmax_src); }
     else { b200::pack_xpose_split_kernel<false><<<grid, 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, Cc, Rpad, dst_c_stride, dst_b_stride, c_inner, dst_chi_stride, dst_base, absmax_src); }
     launched();
@@ -623,6 +632,18 @@ struct run_ctx_t {
     if (vin.dims.dsz("img") != vout.dims.dsz("img") || vin.dims.dsz("chan") != vout.dims.dsz("chan")) { rt_err("pool: img/chan mismatch"); }
     if (scalar("emit_out_in_yx", true, 0) != 0) { unsup_err("pool: emit_out_in_yx (training only) is out of scope for be=b200"); }
     long long const n_out = vout.dims.dims_prod();
+    long long const planes = (long long)vin.dims.dsz("img") * vin.dims.dsz("chan");
+    int const avg = (int)scalar("avg_pool", true, 0);
+    if (KH == KW && sy == sx && ((KH == 3 && sy == 2) || (KH == 3 && sy == 1) || (KH == 2 && sy == 2)) && planes <= 65535ll * 65535ll) {
+      dim3 const grid(ceil_div((long long)OH * OW, 256), (unsigned)std::min<long long>(planes, 65535), (unsigned)ceil_div(planes, 65535));
+      if (planes > 65535 && planes % 65535 != 0) { unsup_err("pool: plane count not expressible as a grid"); }
+      if (KH == 3 && sy == 2) { b200::pool_kernel_fixed<3, 2><<<grid, 256, 0, st>>>(fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, absmax_cell("out")); }
+      else if (KH == 3) { b200::pool_kernel_fixed<3, 1><<<grid, 256, 0, st>>>(fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, absmax_cell("out")); }
+      else { b200::pool_kernel_fixed<2, 2><<<grid, 256, 0, st>>>(fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, absmax_cell("out")); }
+      launched();
+      im.bump(vout);
+      return;
+    }
     b200::pool_kernel<<<ceil_div(n_out, 256), 256, 0, st>>>(fptr(vin), fptr(vout), n_out, H, W, OH, OW, KH, KW, sy, sx, py, px, (int)scalar("avg_pool", true, 0), absmax_cell("out"));
     launched();
     im.bump(vout);
@@ -638,7 +659,7 @@ struct run_ctx_t {
     int const ls = (int)scalar("local_size", true, 5);
     float const alpha = (float)scalar("alpha", true, 1.0), beta = (float)scalar("beta", true, 0.75), k = (float)scalar("k", true, 1.0);
     int const blocks = ceil_div(n_pels, 128);
-    constexpr int kChunk = 32;
+    constexpr int kChunk = 16;
     dim3 const grid(blocks, ceil_div(C, kChunk));
     if (ls == 5) { b200::lrn_kernel<5, kChunk><<<grid, 128, 0, st>>>(fptr(vin), fptr(vout), n_pels, C, HW, alpha, beta, k, absmax_cell("out")); }
     else if (ls == 3) { b200::lrn_kernel<3, kChunk><<<grid, 128, 0, st>>>(fptr(vin), fptr(vout), n_pels, C, HW, alpha, beta, k, absmax_cell("out")); }

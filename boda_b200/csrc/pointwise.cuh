@@ -155,6 +155,54 @@ __global__ void pool_kernel(float const *__restrict__ in, float *__restrict__ ou
   if (out_absmax) { publish_absmax_warp((i < n_out) ? fabsf(out_v) : 0.0f, out_absmax); }  // whole warp reaches this point together
 }
 
+// Fixed-window variant (compile-time kernel / stride, e.g. the 3x3 stride-2 pools of AlexNet / NiN / GoogLeNet): grid.y walks the
+// (img,chan) planes so no thread does a 64-bit divide, the window is fully unrolled (all taps in flight), same tap order as above.
+template <int K, int S>
+__global__ void __launch_bounds__(256)
+pool_kernel_fixed(float const *__restrict__ in, float *__restrict__ out, int H, int W, int OH, int OW, int py, int px, int avg_pool,
+                  unsigned int *out_absmax) {
+  int const p = blockIdx.x * blockDim.x + threadIdx.x;
+  long long const plane = blockIdx.y + static_cast<long long>(blockIdx.z) * gridDim.y;
+  bool const valid = p < OH * OW;
+  float out_v = 0.0f;
+  if (valid) {
+    int const oy = p / OW, ox = p - oy * OW;
+    float const *ip = in + plane * H * W;
+    int const y0 = oy * S - py, x0 = ox * S - px;
+    float v[K][K];  // [kx][ky]
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) {
+#pragma unroll
+      for (int ky = 0; ky < K; ++ky) {
+        int const in_y = y0 + ky, in_x = x0 + kx;
+        bool const ok = in_y >= 0 && in_x >= 0 && in_x < W && in_y < H;
+        v[kx][ky] = ok ? __ldg(ip + in_y * W + in_x) : (avg_pool ? 0.0f : -FLT_MAX);
+      }
+    }
+    if (avg_pool) {
+      float cnt = 0;
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+          int const in_y = y0 + ky, in_x = x0 + kx;
+          if (in_y >= 0 && in_x >= 0 && in_x < W && in_y < H) { out_v += v[kx][ky]; cnt += 1; }
+        }
+      }
+      out_v = __fdiv_rn(out_v, cnt);
+    } else {
+      out_v = -FLT_MAX;
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) { out_v = fmaxf(out_v, v[kx][ky]); }
+      }
+    }
+    out[plane * OH * OW + p] = out_v;
+  }
+  if (out_absmax) { publish_absmax_warp(valid ? fabsf(out_v) : 0.0f, out_absmax); }
+}
+
 // ---- lrn (test/rtc/lrn.cucl:35-50, LRN_MATCH_CAFFE branch) ----------------------------------------------------
 // The reference runs one thread per (img,y,x) that walks ALL channels with a running add-new / subtract-old sum of squares.
 // At B200 widths that is latency-bound (a 27x27 map has too few pixels to fill 148 SMs), so a thread here owns one pixel and
@@ -190,7 +238,7 @@ __global__ void lrn_kernel(float const *__restrict__ in, float *__restrict__ out
         ls_sum = __fmaf_rn(-ls_old, ls_old, ls_sum);
         if (sidx >= 2 * hls) {
           float const scale_base = __fmaf_rn(ls_sum, alpha_over_ls, k);
-          float const scale = powf(scale_base, -beta);
+          float const scale = __powf(scale_base, -beta);  // the reference compiles lrn.cucl with --use_fast_math (src/nvrtc_util.cc:251)
           float const ov = ls_buf[(u + kLS - hls) % kLS] * scale;
           out[base + static_cast<long long>(ic - hls) * HW] = ov;
           amax = fmaxf(amax, fabsf(ov));
@@ -272,6 +320,29 @@ __global__ void finalize_scale_kernel(unsigned int *__restrict__ bits, float *__
   scale2[0] = s;
   scale2[1] = 1.0f / s;
   *bits = 0u;
+}
+
+// HW == 1 activations (fc7 / fc8 inputs): NCHW [img][chan][1][1] already IS the K-major matrix [img][chan]; only scale + split.
+template <bool kBf16>
+__global__ void pack_rows_split_kernel(float const *__restrict__ src, uint16_t *__restrict__ hi, uint16_t *__restrict__ lo, float const *__restrict__ scale2,
+                                       int R, long long dst_b_stride, long long n, unsigned int const *__restrict__ absmax_bits) {
+  float const s = absmax_bits ? scale_from_absmax_bits(*absmax_bits) : scale2[0];
+  if (absmax_bits && threadIdx.x == 0 && blockIdx.x == 0) { const_cast<float *>(scale2)[0] = s; const_cast<float *>(scale2)[1] = 1.0f / s; }
+  long long const i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) { return; }
+  long long const b = i / R;
+  int const r = static_cast<int>(i - b * R);
+  float const v = __ldg(src + i) * s;
+  long long const o = b * dst_b_stride + r;
+  if (kBf16) {
+    __nv_bfloat16 const h = __float2bfloat16_rn(v);
+    reinterpret_cast<__nv_bfloat16 *>(hi)[o] = h;
+    if (lo) { reinterpret_cast<__nv_bfloat16 *>(lo)[o] = __float2bfloat16_rn(v - __bfloat162float(h)); }
+  } else {
+    __half const h = __float2half_rn(v);
+    reinterpret_cast<__half *>(hi)[o] = h;
+    if (lo) { reinterpret_cast<__half *>(lo)[o] = __float2half_rn(v - __half2float(h)); }
+  }
 }
 
 // src [B][R][C] fp32 (C contiguous)  ->  dst planes [B][C][Rpad] 16-bit (R contiguous, zero padded to Rpad):
