@@ -117,7 +117,16 @@ def run_reference_arm(args, rank, world):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "each step = AlexNet-ng forward of %d images (a bounded sample of the 32-image batch) through the oracle port, OpenMP on all host cores; Boda's own binary / Caffe CPU path is not buildable here" % sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
+
+
+def _emit(line: dict):
+    """Exactly one JSON line on the real stdout (fd 1 is pointed at stderr while libraries such as NCCL are chatty)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 
 def main():
@@ -129,7 +138,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prec", default="fp32", choices=["fp32", "fp16", "bf16"])
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
+    if args.impl != "reference":
+        args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -282,7 +292,7 @@ def main():
             v, cores, secs = cpu_reference_forward(32, reps=2)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "2 x AlexNet-ng forward of the full 32-image batch through the oracle port (OpenMP, all host cores), %.1f s" % secs}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if dist:
         dist.barrier()
         dist.destroy_process_group()
