@@ -61,6 +61,9 @@ _SIGS = {
     "b200_fwd_set_param": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_void_p, _c.c_uint64]),
     "b200_fwd_run": (_c.c_int, [_c.c_void_p, _c.c_int, _strp, _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_uint64), _c.c_int, _strp,
                                 _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_uint64)]),
+    "b200_fwd_submit": (_c.c_int, [_c.c_void_p, _c.c_int, _strp, _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_uint64), _c.c_int, _strp,
+                                   _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_uint64)]),
+    "b200_fwd_wait": (_c.c_int, [_c.c_void_p, _c.c_int]),
     "b200_fwd_run_device_only": (_c.c_int, [_c.c_void_p, _c.c_int, _c.POINTER(_c.c_float)]),
     "b200_fwd_set_det_drop_seed": (_c.c_int, [_c.c_void_p, _c.c_uint32]),
     "b200_fwd_get_info_log": (_c.c_char_p, [_c.c_void_p]),
@@ -116,7 +119,7 @@ Dims = Sequence[Tuple[str, int]]
 class B200Compute:
     """`be=b200`: same methods as rtc_compute_t (src/rtc_compute.H:35-97); ndas are numpy arrays + named dims."""
 
-    def __init__(self, prec: str = "fp32", acc_chunk_kblks: Optional[int] = None, device: int = 0):
+    def __init__(self, prec: str = "fp32", acc_chunk_kblks: Optional[int] = None, device: int = 0, use_clusters: Optional[int] = None, use_2cta: Optional[int] = None):
         self._h = lib().b200_rtc_create()
         if not self._h:
             raise RtException(lib().b200_last_error().decode())
@@ -124,6 +127,10 @@ class B200Compute:
         _chk(lib().b200_rtc_set_option(self._h, b"device", _b(str(device))))
         if acc_chunk_kblks is not None:
             _chk(lib().b200_rtc_set_option(self._h, b"acc_chunk_kblks", _b(str(acc_chunk_kblks))))
+        if use_clusters is not None:
+            _chk(lib().b200_rtc_set_option(self._h, b"use_clusters", _b(str(use_clusters))))
+        if use_2cta is not None:
+            _chk(lib().b200_rtc_set_option(self._h, b"use_2cta", _b(str(use_2cta))))
         self._dims: Dict[str, Dims] = {}
 
     def close(self):
@@ -283,6 +290,17 @@ class B200ConvFwd:
         gp = (_c.c_void_p * len(get_names))(*get_ptrs)
         ge = (_c.c_uint64 * len(get_names))(*get_elems)
         _chk(lib().b200_fwd_run(self._h, len(set_names), _str_array(set_names), sp, se, len(get_names), _str_array(get_names), gp, ge))
+
+    def submit_ptrs(self, set_names, set_ptrs, set_elems, get_names, get_ptrs, get_elems) -> int:
+        """Pipelined run_fwd: enqueue H2D (overlapping the previous forward) + forward + D2H, return a ticket for wait()."""
+        sp = (_c.c_void_p * len(set_names))(*set_ptrs)
+        se = (_c.c_uint64 * len(set_names))(*set_elems)
+        gp = (_c.c_void_p * len(get_names))(*get_ptrs)
+        ge = (_c.c_uint64 * len(get_names))(*get_elems)
+        return _chk(lib().b200_fwd_submit(self._h, len(set_names), _str_array(set_names), sp, se, len(get_names), _str_array(get_names), gp, ge))
+
+    def wait(self, ticket: int):
+        _chk(lib().b200_fwd_wait(self._h, ticket))
 
     def run_device_only(self, iters: int) -> float:
         ms = _c.c_float()

@@ -50,6 +50,9 @@ B200_API int b200_rtc_set_option(b200_rtc *r, const char *key, const char *val) 
     string const k = key, v = val;
     if (k == "prec") { r->rtc->prec = (v == "fp32") ? B200_PREC_FP32_SPLIT : (v == "fp16") ? B200_PREC_FP16 : (v == "bf16") ? B200_PREC_BF16 : (rt_err("unknown prec '" + v + "'"), B200_PREC_FP32_SPLIT); }
     else if (k == "acc_chunk_kblks") { r->rtc->acc_chunk_kblks = std::stoi(v); }
+    else if (k == "use_clusters") { r->rtc->use_clusters = std::stoi(v); }
+    else if (k == "use_2cta") { r->rtc->use_2cta = std::stoi(v); }
+    else if (k == "debug_flags") { r->rtc->debug_flags = std::stoi(v); }
     else if (k == "device") { r->rtc->device = std::stoi(v); }
     else { rt_err("be=b200: unused option '" + k + "'"); }
     return 0;
@@ -127,6 +130,11 @@ B200_API int b200_fwd_run(b200_fwd *f, int n_set, const char *const *set_names, 
                           const char *const *get_names, float *const *get_bufs, const uint64_t *get_elems) {
   return guarded([&] { f->fwd->run_fwd_raw(n_set, set_names, set_bufs, set_elems, n_get, get_names, get_bufs, get_elems); return 0; });
 }
+B200_API int b200_fwd_submit(b200_fwd *f, int n_set, const char *const *set_names, const float *const *set_bufs, const uint64_t *set_elems, int n_get,
+                             const char *const *get_names, float *const *get_bufs, const uint64_t *get_elems) {
+  return guarded([&] { return f->fwd->submit(n_set, set_names, set_bufs, set_elems, n_get, get_names, get_bufs, get_elems); });
+}
+B200_API int b200_fwd_wait(b200_fwd *f, int ticket) { return guarded([&] { f->fwd->wait(ticket); return 0; }); }
 B200_API int b200_fwd_run_device_only(b200_fwd *f, int iters, float *ms_per_iter_out) {
   return guarded([&] { *ms_per_iter_out = f->fwd->run_device_only(iters); return 0; });
 }

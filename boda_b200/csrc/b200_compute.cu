@@ -3,6 +3,7 @@
 // rtc_fwd path. There is deliberately NO CPU fallback: every function either launches sm_100a kernels or throws.
 #include "b200_compute.h"
 #include "igemm.cuh"
+#include "igemm2.cuh"
 #include "pointwise.cuh"
 #include <cudaTypedefs.h>
 #include <algorithm>
@@ -97,7 +98,7 @@ CUtensorMap make_tiled_map(void const *base, bool bf16, uint64_t k_extent, uint6
 }
 
 // NHWC activation tensor [N][H][W][Cpad] read in im2col mode: 128 output pixels x 64 channels per load.
-CUtensorMap make_im2col_map(void const *base, bool bf16, conv_plan_t const &cp) {
+CUtensorMap make_im2col_map(void const *base, bool bf16, conv_plan_t const &cp, uint32_t pixels_per_col = 128) {
   CUtensorMap m;
   cuuint64_t gdim[4] = {(cuuint64_t)cp.Cpad, (cuuint64_t)cp.W, (cuuint64_t)cp.H, (cuuint64_t)cp.N};
   cuuint64_t gstride[3] = {(cuuint64_t)cp.Cpad * 2, (cuuint64_t)cp.W * cp.Cpad * 2, (cuuint64_t)cp.H * cp.W * cp.Cpad * 2};
@@ -113,7 +114,7 @@ CUtensorMap make_im2col_map(void const *base, bool bf16, conv_plan_t const &cp) 
     estr[1] = 1;
   }
   CUresult const r = g_encode_im2col(&m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(base), gdim, gstride,
-                                     lower, upper, 64 /*channelsPerPixel*/, 128 /*pixelsPerColumn*/, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                     lower, upper, 64 /*channelsPerPixel*/, pixels_per_col /*pixelsPerColumn*/, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { rt_err("cuTensorMapEncodeIm2col failed with code " + str(int(r))); }
   // driver <= 13.1 quirk for small tensors (same workaround CUTLASS applies when it builds im2col descriptors)
@@ -125,6 +126,32 @@ CUtensorMap make_im2col_map(void const *base, bool bf16, conv_plan_t const &cp) 
 
 int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
+
+// CTA-cluster shape for the contraction kernel. The kernel is bound by L2->SM operand traffic long before the tensor pipe saturates
+// (a 128 x BN tile needs planes*128*(128+BN) bytes per k-block for planes^2-1|1 MMA passes), so CTAs that share an operand tile fetch one
+// slice each and multicast it: cm CTAs along P-tiles share every Q tile, cn CTAs along Q-tiles share every P tile.
+// Cost model: waves x max(MMA cycles, bytes / measured L2 delivery per SM) per k-block; clusters must fit whole GPCs.
+struct cluster_choice_t { int cm = 1, cn = 1; };
+cluster_choice_t choose_cluster(int p_tiles, int q_tiles, int BN, int planes, bool allow) {
+  cluster_choice_t best;
+  if (!allow) { return best; }
+  double best_cost = 1e30;
+  for (int cm : {1, 2, 4}) {
+    for (int cn : {1, 2, 4}) {
+      int const sz = cm * cn;
+      if (sz > 8 || (BN / cm) % 8 != 0 || BN % cm != 0) { continue; }
+      if (round_up(p_tiles, cm) * 3 > (long long)p_tiles * 4 || round_up(q_tiles, cn) * 3 > (long long)q_tiles * 4) { continue; }  // <= 33 % padding CTAs
+      int const per_wave = sz == 1 ? 148 : sz == 2 ? 74 : sz == 4 ? 33 : 16;
+      long long const clusters = (long long)ceil_div(p_tiles, cm) * ceil_div(q_tiles, cn);
+      double const waves = std::ceil((double)clusters / per_wave);
+      double const bytes = planes * 128.0 * (128.0 / cn + (double)BN / cm);
+      double const mma = (planes == 2 ? 12.0 : 4.0) * BN / 2.0;
+      double const cost = waves * std::max(mma, bytes / 33.0) + 0.01 * sz;
+      if (cost < best_cost) { best_cost = cost; best.cm = cm; best.cn = cn; }
+    }
+  }
+  return best;
+}
 
 }  // namespace
 
@@ -229,6 +256,12 @@ void b200_compute_t::copy_var_to_raw_async(void *dst, string const &vn, uint64_t
   var_info_t &v = impl->must_var(vn);
   if (bytes != v.dims.bytes_sz()) { rt_err("copy from var '" + vn + "': asked " + str(bytes) + " bytes, var holds " + str(v.dims.bytes_sz())); }
   CU_CHK(cudaMemcpyAsync(dst, v.buf->p, bytes, cudaMemcpyDeviceToHost, impl->stream));
+}
+void b200_compute_t::copy_device_to_var_async(string const &vn, void const *dev_src, uint64_t bytes) {
+  var_info_t &v = impl->must_var(vn);
+  if (bytes != v.dims.bytes_sz()) { rt_err("copy to var '" + vn + "': got " + str(bytes) + " bytes, var holds " + str(v.dims.bytes_sz())); }
+  CU_CHK(cudaMemcpyAsync(v.buf->p, dev_src, bytes, cudaMemcpyDeviceToDevice, impl->stream));
+  impl->bump(v);
 }
 void b200_compute_t::copy_raw_to_var(string const &vn, void const *src, uint64_t bytes) {
   copy_raw_to_var_async(vn, src, bytes);
@@ -447,7 +480,7 @@ struct run_ctx_t {
 
   // src [B][R][Cc] fp32 -> planes [B][Cc][..R..] 16-bit, with abs-max scaling. Cached on (pointer, generation).
   void pack(packed_t &pk, var_info_t &src, int B, int R, int Cc, int Rpad, long long dst_c_stride, long long dst_b_stride, long long total_elems, bool want_lo, bool bf16,
-            int c_inner = 0, long long dst_chi_stride = 0, long long dst_base = 0, unsigned int const *absmax_src = nullptr) {
+            int c_inner = 0, long long dst_chi_stride = 0, long long dst_base = 0, unsigned int const *absmax_src = nullptr, int smallc_W = 0) {
     if (c_inner <= 0) { c_inner = std::max(Cc, 1); }
     if (pk.src_gen == *src.gen && pk.src_ptr == src.buf->p && pk.hi) { return; }
     if (!pk.hi || pk.hi->bytes < (uint64_t)total_elems * 2) {
@@ -459,7 +492,7 @@ struct run_ctx_t {
       CU_CHK(cudaMemsetAsync(pk.absmax_bits->p, 0, 4, st));
     }
     long long const n = (long long)B * R * Cc;
-    int const blocks = (int)std::min<long long>((n + 1023) / 1024, 148 * 8);
+    int const blocks = (int)std::min<long long>((n + 4095) / 4096, 148 * 8);
     bool const use_scale = !bf16;  // bf16 has fp32's exponent range: no scaling needed
     if (!use_scale) { absmax_src = nullptr; }
     if (!absmax_src) {  // nobody published max|x| for this tensor: reduce it here
@@ -469,6 +502,16 @@ struct run_ctx_t {
     }
     dim3 grid(ceil_div(Rpad, 64), ceil_div(Cc, 32), B);
     uint16_t *hi = static_cast<uint16_t *>(pk.hi->p), *lo = want_lo ? static_cast<uint16_t *>(pk.lo->p) : nullptr;
+    if (smallc_W > 0 && !bf16 && (Rpad == 4 || Rpad == 8)) {  // row-merged conv input: one thread per pixel, vector stores
+      int const H = Cc / smallc_W, Wp = (int)(dst_chi_stride / Rpad), px_off = (int)(dst_base / Rpad);
+      long long const n_pix = (long long)B * Cc;
+      if (Rpad == 4) { b200::pack_smallc_kernel<4><<<ceil_div(n_pix, 256), 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, H, smallc_W, Wp, px_off, n_pix, absmax_src); }
+      else { b200::pack_smallc_kernel<8><<<ceil_div(n_pix, 256), 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, H, smallc_W, Wp, px_off, n_pix, absmax_src); }
+      launched();
+      pk.src_gen = *src.gen;
+      pk.src_ptr = src.buf->p;
+      return;
+    }
     if (Cc == 1 && dst_base == 0) {  // rows are already K-major: elementwise scale + split
       long long const nn = (long long)B * R;
       if (bf16) { b200::pack_rows_split_kernel<true><<<ceil_div(nn, 256), 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, dst_b_stride, nn, absmax_src); }
@@ -493,8 +536,48 @@ struct run_ctx_t {
       CU_CHK(cudaFuncSetAttribute(b200::igemm_umma_kernel<BN, kPlanes>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
       attr_set = true;
     }
-    b200::igemm_umma_kernel<BN, kPlanes><<<grid, b200::IGEMM_THREADS, Cfg::kSmemBytes, st>>>(ph, pl, qh, ql, prm);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(b200::IGEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = prm.cm; attr[0].val.clusterDim.y = prm.cn; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (prm.cm * prm.cn > 1) ? 1 : 0;
+    CU_CHK(cudaLaunchKernelEx(&cfg, b200::igemm_umma_kernel<BN, kPlanes>, ph, pl, qh, ql, prm));
     launched();
+  }
+  template <int BN, int kPlanes>
+  void launch_igemm2_t(dim3 grid, CUtensorMap const &ph, CUtensorMap const &pl, CUtensorMap const &qh, CUtensorMap const &ql, b200::IgemmParams const &prm) {
+    using Cfg = b200::Igemm2Cfg<BN, kPlanes>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      CU_CHK(cudaFuncSetAttribute(b200::igemm_umma_2cta_kernel<BN, kPlanes>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+      attr_set = true;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(b200::IGEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CU_CHK(cudaLaunchKernelEx(&cfg, b200::igemm_umma_2cta_kernel<BN, kPlanes>, ph, pl, qh, ql, prm));
+    launched();
+  }
+  void launch_igemm2(int BN, int planes, dim3 grid, CUtensorMap const &ph, CUtensorMap const &pl, CUtensorMap const &qh, CUtensorMap const &ql, b200::IgemmParams const &prm) {
+    if (planes == 2) {
+      if (BN == 128) { launch_igemm2_t<128, 2>(grid, ph, pl, qh, ql, prm); } else if (BN == 64) { launch_igemm2_t<64, 2>(grid, ph, pl, qh, ql, prm); } else { launch_igemm2_t<32, 2>(grid, ph, pl, qh, ql, prm); }
+    } else {
+      if (BN == 128) { launch_igemm2_t<128, 1>(grid, ph, pl, qh, ql, prm); } else if (BN == 64) { launch_igemm2_t<64, 1>(grid, ph, pl, qh, ql, prm); } else { launch_igemm2_t<32, 1>(grid, ph, pl, qh, ql, prm); }
+    }
   }
   void launch_igemm(int BN, int planes, dim3 grid, CUtensorMap const &ph, CUtensorMap const &pl, CUtensorMap const &qh, CUtensorMap const &ql, b200::IgemmParams const &prm) {
     if (planes == 2) {
@@ -519,7 +602,7 @@ struct run_ctx_t {
     if (cp.rowmerge) {
       pack(f.w_pack, vf, cp.OC, cp.C, cp.KH * cp.KW, cp.Cpad, cp.Cpad, cp.w_row_stride, (long long)cp.OC * cp.w_row_stride, planes == 2, bf16, cp.KW, 64, 0);
       long long const img_elems = (long long)cp.H * cp.Wp * cp.Cpad;
-      pack(f.a_pack, vin, cp.N, cp.C, cp.H * cp.W, cp.Cpad, cp.Cpad, img_elems, (long long)cp.N * img_elems + 64, planes == 2, bf16, cp.W, (long long)cp.Wp * cp.Cpad, (long long)cp.px * cp.Cpad, absmax_cell("in"));
+      pack(f.a_pack, vin, cp.N, cp.C, cp.H * cp.W, cp.Cpad, cp.Cpad, img_elems, (long long)cp.N * img_elems + 64, planes == 2, bf16, cp.W, (long long)cp.Wp * cp.Cpad, (long long)cp.px * cp.Cpad, absmax_cell("in"), cp.W);
     } else {
       pack(f.w_pack, vf, cp.OC, cp.C, cp.KH * cp.KW, cp.Cpad, cp.w_tap_stride, cp.w_row_stride, (long long)cp.OC * cp.w_row_stride, planes == 2, bf16);
       long long const act_elems = (long long)cp.N * cp.H * cp.W * cp.Cpad;
@@ -527,11 +610,17 @@ struct run_ctx_t {
     }
 
     long long const pixels = (long long)cp.N * cp.OH * cp.OW;
+    int const p_rows_n = cp.swapped ? cp.OC : (int)pixels, q_rows_n = cp.swapped ? (int)pixels : cp.OC;
+    int const p_tiles = ceil_div(p_rows_n, b200::IGEMM_BM), q_tiles = ceil_div(q_rows_n, cp.BN);
+    // CTA pairs (tcgen05 cta_group::2, igemm2.cuh) whenever the layer has >= 2 row tiles and needs no split-K; else one CTA per tile,
+    // optionally with TMA-multicast clusters (use_clusters, off by default: measured slower than plain tiles on AlexNet)
+    bool const two_cta = rtc.use_2cta && !cp.swapped && cp.splits == 1 && p_tiles >= 2;
+    cluster_choice_t const cl = choose_cluster(p_tiles, q_tiles, cp.BN, planes, rtc.use_clusters && !two_cta && !cp.swapped && cp.splits == 1);
     CUtensorMap act_hi, act_lo, w_hi, w_lo;
-    uint32_t const act_box = cp.swapped ? cp.BN : IGEMM_BM_host(), w_box = cp.swapped ? IGEMM_BM_host() : cp.BN;
+    uint32_t const act_box = cp.swapped ? cp.BN : b200::IGEMM_BM / cl.cn, w_box = cp.swapped ? b200::IGEMM_BM : (two_cta ? cp.BN / 2 : cp.BN / cl.cm);
     if (cp.im2col) {
-      act_hi = make_im2col_map(f.a_pack.hi->p, bf16, cp);
-      act_lo = planes == 2 ? make_im2col_map(f.a_pack.lo->p, bf16, cp) : act_hi;
+      act_hi = make_im2col_map(f.a_pack.hi->p, bf16, cp, act_box);
+      act_lo = planes == 2 ? make_im2col_map(f.a_pack.lo->p, bf16, cp, act_box) : act_hi;
     } else {
       uint64_t const kext = cp.full_kernel ? (uint64_t)cp.a_row_stride : (uint64_t)cp.Cpad;
       act_hi = make_tiled_map(f.a_pack.hi->p, bf16, kext, cp.a_rows, cp.a_row_stride, act_box);
@@ -557,6 +646,8 @@ struct run_ctx_t {
     prm.p_scale = static_cast<float *>((cp.swapped ? f.w_pack : f.a_pack).scale2->p);
     prm.q_scale = static_cast<float *>((cp.swapped ? f.a_pack : f.w_pack).scale2->p);
     prm.idesc = b200::make_idesc_f16(bf16 ? 1u : 0u, 128, cp.BN);
+    prm.cm = cl.cm; prm.cn = cl.cn;
+    prm.debug = rtc.debug_flags;
     prm.out_absmax = absmax_cell("out");
     long long const out_elems = (long long)cp.N * cp.OC * cp.OH * cp.OW;
     if (cp.splits > 1) {
@@ -568,9 +659,10 @@ struct run_ctx_t {
       prm.out = fptr(vout);
       prm.split_stride = 0;
     }
-    dim3 grid(ceil_div(prm.p_rows, b200::IGEMM_BM), ceil_div(prm.q_rows, cp.BN), cp.splits);
+    dim3 grid((unsigned)round_up(p_tiles, two_cta ? 2 : cl.cm), (unsigned)round_up(q_tiles, cl.cn), cp.splits);
     mark_kernel_begin();
-    if (cp.swapped) { launch_igemm(cp.BN, planes, grid, w_hi, w_lo, act_hi, act_lo, prm); }
+    if (two_cta) { prm.idesc = b200::make_idesc_f16(bf16 ? 1u : 0u, 256, cp.BN); launch_igemm2(cp.BN, planes, grid, act_hi, act_lo, w_hi, w_lo, prm); }
+    else if (cp.swapped) { launch_igemm(cp.BN, planes, grid, w_hi, w_lo, act_hi, act_lo, prm); }
     else { launch_igemm(cp.BN, planes, grid, act_hi, act_lo, w_hi, w_lo, prm); }
     mark_kernel_end();
     if (cp.splits > 1) {
@@ -593,10 +685,14 @@ struct run_ctx_t {
     pack(f.a_pack, va, 1, K, M, (int)Kpad, Kpad, 0, (long long)M * Kpad, planes == 2, bf16);
     pack(f.w_pack, vb, 1, K, N, (int)Kpad, Kpad, 0, (long long)N * Kpad, planes == 2, bf16);
     int const BN = N > 64 ? 128 : (N > 32 ? 64 : 32);
-    CUtensorMap a_hi = make_tiled_map(f.a_pack.hi->p, bf16, Kpad, M, Kpad, b200::IGEMM_BM);
-    CUtensorMap a_lo = planes == 2 ? make_tiled_map(f.a_pack.lo->p, bf16, Kpad, M, Kpad, b200::IGEMM_BM) : a_hi;
-    CUtensorMap b_hi = make_tiled_map(f.w_pack.hi->p, bf16, Kpad, N, Kpad, BN);
-    CUtensorMap b_lo = planes == 2 ? make_tiled_map(f.w_pack.lo->p, bf16, Kpad, N, Kpad, BN) : b_hi;
+    int const p_tiles = ceil_div(M, b200::IGEMM_BM), q_tiles = ceil_div(N, BN);
+    bool const two_cta = rtc.use_2cta && p_tiles >= 2;
+    cluster_choice_t const cl = choose_cluster(p_tiles, q_tiles, BN, planes, rtc.use_clusters && !two_cta);
+    uint32_t const a_box = b200::IGEMM_BM / cl.cn, b_box = two_cta ? BN / 2 : BN / cl.cm;
+    CUtensorMap a_hi = make_tiled_map(f.a_pack.hi->p, bf16, Kpad, M, Kpad, a_box);
+    CUtensorMap a_lo = planes == 2 ? make_tiled_map(f.a_pack.lo->p, bf16, Kpad, M, Kpad, a_box) : a_hi;
+    CUtensorMap b_hi = make_tiled_map(f.w_pack.hi->p, bf16, Kpad, N, Kpad, b_box);
+    CUtensorMap b_lo = planes == 2 ? make_tiled_map(f.w_pack.lo->p, bf16, Kpad, N, Kpad, b_box) : b_hi;
     b200::IgemmParams prm;
     memset(&prm, 0, sizeof(prm));
     prm.p_rows = M; prm.q_rows = N;
@@ -608,9 +704,12 @@ struct run_ctx_t {
     prm.p_scale = static_cast<float *>(f.a_pack.scale2->p);
     prm.q_scale = static_cast<float *>(f.w_pack.scale2->p);
     prm.idesc = b200::make_idesc_f16(bf16 ? 1u : 0u, 128, BN);
-    dim3 grid(ceil_div(M, b200::IGEMM_BM), ceil_div(N, BN), 1);
+    prm.cm = cl.cm; prm.cn = cl.cn;
+    prm.debug = rtc.debug_flags;
+    dim3 grid((unsigned)round_up(p_tiles, two_cta ? 2 : cl.cm), (unsigned)round_up(q_tiles, cl.cn), 1);
     mark_kernel_begin();
-    launch_igemm(BN, planes, grid, a_hi, a_lo, b_hi, b_lo, prm);
+    if (two_cta) { prm.idesc = b200::make_idesc_f16(bf16 ? 1u : 0u, 256, BN); launch_igemm2(BN, planes, grid, a_hi, a_lo, b_hi, b_lo, prm); }
+    else { launch_igemm(BN, planes, grid, a_hi, a_lo, b_hi, b_lo, prm); }
     mark_kernel_end();
     im.bump(vc);
   }

@@ -63,6 +63,9 @@ struct b200_compute_t {
   string be = "b200";
   int device = 0;
   b200_prec_t prec = B200_PREC_FP32_SPLIT;
+  int debug_flags = 0;      // timing experiments on the 1-CTA kernel: 1 = skip TMA loads, 2 = skip MMA issue (results are garbage)
+  int use_2cta = 1;         // CTA pairs: one tcgen05.mma.cta_group::2 per 256 x BN tile (igemm2.cuh)
+  int use_clusters = 0;     // 1-CTA tiles only: let CTAs that share an operand tile form a cluster and TMA-multicast it (choose_cluster)
   int acc_chunk_kblks = 4;  // drain TMEM accumulators into fp32 registers every this many 64-wide k-blocks
 
   b200_compute_t();
@@ -102,6 +105,7 @@ struct b200_compute_t {
   void copy_var_to_raw(void *dst, string const &vn, uint64_t bytes);
   void copy_raw_to_var_async(string const &vn, void const *src, uint64_t bytes);
   void copy_var_to_raw_async(void *dst, string const &vn, uint64_t bytes);
+  void copy_device_to_var_async(string const &vn, void const *dev_src, uint64_t bytes);  // device -> var on the back-end's stream
   cudaStream_t stream() const;
   uint64_t launches() const;  // number of kernels this back-end has launched so far (claimed in bench.py's gpu_launches)
   void set_timing(bool on);   // per-call event recording on/off (off inside CUDA-graph capture)

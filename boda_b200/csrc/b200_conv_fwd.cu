@@ -134,6 +134,10 @@ p_conv_pipe_t make_conv_pipe_from_text(string const &pipe_text) {
 // ---- b200_conv_fwd_t ------------------------------------------------------------------------------------------
 b200_conv_fwd_t::b200_conv_fwd_t() {}
 b200_conv_fwd_t::~b200_conv_fwd_t() {
+  if (rtc && rtc->stream()) { cudaStreamSynchronize(rtc->stream()); }
+  if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
+  for (auto &sl : slots) { for (auto &kv : sl.staging) { cudaFree(kv.second); } if (sl.h2d_done) { cudaEventDestroy(sl.h2d_done); } if (sl.freed) { cudaEventDestroy(sl.freed); } }
+  for (auto &e : ticket_ev) { if (e) { cudaEventDestroy(e); } }
   if (flush_buf) { cudaFree(flush_buf); }
   if (graph_exec) { cudaGraphExecDestroy(graph_exec); }
   if (graph) { cudaGraphDestroy(graph); }
@@ -230,6 +234,8 @@ void b200_conv_fwd_t::init(p_conv_pipe_t const &cp_, string const &opts) {
         if (k == "prec") { rtc->prec = (v == "fp32") ? B200_PREC_FP32_SPLIT : (v == "fp16") ? B200_PREC_FP16 : (v == "bf16") ? B200_PREC_BF16 : (rt_err("unknown prec '" + v + "'"), B200_PREC_FP32_SPLIT); }
         else if (k == "use_graph") { use_graph = (uint32_t)std::stoul(v); }
         else if (k == "acc_chunk_kblks") { rtc->acc_chunk_kblks = std::stoi(v); }
+        else if (k == "use_clusters") { rtc->use_clusters = std::stoi(v); }
+        else if (k == "use_2cta") { rtc->use_2cta = std::stoi(v); }
         else if (k == "device") { rtc->device = std::stoi(v); }
         else if (k == "enable_prof") { enable_prof = (uint32_t)std::stoul(v); }
         else { rt_err("mode=b200: unused option '" + k + "'"); }  // NESI rejects unused keys (src/nesi.cc:25-35)
@@ -263,6 +269,10 @@ void b200_conv_fwd_t::set_param(string const &node_name, float const *src, uint6
   p_conv_node_t n = cp->must_get_node(node_name);
   if (n->dims.dims_prod() != n_elems) { rt_err("set_param '" + node_name + "': got " + str(n_elems) + " elements, node holds " + str(n->dims.dims_prod())); }
   rtc->copy_raw_to_var(node_name, src, n_elems * 4);
+  // the captured graph skips weight packing (packed once per weight version): new weights need a fresh warm-up + capture
+  if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+  if (graph) { cudaGraphDestroy(graph); graph = nullptr; }
+  warmed = false;
 }
 
 void b200_conv_fwd_t::run_calls() {
@@ -271,7 +281,11 @@ void b200_conv_fwd_t::run_calls() {
 }
 
 void b200_conv_fwd_t::ensure_graph() {
-  if (!warmed) {  // first pass eager: allocates packed-operand buffers, packs weights, sets kernel attributes
+  // source nodes are written from outside the call list: mark them modified so that the warm-up passes and, above all, the captured
+  // graph contain the pack of the first convolution's input (derived operands are cached on the source var's write generation)
+  auto touch_sources = [&]() { for (auto const &dn : cp->data_node_names) { rtc->get_var_raw_native_pointer(dn); } };
+  if (!warmed) {
+    touch_sources();  // first pass eager: allocates packed-operand buffers, packs weights, sets kernel attributes
     uint64_t const l0 = rtc->launches();
     rtc->set_timing(false);
     run_calls();
@@ -287,6 +301,7 @@ void b200_conv_fwd_t::ensure_graph() {
   }
   if (use_graph && !graph_exec) {
     rtc->set_timing(false);
+    touch_sources();
     uint64_t const l0 = rtc->launches();
     CU_CHK(cudaStreamBeginCapture(rtc->stream(), cudaStreamCaptureModeThreadLocal));
     try { run_calls(); } catch (...) { cudaGraph_t g = nullptr; cudaStreamEndCapture(rtc->stream(), &g); if (g) { cudaGraphDestroy(g); } throw; }
@@ -296,22 +311,54 @@ void b200_conv_fwd_t::ensure_graph() {
   }
 }
 
-void b200_conv_fwd_t::run_fwd_raw(int n_set, char const *const *set_names, float const *const *set_bufs, uint64_t const *set_elems, int n_get,
-                                  char const *const *get_names, float *const *get_bufs, uint64_t const *get_elems) {
+int b200_conv_fwd_t::submit(int n_set, char const *const *set_names, float const *const *set_bufs, uint64_t const *set_elems, int n_get,
+                            char const *const *get_names, float *const *get_bufs, uint64_t const *get_elems) {
   for (int i = 0; i < n_set; ++i) {
     p_conv_node_t n = cp->must_get_node(set_names[i]);
     if (n->dims.dims_prod() != set_elems[i]) { rt_err(string("run_fwd: input '") + set_names[i] + "' has " + str(set_elems[i]) + " elements, node holds " + str(n->dims.dims_prod())); }
-    rtc->copy_raw_to_var_async(set_names[i], set_bufs[i], set_elems[i] * 4);
   }
   for (int i = 0; i < n_get; ++i) {
     p_conv_node_t n = cp->must_get_node(get_names[i]);
     if (n->dims.dims_prod() != get_elems[i]) { rt_err(string("run_fwd: output '") + get_names[i] + "' has " + str(get_elems[i]) + " elements, node holds " + str(n->dims.dims_prod())); }
   }
   ensure_graph();
-  if (use_graph) { CU_CHK(cudaGraphLaunch(graph_exec, rtc->stream())); graph_launches += kernels_per_fwd; }
+  if (!copy_stream) {
+    CU_CHK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    for (auto &sl : slots) { CU_CHK(cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming)); CU_CHK(cudaEventCreateWithFlags(&sl.freed, cudaEventDisableTiming)); }
+    for (auto &e : ticket_ev) { CU_CHK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); }
+  }
+  int const ticket = (int)(n_submitted % kTickets);
+  slot_t &sl = slots[n_submitted % kSlots];
+  ++n_submitted;
+  cudaStream_t const st = rtc->stream();
+  // copy stream: wait until the slot's previous contents were consumed, then H2D into the staging slot
+  if (sl.used) { CU_CHK(cudaStreamWaitEvent(copy_stream, sl.freed, 0)); }
+  for (int i = 0; i < n_set; ++i) {
+    void *&stg = sl.staging[set_names[i]];
+    if (!stg) { CU_CHK(cudaMalloc(&stg, set_elems[i] * 4)); }
+    CU_CHK(cudaMemcpyAsync(stg, set_bufs[i], set_elems[i] * 4, cudaMemcpyHostToDevice, copy_stream));
+  }
+  CU_CHK(cudaEventRecord(sl.h2d_done, copy_stream));
+  // compute stream: staging -> node vars (device copy), forward, D2H of the requested nodes
+  CU_CHK(cudaStreamWaitEvent(st, sl.h2d_done, 0));
+  for (int i = 0; i < n_set; ++i) { rtc->copy_device_to_var_async(set_names[i], sl.staging[set_names[i]], set_elems[i] * 4); }
+  CU_CHK(cudaEventRecord(sl.freed, st));
+  sl.used = true;
+  if (use_graph) { CU_CHK(cudaGraphLaunch(graph_exec, st)); graph_launches += kernels_per_fwd; }
   else { rtc->set_timing(false); run_calls(); }
   for (int i = 0; i < n_get; ++i) { rtc->copy_var_to_raw_async(get_bufs[i], get_names[i], get_elems[i] * 4); }
-  rtc->finish_and_sync();
+  CU_CHK(cudaEventRecord(ticket_ev[ticket], st));
+  return ticket;
+}
+
+void b200_conv_fwd_t::wait(int ticket) {
+  if (ticket < 0 || ticket >= kTickets || !ticket_ev[ticket]) { rt_err("wait: invalid ticket"); }
+  CU_CHK(cudaEventSynchronize(ticket_ev[ticket]));
+}
+
+void b200_conv_fwd_t::run_fwd_raw(int n_set, char const *const *set_names, float const *const *set_bufs, uint64_t const *set_elems, int n_get,
+                                  char const *const *get_names, float *const *get_bufs, uint64_t const *get_elems) {
+  wait(submit(n_set, set_names, set_bufs, set_elems, n_get, get_names, get_bufs, get_elems));
 }
 
 void b200_conv_fwd_t::run_fwd(vect_string const &to_set_vns, p_map_str_p_nda_float_t const &fwd, vect_string const &to_get_vns) {
@@ -363,6 +410,7 @@ vector<b200_conv_fwd_t::prof_row_t> b200_conv_fwd_t::profile(int iters) {
   for (int it = 0; it < iters; ++it) {
     rtc->release_per_call_id_data();
     vector<uint32_t> ids;
+    for (auto const &dn : cp->data_node_names) { rtc->get_var_raw_native_pointer(dn); }  // inputs count as freshly written: include their pack
     rtc->set_var_to_zero(absmax_cells_vn);
     for (auto const &c : fwd_calls) { ids.push_back(rtc->run(c.rfc)); }
     rtc->finish_and_sync();

@@ -60,6 +60,12 @@ struct b200_conv_fwd_t {
   void set_param(string const &node_name, float const *src, uint64_t n_elems);
   void run_fwd_raw(int n_set, char const *const *set_names, float const *const *set_bufs, uint64_t const *set_elems, int n_get,
                    char const *const *get_names, float *const *get_bufs, uint64_t const *get_elems);
+  // Pipelined form of run_fwd for serving loops: submit() enqueues H2D of this batch's inputs (on a copy stream, into one of two staging
+  // slots, so it overlaps the previous batch's forward), the forward, and D2H of the requested nodes; wait() blocks until that batch's
+  // outputs are in the caller's host buffers. Host buffers must stay valid until wait(). run_fwd_raw == submit + wait.
+  int submit(int n_set, char const *const *set_names, float const *const *set_bufs, uint64_t const *set_elems, int n_get,
+             char const *const *get_names, float *const *get_bufs, uint64_t const *get_elems);
+  void wait(int ticket);
   float run_device_only(int iters);  // ms per forward, CUDA-event timed on the back-end's stream
   struct prof_row_t { string func_name; float call_ms, kernel_ms; double flops; };
   vector<prof_row_t> profile(int iters);
@@ -77,6 +83,11 @@ struct b200_conv_fwd_t {
   cudaGraphExec_t graph_exec = nullptr;
   uint64_t graph_launches = 0, kernels_per_fwd = 0;
   bool warmed = false;
+  static constexpr int kSlots = 2, kTickets = 8;
+  cudaStream_t copy_stream = nullptr;
+  struct slot_t { map<string, void *> staging; cudaEvent_t h2d_done = nullptr, freed = nullptr; bool used = false; } slots[kSlots];
+  cudaEvent_t ticket_ev[kTickets] = {};
+  uint64_t n_submitted = 0;
   void *flush_buf = nullptr;
   uint64_t flush_bytes = 0;
   vector<double> call_flops;

@@ -53,6 +53,9 @@ struct IgemmParams {
   float const *bias;       // per out-chan
   float const *p_scale;    // {scale, inv_scale} of the P tensor
   float const *q_scale;
+  int debug;   // bit 0: skip TMA (MMA runs on whatever is in smem), bit 1: skip MMA issue (loads + barriers only), bit 2: skip the final global stores,
+               // bit 3: skip the TMEM drains -- timing experiments only (results are garbage)
+  int cm, cn;  // CTA-cluster shape: cm CTAs along P-tiles share (multicast) each Q tile, cn CTAs along Q-tiles share each P tile
   unsigned int *out_absmax;  // optional: publish max|out| (bit pattern) for the consumer's operand scaling
   uint32_t idesc;
 };
@@ -69,6 +72,28 @@ struct IgemmCfg {
   static constexpr uint32_t kColsNeeded = (kPlanes == 2 ? 3 : 2) * BN;
   static constexpr uint32_t kTmemCols = kColsNeeded <= 32 ? 32 : kColsNeeded <= 64 ? 64 : kColsNeeded <= 128 ? 128 : kColsNeeded <= 256 ? 256 : 512;
 };
+
+// Final epilogue of one thread (= one P row) shared by the 1-CTA and 2-CTA kernels: out = max(floor, acc * inv + bias[ch]) for the BN
+// channels (or pixels, when swapped) of this tile. `bias_s` is the tile's bias staged in shared memory (zeros when absent / split-K
+// partial) and `floor` is 0 for ReLU, -inf otherwise, so the loop body has no data-dependent global load and no branch but the ragged-edge
+// guard; addresses advance by a constant stride.
+template <int BN>
+__device__ __forceinline__ float igemm_store_row(float const (&acc)[BN], float inv, float const *bias_s, float floor_v, float *o, long long stride, int nvalid) {
+  float amax = 0.0f;
+  uint32_t const bias_sa = smem_u32(bias_s);
+#pragma unroll
+  for (int j = 0; j < BN; ++j) {
+    if (j < nvalid) {
+      float b;
+      asm("ld.shared.f32 %0, [%1];" : "=f"(b) : "r"(bias_sa + 4 * j));  // LDS with an immediate offset (the generic pointer would compile to LD.E)
+      float const v = fmaxf(fmaf(acc[j], inv, b), floor_v);
+      amax = fmaxf(amax, fabsf(v));
+      *o = v;
+    }
+    o += stride;
+  }
+  return amax;
+}
 
 template <int BN, int kPlanes>
 __global__ void __launch_bounds__(IGEMM_THREADS, 1)
@@ -87,6 +112,7 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
   uint64_t *tmem_full_bar = empty_bar + kStages;   // [2]
   uint64_t *tmem_empty_bar = tmem_full_bar + 2;    // [2]
   uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
+  float *bias_s = reinterpret_cast<float *>(bar_mem + 512);  // BN floats (the barrier block is 1 KB)
 
   int const warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int const m0 = blockIdx.x * IGEMM_BM;
@@ -102,49 +128,71 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
     tma_prefetch_desc(&p_hi_map);
     tma_prefetch_desc(&q_hi_map);
     if (kPlanes == 2) { tma_prefetch_desc(&p_lo_map); tma_prefetch_desc(&q_lo_map); }
-    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    // a stage is released by every CTA that consumed data this CTA multicast into it: cm + cn - 1 of them (itself included)
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], prm.cm + prm.cn - 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4); }
     fence_barrier_init();
   }
   if (warp_id == 1) { tmem_alloc<Cfg::kTmemCols>(tmem_ptr_smem); }
   tc_fence_before();
-  __syncthreads();
+  bool const clustered = (prm.cm * prm.cn) > 1;
+  if (clustered) { cluster_sync_all(); } else { __syncthreads(); }  // peers' barriers must exist before anyone multicasts into them
   tc_fence_after();
   uint32_t const tmem_base = *tmem_ptr_smem;
+  // position inside the cluster and the multicast groups: CTAs with the same cx (same P tile) share P, same cy (same Q tile) share Q
+  uint32_t const cx = clustered ? cluster_ctaid_x() : 0u, cy = clustered ? cluster_ctaid_y() : 0u;
+  uint16_t mask_p = 0, mask_q = 0;
+  for (int j = 0; j < prm.cn; ++j) { mask_p |= static_cast<uint16_t>(1u << (cx + j * prm.cm)); }
+  for (int i = 0; i < prm.cm; ++i) { mask_q |= static_cast<uint16_t>(1u << (i + cy * prm.cm)); }
+  int const p_rows_mine = IGEMM_BM / prm.cn, p_row0 = cy * p_rows_mine;  // the slice of the P tile this CTA fetches for its group
+  int const q_rows_mine = BN / prm.cm, q_row0 = cx * q_rows_mine;
 
   if (warp_id == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int img = 0, h_base = 0, w_base = 0;
+      int const pm0 = m0 + p_row0;  // first P row (output pixel) of this CTA's slice
       if (prm.p_im2col) {
-        img = m0 / prm.ohw;
-        int const rem = m0 - img * prm.ohw;
+        img = pm0 / prm.ohw;
+        int const rem = pm0 - img * prm.ohw;
         int const oy = rem / prm.ow, ox = rem - oy * prm.ow;
         h_base = oy * prm.sy - prm.py;
         w_base = ox * prm.sx - prm.px;
       }
-      for (int i = 0; i < nkb; ++i) {
+      bool const mc_p = prm.cn > 1, mc_q = prm.cm > 1;
+      for (int i = 0; i < ((prm.debug & 1) ? 0 : nkb); ++i) {
         int const kb = kb_begin + i;
         int const s = i % kStages;
         uint32_t const ph = (i / kStages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+        mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);  // the whole stage: own slices + the slices the group's other CTAs multicast in
         uint8_t *st = smem + s * Cfg::kStageBytes;
-        uint8_t *p_hi = st, *p_lo = st + kPBytes;
-        uint8_t *q_hi = st + kPlanes * kPBytes, *q_lo = q_hi + kQBytes;
+        uint8_t *p_hi = st + p_row0 * 128, *p_lo = p_hi + kPBytes;
+        uint8_t *q_hi = st + kPlanes * kPBytes + q_row0 * 128, *q_lo = q_hi + kQBytes;
         if (prm.p_im2col) {
           int const tap = kb / prm.cblks, cb = kb - tap * prm.cblks;
           int const ky = tap / prm.kw, kx = tap - ky * prm.kw;
-          tma_load_im2col_4d(p_hi, &p_hi_map, &full_bar[s], cb * IGEMM_BK, w_base, h_base, img, (uint16_t)kx, (uint16_t)ky);
-          if (kPlanes == 2) {
-            tma_load_im2col_4d(p_lo, &p_lo_map, &full_bar[s], cb * IGEMM_BK, w_base, h_base, img, (uint16_t)kx, (uint16_t)ky);
+          if (mc_p) {
+            tma_load_im2col_4d_mc(p_hi, &p_hi_map, &full_bar[s], cb * IGEMM_BK, w_base, h_base, img, (uint16_t)kx, (uint16_t)ky, mask_p);
+            if (kPlanes == 2) { tma_load_im2col_4d_mc(p_lo, &p_lo_map, &full_bar[s], cb * IGEMM_BK, w_base, h_base, img, (uint16_t)kx, (uint16_t)ky, mask_p); }
+          } else {
+            tma_load_im2col_4d(p_hi, &p_hi_map, &full_bar[s], cb * IGEMM_BK, w_base, h_base, img, (uint16_t)kx, (uint16_t)ky);
+            if (kPlanes == 2) { tma_load_im2col_4d(p_lo, &p_lo_map, &full_bar[s], cb * IGEMM_BK, w_base, h_base, img, (uint16_t)kx, (uint16_t)ky); }
           }
+        } else if (mc_p) {
+          tma_load_2d_mc(p_hi, &p_hi_map, &full_bar[s], kb * IGEMM_BK, pm0, mask_p);
+          if (kPlanes == 2) { tma_load_2d_mc(p_lo, &p_lo_map, &full_bar[s], kb * IGEMM_BK, pm0, mask_p); }
         } else {
-          tma_load_2d(p_hi, &p_hi_map, &full_bar[s], kb * IGEMM_BK, m0);
-          if (kPlanes == 2) { tma_load_2d(p_lo, &p_lo_map, &full_bar[s], kb * IGEMM_BK, m0); }
+          tma_load_2d(p_hi, &p_hi_map, &full_bar[s], kb * IGEMM_BK, pm0);
+          if (kPlanes == 2) { tma_load_2d(p_lo, &p_lo_map, &full_bar[s], kb * IGEMM_BK, pm0); }
         }
-        tma_load_2d(q_hi, &q_hi_map, &full_bar[s], kb * IGEMM_BK, n0);
-        if (kPlanes == 2) { tma_load_2d(q_lo, &q_lo_map, &full_bar[s], kb * IGEMM_BK, n0); }
+        if (mc_q) {
+          tma_load_2d_mc(q_hi, &q_hi_map, &full_bar[s], kb * IGEMM_BK, n0 + q_row0, mask_q);
+          if (kPlanes == 2) { tma_load_2d_mc(q_lo, &q_lo_map, &full_bar[s], kb * IGEMM_BK, n0 + q_row0, mask_q); }
+        } else {
+          tma_load_2d(q_hi, &q_hi_map, &full_bar[s], kb * IGEMM_BK, n0);
+          if (kPlanes == 2) { tma_load_2d(q_lo, &q_lo_map, &full_bar[s], kb * IGEMM_BK, n0); }
+        }
       }
     }
   } else if (warp_id == 1) {
@@ -154,7 +202,7 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
       int i = 0;
       for (int c = 0; c < nchunks; ++c) {
         int const buf = c & 1;
-        mbar_wait(&tmem_empty_bar[buf], ((c >> 1) & 1) ^ 1);
+        if (!(prm.debug & 8)) { mbar_wait(&tmem_empty_bar[buf], ((c >> 1) & 1) ^ 1); }
         tc_fence_after();
         uint32_t const tmem_d = tmem_base + buf * BN;
         uint32_t const tmem_x = tmem_base + 2 * BN;  // cross-term accumulator: 2^-11 of the main one, drained once at the end
@@ -163,14 +211,14 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
         for (; i < i_end; ++i) {
           int const s = i % kStages;
           uint32_t const ph = (i / kStages) & 1;
-          mbar_wait(&full_bar[s], ph);
+          if (!(prm.debug & 1)) { mbar_wait(&full_bar[s], ph); }
           tc_fence_after();
           uint32_t const st = smem_u32(smem + s * Cfg::kStageBytes);
           uint64_t const p_hi = make_kmajor_sw128_desc(st), p_lo = make_kmajor_sw128_desc(st + kPBytes);
           uint64_t const q_hi = make_kmajor_sw128_desc(st + kPlanes * kPBytes);
           uint64_t const q_lo = make_kmajor_sw128_desc(st + kPlanes * kPBytes + kQBytes);
 #pragma unroll
-          for (int k = 0; k < IGEMM_BK / IGEMM_UMMA_K; ++k) {
+          for (int k = 0; k < ((prm.debug & 2) ? 0 : IGEMM_BK / IGEMM_UMMA_K); ++k) {
             uint64_t const adv = static_cast<uint64_t>((k * IGEMM_UMMA_K * 2) >> 4);  // +32 B per k-step inside the swizzle row
             umma_f16(tmem_d, p_hi + adv, q_hi + adv, idesc, first ? 0u : 1u);
             first = false;
@@ -179,7 +227,8 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
               umma_f16(tmem_x, p_lo + adv, q_hi + adv, idesc, 1u);
             }
           }
-          umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
+          // frees this smem stage -- in every CTA that multicast a slice into it -- once the MMAs above have read it
+          if (clustered) { umma_commit_mc(&empty_bar[s], static_cast<uint16_t>(mask_p | mask_q)); } else { umma_commit(&empty_bar[s]); }
         }
         umma_commit(&tmem_full_bar[buf]);  // accumulator chunk complete
       }
@@ -188,10 +237,16 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
     // ===================== epilogue warps =====================
     int const q = warp_id & 3;  // TMEM lane quarter this warp may read
     int const row = q * 32 + lane;
+    // stage this tile's bias in shared memory while the main loop runs (zeros when absent, for split-K partials, or in swapped mode)
+    for (int j = row; j < BN; j += 128) {
+      bool const use = prm.has_bias && prm.split_stride == 0 && !prm.swapped && (n0 + j) < prm.q_rows;
+      bias_s[j] = use ? __ldg(prm.bias + n0 + j) : 0.0f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
     float acc[BN];
 #pragma unroll
     for (int j = 0; j < BN; ++j) { acc[j] = 0.0f; }
-    for (int c = 0; c < nchunks; ++c) {
+    for (int c = 0; c < ((prm.debug & 8) ? 0 : nchunks); ++c) {
       int const buf = c & 1;
       mbar_wait(&tmem_full_bar[buf], (c >> 1) & 1);
       tc_fence_after();
@@ -221,28 +276,17 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
     }
     // ---- write out: NCHW fp32 (or split-K partial) ----
     float const inv = prm.p_scale[1] * prm.q_scale[1];
+    bool const final_out = (prm.split_stride == 0);
+    float const floor_v = (final_out && prm.relu) ? 0.0f : -INFINITY;
     int const prow = m0 + row;
     float amax = 0.0f;
-    if (prow < prm.p_rows) {
+    if (prow < prm.p_rows && !(prm.debug & 4)) {
       float *outp = prm.out + static_cast<long long>(split) * prm.split_stride;
-      bool const final_out = (prm.split_stride == 0);
-      if (!prm.swapped) {
+      if (!prm.swapped) {  // row = pixel, columns = channels (bias per column, staged in smem by the prologue)
         int const img = prow / prm.out_hw, pix = prow - img * prm.out_hw;
-        float *o = outp + (static_cast<long long>(img) * prm.out_chans) * prm.out_hw + pix;
-#pragma unroll
-        for (int j = 0; j < BN; ++j) {
-          int const ch = n0 + j;
-          if (ch < prm.q_rows) {
-            float v = acc[j] * inv;
-            if (final_out) {
-              if (prm.has_bias) { v += __ldg(prm.bias + ch); }
-              if (prm.relu) { v = fmaxf(v, 0.0f); }
-            }
-            amax = fmaxf(amax, fabsf(v));
-            o[static_cast<long long>(ch) * prm.out_hw] = v;
-          }
-        }
-      } else {
+        float *o = outp + (static_cast<long long>(img) * prm.out_chans + n0) * prm.out_hw + pix;
+        amax = igemm_store_row<BN>(acc, inv, bias_s, floor_v, o, prm.out_hw, prm.q_rows - n0);
+      } else {  // row = channel, columns = pixels
         int const ch = prow;
         float const b = (final_out && prm.has_bias) ? __ldg(prm.bias + ch) : 0.0f;
 #pragma unroll
@@ -250,8 +294,7 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
           int const pel = n0 + j;
           if (pel < prm.q_rows) {
             int const img = pel / prm.out_hw, pix = pel - img * prm.out_hw;
-            float v = acc[j] * inv + b;
-            if (final_out && prm.relu) { v = fmaxf(v, 0.0f); }
+            float const v = fmaxf(fmaf(acc[j], inv, b), floor_v);
             amax = fmaxf(amax, fabsf(v));
             outp[(static_cast<long long>(img) * prm.out_chans + ch) * prm.out_hw + pix] = v;
           }
@@ -266,7 +309,7 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (clustered) { cluster_sync_all(); } else { __syncthreads(); }  // peers may still be arriving on this CTA's barriers
   if (warp_id == 1) { tmem_dealloc<Cfg::kTmemCols>(tmem_base); }
 }
 

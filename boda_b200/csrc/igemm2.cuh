@@ -1,0 +1,201 @@
+// igemm2.cuh -- CTA-pair (tcgen05 cta_group::2) version of the contraction kernel in igemm.cuh.
+//
+// Why: with a 128 x 128 tile per SM the shared-memory port is the bottleneck, not the tensor pipe: every 128x128x16 fp16 MMA reads
+// 4 KB of A + 4 KB of B from shared memory in 64 cycles (= the 128 B/clk port limit) while TMA is writing the next stage into the same
+// memory, and the three passes of the fp32-parity mode re-read the hi planes. A CTA pair computes a 256 x BN tile with ONE
+// tcgen05.mma.cta_group::2: each SM supplies its own 128 rows of P and only HALF of the Q tile (BN/2 rows), so per SM the
+// shared-memory reads per MMA drop from 8 KB to 6 KB, the TMA fill per k-block from 64 KB to 48 KB (fp32-parity mode, BN = 128), and
+// the L2->SM operand traffic for Q halves.
+//
+// Roles per CTA (192 threads): warp 0 = TMA producer (both CTAs; all transaction bytes are counted on the LEADER's full barrier),
+// warp 1 = TMEM owner; in the leader CTA also the single-thread MMA issuer for the pair, warps 2..5 = epilogue (each CTA drains its own
+// 128 TMEM lanes = its own 128 output rows). Accumulator ping-pong, cross-term accumulator and periodic draining are as in igemm.cuh.
+#pragma once
+#include "igemm.cuh"
+
+namespace b200 {
+
+template <int BN, int kPlanes>
+struct Igemm2Cfg {
+  static constexpr int kQRows = BN / 2;  // Q rows held by each CTA of the pair
+  static constexpr int kStageBytes = kPlanes * (IGEMM_BM * 128 + kQRows * 128);
+  static constexpr int kMaxSmem = 220 * 1024;
+  static constexpr int kStagesRaw = (kMaxSmem - 2048) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 1024;
+  static constexpr uint32_t kColsNeeded = (kPlanes == 2 ? 3 : 2) * BN;
+  static constexpr uint32_t kTmemCols = kColsNeeded <= 32 ? 32 : kColsNeeded <= 64 ? 64 : kColsNeeded <= 128 ? 128 : kColsNeeded <= 256 ? 256 : 512;
+};
+
+template <int BN, int kPlanes>
+__global__ void __launch_bounds__(IGEMM_THREADS, 1)
+igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_constant__ CUtensorMap p_lo_map,
+                       const __grid_constant__ CUtensorMap q_hi_map, const __grid_constant__ CUtensorMap q_lo_map,
+                       const IgemmParams prm) {
+  using Cfg = Igemm2Cfg<BN, kPlanes>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr uint32_t kPBytes = IGEMM_BM * 128, kQBytes = Cfg::kQRows * 128;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *bar_mem = smem + kStages * Cfg::kStageBytes;
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(bar_mem);   // used in the leader CTA only
+  uint64_t *empty_bar = full_bar + kStages;                      // one per CTA, released by the leader's MMA commits
+  uint64_t *tmem_full_bar = empty_bar + kStages;                 // [2], one per CTA
+  uint64_t *tmem_empty_bar = tmem_full_bar + 2;                  // [2], leader's copy collects both CTAs' epilogue warps
+  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
+  float *bias_s = reinterpret_cast<float *>(bar_mem + 512);
+
+  int const warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t const cta_rank = cluster_ctarank();  // 0 = leader, 1 = peer (cluster dims are (2,1,1))
+  bool const leader = (cta_rank == 0);
+  int const m0 = blockIdx.x * IGEMM_BM;         // this CTA's own 128 P rows (the pair covers 256 consecutive ones)
+  int const n0 = blockIdx.y * BN;
+  int const nkb = prm.kblks_total;
+  int const chunk = prm.chunk_kblks;
+  int const nchunks = (nkb + chunk - 1) / chunk;
+
+  if (warp_id == 0 && lane == 0) {
+    tma_prefetch_desc(&p_hi_map);
+    tma_prefetch_desc(&q_hi_map);
+    if (kPlanes == 2) { tma_prefetch_desc(&p_lo_map); tma_prefetch_desc(&q_lo_map); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 2); mbar_init(&empty_bar[i], 1); }  // full: one arrive per CTA's producer
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 8); }  // empty: 4 epilogue warps x 2 CTAs
+    fence_barrier_init();
+  }
+  if (warp_id == 1) { tmem_alloc_2sm<Cfg::kTmemCols>(tmem_ptr_smem); }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t const tmem_base = *tmem_ptr_smem;
+
+  if (warp_id == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int img = 0, h_base = 0, w_base = 0;
+      if (prm.p_im2col) {
+        img = m0 / prm.ohw;
+        int const rem = m0 - img * prm.ohw;
+        int const oy = rem / prm.ow, ox = rem - oy * prm.ow;
+        h_base = oy * prm.sy - prm.py;
+        w_base = ox * prm.sx - prm.px;
+      }
+      int const q_row0 = n0 + static_cast<int>(cta_rank) * Cfg::kQRows;  // this CTA's half of the Q tile
+      for (int i = 0; i < nkb; ++i) {
+        int const s = i % kStages;
+        uint32_t const ph = (i / kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (leader) { mbar_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes); }  // both CTAs' bytes land on the leader's barrier
+        else { mbar_arrive_remote(&full_bar[s], 0); }
+        uint8_t *st = smem + s * Cfg::kStageBytes;
+        uint8_t *p_hi = st, *p_lo = st + kPBytes;
+        uint8_t *q_hi = st + kPlanes * kPBytes, *q_lo = q_hi + kQBytes;
+        if (prm.p_im2col) {
+          int const tap = i / prm.cblks, cb = i - tap * prm.cblks;
+          int const ky = tap / prm.kw, kx = tap - ky * prm.kw;
+          tma_load_im2col_4d_2sm(p_hi, &p_hi_map, &full_bar[s], cb * IGEMM_BK, w_base, h_base, img, (uint16_t)kx, (uint16_t)ky);
+          if (kPlanes == 2) { tma_load_im2col_4d_2sm(p_lo, &p_lo_map, &full_bar[s], cb * IGEMM_BK, w_base, h_base, img, (uint16_t)kx, (uint16_t)ky); }
+        } else {
+          tma_load_2d_2sm(p_hi, &p_hi_map, &full_bar[s], i * IGEMM_BK, m0);
+          if (kPlanes == 2) { tma_load_2d_2sm(p_lo, &p_lo_map, &full_bar[s], i * IGEMM_BK, m0); }
+        }
+        tma_load_2d_2sm(q_hi, &q_hi_map, &full_bar[s], i * IGEMM_BK, q_row0);
+        if (kPlanes == 2) { tma_load_2d_2sm(q_lo, &q_lo_map, &full_bar[s], i * IGEMM_BK, q_row0); }
+      }
+    }
+  } else if (warp_id == 1) {
+    // ===================== MMA issuer (leader CTA only, one thread for the pair) =====================
+    if (leader && lane == 0) {
+      uint32_t const idesc = prm.idesc;  // M = 256 (the pair), N = BN
+      int i = 0;
+      for (int c = 0; c < nchunks; ++c) {
+        int const buf = c & 1;
+        mbar_wait(&tmem_empty_bar[buf], ((c >> 1) & 1) ^ 1);
+        tc_fence_after();
+        uint32_t const tmem_d = tmem_base + buf * BN;
+        uint32_t const tmem_x = tmem_base + 2 * BN;
+        int const i_end = min(i + chunk, nkb);
+        bool first = true;
+        for (; i < i_end; ++i) {
+          int const s = i % kStages;
+          uint32_t const ph = (i / kStages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          uint32_t const st = smem_u32(smem + s * Cfg::kStageBytes);
+          uint64_t const p_hi = make_kmajor_sw128_desc(st), p_lo = make_kmajor_sw128_desc(st + kPBytes);
+          uint64_t const q_hi = make_kmajor_sw128_desc(st + kPlanes * kPBytes);
+          uint64_t const q_lo = make_kmajor_sw128_desc(st + kPlanes * kPBytes + kQBytes);
+#pragma unroll
+          for (int k = 0; k < IGEMM_BK / IGEMM_UMMA_K; ++k) {
+            uint64_t const adv = static_cast<uint64_t>((k * IGEMM_UMMA_K * 2) >> 4);
+            umma_f16_2sm(tmem_d, p_hi + adv, q_hi + adv, idesc, first ? 0u : 1u);
+            first = false;
+            if (kPlanes == 2) {
+              umma_f16_2sm(tmem_x, p_hi + adv, q_lo + adv, idesc, (i == 0 && k == 0) ? 0u : 1u);
+              umma_f16_2sm(tmem_x, p_lo + adv, q_hi + adv, idesc, 1u);
+            }
+          }
+          umma_commit_2sm(&empty_bar[s], 0x3);  // release the stage in both CTAs
+        }
+        umma_commit_2sm(&tmem_full_bar[buf], 0x3);  // wake both CTAs' epilogues
+      }
+    }
+  } else {
+    // ===================== epilogue warps (each CTA: its own 128 rows) =====================
+    int const q = warp_id & 3;
+    int const row = q * 32 + lane;
+    for (int j = row; j < BN; j += 128) { bias_s[j] = (prm.has_bias && (n0 + j) < prm.q_rows) ? __ldg(prm.bias + n0 + j) : 0.0f; }
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
+    float acc[BN];
+#pragma unroll
+    for (int j = 0; j < BN; ++j) { acc[j] = 0.0f; }
+    for (int c = 0; c < nchunks; ++c) {
+      int const buf = c & 1;
+      mbar_wait(&tmem_full_bar[buf], (c >> 1) & 1);
+      tc_fence_after();
+      uint32_t const taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
+#pragma unroll
+      for (int j0 = 0; j0 < BN; j0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + j0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { acc[j0 + j] += __uint_as_float(r[j]); }
+      }
+      if (kPlanes == 2 && c == nchunks - 1) {
+        uint32_t const xaddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 2 * BN;
+#pragma unroll
+        for (int j0 = 0; j0 < BN; j0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(xaddr + j0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { acc[j0 + j] += __uint_as_float(r[j]); }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { if (leader) { mbar_arrive(&tmem_empty_bar[buf]); } else { mbar_arrive_remote(&tmem_empty_bar[buf], 0); } }
+    }
+    float const inv = prm.p_scale[1] * prm.q_scale[1];
+    float const floor_v = prm.relu ? 0.0f : -INFINITY;
+    int const prow = m0 + row;
+    float amax = 0.0f;
+    if (prow < prm.p_rows) {
+      int const img = prow / prm.out_hw, pix = prow - img * prm.out_hw;
+      float *o = prm.out + (static_cast<long long>(img) * prm.out_chans + n0) * prm.out_hw + pix;
+      amax = igemm_store_row<BN>(acc, inv, bias_s, floor_v, o, prm.out_hw, prm.q_rows - n0);
+    }
+    if (prm.out_absmax) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o)); }
+      if (lane == 0 && amax > 0.0f) { atomicMax(prm.out_absmax, __float_as_uint(amax)); }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer may still be arriving on the leader's barriers / the MMA may still read the peer's shared memory
+  if (warp_id == 1) { tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base); }
+}
+
+}  // namespace b200

@@ -307,14 +307,22 @@ __global__ void softmax_kernel(float const *__restrict__ in, float *__restrict__
 __global__ void absmax_kernel(float const *__restrict__ x, long long n, unsigned int *__restrict__ out_bits) {
   float m = 0.0f;
   long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride) { m = fmaxf(m, fabsf(__ldg(x + i))); }
+  long long const tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    long long const n4 = n >> 2;
+    float4 const *x4 = reinterpret_cast<float4 const *>(x);
+    for (long long i = tid; i < n4; i += stride) {
+      float4 const v = __ldg(x4 + i);
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    for (long long i = (n4 << 2) + tid; i < n; i += stride) { m = fmaxf(m, fabsf(__ldg(x + i))); }
+  } else {
+    for (long long i = tid; i < n; i += stride) { m = fmaxf(m, fabsf(__ldg(x + i))); }
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o)); }
   if ((threadIdx.x & 31) == 0 && m > 0.0f) { atomicMax(out_bits, __float_as_uint(m)); }
 }
-// scale = 2^(13 - floor(log2(absmax))) so that scaled values land in [2^13, 2^14) -- well inside fp16 range with the
-// lo-plane residuals (>= 2^-12 relative) still mostly normal. Writes {scale, 1/scale} and re-arms the abs-max cell.
-// mode 0: fixed scale 1 (bf16 storage / caller opts out).
 __global__ void finalize_scale_kernel(unsigned int *__restrict__ bits, float *__restrict__ scale2, int use_scale) {
   float const s = use_scale ? scale_from_absmax_bits(*bits) : 1.0f;
   scale2[0] = s;
@@ -342,6 +350,39 @@ __global__ void pack_rows_split_kernel(float const *__restrict__ src, uint16_t *
     __half const h = __float2half_rn(v);
     reinterpret_cast<__half *>(hi)[o] = h;
     if (lo) { reinterpret_cast<__half *>(lo)[o] = __float2half_rn(v - __half2float(h)); }
+  }
+}
+
+// Few-channel activations for the row-merged conv path (network inputs: chan = 3): one thread per pixel gathers its kCp-padded channel
+// vector (each channel read is coalesced across the warp) and writes it as ONE 8- or 16-byte word per plane:
+// NCHW -> [img][y][x_pitch][kCp], pixel (y,x) at column x + px_off.
+template <int kCp>
+__global__ void __launch_bounds__(256)
+pack_smallc_kernel(float const *__restrict__ src, uint16_t *__restrict__ hi, uint16_t *__restrict__ lo, float const *__restrict__ scale2, int C, int H, int W,
+                   int Wp, int px_off, long long n_pix, unsigned int const *__restrict__ absmax_bits) {
+  float const s = absmax_bits ? scale_from_absmax_bits(*absmax_bits) : scale2[0];
+  if (absmax_bits && threadIdx.x == 0 && blockIdx.x == 0) { const_cast<float *>(scale2)[0] = s; const_cast<float *>(scale2)[1] = 1.0f / s; }
+  long long const i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n_pix) { return; }
+  long long const hw = static_cast<long long>(H) * W;
+  long long const img = i / hw;
+  int const pix = static_cast<int>(i - img * hw);
+  int const y = pix / W, x = pix - y * W;
+  float const *sp = src + img * C * hw + pix;
+  __half h[kCp], l[kCp];
+#pragma unroll
+  for (int c = 0; c < kCp; ++c) {
+    float const v = (c < C) ? __ldg(sp + c * hw) * s : 0.0f;
+    h[c] = __float2half_rn(v);
+    l[c] = __float2half_rn(v - __half2float(h[c]));
+  }
+  long long const o = ((img * H + y) * Wp + x + px_off) * kCp;
+  if (kCp == 4) {
+    *reinterpret_cast<uint2 *>(hi + o) = *reinterpret_cast<uint2 *>(h);
+    if (lo) { *reinterpret_cast<uint2 *>(lo + o) = *reinterpret_cast<uint2 *>(l); }
+  } else {
+    *reinterpret_cast<uint4 *>(hi + o) = *reinterpret_cast<uint4 *>(h);
+    if (lo) { *reinterpret_cast<uint4 *>(lo + o) = *reinterpret_cast<uint4 *>(l); }
   }
 }
 

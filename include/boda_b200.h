@@ -73,6 +73,13 @@ int b200_fwd_set_param(b200_fwd *f, const char *node_name, const float *host_src
  * buffers in, host buffers out; synchronous. n_elems arrays are checked against the node dims. */
 int b200_fwd_run(b200_fwd *f, int n_set, const char *const *set_names, const float *const *set_bufs, const uint64_t *set_elems,
                  int n_get, const char *const *get_names, float *const *get_bufs, const uint64_t *get_elems);
+/* Pipelined form of run_fwd for serving loops (run_fwd == submit + wait): submit() enqueues H2D of this batch's inputs on a copy
+ * stream (two staging slots, so the copy overlaps the previous batch's forward), the forward and the D2H of the requested nodes, and
+ * returns a ticket (>= 0); wait() blocks until that batch's outputs are in the caller's host buffers. At most 2 batches may be
+ * in flight; host buffers (pinned for overlap) must stay valid until the matching wait(). */
+int b200_fwd_submit(b200_fwd *f, int n_set, const char *const *set_names, const float *const *set_bufs, const uint64_t *set_elems,
+                    int n_get, const char *const *get_names, float *const *get_bufs, const uint64_t *get_elems);
+int b200_fwd_wait(b200_fwd *f, int ticket);
 /* device-resident variant for benchmarking the kernels alone: inputs must have been set by a previous b200_fwd_run /
  * b200_fwd_set_param; runs the forward calls only and returns after a stream sync. */
 int b200_fwd_run_device_only(b200_fwd *f, int iters, float *ms_per_iter_out);

@@ -124,3 +124,28 @@ def test_run_fwd_errors():
         bb.B200ConvFwd(txt, "(bogus_option=1)")
     with pytest.raises(bb.RtException):
         bb.B200ConvFwd(txt.replace("type=LRN", "type=BckLRN"), "")  # gen_op: unhandled op (src/rtc_fwd.cc:402-404)
+
+
+def test_submit_wait_pipeline_matches_run_fwd(oracle):
+    """The pipelined serving form (submit / wait, depth 2) must give exactly what synchronous run_fwd gives, batch by batch."""
+    import boda_b200 as bb
+    from boda_b200 import nets
+    txt, i, o = nets.tiny_net(3)
+    params = nets.synth_params(txt)
+    f = bb.B200ConvFwd(txt, "")
+    for k, v in params.items():
+        f.set_param(k, v)
+    xs = [nets.synth_input((3, 3, 31, 29), seed=s) for s in range(5)]
+    want = [f.run_fwd({i: x}, [o])[o].copy() for x in xs]
+    outs = [np.empty_like(want[0]) for _ in xs]
+    n_in, n_out = xs[0].size, outs[0].size
+    prev = None
+    for k, x in enumerate(xs):
+        t = f.submit_ptrs([i], [x.ctypes.data], [n_in], [o], [outs[k].ctypes.data], [n_out])
+        if prev is not None:
+            f.wait(prev)
+        prev = t
+    f.wait(prev)
+    for k in range(len(xs)):
+        assert np.array_equal(outs[k], want[k]), k
+    assert not np.array_equal(want[0], want[1])

@@ -316,3 +316,41 @@ def test_conv_16bit_storage_modes(oracle, prec):
             assert oracle.mrd(ref, got) < TOL, (prec, N, C, H, W, OC, KH)
     finally:
         r.close()
+
+
+@pytest.mark.parametrize("case", [(8, 64, 28, 28, 256, 3, 3, 1, 1, 1, 1), (32, 96, 27, 27, 256, 5, 5, 1, 1, 2, 2), (20, 256, 13, 13, 384, 3, 3, 1, 1, 1, 1),
+                                  (16, 128, 14, 14, 512, 1, 1, 1, 1, 0, 0), (4, 3, 227, 227, 96, 11, 11, 4, 4, 0, 0)])
+def test_conv_cluster_multicast_is_bit_identical(oracle, case):
+    """CTA pairs (cta_group::2) and TMA-multicast clusters only change which SM fetches / multiplies which operand slice, never the
+    per-output arithmetic: results must be bit-identical to the plain one-CTA-per-tile launch (and correct)."""
+    from b200_harness import OpRunner, conv_op_text
+    N, C, H, W, OC, KH, KW, sy, sx, py, px = case
+    x, w, b = oracle.gen_conv_in(N, C, H, W), oracle.gen_conv_filts(OC, C, KH, KW), oracle.gen_conv_biases(OC)
+    ref = oracle.conv_fwd(x, w, b, (sy, sx), (py, px), relu=True, acc64=True)
+    outs = []
+    import boda_b200 as bb
+    for kw in (dict(use_2cta=1), dict(use_2cta=0, use_clusters=1), dict(use_2cta=0, use_clusters=0)):  # CTA pairs | multicast clusters | plain tiles
+        r = OpRunner()
+        r.rtc.close()
+        r.rtc = bb.B200Compute(**kw)
+        r.rtc.init()
+        outs.append(r.run_conv(conv_op_text(N, C, H, W, OC, KH, KW, sy, sx, py, px, 1), x, w, b, ref.shape))
+        r.close()
+    assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[1], outs[2])
+    assert oracle.mrd(ref, outs[0]) < TOL
+
+
+def test_sgemm_cluster_multicast(oracle):
+    from b200_harness import OpRunner
+    import boda_b200 as bb
+    a, b = oracle.gen_sgemm_a(1024, 1000, 5), oracle.gen_sgemm_b(1024, 520, 5)
+    outs = []
+    for kw in (dict(use_2cta=1), dict(use_2cta=0, use_clusters=1), dict(use_2cta=0, use_clusters=0)):
+        r = OpRunner()
+        r.rtc.close()
+        r.rtc = bb.B200Compute(**kw)
+        r.rtc.init()
+        outs.append(r.run_sgemm(a, b))
+        r.close()
+    assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[1], outs[2])
+    assert oracle.mrd(oracle.sgemm(a, b, acc64=True), outs[0]) < TOL
