@@ -124,6 +124,14 @@ CUtensorMap make_im2col_map(void const *base, bool bf16, conv_plan_t const &cp, 
   return m;
 }
 
+// Every kernel of this back-end asks for the maximum shared-memory carve-out: the contraction kernels need ~200 KB of dynamic shared
+// memory, and letting the bandwidth kernels between them run with the default (L1-heavy) split makes the SMs re-partition L1/shared
+// memory at every layer boundary, which drains the SM and costs microseconds per switch.
+template <typename F> void prefer_max_smem(F *func) {
+  cudaFuncSetAttribute(reinterpret_cast<void const *>(func), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+#define B200_CARVEOUT_ONCE(...) do { static bool done_ = false; if (!done_) { prefer_max_smem(__VA_ARGS__); done_ = true; } } while (0)
+
 int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
 
@@ -496,8 +504,8 @@ struct run_ctx_t {
     bool const use_scale = !bf16;  // bf16 has fp32's exponent range: no scaling needed
     if (!use_scale) { absmax_src = nullptr; }
     if (!absmax_src) {  // nobody published max|x| for this tensor: reduce it here
-      if (use_scale) { b200::absmax_kernel<<<std::max(blocks, 1), 256, 0, st>>>(fptr(src), n, static_cast<unsigned int *>(pk.absmax_bits->p)); launched(); }
-      b200::finalize_scale_kernel<<<1, 1, 0, st>>>(static_cast<unsigned int *>(pk.absmax_bits->p), static_cast<float *>(pk.scale2->p), use_scale ? 1 : 0);
+      if (use_scale) { B200_CARVEOUT_ONCE(b200::absmax_kernel); b200::absmax_kernel<<<std::max(blocks, 1), 256, 0, st>>>(fptr(src), n, static_cast<unsigned int *>(pk.absmax_bits->p)); launched(); }
+      B200_CARVEOUT_ONCE(b200::finalize_scale_kernel); b200::finalize_scale_kernel<<<1, 1, 0, st>>>(static_cast<unsigned int *>(pk.absmax_bits->p), static_cast<float *>(pk.scale2->p), use_scale ? 1 : 0);
       launched();
     }
     dim3 grid(ceil_div(Rpad, 64), ceil_div(Cc, 32), B);
@@ -505,8 +513,8 @@ struct run_ctx_t {
     if (smallc_W > 0 && !bf16 && (Rpad == 4 || Rpad == 8)) {  // row-merged conv input: one thread per pixel, vector stores
       int const H = Cc / smallc_W, Wp = (int)(dst_chi_stride / Rpad), px_off = (int)(dst_base / Rpad);
       long long const n_pix = (long long)B * Cc;
-      if (Rpad == 4) { b200::pack_smallc_kernel<4><<<ceil_div(n_pix, 256), 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, H, smallc_W, Wp, px_off, n_pix, absmax_src); }
-      else { b200::pack_smallc_kernel<8><<<ceil_div(n_pix, 256), 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, H, smallc_W, Wp, px_off, n_pix, absmax_src); }
+      if (Rpad == 4) { B200_CARVEOUT_ONCE(b200::pack_smallc_kernel<4>); b200::pack_smallc_kernel<4><<<ceil_div(n_pix, 256), 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, H, smallc_W, Wp, px_off, n_pix, absmax_src); }
+      else { B200_CARVEOUT_ONCE(b200::pack_smallc_kernel<8>); b200::pack_smallc_kernel<8><<<ceil_div(n_pix, 256), 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, H, smallc_W, Wp, px_off, n_pix, absmax_src); }
       launched();
       pk.src_gen = *src.gen;
       pk.src_ptr = src.buf->p;
@@ -514,15 +522,15 @@ struct run_ctx_t {
     }
     if (Cc == 1 && dst_base == 0) {  // rows are already K-major: elementwise scale + split
       long long const nn = (long long)B * R;
-      if (bf16) { b200::pack_rows_split_kernel<true><<<ceil_div(nn, 256), 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, dst_b_stride, nn, absmax_src); }
-      else { b200::pack_rows_split_kernel<false><<<ceil_div(nn, 256), 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, dst_b_stride, nn, absmax_src); }
+      if (bf16) { B200_CARVEOUT_ONCE(b200::pack_rows_split_kernel<true>); b200::pack_rows_split_kernel<true><<<ceil_div(nn, 256), 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, dst_b_stride, nn, absmax_src); }
+      else { B200_CARVEOUT_ONCE(b200::pack_rows_split_kernel<false>); b200::pack_rows_split_kernel<false><<<ceil_div(nn, 256), 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, dst_b_stride, nn, absmax_src); }
       launched();
       pk.src_gen = *src.gen;
       pk.src_ptr = src.buf->p;
       return;
     }
-    if (bf16) { b200::pack_xpose_split_kernel<true><<<grid, 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, Cc, Rpad, dst_c_stride, dst_b_stride, c_inner, dst_chi_stride, dst_base, absmax_src); }
-    else { b200::pack_xpose_split_kernel<false><<<grid, 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, Cc, Rpad, dst_c_stride, dst_b_stride, c_inner, dst_chi_stride, dst_base, absmax_src); }
+    if (bf16) { B200_CARVEOUT_ONCE(b200::pack_xpose_split_kernel<true>); b200::pack_xpose_split_kernel<true><<<grid, 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, Cc, Rpad, dst_c_stride, dst_b_stride, c_inner, dst_chi_stride, dst_base, absmax_src); }
+    else { B200_CARVEOUT_ONCE(b200::pack_xpose_split_kernel<false>); b200::pack_xpose_split_kernel<false><<<grid, 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, Cc, Rpad, dst_c_stride, dst_b_stride, c_inner, dst_chi_stride, dst_base, absmax_src); }
     launched();
     pk.src_gen = *src.gen;
     pk.src_ptr = src.buf->p;
@@ -666,7 +674,7 @@ struct run_ctx_t {
     else { launch_igemm(cp.BN, planes, grid, act_hi, act_lo, w_hi, w_lo, prm); }
     mark_kernel_end();
     if (cp.splits > 1) {
-      b200::splitk_reduce_kernel<<<ceil_div(out_elems, 256), 256, 0, st>>>(static_cast<float *>(f.splitk_ws->p), fptr(vout), bias, out_elems, cp.splits, cp.OC, cp.OH * cp.OW, cp.relu, prm.out_absmax);
+      B200_CARVEOUT_ONCE(b200::splitk_reduce_kernel); b200::splitk_reduce_kernel<<<ceil_div(out_elems, 256), 256, 0, st>>>(static_cast<float *>(f.splitk_ws->p), fptr(vout), bias, out_elems, cp.splits, cp.OC, cp.OH * cp.OW, cp.relu, prm.out_absmax);
       launched();
     }
     im.bump(vout);
@@ -736,14 +744,14 @@ struct run_ctx_t {
     if (KH == KW && sy == sx && ((KH == 3 && sy == 2) || (KH == 3 && sy == 1) || (KH == 2 && sy == 2)) && planes <= 65535ll * 65535ll) {
       dim3 const grid(ceil_div((long long)OH * OW, 256), (unsigned)std::min<long long>(planes, 65535), (unsigned)ceil_div(planes, 65535));
       if (planes > 65535 && planes % 65535 != 0) { unsup_err("pool: plane count not expressible as a grid"); }
-      if (KH == 3 && sy == 2) { b200::pool_kernel_fixed<3, 2><<<grid, 256, 0, st>>>(fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, absmax_cell("out")); }
-      else if (KH == 3) { b200::pool_kernel_fixed<3, 1><<<grid, 256, 0, st>>>(fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, absmax_cell("out")); }
-      else { b200::pool_kernel_fixed<2, 2><<<grid, 256, 0, st>>>(fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, absmax_cell("out")); }
+      if (KH == 3 && sy == 2) { B200_CARVEOUT_ONCE(b200::pool_kernel_fixed<3, 2>); b200::pool_kernel_fixed<3, 2><<<grid, 256, 0, st>>>(fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, absmax_cell("out")); }
+      else if (KH == 3) { B200_CARVEOUT_ONCE(b200::pool_kernel_fixed<3, 1>); b200::pool_kernel_fixed<3, 1><<<grid, 256, 0, st>>>(fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, absmax_cell("out")); }
+      else { B200_CARVEOUT_ONCE(b200::pool_kernel_fixed<2, 2>); b200::pool_kernel_fixed<2, 2><<<grid, 256, 0, st>>>(fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, absmax_cell("out")); }
       launched();
       im.bump(vout);
       return;
     }
-    b200::pool_kernel<<<ceil_div(n_out, 256), 256, 0, st>>>(fptr(vin), fptr(vout), n_out, H, W, OH, OW, KH, KW, sy, sx, py, px, (int)scalar("avg_pool", true, 0), absmax_cell("out"));
+    B200_CARVEOUT_ONCE(b200::pool_kernel); b200::pool_kernel<<<ceil_div(n_out, 256), 256, 0, st>>>(fptr(vin), fptr(vout), n_out, H, W, OH, OW, KH, KW, sy, sx, py, px, (int)scalar("avg_pool", true, 0), absmax_cell("out"));
     launched();
     im.bump(vout);
   }
@@ -760,9 +768,9 @@ struct run_ctx_t {
     int const blocks = ceil_div(n_pels, 128);
     constexpr int kChunk = 16;
     dim3 const grid(blocks, ceil_div(C, kChunk));
-    if (ls == 5) { b200::lrn_kernel<5, kChunk><<<grid, 128, 0, st>>>(fptr(vin), fptr(vout), n_pels, C, HW, alpha, beta, k, absmax_cell("out")); }
-    else if (ls == 3) { b200::lrn_kernel<3, kChunk><<<grid, 128, 0, st>>>(fptr(vin), fptr(vout), n_pels, C, HW, alpha, beta, k, absmax_cell("out")); }
-    else if (ls <= 32) { b200::lrn_kernel_generic<<<blocks, 128, 0, st>>>(fptr(vin), fptr(vout), n_pels, C, HW, ls, alpha, beta, k, absmax_cell("out")); }
+    if (ls == 5) { B200_CARVEOUT_ONCE(b200::lrn_kernel<5, kChunk>); b200::lrn_kernel<5, kChunk><<<grid, 128, 0, st>>>(fptr(vin), fptr(vout), n_pels, C, HW, alpha, beta, k, absmax_cell("out")); }
+    else if (ls == 3) { B200_CARVEOUT_ONCE(b200::lrn_kernel<3, kChunk>); b200::lrn_kernel<3, kChunk><<<grid, 128, 0, st>>>(fptr(vin), fptr(vout), n_pels, C, HW, alpha, beta, k, absmax_cell("out")); }
+    else if (ls <= 32) { B200_CARVEOUT_ONCE(b200::lrn_kernel_generic); b200::lrn_kernel_generic<<<blocks, 128, 0, st>>>(fptr(vin), fptr(vout), n_pels, C, HW, ls, alpha, beta, k, absmax_cell("out")); }
     else { unsup_err("lrn: local_size > 32"); }
     launched();
     im.bump(vout);
@@ -771,7 +779,7 @@ struct run_ctx_t {
   void run_relu() {
     var_info_t &v = var("inout");
     long long const n = v.dims.dims_prod();
-    b200::relu_kernel<<<ceil_div(ceil_div(n, 4), 256), 256, 0, st>>>(fptr(v), n);
+    B200_CARVEOUT_ONCE(b200::relu_kernel); b200::relu_kernel<<<ceil_div(ceil_div(n, 4), 256), 256, 0, st>>>(fptr(v), n);
     launched();
     im.bump(v);
   }
@@ -782,7 +790,7 @@ struct run_ctx_t {
     if (!(vin.dims == vout.dims)) { rt_err("softmax: in/prob dims differ"); }
     int const C = vin.dims.dsz("chan"), HW = vin.dims.dsz("y") * vin.dims.dsz("x");
     long long const n_pels = (long long)vin.dims.dsz("img") * HW;
-    b200::softmax_kernel<<<ceil_div(n_pels * 32, 256), 256, 0, st>>>(fptr(vin), fptr(vout), n_pels, C, HW);
+    B200_CARVEOUT_ONCE(b200::softmax_kernel); b200::softmax_kernel<<<ceil_div(n_pels * 32, 256), 256, 0, st>>>(fptr(vin), fptr(vout), n_pels, C, HW);
     launched();
     im.bump(vout);
   }
@@ -796,7 +804,7 @@ struct run_ctx_t {
     long long const per_img = (long long)C * HW, out_img_stride = (long long)OC * HW, out_off = (long long)ocix * HW;
     int const vec4 = ((per_img % 4) == 0 && (out_img_stride % 4) == 0 && (out_off % 4) == 0) ? 1 : 0;
     long long const work = vec4 ? per_img * n_img / 4 : per_img * n_img;
-    b200::concat_copy_kernel<<<ceil_div(work, 256), 256, 0, st>>>(fptr(vin), fptr(vout), per_img, out_img_stride, out_off, n_img, vec4, absmax_cell("out"));
+    B200_CARVEOUT_ONCE(b200::concat_copy_kernel); b200::concat_copy_kernel<<<ceil_div(work, 256), 256, 0, st>>>(fptr(vin), fptr(vout), per_img, out_img_stride, out_off, n_img, vec4, absmax_cell("out"));
     launched();
     im.bump(vout);
   }
@@ -813,7 +821,7 @@ struct run_ctx_t {
       a.ins[i] = fptr(vi);
     }
     long long const n = vout.dims.dims_prod();
-    b200::reduce_sum_kernel<<<ceil_div(n, 256), 256, 0, st>>>(a, fptr(vout), n);
+    B200_CARVEOUT_ONCE(b200::reduce_sum_kernel); b200::reduce_sum_kernel<<<ceil_div(n, 256), 256, 0, st>>>(a, fptr(vout), n);
     launched();
     im.bump(vout);
   }
@@ -832,7 +840,7 @@ struct run_ctx_t {
     else if (fn == "gen_data_sgemm_a") { kind = 2; inner = v.dims.dsz("M"); inner2 = v.dims.dsz("K"); salt = 12738732u; }
     else if (fn == "gen_data_sgemm_b") { kind = 3; inner = v.dims.dsz("N"); inner2 = v.dims.dsz("K"); salt = 12738732u; }
     else { unsup_err("be=b200: unknown generator '" + fn + "'"); }
-    b200::gen_data_kernel<<<ceil_div(n, 256), 256, 0, st>>>(fptr(v), (uint32_t)n, kind, inner, inner2, mode, vi, salt);
+    B200_CARVEOUT_ONCE(b200::gen_data_kernel); b200::gen_data_kernel<<<ceil_div(n, 256), 256, 0, st>>>(fptr(v), (uint32_t)n, kind, inner, inner2, mode, vi, salt);
     launched();
     im.bump(v);
   }

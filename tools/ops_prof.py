@@ -1,0 +1,145 @@
+#!/usr/bin/env python
+"""ops-prof for be=b200 (the reference's `boda ops-prof`, src/rtc_prof.cc:139-371, for one back-end): for every op line of --ops-fn
+(current or stale syntax) generate the inputs ON DEVICE with gen_data (mode 5), run the op, compare the full output with the CPU oracle
+(mrd), and report time, effective TFLOP/s (2*M*N*K, src/latex-util.H:116-133), arithmetic intensity and fraction of the measured
+B200 roofline min(peak_TC, AI * HBM_BW).  Timing: CUDA events, >= 3 warm-ups, median of --iters launches (the reference times ONE cold
+launch, src/rtc_prof.cc:107,123 -- deliberately not copied).  `kernel_ms` is the contraction kernel alone, `call_ms` adds the operand
+packing the call performs (activation transpose/split; filters are packed once per weight version).
+
+  python tools/ops_prof.py --ops-fn ops/c3-conv-ops-small.txt --prec fp16 --out profiles/ops_prof_c3_fp16.md
+"""
+import argparse, json, os, sys, time
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import boda_b200 as bb
+from oracle import boda_oracle as bo
+from b200_harness import with_relu
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    d = json.load(open(p)) if os.path.exists(p) else {}
+    return d.get("bf16_tflops", 1590.0), d.get("hbm_gbs", 6650.0), ("measured" if d else "fallback")
+
+
+def round_to(a, prec):
+    import torch
+    if prec == "fp16":
+        return torch.from_numpy(a).to(torch.float16).float().numpy()
+    if prec == "bf16":
+        return torch.from_numpy(a).to(torch.bfloat16).float().numpy()
+    return a
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ops-fn", required=True)
+    ap.add_argument("--prec", default="fp32", choices=["fp32", "fp16", "bf16"])
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--out", default="")
+    ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--max-check-gflop", type=float, default=40.0, help="skip the CPU oracle compare for ops larger than this")
+    args = ap.parse_args()
+    peak_tf, hbm_gbs, src = peaks()
+    rtc = bb.B200Compute(prec=args.prec)
+    rtc.init()
+    rows = []
+    for li, line in enumerate(open(args.ops_fn)):
+        line = line.strip()
+        if not line:
+            continue
+        op = bo.parse_op(line)
+        fn = "op%d" % li
+        txt = with_relu(line) if "dims_vals" not in line else line  # stale lines carry no nda_vals list to extend: relu flag via arg below
+        if op.type == "Convolution":
+            if "dims_vals" in line:  # translate to the current syntax with conv_has_relu=1 (per-op flows force it, src/cnn_op.cc:337)
+                d = {k: op.get_dims(k).dims for k in ("in", "filts", "out")}
+                from b200_harness import conv_op_text
+                i, f = d["in"], d["filts"]
+                txt = conv_op_text(i["img"], i["chan"], i["y"], i["x"], f["out_chan"], f["y"], f["x"], *op.pt("stride", (1, 1)), *op.pt("in_pad", (0, 0)), 1)
+            names = {"in": ["img", "chan", "y", "x"], "filts": ["out_chan", "in_chan", "y", "x"], "biases": ["out_chan"], "out": ["img", "chan", "y", "x"]}
+            outs = ["out"]
+        else:
+            names = {"a": ["K", "M"], "b": ["K", "N"], "c": ["M", "N"]}
+            outs = ["c"]
+            txt = "(str_vals=(type=sgemm),nda_vals=(a=(dims=(K=%d,M=%d)),b=(dims=(K=%d,N=%d)),c=(dims=(M=%d,N=%d))))" % (
+                op.get_dims("a").dims["K"], op.get_dims("a").dims["M"], op.get_dims("b").dims["K"], op.get_dims("b").dims["N"], op.get_dims("c").dims["M"], op.get_dims("c").dims["N"])
+        rtc.compile(fn, txt)
+        for k, dn in names.items():
+            d = op.get_dims(k).dims
+            rtc.create_var_with_dims(fn + "_" + k, [(n, d[n]) for n in dn])
+        ins = [k for k in names if k not in outs]
+        flops = bo.op_flops(op)
+        do_check = (not args.no_check) and flops / 1e9 <= args.max_check_gflop
+        host = {}
+        if args.prec == "fp32":
+            for k in ins:  # device-side gen_data, exactly the reference flow (src/rtc_prof.cc:73-90)
+                d = op.get_dims(k).dims
+                g = "%s_gen_%s" % (fn, k)
+                rtc.compile(g, "(str_vals=(type=gen_data,func_name=gen_data_%s_%s),nda_vals=(%s=(dims=(%s)),vi=(tn=float,v=0.0),mode=(tn=uint32_t,v=5)))"
+                            % (op.type, k, k, ",".join("%s=%d" % (n, d[n]) for n in names[k])))
+                rtc.run(g, {k: fn + "_" + k})
+            if do_check:
+                host = bo.gen_op_inputs(op, 5)
+        else:  # fp16 / bf16 storage: same hash values rounded to the storage type on the host, oracle fed the rounded values
+            host = {k: (round_to(v, args.prec) if k != "biases" else v) for k, v in bo.gen_op_inputs(op, 5).items()}
+            for k in ins:
+                rtc.copy_nda_to_var(fn + "_" + k, host[k])
+        amap = {k: fn + "_" + k for k in names}
+        for _ in range(args.warmup):
+            rtc.run(fn, amap)
+        rtc.finish_and_sync()
+        rtc.release_per_call_id_data()
+        ids = []
+        for _ in range(args.iters):
+            if ins:  # mark the activation operand as rewritten so every timed call repacks it, as a forward pass would
+                rtc.get_var_raw_native_pointer(fn + "_" + ins[0])
+            ids.append(rtc.run(fn, amap))
+        rtc.finish_and_sync()
+        call_ms = float(np.median([rtc.get_dur(i, i) for i in ids]))
+        kern_ms = float(np.median([rtc.get_kernel_dur(i) for i in ids]))
+        m = float("nan")
+        if do_check:
+            got = rtc.copy_var_to_nda(fn + "_" + outs[0])
+            ref = bo.run_op(op, host, acc64=True)[outs[0]]
+            m = bo.mrd(ref, got)
+        esz = 4  # algorithmic bytes use the op's declared element type: fp32 tensors at the boundary (src/latex-util.H:119,133)
+        nbytes = esz * sum(int(np.prod(op.get_dims(k).shape())) for k in names)
+        ai = flops / nbytes
+        roof_tf = min(peak_tf, ai * hbm_gbs / 1e3)
+        tf_k, tf_c = flops / kern_ms / 1e9, flops / call_ms / 1e9
+        desc = line[:0]
+        if op.type == "Convolution":
+            i, f, o = op.get_dims("in").dims, op.get_dims("filts").dims, op.get_dims("out").dims
+            desc = "conv %dx%d/%d/%d %d->%d @%dx%d B=%d" % (f["y"], f["x"], op.pt("stride", (1, 1))[0], op.pt("in_pad", (0, 0))[0], i["chan"], f["out_chan"], i["y"], i["x"], i["img"])
+        else:
+            a = op.get_dims("a").dims
+            desc = "sgemm M=%d N=%d K=%d" % (a["M"], op.get_dims("b").dims["N"], a["K"])
+        rows.append(dict(op=desc, gflop=flops / 1e9, mbytes=nbytes / 1e6, ai=ai, kernel_ms=kern_ms, call_ms=call_ms, tflops_kernel=tf_k, tflops_call=tf_c,
+                         roof_tflops=roof_tf, frac_roof=tf_k / roof_tf, frac_tc_peak=tf_k / peak_tf, mrd=m))
+        print("%-44s %7.2f GF  AI %6.0f  kernel %8.4f ms %7.1f TF/s  call %8.4f ms %7.1f TF/s  roof %6.0f  frac %.3f  mrd %.2e" %
+              (desc, flops / 1e9, ai, kern_ms, tf_k, call_ms, tf_c, roof_tf, tf_k / roof_tf, m), flush=True)
+        for k in names:
+            rtc.release_var(fn + "_" + k)
+        rtc.release_all_funcs()
+        rtc.release_per_call_id_data()
+    if args.out:
+        with open(args.out, "w") as f:
+            f.write("# ops-prof, be=b200, prec=%s, %s\n\n" % (args.prec, os.path.basename(args.ops_fn)))
+            f.write("Peaks (%s): tensor %.1f TFLOP/s (bf16 cuBLAS burst), HBM %.0f GB/s. Roofline = min(peak, AI x HBM). Inputs: reference gen_data mode 5%s. "
+                    "Timing: CUDA events, median of %d after %d warm-ups; `kernel` = contraction kernel alone, `call` = with per-call operand packing. "
+                    "mrd = max rel diff (floor 1) vs the CPU oracle (acc64).\n\n" % (src, peak_tf, hbm_gbs, "" if args.prec == "fp32" else " rounded to " + args.prec, args.iters, args.warmup))
+            f.write("| op | GFLOP | MB | AI F/B | kernel ms | kernel TF/s | call ms | call TF/s | roofline TF/s | kernel / roofline | kernel / TC peak | mrd |\n|---|---|---|---|---|---|---|---|---|---|---|---|\n")
+            for r in rows:
+                f.write("| %s | %.2f | %.1f | %.0f | %.4f | %.1f | %.4f | %.1f | %.0f | %.3f | %.3f | %.1e |\n" %
+                        (r["op"], r["gflop"], r["mbytes"], r["ai"], r["kernel_ms"], r["tflops_kernel"], r["call_ms"], r["tflops_call"], r["roof_tflops"], r["frac_roof"], r["frac_tc_peak"], r["mrd"]))
+        with open(os.path.splitext(args.out)[0] + ".json", "w") as f:
+            json.dump(rows, f, indent=1)
+    rtc.close()
+
+
+if __name__ == "__main__":
+    main()
