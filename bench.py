@@ -84,14 +84,18 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": int(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+NET_NAME = "alexnet_ng_conv"
+NET_IN_SZ = 227
+
+
 def cpu_reference_forward(n_images, reps=1):
     """The reference arm / cpu_baseline: the oracle port of Boda's operator semantics, whole AlexNet-ng forward on the host
     cores (OpenMP over all of them). Returns (images/s, cores, seconds). This is the one place bench.py executes oracle/."""
     from boda_b200 import nets
     from oracle import boda_oracle as bo, net_oracle
-    txt, i, o = nets.alexnet_ng_conv(n_images)
+    txt, i, o = nets.NETS[NET_NAME](n_images)
     params = nets.synth_params(txt)
-    x = nets.synth_input((n_images, 3, 227, 227))
+    x = nets.synth_input((n_images, 3, NET_IN_SZ, NET_IN_SZ))
     t0 = time.perf_counter()
     for _ in range(reps):
         net_oracle.run_pipe(txt, {i: x}, params)
@@ -137,7 +141,14 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prec", default="fp32", choices=["fp32", "fp16", "bf16"])
+    ap.add_argument("--net", default="alexnet_ng_conv", choices=["alexnet_ng_conv", "nin_imagenet", "googlenet_conv"],
+                    help="default = BASELINE configs[1]; googlenet_conv --batch 64 --prec bf16 = configs[3]")
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU per step")
     args = ap.parse_args()
+    global NET_NAME, NET_IN_SZ, METRIC
+    NET_NAME = args.net
+    NET_IN_SZ = 224 if args.net == "googlenet_conv" else 227
+    METRIC = "%s_fwd_images_per_sec" % args.net
     if args.impl != "reference":
         args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -162,8 +173,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    B = PER_GPU_BATCH
-    txt, in_node, out_node = nets.alexnet_ng_conv(B)
+    B = args.batch
+    txt, in_node, out_node = nets.NETS[args.net](B)
     extra = os.environ.get("B200_FWD_OPTS", "")  # e.g. "use_2cta=0,use_graph=0" for A/B experiments
     fwd = bb.B200ConvFwd(txt, "(prec=%s,device=%d%s)" % (args.prec, local_rank, ("," + extra) if extra else ""))
 
@@ -190,8 +201,8 @@ def main():
             fwd.set_param(n, params[n])
 
     # ---- inputs: each rank owns its shard of the global batch (images [rank*B, (rank+1)*B)), pinned host memory
-    x_host = torch.from_numpy(nets.synth_input((B, 3, 227, 227), seed=rank)).pin_memory()
-    x_host2 = torch.from_numpy(nets.synth_input((B, 3, 227, 227), seed=rank + 1000)).pin_memory()
+    x_host = torch.from_numpy(nets.synth_input((B, 3, NET_IN_SZ, NET_IN_SZ), seed=rank)).pin_memory()
+    x_host2 = torch.from_numpy(nets.synth_input((B, 3, NET_IN_SZ, NET_IN_SZ), seed=rank + 1000)).pin_memory()
     logits_host = torch.empty((B, 1000, 1, 1), dtype=torch.float32).pin_memory()
     logits_host2 = torch.empty((B, 1000, 1, 1), dtype=torch.float32).pin_memory()
     in_elems, out_elems = x_host.numel(), logits_host.numel()
@@ -295,7 +306,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp32": "f32 (fp16 hi/lo split, 3 tcgen05.mma per k-step, fp32 accumulate)", "fp16": "f16", "bf16": "bf16"}[args.prec], "data": "synthetic",
-            "config": {"workload": "nets/alexnet_ng_conv fwd, batch=32 per GPU, fp32, 227x227 (BASELINE configs[1])", "global_batch": global_batch,
+            "config": {"workload": "nets/%s fwd, batch=%d per GPU, %s, %dx%d%s" % (args.net, B, args.prec, NET_IN_SZ, NET_IN_SZ, " (BASELINE configs[1])" if (args.net, B, args.prec) == ("alexnet_ng_conv", 32, "fp32") else ""), "global_batch": global_batch,
                        "parallelism": "batch-shard x%d, NCCL weight broadcast at init + logits all-gather per step" % world if world > 1 else "single GPU",
                        "l2": "256 MiB scratch buffer overwritten before every timed step (outside the events)", "cuda_graph": True},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": in_elems * 4, "d2h_bytes_per_step": out_elems * 4, "ms_per_step": 1e3 * e2e_s / args.steps,
@@ -303,16 +314,16 @@ def main():
                     "sync_run_fwd_ms_per_step": e2e_sync_ms},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None,
-                         "traffic": None, "kernel": "b200::igemm_umma_kernel (8 launches per forward, one per Convolution)",
+                         "traffic": None, "kernel": "b200::igemm_umma_2cta_kernel / igemm_umma_kernel (%d launches per forward, one per Convolution)" % len(conv_rows),
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernels timed one by one with CUDA events), %s" % peaks["source"],
                          "note": "algorithmic fp32 conv FLOPs / summed launch durations; the fp32-parity mode issues 3 fp16 MMAs per product, so the tensor pipe does 3x this"},
             "clocks": sampler.summary(),
             "per_call": [{"func": r[0], "call_ms": round(r[1], 5), "kernel_ms": round(r[2], 5), "gflop": round(r[3] / 1e9, 3)} for r in prof],
         }
         if not args.no_cpu_baseline and world == 1:
-            v, cores, secs = cpu_reference_forward(32, reps=2)
+            v, cores, secs = cpu_reference_forward(B, reps=2)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "2 x AlexNet-ng forward of the full 32-image batch through the oracle port (OpenMP, all host cores), %.1f s" % secs}
+                                    "sample": "2 x %s forward of the full %d-image batch through the oracle port (OpenMP, all host cores), %.1f s" % (args.net, B, secs)}
         _emit(line)
     if dist:
         dist.barrier()

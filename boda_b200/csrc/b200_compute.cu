@@ -510,11 +510,15 @@ struct run_ctx_t {
     }
     dim3 grid(ceil_div(Rpad, 64), ceil_div(Cc, 32), B);
     uint16_t *hi = static_cast<uint16_t *>(pk.hi->p), *lo = want_lo ? static_cast<uint16_t *>(pk.lo->p) : nullptr;
-    if (smallc_W > 0 && !bf16 && (Rpad == 4 || Rpad == 8)) {  // row-merged conv input: one thread per pixel, vector stores
+    if (smallc_W > 0 && (Rpad == 4 || Rpad == 8)) {  // row-merged conv input: one thread per pixel, vector stores
       int const H = Cc / smallc_W, Wp = (int)(dst_chi_stride / Rpad), px_off = (int)(dst_base / Rpad);
       long long const n_pix = (long long)B * Cc;
-      if (Rpad == 4) { B200_CARVEOUT_ONCE(b200::pack_smallc_kernel<4>); b200::pack_smallc_kernel<4><<<ceil_div(n_pix, 256), 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, H, smallc_W, Wp, px_off, n_pix, absmax_src); }
-      else { B200_CARVEOUT_ONCE(b200::pack_smallc_kernel<8>); b200::pack_smallc_kernel<8><<<ceil_div(n_pix, 256), 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, H, smallc_W, Wp, px_off, n_pix, absmax_src); }
+      float *sc = static_cast<float *>(pk.scale2->p);
+      int const nb = ceil_div(n_pix, 256);
+      if (Rpad == 4 && !bf16) { B200_CARVEOUT_ONCE(b200::pack_smallc_kernel<4, false>); b200::pack_smallc_kernel<4, false><<<nb, 256, 0, st>>>(fptr(src), hi, lo, sc, R, H, smallc_W, Wp, px_off, n_pix, absmax_src); }
+      else if (Rpad == 4) { B200_CARVEOUT_ONCE(b200::pack_smallc_kernel<4, true>); b200::pack_smallc_kernel<4, true><<<nb, 256, 0, st>>>(fptr(src), hi, lo, sc, R, H, smallc_W, Wp, px_off, n_pix, absmax_src); }
+      else if (!bf16) { B200_CARVEOUT_ONCE(b200::pack_smallc_kernel<8, false>); b200::pack_smallc_kernel<8, false><<<nb, 256, 0, st>>>(fptr(src), hi, lo, sc, R, H, smallc_W, Wp, px_off, n_pix, absmax_src); }
+      else { B200_CARVEOUT_ONCE(b200::pack_smallc_kernel<8, true>); b200::pack_smallc_kernel<8, true><<<nb, 256, 0, st>>>(fptr(src), hi, lo, sc, R, H, smallc_W, Wp, px_off, n_pix, absmax_src); }
       launched();
       pk.src_gen = *src.gen;
       pk.src_ptr = src.buf->p;
@@ -741,12 +745,25 @@ struct run_ctx_t {
     long long const n_out = vout.dims.dims_prod();
     long long const planes = (long long)vin.dims.dsz("img") * vin.dims.dsz("chan");
     int const avg = (int)scalar("avg_pool", true, 0);
-    if (KH == KW && sy == sx && ((KH == 3 && sy == 2) || (KH == 3 && sy == 1) || (KH == 2 && sy == 2)) && planes <= 65535ll * 65535ll) {
-      dim3 const grid(ceil_div((long long)OH * OW, 256), (unsigned)std::min<long long>(planes, 65535), (unsigned)ceil_div(planes, 65535));
-      if (planes > 65535 && planes % 65535 != 0) { unsup_err("pool: plane count not expressible as a grid"); }
-      if (KH == 3 && sy == 2) { B200_CARVEOUT_ONCE(b200::pool_kernel_fixed<3, 2>); b200::pool_kernel_fixed<3, 2><<<grid, 256, 0, st>>>(fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, absmax_cell("out")); }
-      else if (KH == 3) { B200_CARVEOUT_ONCE(b200::pool_kernel_fixed<3, 1>); b200::pool_kernel_fixed<3, 1><<<grid, 256, 0, st>>>(fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, absmax_cell("out")); }
-      else { B200_CARVEOUT_ONCE(b200::pool_kernel_fixed<2, 2>); b200::pool_kernel_fixed<2, 2><<<grid, 256, 0, st>>>(fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, absmax_cell("out")); }
+    if (KH == KW && sy == sx && ((KH == 3 && sy == 2) || (KH == 3 && sy == 1) || (KH == 2 && sy == 2)) && (long long)H * W <= 4096 && planes < (1ll << 31)) {  // small planes: stage in smem
+      size_t const smem = (size_t)H * W * 4;
+      unsigned int *cell = absmax_cell("out");
+#define B200_POOL_PLANE(K_, S_) do { \
+        static bool attr_ = false; \
+        if (!attr_) { CU_CHK(cudaFuncSetAttribute(b200::pool_plane_kernel<K_, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); prefer_max_smem(b200::pool_plane_kernel<K_, S_>); attr_ = true; } \
+        b200::pool_plane_kernel<K_, S_><<<(unsigned)planes, 256, smem, st>>>(fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, cell); } while (0)
+      if (KH == 3 && sy == 2) { B200_POOL_PLANE(3, 2); } else if (KH == 3) { B200_POOL_PLANE(3, 1); } else { B200_POOL_PLANE(2, 2); }
+#undef B200_POOL_PLANE
+      launched();
+      im.bump(vout);
+      return;
+    }
+    if (KH == KW && sy == sx && ((KH == 3 && sy == 2) || (KH == 3 && sy == 1) || (KH == 2 && sy == 2)) && planes <= 65535) {
+      dim3 const grid(ceil_div((long long)OH * OW, 256), (unsigned)planes, 1);
+      unsigned int *cell = absmax_cell("out");
+      if (KH == 3 && sy == 2) { B200_CARVEOUT_ONCE(b200::pool_kernel_fixed<3, 2>); b200::pool_kernel_fixed<3, 2><<<grid, 256, 0, st>>>(fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, cell); }
+      else if (KH == 3) { B200_CARVEOUT_ONCE(b200::pool_kernel_fixed<3, 1>); b200::pool_kernel_fixed<3, 1><<<grid, 256, 0, st>>>(fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, cell); }
+      else { B200_CARVEOUT_ONCE(b200::pool_kernel_fixed<2, 2>); b200::pool_kernel_fixed<2, 2><<<grid, 256, 0, st>>>(fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, cell); }
       launched();
       im.bump(vout);
       return;

@@ -203,6 +203,42 @@ pool_kernel_fixed(float const *__restrict__ in, float *__restrict__ out, int H, 
   if (out_absmax) { publish_absmax_warp(valid ? fabsf(out_v) : 0.0f, out_absmax); }
 }
 
+// Whole-plane variant: one CTA stages an (img,chan) plane in shared memory with coalesced loads and computes its outputs from there, so
+// the stride-S window reads never touch L1/L2 (the overlapping-window kernel above reads every input K*K/S^2 times through L1 with
+// half-used sectors). Used when the plane fits (H*W*4 bytes of dynamic shared memory).
+template <int K, int S>
+__global__ void __launch_bounds__(256)
+pool_plane_kernel(float const *__restrict__ in, float *__restrict__ out, int H, int W, int OH, int OW, int py, int px, int avg_pool,
+                  unsigned int *out_absmax) {
+  extern __shared__ float plane_s[];
+  long long const plane = blockIdx.x;
+  float const *ip = in + plane * H * W;
+  int const n_in = H * W, n_out = OH * OW;
+  for (int i = threadIdx.x; i < n_in; i += blockDim.x) { plane_s[i] = __ldg(ip + i); }
+  __syncthreads();
+  float amax = 0.0f;
+  for (int p = threadIdx.x; p < n_out; p += blockDim.x) {
+    int const oy = p / OW, ox = p - oy * OW;
+    int const y0 = oy * S - py, x0 = ox * S - px;
+    float out_v = avg_pool ? 0.0f : -FLT_MAX, cnt = 0;
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) {
+#pragma unroll
+      for (int ky = 0; ky < K; ++ky) {
+        int const in_y = y0 + ky, in_x = x0 + kx;
+        if (in_y >= 0 && in_x >= 0 && in_x < W && in_y < H) {
+          float const v = plane_s[in_y * W + in_x];
+          if (avg_pool) { out_v += v; cnt += 1; } else { out_v = fmaxf(out_v, v); }
+        }
+      }
+    }
+    if (avg_pool) { out_v = __fdiv_rn(out_v, cnt); }
+    out[plane * n_out + p] = out_v;
+    amax = fmaxf(amax, fabsf(out_v));
+  }
+  if (out_absmax) { publish_absmax_warp(amax, out_absmax); }
+}
+
 // ---- lrn (test/rtc/lrn.cucl:35-50, LRN_MATCH_CAFFE branch) ----------------------------------------------------
 // The reference runs one thread per (img,y,x) that walks ALL channels with a running add-new / subtract-old sum of squares.
 // At B200 widths that is latency-bound (a 27x27 map has too few pixels to fill 148 SMs), so a thread here owns one pixel and
@@ -210,39 +246,36 @@ pool_kernel_fixed(float const *__restrict__ in, float *__restrict__ out, int H, 
 // reference's sequence for chunk 0) and then runs the reference's running update inside the chunk. Consecutive threads are
 // consecutive x, so every channel step reads/writes coalesced 128-byte rows. kLS = local_size (ring buffer in registers).
 template <int kLS, int kChunk>
-__global__ void lrn_kernel(float const *__restrict__ in, float *__restrict__ out, long long n_pels, int C, int HW, float alpha,
-                           float beta, float k, unsigned int *out_absmax) {
+__global__ void __launch_bounds__(128)
+lrn_kernel(float const *__restrict__ in, float *__restrict__ out, long long n_pels, int C, int HW, float alpha, float beta, float k,
+           unsigned int *out_absmax) {
   long long const pel = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   bool const valid = pel < n_pels;
   long long const img = valid ? pel / HW : 0;
   long long const base = img * C * HW + (valid ? (pel - img * HW) : 0);
   constexpr int hls = kLS >> 1;
-  float amax = 0.0f;
+  constexpr int kTot = kChunk + 2 * hls;  // input channels c_begin-hls .. c_begin+kChunk-1+hls
   int const c_begin = blockIdx.y * kChunk;
-  int const c_end = min(C, c_begin + kChunk);
-  int const total = valid ? (c_end - c_begin) + 2 * hls : 0;  // input channels c_begin-hls .. c_end-1+hls
   float const alpha_over_ls = alpha / (float)kLS;
-  float ls_buf[kLS];
+  float v[kTot];
 #pragma unroll
-  for (int i = 0; i < kLS; ++i) { ls_buf[i] = 0.0f; }
-  float ls_sum = 0.0f;
-  for (int s0 = 0; s0 < total; s0 += kLS) {  // ring slot == s % kLS is compile-time inside the unrolled body
+  for (int s = 0; s < kTot; ++s) {  // all loads first: kTot independent requests in flight per thread
+    int const ic = c_begin - hls + s;
+    v[s] = (valid && ic >= 0 && ic < C) ? __ldg(in + base + static_cast<long long>(ic) * HW) : 0.0f;
+  }
+  float ls_sum = 0.0f, amax = 0.0f;
 #pragma unroll
-    for (int u = 0; u < kLS; ++u) {
-      int const sidx = s0 + u;
-      if (sidx < total) {
-        int const ic = c_begin - hls + sidx;
-        float const ls_old = ls_buf[u];
-        ls_buf[u] = (ic >= 0 && ic < C) ? __ldg(in + base + static_cast<long long>(ic) * HW) : 0.0f;
-        ls_sum = __fmaf_rn(ls_buf[u], ls_buf[u], ls_sum);
-        ls_sum = __fmaf_rn(-ls_old, ls_old, ls_sum);
-        if (sidx >= 2 * hls) {
-          float const scale_base = __fmaf_rn(ls_sum, alpha_over_ls, k);
-          float const scale = __powf(scale_base, -beta);  // the reference compiles lrn.cucl with --use_fast_math (src/nvrtc_util.cc:251)
-          float const ov = ls_buf[(u + kLS - hls) % kLS] * scale;
-          out[base + static_cast<long long>(ic - hls) * HW] = ov;
-          amax = fmaxf(amax, fabsf(ov));
-        }
+  for (int s = 0; s < kTot; ++s) {  // the reference's running update: add the newest square, subtract the one leaving the window
+    ls_sum = __fmaf_rn(v[s], v[s], ls_sum);
+    if (s >= kLS) { ls_sum = __fmaf_rn(-v[s - kLS], v[s - kLS], ls_sum); }
+    if (s >= 2 * hls) {
+      int const oc = c_begin + s - 2 * hls;
+      if (valid && oc < C) {
+        float const scale_base = __fmaf_rn(ls_sum, alpha_over_ls, k);
+        float const scale = __powf(scale_base, -beta);  // the reference compiles lrn.cucl with --use_fast_math (src/nvrtc_util.cc:251)
+        float const ov = v[s - hls] * scale;
+        out[base + static_cast<long long>(oc) * HW] = ov;
+        amax = fmaxf(amax, fabsf(ov));
       }
     }
   }
@@ -356,7 +389,7 @@ __global__ void pack_rows_split_kernel(float const *__restrict__ src, uint16_t *
 // Few-channel activations for the row-merged conv path (network inputs: chan = 3): one thread per pixel gathers its kCp-padded channel
 // vector (each channel read is coalesced across the warp) and writes it as ONE 8- or 16-byte word per plane:
 // NCHW -> [img][y][x_pitch][kCp], pixel (y,x) at column x + px_off.
-template <int kCp>
+template <int kCp, bool kBf16>
 __global__ void __launch_bounds__(256)
 pack_smallc_kernel(float const *__restrict__ src, uint16_t *__restrict__ hi, uint16_t *__restrict__ lo, float const *__restrict__ scale2, int C, int H, int W,
                    int Wp, int px_off, long long n_pix, unsigned int const *__restrict__ absmax_bits) {
@@ -369,12 +402,19 @@ pack_smallc_kernel(float const *__restrict__ src, uint16_t *__restrict__ hi, uin
   int const pix = static_cast<int>(i - img * hw);
   int const y = pix / W, x = pix - y * W;
   float const *sp = src + img * C * hw + pix;
-  __half h[kCp], l[kCp];
+  uint16_t h[kCp], l[kCp];
 #pragma unroll
   for (int c = 0; c < kCp; ++c) {
     float const v = (c < C) ? __ldg(sp + c * hw) * s : 0.0f;
-    h[c] = __float2half_rn(v);
-    l[c] = __float2half_rn(v - __half2float(h[c]));
+    if (kBf16) {
+      __nv_bfloat16 const hv = __float2bfloat16_rn(v);
+      h[c] = __bfloat16_as_ushort(hv);
+      l[c] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(hv)));
+    } else {
+      __half const hv = __float2half_rn(v);
+      h[c] = __half_as_ushort(hv);
+      l[c] = __half_as_ushort(__float2half_rn(v - __half2float(hv)));
+    }
   }
   long long const o = ((img * H + y) * Wp + x + px_off) * kCp;
   if (kCp == 4) {

@@ -116,6 +116,59 @@ def nin_imagenet(batch: int = 32, in_sz: int = 227) -> Tuple[str, str, str]:
     return p.text(), "data", "pool4"
 
 
+def googlenet_conv(batch: int = 64, in_sz: int = 224) -> Tuple[str, str, str]:
+    """nets/googlenet_conv/train_val.prototxt (BASELINE config C4): 7x7/2 stem, 9 inception modules (4-way Concat), LRN after pool1 and
+    conv2, the two auxiliary classifiers (all present in the TEST graph) and the 7x7 average pool + 1x1 classifier. 64 Convolution layers.
+    Returns (pipe_text, input node, main output node `cls3_fc`); the auxiliary outputs are `cls1_fc2` and `cls2_fc2`."""
+    p = PipeBuilder()
+    p.data("data", batch, 3, in_sz, in_sz)
+    p.conv("conv1", "data", "conv1", 64, 7, 2, 3, relu="relu1")
+    p.pool("pool1", "conv1", "pool1", 3, 2)
+    p.lrn("norm1", "pool1", "norm1")
+    p.conv("reduction2", "norm1", "reduction2", 64, 1, relu="relu_reduction2")
+    p.conv("conv2", "reduction2", "conv2", 192, 3, 1, 1, relu="relu2")
+    p.lrn("norm2", "conv2", "norm2")
+    p.pool("pool2", "norm2", "pool2", 3, 2)
+
+    def inception(n, bot, top, r1, r2, o0, o1, o2, o3):
+        pre = "icp%d_" % n
+        p.conv(pre + "reduction1", bot, pre + "reduction1", r1, 1, relu="relu_" + pre + "reduction1")
+        p.conv(pre + "reduction2", bot, pre + "reduction2", r2, 1, relu="relu_" + pre + "reduction2")
+        p.pool(pre + "pool", bot, pre + "pool", 3, 1, 1)
+        p.conv(pre + "out0", bot, pre + "out0", o0, 1, relu="relu_" + pre + "out0")
+        p.conv(pre + "out1", pre + "reduction1", pre + "out1", o1, 3, 1, 1, relu="relu_" + pre + "out1")
+        p.conv(pre + "out2", pre + "reduction2", pre + "out2", o2, 5, 1, 2, relu="relu_" + pre + "out2")
+        p.conv(pre + "out3", pre + "pool", pre + "out3", o3, 1, relu="relu_" + pre + "out3")
+        p.concat(top, [pre + "out0", pre + "out1", pre + "out2", pre + "out3"], top)
+        return top
+
+    def aux(n, bot):
+        pre = "cls%d_" % n
+        p.pool(pre + "pool", bot, pre + "pool", 5, 3, 0, avg=True)
+        p.conv(pre + "reduction", pre + "pool", pre + "reduction", 128, 1, relu="relu_" + pre + "reduction")
+        p.conv(pre + "fc1-conv", pre + "reduction", pre + "fc1", 1024, 4, 1, 0, relu="relu_" + pre + "fc1")
+        p.dropout(pre + "drop", pre + "fc1", 0.7)
+        p.conv(pre + "fc2-conv", pre + "fc1", pre + "fc2", 1000, 1)
+
+    inception(1, "pool2", "icp2_in", 96, 16, 64, 128, 32, 32)
+    inception(2, "icp2_in", "icp2_out", 128, 32, 128, 192, 96, 64)
+    p.pool("icp3_in", "icp2_out", "icp3_in", 3, 2)
+    inception(3, "icp3_in", "icp3_out", 96, 16, 192, 208, 48, 64)
+    aux(1, "icp3_out")
+    inception(4, "icp3_out", "icp4_out", 112, 24, 160, 224, 64, 64)
+    inception(5, "icp4_out", "icp5_out", 128, 24, 128, 256, 64, 64)
+    inception(6, "icp5_out", "icp6_out", 144, 32, 112, 288, 64, 64)
+    aux(2, "icp6_out")
+    inception(7, "icp6_out", "icp7_out", 160, 32, 256, 320, 128, 128)
+    p.pool("icp8_in", "icp7_out", "icp8_in", 3, 2)
+    inception(8, "icp8_in", "icp8_out", 160, 32, 256, 320, 128, 128)
+    inception(9, "icp8_out", "icp9_out", 192, 48, 384, 384, 128, 128)
+    p.pool("cls3_pool", "icp9_out", "cls3_pool", 7, 1, 0, avg=True)
+    p.dropout("cls3_drop", "cls3_pool", 0.4)
+    p.conv("cls3_fc-conv", "cls3_pool", "cls3_fc", 1000, 1)
+    return p.text(), "data", "cls3_fc"
+
+
 def tiny_net(batch: int = 3) -> Tuple[str, str, str]:
     """A small net touching every forward op kind (conv variants, LRN, max/avg/global pool, concat, eltwise, softmax)."""
     p = PipeBuilder()
@@ -203,3 +256,6 @@ def synth_params(pipe_text: str, seed: int = 0) -> Dict[str, np.ndarray]:
 
 def synth_input(shape, seed: int = 0, scale: float = 25.0) -> np.ndarray:
     return hash_fill(shape, 234234567 + 15485863 * seed, scale)
+
+
+NETS = {"alexnet_ng_conv": alexnet_ng_conv, "nin_imagenet": nin_imagenet, "googlenet_conv": googlenet_conv, "tiny_net": tiny_net}

@@ -149,3 +149,39 @@ def test_submit_wait_pipeline_matches_run_fwd(oracle):
     for k in range(len(xs)):
         assert np.array_equal(outs[k], want[k]), k
     assert not np.array_equal(want[0], want[1])
+
+
+def test_googlenet_conv_b2_all_nodes(oracle):
+    """BASELINE config C4's net (64 convolutions, 9 inception Concats, aux classifiers) at batch 2, fp32-parity mode: every node."""
+    from boda_b200 import nets
+    txt, i, o = nets.googlenet_conv(2)
+    fwd, got, ref, names, x, params = _run_both(txt, i, (2, 3, 224, 224))
+    print("googlenet b=2 worst node mrd vs acc64 oracle %.3e" % _check_nodes(oracle, names, got, ref))
+    assert got["cls3_fc"].shape == (2, 1000, 1, 1) and got["cls1_fc2"].shape == (2, 1000, 1, 1)
+
+
+@pytest.mark.parametrize("prec,tol", [("bf16", 1e-2), ("fp16", 2e-3)])
+def test_googlenet_conv_16bit_storage(oracle, prec, tol):
+    """C4 runs in bf16 storage mode (fp16 = C3's mode). The oracle chain rounds every convolution's operands to the storage type as the
+    back-end does, but each side rounds ITS OWN activations: a 1e-5 difference upstream flips the rounding of ~1 % of the elements
+    (one storage ulp each), so whole-net agreement is bounded by the storage precision, not by 1e-3. Gate: max|a-b| / max|ref| per
+    node below 1e-2 (bf16, 8-bit significand) / 2e-3 (fp16); the per-layer 1e-3 mrd gate on identical pre-rounded inputs is
+    tests/test_gpu_parity.py::test_conv_16bit_storage_modes."""
+    import boda_b200 as bb
+    from boda_b200 import nets
+    from oracle import net_oracle
+    txt, i, o = nets.googlenet_conv(2)
+    params = nets.synth_params(txt)
+    x = nets.synth_input((2, 3, 224, 224))
+    f = bb.B200ConvFwd(txt, "(prec=%s)" % prec)
+    for k, v in params.items():
+        f.set_param(k, v)
+    names = _node_names(txt)
+    got = f.run_fwd({i: x}, names)
+    ref = net_oracle.run_pipe(txt, {i: x}, params, round_to=("bf16" if prec == "bf16" else np.float16), acc64=True)
+    worst = 0.0
+    for n in names:
+        e = float(np.abs(ref[n].astype(np.float64) - got[n]).max() / max(1e-6, np.abs(ref[n]).max()))
+        worst = max(worst, e)
+        assert e < tol, (n, e)
+    print("googlenet %s: worst node max|a-b|/max|ref| = %.3e" % (prec, worst))
