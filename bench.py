@@ -179,26 +179,14 @@ def main():
     fwd = bb.B200ConvFwd(txt, "(prec=%s,device=%d%s)" % (args.prec, local_rank, ("," + extra) if extra else ""))
 
     # ---- weights: rank 0 synthesises, one NCCL broadcast over NVLink distributes (north_star: "single NCCL broadcast of weights")
+    from boda_b200 import shard
     shapes = nets.conv_param_shapes(txt)
-    names = sorted(shapes)
-    total = sum(int(np.prod(shapes[n])) for n in names)
     if world > 1:
-        flat = torch.empty(total, dtype=torch.float32, device="cuda")
-        if rank == 0:
-            params = nets.synth_params(txt)
-            flat.copy_(torch.from_numpy(np.concatenate([params[n].ravel() for n in names])))
-        dist.broadcast(flat, src=0)
-        host = flat.cpu().numpy()
-        off = 0
-        for n in names:
-            sz = int(np.prod(shapes[n]))
-            fwd.set_param(n, host[off:off + sz].reshape(shapes[n]))
-            off += sz
-        del flat
+        params = shard.broadcast_params(dist, shapes, nets.synth_params(txt) if rank == 0 else None, device="cuda")
     else:
         params = nets.synth_params(txt)
-        for n in names:
-            fwd.set_param(n, params[n])
+    for n in sorted(shapes):
+        fwd.set_param(n, params[n])
 
     # ---- inputs: each rank owns its shard of the global batch (images [rank*B, (rank+1)*B)), pinned host memory
     x_host = torch.from_numpy(nets.synth_input((B, 3, NET_IN_SZ, NET_IN_SZ), seed=rank)).pin_memory()
@@ -243,7 +231,7 @@ def main():
     e2e_pipelined(args.warmup)
     fwd.run_timed(args.warmup, L2_FLUSH_BYTES)
     if dist:
-        dist.all_gather_into_tensor(gathered, logits_dev)
+        shard.gather_logits(dist, logits_dev, out=gathered)
     barrier()
 
     sampler.start()
@@ -260,16 +248,14 @@ def main():
         for _ in range(args.steps):
             dev_ms += fwd.run_timed(1, L2_FLUSH_BYTES)[0]
             ev0.record()
-            dist.all_gather_into_tensor(gathered, logits_dev)
+            shard.gather_logits(dist, logits_dev, out=gathered)
             ev1.record()
             ev1.synchronize()
             dev_ms += ev0.elapsed_time(ev1)
     barrier()
     launches = fwd.launches() - launches0
     if dist:
-        t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms = float(t.item())
+        dev_ms = shard.max_over_ranks(dist, dev_ms, device="cuda")
 
     # ---- timed region 2: end to end through run_fwd with host buffers (e2e)
     barrier()
@@ -282,9 +268,7 @@ def main():
         e2e_step()
     e2e_sync_ms = 1e3 * (time.perf_counter() - t0) / min(args.steps, 20)
     if dist:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+        e2e_s = shard.max_over_ranks(dist, e2e_s, device="cuda")
     barrier()
 
     # ---- roofline of the dominant kernel: per-launch CUDA events around every contraction kernel (eager profile pass)

@@ -119,7 +119,8 @@ Dims = Sequence[Tuple[str, int]]
 class B200Compute:
     """`be=b200`: same methods as rtc_compute_t (src/rtc_compute.H:35-97); ndas are numpy arrays + named dims."""
 
-    def __init__(self, prec: str = "fp32", acc_chunk_kblks: Optional[int] = None, device: int = 0, use_clusters: Optional[int] = None, use_2cta: Optional[int] = None):
+    def __init__(self, prec: str = "fp32", acc_chunk_kblks: Optional[int] = None, device: int = 0, use_clusters: Optional[int] = None, use_2cta: Optional[int] = None,
+                 **opts):
         self._h = lib().b200_rtc_create()
         if not self._h:
             raise RtException(lib().b200_last_error().decode())
@@ -131,6 +132,8 @@ class B200Compute:
             _chk(lib().b200_rtc_set_option(self._h, b"use_clusters", _b(str(use_clusters))))
         if use_2cta is not None:
             _chk(lib().b200_rtc_set_option(self._h, b"use_2cta", _b(str(use_2cta))))
+        for k, v in opts.items():  # any other back-end option (use_taps, taps_2cta, acc_chunk_kblks_16, debug_flags ...); unknown keys are errors
+            _chk(lib().b200_rtc_set_option(self._h, _b(k), _b(str(v))))
         self._dims: Dict[str, Dims] = {}
 
     def close(self):

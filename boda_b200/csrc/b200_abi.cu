@@ -50,6 +50,12 @@ B200_API int b200_rtc_set_option(b200_rtc *r, const char *key, const char *val) 
     string const k = key, v = val;
     if (k == "prec") { r->rtc->prec = (v == "fp32") ? B200_PREC_FP32_SPLIT : (v == "fp16") ? B200_PREC_FP16 : (v == "bf16") ? B200_PREC_BF16 : (rt_err("unknown prec '" + v + "'"), B200_PREC_FP32_SPLIT); }
     else if (k == "acc_chunk_kblks") { r->rtc->acc_chunk_kblks = std::stoi(v); }
+    else if (k == "acc_chunk_kblks_16") { r->rtc->acc_chunk_kblks_16 = std::stoi(v); }
+    else if (k == "use_taps") { r->rtc->use_taps = std::stoi(v); }
+    else if (k == "use_pdl") { r->rtc->use_pdl = std::stoi(v); }
+    else if (k == "taps_2cta") { r->rtc->taps_2cta = std::stoi(v); }
+    else if (k == "taps_max_b_stages") { r->rtc->taps_max_b_stages = std::stoi(v); }
+    else if (k == "taps_max_a_stages") { r->rtc->taps_max_a_stages = std::stoi(v); }
     else if (k == "use_clusters") { r->rtc->use_clusters = std::stoi(v); }
     else if (k == "use_2cta") { r->rtc->use_2cta = std::stoi(v); }
     else if (k == "debug_flags") { r->rtc->debug_flags = std::stoi(v); }

@@ -4,6 +4,7 @@
 #include "b200_compute.h"
 #include "igemm.cuh"
 #include "igemm2.cuh"
+#include "igemm3.cuh"
 #include "pointwise.cuh"
 #include <cudaTypedefs.h>
 #include <algorithm>
@@ -50,7 +51,10 @@ struct conv_plan_t {
   bool im2col, full_kernel, swapped;
   bool rowmerge;  // small-chan convs (conv1): K = (ky) x [(kx,chan) run of 64 contiguous NHWC elements], see plan_conv
   int Wp;         // rowmerge: pixel pitch of a packed image row (>= W + 2*px, and long enough for the last 64-element run)
+  bool taps;      // stride-1 KHxKW conv eligible for the tap-reuse kernel (igemm3.cuh): shared-padding NHWC layout, virtual-pixel GEMM rows
+  int tHp, tWp;   // taps: padded image height / row pitch (H + pad_y, W + pad_x)
   int BN, splits, kblks_total, kblks_per_split;
+  int kb_mod, ksteps_last;  // K tail: see IgemmParams
   long long a_rows, a_row_stride;  // activation matrix view (2-d modes)
   long long w_tap_stride, w_row_stride;
   int relu, has_bias;
@@ -387,6 +391,11 @@ void plan_conv(conv_plan_t &cp, op_base_t const &op, int num_sms) {
     cp.a_rows = cp.N; cp.a_row_stride = (long long)cp.H * cp.W * cp.Cpad;
   }
   cp.w_row_stride = cp.rowmerge ? (long long)cp.KH * 64 : round_up((long long)cp.KH * cp.KW * cp.w_tap_stride, 64);
+  {  // real data in the last k-block of a group (rest: zero padding in the packed operands / TMA out-of-bounds fill)
+    long long const k_grp = cp.rowmerge ? (long long)cp.KW * cp.Cpad : (cp.im2col || k1) ? (long long)cp.Cpad : (long long)cp.KH * cp.KW * cp.Cpad;
+    cp.kb_mod = cp.rowmerge ? 1 : ceil_div(k_grp, 64);
+    cp.ksteps_last = ceil_div(k_grp - (long long)(cp.kb_mod - 1) * 64, 16);
+  }
   cp.swapped = (!cp.im2col) && pixels <= 64 && cp.OC >= 128;
   if (cp.swapped) { cp.BN = pixels <= 32 ? 32 : 64; }
   else { cp.BN = cp.OC > 64 ? 128 : (cp.OC > 32 ? 64 : 32); }
@@ -399,6 +408,13 @@ void plan_conv(conv_plan_t &cp, op_base_t const &op, int num_sms) {
   }
   cp.kblks_per_split = ceil_div(cp.kblks_total, cp.splits);
   cp.splits = ceil_div(cp.kblks_total, cp.kblks_per_split);
+  // tap-reuse kernel: stride 1, window > 1x1, padding no larger than the window overhang, and an acceptable share of dropped virtual pixels
+  cp.taps = false; cp.tHp = cp.H + cp.py; cp.tWp = cp.W + cp.px;
+  if (cp.im2col && !cp.rowmerge && cp.sx == 1 && cp.sy == 1 && cp.KH * cp.KW > 1 && cp.px <= cp.KW - 1 && cp.py <= cp.KH - 1 && cp.splits == 1 && !cp.swapped) {
+    double const waste = (double)cp.tHp * cp.tWp / ((double)cp.OH * cp.OW);
+    long long const halo = round_up(128 + (long long)(cp.KH - 1) * cp.tWp + cp.KW - 1, 8);
+    if (waste <= 1.5 && halo <= 768 && (long long)cp.N * cp.tHp * cp.tWp < (1ll << 31)) { cp.taps = true; }
+  }
 }
 
 }  // namespace
@@ -486,6 +502,20 @@ struct run_ctx_t {
   }
   float *fptr(var_info_t &v) { if (v.dims.tn != "float") { unsup_err("be=b200: only float vars are supported, got " + v.dims.pretty()); } return static_cast<float *>(v.buf->p); }
 
+  // Every kernel goes through here: programmatic dependent launch (pdl.cuh) lets it be scheduled while its predecessor drains.
+  template <typename... KArgs, typename... Args>
+  void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args &&...args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = rtc.use_pdl ? 1 : 0;
+    CU_CHK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+  }
+
   // src [B][R][Cc] fp32 -> planes [B][Cc][..R..] 16-bit, with abs-max scaling. Cached on (pointer, generation).
   void pack(packed_t &pk, var_info_t &src, int B, int R, int Cc, int Rpad, long long dst_c_stride, long long dst_b_stride, long long total_elems, bool want_lo, bool bf16,
             int c_inner = 0, long long dst_chi_stride = 0, long long dst_base = 0, unsigned int const *absmax_src = nullptr, int smallc_W = 0) {
@@ -504,8 +534,8 @@ struct run_ctx_t {
     bool const use_scale = !bf16;  // bf16 has fp32's exponent range: no scaling needed
     if (!use_scale) { absmax_src = nullptr; }
     if (!absmax_src) {  // nobody published max|x| for this tensor: reduce it here
-      if (use_scale) { B200_CARVEOUT_ONCE(b200::absmax_kernel); b200::absmax_kernel<<<std::max(blocks, 1), 256, 0, st>>>(fptr(src), n, static_cast<unsigned int *>(pk.absmax_bits->p)); launched(); }
-      B200_CARVEOUT_ONCE(b200::finalize_scale_kernel); b200::finalize_scale_kernel<<<1, 1, 0, st>>>(static_cast<unsigned int *>(pk.absmax_bits->p), static_cast<float *>(pk.scale2->p), use_scale ? 1 : 0);
+      if (use_scale) { B200_CARVEOUT_ONCE(b200::absmax_kernel); launch_k(b200::absmax_kernel, dim3(std::max(blocks, 1)), dim3(256), 0, fptr(src), n, static_cast<unsigned int *>(pk.absmax_bits->p)); launched(); }
+      B200_CARVEOUT_ONCE(b200::finalize_scale_kernel); launch_k(b200::finalize_scale_kernel, dim3(1), dim3(1), 0, static_cast<unsigned int *>(pk.absmax_bits->p), static_cast<float *>(pk.scale2->p), use_scale ? 1 : 0);
       launched();
     }
     dim3 grid(ceil_div(Rpad, 64), ceil_div(Cc, 32), B);
@@ -515,10 +545,10 @@ struct run_ctx_t {
       long long const n_pix = (long long)B * Cc;
       float *sc = static_cast<float *>(pk.scale2->p);
       int const nb = ceil_div(n_pix, 256);
-      if (Rpad == 4 && !bf16) { B200_CARVEOUT_ONCE(b200::pack_smallc_kernel<4, false>); b200::pack_smallc_kernel<4, false><<<nb, 256, 0, st>>>(fptr(src), hi, lo, sc, R, H, smallc_W, Wp, px_off, n_pix, absmax_src); }
-      else if (Rpad == 4) { B200_CARVEOUT_ONCE(b200::pack_smallc_kernel<4, true>); b200::pack_smallc_kernel<4, true><<<nb, 256, 0, st>>>(fptr(src), hi, lo, sc, R, H, smallc_W, Wp, px_off, n_pix, absmax_src); }
-      else if (!bf16) { B200_CARVEOUT_ONCE(b200::pack_smallc_kernel<8, false>); b200::pack_smallc_kernel<8, false><<<nb, 256, 0, st>>>(fptr(src), hi, lo, sc, R, H, smallc_W, Wp, px_off, n_pix, absmax_src); }
-      else { B200_CARVEOUT_ONCE(b200::pack_smallc_kernel<8, true>); b200::pack_smallc_kernel<8, true><<<nb, 256, 0, st>>>(fptr(src), hi, lo, sc, R, H, smallc_W, Wp, px_off, n_pix, absmax_src); }
+      if (Rpad == 4 && !bf16) { B200_CARVEOUT_ONCE(b200::pack_smallc_kernel<4, false>); launch_k(b200::pack_smallc_kernel<4, false>, dim3(nb), dim3(256), 0, fptr(src), hi, lo, sc, R, H, smallc_W, Wp, px_off, n_pix, absmax_src); }
+      else if (Rpad == 4) { B200_CARVEOUT_ONCE(b200::pack_smallc_kernel<4, true>); launch_k(b200::pack_smallc_kernel<4, true>, dim3(nb), dim3(256), 0, fptr(src), hi, lo, sc, R, H, smallc_W, Wp, px_off, n_pix, absmax_src); }
+      else if (!bf16) { B200_CARVEOUT_ONCE(b200::pack_smallc_kernel<8, false>); launch_k(b200::pack_smallc_kernel<8, false>, dim3(nb), dim3(256), 0, fptr(src), hi, lo, sc, R, H, smallc_W, Wp, px_off, n_pix, absmax_src); }
+      else { B200_CARVEOUT_ONCE(b200::pack_smallc_kernel<8, true>); launch_k(b200::pack_smallc_kernel<8, true>, dim3(nb), dim3(256), 0, fptr(src), hi, lo, sc, R, H, smallc_W, Wp, px_off, n_pix, absmax_src); }
       launched();
       pk.src_gen = *src.gen;
       pk.src_ptr = src.buf->p;
@@ -526,15 +556,15 @@ struct run_ctx_t {
     }
     if (Cc == 1 && dst_base == 0) {  // rows are already K-major: elementwise scale + split
       long long const nn = (long long)B * R;
-      if (bf16) { B200_CARVEOUT_ONCE(b200::pack_rows_split_kernel<true>); b200::pack_rows_split_kernel<true><<<ceil_div(nn, 256), 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, dst_b_stride, nn, absmax_src); }
-      else { B200_CARVEOUT_ONCE(b200::pack_rows_split_kernel<false>); b200::pack_rows_split_kernel<false><<<ceil_div(nn, 256), 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, dst_b_stride, nn, absmax_src); }
+      if (bf16) { B200_CARVEOUT_ONCE(b200::pack_rows_split_kernel<true>); launch_k(b200::pack_rows_split_kernel<true>, dim3(ceil_div(nn, 256)), dim3(256), 0, fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, dst_b_stride, nn, absmax_src); }
+      else { B200_CARVEOUT_ONCE(b200::pack_rows_split_kernel<false>); launch_k(b200::pack_rows_split_kernel<false>, dim3(ceil_div(nn, 256)), dim3(256), 0, fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, dst_b_stride, nn, absmax_src); }
       launched();
       pk.src_gen = *src.gen;
       pk.src_ptr = src.buf->p;
       return;
     }
-    if (bf16) { B200_CARVEOUT_ONCE(b200::pack_xpose_split_kernel<true>); b200::pack_xpose_split_kernel<true><<<grid, 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, Cc, Rpad, dst_c_stride, dst_b_stride, c_inner, dst_chi_stride, dst_base, absmax_src); }
-    else { B200_CARVEOUT_ONCE(b200::pack_xpose_split_kernel<false>); b200::pack_xpose_split_kernel<false><<<grid, 256, 0, st>>>(fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, Cc, Rpad, dst_c_stride, dst_b_stride, c_inner, dst_chi_stride, dst_base, absmax_src); }
+    if (bf16) { B200_CARVEOUT_ONCE(b200::pack_xpose_split_kernel<true>); launch_k(b200::pack_xpose_split_kernel<true>, dim3(grid), dim3(256), 0, fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, Cc, Rpad, dst_c_stride, dst_b_stride, c_inner, dst_chi_stride, dst_base, absmax_src); }
+    else { B200_CARVEOUT_ONCE(b200::pack_xpose_split_kernel<false>); launch_k(b200::pack_xpose_split_kernel<false>, dim3(grid), dim3(256), 0, fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, Cc, Rpad, dst_c_stride, dst_b_stride, c_inner, dst_chi_stride, dst_base, absmax_src); }
     launched();
     pk.src_gen = *src.gen;
     pk.src_ptr = src.buf->p;
@@ -554,11 +584,12 @@ struct run_ctx_t {
     cfg.blockDim = dim3(b200::IGEMM_THREADS);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = prm.cm; attr[0].val.clusterDim.y = prm.cn; attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (prm.cm * prm.cn > 1) { attr[na].id = cudaLaunchAttributeClusterDimension; attr[na].val.clusterDim.x = prm.cm; attr[na].val.clusterDim.y = prm.cn; attr[na].val.clusterDim.z = 1; ++na; }
+    if (rtc.use_pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
     cfg.attrs = attr;
-    cfg.numAttrs = (prm.cm * prm.cn > 1) ? 1 : 0;
+    cfg.numAttrs = na;
     CU_CHK(cudaLaunchKernelEx(&cfg, b200::igemm_umma_kernel<BN, kPlanes>, ph, pl, qh, ql, prm));
     launched();
   }
@@ -576,11 +607,12 @@ struct run_ctx_t {
     cfg.blockDim = dim3(b200::IGEMM_THREADS);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = rtc.use_pdl ? 2 : 1;
     CU_CHK(cudaLaunchKernelEx(&cfg, b200::igemm_umma_2cta_kernel<BN, kPlanes>, ph, pl, qh, ql, prm));
     launched();
   }
@@ -599,6 +631,114 @@ struct run_ctx_t {
     }
   }
 
+  // ---- tap-reuse path (igemm3.cuh): returns false when the shape does not fit its shared-memory budget (caller falls back to im2col) ----
+  template <int BN, int kPlanes, bool k2>
+  void launch_taps_t(dim3 grid, size_t smem, CUtensorMap const &ah, CUtensorMap const &al, CUtensorMap const &wh, CUtensorMap const &wl, b200::TapsParams const &prm) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      CU_CHK(cudaFuncSetAttribute(b200::igemm_taps_kernel<BN, kPlanes, k2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_set = true;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(b200::IGEMM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (k2) { attr[na].id = cudaLaunchAttributeClusterDimension; attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1; ++na; }
+    if (rtc.use_pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    CU_CHK(cudaLaunchKernelEx(&cfg, b200::igemm_taps_kernel<BN, kPlanes, k2>, ah, al, wh, wl, prm));
+    launched();
+  }
+  template <int BN>
+  void launch_taps_bn(int planes, bool k2, dim3 grid, size_t smem, CUtensorMap const &ah, CUtensorMap const &al, CUtensorMap const &wh, CUtensorMap const &wl, b200::TapsParams const &prm) {
+    if (planes == 2) { if (k2) { launch_taps_t<BN, 2, true>(grid, smem, ah, al, wh, wl, prm); } else { launch_taps_t<BN, 2, false>(grid, smem, ah, al, wh, wl, prm); } }
+    else { if (k2) { launch_taps_t<BN, 1, true>(grid, smem, ah, al, wh, wl, prm); } else { launch_taps_t<BN, 1, false>(grid, smem, ah, al, wh, wl, prm); } }
+  }
+
+  struct taps_stage_t { int a_stages = 0, b_stages = 0; size_t smem = 0; };
+  taps_stage_t taps_staging(int halo_rows, int planes, int bq) {
+    taps_stage_t r;
+    long long const avail = 224 * 1024 - 1024 - b200::TAPS_BAR_BYTES, a_stage = (long long)planes * halo_rows * 128, b_stage = (long long)planes * bq * 128;
+    for (int as : {3, 2, 1}) {
+      if (as > rtc.taps_max_a_stages) { continue; }
+      long long const bs = std::min<long long>(std::min<long long>((avail - as * a_stage) / b_stage, b200::TAPS_MAX_B_STAGES), rtc.taps_max_b_stages);
+      if (bs >= (as == 3 ? 4 : 3)) { r.a_stages = as; r.b_stages = (int)bs; r.smem = (size_t)(as * a_stage + bs * b_stage + 1024 + b200::TAPS_BAR_BYTES); return r; }
+    }
+    return r;
+  }
+
+  bool run_conv_taps(var_info_t &vin, var_info_t &vf, var_info_t &vout, float const *bias, bool bf16, int planes) {
+    conv_plan_t const &cp = f.cp;
+    int const Hp = cp.tHp, Wp = cp.tWp, taps = cp.KH * cp.KW, BN = cp.BN;
+    int halo_rows = (int)round_up(128 + (long long)(cp.KH - 1) * Wp + cp.KW - 1, 8);
+    int const a_loads = ceil_div(halo_rows, 256), a_box_rows = (int)round_up(ceil_div(halo_rows, a_loads), 8);
+    halo_rows = a_loads * a_box_rows;
+    long long const m_rows = (long long)(cp.N - 1) * Hp * Wp + (long long)(cp.OH - 1) * Wp + cp.OW;
+    int const p_tiles = ceil_div(m_rows, b200::IGEMM_BM), q_tiles = ceil_div(cp.OC, BN);
+    // single CTAs or CTA pairs: waves x max(MMA cycles, operand bytes / sustained L2->SM rate) per 64-channel block
+    taps_stage_t const st1 = taps_staging(halo_rows, planes, BN), st2 = (BN >= 32) ? taps_staging(halo_rows, planes, BN / 2) : taps_stage_t();
+    double const mma = (planes == 2 ? 3.0 : 1.0) * taps * 2.0 * BN;
+    double const cost1 = st1.a_stages ? std::ceil((double)p_tiles * q_tiles / im.num_sms) * std::max(mma, planes * 128.0 * (halo_rows + (double)taps * BN) / 36.0) : 1e30;
+    double const cost2 = (st2.a_stages && p_tiles >= 2) ? std::ceil((double)ceil_div(p_tiles, 2) * q_tiles / (im.num_sms / 2)) * std::max(mma, planes * 128.0 * (halo_rows + (double)taps * BN / 2) / 36.0) : 1e30;
+    bool k2 = cost2 < cost1;
+    if (rtc.taps_2cta == 0 && st1.a_stages) { k2 = false; }
+    if (rtc.taps_2cta == 1 && st2.a_stages && p_tiles >= 2) { k2 = true; }
+    taps_stage_t const stg = k2 ? st2 : st1;
+    if (!stg.a_stages) { return false; }
+
+    // filters: OIHW -> [OC][tap][chan] K-major rows, once per weight version; activations: NCHW -> shared-padding NHWC (see igemm3.cuh)
+    pack(f.w_pack, vf, cp.OC, cp.C, taps, cp.Cpad, cp.w_tap_stride, cp.w_row_stride, (long long)cp.OC * cp.w_row_stride, planes == 2, bf16);
+    long long const img_elems = (long long)Hp * Wp * cp.Cpad;
+    pack(f.a_pack, vin, cp.N, cp.C, cp.H * cp.W, cp.Cpad, cp.Cpad, img_elems, (long long)cp.N * img_elems, planes == 2, bf16, cp.W, (long long)Wp * cp.Cpad,
+         ((long long)cp.py * Wp + cp.px) * cp.Cpad, absmax_cell("in"));
+    CUtensorMap const a_hi = make_tiled_map(f.a_pack.hi->p, bf16, cp.Cpad, (uint64_t)cp.N * Hp * Wp, cp.Cpad, a_box_rows);
+    CUtensorMap const a_lo = planes == 2 ? make_tiled_map(f.a_pack.lo->p, bf16, cp.Cpad, (uint64_t)cp.N * Hp * Wp, cp.Cpad, a_box_rows) : a_hi;
+    uint32_t const w_box = k2 ? BN / 2 : BN;
+    CUtensorMap const w_hi = make_tiled_map(f.w_pack.hi->p, bf16, cp.w_row_stride, cp.OC, cp.w_row_stride, w_box);
+    CUtensorMap const w_lo = planes == 2 ? make_tiled_map(f.w_pack.lo->p, bf16, cp.w_row_stride, cp.OC, cp.w_row_stride, w_box) : w_hi;
+
+    b200::TapsParams prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.m_rows = (int)m_rows; prm.q_rows = cp.OC;
+    prm.cblks = cp.cblks; prm.taps = taps; prm.kw = cp.KW;
+    prm.ksteps_last = cp.ksteps_last;
+    prm.Wp = Wp; prm.HpWp = Hp * Wp; prm.OH = cp.OH; prm.OW = cp.OW;
+    prm.halo_rows = halo_rows; prm.a_loads = a_loads; prm.a_box_rows = a_box_rows;
+    prm.a_stages = stg.a_stages; prm.b_stages = stg.b_stages;
+    prm.chunk_kblks = std::max(1, planes == 2 ? rtc.acc_chunk_kblks : rtc.acc_chunk_kblks_16);
+    prm.out_chans = cp.OC; prm.out_hw = cp.OH * cp.OW;
+    prm.relu = cp.relu; prm.has_bias = bias ? 1 : 0; prm.bias = bias;
+    prm.out = fptr(vout);
+    prm.p_scale = static_cast<float *>(f.a_pack.scale2->p);
+    prm.q_scale = static_cast<float *>(f.w_pack.scale2->p);
+    prm.out_absmax = absmax_cell("out");
+    prm.idesc = b200::make_idesc_f16(bf16 ? 1u : 0u, k2 ? 256 : 128, BN);
+    prm.debug = rtc.debug_flags & 11;
+    long long *ts_dev = nullptr;
+    if (rtc.debug_flags & 4) { CU_CHK(cudaMalloc(&ts_dev, 16 * sizeof(long long))); CU_CHK(cudaMemsetAsync(ts_dev, 0, 16 * sizeof(long long), st)); prm.ts = ts_dev; }
+    dim3 const grid((unsigned)round_up(p_tiles, k2 ? 2 : 1), (unsigned)q_tiles, 1);
+    mark_kernel_begin();
+    if (BN == 128) { launch_taps_bn<128>(planes, k2, grid, stg.smem, a_hi, a_lo, w_hi, w_lo, prm); }
+    else if (BN == 64) { launch_taps_bn<64>(planes, k2, grid, stg.smem, a_hi, a_lo, w_hi, w_lo, prm); }
+    else { launch_taps_bn<32>(planes, k2, grid, stg.smem, a_hi, a_lo, w_hi, w_lo, prm); }
+    mark_kernel_end();
+    if (ts_dev) {  // experiments: phase stamps of CTA (0,0) in SM cycles relative to kernel entry
+      long long ts[16];
+      CU_CHK(cudaStreamSynchronize(st));
+      CU_CHK(cudaMemcpy(ts, ts_dev, sizeof(ts), cudaMemcpyDeviceToHost));
+      cudaFree(ts_dev);
+      fprintf(stderr, "taps stamps (cycles from entry): setup %lld  first_b_full %lld  mma_issue_done %lld  epi_first_chunk %lld  epi_last_chunk %lld  epi_drained %lld  stores_done %lld  end %lld  [steps %d a_stages %d b_stages %d k2 %d]\n",
+              ts[1] - ts[0], ts[2] - ts[0], ts[3] - ts[0], ts[4] - ts[0], ts[5] - ts[0], ts[6] - ts[0], ts[7] - ts[0], ts[8] - ts[0], prm.cblks * prm.taps, prm.a_stages, prm.b_stages, (int)k2);
+    }
+    im.bump(vout);
+    return true;
+  }
+
   void run_conv() {
     conv_plan_t const &cp = f.cp;
     var_info_t &vin = var("in"), &vf = var("filts"), &vout = var("out");
@@ -609,6 +749,7 @@ struct run_ctx_t {
     if (has_arg("biases")) { var_info_t &vb = var("biases"); if ((int)vb.dims.dims_prod() != cp.OC) { rt_err("conv: biases size mismatch"); } bias = fptr(vb); }
     bool const bf16 = (rtc.prec == B200_PREC_BF16);
     int const planes = (rtc.prec == B200_PREC_FP32_SPLIT) ? 2 : 1;
+    if (cp.taps && rtc.use_taps && run_conv_taps(vin, vf, vout, bias, bf16, planes)) { return; }
     // filters: OIHW -> [OC][tap][chan] K-major rows (once per weight version; the reference's xpose_filts, src/rtc_fwd.cc:310-313)
     // activations: NCHW -> NHWC (chan padded to a multiple of 8; row-merged path: chan padded to 4|8 and image rows at pitch Wp with x padding)
     if (cp.rowmerge) {
@@ -647,7 +788,7 @@ struct run_ctx_t {
     prm.q_rows = cp.swapped ? (int)pixels : cp.OC;
     prm.kblks_total = cp.kblks_total;
     prm.kblks_per_split = cp.kblks_per_split;
-    prm.chunk_kblks = std::max(1, rtc.acc_chunk_kblks);
+    prm.chunk_kblks = std::max(1, planes == 2 ? rtc.acc_chunk_kblks : rtc.acc_chunk_kblks_16);
     prm.p_im2col = cp.im2col ? 1 : 0;
     prm.cblks = std::max(cp.cblks, 1); prm.kw = cp.KW; prm.ow = cp.OW; prm.ohw = cp.OH * cp.OW;
     prm.sx = cp.sx; prm.sy = cp.sy; prm.px = cp.px; prm.py = cp.py;
@@ -659,6 +800,7 @@ struct run_ctx_t {
     prm.q_scale = static_cast<float *>((cp.swapped ? f.a_pack : f.w_pack).scale2->p);
     prm.idesc = b200::make_idesc_f16(bf16 ? 1u : 0u, 128, cp.BN);
     prm.cm = cl.cm; prm.cn = cl.cn;
+    prm.kb_mod = cp.kb_mod; prm.ksteps_last = cp.ksteps_last;
     prm.debug = rtc.debug_flags;
     prm.out_absmax = absmax_cell("out");
     long long const out_elems = (long long)cp.N * cp.OC * cp.OH * cp.OW;
@@ -678,7 +820,7 @@ struct run_ctx_t {
     else { launch_igemm(cp.BN, planes, grid, act_hi, act_lo, w_hi, w_lo, prm); }
     mark_kernel_end();
     if (cp.splits > 1) {
-      B200_CARVEOUT_ONCE(b200::splitk_reduce_kernel); b200::splitk_reduce_kernel<<<ceil_div(out_elems, 256), 256, 0, st>>>(static_cast<float *>(f.splitk_ws->p), fptr(vout), bias, out_elems, cp.splits, cp.OC, cp.OH * cp.OW, cp.relu, prm.out_absmax);
+      B200_CARVEOUT_ONCE(b200::splitk_reduce_kernel); launch_k(b200::splitk_reduce_kernel, dim3(ceil_div(out_elems, 256)), dim3(256), 0, static_cast<float *>(f.splitk_ws->p), fptr(vout), bias, out_elems, cp.splits, cp.OC, cp.OH * cp.OW, cp.relu, prm.out_absmax);
       launched();
     }
     im.bump(vout);
@@ -709,7 +851,7 @@ struct run_ctx_t {
     memset(&prm, 0, sizeof(prm));
     prm.p_rows = M; prm.q_rows = N;
     prm.kblks_total = prm.kblks_per_split = (int)(Kpad / 64);
-    prm.chunk_kblks = std::max(1, rtc.acc_chunk_kblks);
+    prm.chunk_kblks = std::max(1, planes == 2 ? rtc.acc_chunk_kblks : rtc.acc_chunk_kblks_16);
     prm.cblks = 1; prm.kw = 1; prm.ow = 1; prm.ohw = 1; prm.sx = prm.sy = 1;
     prm.out_chans = N; prm.out_hw = 1;
     prm.out = fptr(vc);
@@ -717,6 +859,7 @@ struct run_ctx_t {
     prm.q_scale = static_cast<float *>(f.w_pack.scale2->p);
     prm.idesc = b200::make_idesc_f16(bf16 ? 1u : 0u, 128, BN);
     prm.cm = cl.cm; prm.cn = cl.cn;
+    prm.kb_mod = (int)(Kpad / 64); prm.ksteps_last = ceil_div(K - (Kpad / 64 - 1) * 64, 16);
     prm.debug = rtc.debug_flags;
     dim3 grid((unsigned)round_up(p_tiles, two_cta ? 2 : cl.cm), (unsigned)round_up(q_tiles, cl.cn), 1);
     mark_kernel_begin();
@@ -751,7 +894,7 @@ struct run_ctx_t {
 #define B200_POOL_PLANE(K_, S_) do { \
         static bool attr_ = false; \
         if (!attr_) { CU_CHK(cudaFuncSetAttribute(b200::pool_plane_kernel<K_, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); prefer_max_smem(b200::pool_plane_kernel<K_, S_>); attr_ = true; } \
-        b200::pool_plane_kernel<K_, S_><<<(unsigned)planes, 256, smem, st>>>(fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, cell); } while (0)
+        launch_k(b200::pool_plane_kernel<K_, S_>, dim3((unsigned)planes), dim3(256), smem, fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, cell); } while (0)
       if (KH == 3 && sy == 2) { B200_POOL_PLANE(3, 2); } else if (KH == 3) { B200_POOL_PLANE(3, 1); } else { B200_POOL_PLANE(2, 2); }
 #undef B200_POOL_PLANE
       launched();
@@ -761,14 +904,14 @@ struct run_ctx_t {
     if (KH == KW && sy == sx && ((KH == 3 && sy == 2) || (KH == 3 && sy == 1) || (KH == 2 && sy == 2)) && planes <= 65535) {
       dim3 const grid(ceil_div((long long)OH * OW, 256), (unsigned)planes, 1);
       unsigned int *cell = absmax_cell("out");
-      if (KH == 3 && sy == 2) { B200_CARVEOUT_ONCE(b200::pool_kernel_fixed<3, 2>); b200::pool_kernel_fixed<3, 2><<<grid, 256, 0, st>>>(fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, cell); }
-      else if (KH == 3) { B200_CARVEOUT_ONCE(b200::pool_kernel_fixed<3, 1>); b200::pool_kernel_fixed<3, 1><<<grid, 256, 0, st>>>(fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, cell); }
-      else { B200_CARVEOUT_ONCE(b200::pool_kernel_fixed<2, 2>); b200::pool_kernel_fixed<2, 2><<<grid, 256, 0, st>>>(fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, cell); }
+      if (KH == 3 && sy == 2) { B200_CARVEOUT_ONCE(b200::pool_kernel_fixed<3, 2>); launch_k(b200::pool_kernel_fixed<3, 2>, dim3(grid), dim3(256), 0, fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, cell); }
+      else if (KH == 3) { B200_CARVEOUT_ONCE(b200::pool_kernel_fixed<3, 1>); launch_k(b200::pool_kernel_fixed<3, 1>, dim3(grid), dim3(256), 0, fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, cell); }
+      else { B200_CARVEOUT_ONCE(b200::pool_kernel_fixed<2, 2>); launch_k(b200::pool_kernel_fixed<2, 2>, dim3(grid), dim3(256), 0, fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, cell); }
       launched();
       im.bump(vout);
       return;
     }
-    B200_CARVEOUT_ONCE(b200::pool_kernel); b200::pool_kernel<<<ceil_div(n_out, 256), 256, 0, st>>>(fptr(vin), fptr(vout), n_out, H, W, OH, OW, KH, KW, sy, sx, py, px, (int)scalar("avg_pool", true, 0), absmax_cell("out"));
+    B200_CARVEOUT_ONCE(b200::pool_kernel); launch_k(b200::pool_kernel, dim3(ceil_div(n_out, 256)), dim3(256), 0, fptr(vin), fptr(vout), n_out, H, W, OH, OW, KH, KW, sy, sx, py, px, (int)scalar("avg_pool", true, 0), absmax_cell("out"));
     launched();
     im.bump(vout);
   }
@@ -785,9 +928,9 @@ struct run_ctx_t {
     int const blocks = ceil_div(n_pels, 128);
     constexpr int kChunk = 16;
     dim3 const grid(blocks, ceil_div(C, kChunk));
-    if (ls == 5) { B200_CARVEOUT_ONCE(b200::lrn_kernel<5, kChunk>); b200::lrn_kernel<5, kChunk><<<grid, 128, 0, st>>>(fptr(vin), fptr(vout), n_pels, C, HW, alpha, beta, k, absmax_cell("out")); }
-    else if (ls == 3) { B200_CARVEOUT_ONCE(b200::lrn_kernel<3, kChunk>); b200::lrn_kernel<3, kChunk><<<grid, 128, 0, st>>>(fptr(vin), fptr(vout), n_pels, C, HW, alpha, beta, k, absmax_cell("out")); }
-    else if (ls <= 32) { B200_CARVEOUT_ONCE(b200::lrn_kernel_generic); b200::lrn_kernel_generic<<<blocks, 128, 0, st>>>(fptr(vin), fptr(vout), n_pels, C, HW, ls, alpha, beta, k, absmax_cell("out")); }
+    if (ls == 5) { B200_CARVEOUT_ONCE(b200::lrn_kernel<5, kChunk>); launch_k(b200::lrn_kernel<5, kChunk>, dim3(grid), dim3(128), 0, fptr(vin), fptr(vout), n_pels, C, HW, alpha, beta, k, absmax_cell("out")); }
+    else if (ls == 3) { B200_CARVEOUT_ONCE(b200::lrn_kernel<3, kChunk>); launch_k(b200::lrn_kernel<3, kChunk>, dim3(grid), dim3(128), 0, fptr(vin), fptr(vout), n_pels, C, HW, alpha, beta, k, absmax_cell("out")); }
+    else if (ls <= 32) { B200_CARVEOUT_ONCE(b200::lrn_kernel_generic); launch_k(b200::lrn_kernel_generic, dim3(blocks), dim3(128), 0, fptr(vin), fptr(vout), n_pels, C, HW, ls, alpha, beta, k, absmax_cell("out")); }
     else { unsup_err("lrn: local_size > 32"); }
     launched();
     im.bump(vout);
@@ -796,7 +939,7 @@ struct run_ctx_t {
   void run_relu() {
     var_info_t &v = var("inout");
     long long const n = v.dims.dims_prod();
-    B200_CARVEOUT_ONCE(b200::relu_kernel); b200::relu_kernel<<<ceil_div(ceil_div(n, 4), 256), 256, 0, st>>>(fptr(v), n);
+    B200_CARVEOUT_ONCE(b200::relu_kernel); launch_k(b200::relu_kernel, dim3(ceil_div(ceil_div(n, 4), 256)), dim3(256), 0, fptr(v), n);
     launched();
     im.bump(v);
   }
@@ -807,7 +950,7 @@ struct run_ctx_t {
     if (!(vin.dims == vout.dims)) { rt_err("softmax: in/prob dims differ"); }
     int const C = vin.dims.dsz("chan"), HW = vin.dims.dsz("y") * vin.dims.dsz("x");
     long long const n_pels = (long long)vin.dims.dsz("img") * HW;
-    B200_CARVEOUT_ONCE(b200::softmax_kernel); b200::softmax_kernel<<<ceil_div(n_pels * 32, 256), 256, 0, st>>>(fptr(vin), fptr(vout), n_pels, C, HW);
+    B200_CARVEOUT_ONCE(b200::softmax_kernel); launch_k(b200::softmax_kernel, dim3(ceil_div(n_pels * 32, 256)), dim3(256), 0, fptr(vin), fptr(vout), n_pels, C, HW);
     launched();
     im.bump(vout);
   }
@@ -821,7 +964,7 @@ struct run_ctx_t {
     long long const per_img = (long long)C * HW, out_img_stride = (long long)OC * HW, out_off = (long long)ocix * HW;
     int const vec4 = ((per_img % 4) == 0 && (out_img_stride % 4) == 0 && (out_off % 4) == 0) ? 1 : 0;
     long long const work = vec4 ? per_img * n_img / 4 : per_img * n_img;
-    B200_CARVEOUT_ONCE(b200::concat_copy_kernel); b200::concat_copy_kernel<<<ceil_div(work, 256), 256, 0, st>>>(fptr(vin), fptr(vout), per_img, out_img_stride, out_off, n_img, vec4, absmax_cell("out"));
+    B200_CARVEOUT_ONCE(b200::concat_copy_kernel); launch_k(b200::concat_copy_kernel, dim3(ceil_div(work, 256)), dim3(256), 0, fptr(vin), fptr(vout), per_img, out_img_stride, out_off, n_img, vec4, absmax_cell("out"));
     launched();
     im.bump(vout);
   }
@@ -838,7 +981,7 @@ struct run_ctx_t {
       a.ins[i] = fptr(vi);
     }
     long long const n = vout.dims.dims_prod();
-    B200_CARVEOUT_ONCE(b200::reduce_sum_kernel); b200::reduce_sum_kernel<<<ceil_div(n, 256), 256, 0, st>>>(a, fptr(vout), n);
+    B200_CARVEOUT_ONCE(b200::reduce_sum_kernel); launch_k(b200::reduce_sum_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, a, fptr(vout), n);
     launched();
     im.bump(vout);
   }
@@ -857,7 +1000,7 @@ struct run_ctx_t {
     else if (fn == "gen_data_sgemm_a") { kind = 2; inner = v.dims.dsz("M"); inner2 = v.dims.dsz("K"); salt = 12738732u; }
     else if (fn == "gen_data_sgemm_b") { kind = 3; inner = v.dims.dsz("N"); inner2 = v.dims.dsz("K"); salt = 12738732u; }
     else { unsup_err("be=b200: unknown generator '" + fn + "'"); }
-    B200_CARVEOUT_ONCE(b200::gen_data_kernel); b200::gen_data_kernel<<<ceil_div(n, 256), 256, 0, st>>>(fptr(v), (uint32_t)n, kind, inner, inner2, mode, vi, salt);
+    B200_CARVEOUT_ONCE(b200::gen_data_kernel); launch_k(b200::gen_data_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, fptr(v), (uint32_t)n, kind, inner, inner2, mode, vi, salt);
     launched();
     im.bump(v);
   }

@@ -234,6 +234,10 @@ void b200_conv_fwd_t::init(p_conv_pipe_t const &cp_, string const &opts) {
         if (k == "prec") { rtc->prec = (v == "fp32") ? B200_PREC_FP32_SPLIT : (v == "fp16") ? B200_PREC_FP16 : (v == "bf16") ? B200_PREC_BF16 : (rt_err("unknown prec '" + v + "'"), B200_PREC_FP32_SPLIT); }
         else if (k == "use_graph") { use_graph = (uint32_t)std::stoul(v); }
         else if (k == "acc_chunk_kblks") { rtc->acc_chunk_kblks = std::stoi(v); }
+        else if (k == "acc_chunk_kblks_16") { rtc->acc_chunk_kblks_16 = std::stoi(v); }
+        else if (k == "use_taps") { rtc->use_taps = std::stoi(v); }
+    else if (k == "use_pdl") { rtc->use_pdl = std::stoi(v); }
+        else if (k == "taps_2cta") { rtc->taps_2cta = std::stoi(v); }
         else if (k == "use_clusters") { rtc->use_clusters = std::stoi(v); }
         else if (k == "use_2cta") { rtc->use_2cta = std::stoi(v); }
         else if (k == "device") { rtc->device = std::stoi(v); }

@@ -58,6 +58,9 @@ struct IgemmParams {
   int cm, cn;  // CTA-cluster shape: cm CTAs along P-tiles share (multicast) each Q tile, cn CTAs along Q-tiles share each P tile
   unsigned int *out_absmax;  // optional: publish max|out| (bit pattern) for the consumer's operand scaling
   uint32_t idesc;
+  // K tail: k-blocks come in groups of kb_mod (the channel blocks of one filter tap; the whole K for 2-d operands); the last k-block of a
+  // group holds only ksteps_last (1..4) 16-wide k-steps of real data -- the rest is zero padding in both operands and is not multiplied
+  int kb_mod, ksteps_last;
 };
 
 template <int BN, int kPlanes>
@@ -79,8 +82,24 @@ struct IgemmCfg {
 // guard; addresses advance by a constant stride.
 template <int BN>
 __device__ __forceinline__ float igemm_store_row(float const (&acc)[BN], float inv, float const *bias_s, float floor_v, float *o, long long stride, int nvalid) {
-  float amax = 0.0f;
   uint32_t const bias_sa = smem_u32(bias_s);
+  if (nvalid >= BN) {
+    // full tile (the common case): straight-line code -- bias read as 128-bit LDS with immediate offsets, four independent max chains, no
+    // per-element branch (the guarded loop below serialises one LDS latency per element: measured 65 cycles/element, 8.4k cycles per tile)
+    float am0 = 0.0f, am1 = 0.0f, am2 = 0.0f, am3 = 0.0f;
+#pragma unroll
+    for (int j = 0; j < BN; j += 4) {
+      float b0, b1, b2, b3;
+      asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3) : "r"(bias_sa + 4 * j));
+      float const v0 = fmaxf(fmaf(acc[j], inv, b0), floor_v), v1 = fmaxf(fmaf(acc[j + 1], inv, b1), floor_v);
+      float const v2 = fmaxf(fmaf(acc[j + 2], inv, b2), floor_v), v3 = fmaxf(fmaf(acc[j + 3], inv, b3), floor_v);
+      o[0] = v0; o[stride] = v1; o[2 * stride] = v2; o[3 * stride] = v3;
+      o += 4 * stride;
+      am0 = fmaxf(am0, fabsf(v0)); am1 = fmaxf(am1, fabsf(v1)); am2 = fmaxf(am2, fabsf(v2)); am3 = fmaxf(am3, fabsf(v3));
+    }
+    return fmaxf(fmaxf(am0, am1), fmaxf(am2, am3));
+  }
+  float amax = 0.0f;
 #pragma unroll
   for (int j = 0; j < BN; ++j) {
     if (j < nvalid) {
@@ -115,6 +134,7 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
   float *bias_s = reinterpret_cast<float *>(bar_mem + 512);  // BN floats (the barrier block is 1 KB)
 
   int const warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();  // the next kernel of the forward pass may start launching; it waits for this grid before touching memory
   int const m0 = blockIdx.x * IGEMM_BM;
   int const n0 = blockIdx.y * BN;
   int const split = blockIdx.z;
@@ -138,6 +158,7 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
   bool const clustered = (prm.cm * prm.cn) > 1;
   if (clustered) { cluster_sync_all(); } else { __syncthreads(); }  // peers' barriers must exist before anyone multicasts into them
   tc_fence_after();
+  pdl_wait();  // everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped the previous kernel's tail
   uint32_t const tmem_base = *tmem_ptr_smem;
   // position inside the cluster and the multicast groups: CTAs with the same cx (same P tile) share P, same cy (same Q tile) share Q
   uint32_t const cx = clustered ? cluster_ctaid_x() : 0u, cy = clustered ? cluster_ctaid_y() : 0u;
@@ -148,8 +169,10 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
   int const q_rows_mine = BN / prm.cm, q_row0 = cx * q_rows_mine;
 
   if (warp_id == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp walks the loop with warp-uniform state; one elected lane issues) ==========
+    // (with `if (lane == 0)` around the loop the compiler cannot prove the operands of UTMALDG / UTCHMMA -- uniform-register instructions --
+    // uniform and wraps each one in an ELECT / R2UR.BROADCAST retry loop: ~100 SASS instructions per k-block on one thread)
+    {
       int img = 0, h_base = 0, w_base = 0;
       int const pm0 = m0 + p_row0;  // first P row (output pixel) of this CTA's slice
       if (prm.p_im2col) {
@@ -160,18 +183,20 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
         w_base = ox * prm.sx - prm.px;
       }
       bool const mc_p = prm.cn > 1, mc_q = prm.cm > 1;
+      // (tap, channel block) of the current k-block, advanced incrementally: a runtime integer division costs a single thread ~150 cycles
+      int cb = 0, kx = 0, ky = 0;
+      if (prm.p_im2col) { int const tap0 = kb_begin / prm.cblks; cb = kb_begin - tap0 * prm.cblks; ky = tap0 / prm.kw; kx = tap0 - ky * prm.kw; }
       for (int i = 0; i < ((prm.debug & 1) ? 0 : nkb); ++i) {
         int const kb = kb_begin + i;
         int const s = i % kStages;
         uint32_t const ph = (i / kStages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
+        if (elect_one_sync()) {
         mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);  // the whole stage: own slices + the slices the group's other CTAs multicast in
         uint8_t *st = smem + s * Cfg::kStageBytes;
         uint8_t *p_hi = st + p_row0 * 128, *p_lo = p_hi + kPBytes;
         uint8_t *q_hi = st + kPlanes * kPBytes + q_row0 * 128, *q_lo = q_hi + kQBytes;
         if (prm.p_im2col) {
-          int const tap = kb / prm.cblks, cb = kb - tap * prm.cblks;
-          int const ky = tap / prm.kw, kx = tap - ky * prm.kw;
           if (mc_p) {
             tma_load_im2col_4d_mc(p_hi, &p_hi_map, &full_bar[s], cb * IGEMM_BK, w_base, h_base, img, (uint16_t)kx, (uint16_t)ky, mask_p);
             if (kPlanes == 2) { tma_load_im2col_4d_mc(p_lo, &p_lo_map, &full_bar[s], cb * IGEMM_BK, w_base, h_base, img, (uint16_t)kx, (uint16_t)ky, mask_p); }
@@ -193,12 +218,17 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
           tma_load_2d(q_hi, &q_hi_map, &full_bar[s], kb * IGEMM_BK, n0);
           if (kPlanes == 2) { tma_load_2d(q_lo, &q_lo_map, &full_bar[s], kb * IGEMM_BK, n0); }
         }
+        }
+        __syncwarp();
+        if (++cb == prm.cblks) { cb = 0; if (++kx == prm.kw) { kx = 0; ++ky; } }
       }
     }
   } else if (warp_id == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp, one elected lane issues) =====================
+    {
       uint32_t const idesc = prm.idesc;
+      int const kb_mod = prm.kb_mod, ksteps_last = prm.ksteps_last;
+      int kb_in_grp = kb_begin % kb_mod;  // once per CTA
       int i = 0;
       for (int c = 0; c < nchunks; ++c) {
         int const buf = c & 1;
@@ -217,20 +247,28 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
           uint64_t const p_hi = make_kmajor_sw128_desc(st), p_lo = make_kmajor_sw128_desc(st + kPBytes);
           uint64_t const q_hi = make_kmajor_sw128_desc(st + kPlanes * kPBytes);
           uint64_t const q_lo = make_kmajor_sw128_desc(st + kPlanes * kPBytes + kQBytes);
+          int nk = IGEMM_BK / IGEMM_UMMA_K;
+          if (++kb_in_grp == kb_mod) { kb_in_grp = 0; nk = ksteps_last; }
+          if (prm.debug & 2) { nk = 0; }
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < ((prm.debug & 2) ? 0 : IGEMM_BK / IGEMM_UMMA_K); ++k) {
-            uint64_t const adv = static_cast<uint64_t>((k * IGEMM_UMMA_K * 2) >> 4);  // +32 B per k-step inside the swizzle row
-            umma_f16(tmem_d, p_hi + adv, q_hi + adv, idesc, first ? 0u : 1u);
-            first = false;
-            if (kPlanes == 2) {
-              umma_f16(tmem_x, p_hi + adv, q_lo + adv, idesc, (i == 0 && k == 0) ? 0u : 1u);
-              umma_f16(tmem_x, p_lo + adv, q_hi + adv, idesc, 1u);
+            for (int k = 0; k < IGEMM_BK / IGEMM_UMMA_K; ++k) {
+              if (k < nk) {
+                uint64_t const adv = static_cast<uint64_t>((k * IGEMM_UMMA_K * 2) >> 4);  // +32 B per k-step inside the swizzle row
+                umma_f16(tmem_d, p_hi + adv, q_hi + adv, idesc, (first && k == 0) ? 0u : 1u);
+                if (kPlanes == 2) {
+                  umma_f16(tmem_x, p_hi + adv, q_lo + adv, idesc, (i == 0 && k == 0) ? 0u : 1u);
+                  umma_f16(tmem_x, p_lo + adv, q_hi + adv, idesc, 1u);
+                }
+              }
             }
+            // frees this smem stage -- in every CTA that multicast a slice into it -- once the MMAs above have read it
+            if (clustered) { umma_commit_mc(&empty_bar[s], static_cast<uint16_t>(mask_p | mask_q)); } else { umma_commit(&empty_bar[s]); }
+            if (i == i_end - 1) { umma_commit(&tmem_full_bar[buf]); }  // accumulator chunk complete
           }
-          // frees this smem stage -- in every CTA that multicast a slice into it -- once the MMAs above have read it
-          if (clustered) { umma_commit_mc(&empty_bar[s], static_cast<uint16_t>(mask_p | mask_q)); } else { umma_commit(&empty_bar[s]); }
+          __syncwarp();
+          first = false;
         }
-        umma_commit(&tmem_full_bar[buf]);  // accumulator chunk complete
       }
     }
   } else {
@@ -316,6 +354,7 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
 // split-K fix-up: out[i] = relu( sum_s ws[s][i] + bias[chan(i)] )   (deterministic order)
 __global__ void splitk_reduce_kernel(float const *__restrict__ ws, float *__restrict__ out, float const *__restrict__ bias,
                                      long long n, int splits, int out_chans, int out_hw, int relu, unsigned int *out_absmax) {
+  pdl_prologue();
   long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   float v = 0.0f;
   if (i < n) {

@@ -47,6 +47,7 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
   float *bias_s = reinterpret_cast<float *>(bar_mem + 512);
 
   int const warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   uint32_t const cta_rank = cluster_ctarank();  // 0 = leader, 1 = peer (cluster dims are (2,1,1))
   bool const leader = (cta_rank == 0);
   int const m0 = blockIdx.x * IGEMM_BM;         // this CTA's own 128 P rows (the pair covers 256 consecutive ones)
@@ -67,11 +68,12 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
+  pdl_wait();
   uint32_t const tmem_base = *tmem_ptr_smem;
 
   if (warp_id == 0) {
-    // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    // ===================== TMA producer (both CTAs; whole warp walks the loop, one elected lane issues -- see igemm.cuh) ==========
+    {
       int img = 0, h_base = 0, w_base = 0;
       if (prm.p_im2col) {
         img = m0 / prm.ohw;
@@ -81,18 +83,18 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
         w_base = ox * prm.sx - prm.px;
       }
       int const q_row0 = n0 + static_cast<int>(cta_rank) * Cfg::kQRows;  // this CTA's half of the Q tile
+      int cb = 0, kx = 0, ky = 0;  // (tap, channel block) of k-block i, advanced without integer divisions (single-thread loop)
       for (int i = 0; i < nkb; ++i) {
         int const s = i % kStages;
         uint32_t const ph = (i / kStages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
+        if (elect_one_sync()) {
         if (leader) { mbar_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes); }  // both CTAs' bytes land on the leader's barrier
         else { mbar_arrive_remote(&full_bar[s], 0); }
         uint8_t *st = smem + s * Cfg::kStageBytes;
         uint8_t *p_hi = st, *p_lo = st + kPBytes;
         uint8_t *q_hi = st + kPlanes * kPBytes, *q_lo = q_hi + kQBytes;
         if (prm.p_im2col) {
-          int const tap = i / prm.cblks, cb = i - tap * prm.cblks;
-          int const ky = tap / prm.kw, kx = tap - ky * prm.kw;
           tma_load_im2col_4d_2sm(p_hi, &p_hi_map, &full_bar[s], cb * IGEMM_BK, w_base, h_base, img, (uint16_t)kx, (uint16_t)ky);
           if (kPlanes == 2) { tma_load_im2col_4d_2sm(p_lo, &p_lo_map, &full_bar[s], cb * IGEMM_BK, w_base, h_base, img, (uint16_t)kx, (uint16_t)ky); }
         } else {
@@ -101,12 +103,17 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
         }
         tma_load_2d_2sm(q_hi, &q_hi_map, &full_bar[s], i * IGEMM_BK, q_row0);
         if (kPlanes == 2) { tma_load_2d_2sm(q_lo, &q_lo_map, &full_bar[s], i * IGEMM_BK, q_row0); }
+        }
+        __syncwarp();
+        if (++cb == prm.cblks) { cb = 0; if (++kx == prm.kw) { kx = 0; ++ky; } }
       }
     }
   } else if (warp_id == 1) {
     // ===================== MMA issuer (leader CTA only, one thread for the pair) =====================
-    if (leader && lane == 0) {
+    if (leader) {
       uint32_t const idesc = prm.idesc;  // M = 256 (the pair), N = BN
+      int const kb_mod = prm.kb_mod, ksteps_last = prm.ksteps_last;
+      int kb_in_grp = 0;
       int i = 0;
       for (int c = 0; c < nchunks; ++c) {
         int const buf = c & 1;
@@ -125,19 +132,26 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
           uint64_t const p_hi = make_kmajor_sw128_desc(st), p_lo = make_kmajor_sw128_desc(st + kPBytes);
           uint64_t const q_hi = make_kmajor_sw128_desc(st + kPlanes * kPBytes);
           uint64_t const q_lo = make_kmajor_sw128_desc(st + kPlanes * kPBytes + kQBytes);
+          int nk = IGEMM_BK / IGEMM_UMMA_K;
+          if (++kb_in_grp == kb_mod) { kb_in_grp = 0; nk = ksteps_last; }
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < IGEMM_BK / IGEMM_UMMA_K; ++k) {
-            uint64_t const adv = static_cast<uint64_t>((k * IGEMM_UMMA_K * 2) >> 4);
-            umma_f16_2sm(tmem_d, p_hi + adv, q_hi + adv, idesc, first ? 0u : 1u);
-            first = false;
-            if (kPlanes == 2) {
-              umma_f16_2sm(tmem_x, p_hi + adv, q_lo + adv, idesc, (i == 0 && k == 0) ? 0u : 1u);
-              umma_f16_2sm(tmem_x, p_lo + adv, q_hi + adv, idesc, 1u);
+            for (int k = 0; k < IGEMM_BK / IGEMM_UMMA_K; ++k) {
+              if (k < nk) {
+                uint64_t const adv = static_cast<uint64_t>((k * IGEMM_UMMA_K * 2) >> 4);
+                umma_f16_2sm(tmem_d, p_hi + adv, q_hi + adv, idesc, (first && k == 0) ? 0u : 1u);
+                if (kPlanes == 2) {
+                  umma_f16_2sm(tmem_x, p_hi + adv, q_lo + adv, idesc, (i == 0 && k == 0) ? 0u : 1u);
+                  umma_f16_2sm(tmem_x, p_lo + adv, q_hi + adv, idesc, 1u);
+                }
+              }
             }
+            umma_commit_2sm(&empty_bar[s], 0x3);  // release the stage in both CTAs
+            if (i == i_end - 1) { umma_commit_2sm(&tmem_full_bar[buf], 0x3); }  // wake both CTAs' epilogues
           }
-          umma_commit_2sm(&empty_bar[s], 0x3);  // release the stage in both CTAs
+          __syncwarp();
+          first = false;
         }
-        umma_commit_2sm(&tmem_full_bar[buf], 0x3);  // wake both CTAs' epilogues
       }
     }
   } else {

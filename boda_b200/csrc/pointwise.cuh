@@ -7,6 +7,7 @@
 #include <cfloat>
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
+#include "pdl.cuh"
 
 namespace b200 {
 
@@ -49,6 +50,7 @@ __device__ __forceinline__ float det_hash_rand(uint32_t rv) {
 // kind: 0 = Convolution_in / Convolution_filts style 4-d (x,y modes), 1 = biases, 2 = sgemm_a (K:M), 3 = sgemm_b (K:N)
 __global__ void gen_data_kernel(float *__restrict__ dst, uint32_t n, int kind, uint32_t inner /*x | M | N*/,
                                 uint32_t inner2 /*y | K*/, uint32_t mode, float vi, uint32_t salt) {
+  pdl_prologue();
   uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) { return; }
   float val = vi;
@@ -82,6 +84,7 @@ __global__ void gen_data_kernel(float *__restrict__ dst, uint32_t n, int kind, u
 
 // ---- relu (test/rtc/relu.cucl) --------------------------------------------------------------------------------
 __global__ void relu_kernel(float *__restrict__ x, long long n) {
+  pdl_prologue();
   long long const i4 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4;
   if (i4 + 3 < n && ((reinterpret_cast<uintptr_t>(x) & 15) == 0)) {
     float4 v = *reinterpret_cast<float4 *>(x + i4);
@@ -96,6 +99,7 @@ __global__ void relu_kernel(float *__restrict__ x, long long n) {
 // in: [N][C][HW] -> out[:, ocix:ocix+C]; per image the source block is contiguous, so move 128-bit words when aligned.
 __global__ void concat_copy_kernel(float const *__restrict__ in, float *__restrict__ out, long long per_img /*C*HW*/,
                                    long long out_img_stride, long long out_off, int n_img, int vec4, unsigned int *out_absmax) {
+  pdl_prologue();
   long long const total = per_img * n_img;
   float m = 0.0f;
   if (vec4) {
@@ -121,6 +125,7 @@ __global__ void concat_copy_kernel(float const *__restrict__ in, float *__restri
 // ---- reduce: N-ary elementwise sum (test/rtc/reduce.cucl) ------------------------------------------------------
 struct ReduceArgs { float const *ins[8]; int ins_num; };
 __global__ void reduce_sum_kernel(ReduceArgs a, float *__restrict__ out, long long n) {
+  pdl_prologue();
   long long const i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= n) { return; }
   float v = 0;
@@ -131,6 +136,7 @@ __global__ void reduce_sum_kernel(ReduceArgs a, float *__restrict__ out, long lo
 // ---- pool (test/rtc/pool.cucl:13-40) --------------------------------------------------------------------------
 __global__ void pool_kernel(float const *__restrict__ in, float *__restrict__ out, long long n_out, int H, int W, int OH,
                             int OW, int KH, int KW, int sy, int sx, int py, int px, int avg_pool, unsigned int *out_absmax) {
+  pdl_prologue();
   long long const i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   float out_v = 0.0f;
   if (i < n_out) {
@@ -161,6 +167,7 @@ template <int K, int S>
 __global__ void __launch_bounds__(256)
 pool_kernel_fixed(float const *__restrict__ in, float *__restrict__ out, int H, int W, int OH, int OW, int py, int px, int avg_pool,
                   unsigned int *out_absmax) {
+  pdl_prologue();
   int const p = blockIdx.x * blockDim.x + threadIdx.x;
   long long const plane = blockIdx.y + static_cast<long long>(blockIdx.z) * gridDim.y;
   bool const valid = p < OH * OW;
@@ -210,6 +217,7 @@ template <int K, int S>
 __global__ void __launch_bounds__(256)
 pool_plane_kernel(float const *__restrict__ in, float *__restrict__ out, int H, int W, int OH, int OW, int py, int px, int avg_pool,
                   unsigned int *out_absmax) {
+  pdl_prologue();
   extern __shared__ float plane_s[];
   long long const plane = blockIdx.x;
   float const *ip = in + plane * H * W;
@@ -249,6 +257,7 @@ template <int kLS, int kChunk>
 __global__ void __launch_bounds__(128)
 lrn_kernel(float const *__restrict__ in, float *__restrict__ out, long long n_pels, int C, int HW, float alpha, float beta, float k,
            unsigned int *out_absmax) {
+  pdl_prologue();
   long long const pel = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   bool const valid = pel < n_pels;
   long long const img = valid ? pel / HW : 0;
@@ -285,6 +294,7 @@ lrn_kernel(float const *__restrict__ in, float *__restrict__ out, long long n_pe
 // generic local_size fallback (ring in local memory)
 __global__ void lrn_kernel_generic(float const *__restrict__ in, float *__restrict__ out, long long n_pels, int C, int HW,
                                    int local_size, float alpha, float beta, float k, unsigned int *out_absmax) {
+  pdl_prologue();
   long long const pel = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   bool const valid = pel < n_pels;
   long long const img = valid ? pel / HW : 0;
@@ -315,6 +325,7 @@ __global__ void lrn_kernel_generic(float const *__restrict__ in, float *__restri
 // ---- softmax over chan (test/rtc/softmax.cucl:6-21; running max starts at 0.0f) -------------------------------
 // One warp per (img,y,x): lanes stride the channel dim, shuffle-reduce max and sum.
 __global__ void softmax_kernel(float const *__restrict__ in, float *__restrict__ prob, long long n_pels, int C, int HW) {
+  pdl_prologue();
   long long const pel = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   int const lane = threadIdx.x & 31;
   if (pel >= n_pels) { return; }
@@ -338,6 +349,7 @@ __global__ void softmax_kernel(float const *__restrict__ in, float *__restrict__
 // ---- operand pack: abs-max -> power-of-two scale -> transpose + 16-bit split ----------------------------------
 // absmax over a tensor (non-negative floats order like their bit patterns, so atomicMax on uint works).
 __global__ void absmax_kernel(float const *__restrict__ x, long long n, unsigned int *__restrict__ out_bits) {
+  pdl_prologue();
   float m = 0.0f;
   long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
   long long const tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -357,6 +369,7 @@ __global__ void absmax_kernel(float const *__restrict__ x, long long n, unsigned
   if ((threadIdx.x & 31) == 0 && m > 0.0f) { atomicMax(out_bits, __float_as_uint(m)); }
 }
 __global__ void finalize_scale_kernel(unsigned int *__restrict__ bits, float *__restrict__ scale2, int use_scale) {
+  pdl_prologue();
   float const s = use_scale ? scale_from_absmax_bits(*bits) : 1.0f;
   scale2[0] = s;
   scale2[1] = 1.0f / s;
@@ -367,6 +380,7 @@ __global__ void finalize_scale_kernel(unsigned int *__restrict__ bits, float *__
 template <bool kBf16>
 __global__ void pack_rows_split_kernel(float const *__restrict__ src, uint16_t *__restrict__ hi, uint16_t *__restrict__ lo, float const *__restrict__ scale2,
                                        int R, long long dst_b_stride, long long n, unsigned int const *__restrict__ absmax_bits) {
+  pdl_prologue();
   float const s = absmax_bits ? scale_from_absmax_bits(*absmax_bits) : scale2[0];
   if (absmax_bits && threadIdx.x == 0 && blockIdx.x == 0) { const_cast<float *>(scale2)[0] = s; const_cast<float *>(scale2)[1] = 1.0f / s; }
   long long const i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -393,6 +407,7 @@ template <int kCp, bool kBf16>
 __global__ void __launch_bounds__(256)
 pack_smallc_kernel(float const *__restrict__ src, uint16_t *__restrict__ hi, uint16_t *__restrict__ lo, float const *__restrict__ scale2, int C, int H, int W,
                    int Wp, int px_off, long long n_pix, unsigned int const *__restrict__ absmax_bits) {
+  pdl_prologue();
   float const s = absmax_bits ? scale_from_absmax_bits(*absmax_bits) : scale2[0];
   if (absmax_bits && threadIdx.x == 0 && blockIdx.x == 0) { const_cast<float *>(scale2)[0] = s; const_cast<float *>(scale2)[1] = 1.0f / s; }
   long long const i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -438,6 +453,7 @@ __global__ void __launch_bounds__(256)
 pack_xpose_split_kernel(float const *__restrict__ src, uint16_t *__restrict__ hi, uint16_t *__restrict__ lo, float const *__restrict__ scale2,
                         int R, int C, int Rpad, long long dst_c_stride, long long dst_b_stride, int c_inner, long long dst_chi_stride, long long dst_base,
                         unsigned int const *__restrict__ absmax_bits) {
+  pdl_prologue();
   __shared__ float tile[64][33];
   int const tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   int const r0 = blockIdx.x * 64, c0 = blockIdx.y * 32;

@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cuda.h>
+#include "pdl.cuh"
 
 namespace b200 {
 

@@ -1,0 +1,80 @@
+"""Batch sharding of has_conv_fwd_t::run_fwd over the GPUs of one box (the reference has no multi-GPU path).
+
+Every op on the rtc_fwd path is per-image (`img` is the outermost dim of every activation node, src/conv_util.cc:482-503), so the
+ranks split the batch and never exchange activations:
+  * `shard_range`       -- rank r owns the contiguous images [r*ceil(B/G), min(B, (r+1)*ceil(B/G)))
+  * `broadcast_params`  -- ONE collective broadcast of all filts / biases from rank 0 at init (flattened into a single buffer)
+  * `gather_logits`     -- ONE all-gather of the per-rank output node per forward
+Only `torch.distributed` calls; the tensors live wherever the process group's backend wants them (CUDA for NCCL over NVLink on the
+GPU box, CPU for the gloo tests), so the same code is exercised by world_size-2 CPU tests.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Tuple
+
+import numpy as np
+
+
+def shard_range(global_batch: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous split of the `img` dim: [begin, end) for `rank`; trailing ranks may get fewer (or zero) images."""
+    if world < 1 or not (0 <= rank < world) or global_batch < 0:
+        raise ValueError("shard_range: bad world/rank/batch %r/%r/%r" % (world, rank, global_batch))
+    per = -(-global_batch // world)
+    b = min(global_batch, rank * per)
+    return b, min(global_batch, b + per)
+
+
+def param_layout(shapes: Dict[str, Tuple[int, ...]]) -> List[Tuple[str, int, int, Tuple[int, ...]]]:
+    """Deterministic (sorted-by-name) packing of the parameter nodes into one flat buffer: [(name, offset, numel, shape)]."""
+    out, off = [], 0
+    for n in sorted(shapes):
+        sz = int(np.prod(shapes[n]))
+        out.append((n, off, sz, tuple(shapes[n])))
+        off += sz
+    return out
+
+
+def broadcast_params(dist, shapes: Dict[str, Tuple[int, ...]], params_rank0, device="cpu", src: int = 0) -> Dict[str, np.ndarray]:
+    """All filts / biases in ONE broadcast from `src` (north_star: "a single NCCL broadcast of weights"). `params_rank0` is a dict of
+    numpy arrays on the source rank (ignored elsewhere; may be None). Returns the full dict as host arrays on every rank."""
+    import torch
+    layout = param_layout(shapes)
+    total = layout[-1][1] + layout[-1][2] if layout else 0
+    flat = torch.empty(total, dtype=torch.float32, device=device)
+    if dist.get_rank() == src:
+        if params_rank0 is None:
+            raise ValueError("broadcast_params: the source rank needs the parameters")
+        host = np.empty(total, np.float32)
+        for n, off, sz, shape in layout:
+            a = np.asarray(params_rank0[n], np.float32)
+            if tuple(a.shape) != shape:
+                raise ValueError("broadcast_params: '%s' has shape %r, the net wants %r" % (n, a.shape, shape))
+            host[off:off + sz] = a.ravel()
+        flat.copy_(torch.from_numpy(host))
+    dist.broadcast(flat, src=src)
+    host = flat.cpu().numpy()
+    return {n: host[off:off + sz].reshape(shape) for n, off, sz, shape in layout}
+
+
+def gather_logits(dist, local, out=None):
+    """All-gather of each rank's output node ([B_local, ...] with equal B_local on every rank) into [world*B_local, ...], rank-major --
+    i.e. image order of the global batch under `shard_range`."""
+    import torch
+    world = dist.get_world_size()
+    if out is None:
+        out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local.contiguous())
+    return out
+
+
+def max_over_ranks(dist, value: float, device="cpu") -> float:
+    """Timing rule for every multi-GPU number: the slowest rank's device time."""
+    import torch
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def split_inputs(x: np.ndarray, world: int) -> Iterable[np.ndarray]:
+    """Host-side scatter of a global NCHW batch into per-rank shards (each rank H2D-copies only its own)."""
+    return [x[slice(*shard_range(x.shape[0], world, r))] for r in range(world)]

@@ -29,8 +29,8 @@ def with_relu(op_text, relu=1):
 class OpRunner:
     """One rtc_compute_t instance; vars are named <func>_<arg> and released after each op."""
 
-    def __init__(self, prec="fp32", acc_chunk_kblks=None):
-        self.rtc = bb.B200Compute(prec=prec, acc_chunk_kblks=acc_chunk_kblks)
+    def __init__(self, prec="fp32", acc_chunk_kblks=None, **opts):
+        self.rtc = bb.B200Compute(prec=prec, acc_chunk_kblks=acc_chunk_kblks, **opts)
         self.rtc.init()
 
     def close(self):

@@ -330,14 +330,47 @@ def test_conv_cluster_multicast_is_bit_identical(oracle, case):
     outs = []
     import boda_b200 as bb
     for kw in (dict(use_2cta=1), dict(use_2cta=0, use_clusters=1), dict(use_2cta=0, use_clusters=0)):  # CTA pairs | multicast clusters | plain tiles
-        r = OpRunner()
-        r.rtc.close()
-        r.rtc = bb.B200Compute(**kw)
-        r.rtc.init()
+        r = OpRunner(use_taps=0, **kw)  # the im2col kernels (the tap-reuse kernel has its own test below)
         outs.append(r.run_conv(conv_op_text(N, C, H, W, OC, KH, KW, sy, sx, py, px, 1), x, w, b, ref.shape))
         r.close()
     assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[1], outs[2])
     assert oracle.mrd(ref, outs[0]) < TOL
+
+
+TAPS_CASES = [
+    # N, C, H, W, OC, KH, KW, py, px   (stride 1: the tap-reuse kernel, igemm3.cuh)
+    (20, 256, 13, 13, 384, 3, 3, 1, 1),   # AlexNet conv3 (BASELINE C3 op 6): 3 N-tiles, tiles span image boundaries
+    (4, 96, 27, 27, 256, 5, 5, 2, 2),     # AlexNet conv2: 25 taps, channel block of 64 + ragged 32
+    (3, 64, 56, 56, 192, 3, 3, 1, 1),     # GoogLeNet conv2: wide rows (halo of 248 activation rows), BN=128 + ragged N tile
+    (2, 16, 28, 28, 48, 5, 5, 2, 2),      # GoogLeNet 5x5 reduce branch: fewer than 64 channels, BN=64
+    (5, 40, 17, 9, 72, 3, 2, 1, 0),       # non-square window, padding in y only
+    (2, 130, 14, 14, 70, 3, 3, 0, 0),     # no padding ("valid" conv): the dropped virtual pixels are real pixels
+    (1, 8, 40, 40, 24, 3, 3, 2, 2),       # padding = window overhang (pad 2 on a 3x3): BN=32
+]
+
+
+@pytest.mark.parametrize("case", TAPS_CASES)
+def test_conv_tap_reuse_kernel(oracle, case):
+    """The tap-reuse kernel (one activation halo tile in shared memory feeds every filter tap through shifted UMMA descriptors) as single
+    CTAs and as CTA pairs: bit-identical to each other (same per-output arithmetic), and within tolerance of the oracle like the im2col path."""
+    from b200_harness import OpRunner, conv_op_text
+    N, C, H, W, OC, KH, KW, py, px = case
+    rng = np.random.RandomState(N * 100 + C)
+    x = (rng.rand(N, C, H, W).astype(np.float32) - 0.5) * 10
+    w = (rng.rand(OC, C, KH, KW).astype(np.float32) - 0.5) * 10
+    b = (rng.rand(OC).astype(np.float32) - 0.5) * 10
+    ref64 = oracle.conv_fwd(x, w, b, (1, 1), (py, px), relu=True, acc64=True)
+    noise = oracle.mrd(ref64, oracle.conv_fwd(x, w, b, (1, 1), (py, px), relu=True))
+    outs = {}
+    for name, kw in (("taps_1cta", dict(use_taps=1, taps_2cta=0)), ("taps_2cta", dict(use_taps=1, taps_2cta=1)), ("im2col", dict(use_taps=0))):
+        r = OpRunner(**kw)
+        try:
+            outs[name] = r.run_conv(conv_op_text(N, C, H, W, OC, KH, KW, 1, 1, py, px, 1), x, w, b, ref64.shape)
+        finally:
+            r.close()
+        assert oracle.mrd(ref64, outs[name]) < TOL, (name, oracle.mrd(ref64, outs[name]))
+    assert np.array_equal(outs["taps_1cta"], outs["taps_2cta"])
+    assert oracle.mrd(outs["im2col"], outs["taps_1cta"]) < TOL + noise
 
 
 def test_sgemm_cluster_multicast(oracle):

@@ -41,10 +41,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--out", default="")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--opts", default="", help="extra back-end options, e.g. use_taps=0,taps_2cta=1,acc_chunk_kblks_16=4")
     ap.add_argument("--max-check-gflop", type=float, default=40.0, help="skip the CPU oracle compare for ops larger than this")
     args = ap.parse_args()
     peak_tf, hbm_gbs, src = peaks()
-    rtc = bb.B200Compute(prec=args.prec)
+    rtc = bb.B200Compute(prec=args.prec, **dict(kv.split("=") for kv in args.opts.split(",") if kv))
     rtc.init()
     rows = []
     for li, line in enumerate(open(args.ops_fn)):
