@@ -518,7 +518,7 @@ struct run_ctx_t {
 
   // src [B][R][Cc] fp32 -> planes [B][Cc][..R..] 16-bit, with abs-max scaling. Cached on (pointer, generation).
   void pack(packed_t &pk, var_info_t &src, int B, int R, int Cc, int Rpad, long long dst_c_stride, long long dst_b_stride, long long total_elems, bool want_lo, bool bf16,
-            int c_inner = 0, long long dst_chi_stride = 0, long long dst_base = 0, unsigned int const *absmax_src = nullptr, int smallc_W = 0) {
+            int c_inner = 0, long long dst_chi_stride = 0, long long dst_base = 0, unsigned int const *absmax_src = nullptr, int smallc_W = 0, long long kmajor_rows = 0) {
     if (c_inner <= 0) { c_inner = std::max(Cc, 1); }
     if (pk.src_gen == *src.gen && pk.src_ptr == src.buf->p && pk.hi) { return; }
     if (!pk.hi || pk.hi->bytes < (uint64_t)total_elems * 2) {
@@ -556,15 +556,15 @@ struct run_ctx_t {
     }
     if (Cc == 1 && dst_base == 0) {  // rows are already K-major: elementwise scale + split
       long long const nn = (long long)B * R;
-      if (bf16) { B200_CARVEOUT_ONCE(b200::pack_rows_split_kernel<true>); launch_k(b200::pack_rows_split_kernel<true>, dim3(ceil_div(nn, 256)), dim3(256), 0, fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, dst_b_stride, nn, absmax_src); }
-      else { B200_CARVEOUT_ONCE(b200::pack_rows_split_kernel<false>); launch_k(b200::pack_rows_split_kernel<false>, dim3(ceil_div(nn, 256)), dim3(256), 0, fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, dst_b_stride, nn, absmax_src); }
+      if (bf16) { B200_CARVEOUT_ONCE(b200::pack_rows_split_kernel<true>); launch_k(b200::pack_rows_split_kernel<true>, dim3(ceil_div(nn, 256)), dim3(256), 0, fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, dst_b_stride, nn, absmax_src, kmajor_rows); }
+      else { B200_CARVEOUT_ONCE(b200::pack_rows_split_kernel<false>); launch_k(b200::pack_rows_split_kernel<false>, dim3(ceil_div(nn, 256)), dim3(256), 0, fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, dst_b_stride, nn, absmax_src, kmajor_rows); }
       launched();
       pk.src_gen = *src.gen;
       pk.src_ptr = src.buf->p;
       return;
     }
-    if (bf16) { B200_CARVEOUT_ONCE(b200::pack_xpose_split_kernel<true>); launch_k(b200::pack_xpose_split_kernel<true>, dim3(grid), dim3(256), 0, fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, Cc, Rpad, dst_c_stride, dst_b_stride, c_inner, dst_chi_stride, dst_base, absmax_src); }
-    else { B200_CARVEOUT_ONCE(b200::pack_xpose_split_kernel<false>); launch_k(b200::pack_xpose_split_kernel<false>, dim3(grid), dim3(256), 0, fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, Cc, Rpad, dst_c_stride, dst_b_stride, c_inner, dst_chi_stride, dst_base, absmax_src); }
+    if (bf16) { B200_CARVEOUT_ONCE(b200::pack_xpose_split_kernel<true>); launch_k(b200::pack_xpose_split_kernel<true>, dim3(grid), dim3(256), 0, fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, Cc, Rpad, dst_c_stride, dst_b_stride, c_inner, dst_chi_stride, dst_base, absmax_src, kmajor_rows); }
+    else { B200_CARVEOUT_ONCE(b200::pack_xpose_split_kernel<false>); launch_k(b200::pack_xpose_split_kernel<false>, dim3(grid), dim3(256), 0, fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, Cc, Rpad, dst_c_stride, dst_b_stride, c_inner, dst_chi_stride, dst_base, absmax_src, kmajor_rows); }
     launched();
     pk.src_gen = *src.gen;
     pk.src_ptr = src.buf->p;
@@ -692,21 +692,23 @@ struct run_ctx_t {
     if (!stg.a_stages) { return false; }
 
     // filters: OIHW -> [OC][tap][chan] K-major rows, once per weight version; activations: NCHW -> shared-padding NHWC (see igemm3.cuh)
-    pack(f.w_pack, vf, cp.OC, cp.C, taps, cp.Cpad, cp.w_tap_stride, cp.w_row_stride, (long long)cp.OC * cp.w_row_stride, planes == 2, bf16);
+    long long const oc_pad = round_up(cp.OC, 128);  // filters are packed k-block-major: [k-block][out_chan padded][64]
+    pack(f.w_pack, vf, cp.OC, cp.C, taps, cp.Cpad, cp.w_tap_stride, cp.w_row_stride, oc_pad * cp.w_row_stride, planes == 2, bf16, 0, 0, 0, nullptr, 0, oc_pad);
     long long const img_elems = (long long)Hp * Wp * cp.Cpad;
     pack(f.a_pack, vin, cp.N, cp.C, cp.H * cp.W, cp.Cpad, cp.Cpad, img_elems, (long long)cp.N * img_elems, planes == 2, bf16, cp.W, (long long)Wp * cp.Cpad,
          ((long long)cp.py * Wp + cp.px) * cp.Cpad, absmax_cell("in"));
     CUtensorMap const a_hi = make_tiled_map(f.a_pack.hi->p, bf16, cp.Cpad, (uint64_t)cp.N * Hp * Wp, cp.Cpad, a_box_rows);
     CUtensorMap const a_lo = planes == 2 ? make_tiled_map(f.a_pack.lo->p, bf16, cp.Cpad, (uint64_t)cp.N * Hp * Wp, cp.Cpad, a_box_rows) : a_hi;
     uint32_t const w_box = k2 ? BN / 2 : BN;
-    CUtensorMap const w_hi = make_tiled_map(f.w_pack.hi->p, bf16, cp.w_row_stride, cp.OC, cp.w_row_stride, w_box);
-    CUtensorMap const w_lo = planes == 2 ? make_tiled_map(f.w_pack.lo->p, bf16, cp.w_row_stride, cp.OC, cp.w_row_stride, w_box) : w_hi;
+    uint64_t const w_rows = (uint64_t)(cp.w_row_stride / 64) * oc_pad;
+    CUtensorMap const w_hi = make_tiled_map(f.w_pack.hi->p, bf16, 64, w_rows, 64, w_box);
+    CUtensorMap const w_lo = planes == 2 ? make_tiled_map(f.w_pack.lo->p, bf16, 64, w_rows, 64, w_box) : w_hi;
 
     b200::TapsParams prm;
     memset(&prm, 0, sizeof(prm));
     prm.m_rows = (int)m_rows; prm.q_rows = cp.OC;
     prm.cblks = cp.cblks; prm.taps = taps; prm.kw = cp.KW;
-    prm.ksteps_last = cp.ksteps_last;
+    prm.ksteps_last = cp.ksteps_last; prm.w_kb_rows = (int)oc_pad;
     prm.Wp = Wp; prm.HpWp = Hp * Wp; prm.OH = cp.OH; prm.OW = cp.OW;
     prm.halo_rows = halo_rows; prm.a_loads = a_loads; prm.a_box_rows = a_box_rows;
     prm.a_stages = stg.a_stages; prm.b_stages = stg.b_stages;
@@ -750,14 +752,16 @@ struct run_ctx_t {
     bool const bf16 = (rtc.prec == B200_PREC_BF16);
     int const planes = (rtc.prec == B200_PREC_FP32_SPLIT) ? 2 : 1;
     if (cp.taps && rtc.use_taps && run_conv_taps(vin, vf, vout, bias, bf16, planes)) { return; }
-    // filters: OIHW -> [OC][tap][chan] K-major rows (once per weight version; the reference's xpose_filts, src/rtc_fwd.cc:310-313)
+    // filters: OIHW -> K-major rows (k = tap x chan), stored k-block-major [k / 64][OC padded][64] so that every TMA tile is contiguous
+    // (once per weight version; the reference's xpose_filts, src/rtc_fwd.cc:310-313)
+    long long const oc_pad = round_up(cp.OC, 128);
     // activations: NCHW -> NHWC (chan padded to a multiple of 8; row-merged path: chan padded to 4|8 and image rows at pitch Wp with x padding)
     if (cp.rowmerge) {
-      pack(f.w_pack, vf, cp.OC, cp.C, cp.KH * cp.KW, cp.Cpad, cp.Cpad, cp.w_row_stride, (long long)cp.OC * cp.w_row_stride, planes == 2, bf16, cp.KW, 64, 0);
+      pack(f.w_pack, vf, cp.OC, cp.C, cp.KH * cp.KW, cp.Cpad, cp.Cpad, cp.w_row_stride, oc_pad * cp.w_row_stride, planes == 2, bf16, cp.KW, 64, 0, nullptr, 0, oc_pad);
       long long const img_elems = (long long)cp.H * cp.Wp * cp.Cpad;
       pack(f.a_pack, vin, cp.N, cp.C, cp.H * cp.W, cp.Cpad, cp.Cpad, img_elems, (long long)cp.N * img_elems + 64, planes == 2, bf16, cp.W, (long long)cp.Wp * cp.Cpad, (long long)cp.px * cp.Cpad, absmax_cell("in"), cp.W);
     } else {
-      pack(f.w_pack, vf, cp.OC, cp.C, cp.KH * cp.KW, cp.Cpad, cp.w_tap_stride, cp.w_row_stride, (long long)cp.OC * cp.w_row_stride, planes == 2, bf16);
+      pack(f.w_pack, vf, cp.OC, cp.C, cp.KH * cp.KW, cp.Cpad, cp.w_tap_stride, cp.w_row_stride, oc_pad * cp.w_row_stride, planes == 2, bf16, 0, 0, 0, nullptr, 0, oc_pad);
       long long const act_elems = (long long)cp.N * cp.H * cp.W * cp.Cpad;
       pack(f.a_pack, vin, cp.N, cp.C, cp.H * cp.W, cp.Cpad, cp.Cpad, (long long)cp.H * cp.W * cp.Cpad, act_elems, planes == 2, bf16, 0, 0, 0, absmax_cell("in"));
     }
@@ -779,8 +783,9 @@ struct run_ctx_t {
       act_hi = make_tiled_map(f.a_pack.hi->p, bf16, kext, cp.a_rows, cp.a_row_stride, act_box);
       act_lo = planes == 2 ? make_tiled_map(f.a_pack.lo->p, bf16, kext, cp.a_rows, cp.a_row_stride, act_box) : act_hi;
     }
-    w_hi = make_tiled_map(f.w_pack.hi->p, bf16, cp.w_row_stride, cp.OC, cp.w_row_stride, w_box);
-    w_lo = planes == 2 ? make_tiled_map(f.w_pack.lo->p, bf16, cp.w_row_stride, cp.OC, cp.w_row_stride, w_box) : w_hi;
+    uint64_t const w_rows = (uint64_t)(cp.w_row_stride / 64) * oc_pad;
+    w_hi = make_tiled_map(f.w_pack.hi->p, bf16, 64, w_rows, 64, w_box);
+    w_lo = planes == 2 ? make_tiled_map(f.w_pack.lo->p, bf16, 64, w_rows, 64, w_box) : w_hi;
 
     b200::IgemmParams prm;
     memset(&prm, 0, sizeof(prm));
@@ -801,6 +806,7 @@ struct run_ctx_t {
     prm.idesc = b200::make_idesc_f16(bf16 ? 1u : 0u, 128, cp.BN);
     prm.cm = cl.cm; prm.cn = cl.cn;
     prm.kb_mod = cp.kb_mod; prm.ksteps_last = cp.ksteps_last;
+    prm.p_kb_rows = cp.swapped ? (int)oc_pad : 0; prm.q_kb_rows = cp.swapped ? 0 : (int)oc_pad;
     prm.debug = rtc.debug_flags;
     prm.out_absmax = absmax_cell("out");
     long long const out_elems = (long long)cp.N * cp.OC * cp.OH * cp.OW;
@@ -889,12 +895,15 @@ struct run_ctx_t {
     long long const planes = (long long)vin.dims.dsz("img") * vin.dims.dsz("chan");
     int const avg = (int)scalar("avg_pool", true, 0);
     if (KH == KW && sy == sx && ((KH == 3 && sy == 2) || (KH == 3 && sy == 1) || (KH == 2 && sy == 2)) && (long long)H * W <= 4096 && planes < (1ll << 31)) {  // small planes: stage in smem
-      size_t const smem = (size_t)H * W * 4;
+      // planes per CTA: a multiple of 4 (16-byte aligned runs), tile <= 48 KB, and at least ~4 CTAs per SM left to fill the chip
+      int ppc = (int)std::max<long long>(4, std::min<long long>((48 * 1024) / ((long long)H * W * 4) / 4 * 4, round_up(ceil_div(planes, 4 * im.num_sms), 4)));
+      if ((long long)ppc * H * W * 4 > 96 * 1024) { ppc = 1; }
+      size_t const smem = (size_t)ppc * H * W * 4;
       unsigned int *cell = absmax_cell("out");
 #define B200_POOL_PLANE(K_, S_) do { \
         static bool attr_ = false; \
         if (!attr_) { CU_CHK(cudaFuncSetAttribute(b200::pool_plane_kernel<K_, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); prefer_max_smem(b200::pool_plane_kernel<K_, S_>); attr_ = true; } \
-        launch_k(b200::pool_plane_kernel<K_, S_>, dim3((unsigned)planes), dim3(256), smem, fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, cell); } while (0)
+        launch_k(b200::pool_plane_kernel<K_, S_>, dim3((unsigned)ceil_div(planes, ppc)), dim3(256), smem, fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, cell, ppc, planes); } while (0)
       if (KH == 3 && sy == 2) { B200_POOL_PLANE(3, 2); } else if (KH == 3) { B200_POOL_PLANE(3, 1); } else { B200_POOL_PLANE(2, 2); }
 #undef B200_POOL_PLANE
       launched();

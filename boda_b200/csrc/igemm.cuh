@@ -61,6 +61,8 @@ struct IgemmParams {
   // K tail: k-blocks come in groups of kb_mod (the channel blocks of one filter tap; the whole K for 2-d operands); the last k-block of a
   // group holds only ksteps_last (1..4) 16-wide k-steps of real data -- the rest is zero padding in both operands and is not multiplied
   int kb_mod, ksteps_last;
+  // k-block-major operand layout [k-block][rows][64] (packed filters): rows per k-block, 0 = plain row-major [rows][K]
+  int p_kb_rows, q_kb_rows;
 };
 
 template <int BN, int kPlanes>
@@ -204,19 +206,25 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
             tma_load_im2col_4d(p_hi, &p_hi_map, &full_bar[s], cb * IGEMM_BK, w_base, h_base, img, (uint16_t)kx, (uint16_t)ky);
             if (kPlanes == 2) { tma_load_im2col_4d(p_lo, &p_lo_map, &full_bar[s], cb * IGEMM_BK, w_base, h_base, img, (uint16_t)kx, (uint16_t)ky); }
           }
-        } else if (mc_p) {
-          tma_load_2d_mc(p_hi, &p_hi_map, &full_bar[s], kb * IGEMM_BK, pm0, mask_p);
-          if (kPlanes == 2) { tma_load_2d_mc(p_lo, &p_lo_map, &full_bar[s], kb * IGEMM_BK, pm0, mask_p); }
         } else {
-          tma_load_2d(p_hi, &p_hi_map, &full_bar[s], kb * IGEMM_BK, pm0);
-          if (kPlanes == 2) { tma_load_2d(p_lo, &p_lo_map, &full_bar[s], kb * IGEMM_BK, pm0); }
+          int const c0 = prm.p_kb_rows ? 0 : kb * IGEMM_BK, c1 = pm0 + kb * prm.p_kb_rows;
+          if (mc_p) {
+            tma_load_2d_mc(p_hi, &p_hi_map, &full_bar[s], c0, c1, mask_p);
+            if (kPlanes == 2) { tma_load_2d_mc(p_lo, &p_lo_map, &full_bar[s], c0, c1, mask_p); }
+          } else {
+            tma_load_2d(p_hi, &p_hi_map, &full_bar[s], c0, c1);
+            if (kPlanes == 2) { tma_load_2d(p_lo, &p_lo_map, &full_bar[s], c0, c1); }
+          }
         }
-        if (mc_q) {
-          tma_load_2d_mc(q_hi, &q_hi_map, &full_bar[s], kb * IGEMM_BK, n0 + q_row0, mask_q);
-          if (kPlanes == 2) { tma_load_2d_mc(q_lo, &q_lo_map, &full_bar[s], kb * IGEMM_BK, n0 + q_row0, mask_q); }
-        } else {
-          tma_load_2d(q_hi, &q_hi_map, &full_bar[s], kb * IGEMM_BK, n0);
-          if (kPlanes == 2) { tma_load_2d(q_lo, &q_lo_map, &full_bar[s], kb * IGEMM_BK, n0); }
+        {
+          int const c0 = prm.q_kb_rows ? 0 : kb * IGEMM_BK, c1 = n0 + kb * prm.q_kb_rows;
+          if (mc_q) {
+            tma_load_2d_mc(q_hi, &q_hi_map, &full_bar[s], c0, c1 + q_row0, mask_q);
+            if (kPlanes == 2) { tma_load_2d_mc(q_lo, &q_lo_map, &full_bar[s], c0, c1 + q_row0, mask_q); }
+          } else {
+            tma_load_2d(q_hi, &q_hi_map, &full_bar[s], c0, c1);
+            if (kPlanes == 2) { tma_load_2d(q_lo, &q_lo_map, &full_bar[s], c0, c1); }
+          }
         }
         }
         __syncwarp();
@@ -244,24 +252,13 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
           if (!(prm.debug & 1)) { mbar_wait(&full_bar[s], ph); }
           tc_fence_after();
           uint32_t const st = smem_u32(smem + s * Cfg::kStageBytes);
-          uint64_t const p_hi = make_kmajor_sw128_desc(st), p_lo = make_kmajor_sw128_desc(st + kPBytes);
-          uint64_t const q_hi = make_kmajor_sw128_desc(st + kPlanes * kPBytes);
-          uint64_t const q_lo = make_kmajor_sw128_desc(st + kPlanes * kPBytes + kQBytes);
+          uint32_t const p_hi = sw128_desc_lo(st), p_lo = sw128_desc_lo(st + kPBytes);
+          uint32_t const q_hi = sw128_desc_lo(st + kPlanes * kPBytes), q_lo = sw128_desc_lo(st + kPlanes * kPBytes + kQBytes);
           int nk = IGEMM_BK / IGEMM_UMMA_K;
           if (++kb_in_grp == kb_mod) { kb_in_grp = 0; nk = ksteps_last; }
           if (prm.debug & 2) { nk = 0; }
           if (elect_one_sync()) {
-#pragma unroll
-            for (int k = 0; k < IGEMM_BK / IGEMM_UMMA_K; ++k) {
-              if (k < nk) {
-                uint64_t const adv = static_cast<uint64_t>((k * IGEMM_UMMA_K * 2) >> 4);  // +32 B per k-step inside the swizzle row
-                umma_f16(tmem_d, p_hi + adv, q_hi + adv, idesc, (first && k == 0) ? 0u : 1u);
-                if (kPlanes == 2) {
-                  umma_f16(tmem_x, p_hi + adv, q_lo + adv, idesc, (i == 0 && k == 0) ? 0u : 1u);
-                  umma_f16(tmem_x, p_lo + adv, q_hi + adv, idesc, 1u);
-                }
-              }
-            }
+            issue_kblock<kPlanes, false>(tmem_d, tmem_x, p_hi, p_lo, q_hi, q_lo, idesc, first ? 0u : 1u, i == 0 ? 0u : 1u, nk);
             // frees this smem stage -- in every CTA that multicast a slice into it -- once the MMAs above have read it
             if (clustered) { umma_commit_mc(&empty_bar[s], static_cast<uint16_t>(mask_p | mask_q)); } else { umma_commit(&empty_bar[s]); }
             if (i == i_end - 1) { umma_commit(&tmem_full_bar[buf]); }  // accumulator chunk complete

@@ -101,8 +101,9 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
           tma_load_2d_2sm(p_hi, &p_hi_map, &full_bar[s], i * IGEMM_BK, m0);
           if (kPlanes == 2) { tma_load_2d_2sm(p_lo, &p_lo_map, &full_bar[s], i * IGEMM_BK, m0); }
         }
-        tma_load_2d_2sm(q_hi, &q_hi_map, &full_bar[s], i * IGEMM_BK, q_row0);
-        if (kPlanes == 2) { tma_load_2d_2sm(q_lo, &q_lo_map, &full_bar[s], i * IGEMM_BK, q_row0); }
+        int const qc0 = prm.q_kb_rows ? 0 : i * IGEMM_BK, qc1 = q_row0 + i * prm.q_kb_rows;
+        tma_load_2d_2sm(q_hi, &q_hi_map, &full_bar[s], qc0, qc1);
+        if (kPlanes == 2) { tma_load_2d_2sm(q_lo, &q_lo_map, &full_bar[s], qc0, qc1); }
         }
         __syncwarp();
         if (++cb == prm.cblks) { cb = 0; if (++kx == prm.kw) { kx = 0; ++ky; } }
@@ -129,23 +130,12 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           uint32_t const st = smem_u32(smem + s * Cfg::kStageBytes);
-          uint64_t const p_hi = make_kmajor_sw128_desc(st), p_lo = make_kmajor_sw128_desc(st + kPBytes);
-          uint64_t const q_hi = make_kmajor_sw128_desc(st + kPlanes * kPBytes);
-          uint64_t const q_lo = make_kmajor_sw128_desc(st + kPlanes * kPBytes + kQBytes);
+          uint32_t const p_hi = sw128_desc_lo(st), p_lo = sw128_desc_lo(st + kPBytes);
+          uint32_t const q_hi = sw128_desc_lo(st + kPlanes * kPBytes), q_lo = sw128_desc_lo(st + kPlanes * kPBytes + kQBytes);
           int nk = IGEMM_BK / IGEMM_UMMA_K;
           if (++kb_in_grp == kb_mod) { kb_in_grp = 0; nk = ksteps_last; }
           if (elect_one_sync()) {
-#pragma unroll
-            for (int k = 0; k < IGEMM_BK / IGEMM_UMMA_K; ++k) {
-              if (k < nk) {
-                uint64_t const adv = static_cast<uint64_t>((k * IGEMM_UMMA_K * 2) >> 4);
-                umma_f16_2sm(tmem_d, p_hi + adv, q_hi + adv, idesc, (first && k == 0) ? 0u : 1u);
-                if (kPlanes == 2) {
-                  umma_f16_2sm(tmem_x, p_hi + adv, q_lo + adv, idesc, (i == 0 && k == 0) ? 0u : 1u);
-                  umma_f16_2sm(tmem_x, p_lo + adv, q_hi + adv, idesc, 1u);
-                }
-              }
-            }
+            issue_kblock<kPlanes, true>(tmem_d, tmem_x, p_hi, p_lo, q_hi, q_lo, idesc, first ? 0u : 1u, i == 0 ? 0u : 1u, nk);
             umma_commit_2sm(&empty_bar[s], 0x3);  // release the stage in both CTAs
             if (i == i_end - 1) { umma_commit_2sm(&tmem_full_bar[buf], 0x3); }  // wake both CTAs' epilogues
           }

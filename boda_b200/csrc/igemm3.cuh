@@ -27,6 +27,7 @@ struct TapsParams {
   int m_rows;      // virtual pixels that may hold an output: (N-1)*Hp*Wp + (OH-1)*Wp + OW
   int q_rows;      // out chans
   int cblks;       // 64-channel blocks
+  int w_kb_rows;   // packed filters are k-block-major [tap*cblks + block][out_chan (padded to w_kb_rows)][64]
   int ksteps_last; // 16-wide k-steps of real data in the last channel block (1..4): zero-padded channels are not multiplied
   int taps, kw;    // KH*KW, KW
   int Wp, HpWp;    // padded row pitch, virtual pixels per image
@@ -143,19 +144,19 @@ igemm_taps_kernel(const __grid_constant__ CUtensorMap a_hi_map, const __grid_con
       int s = 0;
       uint32_t b_par = 1;
       for (int c = 0; c < cblks; ++c) {
-        int kcol = c * IGEMM_BK;  // packed filters: [out_chan][tap][chan] -> column (t * cblks + c) * 64
-        for (int t = 0; t < taps; ++t, kcol += cblks * IGEMM_BK) {
+        int wrow = c * prm.w_kb_rows + q_row0;  // packed filters: k-block (t * cblks + c) starts at row (t * cblks + c) * w_kb_rows
+        for (int t = 0; t < taps; ++t, wrow += cblks * prm.w_kb_rows) {
           if (t == t_pref && c + a_stages - 1 < cblks) { issue_a(c + a_stages - 1); }
           mbar_wait(&b_empty[s], b_par);
           if (elect_one_sync()) {
             if (leader) { mbar_expect_tx(&b_full[s], (k2 ? 2u : 1u) * kBStage); } else { mbar_arrive_remote(&b_full[s], 0); }
             uint8_t *d = b_ring + s * kBStage;
             if (k2) {
-              tma_load_2d_2sm(d, &w_hi_map, &b_full[s], kcol, q_row0);
-              if (kPlanes == 2) { tma_load_2d_2sm(d + kBBytes, &w_lo_map, &b_full[s], kcol, q_row0); }
+              tma_load_2d_2sm(d, &w_hi_map, &b_full[s], 0, wrow);
+              if (kPlanes == 2) { tma_load_2d_2sm(d + kBBytes, &w_lo_map, &b_full[s], 0, wrow); }
             } else {
-              tma_load_2d(d, &w_hi_map, &b_full[s], kcol, q_row0);
-              if (kPlanes == 2) { tma_load_2d(d + kBBytes, &w_lo_map, &b_full[s], kcol, q_row0); }
+              tma_load_2d(d, &w_hi_map, &b_full[s], 0, wrow);
+              if (kPlanes == 2) { tma_load_2d(d + kBBytes, &w_lo_map, &b_full[s], 0, wrow); }
             }
           }
           __syncwarp();
@@ -191,30 +192,13 @@ igemm_taps_kernel(const __grid_constant__ CUtensorMap a_hi_map, const __grid_con
         if (g == 0 && lane == 0) { TAPS_STAMP(2); }
         uint32_t const a_addr = smem_u32(a_ring + sa * a_stage) + static_cast<uint32_t>(tap_row) * 128u;
         uint32_t const b_addr = smem_u32(b_ring + sb * kBStage);
-        uint64_t const p_hi = make_kmajor_sw128_desc(a_addr), p_lo = make_kmajor_sw128_desc(a_addr + a_plane);
-        uint64_t const q_hi = make_kmajor_sw128_desc(b_addr), q_lo = make_kmajor_sw128_desc(b_addr + kBBytes);
+        uint32_t const p_hi = sw128_desc_lo(a_addr), p_lo = sw128_desc_lo(a_addr + a_plane);
+        uint32_t const q_hi = sw128_desc_lo(b_addr), q_lo = sw128_desc_lo(b_addr + kBBytes);
         bool const last_tap = (t == taps - 1);
         bool const chunk_end = (in_chunk + 1 == chunk || g == nkb - 1);
         int const nk = (cblk == cblks - 1) ? ksteps_last : ksteps_full;
         if (elect_one_sync()) {
-#pragma unroll
-        for (int k = 0; k < IGEMM_BK / IGEMM_UMMA_K; ++k) {
-          if (k >= nk) { continue; }
-          uint64_t const adv = static_cast<uint64_t>((k * IGEMM_UMMA_K * 2) >> 4);
-          if (k2) {
-            umma_f16_2sm(tmem_d, p_hi + adv, q_hi + adv, idesc, (first && k == 0) ? 0u : 1u);
-            if (kPlanes == 2) {
-              umma_f16_2sm(tmem_x, p_hi + adv, q_lo + adv, idesc, (g == 0 && k == 0) ? 0u : 1u);
-              umma_f16_2sm(tmem_x, p_lo + adv, q_hi + adv, idesc, 1u);
-            }
-          } else {
-            umma_f16(tmem_d, p_hi + adv, q_hi + adv, idesc, (first && k == 0) ? 0u : 1u);
-            if (kPlanes == 2) {
-              umma_f16(tmem_x, p_hi + adv, q_lo + adv, idesc, (g == 0 && k == 0) ? 0u : 1u);
-              umma_f16(tmem_x, p_lo + adv, q_hi + adv, idesc, 1u);
-            }
-          }
-        }
+        issue_kblock<kPlanes, k2>(tmem_d, tmem_x, p_hi, p_lo, q_hi, q_lo, idesc, first ? 0u : 1u, g == 0 ? 0u : 1u, nk);
         bool const ring_commits = !(prm.debug & 8);  // experiments (with bit 0): no stage-release commits
         if (k2) { if (ring_commits) { umma_commit_2sm(&b_empty[sb], 0x3); if (last_tap) { umma_commit_2sm(&a_empty[sa], 0x3); } } if (chunk_end) { umma_commit_2sm(&tmem_full_bar[buf], 0x3); } }
         else { if (ring_commits) { umma_commit(&b_empty[sb]); if (last_tap) { umma_commit(&a_empty[sa]); } } if (chunk_end) { umma_commit(&tmem_full_bar[buf]); } }

@@ -210,24 +210,39 @@ pool_kernel_fixed(float const *__restrict__ in, float *__restrict__ out, int H, 
   if (out_absmax) { publish_absmax_warp(valid ? fabsf(out_v) : 0.0f, out_absmax); }
 }
 
-// Whole-plane variant: one CTA stages an (img,chan) plane in shared memory with coalesced loads and computes its outputs from there, so
-// the stride-S window reads never touch L1/L2 (the overlapping-window kernel above reads every input K*K/S^2 times through L1 with
-// half-used sectors). Used when the plane fits (H*W*4 bytes of dynamic shared memory).
+// Plane-group variant: one CTA stages kPPC consecutive (img,chan) planes -- a CONTIGUOUS run of kPPC*H*W floats -- in shared memory with
+// 128-bit loads and computes their kPPC*OH*OW outputs (also contiguous) from there, so the overlapping stride-S window reads never touch
+// L1/L2 and both global streams are long coalesced runs. Small planes (13x13, 27x27) would otherwise mean thousands of tiny CTAs that
+// are all ramp-up and no bandwidth (measured: 15 us for the 6.7 MB of AlexNet pool5 with one plane per CTA). The host picks planes-per-CTA
+// (a multiple of 4, which keeps every run 16-byte aligned) so that the tile fits the dynamic shared memory it requests.
 template <int K, int S>
 __global__ void __launch_bounds__(256)
 pool_plane_kernel(float const *__restrict__ in, float *__restrict__ out, int H, int W, int OH, int OW, int py, int px, int avg_pool,
-                  unsigned int *out_absmax) {
+                  unsigned int *out_absmax, int ppc, long long n_planes) {
   pdl_prologue();
-  extern __shared__ float plane_s[];
-  long long const plane = blockIdx.x;
-  float const *ip = in + plane * H * W;
-  int const n_in = H * W, n_out = OH * OW;
-  for (int i = threadIdx.x; i < n_in; i += blockDim.x) { plane_s[i] = __ldg(ip + i); }
+  extern __shared__ __align__(16) float plane_s[];
+  long long const plane0 = static_cast<long long>(blockIdx.x) * ppc;
+  int const np = static_cast<int>(min(static_cast<long long>(ppc), n_planes - plane0));
+  int const hw = H * W, n_in = np * hw, ohw = OH * OW, n_out = np * ohw;
+  float const *ip = in + plane0 * hw;
+  if ((reinterpret_cast<uintptr_t>(ip) & 15) == 0) {
+    float4 const *ip4 = reinterpret_cast<float4 const *>(ip);
+    float4 *s4 = reinterpret_cast<float4 *>(plane_s);
+    int const n4 = n_in >> 2;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n4; i += 256) { s4[i] = __ldg(ip4 + i); }
+    for (int i = (n4 << 2) + threadIdx.x; i < n_in; i += 256) { plane_s[i] = __ldg(ip + i); }
+  } else {
+    for (int i = threadIdx.x; i < n_in; i += 256) { plane_s[i] = __ldg(ip + i); }
+  }
   __syncthreads();
   float amax = 0.0f;
-  for (int p = threadIdx.x; p < n_out; p += blockDim.x) {
+  float *op = out + plane0 * ohw;
+  for (int o = threadIdx.x; o < n_out; o += 256) {
+    int const pl = o / ohw, p = o - pl * ohw;
     int const oy = p / OW, ox = p - oy * OW;
     int const y0 = oy * S - py, x0 = ox * S - px;
+    float const *ps = plane_s + pl * hw;
     float out_v = avg_pool ? 0.0f : -FLT_MAX, cnt = 0;
 #pragma unroll
     for (int kx = 0; kx < K; ++kx) {
@@ -235,13 +250,13 @@ pool_plane_kernel(float const *__restrict__ in, float *__restrict__ out, int H, 
       for (int ky = 0; ky < K; ++ky) {
         int const in_y = y0 + ky, in_x = x0 + kx;
         if (in_y >= 0 && in_x >= 0 && in_x < W && in_y < H) {
-          float const v = plane_s[in_y * W + in_x];
+          float const v = ps[in_y * W + in_x];
           if (avg_pool) { out_v += v; cnt += 1; } else { out_v = fmaxf(out_v, v); }
         }
       }
     }
     if (avg_pool) { out_v = __fdiv_rn(out_v, cnt); }
-    out[plane * n_out + p] = out_v;
+    op[o] = out_v;
     amax = fmaxf(amax, fabsf(out_v));
   }
   if (out_absmax) { publish_absmax_warp(amax, out_absmax); }
@@ -379,7 +394,7 @@ __global__ void finalize_scale_kernel(unsigned int *__restrict__ bits, float *__
 // HW == 1 activations (fc7 / fc8 inputs): NCHW [img][chan][1][1] already IS the K-major matrix [img][chan]; only scale + split.
 template <bool kBf16>
 __global__ void pack_rows_split_kernel(float const *__restrict__ src, uint16_t *__restrict__ hi, uint16_t *__restrict__ lo, float const *__restrict__ scale2,
-                                       int R, long long dst_b_stride, long long n, unsigned int const *__restrict__ absmax_bits) {
+                                       int R, long long dst_b_stride, long long n, unsigned int const *__restrict__ absmax_bits, long long kmajor_rows) {
   pdl_prologue();
   float const s = absmax_bits ? scale_from_absmax_bits(*absmax_bits) : scale2[0];
   if (absmax_bits && threadIdx.x == 0 && blockIdx.x == 0) { const_cast<float *>(scale2)[0] = s; const_cast<float *>(scale2)[1] = 1.0f / s; }
@@ -388,7 +403,7 @@ __global__ void pack_rows_split_kernel(float const *__restrict__ src, uint16_t *
   long long const b = i / R;
   int const r = static_cast<int>(i - b * R);
   float const v = __ldg(src + i) * s;
-  long long const o = b * dst_b_stride + r;
+  long long const o = kmajor_rows ? ((static_cast<long long>(r) >> 6) * kmajor_rows + b) * 64 + (r & 63) : b * dst_b_stride + r;  // see pack_xpose_split_kernel
   if (kBf16) {
     __nv_bfloat16 const h = __float2bfloat16_rn(v);
     reinterpret_cast<__nv_bfloat16 *>(hi)[o] = h;
@@ -452,7 +467,7 @@ template <bool kBf16>
 __global__ void __launch_bounds__(256)
 pack_xpose_split_kernel(float const *__restrict__ src, uint16_t *__restrict__ hi, uint16_t *__restrict__ lo, float const *__restrict__ scale2,
                         int R, int C, int Rpad, long long dst_c_stride, long long dst_b_stride, int c_inner, long long dst_chi_stride, long long dst_base,
-                        unsigned int const *__restrict__ absmax_bits) {
+                        unsigned int const *__restrict__ absmax_bits, long long kmajor_rows) {
   pdl_prologue();
   __shared__ float tile[64][33];
   int const tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -478,7 +493,10 @@ pack_xpose_split_kernel(float const *__restrict__ src, uint16_t *__restrict__ hi
         float const v0 = tile[2 * tx][cc], v1 = tile[2 * tx + 1][cc];
         // destination of source column c: (c / c_inner) * dst_chi_stride + (c % c_inner) * dst_c_stride  (c_inner >= C: plain c * dst_c_stride);
         // the two-level form lays image rows out with a padded pitch / filter rows as (ky)(kx,chan) for the row-merged conv path
-        long long const o = b * dst_b_stride + dst_base + static_cast<long long>(c / c_inner) * dst_chi_stride + static_cast<long long>(c % c_inner) * dst_c_stride + r;
+        // k = position inside the destination row; plain layout: row-major [b][k]; k-block-major (kmajor_rows > 0, used for filters):
+        // [k / 64][b (padded to kmajor_rows)][k % 64], so that the 128-row x 64-element tile one TMA load fetches is 16 KB CONTIGUOUS
+        long long const k = dst_base + static_cast<long long>(c / c_inner) * dst_chi_stride + static_cast<long long>(c % c_inner) * dst_c_stride + r;
+        long long const o = kmajor_rows ? ((k >> 6) * kmajor_rows + b) * 64 + (k & 63) : b * dst_b_stride + k;
         if (kBf16) {
           __nv_bfloat16 const h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
           *reinterpret_cast<__nv_bfloat162 *>(hi + o) = __nv_bfloat162(h0, h1);

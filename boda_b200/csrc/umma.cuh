@@ -222,6 +222,54 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
+// Lean issue path: the descriptor's high word is a constant (SBO = 1024 B, version 1, SWIZZLE_128B) and only the low word (start address,
+// LBO = 1) varies, so the issuing warp does 32-bit adds instead of rebuilding 64-bit descriptors for every tcgen05.mma. The tensor pipe
+// queues only ~2 MMAs, so every instruction between two tcgen05.mma is tensor-pipe idle time (measured: issue overhead adds to MMA time).
+constexpr uint32_t kSw128DescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t sw128_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+template <bool k2>
+__device__ __forceinline__ void umma_f16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  if (k2) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\tmov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kSw128DescHi)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\tmov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kSw128DescHi)
+        : "memory");
+  }
+}
+// One 64-element k-block (nk = 1..4 k-steps of 16): main accumulator += P_hi * Q_hi; in fp32-parity mode (kPlanes == 2) also the cross-term
+// accumulator += P_hi * Q_lo + P_lo * Q_hi. `main_acc` / `x_acc` = 0 makes the first k-step overwrite its accumulator (start of a chunk).
+template <int kPlanes, bool k2>
+__device__ __forceinline__ void issue_kblock(uint32_t tmem_d, uint32_t tmem_x, uint32_t p_hi, uint32_t p_lo, uint32_t q_hi, uint32_t q_lo, uint32_t idesc,
+                                             uint32_t main_acc, uint32_t x_acc, int nk) {
+  if (nk == 4) {  // the common case: straight-line, no predicates
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      umma_f16_lo<k2>(tmem_d, p_hi + 2 * k, q_hi + 2 * k, idesc, k == 0 ? main_acc : 1u);
+      if (kPlanes == 2) {
+        umma_f16_lo<k2>(tmem_x, p_hi + 2 * k, q_lo + 2 * k, idesc, k == 0 ? x_acc : 1u);
+        umma_f16_lo<k2>(tmem_x, p_lo + 2 * k, q_hi + 2 * k, idesc, 1u);
+      }
+    }
+  } else {
+    for (int k = 0; k < nk; ++k) {
+      umma_f16_lo<k2>(tmem_d, p_hi + 2 * k, q_hi + 2 * k, idesc, k == 0 ? main_acc : 1u);
+      if (kPlanes == 2) {
+        umma_f16_lo<k2>(tmem_x, p_hi + 2 * k, q_lo + 2 * k, idesc, k == 0 ? x_acc : 1u);
+        umma_f16_lo<k2>(tmem_x, p_lo + 2 * k, q_hi + 2 * k, idesc, 1u);
+      }
+    }
+  }
+}
+
 // Instruction descriptor for kind::f16: fp32 accumulate, both operands K-major.
 // ab_format: 0 = fp16, 1 = bf16.
 __host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t ab_format, uint32_t M, uint32_t N) {
