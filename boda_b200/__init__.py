@@ -56,6 +56,7 @@ _SIGS = {
     "b200_rtc_copy_from_var": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_char_p, _c.c_uint64]),
     "b200_rtc_get_var_raw_native_pointer": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.POINTER(_c.c_void_p)]),
     "b200_rtc_launches": (_c.c_uint64, [_c.c_void_p]),
+    "b200_pipe_describe": (_c.c_int64, [_c.c_char_p, _c.c_char_p, _c.c_uint64]),
     "b200_fwd_create": (_c.c_void_p, [_c.c_char_p, _c.c_char_p]),
     "b200_fwd_destroy": (None, [_c.c_void_p]),
     "b200_fwd_set_param": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_void_p, _c.c_uint64]),
@@ -102,6 +103,25 @@ def _chk(rc: int) -> int:
 
 def _b(s: str) -> bytes:
     return s.encode()
+
+
+def pipe_describe(pipe_text: str) -> Dict[str, object]:
+    """Host-only (no GPU): parse a conv_pipe text with the C++ graph IR and return {"nodes": {name: ((dim, size), ...)}, "params": [names],
+    "ops": n, "conv_flops": f} after the dims inference of conv_pipe_t::calc_dims (src/conv_util.cc:405-529)."""
+    need = _chk(lib().b200_pipe_describe(_b(pipe_text), None, 0))
+    buf = ctypes.create_string_buffer(need + 1)
+    _chk(lib().b200_pipe_describe(_b(pipe_text), buf, need + 1))
+    nodes, params, res = {}, [], {}
+    for line in buf.value.decode().splitlines():
+        parts = line.split(" ")
+        if parts[0] == "ops":
+            res["ops"], res["conv_flops"] = int(parts[1]), int(parts[3])
+            continue
+        nodes[parts[0]] = tuple((d.split("=")[0], int(d.split("=")[1])) for d in parts[1].split(":"))
+        if len(parts) > 2 and parts[2] == "param":
+            params.append(parts[0])
+    res["nodes"], res["params"] = nodes, params
+    return res
 
 
 def _str_array(items: Sequence[str]):

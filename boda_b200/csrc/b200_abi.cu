@@ -116,6 +116,27 @@ B200_API int b200_rtc_get_var_raw_native_pointer(b200_rtc *r, const char *vn, vo
 }
 B200_API uint64_t b200_rtc_launches(b200_rtc *r) { return r->rtc->launches(); }
 
+// ---- host-only pipe description ----
+B200_API int64_t b200_pipe_describe(const char *pipe_text, char *buf, uint64_t buf_len) {
+  int64_t need = -1;
+  int const rc = guarded([&] {
+    p_conv_pipe_t cp = make_conv_pipe_from_text(pipe_text);
+    string out;
+    for (auto const &kv : cp->nodes) {
+      out += kv.first + " ";
+      dims_t const &d = kv.second->dims;
+      for (size_t i = 0; i < d.size(); ++i) { out += (i ? ":" : "") + d[i].name + "=" + str(d[i].sz); }
+      if (kv.second->is_param) { out += " param"; }
+      out += "\n";
+    }
+    out += "ops " + str(cp->ops.size()) + " conv_flops " + str(cp->total_conv_flops()) + "\n";
+    need = (int64_t)out.size();
+    if (buf && buf_len) { snprintf(buf, buf_len, "%s", out.c_str()); }
+    return 0;
+  });
+  return rc == 0 ? need : rc;
+}
+
 // ---- tier B ----
 B200_API b200_fwd *b200_fwd_create(const char *pipe_text, const char *opts) {
   b200_fwd *f = nullptr;

@@ -43,7 +43,7 @@ struct packed_t {
   long long rows = 0, row_stride = 0;  // elements
 };
 
-enum func_kind_t { FK_CONV, FK_SGEMM, FK_POOL, FK_LRN, FK_RELU, FK_SOFTMAX, FK_COPY, FK_REDUCE, FK_GEN_DATA };
+enum func_kind_t { FK_CONV, FK_SGEMM, FK_POOL, FK_LRN, FK_RELU, FK_SOFTMAX, FK_COPY, FK_REDUCE, FK_GEN_DATA, FK_BN_FOLD };
 
 struct conv_plan_t {
   int N, C, H, W, OC, KH, KW, sy, sx, py, px, OH, OW;
@@ -320,6 +320,7 @@ func_kind_t resolve_kind(op_base_t const &op, string &gen_arg) {
   if (fn == "softmax") { return FK_SOFTMAX; }
   if (fn == "copy") { return FK_COPY; }
   if (fn == "reduce") { return FK_REDUCE; }
+  if (fn == "bn_fold") { return FK_BN_FOLD; }
   unsup_err("be=b200: unknown function '" + fn + "'");
 }
 
@@ -990,9 +991,32 @@ struct run_ctx_t {
       a.ins[i] = fptr(vi);
     }
     long long const n = vout.dims.dims_prod();
-    B200_CARVEOUT_ONCE(b200::reduce_sum_kernel); launch_k(b200::reduce_sum_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, a, fptr(vout), n);
+    B200_CARVEOUT_ONCE(b200::reduce_sum_kernel); launch_k(b200::reduce_sum_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, a, fptr(vout), n, (int)scalar("relu", true, 0), absmax_cell("out"));
     launched();
     im.bump(vout);
+  }
+
+  // parameter-only: fold BatchNorm (use_global_stats) / Scale into a convolution's filters and biases (pointwise.cuh: bn_fold_kernel)
+  void run_bn_fold() {
+    var_info_t &vf = var("filts"), &vof = var("out_filts"), &vob = var("out_biases");
+    if (!(vf.dims == vof.dims)) { rt_err("bn_fold: out_filts dims differ from filts"); }
+    int const OC = vf.dims.dsz("out_chan");
+    if ((int)vob.dims.dims_prod() != OC) { rt_err("bn_fold: out_biases size mismatch"); }
+    auto opt = [&](char const *an, uint64_t want) -> float const * {
+      if (!has_arg(an)) { return nullptr; }
+      var_info_t &v = var(an);
+      if (v.dims.dims_prod() != want) { rt_err(string("bn_fold: '") + an + "' has " + str(v.dims.dims_prod()) + " elements, expected " + str(want)); }
+      return fptr(v);
+    };
+    float const *biases = opt("biases", OC), *mean = opt("mean", OC), *varp = opt("var", OC), *sf = opt("sf", 1), *gamma = opt("gamma", OC), *beta = opt("beta", OC);
+    if ((mean != nullptr) != (varp != nullptr) || (mean != nullptr) != (sf != nullptr)) { rt_err("bn_fold: mean, var and sf come together"); }
+    if ((gamma != nullptr) != (beta != nullptr)) { rt_err("bn_fold: gamma and beta come together"); }
+    long long const per_oc = (long long)(vf.dims.dims_prod() / OC);
+    B200_CARVEOUT_ONCE(b200::bn_fold_kernel);
+    launch_k(b200::bn_fold_kernel, dim3(ceil_div(per_oc, 256), OC), dim3(256), 0, fptr(vf), biases, mean, varp, sf, gamma, beta, (float)scalar("eps", true, 1e-5), fptr(vof), fptr(vob), per_oc);
+    launched();
+    im.bump(vof);
+    im.bump(vob);
   }
 
   void run_gen_data() {  // test/rtc/gen_data_*.cucl; the generator's name carries the op type and the argument
@@ -1039,6 +1063,7 @@ uint32_t b200_compute_t::run(rtc_func_call_t const &rfc) {
     case FK_COPY: ctx.run_copy(); break;
     case FK_REDUCE: ctx.run_reduce(); break;
     case FK_GEN_DATA: ctx.run_gen_data(); break;
+    case FK_BN_FOLD: ctx.run_bn_fold(); break;
   }
   if (impl->timing) { CU_CHK(cudaEventRecord(ev.e, impl->stream)); }
   impl->calls.push_back(ev);

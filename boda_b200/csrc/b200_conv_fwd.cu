@@ -48,10 +48,20 @@ void conv_pipe_t::add_op_from_lexp(lexp_t const &l) {
   if (!op->has_type()) { rt_err("Operation has no type field; can't determine type."); }
   for (auto const &o : ops) { if (o->tag == op->tag) { rt_err("pipe: duplicate op tag '" + op->tag + "'"); } }
   op->in_place = (op->bots.size() == 1 && op->tops.size() == 1 && op->bots[0] == op->tops[0]);
-  if (op->is("Convolution")) {  // filts / biases are implicit parameter nodes named <tag>_filts / <tag>_biases (src/conv_util.cc:270-293)
-    if (op->bots.size() == 1) { op->bots.push_back(op->tag + "_filts"); op->bots.push_back(op->tag + "_biases"); }
-    if (op->bots.size() != 3) { rt_err("Convolution '" + op->tag + "' needs bots in[:filts:biases]"); }
+  if (op->is("InnerProduct")) {  // an inner product is the convolution whose window is the whole input (the reference reads it as such, src/caffepb.cc:276-279)
+    op->set_type("Convolution");
+    op->set_u32("is_inner_product", 1);
   }
+  if (op->is("Convolution")) {  // filts / biases are implicit parameter nodes named <tag>_filts / <tag>_biases (src/conv_util.cc:270-293)
+    bool const bias_term = !op->has("bias_term") || op->get_u32("bias_term") != 0;  // Caffe convolution_param.bias_term (ResNet: false)
+    if (op->bots.size() == 1) { op->bots.push_back(op->tag + "_filts"); if (bias_term) { op->bots.push_back(op->tag + "_biases"); } }
+    if (op->bots.size() != (bias_term ? 3u : 2u)) { rt_err("Convolution '" + op->tag + "' needs bots in[:filts[:biases]]"); }
+  }
+  // BatchNorm (use_global_stats) and Scale are in-place per-channel affine ops with their own parameter nodes (Caffe blob order):
+  //   BatchNorm: <tag>_mean, <tag>_var (chan), <tag>_sf (1: the moving-average scale factor); Scale: <tag>_gamma, <tag>_beta (chan)
+  if (op->is("BatchNorm") && op->bots.size() == 1) { for (char const *sfx : {"_mean", "_var", "_sf"}) { op->bots.push_back(op->tag + sfx); } }
+  if (op->is("Scale") && op->bots.size() == 1) { for (char const *sfx : {"_gamma", "_beta"}) { op->bots.push_back(op->tag + sfx); } }
+  if (op->is("BatchNorm") || op->is("Scale")) { op->in_place = (op->tops.size() == 1 && op->bots[0] == op->tops[0]); }
   for (auto const &b : op->bots) { get_or_make_node(b)->bot_for.push_back(op->tag); }
   for (auto const &t : op->tops) {
     p_conv_node_t tn = get_or_make_node(t);
@@ -63,23 +73,40 @@ void conv_pipe_t::add_op_from_lexp(lexp_t const &l) {
 
 void conv_pipe_t::calc_dims() {
   for (auto const &op : ops) {
-    if (op->in_place) { if (must_get_node(op->bots[0])->dims.empty()) { rt_err("pipe: in-place op '" + op->tag + "' on node without dims"); } continue; }
+    if (op->in_place) {
+      dims_t const &d = must_get_node(op->bots[0])->dims;
+      if (d.empty()) { rt_err("pipe: in-place op '" + op->tag + "' on node without dims"); }
+      if (op->is("BatchNorm") || op->is("Scale")) {  // per-channel parameter nodes
+        for (size_t i = 1; i < op->bots.size(); ++i) {
+          p_conv_node_t pn = must_get_node(op->bots[i]);
+          bool const scalar = (op->is("BatchNorm") && i == 3);
+          pn->dims = dims_t({scalar ? 1u : d.dsz("chan")}, {scalar ? "v" : "chan"}, "float");
+          if (!pn->is_param) { pn->is_param = true; param_names.push_back(pn->name); }
+        }
+      }
+      continue;
+    }
+    if (op->is("BatchNorm") || op->is("Scale")) { rt_err("'" + op->tag + "': only in-place BatchNorm / Scale (folded into the producing Convolution) are supported"); }
     dims_t const &din = must_get_node(op->bots[0])->dims;
     if (din.empty()) { rt_err("pipe: op '" + op->tag + "' reads node '" + op->bots[0] + "' before it has dims (ops must be in topological order)"); }
     uint32_t const N = din.dsz("img"), C = din.dsz("chan"), H = din.dsz("y"), W = din.dsz("x");
     dims_t dout;
     if (op->is("Convolution")) {
+      if (op->has("is_inner_product")) { op->set_dims("kern_sz", dims_t({H, W}, {"y", "x"}, "none")); }
       uint32_t const KH = op->yx("kern_sz", "y", 0), KW = op->yx("kern_sz", "x", 0);
       if (!KH || !KW) { rt_err("Convolution '" + op->tag + "' needs kern_sz"); }
       uint32_t const sy = op->yx("stride", "y", 1), sx = op->yx("stride", "x", 1), py = op->yx("in_pad", "y", 0), px = op->yx("in_pad", "x", 0);
       uint32_t const OC = op->get_u32("out_chans");
       if (H + 2 * py < KH || W + 2 * px < KW) { rt_err("Convolution '" + op->tag + "': padded input smaller than kernel"); }
       dout = dims_t({N, OC, (H + 2 * py - KH) / sy + 1, (W + 2 * px - KW) / sx + 1}, {"img", "chan", "y", "x"}, "float");
-      p_conv_node_t fn = must_get_node(op->bots[1]), bn = must_get_node(op->bots[2]);
+      p_conv_node_t fn = must_get_node(op->bots[1]);
       fn->dims = dims_t({OC, C, KH, KW}, {"out_chan", "in_chan", "y", "x"}, "float");
-      bn->dims = dims_t({OC}, {"out_chan"}, "float");
       if (!fn->is_param) { fn->is_param = true; param_names.push_back(fn->name); }
-      if (!bn->is_param) { bn->is_param = true; param_names.push_back(bn->name); }
+      if (op->bots.size() > 2) {
+        p_conv_node_t bn = must_get_node(op->bots[2]);
+        bn->dims = dims_t({OC}, {"out_chan"}, "float");
+        if (!bn->is_param) { bn->is_param = true; param_names.push_back(bn->name); }
+      }
     } else if (op->is("Pooling")) {
       if (op->has("kern_sz")) {  // Caffe: any partial window makes an output (src/conv_util.cc:198-204)
         uint32_t const KH = op->yx("kern_sz", "y", 1), KW = op->yx("kern_sz", "x", 1), sy = op->yx("stride", "y", 1), sx = op->yx("stride", "x", 1);
@@ -174,16 +201,57 @@ void b200_conv_fwd_t::gen_op(p_conv_op_t const &op) {
   fop.str_vals = op->str_vals;
   fop.nda_vals = op->nda_vals;
   if (op->is("Convolution")) {
+    dims_t const &fd = cp->must_get_node(op->bots[1])->dims;
+    dims_t const bd({fd.dsz("out_chan")}, {"out_chan"}, "float");
     fop.set_dims("in", cp->must_get_node(op->bots[0])->dims);
-    fop.set_dims("filts", cp->must_get_node(op->bots[1])->dims);
-    fop.set_dims("biases", cp->must_get_node(op->bots[2])->dims);
+    fop.set_dims("filts", fd);
+    fop.set_dims("biases", bd);
     fop.set_dims("out", cp->must_get_node(op->tops[0])->dims);
-    // conv+ReLU fusion: only if ReLU is the FIRST in-place op on the conv's output node (src/rtc_fwd.cc:486-494)
     p_conv_node_t on = cp->must_get_node(op->tops[0]);
+    // Leading in-place BatchNorm / Scale ops on the conv's output are per-out-channel affine maps: fold them into the filters and biases
+    // (the reference only stubs these layers, src/caffepb.cc:231-232). The fold runs on the device whenever the
+    // parameters change (prep_calls), writing <tag>_filts__folded / <tag>_biases__folded, which the convolution then reads.
+    size_t n_aff = 0;
+    p_conv_op_t bn_op, sc_op;
+    while (n_aff < on->in_place_ops.size() && (on->in_place_ops[n_aff]->is("BatchNorm") || on->in_place_ops[n_aff]->is("Scale"))) {
+      p_conv_op_t const &a = on->in_place_ops[n_aff];
+      if (a->is("BatchNorm")) { if (bn_op || sc_op) { break; } bn_op = a; } else { if (sc_op) { break; } sc_op = a; }
+      a->fused = true;
+      ++n_aff;
+    }
+    string filts_vn = op->bots[1], biases_vn = op->bots.size() > 2 ? op->bots[2] : string();
+    if (bn_op || sc_op) {
+      string const ff = op->tag + "_filts__folded", bf = op->tag + "_biases__folded";
+      rtc->create_var_with_dims(ff, fd);
+      rtc->create_var_with_dims(bf, bd);
+      op_base_t pop;
+      pop.set_type("bn_fold");
+      pop.set_dims("filts", fd);
+      float const eps = (bn_op && bn_op->has("eps")) ? (float)nda_scalar_as_double(*bn_op->get("eps")) : 1e-5f;  // Caffe batch_norm_param.eps default
+      pop.set("eps", make_scalar_nda<float>(eps, "float"));
+      map_str_rtc_arg_t pargs{{"filts", filts_vn}, {"out_filts", ff}, {"out_biases", bf}};
+      if (!biases_vn.empty()) { pargs["biases"] = biases_vn; }
+      if (bn_op) { pargs["mean"] = bn_op->bots[1]; pargs["var"] = bn_op->bots[2]; pargs["sf"] = bn_op->bots[3]; }
+      if (sc_op) { pargs["gamma"] = sc_op->bots[1]; pargs["beta"] = sc_op->bots[2]; }
+      fwd_call_t pc;
+      pc.tag = op->tag;
+      pc.func_name = "bn_fold__" + op->tag;
+      rtc_func_info_t fi;
+      fi.func_name = pc.func_name;
+      fi.op = pop;
+      fi.op.set_func_name("bn_fold");
+      rtc->compile({fi}, rtc_compile_opts_t());
+      pc.rfc.rtc_func_name = pc.func_name;
+      pc.rfc.arg_map = pargs;
+      prep_calls.push_back(pc);
+      filts_vn = ff; biases_vn = bf;
+    }
+    // conv+ReLU fusion: only if ReLU is the FIRST remaining in-place op on the conv's output node (src/rtc_fwd.cc:486-494)
     bool relu = false;
-    if (!on->in_place_ops.empty() && on->in_place_ops[0]->is("ReLU")) { relu = true; on->in_place_ops[0]->fused = true; }
+    if (on->in_place_ops.size() > n_aff && on->in_place_ops[n_aff]->is("ReLU")) { relu = true; on->in_place_ops[n_aff]->fused = true; }
     fop.set_u32("conv_has_relu", relu ? 1 : 0);
-    map_str_rtc_arg_t args{{"in", op->bots[0]}, {"filts", op->bots[1]}, {"biases", op->bots[2]}, {"out", op->tops[0]}};
+    map_str_rtc_arg_t args{{"in", op->bots[0]}, {"filts", filts_vn}, {"out", op->tops[0]}};
+    if (!biases_vn.empty()) { args["biases"] = biases_vn; }
     add_absmax_args(args, "in", op->bots[0]);
     add_absmax_args(args, "out", op->tops[0]);
     add_call("conv", *op, fop, args);
@@ -213,10 +281,18 @@ void b200_conv_fwd_t::gen_op(p_conv_op_t const &op) {
       add_call("copy", *op, cop, args);
       chans_out_done += cp->must_get_node(b)->dims.dsz("chan");
     }
+  } else if (op->is("BatchNorm") || op->is("Scale")) {
+    rt_err("'" + op->tag + "': BatchNorm / Scale must directly follow (in place) the Convolution they are folded into");
   } else if (op->is("Eltwise") || op->is("Reduce")) {
     map_str_rtc_arg_t args{{"out", op->tops[0]}};
     for (size_t i = 0; i < op->bots.size(); ++i) { args["ins_" + str(i)] = op->bots[i]; }
     fop.set_u32("ins_num", (uint32_t)op->bots.size());
+    // sum + ReLU fusion, same rule as conv + ReLU: the ReLU must be the first in-place op on the output node (ResNet residual joins)
+    p_conv_node_t on = cp->must_get_node(op->tops[0]);
+    bool relu = false;
+    if (!on->in_place_ops.empty() && on->in_place_ops[0]->is("ReLU")) { relu = true; on->in_place_ops[0]->fused = true; }
+    fop.set_u32("relu", relu ? 1 : 0);
+    add_absmax_args(args, "out", op->tops[0]);
     add_call("reduce", *op, fop, args);
   } else {
     rt_err("gen_op: unhandled op of type: " + op->get_type());  // src/rtc_fwd.cc:402-404
@@ -258,7 +334,7 @@ void b200_conv_fwd_t::init(p_conv_pipe_t const &cp_, string const &opts) {
     if (n.top_for.size() != 1) { continue; }
     p_conv_op_t writer;
     for (auto const &o : cp->ops) { if (o->tag == n.top_for[0]) { writer = o; } }
-    if (!writer || !(writer->is("Convolution") || writer->is("Pooling") || writer->is("LRN") || writer->is("Concat"))) { continue; }
+    if (!writer || !(writer->is("Convolution") || writer->is("Pooling") || writer->is("LRN") || writer->is("Concat") || writer->is("Eltwise") || writer->is("Reduce"))) { continue; }
     bool feeds_conv = false;
     for (auto const &o : cp->ops) { if (o->is("Convolution") && !o->bots.empty() && o->bots[0] == n.name) { feeds_conv = true; } }
     if (feeds_conv) { uint32_t const ix = (uint32_t)absmax_ix.size(); absmax_ix[n.name] = ix; }
@@ -292,6 +368,7 @@ void b200_conv_fwd_t::ensure_graph() {
     touch_sources();  // first pass eager: allocates packed-operand buffers, packs weights, sets kernel attributes
     uint64_t const l0 = rtc->launches();
     rtc->set_timing(false);
+    for (auto const &c : prep_calls) { rtc->run(c.rfc); }  // parameter-only work (BatchNorm / Scale folding): once per weight version
     run_calls();
     rtc->finish_and_sync();
     run_calls();  // second pass = steady state (weights cached): count kernels per forward

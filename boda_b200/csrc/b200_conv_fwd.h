@@ -47,6 +47,7 @@ struct b200_conv_fwd_t {
   p_b200_compute_t rtc;
   p_conv_pipe_t cp;
   vector<fwd_call_t> fwd_calls;
+  vector<fwd_call_t> prep_calls;  // run once per weight version, outside the forward (BatchNorm / Scale folding into the conv parameters)
   string info_log;
 
   b200_conv_fwd_t();

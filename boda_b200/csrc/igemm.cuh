@@ -101,17 +101,31 @@ __device__ __forceinline__ float igemm_store_row(float const (&acc)[BN], float i
     }
     return fmaxf(fmaxf(am0, am1), fmaxf(am2, am3));
   }
+  // ragged tile (out_chans not a multiple of BN): whole groups of four columns take the same straight-line path (nvalid is CTA-uniform, so
+  // the branch does not diverge), the last partial group is guarded per element
   float amax = 0.0f;
 #pragma unroll
-  for (int j = 0; j < BN; ++j) {
-    if (j < nvalid) {
-      float b;
-      asm("ld.shared.f32 %0, [%1];" : "=f"(b) : "r"(bias_sa + 4 * j));  // LDS with an immediate offset (the generic pointer would compile to LD.E)
-      float const v = fmaxf(fmaf(acc[j], inv, b), floor_v);
-      amax = fmaxf(amax, fabsf(v));
-      *o = v;
+  for (int j = 0; j < BN; j += 4) {
+    if (j + 4 <= nvalid) {
+      float b0, b1, b2, b3;
+      asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3) : "r"(bias_sa + 4 * j));
+      float const v0 = fmaxf(fmaf(acc[j], inv, b0), floor_v), v1 = fmaxf(fmaf(acc[j + 1], inv, b1), floor_v);
+      float const v2 = fmaxf(fmaf(acc[j + 2], inv, b2), floor_v), v3 = fmaxf(fmaf(acc[j + 3], inv, b3), floor_v);
+      o[0] = v0; o[stride] = v1; o[2 * stride] = v2; o[3 * stride] = v3;
+      amax = fmaxf(fmaxf(amax, fmaxf(fabsf(v0), fabsf(v1))), fmaxf(fabsf(v2), fabsf(v3)));
+    } else {
+#pragma unroll
+      for (int jj = j; jj < j + 4; ++jj) {
+        if (jj < nvalid) {
+          float b;
+          asm("ld.shared.f32 %0, [%1];" : "=f"(b) : "r"(bias_sa + 4 * jj));  // LDS with an immediate offset (the generic pointer would compile to LD.E)
+          float const v = fmaxf(fmaf(acc[jj], inv, b), floor_v);
+          amax = fmaxf(amax, fabsf(v));
+          o[(jj - j) * stride] = v;
+        }
+      }
     }
-    o += stride;
+    o += 4 * stride;
   }
   return amax;
 }

@@ -124,13 +124,40 @@ __global__ void concat_copy_kernel(float const *__restrict__ in, float *__restri
 
 // ---- reduce: N-ary elementwise sum (test/rtc/reduce.cucl) ------------------------------------------------------
 struct ReduceArgs { float const *ins[8]; int ins_num; };
-__global__ void reduce_sum_kernel(ReduceArgs a, float *__restrict__ out, long long n) {
+// relu != 0 fuses the in-place ReLU that follows a residual join (Eltwise SUM + ReLU in ResNet); the sum order is the reference's.
+__global__ void reduce_sum_kernel(ReduceArgs a, float *__restrict__ out, long long n, int relu, unsigned int *out_absmax) {
   pdl_prologue();
   long long const i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (i >= n) { return; }
   float v = 0;
-  for (int j = 0; j < a.ins_num; ++j) { v += __ldg(a.ins[j] + i); }
-  out[i] = v;
+  if (i < n) {
+    for (int j = 0; j < a.ins_num; ++j) { v += __ldg(a.ins[j] + i); }
+    if (relu) { v = (v <= 0) ? 0.0f : v; }
+    out[i] = v;
+  }
+  if (out_absmax) { publish_absmax_warp(fabsf(v), out_absmax); }
+}
+
+// ---- BatchNorm / Scale folding (parameter-only) ---------------------------------------------------------------
+// conv -> BatchNorm(use_global_stats) -> Scale is   y = gamma * ((W.x + bias) - mean/sf) / sqrt(var/sf + eps) + beta   (Caffe semantics:
+// the stored mean / var blobs are divided by the moving-average scale factor blob sf, 0 -> 0), i.e. a convolution with
+//   W'[oc] = W[oc] * a[oc],  b'[oc] = (bias[oc] - mean[oc]/sf) * a[oc] + beta[oc],  a[oc] = gamma[oc] / sqrt(var[oc]/sf + eps).
+// Any of {biases, (mean,var,sf), (gamma,beta)} may be absent (null). grid = (ceil(per_oc / 256), out_chans).
+__global__ void bn_fold_kernel(float const *__restrict__ filts, float const *__restrict__ biases, float const *__restrict__ mean, float const *__restrict__ var,
+                               float const *__restrict__ sf, float const *__restrict__ gamma, float const *__restrict__ beta, float eps,
+                               float *__restrict__ out_filts, float *__restrict__ out_biases, long long per_oc) {
+  pdl_prologue();
+  int const oc = blockIdx.y;
+  float s = 1.0f, m = 0.0f, inv_std = 1.0f;
+  if (mean) {
+    float const f = __ldg(sf);
+    s = (f == 0.0f) ? 0.0f : __fdiv_rn(1.0f, f);
+    m = __ldg(mean + oc) * s;
+    inv_std = __fdiv_rn(1.0f, __fsqrt_rn(__ldg(var + oc) * s + eps));
+  }
+  float const a = (gamma ? __ldg(gamma + oc) : 1.0f) * inv_std;
+  long long const i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < per_oc) { out_filts[oc * per_oc + i] = __ldg(filts + oc * per_oc + i) * a; }
+  if (i == 0) { out_biases[oc] = ((biases ? __ldg(biases + oc) : 0.0f) - m) * a + (beta ? __ldg(beta + oc) : 0.0f); }
 }
 
 // ---- pool (test/rtc/pool.cucl:13-40) --------------------------------------------------------------------------

@@ -23,13 +23,28 @@ class PipeBuilder:
         self.lines.append("(node=%s,dims=(img=%d,chan=%d,y=%d,x=%d))" % (name, img, chan, y, x))
         return name
 
-    def conv(self, tag: str, bot: str, top: str, out_chans: int, k, stride=1, pad=0, relu: Optional[str] = None):
+    def conv(self, tag: str, bot: str, top: str, out_chans: int, k, stride=1, pad=0, relu: Optional[str] = None, bias: bool = True):
         ky, kx = (k, k) if isinstance(k, int) else k
         self.lines.append(
             "(tag=%s,str_vals=(type=Convolution),nda_vals=(kern_sz=(tn=none,dims=(y=%d,x=%d)),stride=(tn=none,dims=(y=%d,x=%d)),"
-            "in_pad=(tn=none,dims=(y=%d,x=%d)),out_chans=(tn=uint32_t,v=%d)),bots=%s,tops=%s)" % (tag, ky, kx, stride, stride, pad, pad, out_chans, bot, top))
+            "in_pad=(tn=none,dims=(y=%d,x=%d)),out_chans=(tn=uint32_t,v=%d)%s),bots=%s,tops=%s)"
+            % (tag, ky, kx, stride, stride, pad, pad, out_chans, "" if bias else ",bias_term=(tn=uint32_t,v=0)", bot, top))
         if relu:
             self.relu(relu, top)
+        return top
+
+    def batch_norm(self, tag: str, node: str, eps: float = 1e-5):
+        """Caffe BatchNorm with use_global_stats (in place): params <tag>_mean, <tag>_var (chan) and <tag>_sf (1)."""
+        self.lines.append("(tag=%s,str_vals=(type=BatchNorm),nda_vals=(eps=(tn=float,v=%r)),bots=%s,tops=%s)" % (tag, float(eps), node, node))
+        return node
+
+    def scale(self, tag: str, node: str):
+        """Caffe Scale with bias_term (in place): params <tag>_gamma, <tag>_beta (chan)."""
+        self.lines.append("(tag=%s,str_vals=(type=Scale),bots=%s,tops=%s)" % (tag, node, node))
+        return node
+
+    def inner_product(self, tag: str, bot: str, top: str, out_chans: int):
+        self.lines.append("(tag=%s,str_vals=(type=InnerProduct),nda_vals=(out_chans=(tn=uint32_t,v=%d)),bots=%s,tops=%s)" % (tag, out_chans, bot, top))
         return top
 
     def relu(self, tag: str, node: str):
@@ -169,6 +184,79 @@ def googlenet_conv(batch: int = 64, in_sz: int = 224) -> Tuple[str, str, str]:
     return p.text(), "data", "cls3_fc"
 
 
+def resnet50(batch: int = 32, in_sz: int = 224, stages=(3, 4, 6, 3)) -> Tuple[str, str, str]:
+    """nets/resnet-50/train_val.prototxt (BASELINE config C5): 7x7/2 stem, max pool, 16 bottleneck blocks (1x1 -> 3x3 -> 1x1, stride 2 on the
+    first 1x1 of stages 3-5, projection shortcut on the first block of every stage), every Convolution (bias_term false except conv1)
+    followed in place by BatchNorm(use_global_stats) + Scale(bias_term), Eltwise SUM + ReLU joins, 7x7 average pool, InnerProduct(1000), Softmax.
+    The reference cannot run this net (its BatchNorm / Scale / Eltwise readers are stubs, src/caffepb.cc:231-232,308); SURVEY section 8 f4."""
+    p = PipeBuilder()
+    p.data("data", batch, 3, in_sz, in_sz)
+
+    def cbs(name, bn_suffix, bot, oc, k, stride=1, pad=0, relu=True, bias=False):
+        p.conv(name, bot, name, oc, k, stride, pad, bias=bias)
+        p.batch_norm("bn" + bn_suffix, name)
+        p.scale("scale" + bn_suffix, name)
+        if relu:
+            p.relu(name + "_relu", name)
+        return name
+
+    cbs("conv1", "_conv1", "data", 64, 7, 2, 3, bias=True)
+    p.pool("pool1", "conv1", "pool1", 3, 2)
+    prev, width = "pool1", 64
+    for si, n_blocks in enumerate(stages):
+        stage = si + 2
+        for b in range(n_blocks):
+            blk = "%d%s" % (stage, "abcdefgh"[b])
+            stride = 2 if (b == 0 and stage > 2) else 1
+            if b == 0:
+                short = cbs("res%s_branch1" % blk, blk + "_branch1", prev, width * 4, 1, stride, 0, relu=False)
+            else:
+                short = prev
+            x = cbs("res%s_branch2a" % blk, blk + "_branch2a", prev, width, 1, stride, 0)
+            x = cbs("res%s_branch2b" % blk, blk + "_branch2b", x, width, 3, 1, 1)
+            x = cbs("res%s_branch2c" % blk, blk + "_branch2c", x, width * 4, 1, 1, 0, relu=False)
+            p.eltwise("res%s" % blk, [short, x], "res%s" % blk)
+            p.relu("res%s_relu" % blk, "res%s" % blk)
+            prev = "res%s" % blk
+        width *= 2
+    p.pool("pool5", prev, "pool5", 7, 1, 0, avg=True)
+    p.inner_product("fc1000", "pool5", "fc1000", 1000)
+    p.softmax("prob", "fc1000", "prob")
+    return p.text(), "data", "prob"
+
+
+def tiny_resnet(batch: int = 2) -> Tuple[str, str, str]:
+    """Two-stage miniature of resnet50 (same op kinds and wiring, 33x33 input) small enough for the CPU oracle."""
+    p = PipeBuilder()
+    p.data("data", batch, 3, 33, 33)
+
+    def cbs(name, bot, oc, k, stride=1, pad=0, relu=True, bias=False, bn=True, sc=True):
+        p.conv(name, bot, name, oc, k, stride, pad, bias=bias)
+        if bn:
+            p.batch_norm("bn_" + name, name)
+        if sc:
+            p.scale("scale_" + name, name)
+        if relu:
+            p.relu(name + "_relu", name)
+        return name
+
+    cbs("conv1", "data", 16, 7, 2, 3, bias=True)
+    p.pool("pool1", "conv1", "pool1", 3, 2)
+    prev = "pool1"
+    for blk, (width, stride, proj) in {"2a": (8, 1, True), "2b": (8, 1, False), "3a": (16, 2, True)}.items():
+        short = cbs("res%s_branch1" % blk, prev, width * 4, 1, stride, 0, relu=False) if proj else prev
+        x = cbs("res%s_branch2a" % blk, prev, width, 1, stride, 0)
+        x = cbs("res%s_branch2b" % blk, x, width, 3, 1, 1, bn=(blk != "2b"))       # a Scale-only fold
+        x = cbs("res%s_branch2c" % blk, x, width * 4, 1, 1, 0, relu=False, sc=(blk != "3a"))  # a BatchNorm-only fold
+        p.eltwise("res%s" % blk, [short, x], "res%s" % blk)
+        p.relu("res%s_relu" % blk, "res%s" % blk)
+        prev = "res%s" % blk
+    p.pool("pool5", prev, "pool5", None, avg=True)
+    p.inner_product("fc", "pool5", "fc", 10)
+    p.softmax("prob", "fc", "prob")
+    return p.text(), "data", "prob"
+
+
 def tiny_net(batch: int = 3) -> Tuple[str, str, str]:
     """A small net touching every forward op kind (conv variants, LRN, max/avg/global pool, concat, eltwise, softmax)."""
     p = PipeBuilder()
@@ -211,44 +299,83 @@ def hash_fill(shape, salt: int, scale: float) -> np.ndarray:
 
 
 def conv_param_shapes(pipe_text: str) -> Dict[str, Tuple[int, ...]]:
-    """Walk the pipe text and return {<tag>_filts: (OC,C,KH,KW), <tag>_biases: (OC,)} with channel counts inferred."""
+    """Walk the pipe text (dims inferred with the reference's size rules, src/conv_util.cc:167-226) and return the shape of every parameter
+    node: <tag>_filts (OC,C,KH,KW), <tag>_biases (OC,) [absent when bias_term=0], BatchNorm <tag>_mean / _var (C,) and _sf (1,), Scale
+    <tag>_gamma / _beta (C,). An InnerProduct is the convolution whose window is its whole input."""
     import re
-    chans: Dict[str, int] = {}
+    dims: Dict[str, Tuple[int, int, int]] = {}  # node -> (chan, y, x)
     shapes: Dict[str, Tuple[int, ...]] = {}
+
+    def yx(line, name, dflt):
+        m = re.search(name + r"=\(tn=none,dims=\(y=(\d+),x=(\d+)\)\)", line)
+        return (int(m.group(1)), int(m.group(2))) if m else dflt
+
     for line in pipe_text.splitlines():
         line = line.strip()
-        if not line:
+        if not line or line.startswith("#"):
             continue
         m = re.match(r"\(node=([^,]+),dims=\(img=(\d+),chan=(\d+),y=(\d+),x=(\d+)\)\)", line)
         if m:
-            chans[m.group(1)] = int(m.group(3))
+            dims[m.group(1)] = (int(m.group(3)), int(m.group(4)), int(m.group(5)))
             continue
         tag = re.search(r"tag=([^,]+),", line).group(1)
         typ = re.search(r"type=([A-Za-z]+)", line).group(1)
         bots = re.search(r"bots=([^,)]+)", line).group(1).split(":")
         tops = re.search(r"tops=([^,)]+)", line).group(1).split(":")
-        if typ == "Convolution":
+        c, h, w = dims[bots[0]]
+        if typ in ("Convolution", "InnerProduct"):
             oc = int(re.search(r"out_chans=\(tn=uint32_t,v=(\d+)\)", line).group(1))
-            ky, kx = map(int, re.search(r"kern_sz=\(tn=none,dims=\(y=(\d+),x=(\d+)\)\)", line).groups())
-            c = chans[bots[0]]
+            ky, kx = (h, w) if typ == "InnerProduct" else yx(line, "kern_sz", None)
+            sy, sx = yx(line, "stride", (1, 1))
+            py, px = yx(line, "in_pad", (0, 0))
             shapes[tag + "_filts"] = (oc, c, ky, kx)
-            shapes[tag + "_biases"] = (oc,)
-            chans[tops[0]] = oc
+            if "bias_term=(tn=uint32_t,v=0)" not in line:
+                shapes[tag + "_biases"] = (oc,)
+            dims[tops[0]] = (oc, (h + 2 * py - ky) // sy + 1, (w + 2 * px - kx) // sx + 1)
+        elif typ == "Pooling":
+            k = yx(line, "kern_sz", None)
+            if k is None:
+                dims[tops[0]] = (c, 1, 1)
+            else:
+                sy, sx = yx(line, "stride", (1, 1))
+                py, px = yx(line, "in_pad", (0, 0))
+                oh = 1 if h + 2 * py < k[0] else -(-(h + 2 * py - k[0]) // sy) + 1
+                ow = 1 if w + 2 * px < k[1] else -(-(w + 2 * px - k[1]) // sx) + 1
+                dims[tops[0]] = (c, oh, ow)
         elif typ == "Concat":
-            chans[tops[0]] = sum(chans[b] for b in bots)
+            dims[tops[0]] = (sum(dims[b][0] for b in bots), h, w)
+        elif typ == "BatchNorm":
+            shapes[tag + "_mean"] = (c,)
+            shapes[tag + "_var"] = (c,)
+            shapes[tag + "_sf"] = (1,)
+        elif typ == "Scale":
+            shapes[tag + "_gamma"] = (c,)
+            shapes[tag + "_beta"] = (c,)
         else:
-            chans[tops[0]] = chans[bots[0]]
+            dims[tops[0]] = dims[bots[0]]
     return shapes
 
 
 def synth_params(pipe_text: str, seed: int = 0) -> Dict[str, np.ndarray]:
-    """filts ~ U(-a,a) with a = sqrt(6/K) (variance 2/K), biases ~ U(-0.5,0.5)/5: per-layer salts, no RNG state."""
+    """filts ~ U(-a,a) with a = sqrt(6/K) (variance 2/K), biases ~ U(-0.5,0.5)/5: per-layer salts, no RNG state. BatchNorm blobs follow
+    Caffe's storage convention (mean / var blobs hold sf x the statistic): sf = 2, mean ~ U(-.1,.1), var ~ U(.5,1.5); Scale gamma ~ U(.5,1.5),
+    beta ~ U(-.1,.1)."""
     out = {}
     for i, (name, shape) in enumerate(sorted(conv_param_shapes(pipe_text).items())):
         salt = 8753985 + 7919 * i + 104729 * seed
         if name.endswith("_filts"):
             k = shape[1] * shape[2] * shape[3]
             out[name] = hash_fill(shape, salt, np.sqrt(6.0 / k) / 5.0)
+        elif name.endswith("_sf"):
+            out[name] = np.full(shape, 2.0, np.float32)
+        elif name.endswith("_mean"):
+            out[name] = (2.0 * hash_fill(shape, salt + 1, 0.1 / 5.0)).astype(np.float32)
+        elif name.endswith("_var"):
+            out[name] = (2.0 * (1.0 + hash_fill(shape, salt + 2, 0.5 / 5.0))).astype(np.float32)
+        elif name.endswith("_gamma"):
+            out[name] = (1.0 + hash_fill(shape, salt + 3, 0.5 / 5.0)).astype(np.float32)
+        elif name.endswith("_beta"):
+            out[name] = hash_fill(shape, salt + 4, 0.1 / 5.0)
         else:
             out[name] = hash_fill(shape, salt + 39475612, 0.1 / 5.0)
     return out
@@ -258,4 +385,5 @@ def synth_input(shape, seed: int = 0, scale: float = 25.0) -> np.ndarray:
     return hash_fill(shape, 234234567 + 15485863 * seed, scale)
 
 
-NETS = {"alexnet_ng_conv": alexnet_ng_conv, "nin_imagenet": nin_imagenet, "googlenet_conv": googlenet_conv, "tiny_net": tiny_net}
+NETS = {"alexnet_ng_conv": alexnet_ng_conv, "nin_imagenet": nin_imagenet, "googlenet_conv": googlenet_conv, "resnet50": resnet50, "tiny_net": tiny_net,
+        "tiny_resnet": tiny_resnet}

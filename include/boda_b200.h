@@ -59,6 +59,12 @@ int b200_rtc_copy_from_var(b200_rtc *r, void *host_dst, const char *vn, uint64_t
 int b200_rtc_get_var_raw_native_pointer(b200_rtc *r, const char *vn, void **dev_ptr_out);
 uint64_t b200_rtc_launches(b200_rtc *r);           /* kernels launched so far by this instance */
 
+/* ---- host-only: the conv_pipe graph IR (needs no GPU) ---- */
+/* Parse `pipe_text` (same format as b200_fwd_create) and run the dims inference of conv_pipe_t::calc_dims (src/conv_util.cc:405-529):
+ * writes one line per node, "<name> <dim>=<sz>:... [param]" in name order, then "ops <n> conv_flops <f>", into buf (NUL-terminated,
+ * truncated to buf_len). Returns the full length needed (excluding the NUL), or <0 on a malformed pipe (see b200_last_error). */
+int64_t b200_pipe_describe(const char *pipe_text, char *buf, uint64_t buf_len);
+
 /* ---- tier B: has_conv_fwd_t ---- */
 /* has_conv_fwd_t::init(conv_pipe, nia)  src/has_conv_fwd.H:21 (conv_pipe_fwd_t::init, src/rtc_fwd.cc:469-527).
  * `pipe_text`: one conv_op_t per line in NESI text form,

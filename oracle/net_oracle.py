@@ -49,9 +49,22 @@ def run_pipe(pipe_text: str, inputs: Dict[str, np.ndarray], params: Dict[str, np
         def yx(name, dflt):
             return (nv[name].dims["y"], nv[name].dims["x"]) if name in nv else dflt
 
-        if typ == "Convolution":
-            w, b = params[tag + "_filts"], params[tag + "_biases"]
+        if typ in ("Convolution", "InnerProduct"):  # InnerProduct = the convolution whose window is its whole input (src/caffepb.cc:276-279)
+            w = params[tag + "_filts"]
+            b = params[tag + "_biases"] if (tag + "_biases") in params else np.zeros(w.shape[0], np.float32)  # bias_term: false
             nodes[tops[0]] = bo.conv_fwd(rnd(nodes[bots[0]]), rnd(w), b, yx("stride", (1, 1)), yx("in_pad", (0, 0)), relu=False, acc64=acc64)
+        elif typ == "BatchNorm":  # Caffe BatchNormLayer::Forward_cpu with use_global_stats: blobs are divided by the scale-factor blob (0 -> 0)
+            assert bots == tops
+            sf = float(params[tag + "_sf"].ravel()[0])
+            s = np.float32(0.0 if sf == 0 else 1.0 / sf)
+            mean, var = params[tag + "_mean"] * s, params[tag + "_var"] * s
+            eps = np.float32(float(nv["eps"].v) if "eps" in nv else 1e-5)
+            x = nodes[bots[0]]
+            nodes[tops[0]] = ((x - mean[None, :, None, None]) / np.sqrt(var + eps)[None, :, None, None]).astype(np.float32)
+        elif typ == "Scale":  # Caffe ScaleLayer with bias_term: y = gamma * x + beta per channel
+            assert bots == tops
+            x = nodes[bots[0]]
+            nodes[tops[0]] = (x * params[tag + "_gamma"][None, :, None, None] + params[tag + "_beta"][None, :, None, None]).astype(np.float32)
         elif typ == "ReLU":
             assert bots == tops
             nodes[tops[0]] = bo.relu(nodes[bots[0]])

@@ -63,3 +63,31 @@ def test_pipe_text_matches_oracle_dims(bb, oracle):
     assert sum(int(np.prod(s)) for s in shapes.values()) == 62378344  # 62.4 M params
     p = nets.synth_params(txt)
     assert p["conv3_filts"].dtype == np.float32 and abs(float(p["conv3_filts"].mean())) < 1e-3
+
+
+@pytest.mark.parametrize("net,kw", [("alexnet_ng_conv", dict(batch=32)), ("nin_imagenet", dict(batch=4)), ("googlenet_conv", dict(batch=2)),
+                                    ("resnet50", dict(batch=2)), ("tiny_resnet", dict(batch=2)), ("tiny_net", dict(batch=3))])
+def test_cpp_pipe_dims_match_python_walk(bb, net, kw):
+    """The C++ conv_pipe graph IR (text parser + calc_dims, host-only) against nets.py's independent shape walk: same parameter nodes with the
+    same shapes for every net family, incl. ResNet-50's BatchNorm / Scale / InnerProduct / bias-less convolutions."""
+    from boda_b200 import nets
+    txt, i, o = nets.NETS[net](**kw)
+    d = bb.pipe_describe(txt)
+    shapes = nets.conv_param_shapes(txt)
+    assert sorted(d["params"]) == sorted(shapes)
+    for n, shp in shapes.items():
+        assert tuple(sz for _, sz in d["nodes"][n]) == tuple(shp), n
+    assert o in d["nodes"] and i in d["nodes"]
+    if net == "alexnet_ng_conv":
+        assert d["conv_flops"] == 72656390144  # 72.66 GFLOP per 32-image forward (SURVEY 8 a10)
+    if net == "resnet50":
+        assert tuple(sz for _, sz in d["nodes"]["pool5"]) == (2, 2048, 1, 1) and tuple(sz for _, sz in d["nodes"]["res3a"]) == (2, 512, 28, 28)
+        assert abs(d["conv_flops"] / 2 / 2 - 3.86e9) < 0.1e9  # ~3.86 GMAC per image
+
+
+def test_cpp_pipe_errors(bb):
+    from boda_b200 import nets
+    with pytest.raises(bb.RtException):  # BatchNorm that is not in place on a Convolution output
+        bb.pipe_describe("(node=data,dims=(img=1,chan=3,y=8,x=8))\n(tag=bn,str_vals=(type=BatchNorm),bots=data,tops=other)\n")
+    with pytest.raises(bb.RtException):
+        bb.pipe_describe("(node=data,dims=(img=1,chan=3,y=8,x=8))\n(tag=c,str_vals=(type=Convolution),nda_vals=(out_chans=(tn=uint32_t,v=4)),bots=data,tops=c)\n")  # no kern_sz
