@@ -141,13 +141,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prec", default="fp32", choices=["fp32", "fp16", "bf16"])
-    ap.add_argument("--net", default="alexnet_ng_conv", choices=["alexnet_ng_conv", "nin_imagenet", "googlenet_conv"],
-                    help="default = BASELINE configs[1]; googlenet_conv --batch 64 --prec bf16 = configs[3]")
+    ap.add_argument("--net", default="alexnet_ng_conv", choices=["alexnet_ng_conv", "nin_imagenet", "googlenet_conv", "resnet50"],
+                    help="default = BASELINE configs[1]; googlenet_conv --batch 64 --prec bf16 = configs[3]; resnet50 --batch 32 (x8 GPUs = 256) = configs[4]")
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU per step")
     args = ap.parse_args()
     global NET_NAME, NET_IN_SZ, METRIC
     NET_NAME = args.net
-    NET_IN_SZ = 224 if args.net == "googlenet_conv" else 227
+    NET_IN_SZ = 224 if args.net in ("googlenet_conv", "resnet50") else 227
     METRIC = "%s_fwd_images_per_sec" % args.net
     if args.impl != "reference":
         args.warmup = max(args.warmup, 3)

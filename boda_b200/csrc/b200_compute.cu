@@ -399,7 +399,16 @@ void plan_conv(conv_plan_t &cp, op_base_t const &op, int num_sms) {
   }
   cp.swapped = (!cp.im2col) && pixels <= 64 && cp.OC >= 128;
   if (cp.swapped) { cp.BN = pixels <= 32 ? 32 : 64; }
-  else { cp.BN = cp.OC > 64 ? 128 : (cp.OC > 32 ? 64 : 32); }
+  else {  // tile width over out_chans: per k-block a tile costs max(MMA cycles ~ BN, issue overhead), so narrow tiles only pay off when they
+          // remove padding; ties go to less padding, then to the wider tile (fewer re-reads of the activation tile)
+    int best = 0;
+    long long best_cost = 0, best_cols = 0;
+    for (int bn : {128, 96, 64, 32}) {
+      long long const tiles_n = ceil_div(cp.OC, bn), cols = tiles_n * bn, cost = tiles_n * (std::max(4 * bn, 300) + 64);  // + the activation tile every extra N tile re-reads
+      if (!best || cost < best_cost || (cost == best_cost && cols < best_cols)) { best = bn; best_cost = cost; best_cols = cols; }
+    }
+    cp.BN = best;
+  }
   long long const p_rows = cp.swapped ? cp.OC : pixels, q_rows = cp.swapped ? pixels : cp.OC;
   long long const tiles = (long long)ceil_div(p_rows, b200::IGEMM_BM) * ceil_div(q_rows, cp.BN);
   cp.splits = 1;
@@ -619,16 +628,16 @@ struct run_ctx_t {
   }
   void launch_igemm2(int BN, int planes, dim3 grid, CUtensorMap const &ph, CUtensorMap const &pl, CUtensorMap const &qh, CUtensorMap const &ql, b200::IgemmParams const &prm) {
     if (planes == 2) {
-      if (BN == 128) { launch_igemm2_t<128, 2>(grid, ph, pl, qh, ql, prm); } else if (BN == 64) { launch_igemm2_t<64, 2>(grid, ph, pl, qh, ql, prm); } else { launch_igemm2_t<32, 2>(grid, ph, pl, qh, ql, prm); }
+      if (BN == 128) { launch_igemm2_t<128, 2>(grid, ph, pl, qh, ql, prm); } else if (BN == 96) { launch_igemm2_t<96, 2>(grid, ph, pl, qh, ql, prm); } else if (BN == 64) { launch_igemm2_t<64, 2>(grid, ph, pl, qh, ql, prm); } else { launch_igemm2_t<32, 2>(grid, ph, pl, qh, ql, prm); }
     } else {
-      if (BN == 128) { launch_igemm2_t<128, 1>(grid, ph, pl, qh, ql, prm); } else if (BN == 64) { launch_igemm2_t<64, 1>(grid, ph, pl, qh, ql, prm); } else { launch_igemm2_t<32, 1>(grid, ph, pl, qh, ql, prm); }
+      if (BN == 128) { launch_igemm2_t<128, 1>(grid, ph, pl, qh, ql, prm); } else if (BN == 96) { launch_igemm2_t<96, 1>(grid, ph, pl, qh, ql, prm); } else if (BN == 64) { launch_igemm2_t<64, 1>(grid, ph, pl, qh, ql, prm); } else { launch_igemm2_t<32, 1>(grid, ph, pl, qh, ql, prm); }
     }
   }
   void launch_igemm(int BN, int planes, dim3 grid, CUtensorMap const &ph, CUtensorMap const &pl, CUtensorMap const &qh, CUtensorMap const &ql, b200::IgemmParams const &prm) {
     if (planes == 2) {
-      if (BN == 128) { launch_igemm_t<128, 2>(grid, ph, pl, qh, ql, prm); } else if (BN == 64) { launch_igemm_t<64, 2>(grid, ph, pl, qh, ql, prm); } else { launch_igemm_t<32, 2>(grid, ph, pl, qh, ql, prm); }
+      if (BN == 128) { launch_igemm_t<128, 2>(grid, ph, pl, qh, ql, prm); } else if (BN == 96) { launch_igemm_t<96, 2>(grid, ph, pl, qh, ql, prm); } else if (BN == 64) { launch_igemm_t<64, 2>(grid, ph, pl, qh, ql, prm); } else { launch_igemm_t<32, 2>(grid, ph, pl, qh, ql, prm); }
     } else {
-      if (BN == 128) { launch_igemm_t<128, 1>(grid, ph, pl, qh, ql, prm); } else if (BN == 64) { launch_igemm_t<64, 1>(grid, ph, pl, qh, ql, prm); } else { launch_igemm_t<32, 1>(grid, ph, pl, qh, ql, prm); }
+      if (BN == 128) { launch_igemm_t<128, 1>(grid, ph, pl, qh, ql, prm); } else if (BN == 96) { launch_igemm_t<96, 1>(grid, ph, pl, qh, ql, prm); } else if (BN == 64) { launch_igemm_t<64, 1>(grid, ph, pl, qh, ql, prm); } else { launch_igemm_t<32, 1>(grid, ph, pl, qh, ql, prm); }
     }
   }
 
@@ -727,6 +736,7 @@ struct run_ctx_t {
     dim3 const grid((unsigned)round_up(p_tiles, k2 ? 2 : 1), (unsigned)q_tiles, 1);
     mark_kernel_begin();
     if (BN == 128) { launch_taps_bn<128>(planes, k2, grid, stg.smem, a_hi, a_lo, w_hi, w_lo, prm); }
+    else if (BN == 96) { launch_taps_bn<96>(planes, k2, grid, stg.smem, a_hi, a_lo, w_hi, w_lo, prm); }
     else if (BN == 64) { launch_taps_bn<64>(planes, k2, grid, stg.smem, a_hi, a_lo, w_hi, w_lo, prm); }
     else { launch_taps_bn<32>(planes, k2, grid, stg.smem, a_hi, a_lo, w_hi, w_lo, prm); }
     mark_kernel_end();

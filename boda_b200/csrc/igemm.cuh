@@ -65,6 +65,9 @@ struct IgemmParams {
   int p_kb_rows, q_kb_rows;
 };
 
+// TMEM columns reserved per accumulator buffer: BN rounded up to a power of two (BN = 96 accumulators sit at 128-column offsets)
+__host__ __device__ constexpr uint32_t tmem_buf_cols(int bn) { return bn <= 32 ? 32u : bn <= 64 ? 64u : bn <= 128 ? 128u : 256u; }
+
 template <int BN, int kPlanes>
 struct IgemmCfg {
   static constexpr int kStageBytes = kPlanes * (IGEMM_BM * 128 + BN * 128);
@@ -74,7 +77,7 @@ struct IgemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 1024 /*barriers*/;
   // TMEM columns: two ping-pong buffers for the main (hi*hi) accumulator + one for the cross-term (hi*lo + lo*hi)
   // accumulator in split mode; allocation must be a power of two >= 32
-  static constexpr uint32_t kColsNeeded = (kPlanes == 2 ? 3 : 2) * BN;
+  static constexpr uint32_t kColsNeeded = (kPlanes == 2 ? 3 : 2) * tmem_buf_cols(BN);
   static constexpr uint32_t kTmemCols = kColsNeeded <= 32 ? 32 : kColsNeeded <= 64 ? 64 : kColsNeeded <= 128 ? 128 : kColsNeeded <= 256 ? 256 : 512;
 };
 
@@ -256,8 +259,8 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
         int const buf = c & 1;
         if (!(prm.debug & 8)) { mbar_wait(&tmem_empty_bar[buf], ((c >> 1) & 1) ^ 1); }
         tc_fence_after();
-        uint32_t const tmem_d = tmem_base + buf * BN;
-        uint32_t const tmem_x = tmem_base + 2 * BN;  // cross-term accumulator: 2^-11 of the main one, drained once at the end
+        uint32_t const tmem_d = tmem_base + buf * tmem_buf_cols(BN);
+        uint32_t const tmem_x = tmem_base + 2 * tmem_buf_cols(BN);  // cross-term accumulator: 2^-11 of the main one, drained once at the end
         int const i_end = min(i + chunk, nkb);
         bool first = true;
         for (; i < i_end; ++i) {
@@ -299,7 +302,7 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
       int const buf = c & 1;
       mbar_wait(&tmem_full_bar[buf], (c >> 1) & 1);
       tc_fence_after();
-      uint32_t const taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
+      uint32_t const taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * tmem_buf_cols(BN);
 #pragma unroll
       for (int j0 = 0; j0 < BN; j0 += 32) {
         uint32_t r[32];
@@ -309,7 +312,7 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
         for (int j = 0; j < 32; ++j) { acc[j0 + j] += __uint_as_float(r[j]); }
       }
       if (kPlanes == 2 && c == nchunks - 1) {  // the last commit also covers every cross-term MMA
-        uint32_t const xaddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 2 * BN;
+        uint32_t const xaddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 2 * tmem_buf_cols(BN);
 #pragma unroll
         for (int j0 = 0; j0 < BN; j0 += 32) {
           uint32_t r[32];

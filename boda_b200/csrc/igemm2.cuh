@@ -23,7 +23,7 @@ struct Igemm2Cfg {
   static constexpr int kStagesRaw = (kMaxSmem - 2048) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 1024;
-  static constexpr uint32_t kColsNeeded = (kPlanes == 2 ? 3 : 2) * BN;
+  static constexpr uint32_t kColsNeeded = (kPlanes == 2 ? 3 : 2) * tmem_buf_cols(BN);
   static constexpr uint32_t kTmemCols = kColsNeeded <= 32 ? 32 : kColsNeeded <= 64 ? 64 : kColsNeeded <= 128 ? 128 : kColsNeeded <= 256 ? 256 : 512;
 };
 
@@ -120,8 +120,8 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
         int const buf = c & 1;
         mbar_wait(&tmem_empty_bar[buf], ((c >> 1) & 1) ^ 1);
         tc_fence_after();
-        uint32_t const tmem_d = tmem_base + buf * BN;
-        uint32_t const tmem_x = tmem_base + 2 * BN;
+        uint32_t const tmem_d = tmem_base + buf * tmem_buf_cols(BN);
+        uint32_t const tmem_x = tmem_base + 2 * tmem_buf_cols(BN);
         int const i_end = min(i + chunk, nkb);
         bool first = true;
         for (; i < i_end; ++i) {
@@ -157,7 +157,7 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
       int const buf = c & 1;
       mbar_wait(&tmem_full_bar[buf], (c >> 1) & 1);
       tc_fence_after();
-      uint32_t const taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
+      uint32_t const taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * tmem_buf_cols(BN);
 #pragma unroll
       for (int j0 = 0; j0 < BN; j0 += 32) {
         uint32_t r[32];
@@ -167,7 +167,7 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
         for (int j = 0; j < 32; ++j) { acc[j0 + j] += __uint_as_float(r[j]); }
       }
       if (kPlanes == 2 && c == nchunks - 1) {
-        uint32_t const xaddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 2 * BN;
+        uint32_t const xaddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 2 * tmem_buf_cols(BN);
 #pragma unroll
         for (int j0 = 0; j0 < BN; j0 += 32) {
           uint32_t r[32];

@@ -57,7 +57,7 @@ igemm_taps_kernel(const __grid_constant__ CUtensorMap a_hi_map, const __grid_con
                   const __grid_constant__ CUtensorMap w_hi_map, const __grid_constant__ CUtensorMap w_lo_map, const TapsParams prm) {
   constexpr int BQ = k2 ? BN / 2 : BN;  // filter rows held by this CTA
   constexpr uint32_t kBBytes = BQ * 128, kBStage = kPlanes * kBBytes;
-  constexpr uint32_t kColsNeeded = (kPlanes == 2 ? 3 : 2) * BN;
+  constexpr uint32_t kColsNeeded = (kPlanes == 2 ? 3 : 2) * tmem_buf_cols(BN);
   constexpr uint32_t kTmemCols = kColsNeeded <= 32 ? 32 : kColsNeeded <= 64 ? 64 : kColsNeeded <= 128 ? 128 : kColsNeeded <= 256 ? 256 : 512;
   uint32_t const a_plane = static_cast<uint32_t>(prm.halo_rows) * 128, a_stage = kPlanes * a_plane;
   int const a_stages = prm.a_stages, b_stages = prm.b_stages;
@@ -168,7 +168,7 @@ igemm_taps_kernel(const __grid_constant__ CUtensorMap a_hi_map, const __grid_con
     // ===================== MMA issuer (whole warp walks the loop, one elected lane issues; in a pair: the leader's warp) ============
     if (leader) {
       uint32_t const idesc = prm.idesc;
-      uint32_t const tmem_x = tmem_base + 2 * BN;  // cross-term accumulator (hi*lo + lo*hi), drained once at the end
+      uint32_t const tmem_x = tmem_base + 2 * tmem_buf_cols(BN);  // cross-term accumulator (hi*lo + lo*hi), drained once at the end
       uint32_t tmem_d = tmem_base;
       int t = 0, kx = 0, tap_row = 0, buf = 0;  // tap_row = ky*Wp + kx
       int sa = 0, sb = 0, in_chunk = 0, ci = 0;  // ring positions, steps into the current accumulation chunk, chunk index
@@ -181,7 +181,7 @@ igemm_taps_kernel(const __grid_constant__ CUtensorMap a_hi_map, const __grid_con
           buf = ci & 1;
           mbar_wait(&tmem_empty_bar[buf], ((ci >> 1) & 1) ^ 1);
           tc_fence_after();
-          tmem_d = tmem_base + buf * BN;
+          tmem_d = tmem_base + buf * tmem_buf_cols(BN);
           first = true;
         }
         if (!(prm.debug & 1)) {
@@ -227,7 +227,7 @@ igemm_taps_kernel(const __grid_constant__ CUtensorMap a_hi_map, const __grid_con
       tc_fence_after();
       if (threadIdx.x == 64 && c == 0) { TAPS_STAMP(4); }
       if (threadIdx.x == 64 && c == nchunks - 1) { TAPS_STAMP(5); }
-      uint32_t const taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
+      uint32_t const taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * tmem_buf_cols(BN);
 #pragma unroll
       for (int j0 = 0; j0 < BN; j0 += 32) {
         uint32_t r[32];
@@ -237,7 +237,7 @@ igemm_taps_kernel(const __grid_constant__ CUtensorMap a_hi_map, const __grid_con
         for (int j = 0; j < 32; ++j) { acc[j0 + j] += __uint_as_float(r[j]); }
       }
       if (kPlanes == 2 && c == nchunks - 1) {
-        uint32_t const xaddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 2 * BN;
+        uint32_t const xaddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 2 * tmem_buf_cols(BN);
 #pragma unroll
         for (int j0 = 0; j0 < BN; j0 += 32) {
           uint32_t r[32];

@@ -359,7 +359,7 @@ def conv_param_shapes(pipe_text: str) -> Dict[str, Tuple[int, ...]]:
 def synth_params(pipe_text: str, seed: int = 0) -> Dict[str, np.ndarray]:
     """filts ~ U(-a,a) with a = sqrt(6/K) (variance 2/K), biases ~ U(-0.5,0.5)/5: per-layer salts, no RNG state. BatchNorm blobs follow
     Caffe's storage convention (mean / var blobs hold sf x the statistic): sf = 2, mean ~ U(-.1,.1), var ~ U(.5,1.5); Scale gamma ~ U(.5,1.5),
-    beta ~ U(-.1,.1)."""
+    beta ~ U(-.1,.1); two ResNet-specific choices keep activations O(10) through 16 residual blocks (see the comments below)."""
     out = {}
     for i, (name, shape) in enumerate(sorted(conv_param_shapes(pipe_text).items())):
         salt = 8753985 + 7919 * i + 104729 * seed
@@ -372,8 +372,12 @@ def synth_params(pipe_text: str, seed: int = 0) -> Dict[str, np.ndarray]:
             out[name] = (2.0 * hash_fill(shape, salt + 1, 0.1 / 5.0)).astype(np.float32)
         elif name.endswith("_var"):
             out[name] = (2.0 * (1.0 + hash_fill(shape, salt + 2, 0.5 / 5.0))).astype(np.float32)
+            if name == "bn_conv1_var":  # the stem sees +-125 pixel-scale inputs: a variance that brings its output to O(1), as trained statistics do
+                out[name] *= np.float32(9e4)
         elif name.endswith("_gamma"):
             out[name] = (1.0 + hash_fill(shape, salt + 3, 0.5 / 5.0)).astype(np.float32)
+            if "branch2c" in name:  # damp the residual branches so 16 blocks of x + f(x) stay O(10) (cf. zero-gamma initialisation)
+                out[name] *= np.float32(0.35)
         elif name.endswith("_beta"):
             out[name] = hash_fill(shape, salt + 4, 0.1 / 5.0)
         else:

@@ -185,3 +185,46 @@ def test_googlenet_conv_16bit_storage(oracle, prec, tol):
         worst = max(worst, e)
         assert e < tol, (n, e)
     print("googlenet %s: worst node max|a-b|/max|ref| = %.3e" % (prec, worst))
+
+
+def test_tiny_resnet_all_nodes(oracle):
+    """ResNet op kinds: BatchNorm(use_global_stats) + Scale folded into the producing convolution on the device (also a
+    Scale-only and a BatchNorm-only fold, with and without conv bias), Eltwise SUM + fused ReLU, global average pool, InnerProduct, Softmax.
+    The oracle evaluates the layers one by one with Caffe's semantics; the folded result must agree within the conv tolerance on every node."""
+    from boda_b200 import nets
+    txt, i, o = nets.tiny_resnet(2)
+    fwd, got, ref, names, x, params = _run_both(txt, i, (2, 3, 33, 33))
+    worst = _check_nodes(oracle, names, got, ref)
+    print("tiny_resnet worst node mrd %.3e" % worst)
+    assert abs(float(got[o].sum()) - 2.0) < 1e-4  # softmax rows sum to one
+    # new parameters (a different BatchNorm scale factor) must be re-folded on the next run
+    params2 = dict(params)
+    for k in params:
+        if k.endswith("_sf"):
+            params2[k] = np.full((1,), 4.0, np.float32)
+    for k, v in params2.items():
+        fwd.set_param(k, v)
+    from oracle import net_oracle
+    got2 = fwd.run_fwd({i: x}, [o])[o]
+    ref2 = net_oracle.run_pipe(txt, {i: x}, params2, acc64=True)[o]
+    assert oracle.mrd(ref2, got2) < TOL and not np.array_equal(got2, got[o])
+
+
+def test_resnet50_b2_output(oracle):
+    """BASELINE config C5's net at batch 2: the probabilities and the last residual stage against the oracle chain."""
+    from boda_b200 import nets
+    import boda_b200 as bb
+    from oracle import net_oracle
+    txt, i, o = nets.resnet50(2)
+    params = nets.synth_params(txt)
+    x = nets.synth_input((2, 3, 224, 224))
+    fwd = bb.B200ConvFwd(txt, "")
+    for k, v in params.items():
+        fwd.set_param(k, v)
+    want = ["pool1", "res2c", "res3d", "res4f", "res5c", "pool5", "fc1000", o]
+    got = fwd.run_fwd({i: x}, want)
+    ref = net_oracle.run_pipe(txt, {i: x}, params, acc64=True)
+    for n in want:
+        m = oracle.mrd(ref[n], got[n])
+        assert m < TOL, (n, m)
+    assert got[o].shape == (2, 1000, 1, 1)
