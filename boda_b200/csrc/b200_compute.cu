@@ -832,7 +832,12 @@ struct run_ctx_t {
     }
     dim3 grid((unsigned)round_up(p_tiles, two_cta ? 2 : cl.cm), (unsigned)round_up(q_tiles, cl.cn), cp.splits);
     mark_kernel_begin();
-    if (two_cta) { prm.idesc = b200::make_idesc_f16(bf16 ? 1u : 0u, 256, cp.BN); launch_igemm2(cp.BN, planes, grid, act_hi, act_lo, w_hi, w_lo, prm); }
+    if (two_cta) {  // persistent: one cluster per SM pair (or per tile, if fewer), each walking its share of the tiles
+      prm.idesc = b200::make_idesc_f16(bf16 ? 1u : 0u, 256, cp.BN);
+      prm.m_pair_tiles = ceil_div(p_tiles, 2); prm.q_tiles = q_tiles;
+      int const n_clusters = std::min(prm.m_pair_tiles * prm.q_tiles, im.num_sms / 2);
+      launch_igemm2(cp.BN, planes, dim3(2 * n_clusters, 1, 1), act_hi, act_lo, w_hi, w_lo, prm);
+    }
     else if (cp.swapped) { launch_igemm(cp.BN, planes, grid, w_hi, w_lo, act_hi, act_lo, prm); }
     else { launch_igemm(cp.BN, planes, grid, act_hi, act_lo, w_hi, w_lo, prm); }
     mark_kernel_end();
@@ -880,7 +885,12 @@ struct run_ctx_t {
     prm.debug = rtc.debug_flags;
     dim3 grid((unsigned)round_up(p_tiles, two_cta ? 2 : cl.cm), (unsigned)round_up(q_tiles, cl.cn), 1);
     mark_kernel_begin();
-    if (two_cta) { prm.idesc = b200::make_idesc_f16(bf16 ? 1u : 0u, 256, BN); launch_igemm2(BN, planes, grid, a_hi, a_lo, b_hi, b_lo, prm); }
+    if (two_cta) {
+      prm.idesc = b200::make_idesc_f16(bf16 ? 1u : 0u, 256, BN);
+      prm.m_pair_tiles = ceil_div(p_tiles, 2); prm.q_tiles = q_tiles;
+      int const n_clusters = std::min(prm.m_pair_tiles * prm.q_tiles, im.num_sms / 2);
+      launch_igemm2(BN, planes, dim3(2 * n_clusters, 1, 1), a_hi, a_lo, b_hi, b_lo, prm);
+    }
     else { launch_igemm(BN, planes, grid, a_hi, a_lo, b_hi, b_lo, prm); }
     mark_kernel_end();
     im.bump(vc);
@@ -1001,7 +1011,10 @@ struct run_ctx_t {
       a.ins[i] = fptr(vi);
     }
     long long const n = vout.dims.dims_prod();
-    B200_CARVEOUT_ONCE(b200::reduce_sum_kernel); launch_k(b200::reduce_sum_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, a, fptr(vout), n, (int)scalar("relu", true, 0), absmax_cell("out"));
+    int vec4 = (reinterpret_cast<uintptr_t>(fptr(vout)) & 15) == 0 ? 1 : 0;
+    for (int i = 0; i < ins_num; ++i) { if (reinterpret_cast<uintptr_t>(a.ins[i]) & 15) { vec4 = 0; } }
+    int const blocks = (int)std::min<long long>(ceil_div(ceil_div(n, vec4 ? 4 : 1), 256), (long long)im.num_sms * 16);
+    B200_CARVEOUT_ONCE(b200::reduce_sum_kernel); launch_k(b200::reduce_sum_kernel, dim3(std::max(blocks, 1)), dim3(256), 0, a, fptr(vout), n, (int)scalar("relu", true, 0), absmax_cell("out"), vec4);
     launched();
     im.bump(vout);
   }

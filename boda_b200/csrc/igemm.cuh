@@ -63,6 +63,7 @@ struct IgemmParams {
   int kb_mod, ksteps_last;
   // k-block-major operand layout [k-block][rows][64] (packed filters): rows per k-block, 0 = plain row-major [rows][K]
   int p_kb_rows, q_kb_rows;
+  int m_pair_tiles, q_tiles;  // persistent CTA-pair kernel (igemm2.cuh): 256-row tiles along P, BN-wide tiles along Q
 };
 
 // TMEM columns reserved per accumulator buffer: BN rounded up to a power of two (BN = 96 accumulators sit at 128-column offsets)

@@ -20,13 +20,22 @@ struct Igemm2Cfg {
   static constexpr int kQRows = BN / 2;  // Q rows held by each CTA of the pair
   static constexpr int kStageBytes = kPlanes * (IGEMM_BM * 128 + kQRows * 128);
   static constexpr int kMaxSmem = 220 * 1024;
-  static constexpr int kStagesRaw = (kMaxSmem - 2048) / kStageBytes;
+  static constexpr int kStagesRaw = (kMaxSmem - 3072) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 1024;
-  static constexpr uint32_t kColsNeeded = (kPlanes == 2 ? 3 : 2) * tmem_buf_cols(BN);
+  static constexpr int kBarBytes = 2048;  // barriers in the first 512 B, two staged bias vectors (tile parity) at +1024
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + kBarBytes;
+  // TMEM: two ping-pong main accumulators (alternating per accumulation chunk) + in fp32-parity mode two cross-term accumulators
+  // (alternating per TILE, so the MMA warp can start the next tile while the epilogue still reads this tile's cross terms)
+  static constexpr uint32_t kBufCols = tmem_buf_cols(BN);
+  static constexpr uint32_t kColsNeeded = (kPlanes == 2 ? 4 : 2) * kBufCols;
   static constexpr uint32_t kTmemCols = kColsNeeded <= 32 ? 32 : kColsNeeded <= 64 ? 64 : kColsNeeded <= 128 ? 128 : kColsNeeded <= 256 ? 256 : 512;
+  static_assert(kColsNeeded <= 512, "TMEM has 512 columns");
 };
 
+// PERSISTENT: the grid is min(#tiles, #SM pairs) clusters; cluster c walks tiles c, c + #clusters, ... (N tiles fastest, so clusters running
+// side by side share activation tiles in L2). Barrier setup, TMEM allocation and tensor-map prefetch are paid once per CTA instead of once
+// per tile, and the epilogue of tile i (TMEM drain + global stores, ~3k cycles) overlaps the TMA / MMA main loop of tile i+1: the smem
+// ring, the accumulator ping-pong and their mbarrier phases simply keep counting across tiles.
 template <int BN, int kPlanes>
 __global__ void __launch_bounds__(IGEMM_THREADS, 1)
 igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_constant__ CUtensorMap p_lo_map,
@@ -35,6 +44,7 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
   using Cfg = Igemm2Cfg<BN, kPlanes>;
   constexpr int kStages = Cfg::kStages;
   constexpr uint32_t kPBytes = IGEMM_BM * 128, kQBytes = Cfg::kQRows * 128;
+  constexpr uint32_t kBufCols = Cfg::kBufCols;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -43,15 +53,16 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
   uint64_t *empty_bar = full_bar + kStages;                      // one per CTA, released by the leader's MMA commits
   uint64_t *tmem_full_bar = empty_bar + kStages;                 // [2], one per CTA
   uint64_t *tmem_empty_bar = tmem_full_bar + 2;                  // [2], leader's copy collects both CTAs' epilogue warps
-  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
-  float *bias_s = reinterpret_cast<float *>(bar_mem + 512);
+  uint64_t *x_empty_bar = tmem_empty_bar + 2;                    // [2], cross-term accumulators (fp32-parity mode), same counting
+  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(x_empty_bar + 2);
+  float *bias_s = reinterpret_cast<float *>(bar_mem + 1024);     // [2][BN]
 
   int const warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
   uint32_t const cta_rank = cluster_ctarank();  // 0 = leader, 1 = peer (cluster dims are (2,1,1))
   bool const leader = (cta_rank == 0);
-  int const m0 = blockIdx.x * IGEMM_BM;         // this CTA's own 128 P rows (the pair covers 256 consecutive ones)
-  int const n0 = blockIdx.y * BN;
+  int const n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+  int const q_tiles = prm.q_tiles, n_tiles = prm.m_pair_tiles * q_tiles;
   int const nkb = prm.kblks_total;
   int const chunk = prm.chunk_kblks;
   int const nchunks = (nkb + chunk - 1) / chunk;
@@ -61,7 +72,7 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
     tma_prefetch_desc(&q_hi_map);
     if (kPlanes == 2) { tma_prefetch_desc(&p_lo_map); tma_prefetch_desc(&q_lo_map); }
     for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 2); mbar_init(&empty_bar[i], 1); }  // full: one arrive per CTA's producer
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 8); }  // empty: 4 epilogue warps x 2 CTAs
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 8); mbar_init(&x_empty_bar[i], 8); }  // 4 epilogue warps x 2 CTAs
     fence_barrier_init();
   }
   if (warp_id == 1) { tmem_alloc_2sm<Cfg::kTmemCols>(tmem_ptr_smem); }
@@ -73,7 +84,10 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
 
   if (warp_id == 0) {
     // ===================== TMA producer (both CTAs; whole warp walks the loop, one elected lane issues -- see igemm.cuh) ==========
-    {
+    int it = 0;  // k-blocks issued so far, over all tiles: ring position and phase
+    for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+      int const mt = tile / q_tiles, nt = tile - mt * q_tiles;
+      int const m0 = (mt * 2 + static_cast<int>(cta_rank)) * IGEMM_BM;  // this CTA's own 128 P rows (the pair covers 256 consecutive ones)
       int img = 0, h_base = 0, w_base = 0;
       if (prm.p_im2col) {
         img = m0 / prm.ohw;
@@ -82,65 +96,69 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
         h_base = oy * prm.sy - prm.py;
         w_base = ox * prm.sx - prm.px;
       }
-      int const q_row0 = n0 + static_cast<int>(cta_rank) * Cfg::kQRows;  // this CTA's half of the Q tile
+      int const q_row0 = nt * BN + static_cast<int>(cta_rank) * Cfg::kQRows;  // this CTA's half of the Q tile
       int cb = 0, kx = 0, ky = 0;  // (tap, channel block) of k-block i, advanced without integer divisions (single-thread loop)
-      for (int i = 0; i < nkb; ++i) {
-        int const s = i % kStages;
-        uint32_t const ph = (i / kStages) & 1;
+      for (int i = 0; i < nkb; ++i, ++it) {
+        int const s = it % kStages;
+        uint32_t const ph = (it / kStages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         if (elect_one_sync()) {
-        if (leader) { mbar_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes); }  // both CTAs' bytes land on the leader's barrier
-        else { mbar_arrive_remote(&full_bar[s], 0); }
-        uint8_t *st = smem + s * Cfg::kStageBytes;
-        uint8_t *p_hi = st, *p_lo = st + kPBytes;
-        uint8_t *q_hi = st + kPlanes * kPBytes, *q_lo = q_hi + kQBytes;
-        if (prm.p_im2col) {
-          tma_load_im2col_4d_2sm(p_hi, &p_hi_map, &full_bar[s], cb * IGEMM_BK, w_base, h_base, img, (uint16_t)kx, (uint16_t)ky);
-          if (kPlanes == 2) { tma_load_im2col_4d_2sm(p_lo, &p_lo_map, &full_bar[s], cb * IGEMM_BK, w_base, h_base, img, (uint16_t)kx, (uint16_t)ky); }
-        } else {
-          tma_load_2d_2sm(p_hi, &p_hi_map, &full_bar[s], i * IGEMM_BK, m0);
-          if (kPlanes == 2) { tma_load_2d_2sm(p_lo, &p_lo_map, &full_bar[s], i * IGEMM_BK, m0); }
-        }
-        int const qc0 = prm.q_kb_rows ? 0 : i * IGEMM_BK, qc1 = q_row0 + i * prm.q_kb_rows;
-        tma_load_2d_2sm(q_hi, &q_hi_map, &full_bar[s], qc0, qc1);
-        if (kPlanes == 2) { tma_load_2d_2sm(q_lo, &q_lo_map, &full_bar[s], qc0, qc1); }
+          if (leader) { mbar_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes); }  // both CTAs' bytes land on the leader's barrier
+          else { mbar_arrive_remote(&full_bar[s], 0); }
+          uint8_t *st = smem + s * Cfg::kStageBytes;
+          uint8_t *p_hi = st, *p_lo = st + kPBytes;
+          uint8_t *q_hi = st + kPlanes * kPBytes, *q_lo = q_hi + kQBytes;
+          if (prm.p_im2col) {
+            tma_load_im2col_4d_2sm(p_hi, &p_hi_map, &full_bar[s], cb * IGEMM_BK, w_base, h_base, img, (uint16_t)kx, (uint16_t)ky);
+            if (kPlanes == 2) { tma_load_im2col_4d_2sm(p_lo, &p_lo_map, &full_bar[s], cb * IGEMM_BK, w_base, h_base, img, (uint16_t)kx, (uint16_t)ky); }
+          } else {
+            tma_load_2d_2sm(p_hi, &p_hi_map, &full_bar[s], i * IGEMM_BK, m0);
+            if (kPlanes == 2) { tma_load_2d_2sm(p_lo, &p_lo_map, &full_bar[s], i * IGEMM_BK, m0); }
+          }
+          int const qc0 = prm.q_kb_rows ? 0 : i * IGEMM_BK, qc1 = q_row0 + i * prm.q_kb_rows;
+          tma_load_2d_2sm(q_hi, &q_hi_map, &full_bar[s], qc0, qc1);
+          if (kPlanes == 2) { tma_load_2d_2sm(q_lo, &q_lo_map, &full_bar[s], qc0, qc1); }
         }
         __syncwarp();
         if (++cb == prm.cblks) { cb = 0; if (++kx == prm.kw) { kx = 0; ++ky; } }
       }
     }
   } else if (warp_id == 1) {
-    // ===================== MMA issuer (leader CTA only, one thread for the pair) =====================
+    // ===================== MMA issuer (leader CTA only, one elected thread for the pair) =====================
     if (leader) {
       uint32_t const idesc = prm.idesc;  // M = 256 (the pair), N = BN
       int const kb_mod = prm.kb_mod, ksteps_last = prm.ksteps_last;
-      int kb_in_grp = 0;
-      int i = 0;
-      for (int c = 0; c < nchunks; ++c) {
-        int const buf = c & 1;
-        mbar_wait(&tmem_empty_bar[buf], ((c >> 1) & 1) ^ 1);
-        tc_fence_after();
-        uint32_t const tmem_d = tmem_base + buf * tmem_buf_cols(BN);
-        uint32_t const tmem_x = tmem_base + 2 * tmem_buf_cols(BN);
-        int const i_end = min(i + chunk, nkb);
-        bool first = true;
-        for (; i < i_end; ++i) {
-          int const s = i % kStages;
-          uint32_t const ph = (i / kStages) & 1;
-          mbar_wait(&full_bar[s], ph);
+      int it = 0, gc = 0, ti = 0;  // k-blocks, accumulation chunks and tiles done so far
+      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++ti) {
+        uint32_t const tmem_x = tmem_base + (2 + (ti & 1)) * kBufCols;
+        if (kPlanes == 2) { mbar_wait(&x_empty_bar[ti & 1], ((ti >> 1) & 1) ^ 1); }  // the epilogue has read the cross terms of tile ti - 2
+        int kb_in_grp = 0;
+        int i = 0;
+        for (int c = 0; c < nchunks; ++c, ++gc) {
+          int const buf = gc & 1;
+          mbar_wait(&tmem_empty_bar[buf], ((gc >> 1) & 1) ^ 1);
           tc_fence_after();
-          uint32_t const st = smem_u32(smem + s * Cfg::kStageBytes);
-          uint32_t const p_hi = sw128_desc_lo(st), p_lo = sw128_desc_lo(st + kPBytes);
-          uint32_t const q_hi = sw128_desc_lo(st + kPlanes * kPBytes), q_lo = sw128_desc_lo(st + kPlanes * kPBytes + kQBytes);
-          int nk = IGEMM_BK / IGEMM_UMMA_K;
-          if (++kb_in_grp == kb_mod) { kb_in_grp = 0; nk = ksteps_last; }
-          if (elect_one_sync()) {
-            issue_kblock<kPlanes, true>(tmem_d, tmem_x, p_hi, p_lo, q_hi, q_lo, idesc, first ? 0u : 1u, i == 0 ? 0u : 1u, nk);
-            umma_commit_2sm(&empty_bar[s], 0x3);  // release the stage in both CTAs
-            if (i == i_end - 1) { umma_commit_2sm(&tmem_full_bar[buf], 0x3); }  // wake both CTAs' epilogues
+          uint32_t const tmem_d = tmem_base + buf * kBufCols;
+          int const i_end = min(i + chunk, nkb);
+          bool first = true;
+          for (; i < i_end; ++i, ++it) {
+            int const s = it % kStages;
+            uint32_t const ph = (it / kStages) & 1;
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            uint32_t const st = smem_u32(smem + s * Cfg::kStageBytes);
+            uint32_t const p_hi = sw128_desc_lo(st), p_lo = sw128_desc_lo(st + kPBytes);
+            uint32_t const q_hi = sw128_desc_lo(st + kPlanes * kPBytes), q_lo = sw128_desc_lo(st + kPlanes * kPBytes + kQBytes);
+            int nk = IGEMM_BK / IGEMM_UMMA_K;
+            if (++kb_in_grp == kb_mod) { kb_in_grp = 0; nk = ksteps_last; }
+            if (elect_one_sync()) {
+              issue_kblock<kPlanes, true>(tmem_d, tmem_x, p_hi, p_lo, q_hi, q_lo, idesc, first ? 0u : 1u, i == 0 ? 0u : 1u, nk);
+              umma_commit_2sm(&empty_bar[s], 0x3);  // release the stage in both CTAs
+              if (i == i_end - 1) { umma_commit_2sm(&tmem_full_bar[buf], 0x3); }  // wake both CTAs' epilogues
+            }
+            __syncwarp();
+            first = false;
           }
-          __syncwarp();
-          first = false;
         }
       }
     }
@@ -148,26 +166,40 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
     // ===================== epilogue warps (each CTA: its own 128 rows) =====================
     int const q = warp_id & 3;
     int const row = q * 32 + lane;
-    for (int j = row; j < BN; j += 128) { bias_s[j] = (prm.has_bias && (n0 + j) < prm.q_rows) ? __ldg(prm.bias + n0 + j) : 0.0f; }
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
-    float acc[BN];
+    float const inv = prm.p_scale[1] * prm.q_scale[1];
+    float const floor_v = prm.relu ? 0.0f : -INFINITY;
+    float amax = 0.0f;
+    int gc = 0, ti = 0;
+    for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++ti) {
+      int const mt = tile / q_tiles, nt = tile - mt * q_tiles;
+      int const m0 = (mt * 2 + static_cast<int>(cta_rank)) * IGEMM_BM, n0 = nt * BN;
+      // this tile's bias, staged in the buffer of its parity (the other one may still be read by a slower epilogue warp's stores)
+      float *bias_t = bias_s + (ti & 1) * BN;
+      for (int j = row; j < BN; j += 128) { bias_t[j] = (prm.has_bias && (n0 + j) < prm.q_rows) ? __ldg(prm.bias + n0 + j) : 0.0f; }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
+      float acc[BN];
 #pragma unroll
-    for (int j = 0; j < BN; ++j) { acc[j] = 0.0f; }
-    for (int c = 0; c < nchunks; ++c) {
-      int const buf = c & 1;
-      mbar_wait(&tmem_full_bar[buf], (c >> 1) & 1);
-      tc_fence_after();
-      uint32_t const taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * tmem_buf_cols(BN);
+      for (int j = 0; j < BN; ++j) { acc[j] = 0.0f; }
+      for (int c = 0; c < nchunks; ++c, ++gc) {
+        int const buf = gc & 1;
+        mbar_wait(&tmem_full_bar[buf], (gc >> 1) & 1);
+        tc_fence_after();
+        uint32_t const taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kBufCols;
 #pragma unroll
-      for (int j0 = 0; j0 < BN; j0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + j0, r);
-        tmem_ld_wait();
+        for (int j0 = 0; j0 < BN; j0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + j0, r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { acc[j0 + j] += __uint_as_float(r[j]); }
+          for (int j = 0; j < 32; ++j) { acc[j0 + j] += __uint_as_float(r[j]); }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (leader) { mbar_arrive(&tmem_empty_bar[buf]); } else { mbar_arrive_remote(&tmem_empty_bar[buf], 0); } }
       }
-      if (kPlanes == 2 && c == nchunks - 1) {
-        uint32_t const xaddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 2 * tmem_buf_cols(BN);
+      if (kPlanes == 2) {  // the last chunk's commit also covered every cross-term MMA of this tile
+        tc_fence_after();
+        uint32_t const xaddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (2 + (ti & 1)) * kBufCols;
 #pragma unroll
         for (int j0 = 0; j0 < BN; j0 += 32) {
           uint32_t r[32];
@@ -176,19 +208,16 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
 #pragma unroll
           for (int j = 0; j < 32; ++j) { acc[j0 + j] += __uint_as_float(r[j]); }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (leader) { mbar_arrive(&x_empty_bar[ti & 1]); } else { mbar_arrive_remote(&x_empty_bar[ti & 1], 0); } }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) { if (leader) { mbar_arrive(&tmem_empty_bar[buf]); } else { mbar_arrive_remote(&tmem_empty_bar[buf], 0); } }
-    }
-    float const inv = prm.p_scale[1] * prm.q_scale[1];
-    float const floor_v = prm.relu ? 0.0f : -INFINITY;
-    int const prow = m0 + row;
-    float amax = 0.0f;
-    if (prow < prm.p_rows) {
-      int const img = prow / prm.out_hw, pix = prow - img * prm.out_hw;
-      float *o = prm.out + (static_cast<long long>(img) * prm.out_chans + n0) * prm.out_hw + pix;
-      amax = igemm_store_row<BN>(acc, inv, bias_s, floor_v, o, prm.out_hw, prm.q_rows - n0);
+      int const prow = m0 + row;
+      if (prow < prm.p_rows) {
+        int const img = prow / prm.out_hw, pix = prow - img * prm.out_hw;
+        float *o = prm.out + (static_cast<long long>(img) * prm.out_chans + n0) * prm.out_hw + pix;
+        amax = fmaxf(amax, igemm_store_row<BN>(acc, inv, bias_t, floor_v, o, prm.out_hw, prm.q_rows - n0));
+      }
     }
     if (prm.out_absmax) {
 #pragma unroll

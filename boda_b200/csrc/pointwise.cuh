@@ -125,16 +125,36 @@ __global__ void concat_copy_kernel(float const *__restrict__ in, float *__restri
 // ---- reduce: N-ary elementwise sum (test/rtc/reduce.cucl) ------------------------------------------------------
 struct ReduceArgs { float const *ins[8]; int ins_num; };
 // relu != 0 fuses the in-place ReLU that follows a residual join (Eltwise SUM + ReLU in ResNet); the sum order is the reference's.
-__global__ void reduce_sum_kernel(ReduceArgs a, float *__restrict__ out, long long n, int relu, unsigned int *out_absmax) {
+// 128-bit loads / stores when every pointer is 16-byte aligned (n4 = n / 4 vector elements, then a scalar tail), grid-stride so a CTA
+// publishes max|out| once (one atomic per warp-reduction, not one per 32 elements).
+__global__ void __launch_bounds__(256)
+reduce_sum_kernel(ReduceArgs a, float *__restrict__ out, long long n, int relu, unsigned int *out_absmax, int vec4) {
   pdl_prologue();
-  long long const i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  float v = 0;
-  if (i < n) {
+  long long const tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x, nthr = static_cast<long long>(gridDim.x) * blockDim.x;
+  float m = 0.0f;
+  long long done = 0;
+  if (vec4) {
+    long long const n4 = n >> 2;
+    for (long long i = tid; i < n4; i += nthr) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < a.ins_num; ++j) {
+        float4 const x = __ldg(reinterpret_cast<float4 const *>(a.ins[j]) + i);
+        v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+      }
+      if (relu) { v.x = (v.x <= 0) ? 0.0f : v.x; v.y = (v.y <= 0) ? 0.0f : v.y; v.z = (v.z <= 0) ? 0.0f : v.z; v.w = (v.w <= 0) ? 0.0f : v.w; }
+      reinterpret_cast<float4 *>(out)[i] = v;
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    done = n4 << 2;
+  }
+  for (long long i = done + tid; i < n; i += nthr) {
+    float v = 0;
     for (int j = 0; j < a.ins_num; ++j) { v += __ldg(a.ins[j] + i); }
     if (relu) { v = (v <= 0) ? 0.0f : v; }
     out[i] = v;
+    m = fmaxf(m, fabsf(v));
   }
-  if (out_absmax) { publish_absmax_warp(fabsf(v), out_absmax); }
+  if (out_absmax) { publish_absmax_warp(m, out_absmax); }
 }
 
 // ---- BatchNorm / Scale folding (parameter-only) ---------------------------------------------------------------
