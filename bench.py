@@ -36,6 +36,17 @@ PER_GPU_BATCH = 32
 L2_FLUSH_BYTES = 256 << 20
 
 
+def committed_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/roofline_traffic.json, written by
+    tools/ncu_summarise.py runs); None when no capture of this build's kernel is committed."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    with open(p) as f:
+        d = json.load(f)
+    return d.get("dram_bytes_per_launch"), d.get("source")
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -277,6 +288,7 @@ def main():
     sampler.join(timeout=2)
     conv_rows = [r for r in prof if r[3] > 0]
     conv_flops = sum(r[3] for r in conv_rows)
+    conv_bytes = 4.0 * nets.conv_algorithmic_elems(txt)  # (in + out + filts + biases) x 4 B per Convolution, each tensor once (src/latex-util.H:119)
     conv_kernel_ms = sum(r[2] for r in conv_rows)
     peaks = measured_peaks()
     achieved_tf = conv_flops / (conv_kernel_ms * 1e-3) / 1e12 if conv_kernel_ms > 0 else 0.0
@@ -298,7 +310,9 @@ def main():
                     "sync_run_fwd_ms_per_step": e2e_sync_ms},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None,
-                         "traffic": None, "kernel": "b200::igemm_umma_2cta_kernel / igemm_umma_kernel (%d launches per forward, one per Convolution)" % len(conv_rows),
+                         "traffic": committed_traffic()[0] if (args.net, args.prec) == ("alexnet_ng_conv", "fp32") else None, "traffic_source": committed_traffic()[1],
+                         "algorithmic_bytes_per_launch": conv_bytes / max(len(conv_rows), 1),
+                         "kernel": "b200::igemm_umma_2cta_kernel (persistent CTA pairs) / igemm_umma_kernel (fc-shaped layers): %d launches per forward, one per Convolution" % len(conv_rows),
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernels timed one by one with CUDA events), %s" % peaks["source"],
                          "note": "algorithmic fp32 conv FLOPs / summed launch durations; the fp32-parity mode issues 3 fp16 MMAs per product, so the tensor pipe does 3x this"},
             "clocks": sampler.summary(),

@@ -356,6 +356,25 @@ def conv_param_shapes(pipe_text: str) -> Dict[str, Tuple[int, ...]]:
     return shapes
 
 
+def conv_algorithmic_elems(pipe_text: str) -> int:
+    """Sum over the Convolution ops of numel(in) + numel(out) + numel(filts) + numel(biases): the reference's algorithmic-bytes figure / 4
+    (src/latex-util.H:119, pysrc/flops.py:101), from the C++ pipe IR's dims inference."""
+    import re
+    import boda_b200 as bb
+    d = bb.pipe_describe(pipe_text)
+    tot = 0
+    for line in pipe_text.splitlines():
+        if "type=Convolution" not in line and "type=InnerProduct" not in line:
+            continue
+        tag = re.search(r"tag=([^,]+),", line).group(1)
+        bot = re.search(r"bots=([^,)]+)", line).group(1).split(":")[0]
+        top = re.search(r"tops=([^,)]+)", line).group(1).split(":")[0]
+        for n in (bot, top, tag + "_filts", tag + "_biases"):
+            if n in d["nodes"]:
+                tot += int(np.prod([sz for _, sz in d["nodes"][n]]))
+    return tot
+
+
 def synth_params(pipe_text: str, seed: int = 0) -> Dict[str, np.ndarray]:
     """filts ~ U(-a,a) with a = sqrt(6/K) (variance 2/K), biases ~ U(-0.5,0.5)/5: per-layer salts, no RNG state. BatchNorm blobs follow
     Caffe's storage convention (mean / var blobs hold sf x the statistic): sf = 2, mean ~ U(-.1,.1), var ~ U(.5,1.5); Scale gamma ~ U(.5,1.5),
