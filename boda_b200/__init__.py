@@ -57,6 +57,7 @@ _SIGS = {
     "b200_rtc_get_var_raw_native_pointer": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.POINTER(_c.c_void_p)]),
     "b200_rtc_launches": (_c.c_uint64, [_c.c_void_p]),
     "b200_pipe_describe": (_c.c_int64, [_c.c_char_p, _c.c_char_p, _c.c_uint64]),
+    "b200_pipe_from_prototxt": (_c.c_int64, [_c.c_char_p, _c.c_char_p, _c.c_char_p, _c.c_uint64]),
     "b200_fwd_create": (_c.c_void_p, [_c.c_char_p, _c.c_char_p]),
     "b200_fwd_destroy": (None, [_c.c_void_p]),
     "b200_fwd_set_param": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_void_p, _c.c_uint64]),
@@ -103,6 +104,21 @@ def _chk(rc: int) -> int:
 
 def _b(s: str) -> bytes:
     return s.encode()
+
+
+def pipe_from_prototxt(prototxt_text: str, in_dims: Optional[Dict[str, int]] = None, out_node_name: str = "", keep_softmax: bool = False) -> str:
+    """Host-only (no GPU, no protobuf): Caffe prototxt -> the conv_pipe text B200ConvFwd takes; the TEST-phase translation of
+    create_pipe_from_param (src/caffepb.cc:166-326). in_dims overrides source-node dims by name, e.g. {"img": 32}."""
+    kv = ["%s=%d" % (k, v) for k, v in (in_dims or {}).items()]
+    if out_node_name:
+        kv.append("out_node_name=" + out_node_name)
+    if keep_softmax:
+        kv.append("keep_softmax=1")
+    opts = "(" + ",".join(kv) + ")" if kv else ""
+    need = _chk(lib().b200_pipe_from_prototxt(_b(prototxt_text), _b(opts), None, 0))
+    buf = ctypes.create_string_buffer(need + 1)
+    _chk(lib().b200_pipe_from_prototxt(_b(prototxt_text), _b(opts), buf, need + 1))
+    return buf.value.decode()
 
 
 def pipe_describe(pipe_text: str) -> Dict[str, object]:

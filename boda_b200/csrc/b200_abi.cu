@@ -1,6 +1,7 @@
 // b200_abi.cu -- extern "C" surface declared in include/boda_b200.h. No exceptions cross this boundary.
 #include "../../include/boda_b200.h"
 #include "b200_conv_fwd.h"
+#include "caffe_prototxt.h"
 #include <cstdio>
 
 using namespace boda;
@@ -130,6 +131,29 @@ B200_API int64_t b200_pipe_describe(const char *pipe_text, char *buf, uint64_t b
       out += "\n";
     }
     out += "ops " + str(cp->ops.size()) + " conv_flops " + str(cp->total_conv_flops()) + "\n";
+    need = (int64_t)out.size();
+    if (buf && buf_len) { snprintf(buf, buf_len, "%s", out.c_str()); }
+    return 0;
+  });
+  return rc == 0 ? need : rc;
+}
+
+B200_API int64_t b200_pipe_from_prototxt(const char *prototxt_text, const char *opts, char *buf, uint64_t buf_len) {
+  int64_t need = -1;
+  int const rc = guarded([&] {
+    prototxt_opts_t po;
+    if (opts && *opts) {
+      p_lexp_t l = parse_lexp(opts);
+      if (!l->is_leaf) {
+        for (auto const &kv : l->kids) {
+          string const &k = kv.first, &v = kv.second->leaf;
+          if (k == "out_node_name") { po.out_node_name = v; }
+          else if (k == "keep_softmax") { po.keep_softmax = std::stoi(v) != 0; }
+          else { po.in_dims[k] = (uint32_t)std::stoul(v); }
+        }
+      }
+    }
+    string const out = conv_pipe_text_from_prototxt(prototxt_text, po);
     need = (int64_t)out.size();
     if (buf && buf_len) { snprintf(buf, buf_len, "%s", out.c_str()); }
     return 0;

@@ -65,6 +65,12 @@ uint64_t b200_rtc_launches(b200_rtc *r);           /* kernels launched so far by
  * truncated to buf_len). Returns the full length needed (excluding the NUL), or <0 on a malformed pipe (see b200_last_error). */
 int64_t b200_pipe_describe(const char *pipe_text, char *buf, uint64_t buf_len);
 
+/* Caffe prototxt (protobuf text format) -> pipe text, host-only, no protobuf: the translation of create_pipe_from_param
+ * (src/caffepb.cc:166-326) for TEST-phase forward graphs. `opts` is a lexp list: "(img=32)" style dims overrides for the source nodes
+ * (the reference's in_dims), "out_node_name=<node>" to stop after the layer producing it, "keep_softmax=1" to keep Softmax layers (the
+ * reference drops them). Same buffer convention as b200_pipe_describe: returns the length needed, or <0 on error. */
+int64_t b200_pipe_from_prototxt(const char *prototxt_text, const char *opts, char *buf, uint64_t buf_len);
+
 /* ---- tier B: has_conv_fwd_t ---- */
 /* has_conv_fwd_t::init(conv_pipe, nia)  src/has_conv_fwd.H:21 (conv_pipe_fwd_t::init, src/rtc_fwd.cc:469-527).
  * `pipe_text`: one conv_op_t per line in NESI text form,
