@@ -57,6 +57,9 @@ _SIGS = {
     "b200_rtc_get_var_raw_native_pointer": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.POINTER(_c.c_void_p)]),
     "b200_rtc_launches": (_c.c_uint64, [_c.c_void_p]),
     "b200_pipe_describe": (_c.c_int64, [_c.c_char_p, _c.c_char_p, _c.c_uint64]),
+    "b200_nda_digest_hex": (_c.c_int64, [_c.c_char_p, _c.c_int, _c.POINTER(_c.c_char_p), _c.POINTER(_c.c_uint32), _c.c_void_p, _c.c_char_p, _c.c_uint64]),
+    "b200_wisdom_record": (_c.c_int64, [_c.c_char_p, _c.c_int, _c.POINTER(_c.c_char_p), _c.POINTER(_c.c_char_p), _c.c_char_p, _c.c_char_p, _c.c_double, _c.c_char_p,
+                                        _c.c_char_p, _c.c_char_p, _c.c_uint64]),
     "b200_pipe_from_prototxt": (_c.c_int64, [_c.c_char_p, _c.c_char_p, _c.c_char_p, _c.c_uint64]),
     "b200_fwd_create": (_c.c_void_p, [_c.c_char_p, _c.c_char_p]),
     "b200_fwd_destroy": (None, [_c.c_void_p]),
@@ -118,6 +121,28 @@ def pipe_from_prototxt(prototxt_text: str, in_dims: Optional[Dict[str, int]] = N
     need = _chk(lib().b200_pipe_from_prototxt(_b(prototxt_text), _b(opts), None, 0))
     buf = ctypes.create_string_buffer(need + 1)
     _chk(lib().b200_pipe_from_prototxt(_b(prototxt_text), _b(opts), buf, need + 1))
+    return buf.value.decode()
+
+
+def nda_digest_hex(var_name: str, arr: np.ndarray, dim_names: Sequence[str]) -> str:
+    """hex(bwrite(nda_digest_t)) of a float tensor, as Boda's ops-prof stores known-good outputs in wisdom files (src/boda_base.cc:210-383)."""
+    a = np.ascontiguousarray(arr, np.float32)
+    names = _str_array(list(dim_names))
+    sizes = (_c.c_uint32 * a.ndim)(*a.shape)
+    args = (_b(var_name), a.ndim, names, sizes, a.ctypes.data_as(_c.c_void_p))
+    need = _chk(lib().b200_nda_digest_hex(*args, None, 0))
+    buf = ctypes.create_string_buffer(need + 1)
+    _chk(lib().b200_nda_digest_hex(*args, buf, need + 1))
+    return buf.value.decode()
+
+
+def wisdom_record(op_text: str, kgs: Sequence[Tuple[str, str]], op_tune_text: str, be_plat_tag: str, rt_secs: float, err: str = "", run_op_text: str = "") -> str:
+    """One op_wisdom_t text record (src/op-tuner.cc:98-130) for Boda's wisdom files / wis-ana."""
+    kn, kh = _str_array([k for k, _ in kgs]), _str_array([h for _, h in kgs])
+    args = (_b(op_text), len(kgs), kn, kh, _b(op_tune_text), _b(be_plat_tag), float(rt_secs), _b(err), _b(run_op_text or op_text))
+    need = _chk(lib().b200_wisdom_record(*args, None, 0))
+    buf = ctypes.create_string_buffer(need + 1)
+    _chk(lib().b200_wisdom_record(*args, buf, need + 1))
     return buf.value.decode()
 
 

@@ -2,6 +2,7 @@
 #include "../../include/boda_b200.h"
 #include "b200_conv_fwd.h"
 #include "caffe_prototxt.h"
+#include "wisdom.h"
 #include <cstdio>
 
 using namespace boda;
@@ -154,6 +155,33 @@ B200_API int64_t b200_pipe_from_prototxt(const char *prototxt_text, const char *
       }
     }
     string const out = conv_pipe_text_from_prototxt(prototxt_text, po);
+    need = (int64_t)out.size();
+    if (buf && buf_len) { snprintf(buf, buf_len, "%s", out.c_str()); }
+    return 0;
+  });
+  return rc == 0 ? need : rc;
+}
+
+B200_API int64_t b200_nda_digest_hex(const char *var_name, int ndims, const char *const *dim_names, const uint32_t *dim_sizes, const float *host_data,
+                                     char *buf, uint64_t buf_len) {
+  int64_t need = -1;
+  int const rc = guarded([&] {
+    string const out = nda_digest_hex(var_name, make_dims("float", ndims, dim_names, dim_sizes), host_data);
+    need = (int64_t)out.size();
+    if (buf && buf_len) { snprintf(buf, buf_len, "%s", out.c_str()); }
+    return 0;
+  });
+  return rc == 0 ? need : rc;
+}
+B200_API int64_t b200_wisdom_record(const char *op_text, int n_kgs, const char *const *kg_names, const char *const *kg_hex, const char *op_tune_text,
+                                    const char *be_plat_tag, double rt_secs, const char *err, const char *run_op_text, char *buf, uint64_t buf_len) {
+  int64_t need = -1;
+  int const rc = guarded([&] {
+    vector<std::pair<string, string>> kgs;
+    for (int i = 0; i < n_kgs; ++i) { kgs.push_back({kg_names[i], kg_hex[i]}); }
+    wisdom_run_t r;
+    r.op_tune_text = op_tune_text; r.be_plat_tag = be_plat_tag; r.rt_secs = rt_secs; r.err = err ? err : ""; r.run_op_text = run_op_text ? run_op_text : "";
+    string const out = wisdom_record_text(op_text, kgs, {r});
     need = (int64_t)out.size();
     if (buf && buf_len) { snprintf(buf, buf_len, "%s", out.c_str()); }
     return 0;

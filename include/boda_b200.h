@@ -71,6 +71,14 @@ int64_t b200_pipe_describe(const char *pipe_text, char *buf, uint64_t buf_len);
  * reference drops them). Same buffer convention as b200_pipe_describe: returns the length needed, or <0 on error. */
 int64_t b200_pipe_from_prototxt(const char *prototxt_text, const char *opts, char *buf, uint64_t buf_len);
 
+/* Boda wisdom-file records (host-only; src/op-tuner.cc:98-130, src/boda_base.cc:210-383): hex(bwrite(nda_digest_t)) of a host float tensor
+ * with named dims, seeded by std::hash<string>(var_name) as ops-prof does (src/rtc_prof.cc:297-310); and one op_wisdom_t text record with
+ * `n_kgs` (name, digest hex) pairs and one op_tune_wisdom_t/op_run_t block. Same buffer convention as b200_pipe_describe. */
+int64_t b200_nda_digest_hex(const char *var_name, int ndims, const char *const *dim_names, const uint32_t *dim_sizes, const float *host_data,
+                            char *buf, uint64_t buf_len);
+int64_t b200_wisdom_record(const char *op_text, int n_kgs, const char *const *kg_names, const char *const *kg_hex, const char *op_tune_text,
+                           const char *be_plat_tag, double rt_secs, const char *err, const char *run_op_text, char *buf, uint64_t buf_len);
+
 /* ---- tier B: has_conv_fwd_t ---- */
 /* has_conv_fwd_t::init(conv_pipe, nia)  src/has_conv_fwd.H:21 (conv_pipe_fwd_t::init, src/rtc_fwd.cc:469-527).
  * `pipe_text`: one conv_op_t per line in NESI text form,

@@ -41,6 +41,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--out", default="")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--wisdom-out", default="", help="also write the results as a Boda wisdom file (op_wisdom_t records with nda_digest known-good vectors, "
+                    "src/op-tuner.cc:98-130) that Boda's wis-ana / ops-prof flows can read")
     ap.add_argument("--opts", default="", help="extra back-end options, e.g. use_taps=0,taps_2cta=1,acc_chunk_kblks_16=4")
     ap.add_argument("--max-check-gflop", type=float, default=40.0, help="skip the CPU oracle compare for ops larger than this")
     args = ap.parse_args()
@@ -103,6 +105,12 @@ def main():
         call_ms = float(np.median([rtc.get_dur(i, i) for i in ids]))
         kern_ms = float(np.median([rtc.get_kernel_dur(i) for i in ids]))
         m = float("nan")
+        if args.wisdom_out:  # known-good digest of the output actually computed + the timing, in the reference's own record format
+            outv = rtc.copy_var_to_nda(fn + "_" + outs[0])
+            rec = bb.wisdom_record(line, [(outs[0], bb.nda_digest_hex(outs[0], outv, names[outs[0]]))], "(use_be=b200,prec=%s)" % args.prec,
+                                   rtc.get_plat_tag(), kern_ms * 1e-3, run_op_text=txt)
+            with open(args.wisdom_out, "a" if li else "w") as wf:
+                wf.write(rec)
         if do_check:
             got = rtc.copy_var_to_nda(fn + "_" + outs[0])
             ref = bo.run_op(op, host, acc64=True)[outs[0]]
