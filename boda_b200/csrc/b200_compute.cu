@@ -399,12 +399,15 @@ void plan_conv(conv_plan_t &cp, op_base_t const &op, int num_sms) {
   }
   cp.swapped = (!cp.im2col) && pixels <= 64 && cp.OC >= 128;
   if (cp.swapped) { cp.BN = pixels <= 32 ? 32 : 64; }
-  else {  // tile width over out_chans: per k-block a tile costs max(MMA cycles ~ BN, issue overhead), so narrow tiles only pay off when they
-          // remove padding; ties go to less padding, then to the wider tile (fewer re-reads of the activation tile)
+  else {  // tile width over out_chans: per k-block a tile costs max(MMA cycles ~ BN, issue overhead) + the activation tile it re-reads, and the
+          // persistent pair kernel runs ceil(tiles / SM pairs) rounds of tiles -- so a narrower tile can win by filling the chip (AlexNet
+          // conv5: 44 tiles of 128 on 74 pairs vs 66 tiles of 96) as well as by removing padding; ties go to less padding, then wider tiles
     int best = 0;
     long long best_cost = 0, best_cols = 0;
+    long long const m_pairs = ceil_div(ceil_div(pixels, b200::IGEMM_BM), 2), slots = std::max(num_sms / 2, 1);
     for (int bn : {128, 96, 64, 32}) {
-      long long const tiles_n = ceil_div(cp.OC, bn), cols = tiles_n * bn, cost = tiles_n * (std::max(4 * bn, 300) + 64);  // + the activation tile every extra N tile re-reads
+      long long const tiles_n = ceil_div(cp.OC, bn), cols = tiles_n * bn;
+      long long const cost = ceil_div(m_pairs * tiles_n, slots) * (std::max(4 * bn, 300) + 64);
       if (!best || cost < best_cost || (cost == best_cost && cols < best_cols)) { best = bn; best_cost = cost; best_cols = cols; }
     }
     cp.BN = best;

@@ -273,11 +273,18 @@ pool_plane_kernel(float const *__restrict__ in, float *__restrict__ out, int H, 
   int const hw = H * W, n_in = np * hw, ohw = OH * OW, n_out = np * ohw;
   float const *ip = in + plane0 * hw;
   if ((reinterpret_cast<uintptr_t>(ip) & 15) == 0) {
+    // all loads of a batch are issued before the first shared-memory store (8 x 16 B in flight per thread)
     float4 const *ip4 = reinterpret_cast<float4 const *>(ip);
     float4 *s4 = reinterpret_cast<float4 *>(plane_s);
     int const n4 = n_in >> 2;
-#pragma unroll 4
-    for (int i = threadIdx.x; i < n4; i += 256) { s4[i] = __ldg(ip4 + i); }
+    constexpr int kU = 8;
+    for (int base = threadIdx.x; base < n4; base += 256 * kU) {
+      float4 v[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) { int const i = base + u * 256; if (i < n4) { v[u] = __ldg(ip4 + i); } }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) { int const i = base + u * 256; if (i < n4) { s4[i] = v[u]; } }
+    }
     for (int i = (n4 << 2) + threadIdx.x; i < n_in; i += 256) { plane_s[i] = __ldg(ip + i); }
   } else {
     for (int i = threadIdx.x; i < n_in; i += 256) { plane_s[i] = __ldg(ip + i); }
