@@ -18,7 +18,12 @@ namespace b200 {
 template <int BN, int kPlanes>
 struct Igemm2Cfg {
   static constexpr int kQRows = BN / 2;  // Q rows held by each CTA of the pair
-  static constexpr int kStageBytes = kPlanes * (IGEMM_BM * 128 + kQRows * 128);
+  // A pipeline stage always has two P slots and two Q slots: hi + lo planes of ONE k-block in fp32-parity mode, or TWO consecutive k-blocks
+  // in the single-plane 16-bit modes -- there a k-block is only 4 MMAs (256 cycles at BN = 128), less than the barrier wait + commit +
+  // loop overhead of a step, so two k-blocks share one wait and one commit (8 MMAs back to back).
+  static constexpr int kKbPerStage = (kPlanes == 1) ? 2 : 1;
+  static constexpr int kKbBytes = kPlanes * (IGEMM_BM * 128 + kQRows * 128);  // bytes per k-block per CTA
+  static constexpr int kStageBytes = 2 * (IGEMM_BM * 128 + kQRows * 128);
   static constexpr int kMaxSmem = 220 * 1024;
   static constexpr int kStagesRaw = (kMaxSmem - 3072) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
@@ -45,6 +50,7 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
   constexpr int kStages = Cfg::kStages;
   constexpr uint32_t kPBytes = IGEMM_BM * 128, kQBytes = Cfg::kQRows * 128;
   constexpr uint32_t kBufCols = Cfg::kBufCols;
+  constexpr int kKb = Cfg::kKbPerStage;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -64,7 +70,7 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
   int const n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
   int const q_tiles = prm.q_tiles, n_tiles = prm.m_pair_tiles * q_tiles;
   int const nkb = prm.kblks_total;
-  int const chunk = prm.chunk_kblks;
+  int const chunk = (prm.chunk_kblks + kKb - 1) / kKb * kKb;  // accumulation chunks end on stage boundaries
   int const nchunks = (nkb + chunk - 1) / chunk;
 
   if (warp_id == 0 && lane == 0) {
@@ -98,29 +104,39 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
       }
       int const q_row0 = nt * BN + static_cast<int>(cta_rank) * Cfg::kQRows;  // this CTA's half of the Q tile
       int cb = 0, kx = 0, ky = 0;  // (tap, channel block) of k-block i, advanced without integer divisions (single-thread loop)
-      for (int i = 0; i < nkb; ++i, ++it) {
+      for (int i = 0; i < nkb; i += kKb, ++it) {
         int const s = it % kStages;
         uint32_t const ph = (it / kStages) & 1;
+        int const nh = min(kKb, nkb - i);  // k-blocks in this stage
         mbar_wait(&empty_bar[s], ph ^ 1);
-        if (elect_one_sync()) {
-          if (leader) { mbar_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes); }  // both CTAs' bytes land on the leader's barrier
+        bool const issue = elect_one_sync();
+        if (issue) {
+          if (leader) { mbar_expect_tx(&full_bar[s], 2u * nh * Cfg::kKbBytes); }  // both CTAs' bytes land on the leader's barrier
           else { mbar_arrive_remote(&full_bar[s], 0); }
-          uint8_t *st = smem + s * Cfg::kStageBytes;
-          uint8_t *p_hi = st, *p_lo = st + kPBytes;
-          uint8_t *q_hi = st + kPlanes * kPBytes, *q_lo = q_hi + kQBytes;
-          if (prm.p_im2col) {
-            tma_load_im2col_4d_2sm(p_hi, &p_hi_map, &full_bar[s], cb * IGEMM_BK, w_base, h_base, img, (uint16_t)kx, (uint16_t)ky);
-            if (kPlanes == 2) { tma_load_im2col_4d_2sm(p_lo, &p_lo_map, &full_bar[s], cb * IGEMM_BK, w_base, h_base, img, (uint16_t)kx, (uint16_t)ky); }
-          } else {
-            tma_load_2d_2sm(p_hi, &p_hi_map, &full_bar[s], i * IGEMM_BK, m0);
-            if (kPlanes == 2) { tma_load_2d_2sm(p_lo, &p_lo_map, &full_bar[s], i * IGEMM_BK, m0); }
+        }
+        uint8_t *st = smem + s * Cfg::kStageBytes;
+#pragma unroll
+        for (int j = 0; j < kKb; ++j) {
+          if (j < nh) {
+            int const kb = i + j;
+            if (issue) {
+              uint8_t *p_hi = st + (kPlanes == 2 ? 0 : j) * kPBytes, *p_lo = st + kPBytes;              // slot j (16-bit modes) or hi / lo planes
+              uint8_t *q_hi = st + 2 * kPBytes + (kPlanes == 2 ? 0 : j) * kQBytes, *q_lo = st + 2 * kPBytes + kQBytes;
+              if (prm.p_im2col) {
+                tma_load_im2col_4d_2sm(p_hi, &p_hi_map, &full_bar[s], cb * IGEMM_BK, w_base, h_base, img, (uint16_t)kx, (uint16_t)ky);
+                if (kPlanes == 2) { tma_load_im2col_4d_2sm(p_lo, &p_lo_map, &full_bar[s], cb * IGEMM_BK, w_base, h_base, img, (uint16_t)kx, (uint16_t)ky); }
+              } else {
+                tma_load_2d_2sm(p_hi, &p_hi_map, &full_bar[s], kb * IGEMM_BK, m0);
+                if (kPlanes == 2) { tma_load_2d_2sm(p_lo, &p_lo_map, &full_bar[s], kb * IGEMM_BK, m0); }
+              }
+              int const qc0 = prm.q_kb_rows ? 0 : kb * IGEMM_BK, qc1 = q_row0 + kb * prm.q_kb_rows;
+              tma_load_2d_2sm(q_hi, &q_hi_map, &full_bar[s], qc0, qc1);
+              if (kPlanes == 2) { tma_load_2d_2sm(q_lo, &q_lo_map, &full_bar[s], qc0, qc1); }
+            }
+            if (++cb == prm.cblks) { cb = 0; if (++kx == prm.kw) { kx = 0; ++ky; } }
           }
-          int const qc0 = prm.q_kb_rows ? 0 : i * IGEMM_BK, qc1 = q_row0 + i * prm.q_kb_rows;
-          tma_load_2d_2sm(q_hi, &q_hi_map, &full_bar[s], qc0, qc1);
-          if (kPlanes == 2) { tma_load_2d_2sm(q_lo, &q_lo_map, &full_bar[s], qc0, qc1); }
         }
         __syncwarp();
-        if (++cb == prm.cblks) { cb = 0; if (++kx == prm.kw) { kx = 0; ++ky; } }
       }
     }
   } else if (warp_id == 1) {
@@ -141,20 +157,31 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
           uint32_t const tmem_d = tmem_base + buf * kBufCols;
           int const i_end = min(i + chunk, nkb);
           bool first = true;
-          for (; i < i_end; ++i, ++it) {
+          for (; i < i_end; i += kKb, ++it) {
             int const s = it % kStages;
             uint32_t const ph = (it / kStages) & 1;
+            int const nh = min(kKb, nkb - i);
             mbar_wait(&full_bar[s], ph);
             tc_fence_after();
             uint32_t const st = smem_u32(smem + s * Cfg::kStageBytes);
-            uint32_t const p_hi = sw128_desc_lo(st), p_lo = sw128_desc_lo(st + kPBytes);
-            uint32_t const q_hi = sw128_desc_lo(st + kPlanes * kPBytes), q_lo = sw128_desc_lo(st + kPlanes * kPBytes + kQBytes);
-            int nk = IGEMM_BK / IGEMM_UMMA_K;
-            if (++kb_in_grp == kb_mod) { kb_in_grp = 0; nk = ksteps_last; }
+            int nk[kKb];
+#pragma unroll
+            for (int j = 0; j < kKb; ++j) { nk[j] = IGEMM_BK / IGEMM_UMMA_K; if (j < nh && ++kb_in_grp == kb_mod) { kb_in_grp = 0; nk[j] = ksteps_last; } }
             if (elect_one_sync()) {
-              issue_kblock<kPlanes, true>(tmem_d, tmem_x, p_hi, p_lo, q_hi, q_lo, idesc, first ? 0u : 1u, i == 0 ? 0u : 1u, nk);
+              if (kPlanes == 2) {
+                issue_kblock<2, true>(tmem_d, tmem_x, sw128_desc_lo(st), sw128_desc_lo(st + kPBytes), sw128_desc_lo(st + 2 * kPBytes),
+                                      sw128_desc_lo(st + 2 * kPBytes + kQBytes), idesc, first ? 0u : 1u, i == 0 ? 0u : 1u, nk[0]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < kKb; ++j) {
+                  if (j < nh) {
+                    issue_kblock<1, true>(tmem_d, 0u, sw128_desc_lo(st + j * kPBytes), 0u, sw128_desc_lo(st + 2 * kPBytes + j * kQBytes), 0u, idesc,
+                                          (first && j == 0) ? 0u : 1u, 1u, nk[j]);
+                  }
+                }
+              }
               umma_commit_2sm(&empty_bar[s], 0x3);  // release the stage in both CTAs
-              if (i == i_end - 1) { umma_commit_2sm(&tmem_full_bar[buf], 0x3); }  // wake both CTAs' epilogues
+              if (i + kKb >= i_end) { umma_commit_2sm(&tmem_full_bar[buf], 0x3); }  // wake both CTAs' epilogues
             }
             __syncwarp();
             first = false;
