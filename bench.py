@@ -314,7 +314,10 @@ def main():
                          "algorithmic_bytes_per_launch": conv_bytes / max(len(conv_rows), 1),
                          "kernel": "b200::igemm_umma_2cta_kernel (persistent CTA pairs) / igemm_umma_kernel (fc-shaped layers): %d launches per forward, one per Convolution" % len(conv_rows),
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernels timed one by one with CUDA events), %s" % peaks["source"],
-                         "note": "algorithmic fp32 conv FLOPs / summed launch durations; the fp32-parity mode issues 3 fp16 MMAs per product, so the tensor pipe does 3x this"},
+                         "mma_passes": 3 if args.prec == "fp32" else 1,
+                         "tensor_work_frac": (achieved_tf * (3 if args.prec == "fp32" else 1) / peak_tf) if peak_tf else None,
+                         "note": "achieved = algorithmic conv FLOPs / summed launch durations of ALL contraction launches (incl. the HBM-bound fc-shaped layers); "
+                                 "the fp32-parity mode issues 3 fp16 MMAs per product (mma_passes), so tensor_work_frac = achieved x mma_passes / peak is the share of the tensor pipe's peak actually kept busy"},
             "clocks": sampler.summary(),
             "per_call": [{"func": r[0], "call_ms": round(r[1], 5), "kernel_ms": round(r[2], 5), "gflop": round(r[3] / 1e9, 3)} for r in prof],
         }

@@ -170,6 +170,9 @@ cluster_choice_t choose_cluster(int p_tiles, int q_tiles, int BN, int planes, bo
 struct b200_impl_t {
   map<string, var_info_t> vars;
   map<string, func_t> funcs;
+  // NHWC 16-bit planes of activation vars, shared by every Convolution that reads the same var (the four branches of an inception module, the
+  // shortcut + first 1x1 of a ResNet block): the first consumer of a write generation packs, the others reuse. Keyed by the storage pointer.
+  map<void const *, packed_t> act_packs;
   vector<call_ev_t> calls;
   cudaStream_t stream = nullptr;
   bool inited = false, timing = true;
@@ -241,7 +244,11 @@ void b200_compute_t::create_var_with_dims_as_reshaped_view_of_var(string const &
   v.dims.calc_strides();
   impl->vars[vn] = v;
 }
-void b200_compute_t::release_var(string const &vn) { impl->must_var(vn); impl->vars.erase(vn); }
+void b200_compute_t::release_var(string const &vn) {
+  var_info_t &v = impl->must_var(vn);
+  if (v.buf.use_count() == 1) { impl->act_packs.erase(v.buf->p); }  // last name of this storage: drop its packed planes too
+  impl->vars.erase(vn);
+}
 dims_t b200_compute_t::get_var_dims(string const &vn) { return impl->must_var(vn).dims; }
 void b200_compute_t::set_var_to_zero(string const &vn) {
   var_info_t &v = impl->must_var(vn);
@@ -765,7 +772,7 @@ struct run_ctx_t {
     if (has_arg("biases")) { var_info_t &vb = var("biases"); if ((int)vb.dims.dims_prod() != cp.OC) { rt_err("conv: biases size mismatch"); } bias = fptr(vb); }
     bool const bf16 = (rtc.prec == B200_PREC_BF16);
     int const planes = (rtc.prec == B200_PREC_FP32_SPLIT) ? 2 : 1;
-    if (cp.taps && rtc.use_taps && run_conv_taps(vin, vf, vout, bias, bf16, planes)) { return; }
+    if (cp.taps && rtc.use_taps && !has_arg("out_concat") && run_conv_taps(vin, vf, vout, bias, bf16, planes)) { return; }
     // filters: OIHW -> K-major rows (k = tap x chan), stored k-block-major [k / 64][OC padded][64] so that every TMA tile is contiguous
     // (once per weight version; the reference's xpose_filts, src/rtc_fwd.cc:310-313)
     long long const oc_pad = round_up(cp.OC, 128);
@@ -777,9 +784,10 @@ struct run_ctx_t {
     } else {
       pack(f.w_pack, vf, cp.OC, cp.C, cp.KH * cp.KW, cp.Cpad, cp.w_tap_stride, cp.w_row_stride, oc_pad * cp.w_row_stride, planes == 2, bf16, 0, 0, 0, nullptr, 0, oc_pad);
       long long const act_elems = (long long)cp.N * cp.H * cp.W * cp.Cpad;
-      pack(f.a_pack, vin, cp.N, cp.C, cp.H * cp.W, cp.Cpad, cp.Cpad, (long long)cp.H * cp.W * cp.Cpad, act_elems, planes == 2, bf16, 0, 0, 0, absmax_cell("in"));
+      pack(im.act_packs[vin.buf->p], vin, cp.N, cp.C, cp.H * cp.W, cp.Cpad, cp.Cpad, (long long)cp.H * cp.W * cp.Cpad, act_elems, planes == 2, bf16, 0, 0, 0, absmax_cell("in"));
     }
 
+    packed_t &a_pack = cp.rowmerge ? f.a_pack : im.act_packs[vin.buf->p];  // row-merged planes are private to this function; NHWC planes are shared
     long long const pixels = (long long)cp.N * cp.OH * cp.OW;
     int const p_rows_n = cp.swapped ? cp.OC : (int)pixels, q_rows_n = cp.swapped ? (int)pixels : cp.OC;
     int const p_tiles = ceil_div(p_rows_n, b200::IGEMM_BM), q_tiles = ceil_div(q_rows_n, cp.BN);
@@ -790,12 +798,12 @@ struct run_ctx_t {
     CUtensorMap act_hi, act_lo, w_hi, w_lo;
     uint32_t const act_box = cp.swapped ? cp.BN : b200::IGEMM_BM / cl.cn, w_box = cp.swapped ? b200::IGEMM_BM : (two_cta ? cp.BN / 2 : cp.BN / cl.cm);
     if (cp.im2col) {
-      act_hi = make_im2col_map(f.a_pack.hi->p, bf16, cp, act_box);
-      act_lo = planes == 2 ? make_im2col_map(f.a_pack.lo->p, bf16, cp, act_box) : act_hi;
+      act_hi = make_im2col_map(a_pack.hi->p, bf16, cp, act_box);
+      act_lo = planes == 2 ? make_im2col_map(a_pack.lo->p, bf16, cp, act_box) : act_hi;
     } else {
       uint64_t const kext = cp.full_kernel ? (uint64_t)cp.a_row_stride : (uint64_t)cp.Cpad;
-      act_hi = make_tiled_map(f.a_pack.hi->p, bf16, kext, cp.a_rows, cp.a_row_stride, act_box);
-      act_lo = planes == 2 ? make_tiled_map(f.a_pack.lo->p, bf16, kext, cp.a_rows, cp.a_row_stride, act_box) : act_hi;
+      act_hi = make_tiled_map(a_pack.hi->p, bf16, kext, cp.a_rows, cp.a_row_stride, act_box);
+      act_lo = planes == 2 ? make_tiled_map(a_pack.lo->p, bf16, kext, cp.a_rows, cp.a_row_stride, act_box) : act_hi;
     }
     uint64_t const w_rows = (uint64_t)(cp.w_row_stride / 64) * oc_pad;
     w_hi = make_tiled_map(f.w_pack.hi->p, bf16, 64, w_rows, 64, w_box);
@@ -815,8 +823,8 @@ struct run_ctx_t {
     prm.swapped = cp.swapped ? 1 : 0;
     prm.out_chans = cp.OC; prm.out_hw = cp.OH * cp.OW;
     prm.relu = cp.relu; prm.has_bias = bias ? 1 : 0; prm.bias = bias;
-    prm.p_scale = static_cast<float *>((cp.swapped ? f.w_pack : f.a_pack).scale2->p);
-    prm.q_scale = static_cast<float *>((cp.swapped ? f.a_pack : f.w_pack).scale2->p);
+    prm.p_scale = static_cast<float *>((cp.swapped ? f.w_pack : a_pack).scale2->p);
+    prm.q_scale = static_cast<float *>((cp.swapped ? a_pack : f.w_pack).scale2->p);
     prm.idesc = b200::make_idesc_f16(bf16 ? 1u : 0u, 128, cp.BN);
     prm.cm = cl.cm; prm.cn = cl.cn;
     prm.kb_mod = cp.kb_mod; prm.ksteps_last = cp.ksteps_last;
@@ -824,13 +832,28 @@ struct run_ctx_t {
     prm.debug = rtc.debug_flags;
     prm.out_absmax = absmax_cell("out");
     long long const out_elems = (long long)cp.N * cp.OC * cp.OH * cp.OW;
+    // Concat by offset: with an "out_concat" var + by-value "out_ocix" the epilogue writes this convolution's channels
+    // straight into the Concat output at channel offset ocix (the per-image stride is the wider var's channel count); `out` itself is then
+    // not written (split-K layers: the reduce kernel writes the strided slice).
+    float *out_base = fptr(vout);
+    var_info_t *vcat = nullptr;
+    if (has_arg("out_concat")) {
+      vcat = &var("out_concat");
+      check_nchw(vcat->dims, "out_concat");
+      int const ocix = (int)scalar("out_ocix");
+      if ((int)vcat->dims.dsz("img") != cp.N || (int)vcat->dims.dsz("y") != cp.OH || (int)vcat->dims.dsz("x") != cp.OW || ocix + cp.OC > (int)vcat->dims.dsz("chan")) {
+        rt_err("conv: out does not fit into out_concat at out_ocix");
+      }
+      out_base = fptr(*vcat) + (long long)ocix * cp.OH * cp.OW;
+      if (cp.splits == 1) { prm.out_chans = (int)vcat->dims.dsz("chan"); }  // split-K partials keep this layer's own geometry; the reduce kernel strides
+    }
     if (cp.splits > 1) {
       uint64_t const need = (uint64_t)cp.splits * out_elems * 4;
       if (!f.splitk_ws || f.splitk_ws->bytes < need) { f.splitk_ws = std::make_shared<dev_buf_t>(need); }
       prm.out = static_cast<float *>(f.splitk_ws->p);
       prm.split_stride = out_elems;
     } else {
-      prm.out = fptr(vout);
+      prm.out = out_base;
       prm.split_stride = 0;
     }
     dim3 grid((unsigned)round_up(p_tiles, two_cta ? 2 : cl.cm), (unsigned)round_up(q_tiles, cl.cn), cp.splits);
@@ -845,10 +868,11 @@ struct run_ctx_t {
     else { launch_igemm(cp.BN, planes, grid, act_hi, act_lo, w_hi, w_lo, prm); }
     mark_kernel_end();
     if (cp.splits > 1) {
-      B200_CARVEOUT_ONCE(b200::splitk_reduce_kernel); launch_k(b200::splitk_reduce_kernel, dim3(ceil_div(out_elems, 256)), dim3(256), 0, static_cast<float *>(f.splitk_ws->p), fptr(vout), bias, out_elems, cp.splits, cp.OC, cp.OH * cp.OW, cp.relu, prm.out_absmax);
+      B200_CARVEOUT_ONCE(b200::splitk_reduce_kernel); launch_k(b200::splitk_reduce_kernel, dim3(ceil_div(out_elems, 256)), dim3(256), 0, static_cast<float *>(f.splitk_ws->p), out_base, bias, out_elems, cp.splits, cp.OC, cp.OH * cp.OW, cp.relu, prm.out_absmax,
+               vcat ? (long long)vcat->dims.dsz("chan") * cp.OH * cp.OW : 0ll);
       launched();
     }
-    im.bump(vout);
+    im.bump(vcat ? *vcat : vout);
   }
   static constexpr uint32_t IGEMM_BM_host() { return b200::IGEMM_BM; }
 
@@ -992,14 +1016,15 @@ struct run_ctx_t {
     var_info_t &vin = var("in"), &vout = var("out");
     check_nchw(vin.dims, "in"); check_nchw(vout.dims, "out");
     int const ocix = (int)scalar("ocix");
+    int const reverse = (int)scalar("reverse", true, 0);  // 1: in = out[:, ocix:ocix+C] (read a Concat input back out of the Concat output)
     int const C = vin.dims.dsz("chan"), HW = vin.dims.dsz("y") * vin.dims.dsz("x"), OC = vout.dims.dsz("chan"), n_img = vin.dims.dsz("img");
     if (vout.dims.dsz("y") != vin.dims.dsz("y") || vout.dims.dsz("x") != vin.dims.dsz("x") || (int)vout.dims.dsz("img") != n_img || ocix + C > OC) { rt_err("copy: in does not fit into out at ocix"); }
     long long const per_img = (long long)C * HW, out_img_stride = (long long)OC * HW, out_off = (long long)ocix * HW;
     int const vec4 = ((per_img % 4) == 0 && (out_img_stride % 4) == 0 && (out_off % 4) == 0) ? 1 : 0;
     long long const work = vec4 ? per_img * n_img / 4 : per_img * n_img;
-    B200_CARVEOUT_ONCE(b200::concat_copy_kernel); launch_k(b200::concat_copy_kernel, dim3(ceil_div(work, 256)), dim3(256), 0, fptr(vin), fptr(vout), per_img, out_img_stride, out_off, n_img, vec4, absmax_cell("out"));
+    B200_CARVEOUT_ONCE(b200::concat_copy_kernel); launch_k(b200::concat_copy_kernel, dim3(ceil_div(work, 256)), dim3(256), 0, fptr(vin), fptr(vout), per_img, out_img_stride, out_off, n_img, vec4, reverse ? nullptr : absmax_cell("out"), reverse);
     launched();
-    im.bump(vout);
+    im.bump(reverse ? vin : vout);
   }
 
   void run_reduce() {

@@ -67,7 +67,7 @@ struct b200_compute_t {
   int use_2cta = 1;         // CTA pairs: one tcgen05.mma.cta_group::2 per 256 x BN tile (igemm2.cuh)
   int use_clusters = 0;     // 1-CTA tiles only: let CTAs that share an operand tile form a cluster and TMA-multicast it (choose_cluster)
   int acc_chunk_kblks = 4;  // drain TMEM accumulators into fp32 registers every this many 64-wide k-blocks (fp32-parity mode)
-  int acc_chunk_kblks_16 = 32;  // same for the fp16 / bf16 storage modes (operand rounding dominates there; draining costs TMEM bandwidth)
+  int acc_chunk_kblks_16 = 8;   // same for the fp16 / bf16 storage modes (32 measured 1.9e-3 mrd at K = 3456 in fp16 mode: the truncating in-TMEM accumulation drifts)
   int use_pdl = 1;          // programmatic dependent launch between the kernels of a forward pass (pdl.cuh)
   int use_taps = 0;         // stride-1 KHxKW convs: tap-reuse kernel (igemm3.cuh): one activation halo tile feeds every filter tap.
                             // Off by default: measured slower than the CTA-pair im2col kernel on the AlexNet layers (profiles/), kept for A/B runs

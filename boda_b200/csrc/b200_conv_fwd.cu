@@ -253,7 +253,12 @@ void b200_conv_fwd_t::gen_op(p_conv_op_t const &op) {
     map_str_rtc_arg_t args{{"in", op->bots[0]}, {"filts", filts_vn}, {"out", op->tops[0]}};
     if (!biases_vn.empty()) { args["biases"] = biases_vn; }
     add_absmax_args(args, "in", op->bots[0]);
-    add_absmax_args(args, "out", op->tops[0]);
+    auto al = concat_alias.find(op->tops[0]);
+    if (al != concat_alias.end()) {  // write into the Concat output at this input's channel offset; its abs-max cell is the Concat output's
+      args["out_concat"] = rtc_arg_t(al->second.cat_node);
+      args["out_ocix"] = rtc_arg_t(make_scalar_nda<uint32_t>(al->second.ocix, "uint32_t"));
+      add_absmax_args(args, "out", al->second.cat_node);
+    } else { add_absmax_args(args, "out", op->tops[0]); }
     add_call("conv", *op, fop, args);
   } else if (op->is("Pooling")) {
     map_str_rtc_arg_t args{{"in", op->bots[0]}, {"out", op->tops[0]}};
@@ -274,6 +279,7 @@ void b200_conv_fwd_t::gen_op(p_conv_op_t const &op) {
   } else if (op->is("Concat")) {  // one copy per input at a running channel offset (src/rtc_fwd.cc:267-280)
     uint32_t chans_out_done = 0;
     for (auto const &b : op->bots) {
+      if (concat_alias.count(b)) { chans_out_done += cp->must_get_node(b)->dims.dsz("chan"); continue; }  // already written in place by its convolution
       op_base_t cop = fop;
       cop.set_u32("ocix", chans_out_done);
       map_str_rtc_arg_t args{{"in", b}, {"out", op->tops[0]}};
@@ -318,6 +324,7 @@ void b200_conv_fwd_t::init(p_conv_pipe_t const &cp_, string const &opts) {
         else if (k == "use_2cta") { rtc->use_2cta = std::stoi(v); }
         else if (k == "device") { rtc->device = std::stoi(v); }
         else if (k == "enable_prof") { enable_prof = (uint32_t)std::stoul(v); }
+        else if (k == "concat_by_offset") { concat_by_offset = (uint32_t)std::stoul(v); }
         else { rt_err("mode=b200: unused option '" + k + "'"); }  // NESI rejects unused keys (src/nesi.cc:25-35)
       }
     }
@@ -340,7 +347,41 @@ void b200_conv_fwd_t::init(p_conv_pipe_t const &cp_, string const &opts) {
     if (feeds_conv) { uint32_t const ix = (uint32_t)absmax_ix.size(); absmax_ix[n.name] = ix; }
   }
   rtc->create_var_with_dims(absmax_cells_vn, dims_t({(uint32_t)std::max<size_t>(absmax_ix.size(), 1)}, {"cell"}, "uint32_t"));
+  // Concat by offset (the reference copies every Concat input, src/rtc_fwd.cc:267-280): a Concat input qualifies when it is
+  // written by one Convolution, read by nothing but this Concat, and carries no in-place op other than the ReLU the convolution fuses.
+  if (concat_by_offset) {
+    for (auto const &op : cp->ops) {
+      if (!op->is("Concat")) { continue; }
+      uint32_t ocix = 0;
+      for (auto const &b : op->bots) {
+        p_conv_node_t bn = cp->must_get_node(b);
+        bool ok = bn->top_for.size() == 1 && !concat_alias.count(b);
+        for (auto const &reader : bn->bot_for) {  // readers: this Concat, or the node's own in-place ops (they list the node as their bottom)
+          bool in_place_reader = false;
+          for (auto const &ip : bn->in_place_ops) { if (ip->tag == reader) { in_place_reader = true; } }
+          if (reader != op->tag && !in_place_reader) { ok = false; }
+        }
+        p_conv_op_t writer;
+        if (ok) { for (auto const &o : cp->ops) { if (o->tag == bn->top_for[0]) { writer = o; } } }
+        ok = ok && writer && writer->is("Convolution") && !writer->has("is_inner_product");
+        if (ok) { for (auto const &ip : bn->in_place_ops) { if (!(ip->is("ReLU") && ip == bn->in_place_ops[0]) && !ip->is("Dropout")) { ok = false; } } }
+        if (ok) { concat_alias[b] = concat_alias_t{op->tops[0], ocix, string()}; }
+        ocix += bn->dims.dsz("chan");
+      }
+    }
+  }
   for (auto const &op : cp->ops) { gen_op(op); }
+  for (auto &kv : concat_alias) {  // read-back functions: node = Concat output[:, ocix : ocix + chan]
+    op_base_t cop;
+    cop.set_type("Concat");
+    cop.set_u32("ocix", kv.second.ocix);
+    cop.set_u32("reverse", 1);
+    rtc_func_info_t fi;
+    fi.func_name = kv.second.extract_func = "copy__extract__" + kv.first;
+    fi.op = cop;
+    fi.op.set_func_name("copy");
+    rtc->compile({fi}, rtc_compile_opts_t());
+  }
   info_log = "mode=b200 plat=" + rtc->get_plat_tag() + " nodes=" + str(cp->nodes.size()) + " ops=" + str(cp->ops.size()) + " fwd_calls=" + str(fwd_calls.size()) +
              " conv_flops=" + str(cp->total_conv_flops());
 }
@@ -427,9 +468,22 @@ int b200_conv_fwd_t::submit(int n_set, char const *const *set_names, float const
   sl.used = true;
   if (use_graph) { CU_CHK(cudaGraphLaunch(graph_exec, st)); graph_launches += kernels_per_fwd; }
   else { rtc->set_timing(false); run_calls(); }
-  for (int i = 0; i < n_get; ++i) { rtc->copy_var_to_raw_async(get_bufs[i], get_names[i], get_elems[i] * 4); }
+  for (int i = 0; i < n_get; ++i) {
+    materialise_aliased(get_names[i]);
+    rtc->copy_var_to_raw_async(get_bufs[i], get_names[i], get_elems[i] * 4);
+  }
   CU_CHK(cudaEventRecord(ticket_ev[ticket], st));
   return ticket;
+}
+
+void b200_conv_fwd_t::materialise_aliased(string const &node) {
+  auto al = concat_alias.find(node);
+  if (al == concat_alias.end()) { return; }
+  rtc_func_call_t rfc;
+  rfc.rtc_func_name = al->second.extract_func;
+  rfc.arg_map = map_str_rtc_arg_t{{"in", node}, {"out", al->second.cat_node}};
+  rtc->set_timing(false);
+  rtc->run(rfc);
 }
 
 void b200_conv_fwd_t::wait(int ticket) {

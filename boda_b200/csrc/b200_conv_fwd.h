@@ -44,6 +44,8 @@ struct b200_conv_fwd_t {
   // options (conv_pipe_fwd_t fields, src/rtc_fwd.cc:48-66, reduced to what applies)
   uint32_t use_graph = 1;      // replay the forward calls as one CUDA graph (launch-bound at B200 speeds)
   uint32_t enable_prof = 0;
+  uint32_t concat_by_offset = 1;  // Convolutions that only feed a Concat write straight into its output at their channel offset (no copy kernel);
+                                  // their own node is materialised from that slice only when run_fwd is asked for it
   p_b200_compute_t rtc;
   p_conv_pipe_t cp;
   vector<fwd_call_t> fwd_calls;
@@ -93,6 +95,9 @@ struct b200_conv_fwd_t {
   uint64_t flush_bytes = 0;
   vector<double> call_flops;
   map<string, uint32_t> absmax_ix;  // nodes whose producer publishes max|x| for the consuming convolution's operand scaling
+  struct concat_alias_t { string cat_node; uint32_t ocix; string extract_func; };
+  map<string, concat_alias_t> concat_alias;  // node -> (Concat output that holds its channels, channel offset, name of the read-back function)
+  void materialise_aliased(string const &node);  // enqueue the slice copy Concat output -> node var (before reading an aliased node)
   void add_absmax_args(map_str_rtc_arg_t &args, string const &which, string const &node);
 };
 

@@ -366,9 +366,10 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
   if (warp_id == 1) { tmem_dealloc<Cfg::kTmemCols>(tmem_base); }
 }
 
-// split-K fix-up: out[i] = relu( sum_s ws[s][i] + bias[chan(i)] )   (deterministic order)
+// split-K fix-up: out[i] = relu( sum_s ws[s][i] + bias[chan(i)] )   (deterministic order). `out_img_stride` != 0: the result is a channel
+// slice of a wider NCHW var (concat by offset) -- image `img` of the slice starts at out + img * out_img_stride.
 __global__ void splitk_reduce_kernel(float const *__restrict__ ws, float *__restrict__ out, float const *__restrict__ bias,
-                                     long long n, int splits, int out_chans, int out_hw, int relu, unsigned int *out_absmax) {
+                                     long long n, int splits, int out_chans, int out_hw, int relu, unsigned int *out_absmax, long long out_img_stride) {
   pdl_prologue();
   long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   float v = 0.0f;
@@ -376,7 +377,9 @@ __global__ void splitk_reduce_kernel(float const *__restrict__ ws, float *__rest
     for (int s = 0; s < splits; ++s) { v += ws[s * n + i]; }
     if (bias) { v += __ldg(bias + (i / out_hw) % out_chans); }
     if (relu) { v = fmaxf(v, 0.0f); }
-    out[i] = v;
+    long long o = i;
+    if (out_img_stride) { long long const per_img = static_cast<long long>(out_chans) * out_hw, img = i / per_img; o = img * out_img_stride + (i - img * per_img); }
+    out[o] = v;
   }
   if (out_absmax) {
     float m = (i < n) ? fabsf(v) : 0.0f;

@@ -97,8 +97,8 @@ __global__ void relu_kernel(float *__restrict__ x, long long n) {
 
 // ---- copy / Concat (test/rtc/copy.cucl) -----------------------------------------------------------------------
 // in: [N][C][HW] -> out[:, ocix:ocix+C]; per image the source block is contiguous, so move 128-bit words when aligned.
-__global__ void concat_copy_kernel(float const *__restrict__ in, float *__restrict__ out, long long per_img /*C*HW*/,
-                                   long long out_img_stride, long long out_off, int n_img, int vec4, unsigned int *out_absmax) {
+__global__ void concat_copy_kernel(float *__restrict__ in, float *__restrict__ out, long long per_img /*C*HW*/,
+                                   long long out_img_stride, long long out_off, int n_img, int vec4, unsigned int *out_absmax, int reverse) {
   pdl_prologue();
   long long const total = per_img * n_img;
   float m = 0.0f;
@@ -106,17 +106,24 @@ __global__ void concat_copy_kernel(float const *__restrict__ in, float *__restri
     long long const i4 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4;
     if (i4 < total) {
       long long const img = i4 / per_img, r = i4 - img * per_img;
-      float4 const v = __ldg(reinterpret_cast<float4 const *>(in + i4));
-      *reinterpret_cast<float4 *>(out + img * out_img_stride + out_off + r) = v;
-      m = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+      float4 *ip = reinterpret_cast<float4 *>(in + i4), *op = reinterpret_cast<float4 *>(out + img * out_img_stride + out_off + r);
+      if (reverse) { *ip = *op; }  // extract: in = out[:, ocix:ocix+C]
+      else {
+        float4 const v = *ip;
+        *op = v;
+        m = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+      }
     }
   } else {
     long long const i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (i < total) {
       long long const img = i / per_img, r = i - img * per_img;
-      float const v = __ldg(in + i);
-      out[img * out_img_stride + out_off + r] = v;
-      m = fabsf(v);
+      if (reverse) { in[i] = out[img * out_img_stride + out_off + r]; }
+      else {
+        float const v = in[i];
+        out[img * out_img_stride + out_off + r] = v;
+        m = fabsf(v);
+      }
     }
   }
   if (out_absmax) { publish_absmax_warp(m, out_absmax); }

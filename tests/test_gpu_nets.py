@@ -228,3 +228,24 @@ def test_resnet50_b2_output(oracle):
         m = oracle.mrd(ref[n], got[n])
         assert m < TOL, (n, m)
     assert got[o].shape == (2, 1000, 1, 1)
+
+
+def test_concat_by_offset_is_bit_identical(oracle):
+    """GoogLeNet's inception branches write straight into the Concat output (no copy kernels); asking run_fwd for a branch node materialises
+    it from that slice. Every node must equal the copy-based path (concat_by_offset=0) bit for bit, incl. the split-K branches at this batch."""
+    import boda_b200 as bb
+    from boda_b200 import nets
+    txt, i, o = nets.googlenet_conv(2)
+    params = nets.synth_params(txt)
+    x = nets.synth_input((2, 3, 224, 224))
+    names = _node_names(txt)
+    outs = []
+    for opts in ("(concat_by_offset=1)", "(concat_by_offset=0)"):
+        fwd = bb.B200ConvFwd(txt, opts)
+        for k, v in params.items():
+            fwd.set_param(k, v)
+        outs.append((fwd.run_fwd({i: x}, names), fwd.num_calls()))
+    (a, calls_a), (b, calls_b) = outs
+    assert calls_a < calls_b - 30, (calls_a, calls_b)  # 36 Concat copies gone
+    for n in names:
+        assert np.array_equal(a[n], b[n]), n
