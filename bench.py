@@ -117,7 +117,9 @@ def cpu_reference_forward(n_images, reps=1):
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    sample = 4  # images per step: ~1-2 s of CPU work; the whole K+W run stays within a few minutes
+    # images per step: the full 32-image batch when the whole K+W run then stays within ~3 minutes (the port does ~20 images/s on 16 cores and
+    # parallelises over images and output channels, so small samples under-use the cores), else a bounded sample of it
+    sample = int(max(4, min(PER_GPU_BATCH, 180.0 / max(args.steps + args.warmup, 1) / 0.05)))
     for _ in range(args.warmup):
         cpu_reference_forward(sample)
     t0 = time.perf_counter()
