@@ -583,6 +583,16 @@ struct run_ctx_t {
       pk.src_ptr = src.buf->p;
       return;
     }
+    if (kmajor_rows == 0 && dst_chi_stride == 0 && dst_base == 0 && (Cc % 4) == 0 && Cc >= 512 && c_inner >= Cc) {  // big plain-NHWC activations: wide tiles
+      dim3 const g4(ceil_div(Rpad, 64), ceil_div(Cc, 128), B);
+      size_t const smem4 = 64 * 129 * sizeof(float);
+      if (bf16) { B200_CARVEOUT_ONCE(b200::pack_xpose_split_v4_kernel<true>); launch_k(b200::pack_xpose_split_v4_kernel<true>, g4, dim3(256), smem4, fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, Cc, Rpad, dst_c_stride, dst_b_stride, absmax_src); }
+      else { B200_CARVEOUT_ONCE(b200::pack_xpose_split_v4_kernel<false>); launch_k(b200::pack_xpose_split_v4_kernel<false>, g4, dim3(256), smem4, fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, Cc, Rpad, dst_c_stride, dst_b_stride, absmax_src); }
+      launched();
+      pk.src_gen = *src.gen;
+      pk.src_ptr = src.buf->p;
+      return;
+    }
     if (bf16) { B200_CARVEOUT_ONCE(b200::pack_xpose_split_kernel<true>); launch_k(b200::pack_xpose_split_kernel<true>, dim3(grid), dim3(256), 0, fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, Cc, Rpad, dst_c_stride, dst_b_stride, c_inner, dst_chi_stride, dst_base, absmax_src, kmajor_rows); }
     else { B200_CARVEOUT_ONCE(b200::pack_xpose_split_kernel<false>); launch_k(b200::pack_xpose_split_kernel<false>, dim3(grid), dim3(256), 0, fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, Cc, Rpad, dst_c_stride, dst_b_stride, c_inner, dst_chi_stride, dst_base, absmax_src, kmajor_rows); }
     launched();

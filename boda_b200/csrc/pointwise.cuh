@@ -142,15 +142,28 @@ reduce_sum_kernel(ReduceArgs a, float *__restrict__ out, long long n, int relu, 
   long long done = 0;
   if (vec4) {
     long long const n4 = n >> 2;
-    for (long long i = tid; i < n4; i += nthr) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    constexpr int kU = 4;  // four independent 128-bit loads per input in flight per thread
+    for (long long i0 = tid; i0 < n4; i0 += nthr * kU) {
+      float4 v[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) { v[u] = make_float4(0.f, 0.f, 0.f, 0.f); }
       for (int j = 0; j < a.ins_num; ++j) {
-        float4 const x = __ldg(reinterpret_cast<float4 const *>(a.ins[j]) + i);
-        v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+        float4 x[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) { long long const i = i0 + u * nthr; x[u] = (i < n4) ? __ldg(reinterpret_cast<float4 const *>(a.ins[j]) + i) : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) { v[u].x += x[u].x; v[u].y += x[u].y; v[u].z += x[u].z; v[u].w += x[u].w; }
       }
-      if (relu) { v.x = (v.x <= 0) ? 0.0f : v.x; v.y = (v.y <= 0) ? 0.0f : v.y; v.z = (v.z <= 0) ? 0.0f : v.z; v.w = (v.w <= 0) ? 0.0f : v.w; }
-      reinterpret_cast<float4 *>(out)[i] = v;
-      m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        long long const i = i0 + u * nthr;
+        if (i < n4) {
+          float4 w = v[u];
+          if (relu) { w.x = (w.x <= 0) ? 0.0f : w.x; w.y = (w.y <= 0) ? 0.0f : w.y; w.z = (w.z <= 0) ? 0.0f : w.z; w.w = (w.w <= 0) ? 0.0f : w.w; }
+          reinterpret_cast<float4 *>(out)[i] = w;
+          m = fmaxf(m, fmaxf(fmaxf(fabsf(w.x), fabsf(w.y)), fmaxf(fabsf(w.z), fabsf(w.w))));
+        }
+      }
     }
     done = n4 << 2;
   }
@@ -571,6 +584,58 @@ pack_xpose_split_kernel(float const *__restrict__ src, uint16_t *__restrict__ hi
           if (lo) {
             *reinterpret_cast<__half2 *>(lo + o) = __half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
           }
+        }
+      }
+    }
+  }
+}
+
+// Wide-tile variant for the big activation tensors (ResNet / GoogLeNet: 56x56, 28x28, 14x14 maps, pixel counts divisible by 4): a CTA moves a
+// 64-channel x 128-pixel tile, every thread has eight 128-bit loads in flight (512-byte runs per channel row instead of 128), the
+// transposed read of shared memory is conflict-free at a row pitch of 129 floats, stores are 128-byte rows of half2 as before. Plain NHWC
+// destination only: dst[b][pixel][chan] with pitch dst_c_stride.
+template <bool kBf16>
+__global__ void __launch_bounds__(256)
+pack_xpose_split_v4_kernel(float const *__restrict__ src, uint16_t *__restrict__ hi, uint16_t *__restrict__ lo, float const *__restrict__ scale2,
+                           int R, int C, int Rpad, long long dst_c_stride, long long dst_b_stride, unsigned int const *__restrict__ absmax_bits) {
+  pdl_prologue();
+  constexpr int kPitch = 129;
+  extern __shared__ float tile_v4[];  // [64][kPitch]
+  int const tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  int const r0 = blockIdx.x * 64, c0 = blockIdx.y * 128;
+  long long const b = blockIdx.z;
+  float const s = absmax_bits ? scale_from_absmax_bits(*absmax_bits) : scale2[0];
+  if (absmax_bits && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) { const_cast<float *>(scale2)[0] = s; const_cast<float *>(scale2)[1] = 1.0f / s; }
+  float const *sp = src + b * static_cast<long long>(R) * C;
+  int const c = c0 + 4 * tx;
+  float4 v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {  // all loads first
+    int const r = r0 + ty + 8 * k;
+    v[k] = (r < R && c < C) ? __ldg(reinterpret_cast<float4 const *>(sp + static_cast<long long>(r) * C + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float *t = tile_v4 + (ty + 8 * k) * kPitch + 4 * tx;
+    t[0] = v[k].x * s; t[1] = v[k].y * s; t[2] = v[k].z * s; t[3] = v[k].w * s;
+  }
+  __syncthreads();
+  int const r = r0 + 2 * tx;
+  if (r < Rpad) {
+#pragma unroll 4
+    for (int cc = ty; cc < 128; cc += 8) {
+      int const cpix = c0 + cc;
+      if (cpix < C) {
+        float const v0 = tile_v4[(2 * tx) * kPitch + cc], v1 = tile_v4[(2 * tx + 1) * kPitch + cc];
+        long long const o = b * dst_b_stride + static_cast<long long>(cpix) * dst_c_stride + r;
+        if (kBf16) {
+          __nv_bfloat16 const h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+          *reinterpret_cast<__nv_bfloat162 *>(hi + o) = __nv_bfloat162(h0, h1);
+          if (lo) { *reinterpret_cast<__nv_bfloat162 *>(lo + o) = __nv_bfloat162(__float2bfloat16_rn(v0 - __bfloat162float(h0)), __float2bfloat16_rn(v1 - __bfloat162float(h1))); }
+        } else {
+          __half const h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+          *reinterpret_cast<__half2 *>(hi + o) = __half2(h0, h1);
+          if (lo) { *reinterpret_cast<__half2 *>(lo + o) = __half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1))); }
         }
       }
     }
