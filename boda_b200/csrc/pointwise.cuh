@@ -312,26 +312,32 @@ pool_plane_kernel(float const *__restrict__ in, float *__restrict__ out, int H, 
   __syncthreads();
   float amax = 0.0f;
   float *op = out + plane0 * ohw;
+  // (plane, oy, ox) of output o = threadIdx.x + 256 k, advanced by fixed deltas with carries instead of two integer divisions per output; every
+  // tap's bounds test is two unsigned compares (the kernel was issue-bound: ~140 instructions per output, ncu)
+  int pl = threadIdx.x / ohw, p0 = threadIdx.x - pl * ohw;
+  int oy = p0 / OW, ox = p0 - oy * OW;
+  int const d_pl = 256 / ohw, d_p = 256 - d_pl * ohw, d_oy = d_p / OW, d_ox = d_p - d_oy * OW;
+  float const pad_v = avg_pool ? 0.0f : -FLT_MAX;
   for (int o = threadIdx.x; o < n_out; o += 256) {
-    int const pl = o / ohw, p = o - pl * ohw;
-    int const oy = p / OW, ox = p - oy * OW;
     int const y0 = oy * S - py, x0 = ox * S - px;
-    float const *ps = plane_s + pl * hw;
-    float out_v = avg_pool ? 0.0f : -FLT_MAX, cnt = 0;
+    float const *ps = plane_s + pl * hw + y0 * W + x0;
+    float out_v = pad_v, cnt = 0.0f;
 #pragma unroll
     for (int kx = 0; kx < K; ++kx) {
+      bool const xok = static_cast<unsigned>(x0 + kx) < static_cast<unsigned>(W);
 #pragma unroll
       for (int ky = 0; ky < K; ++ky) {
-        int const in_y = y0 + ky, in_x = x0 + kx;
-        if (in_y >= 0 && in_x >= 0 && in_x < W && in_y < H) {
-          float const v = ps[in_y * W + in_x];
-          if (avg_pool) { out_v += v; cnt += 1; } else { out_v = fmaxf(out_v, v); }
-        }
+        bool const ok = xok && static_cast<unsigned>(y0 + ky) < static_cast<unsigned>(H);
+        float const v = ok ? ps[ky * W + kx] : pad_v;
+        if (avg_pool) { out_v += v; cnt += ok ? 1.0f : 0.0f; } else { out_v = fmaxf(out_v, v); }
       }
     }
     if (avg_pool) { out_v = __fdiv_rn(out_v, cnt); }
     op[o] = out_v;
     amax = fmaxf(amax, fabsf(out_v));
+    ox += d_ox; oy += d_oy; pl += d_pl;
+    if (ox >= OW) { ox -= OW; ++oy; }
+    if (oy >= OH) { oy -= OH; ++pl; }
   }
   if (out_absmax) { publish_absmax_warp(amax, out_absmax); }
 }
