@@ -450,6 +450,11 @@ void b200_compute_t::compile(vect_rtc_func_info_t const &func_infos, rtc_compile
     impl->funcs[fi.func_name] = f;
   }
 }
+bool b200_compute_t::conv_plane_writable(op_base_t const &op) {
+  conv_plan_t cp;
+  plan_conv(cp, op, impl->num_sms);
+  return prec == B200_PREC_BF16 && !cp.swapped && cp.splits == 1 && (cp.OC % 8) == 0;
+}
 void b200_compute_t::release_func(string const &func_name) {
   if (!impl->funcs.erase(func_name)) { rt_err("release_func: '" + func_name + "' not found"); }
 }
@@ -857,6 +862,29 @@ struct run_ctx_t {
       out_base = fptr(*vcat) + (long long)ocix * cp.OH * cp.OW;
       if (cp.splits == 1) { prm.out_chans = (int)vcat->dims.dsz("chan"); }  // split-K partials keep this layer's own geometry; the reduce kernel strides
     }
+    // bf16 storage mode + "out_pack": also write the NHWC bf16 plane the consuming convolutions read (shared act_packs entry of the destination
+    // var), so they find it fresh and skip their pack kernel. Needs 16-byte aligned runs: channel offset and channel count multiples of 8.
+    packed_t *out_pk = nullptr;
+    var_info_t &vdst = vcat ? *vcat : vout;
+    if (bf16 && has_arg("out_pack") && scalar("out_pack") != 0 && !cp.swapped && cp.splits == 1 && (cp.OC % 8) == 0) {
+      int const ocix = vcat ? (int)scalar("out_ocix") : 0;
+      int const cdst = (int)vdst.dims.dsz("chan"), cdst_pad = (int)round_up(cdst, 8);
+      if ((ocix % 8) == 0) {
+        out_pk = &im.act_packs[vdst.buf->p];
+        uint64_t const bytes = (uint64_t)cp.N * cp.OH * cp.OW * cdst_pad * 2;
+        if (!out_pk->hi || out_pk->hi->bytes < bytes) {
+          out_pk->hi = std::make_shared<dev_buf_t>(bytes);
+          CU_CHK(cudaMemsetAsync(out_pk->hi->p, 0, bytes, st));
+          out_pk->scale2 = std::make_shared<dev_buf_t>(8);
+          out_pk->absmax_bits = std::make_shared<dev_buf_t>(4);
+          CU_CHK(cudaMemsetAsync(out_pk->absmax_bits->p, 0, 4, st));
+          static float const ones[2] = {1.0f, 1.0f};
+          CU_CHK(cudaMemcpyAsync(out_pk->scale2->p, ones, 8, cudaMemcpyHostToDevice, st));
+        }
+        prm.out16 = static_cast<uint16_t *>(out_pk->hi->p) + ocix;
+        prm.out16_pitch = cdst_pad;
+      }
+    }
     if (cp.splits > 1) {
       uint64_t const need = (uint64_t)cp.splits * out_elems * 4;
       if (!f.splitk_ws || f.splitk_ws->bytes < need) { f.splitk_ws = std::make_shared<dev_buf_t>(need); }
@@ -882,7 +910,8 @@ struct run_ctx_t {
                vcat ? (long long)vcat->dims.dsz("chan") * cp.OH * cp.OW : 0ll);
       launched();
     }
-    im.bump(vcat ? *vcat : vout);
+    im.bump(vdst);
+    if (out_pk) { out_pk->src_gen = *vdst.gen; out_pk->src_ptr = vdst.buf->p; }  // the plane is current for this write generation: consumers skip their pack
   }
   static constexpr uint32_t IGEMM_BM_host() { return b200::IGEMM_BM; }
 

@@ -195,6 +195,57 @@ void b200_conv_fwd_t::add_absmax_args(map_str_rtc_arg_t &args, string const &whi
   args[which + "_absmax_ix"] = rtc_arg_t(make_scalar_nda<uint32_t>(i->second, "uint32_t"));
 }
 
+op_base_t b200_conv_fwd_t::conv_fop(conv_op_t const &op) const {
+  op_base_t fop;
+  fop.str_vals = op.str_vals;
+  fop.nda_vals = op.nda_vals;
+  dims_t const &fd = cp->must_get_node(op.bots[1])->dims;
+  fop.set_dims("in", cp->must_get_node(op.bots[0])->dims);
+  fop.set_dims("filts", fd);
+  fop.set_dims("biases", dims_t({fd.dsz("out_chan")}, {"out_chan"}, "float"));
+  fop.set_dims("out", cp->must_get_node(op.tops[0])->dims);
+  return fop;
+}
+
+// A destination node (a convolution's own output, or the Concat output its channels are written into) gets its NHWC plane from its
+// producers when: some Convolution with more than 8 input channels reads it (the row-merged small-channel path packs differently); every
+// producer is a convolution that can write the plane (b200_compute_t::conv_plane_writable) at a channel offset that is a multiple of 8;
+// for a Concat, every input is written in place (else the plane would have holes); and nothing modifies the node afterwards except the
+// ops the convolution already absorbs (folded BatchNorm / Scale, fused ReLU) or Dropout (identity).
+bool b200_conv_fwd_t::dst_plane_by_producers(string const &dst) {
+  if (!pack_by_producers) { return false; }
+  p_conv_node_t dn = cp->must_get_node(dst);
+  bool feeds = false;
+  for (auto const &o : cp->ops) { if (o->is("Convolution") && !o->bots.empty() && o->bots[0] == dst && dn->dims.dsz("chan") > 8) { feeds = true; } }
+  if (!feeds) { return false; }
+  vector<p_conv_op_t> producers;
+  bool is_cat = false;
+  for (auto const &o : cp->ops) {
+    if (o->is("Concat") && o->tops[0] == dst) {
+      is_cat = true;
+      for (auto const &b : o->bots) {
+        auto al = concat_alias.find(b);
+        if (al == concat_alias.end() || (al->second.ocix % 8) != 0) { return false; }
+        for (auto const &w : cp->ops) { if (w->is("Convolution") && w->tops[0] == b) { producers.push_back(w); } }
+      }
+    }
+  }
+  if (!is_cat) { for (auto const &w : cp->ops) { if (w->is("Convolution") && w->tops[0] == dst) { producers.push_back(w); } } }
+  if (producers.empty()) { return false; }
+  for (auto const &w : producers) { if (!rtc->conv_plane_writable(conv_fop(*w))) { return false; } }
+  for (auto const &ip : dn->in_place_ops) {
+    if (ip->is("Dropout") || ip->is("BatchNorm") || ip->is("Scale")) { continue; }
+    if (ip->is("ReLU") && !is_cat && ip == dn->in_place_ops[0]) { continue; }  // the one the convolution fuses
+    if (ip->is("ReLU") && !is_cat) {  // ReLU right after the folded BatchNorm / Scale ops is fused too
+      size_t k = 0;
+      while (k < dn->in_place_ops.size() && (dn->in_place_ops[k]->is("BatchNorm") || dn->in_place_ops[k]->is("Scale"))) { ++k; }
+      if (k < dn->in_place_ops.size() && dn->in_place_ops[k] == ip) { continue; }
+    }
+    return false;
+  }
+  return true;
+}
+
 void b200_conv_fwd_t::gen_op(p_conv_op_t const &op) {
   if (op->fused) { return; }  // folded into its producer (src/rtc_fwd.cc:266)
   op_base_t fop;              // function signature: op params + the dims of every argument (conv_op_t::set_arg_dims_and_map_from_pipe)
@@ -259,6 +310,8 @@ void b200_conv_fwd_t::gen_op(p_conv_op_t const &op) {
       args["out_ocix"] = rtc_arg_t(make_scalar_nda<uint32_t>(al->second.ocix, "uint32_t"));
       add_absmax_args(args, "out", al->second.cat_node);
     } else { add_absmax_args(args, "out", op->tops[0]); }
+    // layout-transform elimination (bf16 storage mode): also write the NHWC plane the consuming convolutions read (they then skip their pack)
+    if (dst_plane_by_producers((al != concat_alias.end()) ? al->second.cat_node : op->tops[0])) { args["out_pack"] = rtc_arg_t(make_scalar_nda<uint32_t>(1, "uint32_t")); }
     add_call("conv", *op, fop, args);
   } else if (op->is("Pooling")) {
     map_str_rtc_arg_t args{{"in", op->bots[0]}, {"out", op->tops[0]}};
@@ -325,6 +378,7 @@ void b200_conv_fwd_t::init(p_conv_pipe_t const &cp_, string const &opts) {
         else if (k == "device") { rtc->device = std::stoi(v); }
         else if (k == "enable_prof") { enable_prof = (uint32_t)std::stoul(v); }
         else if (k == "concat_by_offset") { concat_by_offset = (uint32_t)std::stoul(v); }
+        else if (k == "pack_by_producers") { pack_by_producers = (uint32_t)std::stoul(v); }
         else { rt_err("mode=b200: unused option '" + k + "'"); }  // NESI rejects unused keys (src/nesi.cc:25-35)
       }
     }

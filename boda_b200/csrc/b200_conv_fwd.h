@@ -44,6 +44,7 @@ struct b200_conv_fwd_t {
   // options (conv_pipe_fwd_t fields, src/rtc_fwd.cc:48-66, reduced to what applies)
   uint32_t use_graph = 1;      // replay the forward calls as one CUDA graph (launch-bound at B200 speeds)
   uint32_t enable_prof = 0;
+  uint32_t pack_by_producers = 1; // bf16 storage mode: convolutions also write the NHWC bf16 plane their consumers read (no activation pack kernel)
   uint32_t concat_by_offset = 1;  // Convolutions that only feed a Concat write straight into its output at their channel offset (no copy kernel);
                                   // their own node is materialised from that slice only when run_fwd is asked for it
   p_b200_compute_t rtc;
@@ -97,7 +98,9 @@ struct b200_conv_fwd_t {
   map<string, uint32_t> absmax_ix;  // nodes whose producer publishes max|x| for the consuming convolution's operand scaling
   struct concat_alias_t { string cat_node; uint32_t ocix; string extract_func; };
   map<string, concat_alias_t> concat_alias;  // node -> (Concat output that holds its channels, channel offset, name of the read-back function)
-  void materialise_aliased(string const &node);  // enqueue the slice copy Concat output -> node var (before reading an aliased node)
+  void materialise_aliased(string const &node);
+  op_base_t conv_fop(conv_op_t const &op) const;  // function signature of a Convolution op: its params + the dims of in / filts / biases / out
+  bool dst_plane_by_producers(string const &dst);  // bf16 mode: every producer of node `dst` can write its NHWC plane and some conv reads it  // enqueue the slice copy Concat output -> node var (before reading an aliased node)
   void add_absmax_args(map_str_rtc_arg_t &args, string const &which, string const &node);
 };
 

@@ -21,6 +21,7 @@
 #pragma once
 #include "umma.cuh"
 #include <cuda_fp16.h>
+#include <cuda_bf16.h>
 
 namespace b200 {
 
@@ -64,6 +65,11 @@ struct IgemmParams {
   // k-block-major operand layout [k-block][rows][64] (packed filters): rows per k-block, 0 = plain row-major [rows][K]
   int p_kb_rows, q_kb_rows;
   int m_pair_tiles, q_tiles;  // persistent CTA-pair kernel (igemm2.cuh): 256-row tiles along P, BN-wide tiles along Q
+  // bf16 storage mode, layout-transform elimination: besides the fp32 NCHW node the epilogue also writes the NHWC bf16
+  // plane the consuming convolutions read ([pixel][out16_pitch] elements, already offset to this layer's first channel), so they skip
+  // their activation pack. null = off.
+  uint16_t *out16;
+  int out16_pitch;
 };
 
 // TMEM columns reserved per accumulator buffer: BN rounded up to a power of two (BN = 96 accumulators sit at 128-column offsets)
@@ -132,6 +138,29 @@ __device__ __forceinline__ float igemm_store_row(float const (&acc)[BN], float i
     o += 4 * stride;
   }
   return amax;
+}
+
+// Second output of a pixel row in bf16 storage mode: the same values (scale, bias, floor) rounded to bf16 and written as 16-byte runs into
+// the consumer's NHWC plane. `dst` is 16-byte aligned (channel offsets and pitches are multiples of 8 elements).
+template <int BN>
+__device__ __forceinline__ void igemm_store_row_bf16(float const (&acc)[BN], float inv, float const *bias_s, float floor_v, uint16_t *dst, int nvalid) {
+  uint32_t const bias_sa = smem_u32(bias_s);
+#pragma unroll
+  for (int j = 0; j < BN; j += 8) {
+    if (j < nvalid) {  // nvalid is a multiple of 8 on this path (host-checked)
+      float b[8];
+      asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b[0]), "=f"(b[1]), "=f"(b[2]), "=f"(b[3]) : "r"(bias_sa + 4 * j));
+      asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b[4]), "=f"(b[5]), "=f"(b[6]), "=f"(b[7]) : "r"(bias_sa + 4 * j + 16));
+      uint32_t w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float const v0 = fmaxf(fmaf(acc[j + 2 * k], inv, b[2 * k]), floor_v), v1 = fmaxf(fmaf(acc[j + 2 * k + 1], inv, b[2 * k + 1]), floor_v);
+        __nv_bfloat162 const h = __floats2bfloat162_rn(v0, v1);
+        w[k] = *reinterpret_cast<uint32_t const *>(&h);
+      }
+      *reinterpret_cast<uint4 *>(dst + j) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
 }
 
 template <int BN, int kPlanes>
@@ -339,6 +368,7 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
         int const img = prow / prm.out_hw, pix = prow - img * prm.out_hw;
         float *o = outp + (static_cast<long long>(img) * prm.out_chans + n0) * prm.out_hw + pix;
         amax = igemm_store_row<BN>(acc, inv, bias_s, floor_v, o, prm.out_hw, prm.q_rows - n0);
+        if (kPlanes == 1 && prm.out16 && final_out) { igemm_store_row_bf16<BN>(acc, inv, bias_s, floor_v, prm.out16 + static_cast<long long>(prow) * prm.out16_pitch + n0, prm.q_rows - n0); }
       } else {  // row = channel, columns = pixels
         int const ch = prow;
         float const b = (final_out && prm.has_bias) ? __ldg(prm.bias + ch) : 0.0f;

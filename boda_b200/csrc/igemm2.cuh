@@ -244,6 +244,7 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
         int const img = prow / prm.out_hw, pix = prow - img * prm.out_hw;
         float *o = prm.out + (static_cast<long long>(img) * prm.out_chans + n0) * prm.out_hw + pix;
         amax = fmaxf(amax, igemm_store_row<BN>(acc, inv, bias_t, floor_v, o, prm.out_hw, prm.q_rows - n0));
+        if (kPlanes == 1 && prm.out16) { igemm_store_row_bf16<BN>(acc, inv, bias_t, floor_v, prm.out16 + static_cast<long long>(prow) * prm.out16_pitch + n0, prm.q_rows - n0); }
       }
     }
     if (prm.out_absmax) {

@@ -249,3 +249,29 @@ def test_concat_by_offset_is_bit_identical(oracle):
     assert calls_a < calls_b - 30, (calls_a, calls_b)  # 36 Concat copies gone
     for n in names:
         assert np.array_equal(a[n], b[n]), n
+
+
+@pytest.mark.parametrize("net,batch,in_sz", [("googlenet_conv", 8, 224), ("resnet50", 4, 224), ("nin_imagenet", 8, 227)])
+def test_bf16_planes_written_by_producers_are_bit_identical(net, batch, in_sz):
+    """bf16 storage mode: convolutions also write the NHWC bf16 plane their consumers read (layout-transform elimination), so those consumers
+    skip their activation pack. The plane holds bf16(the fp32 node value), exactly what the pack kernel would produce: every output must be
+    bit-identical to the pack-based path, with fewer kernels launched."""
+    import boda_b200 as bb
+    from boda_b200 import nets
+    txt, i, o = nets.NETS[net](batch)
+    params = nets.synth_params(txt)
+    x = nets.synth_input((batch, 3, in_sz, in_sz))
+    names = _node_names(txt)[-12:] + [o]
+    res = []
+    for opts in ("(prec=bf16,pack_by_producers=1)", "(prec=bf16,pack_by_producers=0)"):
+        fwd = bb.B200ConvFwd(txt, opts)
+        for k, v in params.items():
+            fwd.set_param(k, v)
+        out = fwd.run_fwd({i: x}, names)
+        l0 = fwd.launches()
+        fwd.run_fwd({i: x}, [o])
+        res.append((out, fwd.launches() - l0))
+    (a, la), (b, lb) = res
+    assert la < lb, (la, lb)
+    for n in names:
+        assert np.array_equal(a[n], b[n]), n
