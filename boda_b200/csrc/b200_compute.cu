@@ -551,17 +551,19 @@ struct run_ctx_t {
       CU_CHK(cudaMemsetAsync(pk.hi->p, 0, total_elems * 2, st));
       if (want_lo) { pk.lo = std::make_shared<dev_buf_t>(total_elems * 2); CU_CHK(cudaMemsetAsync(pk.lo->p, 0, total_elems * 2, st)); }
       pk.scale2 = std::make_shared<dev_buf_t>(8);
-      pk.absmax_bits = std::make_shared<dev_buf_t>(4);
-      CU_CHK(cudaMemsetAsync(pk.absmax_bits->p, 0, 4, st));
+      pk.absmax_bits = std::make_shared<dev_buf_t>(8);  // {max bits, blocks-done counter}
+      CU_CHK(cudaMemsetAsync(pk.absmax_bits->p, 0, 8, st));
+      if (bf16) { static float const ones[2] = {1.0f, 1.0f}; CU_CHK(cudaMemcpyAsync(pk.scale2->p, ones, 8, cudaMemcpyHostToDevice, st)); }  // bf16 has fp32's exponent range: no scaling, ever
     }
     long long const n = (long long)B * R * Cc;
     int const blocks = (int)std::min<long long>((n + 4095) / 4096, 148 * 8);
     bool const use_scale = !bf16;  // bf16 has fp32's exponent range: no scaling needed
     if (!use_scale) { absmax_src = nullptr; }
     if (!absmax_src) {  // nobody published max|x| for this tensor: reduce it here
-      if (use_scale) { B200_CARVEOUT_ONCE(b200::absmax_kernel); launch_k(b200::absmax_kernel, dim3(std::max(blocks, 1)), dim3(256), 0, fptr(src), n, static_cast<unsigned int *>(pk.absmax_bits->p)); launched(); }
-      B200_CARVEOUT_ONCE(b200::finalize_scale_kernel); launch_k(b200::finalize_scale_kernel, dim3(1), dim3(1), 0, static_cast<unsigned int *>(pk.absmax_bits->p), static_cast<float *>(pk.scale2->p), use_scale ? 1 : 0);
-      launched();
+      if (use_scale) {  // max|x| and the scale in one launch (the last block finalises)
+        B200_CARVEOUT_ONCE(b200::absmax_kernel); launch_k(b200::absmax_kernel, dim3(std::max(blocks, 1)), dim3(256), 0, fptr(src), n, static_cast<unsigned int *>(pk.absmax_bits->p), static_cast<float *>(pk.scale2->p));
+        launched();
+      }  // bf16: scale2 = {1, 1} was written when the planes were allocated
     }
     dim3 grid(ceil_div(Rpad, 64), ceil_div(Cc, 32), B);
     uint16_t *hi = static_cast<uint16_t *>(pk.hi->p), *lo = want_lo ? static_cast<uint16_t *>(pk.lo->p) : nullptr;
@@ -876,8 +878,8 @@ struct run_ctx_t {
           out_pk->hi = std::make_shared<dev_buf_t>(bytes);
           CU_CHK(cudaMemsetAsync(out_pk->hi->p, 0, bytes, st));
           out_pk->scale2 = std::make_shared<dev_buf_t>(8);
-          out_pk->absmax_bits = std::make_shared<dev_buf_t>(4);
-          CU_CHK(cudaMemsetAsync(out_pk->absmax_bits->p, 0, 4, st));
+          out_pk->absmax_bits = std::make_shared<dev_buf_t>(8);
+          CU_CHK(cudaMemsetAsync(out_pk->absmax_bits->p, 0, 8, st));
           static float const ones[2] = {1.0f, 1.0f};
           CU_CHK(cudaMemcpyAsync(out_pk->scale2->p, ones, 8, cudaMemcpyHostToDevice, st));
         }

@@ -442,8 +442,11 @@ __global__ void softmax_kernel(float const *__restrict__ in, float *__restrict__
 }
 
 // ---- operand pack: abs-max -> power-of-two scale -> transpose + 16-bit split ----------------------------------
-// absmax over a tensor (non-negative floats order like their bit patterns, so atomicMax on uint works).
-__global__ void absmax_kernel(float const *__restrict__ x, long long n, unsigned int *__restrict__ out_bits) {
+// absmax over a tensor (non-negative floats order like their bit patterns, so atomicMax on uint works) + the power-of-two operand scale
+// derived from it: cells = {max bits, blocks-done counter}; the LAST block to finish turns the max into {scale, 1/scale} and re-arms
+// the cells, so no separate one-thread "finalize" launch is needed. Four independent 128-bit loads in flight per thread.
+__global__ void __launch_bounds__(256)
+absmax_kernel(float const *__restrict__ x, long long n, unsigned int *__restrict__ cells, float *__restrict__ scale2) {
   pdl_prologue();
   float m = 0.0f;
   long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -451,17 +454,37 @@ __global__ void absmax_kernel(float const *__restrict__ x, long long n, unsigned
   if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) {
     long long const n4 = n >> 2;
     float4 const *x4 = reinterpret_cast<float4 const *>(x);
-    for (long long i = tid; i < n4; i += stride) {
-      float4 const v = __ldg(x4 + i);
-      m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    for (long long i0 = tid; i0 < n4; i0 += 4 * stride) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { long long const i = i0 + u * stride; v[u] = (i < n4) ? __ldg(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { m = fmaxf(m, fmaxf(fmaxf(fabsf(v[u].x), fabsf(v[u].y)), fmaxf(fabsf(v[u].z), fabsf(v[u].w)))); }
     }
     for (long long i = (n4 << 2) + tid; i < n; i += stride) { m = fmaxf(m, fabsf(__ldg(x + i))); }
   } else {
     for (long long i = tid; i < n; i += stride) { m = fmaxf(m, fabsf(__ldg(x + i))); }
   }
+  __shared__ float warp_m[8];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o)); }
-  if ((threadIdx.x & 31) == 0 && m > 0.0f) { atomicMax(out_bits, __float_as_uint(m)); }
+  if ((threadIdx.x & 31) == 0) { warp_m[threadIdx.x >> 5] = m; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float bm = 0.0f;
+    for (int w = 0; w < 8; ++w) { bm = fmaxf(bm, warp_m[w]); }
+    if (bm > 0.0f) { atomicMax(cells, __float_as_uint(bm)); }
+    __threadfence();
+    unsigned int const ticket = atomicAdd(cells + 1, 1u);
+    if (ticket == gridDim.x - 1) {  // every block's max is in: publish the scale, re-arm the cells for the next use
+      __threadfence();
+      float const s = scale_from_absmax_bits(*reinterpret_cast<volatile unsigned int *>(cells));
+      scale2[0] = s;
+      scale2[1] = 1.0f / s;
+      cells[0] = 0u;
+      cells[1] = 0u;
+    }
+  }
 }
 __global__ void finalize_scale_kernel(unsigned int *__restrict__ bits, float *__restrict__ scale2, int use_scale) {
   pdl_prologue();
