@@ -66,6 +66,8 @@ struct func_t {
   string gen_arg;  // gen_data: name of the output argument
   conv_plan_t cp;
   packed_t w_pack, a_pack;  // conv: filts / in ; sgemm: b / a
+  p_dev_buf_t w_l1max;      // conv: max over out chans of sum |w| (bound of the outputs, for producer-written fp16 planes)
+  uint64_t w_l1max_gen = ~0ull;
   p_dev_buf_t splitk_ws;
 };
 
@@ -450,10 +452,13 @@ void b200_compute_t::compile(vect_rtc_func_info_t const &func_infos, rtc_compile
     impl->funcs[fi.func_name] = f;
   }
 }
-bool b200_compute_t::conv_plane_writable(op_base_t const &op) {
+bool b200_compute_t::conv_plane_writable(op_base_t const &op, bool dst_is_concat) {
   conv_plan_t cp;
   plan_conv(cp, op, impl->num_sms);
-  return prec == B200_PREC_BF16 && !cp.swapped && cp.splits == 1 && (cp.OC % 8) == 0;
+  // the fp16 planes of the fp32-parity / fp16 modes carry a per-tensor scale that each producer derives from its own output bound: several
+  // producers of one Concat output would not agree on it, so those modes write planes for a convolution's own output node only
+  if (prec != B200_PREC_BF16 && dst_is_concat) { return false; }
+  return !cp.swapped && cp.splits == 1 && (cp.OC % 8) == 0;
 }
 void b200_compute_t::release_func(string const &func_name) {
   if (!impl->funcs.erase(func_name)) { rt_err("release_func: '" + func_name + "' not found"); }
@@ -868,15 +873,16 @@ struct run_ctx_t {
     // var), so they find it fresh and skip their pack kernel. Needs 16-byte aligned runs: channel offset and channel count multiples of 8.
     packed_t *out_pk = nullptr;
     var_info_t &vdst = vcat ? *vcat : vout;
-    if (bf16 && has_arg("out_pack") && scalar("out_pack") != 0 && !cp.swapped && cp.splits == 1 && (cp.OC % 8) == 0) {
+    if (has_arg("out_pack") && scalar("out_pack") != 0 && !cp.swapped && cp.splits == 1 && (cp.OC % 8) == 0 && (bf16 || !vcat)) {
       int const ocix = vcat ? (int)scalar("out_ocix") : 0;
       int const cdst = (int)vdst.dims.dsz("chan"), cdst_pad = (int)round_up(cdst, 8);
       if ((ocix % 8) == 0) {
         out_pk = &im.act_packs[vdst.buf->p];
         uint64_t const bytes = (uint64_t)cp.N * cp.OH * cp.OW * cdst_pad * 2;
-        if (!out_pk->hi || out_pk->hi->bytes < bytes) {
+        if (!out_pk->hi || out_pk->hi->bytes < bytes || (planes == 2 && !out_pk->lo)) {
           out_pk->hi = std::make_shared<dev_buf_t>(bytes);
           CU_CHK(cudaMemsetAsync(out_pk->hi->p, 0, bytes, st));
+          if (planes == 2) { out_pk->lo = std::make_shared<dev_buf_t>(bytes); CU_CHK(cudaMemsetAsync(out_pk->lo->p, 0, bytes, st)); }
           out_pk->scale2 = std::make_shared<dev_buf_t>(8);
           out_pk->absmax_bits = std::make_shared<dev_buf_t>(8);
           CU_CHK(cudaMemsetAsync(out_pk->absmax_bits->p, 0, 8, st));
@@ -885,6 +891,21 @@ struct run_ctx_t {
         }
         prm.out16 = static_cast<uint16_t *>(out_pk->hi->p) + ocix;
         prm.out16_pitch = cdst_pad;
+        if (!bf16) {  // fp16 planes: scale from the output bound (IgemmParams::w_l1max); the filter L1 norm is computed once per weight version
+          if (!f.w_l1max) { f.w_l1max = std::make_shared<dev_buf_t>(4); }
+          if (f.w_l1max_gen != *vf.gen) {
+            CU_CHK(cudaMemsetAsync(f.w_l1max->p, 0, 4, st));
+            B200_CARVEOUT_ONCE(b200::filts_l1max_kernel);
+            launch_k(b200::filts_l1max_kernel, dim3(cp.OC), dim3(256), 0, fptr(vf), (long long)(vf.dims.dims_prod() / cp.OC), static_cast<unsigned int *>(f.w_l1max->p));
+            launched();
+            f.w_l1max_gen = *vf.gen;
+          }
+          prm.w_l1max = static_cast<float *>(f.w_l1max->p);
+          prm.out16_lo = planes == 2 ? static_cast<uint16_t *>(out_pk->lo->p) + ocix : nullptr;
+          prm.out16_scale2 = static_cast<float *>(out_pk->scale2->p);
+          prm.n_bias = cp.OC;
+          prm.in_absmax = absmax_cell("in");
+        }
       }
     }
     if (cp.splits > 1) {

@@ -105,10 +105,10 @@ struct b200_compute_t {
   p_nda_t create_nda_from_var(string const &vn) { p_nda_t r = std::make_shared<nda_t>(get_var_dims(vn)); copy_var_to_nda(r, vn); return r; }
 
   // --- extensions used by the C ABI / whole-net driver ---
-  // can the convolution described by `op` (type + in/filts/out dims + params) also write the consumer's NHWC bf16 plane ("out_pack")? Static:
+  // can the convolution described by `op` (type + in/filts/out dims + params) also write the consumer's NHWC 16-bit plane(s) ("out_pack")? Static:
   // depends only on its plan (not an inner-product-shaped / split-K layer, out_chans a multiple of 8). Every producer of a destination var must
   // be able to, or none may be asked to -- the whole-net driver decides per destination with this.
-  bool conv_plane_writable(op_base_t const &op);
+  bool conv_plane_writable(op_base_t const &op, bool dst_is_concat);
   bool has_var(string const &vn) const;
   bool has_func(string const &fn) const;
   void copy_raw_to_var(string const &vn, void const *src, uint64_t bytes);   // host -> device (async on the stream, then sync)

@@ -232,7 +232,7 @@ bool b200_conv_fwd_t::dst_plane_by_producers(string const &dst) {
   }
   if (!is_cat) { for (auto const &w : cp->ops) { if (w->is("Convolution") && w->tops[0] == dst) { producers.push_back(w); } } }
   if (producers.empty()) { return false; }
-  for (auto const &w : producers) { if (!rtc->conv_plane_writable(conv_fop(*w))) { return false; } }
+  for (auto const &w : producers) { if (!rtc->conv_plane_writable(conv_fop(*w), is_cat)) { return false; } }
   for (auto const &ip : dn->in_place_ops) {
     if (ip->is("Dropout") || ip->is("BatchNorm") || ip->is("Scale")) { continue; }
     if (ip->is("ReLU") && !is_cat && ip == dn->in_place_ops[0]) { continue; }  // the one the convolution fuses

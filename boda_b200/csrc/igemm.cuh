@@ -20,6 +20,7 @@
 // (TMEM lane quarter = warp_id % 4).
 #pragma once
 #include "umma.cuh"
+#include "scale.cuh"
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 
@@ -70,6 +71,16 @@ struct IgemmParams {
   // their activation pack. null = off.
   uint16_t *out16;
   int out16_pitch;
+  // fp32-parity / fp16 modes: the same, with the consumer's hi (+ lo) fp16 planes. Their power-of-two scale must be known BEFORE this kernel
+  // has seen its outputs, so it comes from an upper bound: |out| <= max_oc sum_k |w[oc,k]| * max|in| + max|bias|, with max|in| < 2^14 / s_in
+  // from the input operand's own scale. A bound 2^5..2^7 above the true maximum costs nothing: fp16 is floating point, hi keeps 11 bits at any
+  // magnitude and lo stays normal for every element within ~2^10 of the largest. Every CTA derives the same scale; CTA 0 publishes it.
+  uint16_t *out16_lo;          // null in the single-plane modes
+  float const *w_l1max;        // max over out chans of sum |w| (one float, computed once per weight version); null = out16 is a bf16 plane (no scale)
+  float *out16_scale2;         // {scale, 1/scale} of the destination planes
+  int n_bias;                  // number of biases (out chans) for the max|bias| term
+  unsigned int const *in_absmax;  // optional: the TRUE max|in| its producer published (bit pattern); else 2^14 / s_in bounds it. Using the true
+                                  // value keeps the overestimate from compounding along a chain of convolutions.
 };
 
 // TMEM columns reserved per accumulator buffer: BN rounded up to a power of two (BN = 96 accumulators sit at 128-column offsets)
@@ -161,6 +172,48 @@ __device__ __forceinline__ void igemm_store_row_bf16(float const (&acc)[BN], flo
       *reinterpret_cast<uint4 *>(dst + j) = make_uint4(w[0], w[1], w[2], w[3]);
     }
   }
+}
+
+// fp16 hi (+ lo) planes of a pixel row, scaled by the bound-derived power of two `s_out` (see IgemmParams::w_l1max)
+template <int BN>
+__device__ __forceinline__ void igemm_store_row_split16(float const (&acc)[BN], float inv, float const *bias_s, float floor_v, float s_out, uint16_t *dst_hi,
+                                                        uint16_t *dst_lo, int nvalid) {
+  uint32_t const bias_sa = smem_u32(bias_s);
+#pragma unroll
+  for (int j = 0; j < BN; j += 8) {
+    if (j < nvalid) {
+      float b[8];
+      asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b[0]), "=f"(b[1]), "=f"(b[2]), "=f"(b[3]) : "r"(bias_sa + 4 * j));
+      asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b[4]), "=f"(b[5]), "=f"(b[6]), "=f"(b[7]) : "r"(bias_sa + 4 * j + 16));
+      uint32_t wh[4], wl[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float const t0 = fmaxf(fmaf(acc[j + 2 * k], inv, b[2 * k]), floor_v) * s_out, t1 = fmaxf(fmaf(acc[j + 2 * k + 1], inv, b[2 * k + 1]), floor_v) * s_out;
+        __half2 const h = __floats2half2_rn(t0, t1);
+        float2 const hf = __half22float2(h);
+        __half2 const l = __floats2half2_rn(t0 - hf.x, t1 - hf.y);
+        wh[k] = *reinterpret_cast<uint32_t const *>(&h);
+        wl[k] = *reinterpret_cast<uint32_t const *>(&l);
+      }
+      *reinterpret_cast<uint4 *>(dst_hi + j) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+      if (dst_lo) { *reinterpret_cast<uint4 *>(dst_lo + j) = make_uint4(wl[0], wl[1], wl[2], wl[3]); }
+    }
+  }
+}
+
+// The destination planes' scale from the output bound, computed by the 128 epilogue threads of a CTA (named barrier 1); `red` = 4 floats of smem
+__device__ __forceinline__ float igemm_out_scale(IgemmParams const &prm, float *red, int row /*0..127*/) {
+  float bm = 0.0f;
+  if (prm.has_bias) { for (int j = row; j < prm.n_bias; j += 128) { bm = fmaxf(bm, fabsf(__ldg(prm.bias + j))); } }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, o)); }
+  if ((row & 31) == 0) { red[row >> 5] = bm; }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  bm = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  float in_bound = 16384.0f * prm.p_scale[1];  // max|in| < 2^14 / s_in
+  if (prm.in_absmax) { float const t = __uint_as_float(*prm.in_absmax); if (t > 0.0f) { in_bound = fminf(in_bound, t); } }
+  float const bound = (__ldg(prm.w_l1max) * in_bound + bm) * 1.01f;
+  return scale_from_absmax_bits(__float_as_uint(bound));
 }
 
 template <int BN, int kPlanes>
@@ -359,6 +412,11 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
     // ---- write out: NCHW fp32 (or split-K partial) ----
     float const inv = prm.p_scale[1] * prm.q_scale[1];
     bool const final_out = (prm.split_stride == 0);
+    float s_out = 1.0f;
+    if (prm.out16 && prm.w_l1max) {  // (host: only for non-swapped, non-split launches) -- see IgemmParams::w_l1max
+      s_out = igemm_out_scale(prm, reinterpret_cast<float *>(bar_mem + 256), row);
+      if (blockIdx.x == 0 && blockIdx.y == 0 && row == 0) { prm.out16_scale2[0] = s_out; prm.out16_scale2[1] = 1.0f / s_out; }
+    }
     float const floor_v = (final_out && prm.relu) ? 0.0f : -INFINITY;
     int const prow = m0 + row;
     float amax = 0.0f;
@@ -368,7 +426,11 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
         int const img = prow / prm.out_hw, pix = prow - img * prm.out_hw;
         float *o = outp + (static_cast<long long>(img) * prm.out_chans + n0) * prm.out_hw + pix;
         amax = igemm_store_row<BN>(acc, inv, bias_s, floor_v, o, prm.out_hw, prm.q_rows - n0);
-        if (kPlanes == 1 && prm.out16 && final_out) { igemm_store_row_bf16<BN>(acc, inv, bias_s, floor_v, prm.out16 + static_cast<long long>(prow) * prm.out16_pitch + n0, prm.q_rows - n0); }
+        if (prm.out16 && final_out) {
+          long long const o16 = static_cast<long long>(prow) * prm.out16_pitch + n0;
+          if (prm.w_l1max) { igemm_store_row_split16<BN>(acc, inv, bias_s, floor_v, s_out, prm.out16 + o16, prm.out16_lo ? prm.out16_lo + o16 : nullptr, prm.q_rows - n0); }
+          else { igemm_store_row_bf16<BN>(acc, inv, bias_s, floor_v, prm.out16 + o16, prm.q_rows - n0); }
+        }
       } else {  // row = channel, columns = pixels
         int const ch = prow;
         float const b = (final_out && prm.has_bias) ? __ldg(prm.bias + ch) : 0.0f;

@@ -196,6 +196,11 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
     float const inv = prm.p_scale[1] * prm.q_scale[1];
     float const floor_v = prm.relu ? 0.0f : -INFINITY;
     float amax = 0.0f;
+    float s_out = 1.0f;
+    if (prm.out16 && prm.w_l1max) {  // scale of the consumer's fp16 planes from the output bound (identical in every CTA); CTA 0 publishes it
+      s_out = igemm_out_scale(prm, reinterpret_cast<float *>(bar_mem + 768), row);
+      if (blockIdx.x == 0 && row == 0) { prm.out16_scale2[0] = s_out; prm.out16_scale2[1] = 1.0f / s_out; }
+    }
     int gc = 0, ti = 0;
     for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++ti) {
       int const mt = tile / q_tiles, nt = tile - mt * q_tiles;
@@ -244,7 +249,11 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
         int const img = prow / prm.out_hw, pix = prow - img * prm.out_hw;
         float *o = prm.out + (static_cast<long long>(img) * prm.out_chans + n0) * prm.out_hw + pix;
         amax = fmaxf(amax, igemm_store_row<BN>(acc, inv, bias_t, floor_v, o, prm.out_hw, prm.q_rows - n0));
-        if (kPlanes == 1 && prm.out16) { igemm_store_row_bf16<BN>(acc, inv, bias_t, floor_v, prm.out16 + static_cast<long long>(prow) * prm.out16_pitch + n0, prm.q_rows - n0); }
+        if (prm.out16) {
+          long long const o16 = static_cast<long long>(prow) * prm.out16_pitch + n0;
+          if (prm.w_l1max) { igemm_store_row_split16<BN>(acc, inv, bias_t, floor_v, s_out, prm.out16 + o16, prm.out16_lo ? prm.out16_lo + o16 : nullptr, prm.q_rows - n0); }
+          else { igemm_store_row_bf16<BN>(acc, inv, bias_t, floor_v, prm.out16 + o16, prm.q_rows - n0); }
+        }
       }
     }
     if (prm.out_absmax) {

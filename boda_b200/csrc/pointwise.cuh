@@ -8,6 +8,7 @@
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include "pdl.cuh"
+#include "scale.cuh"
 
 namespace b200 {
 
@@ -22,20 +23,6 @@ __device__ __forceinline__ void publish_absmax_warp(float m, unsigned int *cell)
     if (bits > *reinterpret_cast<volatile unsigned int *>(cell)) { atomicMax(cell, bits); }
   }
 }
-// scale = 2^(13 - floor(log2(absmax))): scaled values land in [2^13, 2^14), well inside fp16 range with most lo-plane residuals normal
-__device__ __forceinline__ float scale_from_absmax_bits(unsigned int bits) {
-  float const m = __uint_as_float(bits);
-  float s = 1.0f;
-  if (m > 0.0f && isfinite(m)) {
-    int e;
-    frexpf(m, &e);  // m = f * 2^e, f in [0.5,1)  -> floor(log2 m) = e-1
-    int sh = 13 - (e - 1);
-    sh = max(-100, min(100, sh));
-    s = ldexpf(1.0f, sh);
-  }
-  return s;
-}
-
 // ---- gen_data (test/rtc/gen-util.h:1-9 and test/rtc/gen_data_*.cucl) -----------------------------------------
 __device__ __forceinline__ float det_hash_rand(uint32_t rv) {
   uint32_t h = rv;
@@ -175,6 +162,25 @@ reduce_sum_kernel(ReduceArgs a, float *__restrict__ out, long long n, int relu, 
     m = fmaxf(m, fabsf(v));
   }
   if (out_absmax) { publish_absmax_warp(m, out_absmax); }
+}
+
+// ---- filter row L1 norm (parameter-only): max over out chans of sum_k |w[oc, k]|, for the output bound of IgemmParams::w_l1max. grid = out chans.
+__global__ void __launch_bounds__(256)
+filts_l1max_kernel(float const *__restrict__ filts, long long per_oc, unsigned int *__restrict__ out_bits) {
+  pdl_prologue();
+  float const *w = filts + static_cast<long long>(blockIdx.x) * per_oc;
+  float s = 0.0f;
+  for (long long i = threadIdx.x; i < per_oc; i += 256) { s += fabsf(__ldg(w + i)); }
+  __shared__ float warp_s[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); }
+  if ((threadIdx.x & 31) == 0) { warp_s[threadIdx.x >> 5] = s; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int k = 0; k < 8; ++k) { t += warp_s[k]; }
+    atomicMax(out_bits, __float_as_uint(t));  // non-negative floats order like their bit patterns
+  }
 }
 
 // ---- BatchNorm / Scale folding (parameter-only) ---------------------------------------------------------------

@@ -251,11 +251,14 @@ def test_concat_by_offset_is_bit_identical(oracle):
         assert np.array_equal(a[n], b[n]), n
 
 
-@pytest.mark.parametrize("net,batch,in_sz", [("googlenet_conv", 8, 224), ("resnet50", 4, 224), ("nin_imagenet", 8, 227)])
-def test_bf16_planes_written_by_producers_are_bit_identical(net, batch, in_sz):
-    """bf16 storage mode: convolutions also write the NHWC bf16 plane their consumers read (layout-transform elimination), so those consumers
-    skip their activation pack. The plane holds bf16(the fp32 node value), exactly what the pack kernel would produce: every output must be
-    bit-identical to the pack-based path, with fewer kernels launched."""
+@pytest.mark.parametrize("prec", ["bf16", "fp32", "fp16"])
+@pytest.mark.parametrize("net,batch,in_sz", [("googlenet_conv", 8, 224), ("resnet50", 4, 224), ("nin_imagenet", 8, 227), ("alexnet_ng_conv", 32, 227)])
+def test_planes_written_by_producers(oracle, net, batch, in_sz, prec):
+    """Layout-transform elimination: convolutions also write the NHWC 16-bit plane(s) their consumers read, so those skip their activation pack.
+    bf16: the plane holds bf16(the fp32 node value), exactly what the pack kernel would produce -> every output BIT-IDENTICAL to the pack-based
+    path. fp32-parity / fp16: the planes' power-of-two scale comes from an output bound instead of the true maximum -> same values up to the
+    rounding of the lo plane: mrd < 5e-4 against the pack-based path at the end of a 12-layer net, and (NiN, where the oracle is cheap) both
+    within the usual 1e-3 of the oracle. Fewer kernels launched in every mode."""
     import boda_b200 as bb
     from boda_b200 import nets
     txt, i, o = nets.NETS[net](batch)
@@ -263,8 +266,8 @@ def test_bf16_planes_written_by_producers_are_bit_identical(net, batch, in_sz):
     x = nets.synth_input((batch, 3, in_sz, in_sz))
     names = _node_names(txt)[-12:] + [o]
     res = []
-    for opts in ("(prec=bf16,pack_by_producers=1)", "(prec=bf16,pack_by_producers=0)"):
-        fwd = bb.B200ConvFwd(txt, opts)
+    for on in (1, 0):
+        fwd = bb.B200ConvFwd(txt, "(prec=%s,pack_by_producers=%d)" % (prec, on))
         for k, v in params.items():
             fwd.set_param(k, v)
         out = fwd.run_fwd({i: x}, names)
@@ -274,4 +277,13 @@ def test_bf16_planes_written_by_producers_are_bit_identical(net, batch, in_sz):
     (a, la), (b, lb) = res
     assert la < lb, (la, lb)
     for n in names:
-        assert np.array_equal(a[n], b[n]), n
+        if prec == "bf16":
+            assert np.array_equal(a[n], b[n]), n
+        else:
+            assert np.isfinite(a[n]).all() and oracle.mrd(a[n], b[n]) < 5e-4, (n, oracle.mrd(a[n], b[n]))
+    if net == "nin_imagenet" and prec == "fp32":
+        from oracle import net_oracle
+        ref = net_oracle.run_pipe(txt, {i: x}, params, acc64=True)
+        ma, mb = oracle.mrd(ref[o], a[o]), oracle.mrd(ref[o], b[o])
+        print("nin b=8 fp32 output mrd vs acc64 oracle: producer-written planes %.2e, pack kernels %.2e" % (ma, mb))
+        assert ma < TOL and mb < TOL
