@@ -289,12 +289,22 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
     conv_rows = [r for r in prof if r[3] > 0]
-    conv_flops = sum(r[3] for r in conv_rows)
-    conv_bytes = 4.0 * nets.conv_algorithmic_elems(txt)  # (in + out + filts + biases) x 4 B per Convolution, each tensor once (src/latex-util.H:119)
-    conv_kernel_ms = sum(r[2] for r in conv_rows)
+    per_op = nets.conv_algorithmic_elems(txt, per_op=True)  # tag -> ((in + out + filts + biases) elements, output pixels per image)
+    def _tag(func):
+        return func.split("__")[1]
+    # the DOMINANT kernel = the persistent CTA-pair contraction kernel (igemm2.cuh) behind every convolution with a spatial output; the
+    # inner-product-shaped layers (1x1 output: M = batch rows) run the one-CTA split-K kernel and are bound by streaming their weights from HBM
+    dom_rows = [r for r in conv_rows if per_op.get(_tag(r[0]), (0, 2))[1] > 1]
+    fc_rows = [r for r in conv_rows if per_op.get(_tag(r[0]), (0, 2))[1] <= 1]
+    conv_flops = sum(r[3] for r in dom_rows)
+    conv_bytes = 4.0 * sum(per_op.get(_tag(r[0]), (0, 0))[0] for r in dom_rows)  # each tensor once, fp32 (src/latex-util.H:119)
+    conv_kernel_ms = sum(r[2] for r in dom_rows)
     peaks = measured_peaks()
     achieved_tf = conv_flops / (conv_kernel_ms * 1e-3) / 1e12 if conv_kernel_ms > 0 else 0.0
     peak_tf = peaks["bf16_tflops"]
+    fc_bytes = 4.0 * sum(per_op.get(_tag(r[0]), (0, 0))[0] for r in fc_rows)
+    fc_ms = sum(r[2] for r in fc_rows)
+    all_flops, all_ms = sum(r[3] for r in conv_rows), sum(r[2] for r in conv_rows)
 
     if rank == 0:
         global_batch = B * world
@@ -313,13 +323,18 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None,
                          "traffic": committed_traffic()[0] if (args.net, args.prec) == ("alexnet_ng_conv", "fp32") else None, "traffic_source": committed_traffic()[1],
-                         "algorithmic_bytes_per_launch": conv_bytes / max(len(conv_rows), 1),
-                         "kernel": "b200::igemm_umma_2cta_kernel (persistent CTA pairs) / igemm_umma_kernel (fc-shaped layers): %d launches per forward, one per Convolution" % len(conv_rows),
+                         "algorithmic_flops_per_launch": conv_flops / max(len(dom_rows), 1), "algorithmic_bytes_per_launch": conv_bytes / max(len(dom_rows), 1),
+                         "avg_launch_ms": conv_kernel_ms / max(len(dom_rows), 1),
+                         "kernel": "b200::igemm_umma_2cta_kernel (persistent CTA pairs, tcgen05 cta_group::2): %d launches per forward, one per Convolution with a spatial output" % len(dom_rows),
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernels timed one by one with CUDA events), %s" % peaks["source"],
                          "mma_passes": 3 if args.prec == "fp32" else 1,
                          "tensor_work_frac": (achieved_tf * (3 if args.prec == "fp32" else 1) / peak_tf) if peak_tf else None,
-                         "note": "achieved = algorithmic conv FLOPs / summed launch durations of ALL contraction launches (incl. the HBM-bound fc-shaped layers); "
-                                 "the fp32-parity mode issues 3 fp16 MMAs per product (mma_passes), so tensor_work_frac = achieved x mma_passes / peak is the share of the tensor pipe's peak actually kept busy"},
+                         "note": "achieved = algorithmic conv FLOPs / summed CUDA-event launch durations of the dominant kernel's launches; the fp32-parity mode issues "
+                                 "3 fp16 MMAs per product (mma_passes), so tensor_work_frac = achieved x mma_passes / peak is the share of the tensor pipe's peak actually kept busy",
+                         "all_contraction_launches": {"launches": len(conv_rows), "achieved": all_flops / (all_ms * 1e-3) / 1e12 if all_ms > 0 else None, "unit": "TFLOP/s"},
+                         "fc_shaped_layers": {"bound": "hbm", "launches": len(fc_rows), "kernel": "b200::igemm_umma_kernel (weights as the 128-row operand, split-K)",
+                                              "achieved": fc_bytes / (fc_ms * 1e-3) / 1e9 if fc_ms > 0 else None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                              "frac": (fc_bytes / (fc_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if fc_ms > 0 else None}},
             "clocks": sampler.summary(),
             "per_call": [{"func": r[0], "call_ms": round(r[1], 5), "kernel_ms": round(r[2], 5), "gflop": round(r[3] / 1e9, 3)} for r in prof],
         }

@@ -356,23 +356,28 @@ def conv_param_shapes(pipe_text: str) -> Dict[str, Tuple[int, ...]]:
     return shapes
 
 
-def conv_algorithmic_elems(pipe_text: str) -> int:
+def conv_algorithmic_elems(pipe_text: str, per_op: bool = False):
     """Sum over the Convolution ops of numel(in) + numel(out) + numel(filts) + numel(biases): the reference's algorithmic-bytes figure / 4
-    (src/latex-util.H:119, pysrc/flops.py:101), from the C++ pipe IR's dims inference."""
+    (src/latex-util.H:119, pysrc/flops.py:101), from the C++ pipe IR's dims inference. per_op=True: {tag: (elems, out_pixels_per_image)}."""
     import re
     import boda_b200 as bb
     d = bb.pipe_describe(pipe_text)
     tot = 0
+    ops = {}
     for line in pipe_text.splitlines():
         if "type=Convolution" not in line and "type=InnerProduct" not in line:
             continue
         tag = re.search(r"tag=([^,]+),", line).group(1)
         bot = re.search(r"bots=([^,)]+)", line).group(1).split(":")[0]
         top = re.search(r"tops=([^,)]+)", line).group(1).split(":")[0]
+        e = 0
         for n in (bot, top, tag + "_filts", tag + "_biases"):
             if n in d["nodes"]:
-                tot += int(np.prod([sz for _, sz in d["nodes"][n]]))
-    return tot
+                e += int(np.prod([sz for _, sz in d["nodes"][n]]))
+        tot += e
+        td = dict(d["nodes"][top])
+        ops[tag] = (e, td["y"] * td["x"])
+    return ops if per_op else tot
 
 
 def synth_params(pipe_text: str, seed: int = 0) -> Dict[str, np.ndarray]:
