@@ -1008,16 +1008,49 @@ struct run_ctx_t {
       // planes per CTA: a multiple of 4 (16-byte aligned runs), tile <= 48 KB, and at least ~4 CTAs per SM left to fill the chip
       int ppc = (int)std::max<long long>(4, std::min<long long>((48 * 1024) / ((long long)H * W * 4) / 4 * 4, round_up(ceil_div(planes, 4 * im.num_sms), 4)));
       if ((long long)ppc * H * W * 4 > 96 * 1024) { ppc = 1; }
-      size_t const smem = (size_t)ppc * H * W * 4;
+      // "out_pack": also write the NHWC 16-bit planes the consuming convolution reads. Needs groups of 8 channels of one image per CTA and
+      // (fp16 planes) the producer-published max|in| for the scale.
+      int const C = (int)vin.dims.dsz("chan");
+      bool const bf16 = (rtc.prec == B200_PREC_BF16);
+      int const npl = (rtc.prec == B200_PREC_FP32_SPLIT) ? 2 : 1;
+      b200::PoolPlanes pp;
+      memset(&pp, 0, sizeof(pp));
+      packed_t *out_pk = nullptr;
+      unsigned int *in_cell = bf16 ? nullptr : absmax_cell("in");
+      if (has_arg("out_pack") && scalar("out_pack") != 0 && (C % 8) == 0 && (bf16 || in_cell)) {
+        int ppc8 = (int)round_up(ppc, 8);
+        while (ppc8 > 8 && ((C % ppc8) != 0 || (long long)ppc8 * (H * W + OH * OW) * 4 > 100 * 1024)) { ppc8 -= 8; }
+        if ((C % ppc8) == 0 && (long long)ppc8 * (H * W + OH * OW) * 4 <= 100 * 1024) {
+          ppc = ppc8;
+          int const cpad = (int)round_up(C, 8);
+          out_pk = &im.act_packs[vout.buf->p];
+          uint64_t const bytes = (uint64_t)vout.dims.dsz("img") * OH * OW * cpad * 2;
+          if (!out_pk->hi || out_pk->hi->bytes < bytes || (npl == 2 && !out_pk->lo)) {
+            out_pk->hi = std::make_shared<dev_buf_t>(bytes);
+            CU_CHK(cudaMemsetAsync(out_pk->hi->p, 0, bytes, st));
+            if (npl == 2) { out_pk->lo = std::make_shared<dev_buf_t>(bytes); CU_CHK(cudaMemsetAsync(out_pk->lo->p, 0, bytes, st)); }
+            out_pk->scale2 = std::make_shared<dev_buf_t>(8);
+            out_pk->absmax_bits = std::make_shared<dev_buf_t>(8);
+            CU_CHK(cudaMemsetAsync(out_pk->absmax_bits->p, 0, 8, st));
+          }
+          pp.hi = static_cast<uint16_t *>(out_pk->hi->p);
+          pp.lo = npl == 2 ? static_cast<uint16_t *>(out_pk->lo->p) : nullptr;
+          pp.scale2 = static_cast<float *>(out_pk->scale2->p);
+          pp.in_absmax = in_cell;
+          pp.C = C; pp.cpad = cpad; pp.bf16 = bf16 ? 1 : 0;
+        }
+      }
+      size_t const smem = (size_t)ppc * (H * W + (pp.hi ? OH * OW : 0)) * 4;
       unsigned int *cell = absmax_cell("out");
 #define B200_POOL_PLANE(K_, S_) do { \
         static bool attr_ = false; \
-        if (!attr_) { CU_CHK(cudaFuncSetAttribute(b200::pool_plane_kernel<K_, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); prefer_max_smem(b200::pool_plane_kernel<K_, S_>); attr_ = true; } \
-        launch_k(b200::pool_plane_kernel<K_, S_>, dim3((unsigned)ceil_div(planes, ppc)), dim3(256), smem, fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, cell, ppc, planes); } while (0)
+        if (!attr_) { CU_CHK(cudaFuncSetAttribute(b200::pool_plane_kernel<K_, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); prefer_max_smem(b200::pool_plane_kernel<K_, S_>); attr_ = true; } \
+        launch_k(b200::pool_plane_kernel<K_, S_>, dim3((unsigned)ceil_div(planes, ppc)), dim3(256), smem, fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, cell, ppc, planes, pp); } while (0)
       if (KH == 3 && sy == 2) { B200_POOL_PLANE(3, 2); } else if (KH == 3) { B200_POOL_PLANE(3, 1); } else { B200_POOL_PLANE(2, 2); }
 #undef B200_POOL_PLANE
       launched();
       im.bump(vout);
+      if (out_pk) { out_pk->src_gen = *vout.gen; out_pk->src_ptr = vout.buf->p; }  // the planes are current: the consuming convolution skips its pack
       return;
     }
     if (KH == KW && sy == sx && ((KH == 3 && sy == 2) || (KH == 3 && sy == 1) || (KH == 2 && sy == 2)) && planes <= 65535) {

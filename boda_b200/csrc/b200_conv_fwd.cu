@@ -316,6 +316,16 @@ void b200_conv_fwd_t::gen_op(p_conv_op_t const &op) {
   } else if (op->is("Pooling")) {
     map_str_rtc_arg_t args{{"in", op->bots[0]}, {"out", op->tops[0]}};
     add_absmax_args(args, "out", op->tops[0]);
+    {  // layout-transform elimination: the pool kernel also writes the NHWC planes of a Convolution that reads its output (no in-place ops between)
+      p_conv_node_t on = cp->must_get_node(op->tops[0]);
+      bool feeds = false, clean = true;
+      for (auto const &o : cp->ops) { if (o->is("Convolution") && !o->bots.empty() && o->bots[0] == op->tops[0] && on->dims.dsz("chan") > 8) { feeds = true; } }
+      for (auto const &ip : on->in_place_ops) { if (!ip->is("Dropout")) { clean = false; } }
+      if (pack_by_producers && feeds && clean) {
+        add_absmax_args(args, "in", op->bots[0]);
+        args["out_pack"] = rtc_arg_t(make_scalar_nda<uint32_t>(1, "uint32_t"));
+      }
+    }
     add_call("pool", *op, fop, args);
   } else if (op->is("LRN")) {
     map_str_rtc_arg_t args{{"in", op->bots[0]}, {"out", op->tops[0]}};
@@ -397,7 +407,13 @@ void b200_conv_fwd_t::init(p_conv_pipe_t const &cp_, string const &opts) {
     for (auto const &o : cp->ops) { if (o->tag == n.top_for[0]) { writer = o; } }
     if (!writer || !(writer->is("Convolution") || writer->is("Pooling") || writer->is("LRN") || writer->is("Concat") || writer->is("Eltwise") || writer->is("Reduce"))) { continue; }
     bool feeds_conv = false;
-    for (auto const &o : cp->ops) { if (o->is("Convolution") && !o->bots.empty() && o->bots[0] == n.name) { feeds_conv = true; } }
+    for (auto const &o : cp->ops) {
+      if (o->is("Convolution") && !o->bots.empty() && o->bots[0] == n.name) { feeds_conv = true; }
+      // ... or a Pooling op whose output a Convolution reads: the pool kernel scales the planes it writes for that convolution by max|in|
+      if (o->is("Pooling") && !o->bots.empty() && o->bots[0] == n.name) {
+        for (auto const &o2 : cp->ops) { if (o2->is("Convolution") && !o2->bots.empty() && o2->bots[0] == o->tops[0]) { feeds_conv = true; } }
+      }
+    }
     if (feeds_conv) { uint32_t const ix = (uint32_t)absmax_ix.size(); absmax_ix[n.name] = ix; }
   }
   rtc->create_var_with_dims(absmax_cells_vn, dims_t({(uint32_t)std::max<size_t>(absmax_ix.size(), 1)}, {"cell"}, "uint32_t"));

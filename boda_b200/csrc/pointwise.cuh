@@ -283,6 +283,14 @@ pool_kernel_fixed(float const *__restrict__ in, float *__restrict__ out, int H, 
   if (out_absmax) { publish_absmax_warp(valid ? fabsf(out_v) : 0.0f, out_absmax); }
 }
 
+// optional second output of pool_plane_kernel: the consumer convolution's NHWC 16-bit planes (see the end of the kernel)
+struct PoolPlanes {
+  uint16_t *hi, *lo;              // null hi = off; lo only in the fp32-parity mode
+  float *scale2;                  // {scale, 1/scale} of the planes
+  unsigned int const *in_absmax;  // max|in| bit pattern (fp16 planes); null = bf16 planes, scale 1
+  int C, cpad, bf16;              // channels of the pooled node, its padded NHWC pitch, storage type
+};
+
 // Plane-group variant: one CTA stages kPPC consecutive (img,chan) planes -- a CONTIGUOUS run of kPPC*H*W floats -- in shared memory with
 // 128-bit loads and computes their kPPC*OH*OW outputs (also contiguous) from there, so the overlapping stride-S window reads never touch
 // L1/L2 and both global streams are long coalesced runs. Small planes (13x13, 27x27) would otherwise mean thousands of tiny CTAs that
@@ -291,7 +299,7 @@ pool_kernel_fixed(float const *__restrict__ in, float *__restrict__ out, int H, 
 template <int K, int S>
 __global__ void __launch_bounds__(256)
 pool_plane_kernel(float const *__restrict__ in, float *__restrict__ out, int H, int W, int OH, int OW, int py, int px, int avg_pool,
-                  unsigned int *out_absmax, int ppc, long long n_planes) {
+                  unsigned int *out_absmax, int ppc, long long n_planes, PoolPlanes pp) {
   pdl_prologue();
   extern __shared__ __align__(16) float plane_s[];
   long long const plane0 = static_cast<long long>(blockIdx.x) * ppc;
@@ -340,12 +348,46 @@ pool_plane_kernel(float const *__restrict__ in, float *__restrict__ out, int H, 
     }
     if (avg_pool) { out_v = __fdiv_rn(out_v, cnt); }
     op[o] = out_v;
+    if (pp.hi) { plane_s[n_in + o] = out_v; }  // staged for the transposed (NHWC) plane write below
     amax = fmaxf(amax, fabsf(out_v));
     ox += d_ox; oy += d_oy; pl += d_pl;
     if (ox >= OW) { ox -= OW; ++oy; }
     if (oy >= OH) { oy -= OH; ++pl; }
   }
   if (out_absmax) { publish_absmax_warp(amax, out_absmax); }
+  if (pp.hi) {
+    // Layout-transform elimination: also write the NHWC 16-bit plane(s) the consuming convolution reads (it then skips its pack kernel). The
+    // CTA's planes are np (a multiple of 8) consecutive channels of ONE image, so every pixel gets 16-byte runs of 8 channels. The fp16 planes'
+    // power-of-two scale comes from max|in| (published by the producer of the pooled node): pooling never increases max|x|.
+    float const s = pp.in_absmax ? scale_from_absmax_bits(*pp.in_absmax) : 1.0f;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { pp.scale2[0] = s; pp.scale2[1] = 1.0f / s; }
+    __syncthreads();
+    long long const img = plane0 / pp.C;
+    int const chan0 = static_cast<int>(plane0 - img * pp.C), groups = np >> 3;
+    float const *os = plane_s + n_in;
+    for (int idx = threadIdx.x; idx < ohw * groups; idx += 256) {
+      int const pix = idx / groups, g = idx - pix * groups;
+      uint32_t wh[4], wl[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float const t0 = os[(8 * g + 2 * k) * ohw + pix] * s, t1 = os[(8 * g + 2 * k + 1) * ohw + pix] * s;
+        if (pp.bf16) {
+          __nv_bfloat162 const h = __floats2bfloat162_rn(t0, t1);
+          wh[k] = *reinterpret_cast<uint32_t const *>(&h);
+          wl[k] = 0u;
+        } else {
+          __half2 const h = __floats2half2_rn(t0, t1);
+          float2 const hf = __half22float2(h);
+          __half2 const l = __floats2half2_rn(t0 - hf.x, t1 - hf.y);
+          wh[k] = *reinterpret_cast<uint32_t const *>(&h);
+          wl[k] = *reinterpret_cast<uint32_t const *>(&l);
+        }
+      }
+      long long const o16 = (img * ohw + pix) * pp.cpad + chan0 + 8 * g;
+      *reinterpret_cast<uint4 *>(pp.hi + o16) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+      if (pp.lo) { *reinterpret_cast<uint4 *>(pp.lo + o16) = make_uint4(wl[0], wl[1], wl[2], wl[3]); }
+    }
+  }
 }
 
 // ---- lrn (test/rtc/lrn.cucl:35-50, LRN_MATCH_CAFFE branch) ----------------------------------------------------
