@@ -77,6 +77,9 @@ _SIGS = {
     "b200_fwd_launches": (_c.c_uint64, [_c.c_void_p]),
     "b200_fwd_profile": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_char_p, _c.c_int, _c.POINTER(_c.c_float), _c.POINTER(_c.c_float), _c.POINTER(_c.c_double), _c.c_int]),
     "b200_fwd_run_timed": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_uint64, _c.POINTER(_c.c_float)]),
+    "b200_fwd_get_stream": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_void_p)]),
+    "b200_fwd_enqueue": (_c.c_int, [_c.c_void_p]),
+    "b200_fwd_flush_l2": (_c.c_int, [_c.c_void_p, _c.c_uint64]),
     "b200_fwd_get_node_raw_native_pointer": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.POINTER(_c.c_void_p)]),
     "b200_rtc_get_kernel_dur": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.POINTER(_c.c_float)]),
 }
@@ -398,6 +401,19 @@ class B200ConvFwd:
         ms = (_c.c_float * max(iters, 1))()
         _chk(lib().b200_fwd_run_timed(self._h, iters, l2_flush_bytes, ms))
         return [float(ms[i]) for i in range(iters)]
+
+    def stream_ptr(self) -> int:
+        """The back-end's cudaStream_t, e.g. for torch.cuda.ExternalStream."""
+        p = _c.c_void_p()
+        _chk(lib().b200_fwd_get_stream(self._h, ctypes.byref(p)))
+        return int(p.value or 0)
+
+    def enqueue(self):
+        """Queue one forward on device-resident inputs; returns without synchronising."""
+        _chk(lib().b200_fwd_enqueue(self._h))
+
+    def flush_l2(self, nbytes: int):
+        _chk(lib().b200_fwd_flush_l2(self._h, nbytes))
 
     def node_device_ptr(self, name: str) -> int:
         p = _c.c_void_p()

@@ -250,6 +250,9 @@ B200_API int b200_fwd_run_timed(b200_fwd *f, int iters, uint64_t l2_flush_bytes,
     return 0;
   });
 }
+B200_API int b200_fwd_enqueue(b200_fwd *f) { return guarded([&] { f->fwd->enqueue_fwd(); return 0; }); }
+B200_API int b200_fwd_flush_l2(b200_fwd *f, uint64_t bytes) { return guarded([&] { f->fwd->flush_l2(bytes); return 0; }); }
+B200_API int b200_fwd_get_stream(b200_fwd *f, void **stream_out) { return guarded([&] { *stream_out = f->fwd->stream(); return 0; }); }
 B200_API int b200_fwd_get_node_raw_native_pointer(b200_fwd *f, const char *node_name, void **dev_ptr_out) {
   return guarded([&] { *dev_ptr_out = f->fwd->rtc->get_var_raw_native_pointer(node_name)->rp_elems(); return 0; });
 }

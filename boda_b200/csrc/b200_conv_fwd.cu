@@ -626,21 +626,32 @@ vector<b200_conv_fwd_t::prof_row_t> b200_conv_fwd_t::profile(int iters) {
   return res;
 }
 
+void b200_conv_fwd_t::flush_l2(uint64_t bytes) {
+  if (!bytes) { return; }
+  if (bytes > flush_bytes) {
+    if (flush_buf) { CU_CHK(cudaStreamSynchronize(rtc->stream())); cudaFree(flush_buf); flush_buf = nullptr; }
+    CU_CHK(cudaMalloc(&flush_buf, bytes));
+    flush_bytes = bytes;
+  }
+  CU_CHK(cudaMemsetAsync(flush_buf, (int)(flush_count++ & 0xff), bytes, rtc->stream()));
+}
+
+void b200_conv_fwd_t::enqueue_fwd() {
+  ensure_graph();
+  rtc->set_timing(false);
+  if (use_graph) { CU_CHK(cudaGraphLaunch(graph_exec, rtc->stream())); graph_launches += kernels_per_fwd; }
+  else { run_calls(); }
+}
+
 vector<float> b200_conv_fwd_t::run_timed(int iters, uint64_t l2_flush_bytes) {
   ensure_graph();
-  if (l2_flush_bytes > flush_bytes) {
-    if (flush_buf) { cudaFree(flush_buf); flush_buf = nullptr; }
-    CU_CHK(cudaMalloc(&flush_buf, l2_flush_bytes));
-    flush_bytes = l2_flush_bytes;
-  }
   rtc->set_timing(false);
   vector<cudaEvent_t> evb(iters), eve(iters);
   for (int i = 0; i < iters; ++i) { CU_CHK(cudaEventCreate(&evb[i])); CU_CHK(cudaEventCreate(&eve[i])); }
   for (int i = 0; i < iters; ++i) {
-    if (l2_flush_bytes) { CU_CHK(cudaMemsetAsync(flush_buf, i & 0xff, l2_flush_bytes, rtc->stream())); }
+    flush_l2(l2_flush_bytes);
     CU_CHK(cudaEventRecord(evb[i], rtc->stream()));
-    if (use_graph) { CU_CHK(cudaGraphLaunch(graph_exec, rtc->stream())); graph_launches += kernels_per_fwd; }
-    else { run_calls(); }
+    enqueue_fwd();
     CU_CHK(cudaEventRecord(eve[i], rtc->stream()));
   }
   rtc->finish_and_sync();

@@ -76,6 +76,12 @@ struct b200_conv_fwd_t {
   // `iters` forwards, each bracketed by its own CUDA events on the back-end's stream; when l2_flush_bytes > 0 a scratch buffer of that size is
   // overwritten before every forward (outside the events) so no iteration starts with a warm L2. Returns ms per forward.
   vector<float> run_timed(int iters, uint64_t l2_flush_bytes);
+  // Asynchronous pieces for a caller that orders its own device work (e.g. an NCCL gather of the logits on another stream) against the
+  // forward: stream() is the back-end's cudaStream_t; enqueue_fwd() queues one forward on device-resident inputs and returns without a
+  // sync; flush_l2() queues an overwrite of a scratch buffer of `bytes`.
+  void *stream() const { return (void *)rtc->stream(); }
+  void enqueue_fwd();
+  void flush_l2(uint64_t bytes);
   uint64_t launches() const { return rtc->launches() + graph_launches; }
 
  private:
@@ -93,7 +99,7 @@ struct b200_conv_fwd_t {
   cudaEvent_t ticket_ev[kTickets] = {};
   uint64_t n_submitted = 0;
   void *flush_buf = nullptr;
-  uint64_t flush_bytes = 0;
+  uint64_t flush_bytes = 0, flush_count = 0;
   vector<double> call_flops;
   map<string, uint32_t> absmax_ix;  // nodes whose producer publishes max|x| for the consuming convolution's operand scaling
   struct concat_alias_t { string cat_node; uint32_t ocix; string extract_func; };

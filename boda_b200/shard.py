@@ -5,6 +5,7 @@ ranks split the batch and never exchange activations:
   * `shard_range`       -- rank r owns the contiguous images [r*ceil(B/G), min(B, (r+1)*ceil(B/G)))
   * `broadcast_params`  -- ONE collective broadcast of all filts / biases from rank 0 at init (flattened into a single buffer)
   * `gather_logits`     -- ONE all-gather of the per-rank output node per forward
+  * `GatherPipeline`    -- the same gather, issued asynchronously one step late so that it overlaps the next batch's forward
 Only `torch.distributed` calls; the tensors live wherever the process group's backend wants them (CUDA for NCCL over NVLink on the
 GPU box, CPU for the gloo tests), so the same code is exercised by world_size-2 CPU tests.
 """
@@ -65,6 +66,40 @@ def gather_logits(dist, local, out=None):
         out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, local.contiguous())
     return out
+
+
+class GatherPipeline:
+    """Double-buffered, one-step-late logits gather for serving loops: step i stages its logits (a device copy on the caller's current
+    stream), step i+1 opens by issuing the asynchronous all-gather of that staged copy and closes by joining it, so the collective runs
+    beside forward i+1 instead of after forward i. Per step:  begin_step(i); <enqueue forward i>; stage(i, logits); out = end_step().
+    `end_step` returns the gathered logits of step i-1 (None at i == 0); `drain(i)` after the last step returns the final one.
+    With NCCL the joins are stream-level (no host block); with gloo they block the host -- same results either way."""
+
+    def __init__(self, dist, local_like):
+        import torch
+        self.dist = dist
+        world = dist.get_world_size()
+        self.staging = [torch.empty_like(local_like) for _ in range(2)]
+        self.out = torch.empty((world * local_like.shape[0],) + tuple(local_like.shape[1:]), dtype=local_like.dtype, device=local_like.device)
+        self.work = None
+
+    def begin_step(self, i: int):
+        if i > 0:
+            self.work = self.dist.all_gather_into_tensor(self.out, self.staging[(i - 1) & 1], async_op=True)
+
+    def stage(self, i: int, local):
+        self.staging[i & 1].copy_(local, non_blocking=True)
+
+    def end_step(self):
+        if self.work is None:
+            return None
+        self.work.wait()
+        self.work = None
+        return self.out
+
+    def drain(self, n_steps: int):
+        self.begin_step(n_steps)
+        return self.end_step()
 
 
 def max_over_ranks(dist, value: float, device="cpu") -> float:

@@ -115,6 +115,12 @@ int b200_fwd_profile(b200_fwd *f, int iters, char *tags_buf, int tags_buf_len, f
 /* `iters` forwards on device-resident inputs, each bracketed by its own CUDA events on the back-end's stream; a scratch
  * buffer of l2_flush_bytes (0 = off) is overwritten before each one, outside the events. ms_each_out[iters]. */
 int b200_fwd_run_timed(b200_fwd *f, int iters, uint64_t l2_flush_bytes, float *ms_each_out);
+/* Asynchronous pieces for a caller that orders its own device work against the forward (bench.py overlaps the NCCL gather of batch
+ * i's logits with batch i+1's forward): the back-end's cudaStream_t; one forward on device-resident inputs queued without a sync; an
+ * overwrite of a scratch buffer of `bytes` queued on the same stream (L2 flush between timed iterations). */
+int b200_fwd_get_stream(b200_fwd *f, void **stream_out);
+int b200_fwd_enqueue(b200_fwd *f);
+int b200_fwd_flush_l2(b200_fwd *f, uint64_t bytes);
 /* device pointer of a node's fp32 NCHW var (e.g. to hand the logits to NCCL) */
 int b200_fwd_get_node_raw_native_pointer(b200_fwd *f, const char *node_name, void **dev_ptr_out);
 

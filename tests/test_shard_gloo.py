@@ -55,8 +55,20 @@ def _worker(rank, world, port, q):
         x_local = shard.split_inputs(x_global, world)[rank]
         local = net_oracle.run_pipe(txt_local, {in_node: x_local}, params)[out_node]
         gathered = shard.gather_logits(dist, torch.from_numpy(np.ascontiguousarray(local))).numpy()
+        # the one-step-late gather pipeline bench.py runs: step i's logits (here: local * (i + 1)) come out of step i+1's end_step()
+        gp = shard.GatherPipeline(dist, torch.from_numpy(np.ascontiguousarray(local)))
+        pipe_ok, outs = True, []
+        for i in range(3):
+            gp.begin_step(i)
+            gp.stage(i, torch.from_numpy(np.ascontiguousarray(local * np.float32(i + 1))))
+            o = gp.end_step()
+            pipe_ok &= (o is None) == (i == 0)
+            if o is not None:
+                outs.append(o.numpy().copy())
+        outs.append(gp.drain(3).numpy().copy())
+        pipe_ok &= len(outs) == 3 and all(np.array_equal(o, gathered * np.float32(i + 1)) for i, o in enumerate(outs))
         t = shard.max_over_ranks(dist, float(rank + 1))
-        res = {"rank": rank, "ok_t": t == float(world), "params_sum": float(sum(float(np.abs(v).sum()) for v in params.values())), "gathered": gathered}
+        res = {"rank": rank, "ok_t": t == float(world), "pipe_ok": bool(pipe_ok), "params_sum": float(sum(float(np.abs(v).sum()) for v in params.values())), "gathered": gathered}
         if rank == 0:
             txt_full, i2, o2 = nets.tiny_net(B)
             full = net_oracle.run_pipe(txt_full, {i2: x_global}, nets.synth_params(txt_full))[o2]
@@ -89,3 +101,4 @@ def test_two_rank_broadcast_shard_gather_matches_unsharded_forward(oracle):
     assert res[0]["gathered"].shape[0] == 4
     assert res[0]["match_full"]
     assert all(r["ok_t"] for r in res)
+    assert all(r["pipe_ok"] for r in res)
