@@ -460,6 +460,11 @@ bool b200_compute_t::conv_plane_writable(op_base_t const &op, bool dst_is_concat
   if (prec != B200_PREC_BF16 && dst_is_concat) { return false; }
   return !cp.swapped && cp.splits == 1 && (cp.OC % 8) == 0;
 }
+bool b200_compute_t::conv_res_fusable(op_base_t const &op) {
+  conv_plan_t cp;
+  plan_conv(cp, op, impl->num_sms);
+  return !cp.swapped && cp.splits == 1;
+}
 void b200_compute_t::release_func(string const &func_name) {
   if (!impl->funcs.erase(func_name)) { rt_err("release_func: '" + func_name + "' not found"); }
 }
@@ -794,7 +799,15 @@ struct run_ctx_t {
     if (has_arg("biases")) { var_info_t &vb = var("biases"); if ((int)vb.dims.dims_prod() != cp.OC) { rt_err("conv: biases size mismatch"); } bias = fptr(vb); }
     bool const bf16 = (rtc.prec == B200_PREC_BF16);
     int const planes = (rtc.prec == B200_PREC_FP32_SPLIT) ? 2 : 1;
-    if (cp.taps && rtc.use_taps && !has_arg("out_concat") && run_conv_taps(vin, vf, vout, bias, bf16, planes)) { return; }
+    // optional residual input (IgemmParams::res): out = relu?((conv + bias) + res)
+    float const *res = nullptr;
+    if (has_arg("res")) {
+      var_info_t &vr = var("res");
+      if (!(vr.dims == vout.dims)) { rt_err("conv: res dims differ from out"); }
+      if (cp.swapped || cp.splits != 1 || has_arg("out_concat")) { unsup_err("conv: a residual input needs a pixel-major, un-split launch without out_concat (conv_res_fusable)"); }
+      res = fptr(vr);
+    }
+    if (cp.taps && rtc.use_taps && !res && !has_arg("out_concat") && run_conv_taps(vin, vf, vout, bias, bf16, planes)) { return; }
     // filters: OIHW -> K-major rows (k = tap x chan), stored k-block-major [k / 64][OC padded][64] so that every TMA tile is contiguous
     // (once per weight version; the reference's xpose_filts, src/rtc_fwd.cc:310-313)
     long long const oc_pad = round_up(cp.OC, 128);
@@ -873,7 +886,10 @@ struct run_ctx_t {
     // var), so they find it fresh and skip their pack kernel. Needs 16-byte aligned runs: channel offset and channel count multiples of 8.
     packed_t *out_pk = nullptr;
     var_info_t &vdst = vcat ? *vcat : vout;
-    if (has_arg("out_pack") && scalar("out_pack") != 0 && !cp.swapped && cp.splits == 1 && (cp.OC % 8) == 0 && (bf16 || !vcat)) {
+    prm.res = res;
+    prm.res_absmax = res ? absmax_cell("res") : nullptr;
+    // (beside a residual the fp16 planes' bound needs max|res|: without that cell only bf16 planes are written; consumers then pack as usual)
+    if (has_arg("out_pack") && scalar("out_pack") != 0 && !cp.swapped && cp.splits == 1 && (cp.OC % 8) == 0 && (bf16 || !vcat) && (bf16 || !res || prm.res_absmax)) {
       int const ocix = vcat ? (int)scalar("out_ocix") : 0;
       int const cdst = (int)vdst.dims.dsz("chan"), cdst_pad = (int)round_up(cdst, 8);
       if ((ocix % 8) == 0) {

@@ -109,6 +109,8 @@ struct b200_compute_t {
   // depends only on its plan (not an inner-product-shaped / split-K layer, out_chans a multiple of 8). Every producer of a destination var must
   // be able to, or none may be asked to -- the whole-net driver decides per destination with this.
   bool conv_plane_writable(op_base_t const &op, bool dst_is_concat);
+  // whether this convolution's launch can take a residual input ("res" argument): pixel-major, un-split launches only
+  bool conv_res_fusable(op_base_t const &op);
   bool has_var(string const &vn) const;
   bool has_func(string const &fn) const;
   void copy_raw_to_var(string const &vn, void const *src, uint64_t bytes);   // host -> device (async on the stream, then sync)

@@ -230,7 +230,13 @@ bool b200_conv_fwd_t::dst_plane_by_producers(string const &dst) {
       }
     }
   }
-  if (!is_cat) { for (auto const &w : cp->ops) { if (w->is("Convolution") && w->tops[0] == dst) { producers.push_back(w); } } }
+  if (!is_cat) {
+    for (auto const &w : cp->ops) {
+      if (!w->is("Convolution")) { continue; }
+      auto rf = res_fuse.find(w->tag);  // a convolution with a residual join in its epilogue produces the join's output node
+      if (rf != res_fuse.end() ? rf->second.out_node == dst : w->tops[0] == dst) { producers.push_back(w); }
+    }
+  }
   if (producers.empty()) { return false; }
   for (auto const &w : producers) { if (!rtc->conv_plane_writable(conv_fop(*w), is_cat)) { return false; } }
   for (auto const &ip : dn->in_place_ops) {
@@ -304,6 +310,34 @@ void b200_conv_fwd_t::gen_op(p_conv_op_t const &op) {
     map_str_rtc_arg_t args{{"in", op->bots[0]}, {"filts", filts_vn}, {"out", op->tops[0]}};
     if (!biases_vn.empty()) { args["biases"] = biases_vn; }
     add_absmax_args(args, "in", op->bots[0]);
+    auto rf = res_fuse.find(op->tag);
+    if (rf != res_fuse.end()) {
+      // Residual join in the epilogue: this convolution adds the join's other input and writes the Eltwise output
+      // directly, with the join's ReLU. Its own output node is bypassed; a plain call that computes it is kept for readers of that node.
+      fwd_call_t pc;
+      pc.tag = op->tag;
+      pc.func_name = "conv__" + op->tag + "__plain";
+      rtc_func_info_t fi;
+      fi.func_name = pc.func_name;
+      fi.op = fop;
+      fi.op.set_func_name("conv");
+      rtc->compile({fi}, rtc_compile_opts_t());
+      pc.rfc.rtc_func_name = pc.func_name;
+      pc.rfc.arg_map = args;
+      elided_calls[op->tops[0]] = pc.rfc;
+      p_conv_node_t jn = cp->must_get_node(rf->second.out_node);
+      bool jrelu = false;
+      if (!jn->in_place_ops.empty() && jn->in_place_ops[0]->is("ReLU")) { jrelu = true; jn->in_place_ops[0]->fused = true; }
+      fop.erase("conv_has_relu");
+      fop.set_u32("conv_has_relu", jrelu ? 1 : 0);
+      args["out"] = rtc_arg_t(rf->second.out_node);
+      args["res"] = rtc_arg_t(rf->second.res_node);
+      add_absmax_args(args, "out", rf->second.out_node);
+      add_absmax_args(args, "res", rf->second.res_node);
+      if (dst_plane_by_producers(rf->second.out_node)) { args["out_pack"] = rtc_arg_t(make_scalar_nda<uint32_t>(1, "uint32_t")); }
+      add_call("conv", *op, fop, args);
+      return;
+    }
     auto al = concat_alias.find(op->tops[0]);
     if (al != concat_alias.end()) {  // write into the Concat output at this input's channel offset; its abs-max cell is the Concat output's
       args["out_concat"] = rtc_arg_t(al->second.cat_node);
@@ -388,6 +422,7 @@ void b200_conv_fwd_t::init(p_conv_pipe_t const &cp_, string const &opts) {
         else if (k == "device") { rtc->device = std::stoi(v); }
         else if (k == "enable_prof") { enable_prof = (uint32_t)std::stoul(v); }
         else if (k == "concat_by_offset") { concat_by_offset = (uint32_t)std::stoul(v); }
+        else if (k == "fuse_eltwise") { fuse_eltwise = (uint32_t)std::stoul(v); }
         else if (k == "pack_by_producers") { pack_by_producers = (uint32_t)std::stoul(v); }
         else { rt_err("mode=b200: unused option '" + k + "'"); }  // NESI rejects unused keys (src/nesi.cc:25-35)
       }
@@ -398,25 +433,6 @@ void b200_conv_fwd_t::init(p_conv_pipe_t const &cp_, string const &opts) {
     if (kv.second->dims.empty()) { rt_err("pipe: node '" + kv.first + "' has no dims (unused / unreachable?)"); }
     rtc->create_var_with_dims(kv.first, kv.second->dims);
   }
-  // abs-max side channel: a node gets a cell when its (single) writer can publish max|x| and some Convolution reads it.
-  // In-place ReLU/Dropout on the node only shrink max|x|, so the published value stays a valid bound.
-  for (auto const &kv : cp->nodes) {
-    conv_node_t const &n = *kv.second;
-    if (n.top_for.size() != 1) { continue; }
-    p_conv_op_t writer;
-    for (auto const &o : cp->ops) { if (o->tag == n.top_for[0]) { writer = o; } }
-    if (!writer || !(writer->is("Convolution") || writer->is("Pooling") || writer->is("LRN") || writer->is("Concat") || writer->is("Eltwise") || writer->is("Reduce"))) { continue; }
-    bool feeds_conv = false;
-    for (auto const &o : cp->ops) {
-      if (o->is("Convolution") && !o->bots.empty() && o->bots[0] == n.name) { feeds_conv = true; }
-      // ... or a Pooling op whose output a Convolution reads: the pool kernel scales the planes it writes for that convolution by max|in|
-      if (o->is("Pooling") && !o->bots.empty() && o->bots[0] == n.name) {
-        for (auto const &o2 : cp->ops) { if (o2->is("Convolution") && !o2->bots.empty() && o2->bots[0] == o->tops[0]) { feeds_conv = true; } }
-      }
-    }
-    if (feeds_conv) { uint32_t const ix = (uint32_t)absmax_ix.size(); absmax_ix[n.name] = ix; }
-  }
-  rtc->create_var_with_dims(absmax_cells_vn, dims_t({(uint32_t)std::max<size_t>(absmax_ix.size(), 1)}, {"cell"}, "uint32_t"));
   // Concat by offset (the reference copies every Concat input, src/rtc_fwd.cc:267-280): a Concat input qualifies when it is
   // written by one Convolution, read by nothing but this Concat, and carries no in-place op other than the ReLU the convolution fuses.
   if (concat_by_offset) {
@@ -440,6 +456,53 @@ void b200_conv_fwd_t::init(p_conv_pipe_t const &cp_, string const &opts) {
       }
     }
   }
+  // Residual joins: Eltwise SUM of two inputs, one of them written by a Convolution (folded BatchNorm / Scale allowed, no
+  // other in-place op), read by nothing but this Eltwise, with the other input complete before that convolution runs.
+  if (fuse_eltwise) {
+    map<string, size_t> op_ix;
+    for (size_t i = 0; i < cp->ops.size(); ++i) { op_ix[cp->ops[i]->tag] = i; }
+    for (auto const &e : cp->ops) {
+      if (!(e->is("Eltwise") || e->is("Reduce")) || e->bots.size() != 2 || e->bots[0] == e->bots[1] || e->in_place) { continue; }
+      for (int side = 1; side >= 0 && !e->fused; --side) {
+        string const &n = e->bots[side], &other = e->bots[1 - side];
+        p_conv_node_t nn = cp->must_get_node(n), on = cp->must_get_node(other);
+        if (nn->top_for.size() != 1 || concat_alias.count(n) || e->tops[0] == n || e->tops[0] == other) { continue; }
+        bool ok = true;
+        for (auto const &reader : nn->bot_for) {
+          bool in_place_reader = false;
+          for (auto const &ip : nn->in_place_ops) { if (ip->tag == reader) { in_place_reader = true; } }
+          if (reader != e->tag && !in_place_reader) { ok = false; }
+        }
+        for (auto const &ip : nn->in_place_ops) { if (!(ip->is("BatchNorm") || ip->is("Scale"))) { ok = false; } }
+        p_conv_op_t const &w = cp->ops[op_ix.at(nn->top_for[0])];
+        ok = ok && w->is("Convolution") && !w->has("is_inner_product") && !res_fuse.count(w->tag);
+        size_t const wi = op_ix.at(w->tag);
+        for (auto const &t : on->top_for) { if (op_ix.at(t) > wi) { ok = false; } }
+        for (auto const &ip : on->in_place_ops) { if (op_ix.at(ip->tag) > wi) { ok = false; } }
+        if (ok && rtc->conv_res_fusable(conv_fop(*w))) { res_fuse[w->tag] = res_fuse_t{e->tops[0], other}; e->fused = true; }
+      }
+    }
+  }
+  // abs-max side channel: a node gets a cell when its (single) writer can publish max|x| and some Convolution reads it.
+  // In-place ReLU/Dropout on the node only shrink max|x|, so the published value stays a valid bound.
+  for (auto const &kv : cp->nodes) {
+    conv_node_t const &n = *kv.second;
+    if (n.top_for.size() != 1) { continue; }
+    p_conv_op_t writer;
+    for (auto const &o : cp->ops) { if (o->tag == n.top_for[0]) { writer = o; } }
+    if (!writer || !(writer->is("Convolution") || writer->is("Pooling") || writer->is("LRN") || writer->is("Concat") || writer->is("Eltwise") || writer->is("Reduce"))) { continue; }
+    bool feeds_conv = false;
+    for (auto const &o : cp->ops) {
+      if (o->is("Convolution") && !o->bots.empty() && o->bots[0] == n.name) { feeds_conv = true; }
+      // ... or a Pooling op whose output a Convolution reads: the pool kernel scales the planes it writes for that convolution by max|in|
+      if (o->is("Pooling") && !o->bots.empty() && o->bots[0] == n.name) {
+        for (auto const &o2 : cp->ops) { if (o2->is("Convolution") && !o2->bots.empty() && o2->bots[0] == o->tops[0]) { feeds_conv = true; } }
+      }
+    }
+    for (auto const &rf : res_fuse) { if (rf.second.res_node == n.name) { feeds_conv = true; } }  // a residual input: its max bounds the join's output
+    if (feeds_conv) { uint32_t const ix = (uint32_t)absmax_ix.size(); absmax_ix[n.name] = ix; }
+  }
+  rtc->create_var_with_dims(absmax_cells_vn, dims_t({(uint32_t)std::max<size_t>(absmax_ix.size(), 1)}, {"cell"}, "uint32_t"));
   for (auto const &op : cp->ops) { gen_op(op); }
   for (auto &kv : concat_alias) {  // read-back functions: node = Concat output[:, ocix : ocix + chan]
     op_base_t cop;
@@ -547,6 +610,12 @@ int b200_conv_fwd_t::submit(int n_set, char const *const *set_names, float const
 }
 
 void b200_conv_fwd_t::materialise_aliased(string const &node) {
+  auto el = elided_calls.find(node);
+  if (el != elided_calls.end()) {  // bypassed by a residual join in its convolution's epilogue: compute it now (inputs are still in their vars)
+    rtc->set_timing(false);
+    rtc->run(el->second);
+    return;
+  }
   auto al = concat_alias.find(node);
   if (al == concat_alias.end()) { return; }
   rtc_func_call_t rfc;

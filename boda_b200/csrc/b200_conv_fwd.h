@@ -45,6 +45,8 @@ struct b200_conv_fwd_t {
   uint32_t use_graph = 1;      // replay the forward calls as one CUDA graph (launch-bound at B200 speeds)
   uint32_t enable_prof = 0;
   uint32_t pack_by_producers = 1; // bf16 storage mode: convolutions also write the NHWC bf16 plane their consumers read (no activation pack kernel)
+  uint32_t fuse_eltwise = 1;      // residual joins: a two-input Eltwise SUM (+ReLU) whose one input is written by a Convolution and read by nothing else is
+                                  // folded into that convolution's epilogue; the bypassed node is recomputed on demand when read
   uint32_t concat_by_offset = 1;  // Convolutions that only feed a Concat write straight into its output at their channel offset (no copy kernel);
                                   // their own node is materialised from that slice only when run_fwd is asked for it
   p_b200_compute_t rtc;
@@ -103,6 +105,9 @@ struct b200_conv_fwd_t {
   vector<double> call_flops;
   map<string, uint32_t> absmax_ix;  // nodes whose producer publishes max|x| for the consuming convolution's operand scaling
   struct concat_alias_t { string cat_node; uint32_t ocix; string extract_func; };
+  struct res_fuse_t { string out_node, res_node; };
+  map<string, res_fuse_t> res_fuse;          // Convolution tag -> (Eltwise output it writes, the join's other input)
+  map<string, rtc_func_call_t> elided_calls; // bypassed node -> the plain convolution call that materialises it when somebody reads it
   map<string, concat_alias_t> concat_alias;  // node -> (Concat output that holds its channels, channel offset, name of the read-back function)
   void materialise_aliased(string const &node);
   op_base_t conv_fop(conv_op_t const &op) const;  // function signature of a Convolution op: its params + the dims of in / filts / biases / out

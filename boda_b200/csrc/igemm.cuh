@@ -53,6 +53,10 @@ struct IgemmParams {
   long long split_stride;  // elements between split-K partial buffers (0 when writing final output)
   float *out;              // NCHW fp32 output, or split-K workspace
   float const *bias;       // per out-chan
+  // residual join fused into the convolution (ResNet Eltwise SUM): out = max(floor, conv + bias + res), `res` an fp32
+  // NCHW tensor with the output's dims, addressed like `out` (see igemm_acc_init). Non-swapped, non-split launches only (host-checked); null = off.
+  float const *res;
+  unsigned int const *res_absmax;  // max|res| published by its producer (bit pattern): the residual's term of the fp16 planes' output bound
   float const *p_scale;    // {scale, inv_scale} of the P tensor
   float const *q_scale;
   int debug;   // bit 0: skip TMA (MMA runs on whatever is in smem), bit 1: skip MMA issue (loads + barriers only), bit 2: skip the final global stores,
@@ -151,6 +155,26 @@ __device__ __forceinline__ float igemm_store_row(float const (&acc)[BN], float i
   return amax;
 }
 
+// Residual join (IgemmParams::res): the accumulators of a pixel row START at res / inv instead of zero, so the unchanged epilogue
+// max(floor, acc * inv + bias) yields conv + bias + res. inv is a product of power-of-two operand scales, so the division is exact and the
+// residual enters the fp32 sum like one more partial product; its BN loads are issued together at the top of the tile, before the first wait
+// on the tensor pipe, and so overlap the main loop instead of serialising behind it. `r` = address of this row's first channel in `res`.
+template <int BN>
+__device__ __forceinline__ void igemm_acc_init(float (&acc)[BN], float const *r, long long stride, int nvalid, float inv_recip) {
+  if (r == nullptr) {
+#pragma unroll
+    for (int j = 0; j < BN; ++j) { acc[j] = 0.0f; }
+    return;
+  }
+  if (nvalid >= BN) {
+#pragma unroll
+    for (int j = 0; j < BN; ++j) { acc[j] = __ldg(r + j * stride) * inv_recip; }
+  } else {
+#pragma unroll
+    for (int j = 0; j < BN; ++j) { acc[j] = (j < nvalid) ? __ldg(r + j * stride) * inv_recip : 0.0f; }
+  }
+}
+
 // Second output of a pixel row in bf16 storage mode: the same values (scale, bias, floor) rounded to bf16 and written as 16-byte runs into
 // the consumer's NHWC plane. `dst` is 16-byte aligned (channel offsets and pitches are multiples of 8 elements).
 template <int BN>
@@ -212,7 +236,8 @@ __device__ __forceinline__ float igemm_out_scale(IgemmParams const &prm, float *
   bm = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
   float in_bound = 16384.0f * prm.p_scale[1];  // max|in| < 2^14 / s_in
   if (prm.in_absmax) { float const t = __uint_as_float(*prm.in_absmax); if (t > 0.0f) { in_bound = fminf(in_bound, t); } }
-  float const bound = (__ldg(prm.w_l1max) * in_bound + bm) * 1.01f;
+  float const res_bound = prm.res_absmax ? __uint_as_float(*prm.res_absmax) : 0.0f;  // host: fp16 planes beside a residual only with this cell
+  float const bound = (__ldg(prm.w_l1max) * in_bound + bm + res_bound) * 1.01f;
   return scale_from_absmax_bits(__float_as_uint(bound));
 }
 
@@ -379,8 +404,14 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
     float acc[BN];
-#pragma unroll
-    for (int j = 0; j < BN; ++j) { acc[j] = 0.0f; }
+    {
+      float const *res_row = nullptr;  // (host: a residual input only on non-swapped, non-split launches)
+      if (prm.res && m0 + row < prm.p_rows) {
+        int const img = (m0 + row) / prm.out_hw, pix = (m0 + row) - img * prm.out_hw;
+        res_row = prm.res + (static_cast<long long>(img) * prm.out_chans + n0) * prm.out_hw + pix;
+      }
+      igemm_acc_init<BN>(acc, res_row, prm.out_hw, prm.q_rows - n0, prm.p_scale[0] * prm.q_scale[0]);
+    }
     for (int c = 0; c < ((prm.debug & 8) ? 0 : nchunks); ++c) {
       int const buf = c & 1;
       mbar_wait(&tmem_full_bar[buf], (c >> 1) & 1);

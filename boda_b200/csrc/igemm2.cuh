@@ -193,7 +193,7 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
     // ===================== epilogue warps (each CTA: its own 128 rows) =====================
     int const q = warp_id & 3;
     int const row = q * 32 + lane;
-    float const inv = prm.p_scale[1] * prm.q_scale[1];
+    float const inv = prm.p_scale[1] * prm.q_scale[1], inv_recip = prm.p_scale[0] * prm.q_scale[0];
     float const floor_v = prm.relu ? 0.0f : -INFINITY;
     float amax = 0.0f;
     float s_out = 1.0f;
@@ -210,8 +210,14 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
       for (int j = row; j < BN; j += 128) { bias_t[j] = (prm.has_bias && (n0 + j) < prm.q_rows) ? __ldg(prm.bias + n0 + j) : 0.0f; }
       asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
       float acc[BN];
-#pragma unroll
-      for (int j = 0; j < BN; ++j) { acc[j] = 0.0f; }
+      {
+        float const *res_row = nullptr;
+        if (prm.res && m0 + row < prm.p_rows) {
+          int const img = (m0 + row) / prm.out_hw, pix = (m0 + row) - img * prm.out_hw;
+          res_row = prm.res + (static_cast<long long>(img) * prm.out_chans + n0) * prm.out_hw + pix;
+        }
+        igemm_acc_init<BN>(acc, res_row, prm.out_hw, prm.q_rows - n0, inv_recip);
+      }
       for (int c = 0; c < nchunks; ++c, ++gc) {
         int const buf = gc & 1;
         mbar_wait(&tmem_full_bar[buf], (gc >> 1) & 1);

@@ -36,7 +36,7 @@ class OpRunner:
     def close(self):
         self.rtc.close()
 
-    def run_conv(self, op_text, inp, filts, biases, out_shape, iters=1):
+    def run_conv(self, op_text, inp, filts, biases, out_shape, iters=1, res=None):
         rtc = self.rtc
         fn = "conv_%d" % next(_uid)
         rtc.compile(fn, op_text)
@@ -46,13 +46,16 @@ class OpRunner:
             rtc.create_var_from_nda(fn + "_biases", biases, ["out_chan"])
             rtc.create_var_with_dims(fn + "_out", list(zip(["img", "chan", "y", "x"], out_shape)))
             args = {"in": fn + "_in", "filts": fn + "_filts", "biases": fn + "_biases", "out": fn + "_out"}
+            if res is not None:  # residual join in the epilogue: out = relu?((conv + bias) + res)
+                rtc.create_var_from_nda(fn + "_res", res, ["img", "chan", "y", "x"])
+                args["res"] = fn + "_res"
             ids = [rtc.run(fn, args) for _ in range(iters)]
             rtc.finish_and_sync()
             out = rtc.copy_var_to_nda(fn + "_out")
             self.last_ms = min(rtc.get_dur(i, i) for i in ids)
             return out
         finally:
-            for k in ("in", "filts", "biases", "out"):
+            for k in ("in", "filts", "biases", "out", "res"):
                 try:
                     rtc.release_var(fn + "_" + k)
                 except bb.RtException:

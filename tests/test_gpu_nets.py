@@ -210,6 +210,42 @@ def test_tiny_resnet_all_nodes(oracle):
     assert oracle.mrd(ref2, got2) < TOL and not np.array_equal(got2, got[o])
 
 
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-4), ("bf16", 3e-2)])
+@pytest.mark.parametrize("net,in_sz", [("tiny_resnet", 33), ("resnet50", 224)])
+def test_residual_join_in_convolution_matches_unfused(oracle, net, in_sz, prec, tol):
+    """fuse_eltwise=1 (default): the convolution in front of a residual join starts its accumulators at the shortcut and writes the Eltwise
+    output (with its ReLU) directly -- no reduce kernel, no round trip of the branch output through HBM. Only the fp32 rounding order
+    differs from the separate kernels, so every node must match the unfused path (fuse_eltwise=0) to fp32 noise in fp32-parity mode and to
+    the storage precision in bf16 mode (a 1e-7 upstream difference flips a bf16 rounding here and there, see
+    test_googlenet_conv_16bit_storage; 45 layers deep that reaches 2-3 bf16 ulps of a node's maximum: measured 1.0e-2) -- including the bypassed branch nodes, which run_fwd recomputes on demand."""
+    import boda_b200 as bb
+    from boda_b200 import nets
+    txt, i, o = (nets.tiny_resnet if net == "tiny_resnet" else nets.resnet50)(2)
+    params = nets.synth_params(txt)
+    x = nets.synth_input((2, 3, in_sz, in_sz))
+    names = _node_names(txt)
+    outs = []
+    for on in (1, 0):
+        fwd = bb.B200ConvFwd(txt, "(prec=%s,fuse_eltwise=%d)" % (prec, on))
+        for k, v in params.items():
+            fwd.set_param(k, v)
+        first = fwd.run_fwd({i: x}, [o])[o].copy()  # outputs only: nothing materialised
+        allv = fwd.run_fwd({i: x}, names)
+        assert np.array_equal(first, allv[o])
+        outs.append((allv, fwd.num_calls()))
+    (a, calls_a), (b, calls_b) = outs
+    n_joins = txt.count("type=Eltwise")
+    assert n_joins >= 1 and calls_a < calls_b, (calls_a, calls_b, n_joins)
+    if net == "resnet50":
+        assert n_joins == 16 and calls_a <= calls_b - 16, (calls_a, calls_b)  # every residual join of ResNet-50 is fused
+    worst = 0.0
+    for n in names:
+        e = float(np.abs(a[n].astype(np.float64) - b[n]).max()) / max(float(np.abs(b[n]).max()), 1e-30)
+        worst = max(worst, e)
+        assert e < tol, (n, e)
+    print("%s %s fused vs unfused: worst node max|a-b|/max|ref| = %.3e" % (net, prec, worst))
+
+
 def test_resnet50_b2_output(oracle):
     """BASELINE config C5's net at batch 2: the probabilities and the last residual stage against the oracle chain."""
     from boda_b200 import nets

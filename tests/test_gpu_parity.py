@@ -174,6 +174,52 @@ def test_conv_edge_cases(runner, oracle, case, relu):
     assert oracle.mrd(ref32, got) < TOL + oracle.mrd(ref64, ref32)
 
 
+RES_CASES = [
+    (2, 64, 14, 14, 256, 1, 1, 1, 1, 0, 0),     # ResNet branch2c shape: 1x1, 2 full N tiles (CTA-pair kernel)
+    (3, 16, 9, 9, 40, 3, 3, 1, 1, 1, 1),        # ragged N tile, 243 pixels
+    (1, 8, 6, 6, 24, 1, 1, 1, 1, 0, 0),         # single 128-row tile (one-CTA kernel)
+    (2, 32, 20, 20, 136, 3, 3, 2, 2, 1, 1),     # stride 2, ragged second N tile
+]
+
+
+@pytest.mark.parametrize("case", RES_CASES)
+@pytest.mark.parametrize("relu", [1, 0])
+def test_conv_residual_input(runner, oracle, case, relu):
+    """Residual join fused into the convolution: out = relu?(conv + bias + res); the residual enters as the accumulators'
+    initial value. Against the oracle within the conv tolerance, and against the unfused pair -- this back-end's convolution (no ReLU) followed
+    by an fp32 add, as its Eltwise-SUM kernel does -- to a few fp32 ulps of the largest magnitude (only the rounding order differs)."""
+    from b200_harness import conv_op_text
+    N, C, H, W, OC, KH, KW, sy, sx, py, px = case
+    rng = np.random.RandomState(C * 77 + OC)
+    x = (rng.rand(N, C, H, W).astype(np.float32) - 0.5) * 10
+    w = (rng.rand(OC, C, KH, KW).astype(np.float32) - 0.5) * 10
+    b = (rng.rand(OC).astype(np.float32) - 0.5) * 10
+    plain64 = oracle.conv_fwd(x, w, b, (sy, sx), (py, px), relu=False, acc64=True)
+    r = ((rng.rand(*plain64.shape).astype(np.float32) - 0.5) * 4 * float(np.abs(plain64).max())).astype(np.float32)
+    ref = plain64 + r
+    if relu:
+        ref = np.maximum(ref, 0)
+    got = runner.run_conv(conv_op_text(N, C, H, W, OC, KH, KW, sy, sx, py, px, relu), x, w, b, plain64.shape, res=r)
+    assert oracle.mrd(ref.astype(np.float32), got) < TOL
+    plain = runner.run_conv(conv_op_text(N, C, H, W, OC, KH, KW, sy, sx, py, px, 0), x, w, b, plain64.shape)
+    two_step = (r + plain).astype(np.float32)
+    if relu:
+        two_step = np.maximum(two_step, 0)
+    assert float(np.abs(two_step.astype(np.float64) - got).max()) <= 4e-6 * float(np.abs(ref).max())
+
+
+def test_conv_residual_input_errors(runner):
+    """A residual input on a launch shape that cannot take one (inner-product shaped: swapped / split-K) is refused, not ignored."""
+    import boda_b200 as bb
+    from b200_harness import conv_op_text
+    x = np.zeros((4, 32, 6, 6), np.float32); w = np.zeros((200, 32, 6, 6), np.float32); b = np.zeros(200, np.float32)
+    with pytest.raises((bb.UnsupException, bb.RtException)):
+        runner.run_conv(conv_op_text(4, 32, 6, 6, 200, 6, 6, 1, 1, 0, 0, 0), x, w, b, (4, 200, 1, 1), res=np.zeros((4, 200, 1, 1), np.float32))
+    with pytest.raises(bb.RtException):  # dims must equal the output's
+        runner.run_conv(conv_op_text(2, 64, 14, 14, 256, 1, 1, 1, 1, 0, 0, 0), np.zeros((2, 64, 14, 14), np.float32), np.zeros((256, 64, 1, 1), np.float32),
+                        np.zeros(256, np.float32), (2, 256, 14, 14), res=np.zeros((2, 256, 14, 7), np.float32))
+
+
 def test_conv_wide_dynamic_range(runner, oracle):
     """Per-tensor power-of-two scaling must keep tiny and huge operands accurate (fp16 planes would under/overflow unscaled)."""
     from b200_harness import conv_op_text
