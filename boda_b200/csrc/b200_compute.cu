@@ -1020,7 +1020,10 @@ struct run_ctx_t {
     long long const n_out = vout.dims.dims_prod();
     long long const planes = (long long)vin.dims.dsz("img") * vin.dims.dsz("chan");
     int const avg = (int)scalar("avg_pool", true, 0);
-    if (KH == KW && sy == sx && ((KH == 3 && sy == 2) || (KH == 3 && sy == 1) || (KH == 2 && sy == 2)) && (long long)H * W <= 4096 && planes < (1ll << 31)) {  // small planes: stage in smem
+    // planes that fit shared memory are staged there (pool_plane_kernel): the 3x3 / 2x2 max pools of AlexNet / NiN / GoogLeNet / ResNet incl.
+    // their 112x112 first pools (one 49 KB plane per CTA), GoogLeNet's 5x5 stride-3 average pools, 7x7 (global) average pools
+    bool const plane_ks = KH == KW && sy == sx && ((KH == 3 && sy == 2) || (KH == 3 && sy == 1) || (KH == 2 && sy == 2) || (KH == 5 && sy == 3) || (KH == 7 && sy == 1));
+    if (plane_ks && (long long)H * W <= 16384 && planes < (1ll << 31)) {
       // planes per CTA: a multiple of 4 (16-byte aligned runs), tile <= 48 KB, and at least ~4 CTAs per SM left to fill the chip
       int ppc = (int)std::max<long long>(4, std::min<long long>((48 * 1024) / ((long long)H * W * 4) / 4 * 4, round_up(ceil_div(planes, 4 * im.num_sms), 4)));
       if ((long long)ppc * H * W * 4 > 96 * 1024) { ppc = 1; }
@@ -1062,7 +1065,8 @@ struct run_ctx_t {
         static bool attr_ = false; \
         if (!attr_) { CU_CHK(cudaFuncSetAttribute(b200::pool_plane_kernel<K_, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); prefer_max_smem(b200::pool_plane_kernel<K_, S_>); attr_ = true; } \
         launch_k(b200::pool_plane_kernel<K_, S_>, dim3((unsigned)ceil_div(planes, ppc)), dim3(256), smem, fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, cell, ppc, planes, pp); } while (0)
-      if (KH == 3 && sy == 2) { B200_POOL_PLANE(3, 2); } else if (KH == 3) { B200_POOL_PLANE(3, 1); } else { B200_POOL_PLANE(2, 2); }
+      if (KH == 3 && sy == 2) { B200_POOL_PLANE(3, 2); } else if (KH == 3) { B200_POOL_PLANE(3, 1); } else if (KH == 2) { B200_POOL_PLANE(2, 2); }
+      else if (KH == 5) { B200_POOL_PLANE(5, 3); } else { B200_POOL_PLANE(7, 1); }
 #undef B200_POOL_PLANE
       launched();
       im.bump(vout);

@@ -326,33 +326,76 @@ pool_plane_kernel(float const *__restrict__ in, float *__restrict__ out, int H, 
   __syncthreads();
   float amax = 0.0f;
   float *op = out + plane0 * ohw;
-  // (plane, oy, ox) of output o = threadIdx.x + 256 k, advanced by fixed deltas with carries instead of two integer divisions per output; every
-  // tap's bounds test is two unsigned compares (the kernel was issue-bound: ~140 instructions per output, ncu)
-  int pl = threadIdx.x / ohw, p0 = threadIdx.x - pl * ohw;
-  int oy = p0 / OW, ox = p0 - oy * OW;
-  int const d_pl = 256 / ohw, d_p = 256 - d_pl * ohw, d_oy = d_p / OW, d_ox = d_p - d_oy * OW;
-  float const pad_v = avg_pool ? 0.0f : -FLT_MAX;
-  for (int o = threadIdx.x; o < n_out; o += 256) {
-    int const y0 = oy * S - py, x0 = ox * S - px;
-    float const *ps = plane_s + pl * hw + y0 * W + x0;
-    float out_v = pad_v, cnt = 0.0f;
+  if (!avg_pool) {
+    // Max pooling: a work item is one output column (plane, ox) over a segment of kSeg output rows. It keeps the horizontal maxima of the K
+    // input rows under the current window in registers, so moving down one output row costs S new rows of K shared-memory loads and the
+    // K - S others are reused; the x bounds tests are per item, the y test per row. Max is exact in any order, so this equals the
+    // reference's tap loop bit for bit (~20 instructions per output instead of ~140: the tap loop was issue-bound, ncu).
+    constexpr int kSeg = 8;
+    int const nseg = (OH + kSeg - 1) / kSeg, items = np * nseg * OW;
+    for (int it = threadIdx.x; it < items; it += 256) {
+      int const t = it / OW, ox = it - t * OW, pl = t / nseg, seg = t - pl * nseg;
+      int const oy0 = seg * kSeg, oy1 = min(oy0 + kSeg, OH), x0 = ox * S - px;
+      bool xok[K];
 #pragma unroll
-    for (int kx = 0; kx < K; ++kx) {
-      bool const xok = static_cast<unsigned>(x0 + kx) < static_cast<unsigned>(W);
+      for (int kx = 0; kx < K; ++kx) { xok[kx] = static_cast<unsigned>(x0 + kx) < static_cast<unsigned>(W); }
+      float const *pc = plane_s + pl * hw + x0;
+      auto hrow = [&](int y) -> float {
+        float m = -FLT_MAX;
+        if (static_cast<unsigned>(y) < static_cast<unsigned>(H)) {
+          float const *pr = pc + y * W;
 #pragma unroll
-      for (int ky = 0; ky < K; ++ky) {
-        bool const ok = xok && static_cast<unsigned>(y0 + ky) < static_cast<unsigned>(H);
-        float const v = ok ? ps[ky * W + kx] : pad_v;
-        if (avg_pool) { out_v += v; cnt += ok ? 1.0f : 0.0f; } else { out_v = fmaxf(out_v, v); }
+          for (int kx = 0; kx < K; ++kx) { float v = -FLT_MAX; if (xok[kx]) { v = pr[kx]; } m = fmaxf(m, v); }
+        }
+        return m;
+      };
+      int y0 = oy0 * S - py;
+      float hr[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) { hr[k] = hrow(y0 + k); }
+      int const obase = pl * ohw + ox;
+      for (int oy = oy0; oy < oy1; ++oy) {
+        float out_v = hr[0];
+#pragma unroll
+        for (int k = 1; k < K; ++k) { out_v = fmaxf(out_v, hr[k]); }
+        op[obase + oy * OW] = out_v;
+        if (pp.hi) { plane_s[n_in + obase + oy * OW] = out_v; }  // staged for the transposed (NHWC) plane write below
+        amax = fmaxf(amax, fabsf(out_v));
+        y0 += S;
+        if (oy + 1 < oy1) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) { if (k + S < K) { hr[k] = hr[k + S]; } else { hr[k] = hrow(y0 + k); } }
+        }
       }
     }
-    if (avg_pool) { out_v = __fdiv_rn(out_v, cnt); }
-    op[o] = out_v;
-    if (pp.hi) { plane_s[n_in + o] = out_v; }  // staged for the transposed (NHWC) plane write below
-    amax = fmaxf(amax, fabsf(out_v));
-    ox += d_ox; oy += d_oy; pl += d_pl;
-    if (ox >= OW) { ox -= OW; ++oy; }
-    if (oy >= OH) { oy -= OH; ++pl; }
+  } else {
+    // Average pooling keeps the reference's tap order (the fp32 sum is order-dependent): one output per thread per step.
+    // (plane, oy, ox) of output o = threadIdx.x + 256 k, advanced by fixed deltas with carries instead of two integer divisions per output;
+    // every tap's bounds test is two unsigned compares
+    int pl = threadIdx.x / ohw, p0 = threadIdx.x - pl * ohw;
+    int oy = p0 / OW, ox = p0 - oy * OW;
+    int const d_pl = 256 / ohw, d_p = 256 - d_pl * ohw, d_oy = d_p / OW, d_ox = d_p - d_oy * OW;
+    for (int o = threadIdx.x; o < n_out; o += 256) {
+      int const y0 = oy * S - py, x0 = ox * S - px;
+      float const *ps = plane_s + pl * hw + y0 * W + x0;
+      float out_v = 0.0f, cnt = 0.0f;
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        bool const xok = static_cast<unsigned>(x0 + kx) < static_cast<unsigned>(W);
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+          bool const ok = xok && static_cast<unsigned>(y0 + ky) < static_cast<unsigned>(H);
+          if (ok) { out_v += ps[ky * W + kx]; cnt += 1.0f; }
+        }
+      }
+      out_v = __fdiv_rn(out_v, cnt);
+      op[o] = out_v;
+      if (pp.hi) { plane_s[n_in + o] = out_v; }
+      amax = fmaxf(amax, fabsf(out_v));
+      ox += d_ox; oy += d_oy; pl += d_pl;
+      if (ox >= OW) { ox -= OW; ++oy; }
+      if (oy >= OH) { oy -= OH; ++pl; }
+    }
   }
   if (out_absmax) { publish_absmax_warp(amax, out_absmax); }
   if (pp.hi) {

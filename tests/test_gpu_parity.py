@@ -255,7 +255,12 @@ def test_pool(runner, oracle):
     from b200_harness import nchw_dims_text
     rng = np.random.RandomState(11)
     for (shape, k, s, p, avg) in [((2, 5, 55, 55), 3, 2, 0, 0), ((3, 4, 27, 27), 3, 2, 0, 0), ((2, 6, 8, 8), 3, 2, 0, 0), ((2, 3, 14, 14), 3, 1, 1, 0),
-                                  ((2, 3, 14, 14), 5, 3, 0, 1), ((2, 7, 7, 7), 7, 1, 0, 1), ((2, 3, 13, 12), 3, 2, 1, 1), ((2, 9, 6, 5), None, 1, 0, 1), ((1, 2, 4, 4), None, 1, 0, 0)]:
+                                  ((2, 3, 14, 14), 5, 3, 0, 1), ((2, 7, 7, 7), 7, 1, 0, 1), ((2, 3, 13, 12), 3, 2, 1, 1), ((2, 9, 6, 5), None, 1, 0, 1), ((1, 2, 4, 4), None, 1, 0, 0),
+                                  # shared-memory plane kernel: column-walk max path (segments of 8 output rows, ragged last segment, padding on every side,
+                                  # many planes per CTA, a ragged last CTA), one 112x112 plane per CTA, 5x5 / 7x7 average windows, 7x7 max
+                                  ((2, 3, 112, 112), 3, 2, 0, 0), ((3, 37, 28, 28), 3, 1, 1, 0), ((2, 50, 13, 13), 3, 2, 0, 0), ((2, 11, 17, 9), 3, 1, 1, 0),
+                                  ((5, 29, 14, 14), 5, 3, 0, 1), ((3, 130, 7, 7), 7, 1, 0, 1), ((2, 5, 9, 9), 7, 1, 0, 0), ((2, 9, 12, 12), 2, 2, 0, 0),
+                                  ((2, 4, 15, 15), 5, 3, 0, 0), ((2, 6, 10, 10), 3, 2, 1, 0), ((1, 3, 20, 20), 3, 1, 1, 1)]:
         x = rng.randn(*shape).astype(np.float32)
         ref = oracle.pool_fwd(x, None if k is None else (k, k), (s, s), (p, p), avg_pool=bool(avg))
         kern = "" if k is None else ",kern_sz=(tn=none,dims=(y=%d,x=%d)),stride=(tn=none,dims=(y=%d,x=%d)),in_pad=(tn=none,dims=(y=%d,x=%d))" % (k, k, s, s, p, p)
