@@ -1024,47 +1024,80 @@ struct run_ctx_t {
     // their 112x112 first pools (one 49 KB plane per CTA), GoogLeNet's 5x5 stride-3 average pools, 7x7 (global) average pools
     bool const plane_ks = KH == KW && sy == sx && ((KH == 3 && sy == 2) || (KH == 3 && sy == 1) || (KH == 2 && sy == 2) || (KH == 5 && sy == 3) || (KH == 7 && sy == 1));
     if (plane_ks && (long long)H * W <= 16384 && planes < (1ll << 31)) {
-      // planes per CTA: a multiple of 4 (16-byte aligned runs), tile <= 48 KB, and at least ~4 CTAs per SM left to fill the chip
-      int ppc = (int)std::max<long long>(4, std::min<long long>((48 * 1024) / ((long long)H * W * 4) / 4 * 4, round_up(ceil_div(planes, 4 * im.num_sms), 4)));
-      if ((long long)ppc * H * W * 4 > 96 * 1024) { ppc = 1; }
-      // "out_pack": also write the NHWC 16-bit planes the consuming convolution reads. Needs groups of 8 channels of one image per CTA and
-      // (fp16 planes) the producer-published max|in| for the scale.
       int const C = (int)vin.dims.dsz("chan");
       bool const bf16 = (rtc.prec == B200_PREC_BF16);
       int const npl = (rtc.prec == B200_PREC_FP32_SPLIT) ? 2 : 1;
+      long long const hw = (long long)H * W, ohw = (long long)OH * OW;
+      unsigned int *in_cell = bf16 ? nullptr : absmax_cell("in");
+      bool const want_planes = has_arg("out_pack") && scalar("out_pack") != 0 && (C % 8) == 0 && (bf16 || in_cell);
+      // Persistent double-buffered kernel (pool_plane_pipe_kernel): groups of ~24 KB fetched by bulk copies, which need 16-byte multiples: the
+      // group size is a multiple of q planes. With "out_pack" a group is a multiple of 8 channels of ONE image (16-byte NHWC runs).
+      int pipe_ppc = 0, ppc = 0;
+      size_t pipe_smem = 0;
+      bool planes_ok = false;
+      {
+        int const q = (hw % 4 == 0) ? 1 : (hw % 2 == 0) ? 2 : 4;
+        long long const target = std::max<long long>(1, (24 * 1024) / (hw * 4));
+        auto smem_of = [&](long long ppc_, bool pl) { return (size_t)(2 * round_up(ppc_ * hw, 32) * 4 + (pl ? ppc_ * ohw * 4 : 0)); };
+        auto bulk_ok = [&](long long c) {
+          long long const tail = planes % c;
+          return (reinterpret_cast<uintptr_t>(fptr(vin)) & 15) == 0 && ((c * hw) % 4) == 0 && ((tail * hw) % 4) == 0 && c * hw * 4 < (1ll << 20);
+        };
+        // classic form (one group per CTA, loads by all threads): planes per CTA a multiple of 4 (16-byte aligned runs), tile <= 48 KB, and
+        // at least ~4 CTAs per SM left to fill the chip
+        int cl_ppc = (int)std::max<long long>(4, std::min<long long>((48 * 1024) / (hw * 4) / 4 * 4, round_up(ceil_div(planes, 4 * im.num_sms), 4)));
+        if ((long long)cl_ppc * hw * 4 > 96 * 1024) { cl_ppc = 1; }
+        int cl_ppc8 = 0;
+        if (want_planes) {
+          int p8 = (int)round_up(cl_ppc, 8);
+          while (p8 > 8 && ((C % p8) != 0 || (long long)p8 * (hw + ohw) * 4 > 100 * 1024)) { p8 -= 8; }
+          if ((C % p8) == 0 && (long long)p8 * (hw + ohw) * 4 <= 100 * 1024) { cl_ppc8 = p8; }
+        }
+        long long pipe8 = 0, pipe1 = std::max<long long>(q, target / q * q);
+        if (want_planes) {
+          for (long long c8 = std::max<long long>(8, target / 8 * 8); c8 >= 8; c8 -= 8) { if ((C % c8) == 0 && smem_of(c8, true) <= 100 * 1024 && bulk_ok(c8)) { pipe8 = c8; break; } }
+        }
+        if (smem_of(pipe1, false) > 100 * 1024 || !bulk_ok(pipe1)) { pipe1 = 0; }
+        // preference: writing the consumer's planes (saves a pack kernel) first, the pipelined form second
+        if (pipe8) { pipe_ppc = ppc = (int)pipe8; pipe_smem = smem_of(pipe8, true); planes_ok = true; }
+        else if (cl_ppc8) { ppc = cl_ppc8; planes_ok = true; }
+        else if (pipe1) { pipe_ppc = ppc = (int)pipe1; pipe_smem = smem_of(pipe1, false); }
+        else { ppc = cl_ppc; }
+      }
       b200::PoolPlanes pp;
       memset(&pp, 0, sizeof(pp));
       packed_t *out_pk = nullptr;
-      unsigned int *in_cell = bf16 ? nullptr : absmax_cell("in");
-      if (has_arg("out_pack") && scalar("out_pack") != 0 && (C % 8) == 0 && (bf16 || in_cell)) {
-        int ppc8 = (int)round_up(ppc, 8);
-        while (ppc8 > 8 && ((C % ppc8) != 0 || (long long)ppc8 * (H * W + OH * OW) * 4 > 100 * 1024)) { ppc8 -= 8; }
-        if ((C % ppc8) == 0 && (long long)ppc8 * (H * W + OH * OW) * 4 <= 100 * 1024) {
-          ppc = ppc8;
-          int const cpad = (int)round_up(C, 8);
-          out_pk = &im.act_packs[vout.buf->p];
-          uint64_t const bytes = (uint64_t)vout.dims.dsz("img") * OH * OW * cpad * 2;
-          if (!out_pk->hi || out_pk->hi->bytes < bytes || (npl == 2 && !out_pk->lo)) {
-            out_pk->hi = std::make_shared<dev_buf_t>(bytes);
-            CU_CHK(cudaMemsetAsync(out_pk->hi->p, 0, bytes, st));
-            if (npl == 2) { out_pk->lo = std::make_shared<dev_buf_t>(bytes); CU_CHK(cudaMemsetAsync(out_pk->lo->p, 0, bytes, st)); }
-            out_pk->scale2 = std::make_shared<dev_buf_t>(8);
-            out_pk->absmax_bits = std::make_shared<dev_buf_t>(8);
-            CU_CHK(cudaMemsetAsync(out_pk->absmax_bits->p, 0, 8, st));
-          }
-          pp.hi = static_cast<uint16_t *>(out_pk->hi->p);
-          pp.lo = npl == 2 ? static_cast<uint16_t *>(out_pk->lo->p) : nullptr;
-          pp.scale2 = static_cast<float *>(out_pk->scale2->p);
-          pp.in_absmax = in_cell;
-          pp.C = C; pp.cpad = cpad; pp.bf16 = bf16 ? 1 : 0;
+      if (planes_ok) {
+        int const cpad = (int)round_up(C, 8);
+        out_pk = &im.act_packs[vout.buf->p];
+        uint64_t const bytes = (uint64_t)vout.dims.dsz("img") * OH * OW * cpad * 2;
+        if (!out_pk->hi || out_pk->hi->bytes < bytes || (npl == 2 && !out_pk->lo)) {
+          out_pk->hi = std::make_shared<dev_buf_t>(bytes);
+          CU_CHK(cudaMemsetAsync(out_pk->hi->p, 0, bytes, st));
+          if (npl == 2) { out_pk->lo = std::make_shared<dev_buf_t>(bytes); CU_CHK(cudaMemsetAsync(out_pk->lo->p, 0, bytes, st)); }
+          out_pk->scale2 = std::make_shared<dev_buf_t>(8);
+          out_pk->absmax_bits = std::make_shared<dev_buf_t>(8);
+          CU_CHK(cudaMemsetAsync(out_pk->absmax_bits->p, 0, 8, st));
         }
+        pp.hi = static_cast<uint16_t *>(out_pk->hi->p);
+        pp.lo = npl == 2 ? static_cast<uint16_t *>(out_pk->lo->p) : nullptr;
+        pp.scale2 = static_cast<float *>(out_pk->scale2->p);
+        pp.in_absmax = in_cell;
+        pp.C = C; pp.cpad = cpad; pp.bf16 = bf16 ? 1 : 0;
       }
-      size_t const smem = (size_t)ppc * (H * W + (pp.hi ? OH * OW : 0)) * 4;
+      size_t const smem = pipe_ppc ? pipe_smem : (size_t)ppc * (H * W + (pp.hi ? OH * OW : 0)) * 4;
       unsigned int *cell = absmax_cell("out");
+      long long const n_groups = ceil_div(planes, ppc);
+      // persistent grid: as many CTAs as fit the chip at this shared-memory footprint, each walking its share of the groups
+      unsigned const pipe_grid = (unsigned)std::min<long long>(n_groups, (long long)im.num_sms * std::max<long long>(1, std::min<long long>(8, (224 * 1024) / (long long)(smem + 1024))));
 #define B200_POOL_PLANE(K_, S_) do { \
         static bool attr_ = false; \
-        if (!attr_) { CU_CHK(cudaFuncSetAttribute(b200::pool_plane_kernel<K_, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); prefer_max_smem(b200::pool_plane_kernel<K_, S_>); attr_ = true; } \
-        launch_k(b200::pool_plane_kernel<K_, S_>, dim3((unsigned)ceil_div(planes, ppc)), dim3(256), smem, fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, cell, ppc, planes, pp); } while (0)
+        if (!attr_) { \
+          CU_CHK(cudaFuncSetAttribute(b200::pool_plane_kernel<K_, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); prefer_max_smem(b200::pool_plane_kernel<K_, S_>); \
+          CU_CHK(cudaFuncSetAttribute(b200::pool_plane_pipe_kernel<K_, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); prefer_max_smem(b200::pool_plane_pipe_kernel<K_, S_>); \
+          attr_ = true; } \
+        if (pipe_ppc) { launch_k(b200::pool_plane_pipe_kernel<K_, S_>, dim3(pipe_grid), dim3(256), smem, fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, cell, ppc, planes, pp); } \
+        else { launch_k(b200::pool_plane_kernel<K_, S_>, dim3((unsigned)n_groups), dim3(256), smem, fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, cell, ppc, planes, pp); } } while (0)
       if (KH == 3 && sy == 2) { B200_POOL_PLANE(3, 2); } else if (KH == 3) { B200_POOL_PLANE(3, 1); } else if (KH == 2) { B200_POOL_PLANE(2, 2); }
       else if (KH == 5) { B200_POOL_PLANE(5, 3); } else { B200_POOL_PLANE(7, 1); }
 #undef B200_POOL_PLANE

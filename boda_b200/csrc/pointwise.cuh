@@ -296,37 +296,52 @@ struct PoolPlanes {
 // L1/L2 and both global streams are long coalesced runs. Small planes (13x13, 27x27) would otherwise mean thousands of tiny CTAs that
 // are all ramp-up and no bandwidth (measured: 15 us for the 6.7 MB of AlexNet pool5 with one plane per CTA). The host picks planes-per-CTA
 // (a multiple of 4, which keeps every run 16-byte aligned) so that the tile fits the dynamic shared memory it requests.
+// Compute phase of the plane-group pool kernels: the np planes staged at plane_s ([np][H][W]) -> op ([np][OH][OW], global) and, when
+// `stage` is non-null, a shared-memory copy of the outputs for the NHWC plane write. Returns this thread's max|out|.
 template <int K, int S>
-__global__ void __launch_bounds__(256)
-pool_plane_kernel(float const *__restrict__ in, float *__restrict__ out, int H, int W, int OH, int OW, int py, int px, int avg_pool,
-                  unsigned int *out_absmax, int ppc, long long n_planes, PoolPlanes pp) {
-  pdl_prologue();
-  extern __shared__ __align__(16) float plane_s[];
-  long long const plane0 = static_cast<long long>(blockIdx.x) * ppc;
-  int const np = static_cast<int>(min(static_cast<long long>(ppc), n_planes - plane0));
-  int const hw = H * W, n_in = np * hw, ohw = OH * OW, n_out = np * ohw;
-  float const *ip = in + plane0 * hw;
-  if ((reinterpret_cast<uintptr_t>(ip) & 15) == 0) {
-    // all loads of a batch are issued before the first shared-memory store (8 x 16 B in flight per thread)
-    float4 const *ip4 = reinterpret_cast<float4 const *>(ip);
-    float4 *s4 = reinterpret_cast<float4 *>(plane_s);
-    int const n4 = n_in >> 2;
-    constexpr int kU = 8;
-    for (int base = threadIdx.x; base < n4; base += 256 * kU) {
-      float4 v[kU];
-#pragma unroll
-      for (int u = 0; u < kU; ++u) { int const i = base + u * 256; if (i < n4) { v[u] = __ldg(ip4 + i); } }
-#pragma unroll
-      for (int u = 0; u < kU; ++u) { int const i = base + u * 256; if (i < n4) { s4[i] = v[u]; } }
-    }
-    for (int i = (n4 << 2) + threadIdx.x; i < n_in; i += 256) { plane_s[i] = __ldg(ip + i); }
-  } else {
-    for (int i = threadIdx.x; i < n_in; i += 256) { plane_s[i] = __ldg(ip + i); }
-  }
-  __syncthreads();
+__device__ __forceinline__ float pool_planes_compute(float const *plane_s, float *stage, float *op, int np, int H, int W, int OH, int OW, int py, int px, int avg_pool) {
+  int const hw = H * W, ohw = OH * OW, n_out = np * ohw;
   float amax = 0.0f;
-  float *op = out + plane0 * ohw;
-  if (!avg_pool) {
+  if (!avg_pool && S == 1) {
+    // Stride-1 max pooling (GoogLeNet's inception pools): a work item is a run of kC outputs of one output row. It folds the K input rows
+    // into kC + K - 1 column maxima in registers (every input is loaded once per item, bounds tests hoisted per column / per row), then
+    // each output is the max of K neighbouring column maxima. Max is exact in any order, so this equals the reference's tap loop bit for
+    // bit. (The column-walk form below measured 98 instructions per output on 14x14 planes -- its per-column setup is not amortised over
+    // short columns -- and ran at 75 % issue utilisation, 11 % of DRAM peak: ncu, profiles/ncu_r01_googlenet_pool_fc.md.)
+    constexpr int kC = 8, kIn = kC + K - 1;
+    int const ncx = (OW + kC - 1) / kC, items = np * OH * ncx;
+    for (int it = threadIdx.x; it < items; it += 256) {
+      int const t = it / ncx, cx = it - t * ncx, pl = t / OH, oy = t - pl * OH;
+      int const ox0 = cx * kC, x_in0 = ox0 - px, y0 = oy - py;
+      bool xok[kIn];
+#pragma unroll
+      for (int c = 0; c < kIn; ++c) { xok[c] = static_cast<unsigned>(x_in0 + c) < static_cast<unsigned>(W); }
+      float vm[kIn];
+#pragma unroll
+      for (int c = 0; c < kIn; ++c) { vm[c] = -FLT_MAX; }
+      float const *pb = plane_s + pl * hw + x_in0;
+#pragma unroll
+      for (int ky = 0; ky < K; ++ky) {
+        if (static_cast<unsigned>(y0 + ky) < static_cast<unsigned>(H)) {
+          float const *pr = pb + (y0 + ky) * W;
+#pragma unroll
+          for (int c = 0; c < kIn; ++c) { if (xok[c]) { vm[c] = fmaxf(vm[c], pr[c]); } }
+        }
+      }
+      int const obase = pl * ohw + oy * OW + ox0;
+#pragma unroll
+      for (int o = 0; o < kC; ++o) {
+        if (ox0 + o < OW) {
+          float out_v = vm[o];
+#pragma unroll
+          for (int k = 1; k < K; ++k) { out_v = fmaxf(out_v, vm[o + k]); }
+          op[obase + o] = out_v;
+          if (stage) { stage[obase + o] = out_v; }
+          amax = fmaxf(amax, fabsf(out_v));
+        }
+      }
+    }
+  } else if (!avg_pool) {
     // Max pooling: a work item is one output column (plane, ox) over a segment of kSeg output rows. It keeps the horizontal maxima of the K
     // input rows under the current window in registers, so moving down one output row costs S new rows of K shared-memory loads and the
     // K - S others are reused; the x bounds tests are per item, the y test per row. Max is exact in any order, so this equals the
@@ -359,7 +374,7 @@ pool_plane_kernel(float const *__restrict__ in, float *__restrict__ out, int H, 
 #pragma unroll
         for (int k = 1; k < K; ++k) { out_v = fmaxf(out_v, hr[k]); }
         op[obase + oy * OW] = out_v;
-        if (pp.hi) { plane_s[n_in + obase + oy * OW] = out_v; }  // staged for the transposed (NHWC) plane write below
+        if (stage) { stage[obase + oy * OW] = out_v; }  // staged for the transposed (NHWC) plane write below
         amax = fmaxf(amax, fabsf(out_v));
         y0 += S;
         if (oy + 1 < oy1) {
@@ -390,24 +405,24 @@ pool_plane_kernel(float const *__restrict__ in, float *__restrict__ out, int H, 
       }
       out_v = __fdiv_rn(out_v, cnt);
       op[o] = out_v;
-      if (pp.hi) { plane_s[n_in + o] = out_v; }
+      if (stage) { stage[o] = out_v; }
       amax = fmaxf(amax, fabsf(out_v));
       ox += d_ox; oy += d_oy; pl += d_pl;
       if (ox >= OW) { ox -= OW; ++oy; }
       if (oy >= OH) { oy -= OH; ++pl; }
     }
   }
-  if (out_absmax) { publish_absmax_warp(amax, out_absmax); }
-  if (pp.hi) {
+  return amax;
+}
+
+// NHWC 16-bit plane write of the staged outputs `os` ([np][ohw], np a multiple of 8 consecutive channels of ONE image starting at plane0).
+__device__ __forceinline__ void pool_planes_write16(float const *os, PoolPlanes const &pp, long long plane0, int np, int ohw, float s) {
+  {
     // Layout-transform elimination: also write the NHWC 16-bit plane(s) the consuming convolution reads (it then skips its pack kernel). The
     // CTA's planes are np (a multiple of 8) consecutive channels of ONE image, so every pixel gets 16-byte runs of 8 channels. The fp16 planes'
     // power-of-two scale comes from max|in| (published by the producer of the pooled node): pooling never increases max|x|.
-    float const s = pp.in_absmax ? scale_from_absmax_bits(*pp.in_absmax) : 1.0f;
-    if (blockIdx.x == 0 && threadIdx.x == 0) { pp.scale2[0] = s; pp.scale2[1] = 1.0f / s; }
-    __syncthreads();
     long long const img = plane0 / pp.C;
     int const chan0 = static_cast<int>(plane0 - img * pp.C), groups = np >> 3;
-    float const *os = plane_s + n_in;
     for (int idx = threadIdx.x; idx < ohw * groups; idx += 256) {
       int const pix = idx / groups, g = idx - pix * groups;
       uint32_t wh[4], wl[4];
@@ -431,6 +446,96 @@ pool_plane_kernel(float const *__restrict__ in, float *__restrict__ out, int H, 
       if (pp.lo) { *reinterpret_cast<uint4 *>(pp.lo + o16) = make_uint4(wl[0], wl[1], wl[2], wl[3]); }
     }
   }
+}
+
+template <int K, int S>
+__global__ void __launch_bounds__(256)
+pool_plane_kernel(float const *__restrict__ in, float *__restrict__ out, int H, int W, int OH, int OW, int py, int px, int avg_pool,
+                  unsigned int *out_absmax, int ppc, long long n_planes, PoolPlanes pp) {
+  pdl_prologue();
+  extern __shared__ __align__(16) float plane_s[];
+  long long const plane0 = static_cast<long long>(blockIdx.x) * ppc;
+  int const np = static_cast<int>(min(static_cast<long long>(ppc), n_planes - plane0));
+  int const hw = H * W, n_in = np * hw, ohw = OH * OW, n_out = np * ohw;
+  float const *ip = in + plane0 * hw;
+  if ((reinterpret_cast<uintptr_t>(ip) & 15) == 0) {
+    // all loads of a batch are issued before the first shared-memory store (8 x 16 B in flight per thread)
+    float4 const *ip4 = reinterpret_cast<float4 const *>(ip);
+    float4 *s4 = reinterpret_cast<float4 *>(plane_s);
+    int const n4 = n_in >> 2;
+    constexpr int kU = 8;
+    for (int base = threadIdx.x; base < n4; base += 256 * kU) {
+      float4 v[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) { int const i = base + u * 256; if (i < n4) { v[u] = __ldg(ip4 + i); } }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) { int const i = base + u * 256; if (i < n4) { s4[i] = v[u]; } }
+    }
+    for (int i = (n4 << 2) + threadIdx.x; i < n_in; i += 256) { plane_s[i] = __ldg(ip + i); }
+  } else {
+    for (int i = threadIdx.x; i < n_in; i += 256) { plane_s[i] = __ldg(ip + i); }
+  }
+  __syncthreads();
+  float amax = 0.0f;
+  float *op = out + plane0 * ohw;
+  bool const stage_out = pp.hi != nullptr;
+  amax = pool_planes_compute<K, S>(plane_s, stage_out ? plane_s + n_in : nullptr, op, np, H, W, OH, OW, py, px, avg_pool);
+  if (out_absmax) { publish_absmax_warp(amax, out_absmax); }
+  if (pp.hi) {
+    // Layout-transform elimination: also write the NHWC 16-bit plane(s) the consuming convolution reads (it then skips its pack kernel). The
+    // CTA's planes are np (a multiple of 8) consecutive channels of ONE image, so every pixel gets 16-byte runs of 8 channels. The fp16 planes'
+    // power-of-two scale comes from max|in| (published by the producer of the pooled node): pooling never increases max|x|.
+    float const s = pp.in_absmax ? scale_from_absmax_bits(*pp.in_absmax) : 1.0f;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { pp.scale2[0] = s; pp.scale2[1] = 1.0f / s; }
+    __syncthreads();
+    pool_planes_write16(plane_s + n_in, pp, plane0, np, ohw, s);
+  }
+}
+
+// Persistent, double-buffered form of the same kernel: each CTA walks plane groups g = blockIdx.x, blockIdx.x + gridDim.x, ... and one
+// thread fetches group g+1 with a 1-D bulk copy (cp.async.bulk, completion on an mbarrier) while all threads pool group g, so the HBM read
+// stream never stops for the compute phase (with one group per CTA, co-resident CTAs load together and then compute together: 21 % of DRAM
+// peak on AlexNet pool1, ncu). Host guarantees: every group's byte count is a multiple of 16 and `in` is 16-byte aligned.
+template <int K, int S>
+__global__ void __launch_bounds__(256)
+pool_plane_pipe_kernel(float const *__restrict__ in, float *__restrict__ out, int H, int W, int OH, int OW, int py, int px, int avg_pool,
+                       unsigned int *out_absmax, int ppc, long long n_planes, PoolPlanes pp) {
+  extern __shared__ __align__(128) float plane_s[];
+  __shared__ __align__(8) uint64_t full_bar[2];
+  int const hw = H * W, ohw = OH * OW;
+  int const buf_floats = (ppc * hw + 31) & ~31;  // 128-byte aligned buffers
+  float *stage = pp.hi ? plane_s + 2 * buf_floats : nullptr;
+  long long const n_groups = (n_planes + ppc - 1) / ppc;
+  if (threadIdx.x == 0) { mbar_init(&full_bar[0], 1); mbar_init(&full_bar[1], 1); fence_barrier_init(); }
+  __syncthreads();
+  pdl_prologue();
+  auto fetch = [&](long long g, int b) {  // one thread
+    long long const p0 = g * ppc;
+    uint32_t const bytes = static_cast<uint32_t>(min(static_cast<long long>(ppc), n_planes - p0)) * static_cast<uint32_t>(hw) * 4u;
+    mbar_expect_tx(&full_bar[b], bytes);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(plane_s + b * buf_floats)),
+                 "l"(in + p0 * hw), "r"(bytes), "r"(smem_u32(&full_bar[b]))
+                 : "memory");
+  };
+  float const s = (pp.hi && pp.in_absmax) ? scale_from_absmax_bits(*pp.in_absmax) : 1.0f;
+  if (pp.hi && blockIdx.x == 0 && threadIdx.x == 0) { pp.scale2[0] = s; pp.scale2[1] = 1.0f / s; }
+  float amax = 0.0f;
+  long long g = blockIdx.x;
+  if (threadIdx.x == 0 && g < n_groups) { fetch(g, 0); }
+  for (int it = 0; g < n_groups; g += gridDim.x, ++it) {
+    int const b = it & 1;
+    if (threadIdx.x == 0 && g + gridDim.x < n_groups) { fetch(g + gridDim.x, b ^ 1); }  // (buffer b^1 was released by the barrier below)
+    mbar_wait(&full_bar[b], (it >> 1) & 1);
+    long long const plane0 = g * ppc;
+    int const np = static_cast<int>(min(static_cast<long long>(ppc), n_planes - plane0));
+    amax = fmaxf(amax, pool_planes_compute<K, S>(plane_s + b * buf_floats, stage, out + plane0 * ohw, np, H, W, OH, OW, py, px, avg_pool));
+    __syncthreads();  // everybody is done with buffer b; the staged outputs are complete
+    if (pp.hi) {
+      pool_planes_write16(stage, pp, plane0, np, ohw, s);
+      __syncthreads();  // ... before the next group overwrites the stage
+    }
+  }
+  if (out_absmax) { publish_absmax_warp(amax, out_absmax); }
 }
 
 // ---- lrn (test/rtc/lrn.cucl:35-50, LRN_MATCH_CAFFE branch) ----------------------------------------------------
