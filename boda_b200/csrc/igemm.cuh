@@ -465,15 +465,20 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
       } else {  // row = channel, columns = pixels
         int const ch = prow;
         float const b = (final_out && prm.has_bias) ? __ldg(prm.bias + ch) : 0.0f;
+        // (img, pix) of column j advance by carries: one integer division per row, not per element -- with it the 64 stores of an
+        // inner-product layer's tile took 9 us, half of the kernel (tools/fc_experiments.py)
+        int const img0 = n0 / prm.out_hw;
+        int pix = n0 - img0 * prm.out_hw;
+        long long off = (static_cast<long long>(img0) * prm.out_chans + ch) * prm.out_hw + pix;
+        long long const img_step = static_cast<long long>(prm.out_chans) * prm.out_hw - (prm.out_hw - 1);  // last pixel of an image -> first of the next
 #pragma unroll
         for (int j = 0; j < BN; ++j) {
-          int const pel = n0 + j;
-          if (pel < prm.q_rows) {
-            int const img = pel / prm.out_hw, pix = pel - img * prm.out_hw;
+          if (n0 + j < prm.q_rows) {
             float const v = fmaxf(fmaf(acc[j], inv, b), floor_v);
             amax = fmaxf(amax, fabsf(v));
-            outp[(static_cast<long long>(img) * prm.out_chans + ch) * prm.out_hw + pix] = v;
+            outp[off] = v;
           }
+          if (++pix == prm.out_hw) { pix = 0; off += img_step; } else { off += 1; }
         }
       }
     }
@@ -497,8 +502,18 @@ __global__ void splitk_reduce_kernel(float const *__restrict__ ws, float *__rest
   long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   float v = 0.0f;
   if (i < n) {
-    for (int s = 0; s < splits; ++s) { v += ws[s * n + i]; }
-    if (bias) { v += __ldg(bias + (i / out_hw) % out_chans); }
+    // partial sums are added in split order (deterministic); four loads in flight at a time instead of one load -> add chain per split
+    int s = 0;
+    for (; s + 4 <= splits; s += 4) {
+      float const a0 = ws[s * n + i], a1 = ws[(s + 1) * n + i], a2 = ws[(s + 2) * n + i], a3 = ws[(s + 3) * n + i];
+      v += a0; v += a1; v += a2; v += a3;
+    }
+    for (; s < splits; ++s) { v += ws[s * n + i]; }
+    if (bias) {
+      long long const c = (n < (1ll << 31)) ? static_cast<long long>((static_cast<unsigned>(i) / static_cast<unsigned>(out_hw)) % static_cast<unsigned>(out_chans))
+                                            : (i / out_hw) % out_chans;
+      v += __ldg(bias + c);
+    }
     if (relu) { v = fmaxf(v, 0.0f); }
     long long o = i;
     if (out_img_stride) { long long const per_img = static_cast<long long>(out_chans) * out_hw, img = i / per_img; o = img * out_img_stride + (i - img * per_img); }
