@@ -293,7 +293,7 @@ def test_relu_softmax_copy_reduce(runner, oracle):
         x = rng.randn(*shape).astype(np.float32)
         got = runner.run_unary("relu", "(str_vals=(type=ReLU),nda_vals=(inout=(%s)))" % nchw_dims_text(shape), x, shape, in_name="inout", out_name="inout")
         assert np.array_equal(got, oracle.relu(x))
-    for shape in [(4, 1000, 1, 1), (2, 10, 3, 4), (1, 33, 1, 1)]:
+    for shape in [(4, 1000, 1, 1), (2, 10, 3, 4), (1, 33, 1, 1), (2, 1500, 1, 2), (3, 1024, 1, 1)]:  # > 1024 channels: the three-pass form
         x = (rng.randn(*shape) * 4).astype(np.float32)
         got = runner.run_unary("softmax", "(str_vals=(type=Softmax),nda_vals=(in=(%s),prob=(%s)))" % (nchw_dims_text(shape), nchw_dims_text(shape)), x, shape, out_name="prob")
         assert oracle.mrd(oracle.softmax(x), got) < 1e-5
