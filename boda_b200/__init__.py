@@ -61,6 +61,7 @@ _SIGS = {
     "b200_wisdom_record": (_c.c_int64, [_c.c_char_p, _c.c_int, _c.POINTER(_c.c_char_p), _c.POINTER(_c.c_char_p), _c.c_char_p, _c.c_char_p, _c.c_double, _c.c_char_p,
                                         _c.c_char_p, _c.c_char_p, _c.c_uint64]),
     "b200_pipe_from_prototxt": (_c.c_int64, [_c.c_char_p, _c.c_char_p, _c.c_char_p, _c.c_uint64]),
+    "b200_fwd_plan": (_c.c_int64, [_c.c_char_p, _c.c_char_p, _c.c_char_p, _c.c_uint64]),
     "b200_fwd_create": (_c.c_void_p, [_c.c_char_p, _c.c_char_p]),
     "b200_fwd_destroy": (None, [_c.c_void_p]),
     "b200_fwd_set_param": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_void_p, _c.c_uint64]),
@@ -165,6 +166,27 @@ def pipe_describe(pipe_text: str) -> Dict[str, object]:
         if len(parts) > 2 and parts[2] == "param":
             params.append(parts[0])
     res["nodes"], res["params"] = nodes, params
+    return res
+
+
+def fwd_plan(pipe_text: str, opts: str = "") -> Dict[str, object]:
+    """Host-only (no GPU): the forward as B200ConvFwd would plan it for this pipe and these options -- graph passes and per-layer launch
+    plans for a 148-SM device (b200_fwd_plan). Returns {"calls": [(func_name, {arg: var-or-scalar})], "prep": [...], "alias": {node: (concat
+    node, chan offset)}, "join": {conv tag: (join node, residual node)}, "absmax": {node: cell}}. A plan cannot compute anything."""
+    need = _chk(lib().b200_fwd_plan(_b(pipe_text), _b(opts), None, 0))
+    buf = ctypes.create_string_buffer(need + 1)
+    _chk(lib().b200_fwd_plan(_b(pipe_text), _b(opts), buf, need + 1))
+    res: Dict[str, object] = {"calls": [], "prep": [], "alias": {}, "join": {}, "absmax": {}}
+    for line in buf.value.decode().splitlines():
+        parts = line.split(" ")
+        if parts[0] in ("call", "prep"):
+            res["calls" if parts[0] == "call" else "prep"].append((parts[1], dict(p.split("=", 1) for p in parts[2:])))
+        elif parts[0] == "alias":
+            res["alias"][parts[1]] = (parts[2], int(parts[3]))
+        elif parts[0] == "join":
+            res["join"][parts[1]] = (parts[2], parts[3])
+        elif parts[0] == "absmax":
+            res["absmax"][parts[1]] = int(parts[2])
     return res
 
 

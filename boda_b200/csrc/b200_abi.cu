@@ -139,6 +139,23 @@ B200_API int64_t b200_pipe_describe(const char *pipe_text, char *buf, uint64_t b
   return rc == 0 ? need : rc;
 }
 
+B200_API int64_t b200_fwd_plan(const char *pipe_text, const char *opts, char *buf, uint64_t buf_len) {
+  int64_t need = -1;
+  int const rc = guarded([&] {
+    string o = (opts && opts[0]) ? string(opts) : string("()");
+    size_t const close = o.rfind(')');
+    if (o.empty() || o[0] != '(' || close == string::npos) { rt_err("b200_fwd_plan: opts must be a (key=value,...) list"); }
+    o = o.substr(0, close) + (close > 1 ? "," : "") + "plan_only=1)";
+    b200_conv_fwd_t fwd;
+    fwd.init(make_conv_pipe_from_text(pipe_text), o);
+    string const out = fwd.plan_text();
+    need = (int64_t)out.size();
+    if (buf && buf_len) { snprintf(buf, buf_len, "%s", out.c_str()); }
+    return 0;
+  });
+  return rc == 0 ? need : rc;
+}
+
 B200_API int64_t b200_pipe_from_prototxt(const char *prototxt_text, const char *opts, char *buf, uint64_t buf_len) {
   int64_t need = -1;
   int const rc = guarded([&] {

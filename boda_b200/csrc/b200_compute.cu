@@ -193,7 +193,7 @@ struct b200_impl_t {
 b200_compute_t::b200_compute_t() : impl(new b200_impl_t) {}
 b200_compute_t::~b200_compute_t() {
   if (impl) {
-    if (impl->inited) { cudaStreamSynchronize(impl->stream); }
+    if (impl->inited && !plan_only) { cudaStreamSynchronize(impl->stream); }
     release_per_call_id_data();
     impl->funcs.clear();
     impl->vars.clear();
@@ -204,6 +204,12 @@ b200_compute_t::~b200_compute_t() {
 
 void b200_compute_t::init() {
   if (impl->inited) { return; }
+  if (plan_only) {  // no device: launch plans only (b200_fwd_plan); run() and every copy refuse
+    impl->num_sms = plan_num_sms;
+    impl->plat_tag = "b200:plan-only";
+    impl->inited = true;
+    return;
+  }
   int ndev = 0;
   cudaError_t const e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) { rt_err(string("be=b200 needs a CUDA device and there is no CPU fallback: ") + cudaGetErrorString(e)); }
@@ -232,9 +238,11 @@ void b200_compute_t::create_var_with_dims(string const &vn, dims_t const &dims) 
   var_info_t v;
   v.dims = dims;
   v.dims.calc_strides();
-  v.buf = std::make_shared<dev_buf_t>(dims.bytes_sz());
   v.gen = std::make_shared<uint64_t>(1);
-  CU_CHK(cudaMemsetAsync(v.buf->p, 0, std::max<uint64_t>(dims.bytes_sz(), 16), impl->stream));  // new vars are zero-filled
+  if (!plan_only) {
+    v.buf = std::make_shared<dev_buf_t>(dims.bytes_sz());
+    CU_CHK(cudaMemsetAsync(v.buf->p, 0, std::max<uint64_t>(dims.bytes_sz(), 16), impl->stream));  // new vars are zero-filled
+  }
   impl->vars[vn] = v;
 }
 void b200_compute_t::create_var_with_dims_as_reshaped_view_of_var(string const &vn, dims_t const &dims, string const &src_vn) {
@@ -248,11 +256,12 @@ void b200_compute_t::create_var_with_dims_as_reshaped_view_of_var(string const &
 }
 void b200_compute_t::release_var(string const &vn) {
   var_info_t &v = impl->must_var(vn);
-  if (v.buf.use_count() == 1) { impl->act_packs.erase(v.buf->p); }  // last name of this storage: drop its packed planes too
+  if (v.buf && v.buf.use_count() == 1) { impl->act_packs.erase(v.buf->p); }  // last name of this storage: drop its packed planes too
   impl->vars.erase(vn);
 }
 dims_t b200_compute_t::get_var_dims(string const &vn) { return impl->must_var(vn).dims; }
 void b200_compute_t::set_var_to_zero(string const &vn) {
+  if (plan_only) { rt_err("plan-only instance (no device): vars have no storage; there is no CPU fallback"); }
   var_info_t &v = impl->must_var(vn);
   CU_CHK(cudaMemsetAsync(v.buf->p, 0, v.dims.bytes_sz(), impl->stream));
   impl->bump(v);
@@ -268,17 +277,20 @@ void b200_compute_t::copy_var_to_nda(p_nda_t const &nda, string const &vn) {
   copy_var_to_raw(nda->rp_elems(), vn, v.dims.bytes_sz());
 }
 void b200_compute_t::copy_raw_to_var_async(string const &vn, void const *src, uint64_t bytes) {
+  if (plan_only) { rt_err("plan-only instance (no device): vars have no storage; there is no CPU fallback"); }
   var_info_t &v = impl->must_var(vn);
   if (bytes != v.dims.bytes_sz()) { rt_err("copy to var '" + vn + "': got " + str(bytes) + " bytes, var holds " + str(v.dims.bytes_sz())); }
   CU_CHK(cudaMemcpyAsync(v.buf->p, src, bytes, cudaMemcpyHostToDevice, impl->stream));
   impl->bump(v);
 }
 void b200_compute_t::copy_var_to_raw_async(void *dst, string const &vn, uint64_t bytes) {
+  if (plan_only) { rt_err("plan-only instance (no device): vars have no storage; there is no CPU fallback"); }
   var_info_t &v = impl->must_var(vn);
   if (bytes != v.dims.bytes_sz()) { rt_err("copy from var '" + vn + "': asked " + str(bytes) + " bytes, var holds " + str(v.dims.bytes_sz())); }
   CU_CHK(cudaMemcpyAsync(dst, v.buf->p, bytes, cudaMemcpyDeviceToHost, impl->stream));
 }
 void b200_compute_t::copy_device_to_var_async(string const &vn, void const *dev_src, uint64_t bytes) {
+  if (plan_only) { rt_err("plan-only instance (no device): vars have no storage; there is no CPU fallback"); }
   var_info_t &v = impl->must_var(vn);
   if (bytes != v.dims.bytes_sz()) { rt_err("copy to var '" + vn + "': got " + str(bytes) + " bytes, var holds " + str(v.dims.bytes_sz())); }
   CU_CHK(cudaMemcpyAsync(v.buf->p, dev_src, bytes, cudaMemcpyDeviceToDevice, impl->stream));
@@ -293,6 +305,7 @@ void b200_compute_t::copy_var_to_raw(void *dst, string const &vn, uint64_t bytes
   CU_CHK(cudaStreamSynchronize(impl->stream));
 }
 p_nda_t b200_compute_t::get_var_raw_native_pointer(string const &vn) {
+  if (plan_only) { rt_err("plan-only instance (no device): vars have no storage; there is no CPU fallback"); }
   var_info_t &v = impl->must_var(vn);
   impl->bump(v);  // the caller may write through the pointer: invalidate anything derived from this var
   p_nda_t r = std::make_shared<nda_t>(v.dims, false);
@@ -469,7 +482,7 @@ void b200_compute_t::release_func(string const &func_name) {
   if (!impl->funcs.erase(func_name)) { rt_err("release_func: '" + func_name + "' not found"); }
 }
 void b200_compute_t::release_all_funcs() { impl->funcs.clear(); }
-void b200_compute_t::finish_and_sync() { CU_CHK(cudaStreamSynchronize(impl->stream)); }
+void b200_compute_t::finish_and_sync() { if (!plan_only) { CU_CHK(cudaStreamSynchronize(impl->stream)); } }
 void b200_compute_t::release_per_call_id_data() {
   for (auto &c : impl->calls) { for (cudaEvent_t ev : {c.b, c.e, c.kb, c.ke}) { if (ev) { cudaEventDestroy(ev); } } }
   impl->calls.clear();
@@ -1242,6 +1255,7 @@ struct run_ctx_t {
 
 uint32_t b200_compute_t::run(rtc_func_call_t const &rfc) {
   assert_st(impl->inited);
+  if (plan_only) { rt_err("run: this is a plan-only instance (no device); there is no CPU fallback"); }
   auto fi = impl->funcs.find(rfc.rtc_func_name);
   if (fi == impl->funcs.end()) { rt_err("run: function '" + rfc.rtc_func_name + "' was not compiled"); }
   for (auto const &kv : rfc.arg_map) { if (!kv.second.is_valid()) { rt_err("run: invalid argument '" + kv.first + "'"); } }

@@ -73,6 +73,8 @@ struct b200_compute_t {
                             // Off by default: measured slower than the CTA-pair im2col kernel on the AlexNet layers (profiles/), kept for A/B runs
   int taps_max_b_stages = 8, taps_max_a_stages = 3;  // experiments: cap the tap-reuse kernel's ring depths
   int taps_2cta = -1;       // tap-reuse kernel: -1 = cost model picks single CTAs or CTA pairs, 0 / 1 = force
+  int plan_only = 0;        // host-side planning / inspection only: init() touches no device (plans for plan_num_sms SMs), vars carry dims but no
+  int plan_num_sms = 148;   // storage, compile() plans as usual and every call that would compute or copy throws. Never a compute path.
 
   b200_compute_t();
   ~b200_compute_t();

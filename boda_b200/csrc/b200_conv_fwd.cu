@@ -423,6 +423,8 @@ void b200_conv_fwd_t::init(p_conv_pipe_t const &cp_, string const &opts) {
         else if (k == "enable_prof") { enable_prof = (uint32_t)std::stoul(v); }
         else if (k == "concat_by_offset") { concat_by_offset = (uint32_t)std::stoul(v); }
         else if (k == "fuse_eltwise") { fuse_eltwise = (uint32_t)std::stoul(v); }
+        else if (k == "plan_only") { rtc->plan_only = std::stoi(v); }
+        else if (k == "plan_num_sms") { rtc->plan_num_sms = std::stoi(v); }
         else if (k == "pack_by_producers") { pack_by_producers = (uint32_t)std::stoul(v); }
         else { rt_err("mode=b200: unused option '" + k + "'"); }  // NESI rejects unused keys (src/nesi.cc:25-35)
       }
@@ -517,6 +519,24 @@ void b200_conv_fwd_t::init(p_conv_pipe_t const &cp_, string const &opts) {
   }
   info_log = "mode=b200 plat=" + rtc->get_plat_tag() + " nodes=" + str(cp->nodes.size()) + " ops=" + str(cp->ops.size()) + " fwd_calls=" + str(fwd_calls.size()) +
              " conv_flops=" + str(cp->total_conv_flops());
+}
+
+string b200_conv_fwd_t::plan_text() const {
+  string out;
+  auto put_call = [&](char const *kind, fwd_call_t const &c) {
+    out += string(kind) + " " + c.func_name;
+    for (auto const &kv : c.rfc.arg_map) {
+      out += " " + kv.first + "=";
+      if (kv.second.is_var()) { out += kv.second.get_var(); } else { out += str((uint64_t)nda_scalar_as_double(*kv.second.get_nda())); }
+    }
+    out += "\n";
+  };
+  for (auto const &c : prep_calls) { put_call("prep", c); }
+  for (auto const &c : fwd_calls) { put_call("call", c); }
+  for (auto const &kv : concat_alias) { out += "alias " + kv.first + " " + kv.second.cat_node + " " + str(kv.second.ocix) + "\n"; }
+  for (auto const &kv : res_fuse) { out += "join " + kv.first + " " + kv.second.out_node + " " + kv.second.res_node + "\n"; }
+  for (auto const &kv : absmax_ix) { out += "absmax " + kv.first + " " + str(kv.second) + "\n"; }
+  return out;
 }
 
 void b200_conv_fwd_t::set_param(string const &node_name, float const *src, uint64_t n_elems) {

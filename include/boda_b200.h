@@ -65,6 +65,12 @@ uint64_t b200_rtc_launches(b200_rtc *r);           /* kernels launched so far by
  * truncated to buf_len). Returns the full length needed (excluding the NUL), or <0 on a malformed pipe (see b200_last_error). */
 int64_t b200_pipe_describe(const char *pipe_text, char *buf, uint64_t buf_len);
 
+/* Host-only: the forward as b200_fwd_create would plan it for this pipe and these options -- graph passes (concat by offset, residual joins
+ * in the convolution, producer-written planes, abs-max cells) and the launch plan of every convolution for a 148-SM device -- without touching
+ * a device ("plan_only=1" instance: it cannot compute). Text, one item per line: "call <func> <arg>=<var|scalar> ...", "prep <func> ...",
+ * "alias <node> <concat node> <chan offset>", "join <conv tag> <join node> <residual node>", "absmax <node> <cell>".
+ * Returns the text length (the buffer gets at most buf_len-1 chars) or <0. */
+int64_t b200_fwd_plan(const char *pipe_text, const char *opts, char *buf, uint64_t buf_len);
 /* Caffe prototxt (protobuf text format) -> pipe text, host-only, no protobuf: the translation of create_pipe_from_param
  * (src/caffepb.cc:166-326) for TEST-phase forward graphs. `opts` is a lexp list: "(img=32)" style dims overrides for the source nodes
  * (the reference's in_dims), "out_node_name=<node>" to stop after the layer producing it, "keep_softmax=1" to keep Softmax layers (the

@@ -1,0 +1,92 @@
+"""Host-only tests of the forward PLAN (b200_fwd_plan: graph passes + launch plans, no device): concat by offset, residual joins inside the
+producing convolution, producer-written planes, abs-max cells. The same decisions are exercised numerically by tests/test_gpu_nets.py; here
+their structure is checked on the CPU, on the four BASELINE nets at their bench batch sizes."""
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def bb():
+    import boda_b200
+    boda_b200.lib()
+    return boda_b200
+
+
+def _kinds(plan):
+    k = {}
+    for f, _ in plan["calls"]:
+        k[f.split("__")[0]] = k.get(f.split("__")[0], 0) + 1
+    return k
+
+
+def test_resnet50_joins_are_planned_into_their_convolutions(bb):
+    from boda_b200 import nets
+    txt, i, o = nets.resnet50(32)
+    plan = bb.fwd_plan(txt, "")
+    assert _kinds(plan) == {"conv": 54, "pool": 2, "softmax": 1}  # 53 convolutions + fc1000; no reduce kernels left
+    assert len(plan["join"]) == 16 and len(plan["prep"]) == 53     # one BatchNorm/Scale fold per convolution
+    order = {f.split("__")[1]: n for n, (f, _) in enumerate(plan["calls"])}
+    writer_of = {a["out"]: f.split("__")[1] for f, a in plan["calls"] if "out" in a}
+    for conv_tag, (join_node, res_node) in plan["join"].items():
+        assert conv_tag.endswith("_branch2c") and join_node == conv_tag[:-len("_branch2c")]
+        args = dict(plan["calls"][order[conv_tag]][1])
+        assert args["out"] == join_node and args["res"] == res_node
+        assert res_node in plan["absmax"] and join_node in plan["absmax"]    # the residual's max bounds the fp16 planes of the join
+        feeds_conv = any(f.startswith("conv__") and a.get("in") == join_node for f, a in plan["calls"])
+        assert "res_absmax_cells" in args and ("out_pack" in args) == feeds_conv  # the epilogue also writes the consumers' planes (res5c feeds a pool)
+        assert order[writer_of[res_node]] < order[conv_tag]                  # the shortcut is complete before the convolution runs
+        # projection blocks join with their branch1 convolution, identity blocks with the previous join
+        assert res_node == (join_node + "_branch1" if join_node.endswith("a") else writer_of[res_node]) or res_node.startswith("res")
+    unfused = bb.fwd_plan(txt, "(fuse_eltwise=0)")
+    assert _kinds(unfused) == {"conv": 54, "pool": 2, "softmax": 1, "reduce": 16} and not unfused["join"]
+    assert len(unfused["calls"]) == len(plan["calls"]) + 16
+
+
+def test_googlenet_concat_inputs_are_written_in_place(bb):
+    from boda_b200 import nets
+    txt, i, o = nets.googlenet_conv(64)
+    desc = bb.pipe_describe(txt)["nodes"]
+    plan = bb.fwd_plan(txt, "(prec=bf16)")
+    assert _kinds(plan) == {"conv": 64, "pool": 16, "lrn": 2} and len(plan["alias"]) == 36   # 9 inception Concats x 4 inputs, no copy kernels
+    chans = lambda n: dict(desc[n])["chan"]
+    per_cat = {}
+    for node, (cat, ocix) in plan["alias"].items():
+        per_cat.setdefault(cat, []).append((ocix, chans(node)))
+        call = next(a for f, a in plan["calls"] if a.get("out") == node)
+        assert call["out_concat"] == cat and int(call["out_ocix"]) == ocix and ocix % 8 == 0
+    assert len(per_cat) == 9
+    for cat, parts in per_cat.items():  # the four slices tile the Concat output exactly
+        parts.sort()
+        assert parts[0][0] == 0 and all(a[0] + a[1] == b[0] for a, b in zip(parts, parts[1:])) and parts[-1][0] + parts[-1][1] == chans(cat)
+    copies = bb.fwd_plan(txt, "(prec=bf16,concat_by_offset=0)")
+    assert _kinds(copies).get("copy") == 36 and not copies["alias"]
+    # bf16 planes pass through Concats; the fp16 planes of the fp32-parity mode do not (each producer would derive its own scale)
+    n_pack = lambda p: sum(1 for _, a in p["calls"] if "out_pack" in a)
+    assert n_pack(plan) > n_pack(bb.fwd_plan(txt, "")) > 0 and n_pack(bb.fwd_plan(txt, "(pack_by_producers=0)")) == 0
+
+
+@pytest.mark.parametrize("net,batch,n_calls", [("alexnet_ng_conv", 32, 13), ("nin_imagenet", 32, 16)])
+def test_plain_chains_plan_one_call_per_layer(bb, net, batch, n_calls):
+    from boda_b200 import nets
+    txt, i, o = nets.NETS[net](batch)
+    plan = bb.fwd_plan(txt, "")
+    assert len(plan["calls"]) == n_calls and not plan["alias"] and not plan["join"] and not plan["prep"]
+    convs = [a for f, a in plan["calls"] if f.startswith("conv__")]
+    assert all("in_absmax_cells" in a for a in convs[1:])  # every convolution but the first gets max|in| from its producer
+
+
+def test_a_plan_cannot_compute(bb):
+    """plan_only instances exist for inspection; anything that would need the device refuses (there is no CPU fallback)."""
+    from boda_b200 import nets
+    txt, i, o = nets.tiny_resnet(2)
+    plan = bb.fwd_plan(txt, "")
+    assert len(plan["join"]) == 3 and "reduce" not in _kinds(plan)
+    f = bb.B200ConvFwd(txt, "(plan_only=1)")
+    with pytest.raises(bb.RtException):
+        f.set_param("conv1_filts", np.zeros((16, 3, 7, 7), np.float32))
+    with pytest.raises(bb.RtException):
+        f.run_fwd({i: np.zeros((2, 3, 33, 33), np.float32)}, [o])
+    with pytest.raises(bb.RtException):
+        bb.fwd_plan(txt, "(bogus=1)")
+    with pytest.raises(bb.RtException):
+        bb.fwd_plan(txt, "prec=bf16")  # not a (key=value,...) list
