@@ -62,6 +62,7 @@ _SIGS = {
                                         _c.c_char_p, _c.c_char_p, _c.c_uint64]),
     "b200_pipe_from_prototxt": (_c.c_int64, [_c.c_char_p, _c.c_char_p, _c.c_char_p, _c.c_uint64]),
     "b200_fwd_plan": (_c.c_int64, [_c.c_char_p, _c.c_char_p, _c.c_char_p, _c.c_uint64]),
+    "b200_wis_ana": (_c.c_int64, [_c.c_char_p, _c.c_uint32, _c.c_char_p, _c.c_char_p, _c.c_double, _c.c_int, _c.c_char_p, _c.c_uint64]),
     "b200_fwd_create": (_c.c_void_p, [_c.c_char_p, _c.c_char_p]),
     "b200_fwd_destroy": (None, [_c.c_void_p]),
     "b200_fwd_set_param": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_void_p, _c.c_uint64]),
@@ -187,6 +188,25 @@ def fwd_plan(pipe_text: str, opts: str = "") -> Dict[str, object]:
             res["join"][parts[1]] = (parts[2], parts[3])
         elif parts[0] == "absmax":
             res["absmax"][parts[1]] = int(parts[2])
+    return res
+
+
+def wis_ana(wisdom_text: str, s_img: int = 0, s_plat: str = ".*", ref_tune: str = "", min_flops: float = 0.0, csv: bool = False):
+    """The reference's wis-ana analysis (src/op-tuner.cc:204-396) over wisdom text in its format. csv=True: the text wis-plot.py reads.
+    Otherwise {"aom_tune": tune, "tot_runs": n, "rows": [{"op", "flops", "aom", "pom", "ref", "pom_tune"}]} (seconds; NaN = no such run)."""
+    args = (_b(wisdom_text), s_img, _b(s_plat), _b(ref_tune), float(min_flops), 0 if csv else 1)
+    need = _chk(lib().b200_wis_ana(*args, None, 0))
+    buf = ctypes.create_string_buffer(need + 1)
+    _chk(lib().b200_wis_ana(*args, buf, need + 1))
+    text = buf.value.decode()
+    if csv:
+        return text
+    lines = text.splitlines()
+    head = lines[0].split("\t")
+    res = {"aom_tune": head[1], "tot_runs": int(head[3]), "rows": []}
+    for l in lines[1:]:
+        fl, aom, pom, ref, tune, op = l.split("\t")
+        res["rows"].append({"op": op, "flops": int(fl), "aom": float(aom), "pom": float(pom), "ref": float(ref), "pom_tune": tune})
     return res
 
 

@@ -206,6 +206,29 @@ B200_API int64_t b200_wisdom_record(const char *op_text, int n_kgs, const char *
   return rc == 0 ? need : rc;
 }
 
+B200_API int64_t b200_wis_ana(const char *wisdom_text, uint32_t s_img, const char *s_plat, const char *ref_tune, double min_flops, int detail, char *buf,
+                              uint64_t buf_len) {
+  int64_t need = -1;
+  int const rc = guarded([&] {
+    wis_ana_opts_t o;
+    o.s_img = s_img; o.min_flops = min_flops;
+    if (s_plat && s_plat[0]) { o.s_plat = s_plat; }
+    if (ref_tune) { o.ref_tune = ref_tune; }
+    wis_ana_res_t const res = wis_ana(read_wisdom_text(wisdom_text), o);
+    string out;
+    if (!detail) { out = wis_ana_csv(res, o); }
+    else {
+      auto num = [](double v) { char b[64]; snprintf(b, sizeof(b), "%.9g", v); return string(b); };
+      out = "#aom_tune\t" + res.aom_tune + "\ttot_runs\t" + str(res.tot_runs) + "\n";
+      for (auto const &r : res.rows) { out += str(r.flops) + "\t" + num(r.aom) + "\t" + num(r.pom) + "\t" + num(r.ref) + "\t" + r.pom_tune + "\t" + r.op_text + "\n"; }
+    }
+    need = (int64_t)out.size();
+    if (buf && buf_len) { snprintf(buf, buf_len, "%s", out.c_str()); }
+    return 0;
+  });
+  return rc == 0 ? need : rc;
+}
+
 // ---- tier B ----
 B200_API b200_fwd *b200_fwd_create(const char *pipe_text, const char *opts) {
   b200_fwd *f = nullptr;

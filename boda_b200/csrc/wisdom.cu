@@ -1,6 +1,8 @@
 // wisdom.cu -- see wisdom.h. Host-only code.
 #include "wisdom.h"
+#include <cmath>
 #include <functional>
+#include <regex>
 #include <limits>
 #include <random>
 #include <set>
@@ -95,6 +97,141 @@ string wisdom_record_text(string const &op_text, vector<std::pair<string, string
   }
   out << "/op_wisdom_t\n";
   return out.str();
+}
+
+// ---- reader (src/op-tuner.cc:17-93) ----------------------------------------------------------------------------------
+namespace {
+struct line_reader_t {
+  string const &t;
+  size_t pos = 0;
+  explicit line_reader_t(string const &t_) : t(t_) {}
+  bool getline(string &out) {  // false at EOF
+    if (pos >= t.size()) { return false; }
+    size_t const e = t.find('\n', pos);
+    out = t.substr(pos, (e == string::npos ? t.size() : e) - pos);
+    pos = (e == string::npos) ? t.size() : e + 1;
+    return true;
+  }
+  string must_getline() {
+    string r;
+    if (!getline(r)) { rt_err("error reading line-oriented text stream. expected a non-empty line, but got EOF."); }
+    return r;
+  }
+};
+double parse_secs(string const &s) {
+  if (s == "nan" || s == "-nan") { return std::nan(""); }
+  try { size_t n = 0; double const v = std::stod(s, &n); if (n != s.size()) { throw 0; } return v; }
+  catch (...) { rt_err("can't convert '" + s + "' to double."); }
+  return 0;
+}
+}  // namespace
+
+vector<wis_op_t> read_wisdom_text(string const &text) {
+  vector<wis_op_t> ret;
+  line_reader_t in(text);
+  string line;
+  while (in.getline(line)) {
+    if (line != "op_wisdom_t") { rt_err("error reading line-oriented text stream. expected a line with 'op_wisdom_t', but saw '" + line + "'."); }
+    wis_op_t op;
+    op.op_text = in.must_getline();
+    make_p_op_base_t_from_str(op.op_text);  // must parse as an op (throws otherwise)
+    while (true) {
+      line = in.must_getline();
+      if (line == "/op_wisdom_t") { break; }
+      else if (line == "kg") { string const n = in.must_getline(); op.kgs.push_back({n, in.must_getline()}); }
+      else if (line == "op_tune_wisdom_t") {
+        wis_tune_t tune;
+        tune.tune_text = in.must_getline();
+        while (true) {
+          line = in.must_getline();
+          if (line == "/op_tune_wisdom_t") { break; }
+          else if (line == "op_run_t") {
+            wis_run_t r;
+            r.be_plat_tag = in.must_getline();
+            r.rt_secs = parse_secs(in.must_getline());
+            r.err = in.must_getline();
+            if (r.err.empty()) { r.op_text = in.must_getline(); }
+            for (auto const &o : tune.runs) { if (o.be_plat_tag == r.be_plat_tag) { rt_err("duplicate run for platform '" + r.be_plat_tag + "' in one op_tune_wisdom_t"); } }
+            tune.runs.push_back(r);
+          } else { rt_err("unknown op_tune_wisdom_t text format stream command read '" + line + "'"); }
+        }
+        op.tunes.push_back(tune);
+      } else { rt_err("unknown op_wisdom_t text format stream command read '" + line + "'"); }
+    }
+    ret.push_back(op);
+  }
+  return ret;
+}
+
+uint64_t op_text_flops(string const &op_text) {
+  p_op_base_t op = make_p_op_base_t_from_str(op_text);
+  if (op->has_type() && op->get_type() == "sgemm") {
+    dims_t const &a = op->get_dims("a"), &b = op->get_dims("b");
+    return 2ull * a.dsz("M") * b.dsz("N") * a.dsz("K");
+  }
+  dims_t const &dout = op->get_dims("out"), &din = op->get_dims("in"), &filts = op->get_dims("filts");
+  if (din.dsz("img") != dout.dsz("img")) { rt_err("op flops: in / out disagree in img"); }
+  uint64_t const M = (uint64_t)dout.dsz("img") * dout.dsz("x") * dout.dsz("y"), K = (uint64_t)filts.dsz("in_chan") * filts.dsz("x") * filts.dsz("y"), N = filts.dsz("out_chan");
+  return M * N * K * 2;
+}
+
+wis_ana_res_t wis_ana(vector<wis_op_t> const &ops_in, wis_ana_opts_t const &opts) {
+  std::regex const r_plat(opts.s_plat);
+  struct score_t { double tot_rt_secs = 0; uint32_t tot_num = 0; };
+  map<string, score_t> scores;
+  // select ops, drop runs with errors / of other platforms (filter_runs)
+  vector<wis_op_t> ops;
+  for (auto const &o : ops_in) {
+    p_op_base_t op = make_p_op_base_t_from_str(o.op_text);
+    if (opts.s_img && op->get_dims("in").dsz("img") != opts.s_img) { continue; }
+    if (!((double)op_text_flops(o.op_text) >= opts.min_flops)) { continue; }
+    for (auto const &p : ops) { if (p.op_text == o.op_text) { rt_err("wis-ana: duplicate op in wisdom input: " + o.op_text); } }
+    wis_op_t f = o;
+    for (auto &t : f.tunes) {
+      vector<wis_run_t> keep;
+      for (auto const &r : t.runs) { if (r.err.empty() && std::regex_search(r.be_plat_tag, r_plat)) { keep.push_back(r); } }
+      t.runs = keep;
+    }
+    ops.push_back(f);
+  }
+  std::sort(ops.begin(), ops.end(), [](wis_op_t const &a, wis_op_t const &b) { return a.op_text < b.op_text; });
+  wis_ana_res_t res;
+  double const nan = std::nan("");
+  for (auto const &o : ops) {
+    wis_ana_row_t row;
+    row.op_text = o.op_text; row.flops = op_text_flops(o.op_text); row.aom = row.pom = row.ref = nan;
+    double min_time = std::numeric_limits<double>::max();
+    bool have_ref = false;
+    for (auto const &t : o.tunes) {
+      for (auto const &r : t.runs) {
+        if (!opts.ref_tune.empty() && t.tune_text == opts.ref_tune) {
+          if (have_ref) { rt_err("wis-ana: more than one reference-tune run for an op (only one-platform filters are supported)"); }
+          have_ref = true; row.ref = r.rt_secs;
+        } else {
+          ++res.tot_runs;
+          score_t &s = scores[t.tune_text]; ++s.tot_num; s.tot_rt_secs += r.rt_secs;
+          if (r.rt_secs < min_time) { min_time = r.rt_secs; row.pom = r.rt_secs; row.pom_tune = t.tune_text; }
+        }
+      }
+    }
+    res.rows.push_back(row);
+  }
+  // best overall tune: most cases handled without error first, least total time second
+  score_t const *best = nullptr;
+  for (auto const &kv : scores) {
+    if (!best || kv.second.tot_num > best->tot_num || (kv.second.tot_num == best->tot_num && kv.second.tot_rt_secs < best->tot_rt_secs)) { best = &kv.second; res.aom_tune = kv.first; }
+  }
+  for (size_t i = 0; i < ops.size(); ++i) {
+    for (auto const &t : ops[i].tunes) { if (t.tune_text == res.aom_tune) { for (auto const &r : t.runs) { res.rows[i].aom = r.rt_secs; } } }
+  }
+  return res;
+}
+
+string wis_ana_csv(wis_ana_res_t const &res, wis_ana_opts_t const &opts) {
+  auto num = [](double v) { if (std::isnan(v)) { return string("nan"); } std::ostringstream o; o << v; return o.str(); };
+  string out = "OP FLOPS " + opts.aom_tag + " " + opts.pom_tag + " " + opts.ref_tag + "\n";
+  for (auto const &r : res.rows) { out += r.op_text + " " + str(r.flops) + " " + num(r.aom) + " " + num(r.pom) + " " + num(r.ref) + "\n"; }
+  return out;
 }
 
 }  // namespace boda

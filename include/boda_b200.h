@@ -84,6 +84,14 @@ int64_t b200_nda_digest_hex(const char *var_name, int ndims, const char *const *
                             char *buf, uint64_t buf_len);
 int64_t b200_wisdom_record(const char *op_text, int n_kgs, const char *const *kg_names, const char *const *kg_hex, const char *op_tune_text,
                            const char *be_plat_tag, double rt_secs, const char *err, const char *run_op_text, char *buf, uint64_t buf_len);
+/* The reference's wis-ana analysis (src/op-tuner.cc:204-396) over wisdom text in its own format (test/wisdom-merged.wis, or records written
+ * by b200_wisdom_record): runs with errors or of platforms not matching the regex s_plat are dropped, ops are filtered by batch size s_img
+ * (0 = all) and min_flops; per op it reports FLOPs, AOM (time of the single best overall tune), POM (per-op minimum over the non-reference
+ * tunes) and REF (time of the tune equal to ref_tune, "" = none). detail == 0: the csv wis-plot.py reads ("OP FLOPS boda-manual-tune
+ * boda-autotuned REF"); detail == 1: "#aom_tune\t<tune>\ttot_runs\t<n>" then tab-separated flops, aom, pom, ref, pom tune, op text per op.
+ * Host-only. Returns the text length or <0. */
+int64_t b200_wis_ana(const char *wisdom_text, uint32_t s_img, const char *s_plat, const char *ref_tune, double min_flops, int detail, char *buf,
+                     uint64_t buf_len);
 
 /* ---- tier B: has_conv_fwd_t ---- */
 /* has_conv_fwd_t::init(conv_pipe, nia)  src/has_conv_fwd.H:21 (conv_pipe_fwd_t::init, src/rtc_fwd.cc:469-527).
