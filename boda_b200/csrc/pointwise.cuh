@@ -702,14 +702,6 @@ absmax_kernel(float const *__restrict__ x, long long n, unsigned int *__restrict
     }
   }
 }
-__global__ void finalize_scale_kernel(unsigned int *__restrict__ bits, float *__restrict__ scale2, int use_scale) {
-  pdl_prologue();
-  float const s = use_scale ? scale_from_absmax_bits(*bits) : 1.0f;
-  scale2[0] = s;
-  scale2[1] = 1.0f / s;
-  *bits = 0u;
-}
-
 // HW == 1 activations (fc7 / fc8 inputs): NCHW [img][chan][1][1] already IS the K-major matrix [img][chan]; only scale + split.
 template <bool kBf16>
 __global__ void pack_rows_split_kernel(float const *__restrict__ src, uint16_t *__restrict__ hi, uint16_t *__restrict__ lo, float const *__restrict__ scale2,

@@ -18,7 +18,6 @@ CUDNN_TUNE = "(use_be=nvrtc,use_culibs=1,MNt=8 8,MNb=8 16,tconv_max_ksz=11 11)"
 
 
 def short_op(op_text):
-    d = bb.pipe_describe  # noqa: F841 (keeps the import obviously used for lib loading)
     import re
     g = lambda pat: re.search(pat, op_text)
     f = g(r"filts=\(dims=\(out_chan=(\d+),in_chan=(\d+),y=(\d+),x=(\d+)\)\)")
