@@ -90,3 +90,37 @@ def test_a_plan_cannot_compute(bb):
         bb.fwd_plan(txt, "(bogus=1)")
     with pytest.raises(bb.RtException):
         bb.fwd_plan(txt, "prec=bf16")  # not a (key=value,...) list
+
+
+RES_BLOCK = '''
+input: "data" input_dim: 2 input_dim: 16 input_dim: 12 input_dim: 12
+%s
+layer { name: "sum" type: "Eltwise" bottom: "short" bottom: "main" top: "sum" }
+layer { name: "sum_relu" type: "ReLU" bottom: "sum" top: "sum" }
+layer { name: "next" type: "Convolution" bottom: "sum" top: "next" convolution_param { num_output: 24 kernel_size: 3 pad: 1 } }
+'''
+SHORT = 'layer { name: "short" type: "Convolution" bottom: "data" top: "short" convolution_param { num_output: 32 kernel_size: 1 } }\n'
+MAIN = ('layer { name: "main" type: "Convolution" bottom: "data" top: "main" convolution_param { num_output: 32 kernel_size: 3 pad: 1 bias_term: false } }\n'
+        'layer { name: "bn" type: "BatchNorm" bottom: "main" top: "main" batch_norm_param { use_global_stats: true } }\n'
+        'layer { name: "sc" type: "Scale" bottom: "main" top: "main" scale_param { bias_term: true } }\n')
+
+
+def test_join_rules_on_a_prototxt_block(bb):
+    """From a Caffe prototxt (f1) to the plan (f4): the join goes into the convolution that runs LAST; a branch with other readers, or with
+    a ReLU of its own in front of the join, keeps the separate reduce kernel."""
+    def plan_of(layers, opts=""):
+        return bb.fwd_plan(bb.pipe_from_prototxt(RES_BLOCK % layers), opts)
+    p = plan_of(SHORT + MAIN)
+    assert p["join"] == {"main": ("sum", "short")} and "reduce" not in _kinds(p)
+    call = dict(next(a for f, a in p["calls"] if f.startswith("conv__main__")))
+    assert call["out"] == "sum" and call["res"] == "short" and call["filts"] == "main_filts__folded" and "out_pack" in call
+    assert "short" in p["absmax"] and [f for f, _ in p["prep"]] == ["bn_fold__main"]
+    # the shortcut produced after the main branch: the join moves into the shortcut's convolution instead
+    assert plan_of(MAIN + SHORT)["join"] == {"short": ("sum", "main")}
+    # a second reader of the would-be bypassed node, or a ReLU on it, forbids the fusion on that side ...
+    two_readers = plan_of(SHORT + MAIN.replace('name: "sc"', 'name: "sc"') + 'layer { name: "p" type: "Pooling" bottom: "main" top: "p" pooling_param { pool: MAX kernel_size: 2 stride: 2 } }\n')
+    assert two_readers["join"] == {} and _kinds(two_readers)["reduce"] == 1
+    relu_first = plan_of(SHORT + MAIN + 'layer { name: "mr" type: "ReLU" bottom: "main" top: "main" }\n')
+    assert relu_first["join"] == {} and _kinds(relu_first)["reduce"] == 1
+    # ... and the option turns it off altogether
+    assert plan_of(SHORT + MAIN, "(fuse_eltwise=0)")["join"] == {}
