@@ -544,40 +544,64 @@ pool_plane_pipe_kernel(float const *__restrict__ in, float *__restrict__ out, in
 // one CHUNK of kChunk output channels: it rebuilds the window sum at the chunk start (ascending-order FMAs, exactly the
 // reference's sequence for chunk 0) and then runs the reference's running update inside the chunk. Consecutive threads are
 // consecutive x, so every channel step reads/writes coalesced 128-byte rows. kLS = local_size (ring buffer in registers).
-template <int kLS, int kChunk>
-__global__ void __launch_bounds__(128)
-lrn_kernel(float const *__restrict__ in, float *__restrict__ out, long long n_pels, int C, int HW, float alpha, float beta, float k,
-           unsigned int *out_absmax) {
-  pdl_prologue();
-  long long const pel = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  bool const valid = pel < n_pels;
-  long long const img = valid ? pel / HW : 0;
-  long long const base = img * C * HW + (valid ? (pel - img * HW) : 0);
+// x^(-beta) for the LRN scale: exp2(-beta * log2(x)), the same two approximations and the same product as __powf (the reference compiles
+// lrn.cucl with --use_fast_math, src/nvrtc_util.cc:251), in their flush-to-zero forms: __powf's non-ftz expansion wraps both in subnormal
+// range fix-ups (8 instructions, 2 predicates) that a scale base >= k can never need. Identical bits for normal-range arguments.
+__device__ __forceinline__ float lrn_pow_neg(float x, float neg_beta) {
+  float l, e;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(l * neg_beta));
+  return e;
+}
+
+// One pixel, one chunk of kChunk output channels. kInterior: the chunk and its window halo lie inside [0, C) -- no channel bounds tests.
+template <int kLS, int kChunk, bool kInterior>
+__device__ __forceinline__ float lrn_chunk(float const *__restrict__ in, float *__restrict__ out, long long base, int c_begin, int C, int HW, float alpha_over_ls,
+                                           float neg_beta, float k) {
   constexpr int hls = kLS >> 1;
   constexpr int kTot = kChunk + 2 * hls;  // input channels c_begin-hls .. c_begin+kChunk-1+hls
-  int const c_begin = blockIdx.y * kChunk;
-  float const alpha_over_ls = alpha / (float)kLS;
   float v[kTot];
+  float const *ip = in + base + static_cast<long long>(c_begin - hls) * HW;
 #pragma unroll
   for (int s = 0; s < kTot; ++s) {  // all loads first: kTot independent requests in flight per thread
     int const ic = c_begin - hls + s;
-    v[s] = (valid && ic >= 0 && ic < C) ? __ldg(in + base + static_cast<long long>(ic) * HW) : 0.0f;
+    v[s] = (kInterior || (ic >= 0 && ic < C)) ? __ldg(ip + static_cast<long long>(s) * HW) : 0.0f;
   }
+  float *op = out + base + static_cast<long long>(c_begin) * HW;
   float ls_sum = 0.0f, amax = 0.0f;
 #pragma unroll
   for (int s = 0; s < kTot; ++s) {  // the reference's running update: add the newest square, subtract the one leaving the window
     ls_sum = __fmaf_rn(v[s], v[s], ls_sum);
     if (s >= kLS) { ls_sum = __fmaf_rn(-v[s - kLS], v[s - kLS], ls_sum); }
     if (s >= 2 * hls) {
-      int const oc = c_begin + s - 2 * hls;
-      if (valid && oc < C) {
+      int const j = s - 2 * hls;  // output channel c_begin + j
+      if (kInterior || c_begin + j < C) {
         float const scale_base = __fmaf_rn(ls_sum, alpha_over_ls, k);
-        float const scale = __powf(scale_base, -beta);  // the reference compiles lrn.cucl with --use_fast_math (src/nvrtc_util.cc:251)
-        float const ov = v[s - hls] * scale;
-        out[base + static_cast<long long>(oc) * HW] = ov;
+        float const ov = v[s - hls] * lrn_pow_neg(scale_base, neg_beta);
+        op[static_cast<long long>(j) * HW] = ov;
         amax = fmaxf(amax, fabsf(ov));
       }
     }
+  }
+  return amax;
+}
+
+template <int kLS, int kChunk>
+__global__ void __launch_bounds__(128)
+lrn_kernel(float const *__restrict__ in, float *__restrict__ out, long long n_pels, int C, int HW, float alpha, float beta, float k,
+           unsigned int *out_absmax) {
+  pdl_prologue();
+  long long const pel = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  constexpr int hls = kLS >> 1;
+  int const c_begin = blockIdx.y * kChunk;
+  float amax = 0.0f;
+  if (pel < n_pels) {
+    long long const img = pel / HW;
+    long long const base = img * C * HW + (pel - img * HW);
+    float const alpha_over_ls = alpha / (float)kLS;
+    // (measured before this split: 67 SASS instructions per output, most of them channel-bounds predicates and __powf's subnormal fix-ups)
+    if (c_begin - hls >= 0 && c_begin + kChunk + hls <= C) { amax = lrn_chunk<kLS, kChunk, true>(in, out, base, c_begin, C, HW, alpha_over_ls, -beta, k); }
+    else { amax = lrn_chunk<kLS, kChunk, false>(in, out, base, c_begin, C, HW, alpha_over_ls, -beta, k); }
   }
   if (out_absmax) { publish_absmax_warp(amax, out_absmax); }
 }
