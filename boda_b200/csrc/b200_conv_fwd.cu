@@ -415,7 +415,7 @@ void b200_conv_fwd_t::init(p_conv_pipe_t const &cp_, string const &opts) {
         else if (k == "acc_chunk_kblks") { rtc->acc_chunk_kblks = std::stoi(v); }
         else if (k == "acc_chunk_kblks_16") { rtc->acc_chunk_kblks_16 = std::stoi(v); }
         else if (k == "use_taps") { rtc->use_taps = std::stoi(v); }
-    else if (k == "use_pdl") { rtc->use_pdl = std::stoi(v); }
+        else if (k == "use_pdl") { rtc->use_pdl = std::stoi(v); }
         else if (k == "taps_2cta") { rtc->taps_2cta = std::stoi(v); }
         else if (k == "use_clusters") { rtc->use_clusters = std::stoi(v); }
         else if (k == "use_2cta") { rtc->use_2cta = std::stoi(v); }
