@@ -181,7 +181,7 @@ def fwd_plan(pipe_text: str, opts: str = "") -> Dict[str, object]:
     for line in buf.value.decode().splitlines():
         parts = line.split(" ")
         if parts[0] in ("call", "prep"):
-            res["calls" if parts[0] == "call" else "prep"].append((parts[1], dict(p.split("=", 1) for p in parts[2:])))
+            res["calls" if parts[0] == "call" else "prep"].append((parts[1], dict(p.split("=", 1) for p in parts[2:])))  # incl. "plan:<key>" items
         elif parts[0] == "alias":
             res["alias"][parts[1]] = (parts[2], int(parts[3]))
         elif parts[0] == "join":

@@ -465,6 +465,21 @@ void b200_compute_t::compile(vect_rtc_func_info_t const &func_infos, rtc_compile
     impl->funcs[fi.func_name] = f;
   }
 }
+string b200_compute_t::func_plan_text(string const &fn) const {
+  auto fi = impl->funcs.find(fn);
+  if (fi == impl->funcs.end()) { rt_err("func_plan_text: function '" + fn + "' was not compiled"); }
+  if (fi->second.kind != FK_CONV) { return string(); }
+  conv_plan_t const &cp = fi->second.cp;
+  long long const pixels = (long long)cp.N * cp.OH * cp.OW;
+  int const p_rows_n = cp.swapped ? cp.OC : (int)pixels, q_rows_n = cp.swapped ? (int)pixels : cp.OC;
+  int const p_tiles = ceil_div(p_rows_n, b200::IGEMM_BM), q_tiles = ceil_div(q_rows_n, cp.BN);
+  bool const two_cta = use_2cta && !cp.swapped && cp.splits == 1 && p_tiles >= 2;  // the rule of run_conv
+  string grid;
+  if (two_cta) { grid = str(2 * std::min(ceil_div(p_tiles, 2) * q_tiles, impl->num_sms / 2)) + "x1x1"; }
+  else { grid = str(p_tiles) + "x" + str(q_tiles) + "x" + str(cp.splits); }
+  return string("kernel=") + (two_cta ? "pair" : "single") + " bn=" + str(cp.BN) + " kblks=" + str(cp.kblks_total) + " splits=" + str(cp.splits) + " swapped=" + str((int)cp.swapped) +
+         " rowmerge=" + str((int)cp.rowmerge) + " im2col=" + str((int)cp.im2col) + " grid=" + grid;
+}
 bool b200_compute_t::conv_plane_writable(op_base_t const &op, bool dst_is_concat) {
   conv_plan_t cp;
   plan_conv(cp, op, impl->num_sms);

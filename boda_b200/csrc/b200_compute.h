@@ -115,6 +115,10 @@ struct b200_compute_t {
   bool conv_res_fusable(op_base_t const &op);
   bool has_var(string const &vn) const;
   bool has_func(string const &fn) const;
+  // host-only: the launch plan compile() made for a convolution function, as "kernel=pair|single bn=<N tile> kblks=<64-wide k-blocks>
+  // splits=<split-K> swapped=0|1 rowmerge=0|1 im2col=0|1 grid=<x>x<y>x<z>" ("" for other function kinds). pair = the persistent CTA-pair
+  // kernel (igemm2.cuh), single = one CTA per tile (igemm.cuh). What run() launches, without launching it.
+  string func_plan_text(string const &fn) const;
   void copy_raw_to_var(string const &vn, void const *src, uint64_t bytes);   // host -> device (async on the stream, then sync)
   void copy_var_to_raw(void *dst, string const &vn, uint64_t bytes);
   void copy_raw_to_var_async(string const &vn, void const *src, uint64_t bytes);

@@ -529,6 +529,9 @@ string b200_conv_fwd_t::plan_text() const {
       out += " " + kv.first + "=";
       if (kv.second.is_var()) { out += kv.second.get_var(); } else { out += str((uint64_t)nda_scalar_as_double(*kv.second.get_nda())); }
     }
+    string const lp = rtc->func_plan_text(c.func_name);  // convolutions: the launch plan, as "plan:<key>=<value>" items
+    size_t b = 0;
+    while (b < lp.size()) { size_t e = lp.find(' ', b); if (e == string::npos) { e = lp.size(); } out += " plan:" + lp.substr(b, e - b); b = e + 1; }
     out += "\n";
   };
   for (auto const &c : prep_calls) { put_call("prep", c); }

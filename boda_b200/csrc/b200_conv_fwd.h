@@ -86,7 +86,8 @@ struct b200_conv_fwd_t {
   void flush_l2(uint64_t bytes);
   uint64_t launches() const { return rtc->launches() + graph_launches; }
   // The forward as planned at init, one line per item, for inspection and host-only tests (also on a plan_only=1 instance, which needs no
-  // device):  "call <func_name> <arg>=<var or by-value scalar> ..." in launch order, "prep <func_name>" (parameter-only calls),
+  // device):  "call <func_name> <arg>=<var or by-value scalar> ... [plan:<key>=<value> ...]" in launch order (convolutions carry their launch plan,
+  // b200_compute_t::func_plan_text), "prep <func_name>" (parameter-only calls),
   // "alias <node> <concat node> <channel offset>", "join <conv tag> <join node> <residual node>", "absmax <node> <cell>".
   string plan_text() const;
 

@@ -67,7 +67,8 @@ int64_t b200_pipe_describe(const char *pipe_text, char *buf, uint64_t buf_len);
 
 /* Host-only: the forward as b200_fwd_create would plan it for this pipe and these options -- graph passes (concat by offset, residual joins
  * in the convolution, producer-written planes, abs-max cells) and the launch plan of every convolution for a 148-SM device -- without touching
- * a device ("plan_only=1" instance: it cannot compute). Text, one item per line: "call <func> <arg>=<var|scalar> ...", "prep <func> ...",
+ * a device ("plan_only=1" instance: it cannot compute). Text, one item per line: "call <func> <arg>=<var|scalar> ... plan:<key>=<value> ..."
+ * (convolutions carry their launch plan: kernel=pair|single, bn, kblks, splits, swapped, rowmerge, im2col, grid), "prep <func> ...",
  * "alias <node> <concat node> <chan offset>", "join <conv tag> <join node> <residual node>", "absmax <node> <cell>".
  * Returns the text length (the buffer gets at most buf_len-1 chars) or <0. */
 int64_t b200_fwd_plan(const char *pipe_text, const char *opts, char *buf, uint64_t buf_len);

@@ -124,3 +124,23 @@ def test_join_rules_on_a_prototxt_block(bb):
     assert relu_first["join"] == {} and _kinds(relu_first)["reduce"] == 1
     # ... and the option turns it off altogether
     assert plan_of(SHORT + MAIN, "(fuse_eltwise=0)")["join"] == {}
+
+
+def test_alexnet_launch_plans_match_the_measured_launch_list(bb):
+    """The per-layer launch plans (tile width from the wave-aware cost model, CTA pairs vs single CTAs, swapped + split-K for the inner-product
+    layers) equal what ncu saw on the B200: profiles/launches_r01_final_ncu_graph_nodes.md -- igemm_umma_2cta_kernel<96|128, 2> with grids
+    148 / 148 / 132 / 132 / 132 for conv1..conv5, igemm_umma_kernel<32, 2> with grids (32,1,4), (32,1,4), (8,1,8) for fc6..fc8."""
+    from boda_b200 import nets
+    txt, i, o = nets.alexnet_ng_conv(32)
+    plan = bb.fwd_plan(txt, "")
+    got = [(f.split("__")[1], {k[5:]: v for k, v in a.items() if k.startswith("plan:")}) for f, a in plan["calls"] if f.startswith("conv__")]
+    want = [("conv1", "pair", 96, "148x1x1", 11), ("conv2", "pair", 128, "148x1x1", 50), ("conv3", "pair", 128, "132x1x1", 36), ("conv4", "pair", 128, "132x1x1", 54),
+            ("conv5", "pair", 96, "132x1x1", 54), ("fc6-conv", "single", 32, "32x1x4", 144), ("fc7-conv", "single", 32, "32x1x4", 64), ("fc8-conv", "single", 32, "8x1x8", 64)]
+    assert [(t, p["kernel"], int(p["bn"]), p["grid"], int(p["kblks"])) for t, p in got] == want
+    assert [int(p["swapped"]) for _, p in got] == [0, 0, 0, 0, 0, 1, 1, 1] and [int(p["rowmerge"]) for _, p in got] == [1, 0, 0, 0, 0, 0, 0, 0]
+    # a smaller chip (plan_num_sms) re-plans: fewer SM pairs -> fewer persistent clusters
+    small = bb.fwd_plan(txt, "(plan_num_sms=64)")
+    g = dict(next(a for f, a in small["calls"] if f.startswith("conv__conv2__")))
+    assert g["plan:grid"] == "64x1x1"
+    # pooling / LRN calls carry no launch plan
+    assert not any(k.startswith("plan:") for f, a in plan["calls"] if not f.startswith("conv__") for k in a)
