@@ -132,9 +132,10 @@ def run_reference_arm(args, rank, world):
     val = sample * args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "nets/alexnet_ng_conv fwd, batch=32 per GPU, fp32, 227x227 (BASELINE configs[1])", "parallelism": "host cores only"},
+            "config": {"workload": "nets/%s fwd, batch=%d per GPU, fp32, %dx%d%s" % (NET_NAME, PER_GPU_BATCH, NET_IN_SZ, NET_IN_SZ, " (BASELINE configs[1])" if NET_NAME == "alexnet_ng_conv" else ""),
+                       "parallelism": "host cores only"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "each step = AlexNet-ng forward of %d images (a bounded sample of the 32-image batch) through the oracle port, OpenMP on all host cores; Boda's own binary / Caffe CPU path is not buildable here" % sample},
+                             "sample": "each step = %s forward of %d images (a bounded sample of the %d-image batch) through the oracle port, OpenMP on all host cores; Boda's own binary / Caffe CPU path is not buildable here" % (NET_NAME, sample, PER_GPU_BATCH)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     _emit(line)
 
