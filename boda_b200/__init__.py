@@ -62,6 +62,7 @@ _SIGS = {
                                         _c.c_char_p, _c.c_char_p, _c.c_uint64]),
     "b200_pipe_from_prototxt": (_c.c_int64, [_c.c_char_p, _c.c_char_p, _c.c_char_p, _c.c_uint64]),
     "b200_fwd_plan": (_c.c_int64, [_c.c_char_p, _c.c_char_p, _c.c_char_p, _c.c_uint64]),
+    "b200_pipe_op_sigs": (_c.c_int64, [_c.c_char_p, _c.c_char_p, _c.c_uint64]),
     "b200_wis_ana": (_c.c_int64, [_c.c_char_p, _c.c_uint32, _c.c_char_p, _c.c_char_p, _c.c_double, _c.c_int, _c.c_char_p, _c.c_uint64]),
     "b200_fwd_create": (_c.c_void_p, [_c.c_char_p, _c.c_char_p]),
     "b200_fwd_destroy": (None, [_c.c_void_p]),
@@ -168,6 +169,14 @@ def pipe_describe(pipe_text: str) -> Dict[str, object]:
             params.append(parts[0])
     res["nodes"], res["params"] = nodes, params
     return res
+
+
+def pipe_op_sigs(pipe_text: str) -> List[str]:
+    """Host-only: the unique Convolution signatures of a pipe as canonical op lines (the reference's write_op_sigs, src/rtc_fwd.cc:246-264)."""
+    need = _chk(lib().b200_pipe_op_sigs(_b(pipe_text), None, 0))
+    buf = ctypes.create_string_buffer(need + 1)
+    _chk(lib().b200_pipe_op_sigs(_b(pipe_text), buf, need + 1))
+    return buf.value.decode().splitlines()
 
 
 def fwd_plan(pipe_text: str, opts: str = "") -> Dict[str, object]:

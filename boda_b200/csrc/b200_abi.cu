@@ -139,6 +139,17 @@ B200_API int64_t b200_pipe_describe(const char *pipe_text, char *buf, uint64_t b
   return rc == 0 ? need : rc;
 }
 
+B200_API int64_t b200_pipe_op_sigs(const char *pipe_text, char *buf, uint64_t buf_len) {
+  int64_t need = -1;
+  int const rc = guarded([&] {
+    string const out = conv_pipe_op_sigs_text(*make_conv_pipe_from_text(pipe_text));
+    need = (int64_t)out.size();
+    if (buf && buf_len) { snprintf(buf, buf_len, "%s", out.c_str()); }
+    return 0;
+  });
+  return rc == 0 ? need : rc;
+}
+
 B200_API int64_t b200_fwd_plan(const char *pipe_text, const char *opts, char *buf, uint64_t buf_len) {
   int64_t need = -1;
   int const rc = guarded([&] {

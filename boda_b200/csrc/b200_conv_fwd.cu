@@ -2,6 +2,7 @@
 // (src/rtc_fwd.cc:469-527, :436-465, :263-405); every node is an fp32 NCHW var as in the reference, so
 // test_compute-style per-node comparison works on any node (src/test_compute.cc:165-169).
 #include "b200_conv_fwd.h"
+#include <set>
 #include <algorithm>
 
 namespace boda {
@@ -168,6 +169,26 @@ b200_conv_fwd_t::~b200_conv_fwd_t() {
   if (flush_buf) { cudaFree(flush_buf); }
   if (graph_exec) { cudaGraphExecDestroy(graph_exec); }
   if (graph) { cudaGraphDestroy(graph); }
+}
+
+string conv_pipe_op_sigs_text(conv_pipe_t const &cp) {
+  std::set<string> sigs;
+  for (auto const &op : cp.ops) {
+    if (!op->is("Convolution") || op->has("is_inner_product")) { continue; }
+    op_base_t sig;
+    sig.str_vals = op->str_vals;
+    sig.nda_vals = op->nda_vals;
+    dims_t const &fd = cp.must_get_node(op->bots[1])->dims;
+    for (char const *an : {"in", "filts", "biases", "out"}) { if (sig.has(an)) { sig.erase(an); } }
+    sig.set_dims("in", cp.must_get_node(op->bots[0])->dims);
+    sig.set_dims("filts", fd);
+    if (op->bots.size() > 2) { sig.set_dims("biases", dims_t({fd.dsz("out_chan")}, {"out_chan"}, "float")); }
+    sig.set_dims("out", cp.must_get_node(op->tops[0])->dims);
+    sigs.insert(op_base_text(sig));
+  }
+  string out;
+  for (auto const &l : sigs) { out += l + "\n"; }
+  return out;
 }
 
 void b200_conv_fwd_t::add_call(string const &fn_base, conv_op_t const &op, op_base_t const &fop, map_str_rtc_arg_t const &args) {

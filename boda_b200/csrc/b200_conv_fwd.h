@@ -37,6 +37,11 @@ struct conv_pipe_t {  // src/conv_util.H:172-243
 typedef shared_ptr<conv_pipe_t> p_conv_pipe_t;
 p_conv_pipe_t make_conv_pipe_from_text(string const &pipe_text);
 
+// The unique Convolution signatures of a pipe -- op parameters plus the dims of in / filts / biases / out, without tags -- one canonical op
+// line per signature, sorted: what the reference's write_op_sigs option collects (src/rtc_fwd.cc:246-264) and its per-op flows read back
+// (test/conv-ops-*.txt). Host-only.
+string conv_pipe_op_sigs_text(conv_pipe_t const &cp);
+
 struct fwd_call_t { string func_name, tag; rtc_func_call_t rfc; };
 
 struct b200_conv_fwd_t {

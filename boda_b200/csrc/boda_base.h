@@ -320,6 +320,46 @@ inline void fill_op_base_from_lexp(op_base_t &op, lexp_t const &l, std::set<stri
     }
   }
 }
+// canonical text of an nda / op (the form the reference prints and its op-list files hold: src/boda_base.cc:392-420 for ndas -- tn omitted
+// when it is float and dims are given, dims omitted for scalars, values ':'-separated -- inside NESI's "(str_vals=(..),nda_vals=(..))")
+inline string nda_text(nda_t const &o) {
+  std::ostringstream out;
+  out << "(";
+  bool const show_dims = !o.dims.empty();
+  bool const show_tn = !show_dims || o.dims.tn != "float";
+  if (show_tn) { out << "tn=" << o.dims.tn; }
+  if (show_dims) {
+    if (show_tn) { out << ","; }
+    out << "dims=(";
+    for (size_t i = 0; i < o.dims.size(); ++i) { out << (i ? "," : "") << o.dims[i].name << "=" << o.dims[i].sz; }
+    out << ")";
+  }
+  if (o.has_data()) {
+    out << ",v=";
+    string const &tn = o.dims.tn;
+    void *p = o.rp_elems();
+    for (uint64_t i = 0; i < o.elems_sz(); ++i) {
+      if (i) { out << ":"; }
+      if (tn == "float") { out << static_cast<float *>(p)[i]; }
+      else if (tn == "double") { out << static_cast<double *>(p)[i]; }
+      else if (tn == "uint32_t") { out << static_cast<uint32_t *>(p)[i]; }
+      else if (tn == "int32_t") { out << static_cast<int32_t *>(p)[i]; }
+      else if (tn == "uint64_t") { out << static_cast<uint64_t *>(p)[i]; }
+      else { rt_err("nda_text: unhandled type " + tn); }
+    }
+  }
+  out << ")";
+  return out.str();
+}
+inline string op_base_text(op_base_t const &op) {
+  string out = "(str_vals=(";
+  bool first = true;
+  for (auto const &kv : op.str_vals) { out += (first ? "" : ",") + kv.first + "=" + kv.second; first = false; }
+  out += "),nda_vals=(";
+  first = true;
+  for (auto const &kv : op.nda_vals) { out += (first ? "" : ",") + kv.first + "=" + nda_text(*kv.second); first = false; }
+  return out + "))";
+}
 inline p_op_base_t make_p_op_base_t_from_str(string const &line) {
   p_op_base_t op = std::make_shared<op_base_t>();
   fill_op_base_from_lexp(*op, *parse_lexp(line));

@@ -65,6 +65,10 @@ uint64_t b200_rtc_launches(b200_rtc *r);           /* kernels launched so far by
  * truncated to buf_len). Returns the full length needed (excluding the NUL), or <0 on a malformed pipe (see b200_last_error). */
 int64_t b200_pipe_describe(const char *pipe_text, char *buf, uint64_t buf_len);
 
+/* Host-only: the unique Convolution signatures of a pipe (op parameters + dims of in / filts / biases / out, no tags), one canonical op line
+ * each, sorted -- what the reference's write_op_sigs option collects (src/rtc_fwd.cc:246-264) and what its per-op test files hold
+ * (test/conv-ops-*.txt); feed them to b200_rtc_compile / tools/ops_prof.py. Returns the text length or <0. */
+int64_t b200_pipe_op_sigs(const char *pipe_text, char *buf, uint64_t buf_len);
 /* Host-only: the forward as b200_fwd_create would plan it for this pipe and these options -- graph passes (concat by offset, residual joins
  * in the convolution, producer-written planes, abs-max cells) and the launch plan of every convolution for a 148-SM device -- without touching
  * a device ("plan_only=1" instance: it cannot compute). Text, one item per line: "call <func> <arg>=<var|scalar> ... plan:<key>=<value> ..."

@@ -91,3 +91,30 @@ def test_cpp_pipe_errors(bb):
         bb.pipe_describe("(node=data,dims=(img=1,chan=3,y=8,x=8))\n(tag=bn,str_vals=(type=BatchNorm),bots=data,tops=other)\n")
     with pytest.raises(bb.RtException):
         bb.pipe_describe("(node=data,dims=(img=1,chan=3,y=8,x=8))\n(tag=c,str_vals=(type=Convolution),nda_vals=(out_chans=(tn=uint32_t,v=4)),bots=data,tops=c)\n")  # no kern_sz
+
+
+def test_pipe_op_signatures_equal_the_reference_op_list(bb):
+    """write_op_sigs restated (src/rtc_fwd.cc:246-264): the unique Convolution signatures of AlexNet-ng, NiN (native 224 crop) and GoogLeNet at
+    batch 1 / 5 / 20, printed by the C++ pipe IR's canonical op printer, are TEXT-IDENTICAL to the 204 ops of the reference's
+    conv-ops-1-5-20-nin-alex-gn list (taken from its committed test/good_tr/conv-full-gen5/wisdom.wis) -- which pins the three net
+    descriptions, the dims inference and the op-line printer against the reference's own output."""
+    import json
+    from boda_b200 import nets
+    gold = {}
+    for e in json.load(open(os.path.join(ROOT, "tests", "golden", "wisdom_digests.json")))["tests"]["conv-full-gen5"]:
+        gold.setdefault(int(e["op"].split("in=(dims=(img=")[1].split(",")[0]), set()).add(e["op"])
+    assert sorted(gold) == [1, 5, 20] and all(len(v) == 68 for v in gold.values())
+    for B in (1, 5, 20):
+        mine = set()
+        for txt in (nets.alexnet_ng_conv(B)[0], nets.nin_imagenet(B, in_sz=224)[0], nets.googlenet_conv(B)[0]):
+            sigs = bb.pipe_op_sigs(txt)
+            assert sigs == sorted(set(sigs))  # unique, sorted
+            mine |= set(sigs)
+        assert mine == gold[B], (B, sorted(mine ^ gold[B])[:2])
+    # the per-op sweep file of BASELINE config C2 is exactly AlexNet-ng's signature set at batch 32
+    c2 = [l.strip() for l in open(os.path.join(ROOT, "ops", "c2-alexnet-ng-b32-convs.txt")) if l.strip()]
+    assert set(c2) == set(bb.pipe_op_sigs(nets.alexnet_ng_conv(32)[0])) and len(c2) == 8
+    # every signature is a valid op line for the per-op tier (round trip through the op parser of b200_wis_ana's reader)
+    one = sorted(gold[20])[0]
+    rec = bb.wisdom_record(one, [], "(use_be=b200)", "b200:x", 1e-3)
+    assert bb.wis_ana(rec, s_plat="b200:")["rows"][0]["op"] == one
