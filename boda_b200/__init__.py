@@ -63,6 +63,7 @@ _SIGS = {
     "b200_pipe_from_prototxt": (_c.c_int64, [_c.c_char_p, _c.c_char_p, _c.c_char_p, _c.c_uint64]),
     "b200_fwd_plan": (_c.c_int64, [_c.c_char_p, _c.c_char_p, _c.c_char_p, _c.c_uint64]),
     "b200_pipe_op_sigs": (_c.c_int64, [_c.c_char_p, _c.c_char_p, _c.c_uint64]),
+    "b200_op_canonical": (_c.c_int64, [_c.c_char_p, _c.c_char_p, _c.c_uint64]),
     "b200_wis_ana": (_c.c_int64, [_c.c_char_p, _c.c_uint32, _c.c_char_p, _c.c_char_p, _c.c_double, _c.c_int, _c.c_char_p, _c.c_uint64]),
     "b200_fwd_create": (_c.c_void_p, [_c.c_char_p, _c.c_char_p]),
     "b200_fwd_destroy": (None, [_c.c_void_p]),
@@ -169,6 +170,14 @@ def pipe_describe(pipe_text: str) -> Dict[str, object]:
             params.append(parts[0])
     res["nodes"], res["params"] = nodes, params
     return res
+
+
+def op_canonical(op_text: str) -> str:
+    """Host-only: an op line in the current or the stale op-list syntax -> the canonical current-syntax line (the reference's printer)."""
+    need = _chk(lib().b200_op_canonical(_b(op_text), None, 0))
+    buf = ctypes.create_string_buffer(need + 1)
+    _chk(lib().b200_op_canonical(_b(op_text), buf, need + 1))
+    return buf.value.decode()
 
 
 def pipe_op_sigs(pipe_text: str) -> List[str]:

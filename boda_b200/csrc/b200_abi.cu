@@ -139,6 +139,17 @@ B200_API int64_t b200_pipe_describe(const char *pipe_text, char *buf, uint64_t b
   return rc == 0 ? need : rc;
 }
 
+B200_API int64_t b200_op_canonical(const char *op_text, char *buf, uint64_t buf_len) {
+  int64_t need = -1;
+  int const rc = guarded([&] {
+    string const out = op_base_text(*make_p_op_base_t_from_str(op_text));
+    need = (int64_t)out.size();
+    if (buf && buf_len) { snprintf(buf, buf_len, "%s", out.c_str()); }
+    return 0;
+  });
+  return rc == 0 ? need : rc;
+}
+
 B200_API int64_t b200_pipe_op_sigs(const char *pipe_text, char *buf, uint64_t buf_len) {
   int64_t need = -1;
   int const rc = guarded([&] {

@@ -65,6 +65,10 @@ uint64_t b200_rtc_launches(b200_rtc *r);           /* kernels launched so far by
  * truncated to buf_len). Returns the full length needed (excluding the NUL), or <0 on a malformed pipe (see b200_last_error). */
 int64_t b200_pipe_describe(const char *pipe_text, char *buf, uint64_t buf_len);
 
+/* Host-only: an op line in either syntax of the reference's op-list files (current "(str_vals=(type=..),nda_vals=(..))" or the stale
+ * "(type=..,dims_vals=(..),str_vals=(out_chans=N))") -> its canonical current-syntax line (the reference's printer:
+ * src/boda_base.cc:392-420 inside NESI's struct dump). Returns the text length or <0. */
+int64_t b200_op_canonical(const char *op_text, char *buf, uint64_t buf_len);
 /* Host-only: the unique Convolution signatures of a pipe (op parameters + dims of in / filts / biases / out, no tags), one canonical op line
  * each, sorted -- what the reference's write_op_sigs option collects (src/rtc_fwd.cc:246-264) and what its per-op test files hold
  * (test/conv-ops-*.txt); feed them to b200_rtc_compile / tools/ops_prof.py. Returns the text length or <0. */

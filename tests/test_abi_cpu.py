@@ -118,3 +118,28 @@ def test_pipe_op_signatures_equal_the_reference_op_list(bb):
     one = sorted(gold[20])[0]
     rec = bb.wisdom_record(one, [], "(use_be=b200)", "b200:x", 1e-3)
     assert bb.wis_ana(rec, s_plat="b200:")["rows"][0]["op"] == one
+
+
+def test_stale_op_syntax_canonicalises_to_the_current_one(bb):
+    """The reference's older op lists (test/conv-ops-small.txt, test/sgemm-ops-tiny.txt) use the stale `type/dims_vals` syntax (SURVEY Appendix
+    A). The C++ op parser + canonical printer turn them into the current-syntax lines its newer lists and wisdom files hold."""
+    import json
+    stale = ["(type=Convolution,dims_vals=(biases=(out_chan=96),filts=(out_chan=96,in_chan=3,y=11,x=11),in=(img=20,chan=3,y=227,x=227),in_pad=(y=0,x=0),"
+             "kern_sz=(y=11,x=11),out=(img=20,chan=96,y=55,x=55),stride=(y=4,x=4)),str_vals=(out_chans=96))",
+             "(type=Convolution,dims_vals=(biases=(out_chan=1024),filts=(out_chan=1024,in_chan=384,y=3,x=3),in=(img=20,chan=384,y=6,x=6),in_pad=(y=1,x=1),"
+             "kern_sz=(y=3,x=3),out=(img=20,chan=1024,y=6,x=6),stride=(y=1,x=1)),str_vals=(out_chans=1024))",
+             "(type=sgemm,dims_vals=(a=(K=2048,M=2048),b=(K=2048,N=2048),c=(M=2048,N=2048)))"]
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "wisdom_digests.json")))["tests"]
+    known = set(e["op"] for e in g["conv-full-gen5"]) | set(e["op"] for e in g["sgemm-gen5"])
+    for l in stale:
+        c = bb.op_canonical(l)
+        assert c in known and bb.op_canonical(c) == c  # the reference's own text for this op; canonical lines are fixed points
+    for fn in ("c1-sgemm-ops-tiny.txt", "c2-alexnet-ng-b32-convs.txt", "c3-conv-ops-small.txt"):
+        for l in open(os.path.join(ROOT, "ops", fn)):
+            if l.strip():
+                assert bb.op_canonical(l.strip()) == l.strip()
+    # scalar / float / typed-dims ndas print in the reference's minimal form
+    assert bb.op_canonical("(str_vals=(type=LRN),nda_vals=(alpha=(tn=float,v=0.0001),local_size=(tn=uint32_t,v=5),in=(tn=float,dims=(img=2,chan=3))))") == \
+        "(str_vals=(type=LRN),nda_vals=(alpha=(tn=float,v=0.0001),in=(dims=(img=2,chan=3)),local_size=(tn=uint32_t,v=5)))"
+    with pytest.raises(bb.RtException):
+        bb.op_canonical("(type=Convolution,bogus_vals=())")
