@@ -116,6 +116,83 @@ def cpu_reference_forward(n_images, reps=1, min_seconds=0.0, max_reps=16):
     return n_images * done / dt, bo.num_threads(), dt, done
 
 
+def torch_cpu_forward(n_images, min_seconds=3.0, check=False):
+    """Second CPU figure of SURVEY section 8(d): the same net through torch's CPU operators (oneDNN convolutions) on all host cores, in the
+    same run. A LIBRARY number for scale only -- not the reference's algorithm, not the reported baseline (that is the oracle port above).
+    Walks the same conv_pipe text. Returns (images/s, threads, seconds, forwards) [+ the output node when check=True]."""
+    import torch
+    import torch.nn.functional as F
+    from boda_b200 import nets
+    from oracle import boda_oracle as bo
+    txt, i, o = nets.NETS[NET_NAME](n_images)
+    params = {k: torch.from_numpy(v) for k, v in nets.synth_params(txt).items()}
+    x0 = torch.from_numpy(nets.synth_input((n_images, 3, NET_IN_SZ, NET_IN_SZ)))
+    ops = []
+    for line in txt.splitlines():
+        line = line.strip()
+        if not line or line.startswith("#"):
+            continue
+        d = bo.parse_lexp(line)
+        if "node" in d:
+            continue
+        nv = {k: bo._nda_from_lexp(v) for k, v in (d.get("nda_vals") or {}).items()}
+        ops.append((d["str_vals"]["type"], d["tag"], [b for b in d["bots"].split(":") if b], [t for t in d["tops"].split(":") if t], nv))
+
+    def yx(nv, name, dflt):
+        return (nv[name].dims["y"], nv[name].dims["x"]) if name in nv else dflt
+
+    def fwd():
+        nodes = {i: x0}
+        for typ, tag, bots, tops, nv in ops:
+            x = nodes[bots[0]]
+            if typ in ("Convolution", "InnerProduct"):
+                y = F.conv2d(x, params[tag + "_filts"], params.get(tag + "_biases"), stride=yx(nv, "stride", (1, 1)), padding=yx(nv, "in_pad", (0, 0)))
+            elif typ == "BatchNorm":
+                sf = float(params[tag + "_sf"].reshape(-1)[0])
+                sc = 0.0 if sf == 0 else 1.0 / sf
+                eps = float(nv["eps"].v) if "eps" in nv else 1e-5
+                y = (x - (params[tag + "_mean"] * sc)[None, :, None, None]) / torch.sqrt(params[tag + "_var"] * sc + eps)[None, :, None, None]
+            elif typ == "Scale":
+                y = x * params[tag + "_gamma"][None, :, None, None] + params[tag + "_beta"][None, :, None, None]
+            elif typ == "ReLU":
+                y = F.relu(x)
+            elif typ == "Dropout":
+                y = x
+            elif typ == "LRN":
+                y = F.local_response_norm(x, int(nv["local_size"].v), float(nv["alpha"].v), float(nv["beta"].v), float(nv["k"].v))
+            elif typ == "Pooling":
+                avg = bool(int(nv["avg_pool"].v)) if "avg_pool" in nv else False
+                if "kern_sz" not in nv:
+                    y = x.mean(dim=(2, 3), keepdim=True) if avg else x.amax(dim=(2, 3), keepdim=True)
+                elif avg:
+                    y = F.avg_pool2d(x, yx(nv, "kern_sz", None), yx(nv, "stride", (1, 1)), yx(nv, "in_pad", (0, 0)), ceil_mode=True, count_include_pad=False)
+                else:
+                    y = F.max_pool2d(x, yx(nv, "kern_sz", None), yx(nv, "stride", (1, 1)), yx(nv, "in_pad", (0, 0)), ceil_mode=True)
+            elif typ == "Concat":
+                y = torch.cat([nodes[b] for b in bots], dim=1)
+            elif typ in ("Eltwise", "Reduce"):
+                y = sum(nodes[b] for b in bots)
+            elif typ == "Softmax":
+                y = F.softmax(x, dim=1)
+            else:
+                raise ValueError("torch_cpu_forward: unhandled op type " + typ)
+            nodes[tops[0]] = y
+        return nodes[o]
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    with torch.no_grad():
+        out = fwd()  # warm-up (oneDNN primitive creation, weight reorders)
+        t0 = time.perf_counter()
+        done = 0
+        while done < 2 or (time.perf_counter() - t0 < min_seconds and done < 64):
+            out = fwd()
+            done += 1
+        dt = time.perf_counter() - t0
+    res = (n_images * done / dt, threads, dt, done)
+    return res + (out.numpy(),) if check else res
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -160,11 +237,16 @@ def main():
     ap.add_argument("--net", default="alexnet_ng_conv", choices=["alexnet_ng_conv", "nin_imagenet", "googlenet_conv", "resnet50"],
                     help="default = BASELINE configs[1]; googlenet_conv --batch 64 --prec bf16 = configs[3]; resnet50 --batch 32 (x8 GPUs = 256) = configs[4]")
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU per step")
+    ap.add_argument("--torch-cpu-child", action="store_true", help=argparse.SUPPRESS)  # internal: the torch-CPU figure of cpu_baseline, run as a child process
     args = ap.parse_args()
     global NET_NAME, NET_IN_SZ, METRIC
     NET_NAME = args.net
     NET_IN_SZ = 224 if args.net in ("googlenet_conv", "resnet50") else 227
     METRIC = "%s_fwd_images_per_sec" % args.net
+    if args.torch_cpu_child:
+        v, cores, secs, n = torch_cpu_forward(args.batch)
+        print(json.dumps({"value": v, "cores": cores, "seconds": secs, "forwards": n}))
+        return
     if args.impl != "reference":
         args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -368,6 +450,16 @@ def main():
             v, cores, secs, n_fwd = cpu_reference_forward(B, reps=2, min_seconds=10.0)  # a bounded sample: >= 10 s of CPU work, at most 16 forwards
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "%d x %s forward of the full %d-image batch through the oracle port (OpenMP, all host cores), %.1f s" % (n_fwd, args.net, B, secs)}
+            try:  # torch's CPU operators (oneDNN) on the same box in the same run -- a library figure, for scale only.
+                # In a child process (no GPU, its own thread pools, bounded time) so that nothing it does can cost the bench line.
+                import subprocess
+                env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+                cp_ = subprocess.run([sys.executable, os.path.abspath(__file__), "--torch-cpu-child", "--net", args.net, "--batch", str(B)], env=env, capture_output=True, text=True, timeout=180)
+                tc = json.loads(cp_.stdout.strip().splitlines()[-1])
+                line["cpu_baseline"]["torch_cpu"] = {"value": tc["value"], "unit": UNIT, "cores": tc["cores"], "kind": "library (torch CPU / oneDNN; not the reference's algorithm)",
+                                                     "sample": "%d x %s forward of the full %d-image batch, %.1f s" % (tc["forwards"], args.net, B, tc["seconds"])}
+            except Exception as e:  # never let the extra figure break the bench line
+                line["cpu_baseline"]["torch_cpu"] = {"unavailable": repr(e)[:200]}
         _emit(line)
     if dist:
         dist.barrier()
