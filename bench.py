@@ -245,7 +245,7 @@ def main():
     METRIC = "%s_fwd_images_per_sec" % args.net
     if args.torch_cpu_child:
         v, cores, secs, n = torch_cpu_forward(args.batch)
-        print(json.dumps({"value": v, "cores": cores, "seconds": secs, "forwards": n}))
+        _emit({"value": v, "cores": cores, "seconds": secs, "forwards": n})
         return
     if args.impl != "reference":
         args.warmup = max(args.warmup, 3)
