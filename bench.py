@@ -12,7 +12,8 @@ A step = one whole-net forward of one batch (32 images per GPU) of synthetic NCH
 `roofline`: the dominant kernel (the tcgen05 implicit-GEMM contraction behind every Convolution): algorithmic conv FLOPs
             (2*B*OC*OH*OW*IC*KH*KW, src/latex-util.H:116-120) / its CUDA-event launch durations, vs the measured bf16 peak.
 `cpu_baseline` / `--impl reference`: the oracle port of the reference's operator semantics (Boda itself cannot be built
-            here: boost/protobuf/python2/Caffe missing) on all host cores, on a bounded sample of the same workload.
+            here: boost/protobuf/python2/Caffe missing) on all host cores, on a bounded sample of the same workload (>= 10 s of CPU
+            work). `cpu_baseline.torch_cpu` adds SURVEY 8(d)'s second figure, torch's CPU operators (oneDNN), from a child process.
 Multi-GPU: images are independent units of the path, so ranks shard the batch dimension (weak scaling, 32 images per
 GPU); weights are broadcast once from rank 0 over NCCL at init and the logits are all-gathered over NCCL every step.
 """
