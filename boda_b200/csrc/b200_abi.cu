@@ -20,6 +20,11 @@ template <typename F> int guarded(F &&f) {
   catch (...) { g_last_error = "unknown exception"; return -1; }
 }
 
+// entries that take an instance first make its device current for the calling thread (another instance, or the caller's own framework, may
+// have switched it since): allocations, launches, copies and graph replays below all use the current device
+template <typename F> int guarded_dev(b200_rtc *r, F &&f) { return guarded([&] { r->rtc->bind_device(); return f(); }); }
+template <typename F> int guarded_dev(b200_fwd *f_, F &&f) { return guarded([&] { if (f_->fwd && f_->fwd->rtc) { f_->fwd->rtc->bind_device(); } return f(); }); }
+
 dims_t make_dims(char const *tn, int ndims, char const *const *dim_names, uint32_t const *dim_sizes) {
   dims_t d;
   d.tn = tn ? tn : "float";
@@ -50,33 +55,22 @@ B200_API void b200_rtc_destroy(b200_rtc *r) { guarded([&] { delete r; return 0; 
 B200_API int b200_rtc_set_option(b200_rtc *r, const char *key, const char *val) {
   return guarded([&] {
     string const k = key, v = val;
-    if (k == "prec") { r->rtc->prec = (v == "fp32") ? B200_PREC_FP32_SPLIT : (v == "fp16") ? B200_PREC_FP16 : (v == "bf16") ? B200_PREC_BF16 : (rt_err("unknown prec '" + v + "'"), B200_PREC_FP32_SPLIT); }
-    else if (k == "acc_chunk_kblks") { r->rtc->acc_chunk_kblks = std::stoi(v); }
-    else if (k == "acc_chunk_kblks_16") { r->rtc->acc_chunk_kblks_16 = std::stoi(v); }
-    else if (k == "use_taps") { r->rtc->use_taps = std::stoi(v); }
-    else if (k == "use_pdl") { r->rtc->use_pdl = std::stoi(v); }
-    else if (k == "taps_2cta") { r->rtc->taps_2cta = std::stoi(v); }
-    else if (k == "taps_max_b_stages") { r->rtc->taps_max_b_stages = std::stoi(v); }
-    else if (k == "taps_max_a_stages") { r->rtc->taps_max_a_stages = std::stoi(v); }
-    else if (k == "use_clusters") { r->rtc->use_clusters = std::stoi(v); }
-    else if (k == "use_2cta") { r->rtc->use_2cta = std::stoi(v); }
-    else if (k == "debug_flags") { r->rtc->debug_flags = std::stoi(v); }
-    else if (k == "device") { r->rtc->device = std::stoi(v); }
+    if (r->rtc->set_option(k, v)) {}
     else { rt_err("be=b200: unused option '" + k + "'"); }
     return 0;
   });
 }
-B200_API int b200_rtc_init(b200_rtc *r) { return guarded([&] { r->rtc->init(); return 0; }); }
+B200_API int b200_rtc_init(b200_rtc *r) { return guarded_dev(r, [&] { r->rtc->init(); return 0; }); }
 B200_API const char *b200_rtc_get_plat_tag(b200_rtc *r) { r->tmp = r->rtc->get_plat_tag(); return r->tmp.c_str(); }
 B200_API int b200_rtc_create_var(b200_rtc *r, const char *vn, const char *tn, int ndims, const char *const *dim_names, const uint32_t *dim_sizes) {
-  return guarded([&] { r->rtc->create_var_with_dims(vn, make_dims(tn, ndims, dim_names, dim_sizes)); return 0; });
+  return guarded_dev(r, [&] { r->rtc->create_var_with_dims(vn, make_dims(tn, ndims, dim_names, dim_sizes)); return 0; });
 }
 B200_API int b200_rtc_create_view(b200_rtc *r, const char *vn, const char *tn, int ndims, const char *const *dim_names, const uint32_t *dim_sizes, const char *src_vn) {
-  return guarded([&] { r->rtc->create_var_with_dims_as_reshaped_view_of_var(vn, make_dims(tn, ndims, dim_names, dim_sizes), src_vn); return 0; });
+  return guarded_dev(r, [&] { r->rtc->create_var_with_dims_as_reshaped_view_of_var(vn, make_dims(tn, ndims, dim_names, dim_sizes), src_vn); return 0; });
 }
-B200_API int b200_rtc_release_var(b200_rtc *r, const char *vn) { return guarded([&] { r->rtc->release_var(vn); return 0; }); }
+B200_API int b200_rtc_release_var(b200_rtc *r, const char *vn) { return guarded_dev(r, [&] { r->rtc->release_var(vn); return 0; }); }
 B200_API int b200_rtc_get_var_dims(b200_rtc *r, const char *vn, int max_dims, uint32_t *dim_sizes, char *names_buf, int names_buf_len) {
-  return guarded([&] {
+  return guarded_dev(r, [&] {
     dims_t const d = r->rtc->get_var_dims(vn);
     string names;
     for (size_t i = 0; i < d.size(); ++i) { if ((int)i < max_dims) { dim_sizes[i] = d[i].sz; } names += (i ? ":" : "") + d[i].name; }
@@ -84,9 +78,9 @@ B200_API int b200_rtc_get_var_dims(b200_rtc *r, const char *vn, int max_dims, ui
     return (int)d.size();
   });
 }
-B200_API int b200_rtc_set_var_to_zero(b200_rtc *r, const char *vn) { return guarded([&] { r->rtc->set_var_to_zero(vn); return 0; }); }
+B200_API int b200_rtc_set_var_to_zero(b200_rtc *r, const char *vn) { return guarded_dev(r, [&] { r->rtc->set_var_to_zero(vn); return 0; }); }
 B200_API int b200_rtc_compile(b200_rtc *r, const char *func_name, const char *op_text) {
-  return guarded([&] {
+  return guarded_dev(r, [&] {
     rtc_func_info_t fi;
     fi.func_name = func_name;
     fi.op = *make_p_op_base_t_from_str(op_text);
@@ -94,9 +88,9 @@ B200_API int b200_rtc_compile(b200_rtc *r, const char *func_name, const char *op
     return 0;
   });
 }
-B200_API int b200_rtc_release_func(b200_rtc *r, const char *func_name) { return guarded([&] { r->rtc->release_func(func_name); return 0; }); }
+B200_API int b200_rtc_release_func(b200_rtc *r, const char *func_name) { return guarded_dev(r, [&] { r->rtc->release_func(func_name); return 0; }); }
 B200_API int b200_rtc_run(b200_rtc *r, const char *func_name, int nargs, const char *const *arg_names, const char *const *arg_vals) {
-  return guarded([&] {
+  return guarded_dev(r, [&] {
     rtc_func_call_t rfc;
     rfc.rtc_func_name = func_name;
     for (int i = 0; i < nargs; ++i) {
@@ -107,14 +101,14 @@ B200_API int b200_rtc_run(b200_rtc *r, const char *func_name, int nargs, const c
     return (int)r->rtc->run(rfc);
   });
 }
-B200_API int b200_rtc_finish_and_sync(b200_rtc *r) { return guarded([&] { r->rtc->finish_and_sync(); return 0; }); }
-B200_API int b200_rtc_release_per_call_id_data(b200_rtc *r) { return guarded([&] { r->rtc->release_per_call_id_data(); return 0; }); }
-B200_API int b200_rtc_release_all_funcs(b200_rtc *r) { return guarded([&] { r->rtc->release_all_funcs(); return 0; }); }
-B200_API int b200_rtc_get_dur(b200_rtc *r, uint32_t b, uint32_t e, float *ms_out) { return guarded([&] { *ms_out = r->rtc->get_dur(b, e); return 0; }); }
-B200_API int b200_rtc_copy_to_var(b200_rtc *r, const char *vn, const void *host_src, uint64_t bytes) { return guarded([&] { r->rtc->copy_raw_to_var(vn, host_src, bytes); return 0; }); }
-B200_API int b200_rtc_copy_from_var(b200_rtc *r, void *host_dst, const char *vn, uint64_t bytes) { return guarded([&] { r->rtc->copy_var_to_raw(host_dst, vn, bytes); return 0; }); }
+B200_API int b200_rtc_finish_and_sync(b200_rtc *r) { return guarded_dev(r, [&] { r->rtc->finish_and_sync(); return 0; }); }
+B200_API int b200_rtc_release_per_call_id_data(b200_rtc *r) { return guarded_dev(r, [&] { r->rtc->release_per_call_id_data(); return 0; }); }
+B200_API int b200_rtc_release_all_funcs(b200_rtc *r) { return guarded_dev(r, [&] { r->rtc->release_all_funcs(); return 0; }); }
+B200_API int b200_rtc_get_dur(b200_rtc *r, uint32_t b, uint32_t e, float *ms_out) { return guarded_dev(r, [&] { *ms_out = r->rtc->get_dur(b, e); return 0; }); }
+B200_API int b200_rtc_copy_to_var(b200_rtc *r, const char *vn, const void *host_src, uint64_t bytes) { return guarded_dev(r, [&] { r->rtc->copy_raw_to_var(vn, host_src, bytes); return 0; }); }
+B200_API int b200_rtc_copy_from_var(b200_rtc *r, void *host_dst, const char *vn, uint64_t bytes) { return guarded_dev(r, [&] { r->rtc->copy_var_to_raw(host_dst, vn, bytes); return 0; }); }
 B200_API int b200_rtc_get_var_raw_native_pointer(b200_rtc *r, const char *vn, void **dev_ptr_out) {
-  return guarded([&] { *dev_ptr_out = r->rtc->get_var_raw_native_pointer(vn)->rp_elems(); return 0; });
+  return guarded_dev(r, [&] { *dev_ptr_out = r->rtc->get_var_raw_native_pointer(vn)->rp_elems(); return 0; });
 }
 B200_API uint64_t b200_rtc_launches(b200_rtc *r) { return r->rtc->launches(); }
 
@@ -265,24 +259,24 @@ B200_API b200_fwd *b200_fwd_create(const char *pipe_text, const char *opts) {
 }
 B200_API void b200_fwd_destroy(b200_fwd *f) { guarded([&] { delete f; return 0; }); }
 B200_API int b200_fwd_set_param(b200_fwd *f, const char *node_name, const float *host_src, uint64_t n_elems) {
-  return guarded([&] { f->fwd->set_param(node_name, host_src, n_elems); return 0; });
+  return guarded_dev(f, [&] { f->fwd->set_param(node_name, host_src, n_elems); return 0; });
 }
 B200_API int b200_fwd_run(b200_fwd *f, int n_set, const char *const *set_names, const float *const *set_bufs, const uint64_t *set_elems, int n_get,
                           const char *const *get_names, float *const *get_bufs, const uint64_t *get_elems) {
-  return guarded([&] { f->fwd->run_fwd_raw(n_set, set_names, set_bufs, set_elems, n_get, get_names, get_bufs, get_elems); return 0; });
+  return guarded_dev(f, [&] { f->fwd->run_fwd_raw(n_set, set_names, set_bufs, set_elems, n_get, get_names, get_bufs, get_elems); return 0; });
 }
 B200_API int b200_fwd_submit(b200_fwd *f, int n_set, const char *const *set_names, const float *const *set_bufs, const uint64_t *set_elems, int n_get,
                              const char *const *get_names, float *const *get_bufs, const uint64_t *get_elems) {
-  return guarded([&] { return f->fwd->submit(n_set, set_names, set_bufs, set_elems, n_get, get_names, get_bufs, get_elems); });
+  return guarded_dev(f, [&] { return f->fwd->submit(n_set, set_names, set_bufs, set_elems, n_get, get_names, get_bufs, get_elems); });
 }
-B200_API int b200_fwd_wait(b200_fwd *f, int ticket) { return guarded([&] { f->fwd->wait(ticket); return 0; }); }
+B200_API int b200_fwd_wait(b200_fwd *f, int ticket) { return guarded_dev(f, [&] { f->fwd->wait(ticket); return 0; }); }
 B200_API int b200_fwd_run_device_only(b200_fwd *f, int iters, float *ms_per_iter_out) {
-  return guarded([&] { *ms_per_iter_out = f->fwd->run_device_only(iters); return 0; });
+  return guarded_dev(f, [&] { *ms_per_iter_out = f->fwd->run_device_only(iters); return 0; });
 }
-B200_API int b200_fwd_set_det_drop_seed(b200_fwd *f, uint32_t seed) { return guarded([&] { f->fwd->set_det_drop_seed(seed); return 0; }); }
+B200_API int b200_fwd_set_det_drop_seed(b200_fwd *f, uint32_t seed) { return guarded_dev(f, [&] { f->fwd->set_det_drop_seed(seed); return 0; }); }
 B200_API const char *b200_fwd_get_info_log(b200_fwd *f) { f->tmp = f->fwd->get_info_log(); return f->tmp.c_str(); }
 B200_API int b200_fwd_get_node_dims(b200_fwd *f, const char *node_name, uint32_t *dims4) {
-  return guarded([&] {
+  return guarded_dev(f, [&] {
     dims_t const &d = f->fwd->cp->must_get_node(node_name)->dims;
     for (size_t i = 0; i < d.size() && i < 4; ++i) { dims4[i] = d[i].sz; }
     return (int)d.size();
@@ -291,7 +285,7 @@ B200_API int b200_fwd_get_node_dims(b200_fwd *f, const char *node_name, uint32_t
 B200_API int b200_fwd_num_calls(b200_fwd *f) { return (int)f->fwd->fwd_calls.size(); }
 B200_API uint64_t b200_fwd_launches(b200_fwd *f) { return f->fwd->launches(); }
 B200_API int b200_fwd_profile(b200_fwd *f, int iters, char *tags_buf, int tags_buf_len, float *call_ms_out, float *kernel_ms_out, double *flops_out, int max_calls) {
-  return guarded([&] {
+  return guarded_dev(f, [&] {
     auto res = f->fwd->profile(iters);
     string tags;
     int n = 0;
@@ -306,18 +300,18 @@ B200_API int b200_fwd_profile(b200_fwd *f, int iters, char *tags_buf, int tags_b
   });
 }
 B200_API int b200_fwd_run_timed(b200_fwd *f, int iters, uint64_t l2_flush_bytes, float *ms_each_out) {
-  return guarded([&] {
+  return guarded_dev(f, [&] {
     vector<float> ms = f->fwd->run_timed(iters, l2_flush_bytes);
     for (int i = 0; i < iters; ++i) { ms_each_out[i] = ms[i]; }
     return 0;
   });
 }
-B200_API int b200_fwd_enqueue(b200_fwd *f) { return guarded([&] { f->fwd->enqueue_fwd(); return 0; }); }
-B200_API int b200_fwd_flush_l2(b200_fwd *f, uint64_t bytes) { return guarded([&] { f->fwd->flush_l2(bytes); return 0; }); }
-B200_API int b200_fwd_get_stream(b200_fwd *f, void **stream_out) { return guarded([&] { *stream_out = f->fwd->stream(); return 0; }); }
+B200_API int b200_fwd_enqueue(b200_fwd *f) { return guarded_dev(f, [&] { f->fwd->enqueue_fwd(); return 0; }); }
+B200_API int b200_fwd_flush_l2(b200_fwd *f, uint64_t bytes) { return guarded_dev(f, [&] { f->fwd->flush_l2(bytes); return 0; }); }
+B200_API int b200_fwd_get_stream(b200_fwd *f, void **stream_out) { return guarded_dev(f, [&] { *stream_out = f->fwd->stream(); return 0; }); }
 B200_API int b200_fwd_get_node_raw_native_pointer(b200_fwd *f, const char *node_name, void **dev_ptr_out) {
-  return guarded([&] { *dev_ptr_out = f->fwd->rtc->get_var_raw_native_pointer(node_name)->rp_elems(); return 0; });
+  return guarded_dev(f, [&] { *dev_ptr_out = f->fwd->rtc->get_var_raw_native_pointer(node_name)->rp_elems(); return 0; });
 }
-B200_API int b200_rtc_get_kernel_dur(b200_rtc *r, uint32_t id, float *ms_out) { return guarded([&] { *ms_out = r->rtc->get_kernel_dur(id); return 0; }); }
+B200_API int b200_rtc_get_kernel_dur(b200_rtc *r, uint32_t id, float *ms_out) { return guarded_dev(r, [&] { *ms_out = r->rtc->get_kernel_dur(id); return 0; }); }
 
 }  // extern "C"

@@ -7,6 +7,7 @@
 #include "igemm3.cuh"
 #include "pointwise.cuh"
 #include <cudaTypedefs.h>
+#include <cuda_profiler_api.h>
 #include <algorithm>
 #include <cmath>
 
@@ -41,7 +42,16 @@ struct packed_t {
   uint64_t src_gen = ~0ull;
   void const *src_ptr = nullptr;
   long long rows = 0, row_stride = 0;  // elements
+  uint64_t layout_key = 0;  // geometry the planes were written for (pack_layout_key): reshaped views share storage AND generation, so a
+                            // consumer reading the same storage through other dims must not reuse planes packed for this geometry
 };
+
+// FNV-1a over the arguments that determine where pack() puts every element
+uint64_t pack_layout_key(std::initializer_list<long long> v) {
+  uint64_t h = 1469598103934665603ull;
+  for (long long x : v) { for (int i = 0; i < 8; ++i) { h ^= (uint64_t)(x >> (8 * i)) & 0xff; h *= 1099511628211ull; } }
+  return h ? h : 1;
+}
 
 enum func_kind_t { FK_CONV, FK_SGEMM, FK_POOL, FK_LRN, FK_RELU, FK_SOFTMAX, FK_COPY, FK_REDUCE, FK_GEN_DATA, FK_BN_FOLD };
 
@@ -136,7 +146,10 @@ CUtensorMap make_im2col_map(void const *base, bool bf16, conv_plan_t const &cp, 
 template <typename F> void prefer_max_smem(F *func) {
   cudaFuncSetAttribute(reinterpret_cast<void const *>(func), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
-#define B200_CARVEOUT_ONCE(...) do { static bool done_ = false; if (!done_) { prefer_max_smem(__VA_ARGS__); done_ = true; } } while (0)
+// cudaFuncSetAttribute is per device (context): the "already done" state is a bit per device ordinal, so a second instance on another GPU of
+// the same process gets its own opt-ins (carve-out preference, > 48 KB dynamic shared memory)
+inline bool first_use_on_device(uint64_t &mask, int dev) { uint64_t const b = 1ull << (dev & 63); if (mask & b) { return false; } mask |= b; return true; }
+#define B200_CARVEOUT_ONCE(...) do { static uint64_t done_ = 0; if (first_use_on_device(done_, rtc.device)) { prefer_max_smem(__VA_ARGS__); } } while (0)
 
 int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
@@ -202,6 +215,33 @@ b200_compute_t::~b200_compute_t() {
   }
 }
 
+bool b200_compute_t::set_option(string const &k, string const &v) {
+  if (k == "prec") { prec = (v == "fp32") ? B200_PREC_FP32_SPLIT : (v == "fp16") ? B200_PREC_FP16 : (v == "bf16") ? B200_PREC_BF16 : (rt_err("unknown prec '" + v + "'"), B200_PREC_FP32_SPLIT); }
+  else if (k == "acc_chunk_kblks") { acc_chunk_kblks = std::stoi(v); }
+  else if (k == "acc_chunk_kblks_16") { acc_chunk_kblks_16 = std::stoi(v); }
+  else if (k == "use_taps") { use_taps = std::stoi(v); }
+  else if (k == "use_pdl") { use_pdl = std::stoi(v); }
+  else if (k == "taps_2cta") { taps_2cta = std::stoi(v); }
+  else if (k == "taps_max_b_stages") { taps_max_b_stages = std::stoi(v); }
+  else if (k == "taps_max_a_stages") { taps_max_a_stages = std::stoi(v); }
+  else if (k == "use_clusters") { use_clusters = std::stoi(v); }
+  else if (k == "use_2cta") { use_2cta = std::stoi(v); }
+  else if (k == "debug_flags") { debug_flags = std::stoi(v); }
+  else if (k == "device") { device = std::stoi(v); }
+  else if (k == "plan_only") { plan_only = std::stoi(v); }
+  else if (k == "plan_num_sms") { plan_num_sms = std::stoi(v); }
+  else if (k == "use_be") {  // src/cnn_op.H:13: "if non-empty, use this tune only with the specific named backend"
+    if (!v.empty() && v != "b200") { rt_err("op_tune use_be='" + v + "' names another back-end; this is be=b200"); }
+    ignored_knobs += (ignored_knobs.empty() ? "" : ",") + k;
+  }
+  else if (k == "use_culibs" || k == "MNt" || k == "MNb" || k == "Kb" || k == "use_local_mem" || k == "prof_variant" || k == "vw" || k == "k1conv" || k == "tconv" ||
+           k == "tconv_max_ksz" || k == "ipconv") {
+    ignored_knobs += (ignored_knobs.empty() ? "" : ",") + k;  // CUCL variant selection: one hand-written kernel family here, chosen by plan_conv
+  }
+  else { return false; }
+  return true;
+}
+
 void b200_compute_t::init() {
   if (impl->inited) { return; }
   if (plan_only) {  // no device: launch plans only (b200_fwd_plan); run() and every copy refuse
@@ -223,6 +263,7 @@ void b200_compute_t::init() {
   load_driver_entry_points();
   impl->inited = true;
 }
+void b200_compute_t::bind_device() { if (impl->inited && !plan_only) { CU_CHK(cudaSetDevice(device)); } }
 string b200_compute_t::get_plat_tag() { return impl->plat_tag.empty() ? string("b200:uninit") : impl->plat_tag; }
 cudaStream_t b200_compute_t::stream() const { return impl->stream; }
 uint64_t b200_compute_t::launches() const { return impl->n_launches; }
@@ -519,8 +560,9 @@ float b200_compute_t::get_kernel_dur(uint32_t const &id) {
   CU_CHK(cudaEventElapsedTime(&ms, c.kb, c.ke));
   return ms;
 }
-void b200_compute_t::profile_start() {}
-void b200_compute_t::profile_stop() {}
+// src/nvrtc_util.cc:388-389 (cuProfilerStart / cuProfilerStop): brackets the region a profiler launched with --profile-from-start off captures
+void b200_compute_t::profile_start() { if (!plan_only) { CU_CHK(cudaSetDevice(device)); CU_CHK(cudaProfilerStart()); } }
+void b200_compute_t::profile_stop() { if (!plan_only) { CU_CHK(cudaSetDevice(device)); CU_CHK(cudaProfilerStop()); } }
 
 // ---- run ------------------------------------------------------------------------------------------------------
 namespace {
@@ -583,8 +625,10 @@ struct run_ctx_t {
   void pack(packed_t &pk, var_info_t &src, int B, int R, int Cc, int Rpad, long long dst_c_stride, long long dst_b_stride, long long total_elems, bool want_lo, bool bf16,
             int c_inner = 0, long long dst_chi_stride = 0, long long dst_base = 0, unsigned int const *absmax_src = nullptr, int smallc_W = 0, long long kmajor_rows = 0) {
     if (c_inner <= 0) { c_inner = std::max(Cc, 1); }
-    if (pk.src_gen == *src.gen && pk.src_ptr == src.buf->p && pk.hi) { return; }
-    if (!pk.hi || pk.hi->bytes < (uint64_t)total_elems * 2) {
+    uint64_t const lkey = pack_layout_key({B, R, Cc, Rpad, dst_c_stride, dst_b_stride, c_inner, dst_chi_stride, dst_base, want_lo, bf16, smallc_W, kmajor_rows});
+    if (pk.src_gen == *src.gen && pk.src_ptr == src.buf->p && pk.hi && pk.layout_key == lkey && (!want_lo || pk.lo)) { return; }
+    pk.layout_key = lkey;
+    if (!pk.hi || pk.hi->bytes < (uint64_t)total_elems * 2 || (want_lo && !pk.lo)) {
       pk.hi = std::make_shared<dev_buf_t>(total_elems * 2);
       CU_CHK(cudaMemsetAsync(pk.hi->p, 0, total_elems * 2, st));
       if (want_lo) { pk.lo = std::make_shared<dev_buf_t>(total_elems * 2); CU_CHK(cudaMemsetAsync(pk.lo->p, 0, total_elems * 2, st)); }
@@ -648,10 +692,9 @@ struct run_ctx_t {
   template <int BN, int kPlanes>
   void launch_igemm_t(dim3 grid, CUtensorMap const &ph, CUtensorMap const &pl, CUtensorMap const &qh, CUtensorMap const &ql, b200::IgemmParams const &prm) {
     using Cfg = b200::IgemmCfg<BN, kPlanes>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static uint64_t attr_set = 0;
+    if (first_use_on_device(attr_set, rtc.device)) {
       CU_CHK(cudaFuncSetAttribute(b200::igemm_umma_kernel<BN, kPlanes>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-      attr_set = true;
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -671,10 +714,9 @@ struct run_ctx_t {
   template <int BN, int kPlanes>
   void launch_igemm2_t(dim3 grid, CUtensorMap const &ph, CUtensorMap const &pl, CUtensorMap const &qh, CUtensorMap const &ql, b200::IgemmParams const &prm) {
     using Cfg = b200::Igemm2Cfg<BN, kPlanes>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static uint64_t attr_set = 0;
+    if (first_use_on_device(attr_set, rtc.device)) {
       CU_CHK(cudaFuncSetAttribute(b200::igemm_umma_2cta_kernel<BN, kPlanes>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-      attr_set = true;
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -709,10 +751,9 @@ struct run_ctx_t {
   // ---- tap-reuse path (igemm3.cuh): returns false when the shape does not fit its shared-memory budget (caller falls back to im2col) ----
   template <int BN, int kPlanes, bool k2>
   void launch_taps_t(dim3 grid, size_t smem, CUtensorMap const &ah, CUtensorMap const &al, CUtensorMap const &wh, CUtensorMap const &wl, b200::TapsParams const &prm) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static uint64_t attr_set = 0;
+    if (first_use_on_device(attr_set, rtc.device)) {
       CU_CHK(cudaFuncSetAttribute(b200::igemm_taps_kernel<BN, kPlanes, k2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attr_set = true;
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -978,7 +1019,11 @@ struct run_ctx_t {
       launched();
     }
     im.bump(vdst);
-    if (out_pk) { out_pk->src_gen = *vdst.gen; out_pk->src_ptr = vdst.buf->p; }  // the plane is current for this write generation: consumers skip their pack
+    if (out_pk) {  // the plane is current for this write generation: consumers skip their pack (same key as their pack() call: plain NHWC)
+      out_pk->src_gen = *vdst.gen; out_pk->src_ptr = vdst.buf->p;
+      long long const cd = (long long)vdst.dims.dsz("chan"), cdp = round_up(cd, 8), hw = (long long)cp.OH * cp.OW;
+      out_pk->layout_key = pack_layout_key({cp.N, cd, hw, cdp, cdp, hw * cdp, std::max<long long>(hw, 1), 0, 0, planes == 2, bf16, 0, 0});
+    }
   }
   static constexpr uint32_t IGEMM_BM_host() { return b200::IGEMM_BM; }
 
@@ -1119,11 +1164,11 @@ struct run_ctx_t {
       // persistent grid: as many CTAs as fit the chip at this shared-memory footprint, each walking its share of the groups
       unsigned const pipe_grid = (unsigned)std::min<long long>(n_groups, (long long)im.num_sms * std::max<long long>(1, std::min<long long>(8, (224 * 1024) / (long long)(smem + 1024))));
 #define B200_POOL_PLANE(K_, S_) do { \
-        static bool attr_ = false; \
-        if (!attr_) { \
+        static uint64_t attr_ = 0; \
+        if (first_use_on_device(attr_, rtc.device)) { \
           CU_CHK(cudaFuncSetAttribute(b200::pool_plane_kernel<K_, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); prefer_max_smem(b200::pool_plane_kernel<K_, S_>); \
           CU_CHK(cudaFuncSetAttribute(b200::pool_plane_pipe_kernel<K_, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); prefer_max_smem(b200::pool_plane_pipe_kernel<K_, S_>); \
-          attr_ = true; } \
+          } \
         if (pipe_ppc) { launch_k(b200::pool_plane_pipe_kernel<K_, S_>, dim3(pipe_grid), dim3(256), smem, fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, cell, ppc, planes, pp); } \
         else { launch_k(b200::pool_plane_kernel<K_, S_>, dim3((unsigned)n_groups), dim3(256), smem, fptr(vin), fptr(vout), H, W, OH, OW, py, px, avg, cell, ppc, planes, pp); } } while (0)
       if (KH == 3 && sy == 2) { B200_POOL_PLANE(3, 2); } else if (KH == 3) { B200_POOL_PLANE(3, 1); } else if (KH == 2) { B200_POOL_PLANE(2, 2); }
@@ -1131,7 +1176,11 @@ struct run_ctx_t {
 #undef B200_POOL_PLANE
       launched();
       im.bump(vout);
-      if (out_pk) { out_pk->src_gen = *vout.gen; out_pk->src_ptr = vout.buf->p; }  // the planes are current: the consuming convolution skips its pack
+      if (out_pk) {  // the planes are current: the consuming convolution skips its pack (same key as its pack() call: plain NHWC)
+        out_pk->src_gen = *vout.gen; out_pk->src_ptr = vout.buf->p;
+        long long const nimg = (long long)vout.dims.dsz("img"), cdp = round_up(C, 8), ohw2 = (long long)OH * OW;
+        out_pk->layout_key = pack_layout_key({nimg, C, ohw2, cdp, cdp, ohw2 * cdp, std::max<long long>(ohw2, 1), 0, 0, npl == 2, bf16, 0, 0});
+      }
       return;
     }
     if (KH == KW && sy == sx && ((KH == 3 && sy == 2) || (KH == 3 && sy == 1) || (KH == 2 && sy == 2)) && planes <= 65535) {

@@ -79,7 +79,17 @@ struct b200_compute_t {
   b200_compute_t();
   ~b200_compute_t();
 
+  // One option parser for both ABI tiers (b200_rtc_set_option, the opts of b200_fwd_create). Returns false for a key this class does not know
+  // (the caller may know it, else rejects it the way NESI rejects unused keys, src/nesi.cc:25-35). The reference's own op_tune_t knob names
+  // (src/cnn_op.H:10-32: use_be, use_culibs, MNt, MNb, Kb, use_local_mem, prof_variant, vw, k1conv, tconv, tconv_max_ksz, ipconv) are accepted
+  // and ignored -- they select among CUCL variants that do not exist here -- so existing --op-tune=(...) command lines keep working
+  // (SURVEY section 5 "Config/flags"); they are listed in ignored_tune_knobs() so that a caller can log what was dropped.
+  bool set_option(string const &key, string const &val);
+  string const &ignored_tune_knobs() const { return ignored_knobs; }
+  string ignored_knobs;
+
   void init();
+  void bind_device();  // cudaSetDevice(device) for the calling thread (no-op before init() and on plan-only instances)
   string get_plat_tag();
 
   void create_var_with_dims(string const &vn, dims_t const &dims);

@@ -431,22 +431,15 @@ void b200_conv_fwd_t::init(p_conv_pipe_t const &cp_, string const &opts) {
     if (!l->is_leaf) {
       for (auto const &kv : l->kids) {
         string const &k = kv.first, &v = kv.second->leaf;
-        if (k == "prec") { rtc->prec = (v == "fp32") ? B200_PREC_FP32_SPLIT : (v == "fp16") ? B200_PREC_FP16 : (v == "bf16") ? B200_PREC_BF16 : (rt_err("unknown prec '" + v + "'"), B200_PREC_FP32_SPLIT); }
-        else if (k == "use_graph") { use_graph = (uint32_t)std::stoul(v); }
-        else if (k == "acc_chunk_kblks") { rtc->acc_chunk_kblks = std::stoi(v); }
-        else if (k == "acc_chunk_kblks_16") { rtc->acc_chunk_kblks_16 = std::stoi(v); }
-        else if (k == "use_taps") { rtc->use_taps = std::stoi(v); }
-        else if (k == "use_pdl") { rtc->use_pdl = std::stoi(v); }
-        else if (k == "taps_2cta") { rtc->taps_2cta = std::stoi(v); }
-        else if (k == "use_clusters") { rtc->use_clusters = std::stoi(v); }
-        else if (k == "use_2cta") { rtc->use_2cta = std::stoi(v); }
-        else if (k == "device") { rtc->device = std::stoi(v); }
+        if (k == "use_graph") { use_graph = (uint32_t)std::stoul(v); }
         else if (k == "enable_prof") { enable_prof = (uint32_t)std::stoul(v); }
         else if (k == "concat_by_offset") { concat_by_offset = (uint32_t)std::stoul(v); }
         else if (k == "fuse_eltwise") { fuse_eltwise = (uint32_t)std::stoul(v); }
-        else if (k == "plan_only") { rtc->plan_only = std::stoi(v); }
-        else if (k == "plan_num_sms") { rtc->plan_num_sms = std::stoi(v); }
         else if (k == "pack_by_producers") { pack_by_producers = (uint32_t)std::stoul(v); }
+        else if (k == "op_tune" && !kv.second->is_leaf) {  // the reference's nested form, op_tune=(k1conv=1,tconv=1,...) (src/rtc_fwd.cc:36)
+          for (auto const &tk : kv.second->kids) { if (!rtc->set_option(tk.first, tk.second->is_leaf ? tk.second->leaf : string())) { rt_err("mode=b200: unused op_tune option '" + tk.first + "'"); } }
+        }
+        else if (rtc->set_option(k, v)) {}  // back-end options, and the reference's op_tune_t knob names (accepted, ignored)
         else { rt_err("mode=b200: unused option '" + k + "'"); }  // NESI rejects unused keys (src/nesi.cc:25-35)
       }
     }
@@ -464,7 +457,8 @@ void b200_conv_fwd_t::init(p_conv_pipe_t const &cp_, string const &opts) {
       uint32_t ocix = 0;
       for (auto const &b : op->bots) {
         p_conv_node_t bn = cp->must_get_node(b);
-        bool ok = bn->top_for.size() == 1 && !concat_alias.count(b);
+        // (a node listed twice among this Concat's bottoms has two destinations: it keeps its own var and is copied both times, as the reference does)
+        bool ok = bn->top_for.size() == 1 && !concat_alias.count(b) && std::count(op->bots.begin(), op->bots.end(), b) == 1;
         for (auto const &reader : bn->bot_for) {  // readers: this Concat, or the node's own in-place ops (they list the node as their bottom)
           bool in_place_reader = false;
           for (auto const &ip : bn->in_place_ops) { if (ip->tag == reader) { in_place_reader = true; } }
@@ -676,7 +670,9 @@ void b200_conv_fwd_t::wait(int ticket) {
 
 void b200_conv_fwd_t::run_fwd_raw(int n_set, char const *const *set_names, float const *const *set_bufs, uint64_t const *set_elems, int n_get,
                                   char const *const *get_names, float *const *get_bufs, uint64_t const *get_elems) {
+  if (enable_prof) { rtc->profile_start(); }  // src/rtc_fwd.cc:537
   wait(submit(n_set, set_names, set_bufs, set_elems, n_get, get_names, get_bufs, get_elems));
+  if (enable_prof) { rtc->profile_stop(); }   // src/rtc_fwd.cc:559
 }
 
 void b200_conv_fwd_t::run_fwd(vect_string const &to_set_vns, p_map_str_p_nda_float_t const &fwd, vect_string const &to_get_vns) {

@@ -161,6 +161,7 @@ string conv_pipe_text_from_prototxt(string const &prototxt, prototxt_opts_t cons
       p_pb_msg_t p = l.sub("convolution_param");
       if (!p) { rt_err("layer '" + tag + "': Convolution without convolution_param"); }
       if (p->has("group") && to_u32(p->str("group"), "group") != 1) { rt_err("layer '" + tag + "': grouped convolutions are not supported (nor by the reference)"); }
+      if (p->has("dilation") && to_u32(p->str("dilation"), "dilation") != 1) { rt_err("layer '" + tag + "': dilated convolutions are not supported"); }
       conv_geom(*p, "kernel_size", "kernel_h", "kernel_w", "kern_sz", ndas, tag);
       if (ndas.empty()) { rt_err("layer '" + tag + "': Convolution needs a kernel size"); }
       conv_geom(*p, "stride", "stride_h", "stride_w", "stride", ndas, tag);
@@ -175,6 +176,7 @@ string conv_pipe_text_from_prototxt(string const &prototxt, prototxt_opts_t cons
     } else if (type == "Pooling") {
       p_pb_msg_t p = l.sub("pooling_param");
       if (!p) { rt_err("layer '" + tag + "': Pooling without pooling_param"); }
+      if (p->has("round_mode") && p->str("round_mode") != "CEIL") { rt_err("layer '" + tag + "': only the ceil output-size rule is supported (src/conv_util.cc:198-204), got round_mode " + p->str("round_mode")); }
       string const method = p->str("pool", "MAX");
       if (method != "MAX" && method != "AVE") { rt_err("layer '" + tag + "': unhandled pooling method " + method); }
       ndas.push_back(string("avg_pool=(tn=uint32_t,v=") + (method == "AVE" ? "1" : "0") + ")");
@@ -200,7 +202,12 @@ string conv_pipe_text_from_prototxt(string const &prototxt, prototxt_opts_t cons
       ndas.push_back("alpha=(tn=float,v=" + pp.str("alpha", "1") + ")");
       ndas.push_back("beta=(tn=float,v=" + pp.str("beta", "0.75") + ")");
       ndas.push_back("k=(tn=float,v=" + pp.str("k", "1") + ")");
-    } else if (type == "ReLU" || type == "Concat") {
+    } else if (type == "ReLU") {
+      p_pb_msg_t p = l.sub("relu_param");
+      if (p && p->has("negative_slope") && std::stod(p->str("negative_slope")) != 0.0) { rt_err("layer '" + tag + "': leaky ReLU (negative_slope != 0) is not supported"); }
+    } else if (type == "Concat") {
+      p_pb_msg_t p = l.sub("concat_param");
+      if (p && ((p->has("axis") && p->str("axis") != "1") || (p->has("concat_dim") && p->str("concat_dim") != "1"))) { rt_err("layer '" + tag + "': only channel (axis 1) Concat is supported"); }
     } else if (type == "Eltwise") {
       p_pb_msg_t p = l.sub("eltwise_param");
       if (p && p->str("operation", "SUM") != "SUM") { rt_err("layer '" + tag + "': only Eltwise SUM is supported"); }
@@ -212,6 +219,7 @@ string conv_pipe_text_from_prototxt(string const &prototxt, prototxt_opts_t cons
     } else if (type == "Scale") {
       p_pb_msg_t p = l.sub("scale_param");
       if (!p || p->str("bias_term", "false") != "true") { rt_err("layer '" + tag + "': Scale without bias_term is not supported"); }
+      if ((p->has("axis") && p->str("axis") != "1") || (p->has("num_axes") && p->str("num_axes") != "1")) { rt_err("layer '" + tag + "': only per-channel Scale (axis 1, num_axes 1) is supported"); }
     } else if (type == "Dropout") {
       if (tops != bots) { rt_err("layer '" + tag + "': a Dropout that is not in place becomes `clone`, which rtc_fwd cannot run (src/caffepb.cc:235-238)"); }
       p_pb_msg_t p = l.sub("dropout_param");

@@ -428,6 +428,15 @@ ORACLE_API void oracle_min_max(float const *ve, uint64_t sz, float *min_v, float
   *min_v = mn; *max_v = mx;
 }
 
+/* bench.py's reference arm: use all host cores even when the launcher (torch.distributed.run) exported OMP_NUM_THREADS=1 */
+ORACLE_API void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) { omp_set_num_threads(n); }
+#else
+  (void)n;
+#endif
+}
+
 ORACLE_API int oracle_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -63,6 +63,11 @@ def num_threads() -> int:
     return int(lib().oracle_num_threads())
 
 
+def set_num_threads(n: int) -> None:
+    """OpenMP team size of the C restatement (bench.py's reference arm: all host cores, whatever OMP_NUM_THREADS the launcher exported)."""
+    lib().oracle_set_num_threads(ctypes.c_int(int(n)))
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # gen_data (test/rtc/gen-util.h, test/rtc/gen_data_*.cucl)
 # ---------------------------------------------------------------------------------------------------------------
