@@ -858,6 +858,24 @@ struct run_ctx_t {
     return true;
   }
 
+  // experiments (debug_flags bit 4): role stall counters of the persistent CTA-pair kernel, median / max over clusters, in SM cycles
+  void print_role_stamps(long long *ts_dev, int n_clusters, int BN, int planes, int kblks) {
+    std::vector<long long> ts((size_t)n_clusters * 16);
+    CU_CHK(cudaStreamSynchronize(st));
+    CU_CHK(cudaMemcpy(ts.data(), ts_dev, ts.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(ts_dev);
+    static char const *names[16] = {"prod_total", "prod_wait_empty", "mma_total", "mma_wait_full", "mma_wait_tmem_empty", "mma_first_full", "mma_stages", "", "epi_total", "epi_wait_tmem_full", "epi_drain", "epi_store", "epi_tiles", "", "", ""};
+    string line = "role stamps '" + rfc.rtc_func_name + "' bn=" + str(BN) + " planes=" + str(planes) + " kblks/tile=" + str(kblks) + " clusters=" + str(n_clusters) + " (median/max cycles):";
+    for (int k = 0; k < 13; ++k) {
+      if (!names[k][0]) { continue; }
+      std::vector<long long> v;
+      for (int c = 0; c < n_clusters; ++c) { v.push_back(ts[(size_t)c * 16 + k]); }
+      std::sort(v.begin(), v.end());
+      line += string(" ") + names[k] + "=" + str(v[v.size() / 2]) + "/" + str(v.back());
+    }
+    fprintf(stderr, "%s\n", line.c_str());
+  }
+
   void run_conv() {
     conv_plan_t const &cp = f.cp;
     var_info_t &vin = var("in"), &vf = var("filts"), &vout = var("out");
@@ -1003,16 +1021,20 @@ struct run_ctx_t {
       prm.split_stride = 0;
     }
     dim3 grid((unsigned)round_up(p_tiles, two_cta ? 2 : cl.cm), (unsigned)round_up(q_tiles, cl.cn), cp.splits);
+    long long *ts_dev = nullptr;
+    int ts_clusters = 0;
     mark_kernel_begin();
     if (two_cta) {  // persistent: one cluster per SM pair (or per tile, if fewer), each walking its share of the tiles
       prm.idesc = b200::make_idesc_f16(bf16 ? 1u : 0u, 256, cp.BN);
       prm.m_pair_tiles = ceil_div(p_tiles, 2); prm.q_tiles = q_tiles;
       int const n_clusters = std::min(prm.m_pair_tiles * prm.q_tiles, im.num_sms / 2);
+      if (rtc.debug_flags & 16) { ts_clusters = n_clusters; CU_CHK(cudaMalloc(&ts_dev, (size_t)n_clusters * 16 * sizeof(long long))); CU_CHK(cudaMemsetAsync(ts_dev, 0, (size_t)n_clusters * 16 * sizeof(long long), st)); prm.ts = ts_dev; }
       launch_igemm2(cp.BN, planes, dim3(2 * n_clusters, 1, 1), act_hi, act_lo, w_hi, w_lo, prm);
     }
     else if (cp.swapped) { launch_igemm(cp.BN, planes, grid, w_hi, w_lo, act_hi, act_lo, prm); }
     else { launch_igemm(cp.BN, planes, grid, act_hi, act_lo, w_hi, w_lo, prm); }
     mark_kernel_end();
+    if (ts_dev) { print_role_stamps(ts_dev, ts_clusters, cp.BN, planes, cp.kblks_total); }
     if (cp.splits > 1) {
       B200_CARVEOUT_ONCE(b200::splitk_reduce_kernel); launch_k(b200::splitk_reduce_kernel, dim3(ceil_div(out_elems, 256)), dim3(256), 0, static_cast<float *>(f.splitk_ws->p), out_base, bias, out_elems, cp.splits, cp.OC, cp.OH * cp.OW, cp.relu, prm.out_absmax,
                vcat ? (long long)vcat->dims.dsz("chan") * cp.OH * cp.OW : 0ll);

@@ -59,6 +59,7 @@ struct IgemmParams {
   unsigned int const *res_absmax;  // max|res| published by its producer (bit pattern): the residual's term of the fp16 planes' output bound
   float const *p_scale;    // {scale, inv_scale} of the P tensor
   float const *q_scale;
+  long long *ts;  // experiments (debug_flags bit 4): per-cluster role stall counters of the CTA-pair kernel, [cluster][16] SM cycles (null = off)
   int debug;   // bit 0: skip TMA (MMA runs on whatever is in smem), bit 1: skip MMA issue (loads + barriers only), bit 2: skip the final global stores,
                // bit 3: skip the TMEM drains -- timing experiments only (results are garbage)
   int cm, cn;  // CTA-cluster shape: cm CTAs along P-tiles share (multicast) each Q tile, cn CTAs along Q-tiles share each P tile

@@ -91,7 +91,9 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
   if (warp_id == 0) {
     // ===================== TMA producer (both CTAs; whole warp walks the loop, one elected lane issues -- see igemm.cuh) ==========
     int it = 0;  // k-blocks issued so far, over all tiles: ring position and phase
-    for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+    long long const t_begin = prm.ts ? clock64() : 0;
+    long long w_empty = 0;
+    for (int tile = cluster_id; tile < ((prm.debug & 1) ? 0 : n_tiles); tile += n_clusters) {  // (debug bit 0: no loads at all)
       int const mt = tile / q_tiles, nt = tile - mt * q_tiles;
       int const m0 = (mt * 2 + static_cast<int>(cta_rank)) * IGEMM_BM;  // this CTA's own 128 P rows (the pair covers 256 consecutive ones)
       int img = 0, h_base = 0, w_base = 0;
@@ -108,7 +110,7 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
         int const s = it % kStages;
         uint32_t const ph = (it / kStages) & 1;
         int const nh = min(kKb, nkb - i);  // k-blocks in this stage
-        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (prm.ts) { long long const t0 = clock64(); mbar_wait(&empty_bar[s], ph ^ 1); w_empty += clock64() - t0; } else { mbar_wait(&empty_bar[s], ph ^ 1); }
         bool const issue = elect_one_sync();
         if (issue) {
           if (leader) { mbar_expect_tx(&full_bar[s], 2u * nh * Cfg::kKbBytes); }  // both CTAs' bytes land on the leader's barrier
@@ -139,9 +141,12 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
         __syncwarp();
       }
     }
+    if (prm.ts && leader && lane == 0) { long long *t = prm.ts + cluster_id * 16; t[0] = clock64() - t_begin; t[1] = w_empty; }
   } else if (warp_id == 1) {
     // ===================== MMA issuer (leader CTA only, one elected thread for the pair) =====================
     if (leader) {
+      long long const t_begin = prm.ts ? clock64() : 0;
+      long long w_full = 0, w_tmem = 0, t_first_full = 0;
       uint32_t const idesc = prm.idesc;  // M = 256 (the pair), N = BN
       int const kb_mod = prm.kb_mod, ksteps_last = prm.ksteps_last;
       int it = 0, gc = 0, ti = 0;  // k-blocks, accumulation chunks and tiles done so far
@@ -152,7 +157,7 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
         int i = 0;
         for (int c = 0; c < nchunks; ++c, ++gc) {
           int const buf = gc & 1;
-          mbar_wait(&tmem_empty_bar[buf], ((gc >> 1) & 1) ^ 1);
+          if (prm.ts) { long long const t0 = clock64(); mbar_wait(&tmem_empty_bar[buf], ((gc >> 1) & 1) ^ 1); w_tmem += clock64() - t0; } else { mbar_wait(&tmem_empty_bar[buf], ((gc >> 1) & 1) ^ 1); }
           tc_fence_after();
           uint32_t const tmem_d = tmem_base + buf * kBufCols;
           int const i_end = min(i + chunk, nkb);
@@ -161,12 +166,13 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
             int const s = it % kStages;
             uint32_t const ph = (it / kStages) & 1;
             int const nh = min(kKb, nkb - i);
-            mbar_wait(&full_bar[s], ph);
+            if (prm.debug & 1) {}  // experiments: MMA on whatever the shared memory holds
+            else if (prm.ts) { long long const t0 = clock64(); mbar_wait(&full_bar[s], ph); long long const t1 = clock64(); if (it == 0) { t_first_full = t1 - t_begin; } else { w_full += t1 - t0; } } else { mbar_wait(&full_bar[s], ph); }
             tc_fence_after();
             uint32_t const st = smem_u32(smem + s * Cfg::kStageBytes);
             int nk[kKb];
 #pragma unroll
-            for (int j = 0; j < kKb; ++j) { nk[j] = IGEMM_BK / IGEMM_UMMA_K; if (j < nh && ++kb_in_grp == kb_mod) { kb_in_grp = 0; nk[j] = ksteps_last; } }
+            for (int j = 0; j < kKb; ++j) { nk[j] = IGEMM_BK / IGEMM_UMMA_K; if (j < nh && ++kb_in_grp == kb_mod) { kb_in_grp = 0; nk[j] = ksteps_last; } if (prm.debug & 2) { nk[j] = 0; } }  // (debug bit 1: barrier traffic only)
             if (elect_one_sync()) {
               if (kPlanes == 2) {
                 issue_kblock<2, true>(tmem_d, tmem_x, sw128_desc_lo(st), sw128_desc_lo(st + kPBytes), sw128_desc_lo(st + 2 * kPBytes),
@@ -188,6 +194,7 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
           }
         }
       }
+      if (prm.ts && lane == 0) { long long *t = prm.ts + cluster_id * 16; t[2] = clock64() - t_begin; t[3] = w_full; t[4] = w_tmem; t[5] = t_first_full; t[6] = it; }
     }
   } else {
     // ===================== epilogue warps (each CTA: its own 128 rows) =====================
@@ -202,6 +209,8 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
       if (blockIdx.x == 0 && row == 0) { prm.out16_scale2[0] = s_out; prm.out16_scale2[1] = 1.0f / s_out; }
     }
     int gc = 0, ti = 0;
+    long long const t_begin = prm.ts ? clock64() : 0;
+    long long w_acc = 0, t_drain = 0, t_store = 0;
     for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++ti) {
       int const mt = tile / q_tiles, nt = tile - mt * q_tiles;
       int const m0 = (mt * 2 + static_cast<int>(cta_rank)) * IGEMM_BM, n0 = nt * BN;
@@ -220,7 +229,8 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
       }
       for (int c = 0; c < nchunks; ++c, ++gc) {
         int const buf = gc & 1;
-        mbar_wait(&tmem_full_bar[buf], (gc >> 1) & 1);
+        long long t0 = 0;
+        if (prm.ts) { t0 = clock64(); mbar_wait(&tmem_full_bar[buf], (gc >> 1) & 1); long long const t1 = clock64(); w_acc += t1 - t0; t0 = t1; } else { mbar_wait(&tmem_full_bar[buf], (gc >> 1) & 1); }
         tc_fence_after();
         uint32_t const taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kBufCols;
 #pragma unroll
@@ -234,7 +244,9 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { if (leader) { mbar_arrive(&tmem_empty_bar[buf]); } else { mbar_arrive_remote(&tmem_empty_bar[buf], 0); } }
+        if (prm.ts) { t_drain += clock64() - t0; }
       }
+      long long const t_st0 = prm.ts ? clock64() : 0;
       if (kPlanes == 2) {  // the last chunk's commit also covered every cross-term MMA of this tile
         tc_fence_after();
         uint32_t const xaddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (2 + (ti & 1)) * kBufCols;
@@ -261,7 +273,9 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
           else { igemm_store_row_bf16<BN>(acc, inv, bias_t, floor_v, prm.out16 + o16, prm.q_rows - n0); }
         }
       }
+      if (prm.ts) { t_store += clock64() - t_st0; }
     }
+    if (prm.ts && leader && warp_id == 2 && lane == 0) { long long *t = prm.ts + cluster_id * 16; t[8] = clock64() - t_begin; t[9] = w_acc; t[10] = t_drain; t[11] = t_store; t[12] = ti; }
     if (prm.out_absmax) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) { amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o)); }
