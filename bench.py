@@ -301,15 +301,37 @@ def main():
     extra = os.environ.get("B200_FWD_OPTS", "")  # e.g. "use_2cta=0,use_graph=0" for A/B experiments
     fwd = bb.B200ConvFwd(txt, "(prec=%s,device=%d%s)" % (args.prec, local_rank, ("," + extra) if extra else ""))
 
-    # ---- weights: rank 0 synthesises, one NCCL broadcast over NVLink distributes (north_star: "single NCCL broadcast of weights")
+    # ---- weights: rank 0 synthesises; ONE NCCL broadcast of a flat DEVICE buffer over NVLink (north_star: "single NCCL broadcast of weights"),
+    # issued through the C ABI (b200_shard_broadcast); every rank then slices it into its parameter vars device-to-device
     from boda_b200 import shard
     shapes = nets.conv_param_shapes(txt)
+    sh = None
     if world > 1:
-        params = shard.broadcast_params(dist, shapes, nets.synth_params(txt) if rank == 0 else None, device="cuda")
+        def exchange(obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+        sh = bb.B200Shard(local_rank, rank, world)
+        sh.nccl_init(exchange)
+        layout = shard.param_layout(shapes)
+        total = layout[-1][1] + layout[-1][2]
+        flat = torch.empty(total, dtype=torch.float32, device="cuda")
+        if rank == 0:
+            params0 = nets.synth_params(txt)
+            host = np.empty(total, np.float32)
+            for n, off, sz, shape in layout:
+                host[off:off + sz] = np.asarray(params0[n], np.float32).ravel()
+            flat.copy_(torch.from_numpy(host))
+        torch.cuda.synchronize()
+        sh.broadcast(flat.data_ptr(), total * 4, 0, 0)
+        torch.cuda.synchronize()
+        for n, off, sz, shape in layout:
+            fwd.set_param_device(n, flat.data_ptr() + 4 * off, sz)
+        del flat
     else:
         params = nets.synth_params(txt)
-    for n in sorted(shapes):
-        fwd.set_param(n, params[n])
+        for n in sorted(shapes):
+            fwd.set_param(n, params[n])
 
     # ---- inputs: each rank owns its shard of the global batch (images [rank*B, (rank+1)*B)), pinned host memory
     x_host = torch.from_numpy(nets.synth_input((B, 3, NET_IN_SZ, NET_IN_SZ), seed=rank)).pin_memory()
@@ -337,8 +359,11 @@ def main():
     class _DevView:
         def __init__(self, ptr, shape):
             self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
-    logits_dev = torch.as_tensor(_DevView(fwd.node_device_ptr(out_node), (B, 1000)), device="cuda")
-    gathered = torch.empty((world * B, 1000), dtype=torch.float32, device="cuda") if world > 1 else None
+    n_logits = int(np.prod(fwd.node_dims(out_node)[1:]))
+    logits_dev = torch.as_tensor(_DevView(fwd.node_device_ptr(out_node), (B, n_logits)), device="cuda")
+    gathered = None
+    if world > 1:  # every rank's gather buffer [world][B * n_logits] is mapped by its peers (CUDA IPC): logits are written into it over NVLink by one small kernel
+        sh.gather_setup(B * n_logits * 4, exchange)
 
     sampler = ClockSampler(local_rank)
 
@@ -353,8 +378,18 @@ def main():
         e2e_step()
     e2e_pipelined(args.warmup)
     fwd.run_timed(args.warmup, L2_FLUSH_BYTES)
-    if dist:
-        shard.gather_logits(dist, logits_dev, out=gathered)
+    if dist:  # one checked gather: every rank must see every rank's logits, image order = rank order
+        st_ptr = fwd.stream_ptr()
+        fwd.enqueue()
+        step = sh.gather_push(fwd.node_device_ptr(out_node), st_ptr)
+        sh.gather_wait(step, st_ptr)
+        barrier()
+        ref = torch.empty((world * B, n_logits), dtype=torch.float32, device="cuda")
+        dist.all_gather_into_tensor(ref, logits_dev.contiguous())
+        torch.cuda.synchronize()
+        gathered = torch.as_tensor(_DevView(sh.gather_ptr(step), (world * B, n_logits)), device="cuda")
+        if not torch.equal(ref, gathered):
+            raise RuntimeError("peer-memory logits gather disagrees with the NCCL all-gather of the same data")
     barrier()
 
     sampler.start()
@@ -364,42 +399,47 @@ def main():
     if world == 1:
         ms_each = fwd.run_timed(args.steps, L2_FLUSH_BYTES)
         dev_ms = float(sum(ms_each))
-    elif os.environ.get("B200_BENCH_SERIAL_GATHER", "0") == "1":
-        # A/B: forward (events on the back-end's stream), then the NCCL all-gather of its logits (events on torch's stream), host-synchronised
+    elif os.environ.get("B200_BENCH_GATHER", "peer") == "nccl":
+        # A/B: the round-1 form -- forward (events on the back-end's stream), then the NCCL all-gather of its logits, host-synchronised
         dev_ms = 0.0
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for _ in range(args.steps):
             dev_ms += fwd.run_timed(1, L2_FLUSH_BYTES)[0]
             ev0.record()
-            shard.gather_logits(dist, logits_dev, out=gathered)
+            shard.gather_logits(dist, logits_dev, out=ref)
             ev1.record()
             ev1.synchronize()
             dev_ms += ev0.elapsed_time(ev1)
     else:
-        # Serving pipeline: the NCCL all-gather of batch i-1's logits runs on NCCL's stream while batch i's forward runs on the back-end's
-        # stream. K forwards + K gathers = K+1 event-bracketed windows on the back-end's stream (the first has no gather, the last no
-        # forward); a window closes only after both its forward and its gather have finished, the L2 flush sits between windows, and
-        # the gather is issued after the window's opening event so none of it hides under the flush.
+        # Serving pipeline on ONE stream (the back-end's): step i = forward i, push of its logits into every rank's gather buffer, then the wait
+        # for the logits of step i-1 from all ranks (one step late, so a rank never idles on its slowest peer inside a step). K forwards +
+        # K gathers = K+1 event-bracketed windows (the first has no wait, the last no forward), the L2 flush sits between windows.
         s_fwd = torch.cuda.ExternalStream(fwd.stream_ptr(), device=torch.device("cuda", local_rank))
-        pipe = shard.GatherPipeline(dist, logits_dev)
+        st_ptr = fwd.stream_ptr()
+        out_ptr = fwd.node_device_ptr(out_node)
         windows = []
+        sh_launches0 = sh.launches()
         torch.cuda.synchronize()
         with torch.cuda.stream(s_fwd):
+            prev_step = None
             for i in range(args.steps + 1):
                 fwd.flush_l2(L2_FLUSH_BYTES)
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
-                pipe.begin_step(i)  # async all-gather of batch i-1's staged logits
+                step = None
                 if i < args.steps:
                     fwd.enqueue()
-                    pipe.stage(i, logits_dev)
-                pipe.end_step()  # stream-level join: the back-end's stream waits for the gather
+                    step = sh.gather_push(out_ptr, st_ptr)
+                if prev_step is not None:
+                    sh.gather_wait(prev_step, st_ptr)
+                prev_step = step
                 ev1.record()
                 windows.append((ev0, ev1))
             s_fwd.synchronize()
         dev_ms = float(sum(a.elapsed_time(b) for a, b in windows))
+        shard_launches = sh.launches() - sh_launches0
     barrier()
-    launches = fwd.launches() - launches0
+    launches = fwd.launches() - launches0 + (shard_launches if world > 1 and os.environ.get("B200_BENCH_GATHER", "peer") != "nccl" else 0)
     if dist:
         dev_ms = shard.max_over_ranks(dist, dev_ms, device="cuda")
 
@@ -448,7 +488,8 @@ def main():
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp32": "f32 (fp16 hi/lo split, 3 tcgen05.mma per k-step, fp32 accumulate)", "fp16": "f16", "bf16": "bf16"}[args.prec], "data": "synthetic",
             "config": {"workload": "nets/%s fwd, batch=%d per GPU, %s, %dx%d%s" % (args.net, B, args.prec, NET_IN_SZ, NET_IN_SZ, " (BASELINE configs[1])" if (args.net, B, args.prec) == ("alexnet_ng_conv", 32, "fp32") else ""), "global_batch": global_batch,
-                       "parallelism": "batch-shard x%d, NCCL weight broadcast at init + logits all-gather per step (issued one step late, beside the next forward)" % world if world > 1 else "single GPU",
+                       "parallelism": ("batch-shard x%d, one NCCL broadcast of the weights at init (device-resident) + per-step logits gather into every rank's peer-mapped buffer "
+                                       "over NVLink (b200_shard_gather_push / _wait, awaited one step late)" % world) if world > 1 else "single GPU",
                        "l2": "256 MiB scratch buffer overwritten before every timed step (outside the events)", "cuda_graph": True},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": in_elems * 4, "d2h_bytes_per_step": out_elems * 4, "ms_per_step": 1e3 * e2e_s / args.steps,
                     "api": "b200_fwd_submit / b200_fwd_wait (pipelined run_fwd, depth 2: H2D of batch i+1 overlaps the forward of batch i)",

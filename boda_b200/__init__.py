@@ -86,6 +86,19 @@ _SIGS = {
     "b200_fwd_flush_l2": (_c.c_int, [_c.c_void_p, _c.c_uint64]),
     "b200_fwd_get_node_raw_native_pointer": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.POINTER(_c.c_void_p)]),
     "b200_rtc_get_kernel_dur": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.POINTER(_c.c_float)]),
+    "b200_fwd_set_param_device": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_void_p, _c.c_uint64]),
+    "b200_shard_create": (_c.c_void_p, [_c.c_int, _c.c_int, _c.c_int]),
+    "b200_shard_destroy": (None, [_c.c_void_p]),
+    "b200_shard_nccl_unique_id": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
+    "b200_shard_nccl_init": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
+    "b200_shard_broadcast": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_uint64, _c.c_int, _c.c_void_p]),
+    "b200_shard_gather_export": (_c.c_int, [_c.c_void_p, _c.c_uint64, _c.c_void_p]),
+    "b200_shard_gather_import": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
+    "b200_shard_gather_push": (_c.c_int64, [_c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    "b200_shard_gather_wait": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_void_p]),
+    "b200_shard_gather_ptr": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.POINTER(_c.c_void_p)]),
+    "b200_shard_all_gather_nccl": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_uint64, _c.c_void_p]),
+    "b200_shard_launches": (_c.c_uint64, [_c.c_void_p]),
 }
 ABI_SYMBOLS = tuple(_SIGS)
 
@@ -395,6 +408,10 @@ class B200ConvFwd:
         a = np.ascontiguousarray(arr, np.float32)
         _chk(lib().b200_fwd_set_param(self._h, _b(name), a.ctypes.data_as(_c.c_void_p), a.size))
 
+    def set_param_device(self, name: str, dev_ptr: int, n_elems: int):
+        """Parameter upload from a device buffer (a slice of the flat buffer the weights were broadcast in): no host round trip."""
+        _chk(lib().b200_fwd_set_param_device(self._h, _b(name), _c.c_void_p(dev_ptr), n_elems))
+
     def run_fwd(self, to_set: Dict[str, np.ndarray], to_get: Sequence[str], out_bufs: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
         """has_conv_fwd_t::run_fwd(to_set_vns, fwd, to_get_vns): host fp32 NCHW in, host out, synchronous."""
         sn = list(to_set)
@@ -479,3 +496,63 @@ class B200ConvFwd:
         p = _c.c_void_p()
         _chk(lib().b200_fwd_get_node_raw_native_pointer(self._h, _b(name), ctypes.byref(p)))
         return int(p.value or 0)
+
+
+class B200Shard:
+    """One process's end of the batch-sharded forward (include/boda_b200.h, `b200_shard_*`): the NCCL communicator for the
+    one weight broadcast and the peer-mapped gather buffers for the per-step logits gather. `exchange(obj) -> [obj of rank 0, 1, ...]` is the
+    caller's transport for the rendezvous bytes (e.g. torch.distributed.all_gather_object)."""
+
+    def __init__(self, device: int, rank: int, world: int):
+        self.rank, self.world = rank, world
+        self._h = lib().b200_shard_create(device, rank, world)
+        if not self._h:
+            raise RtException(lib().b200_last_error().decode())
+
+    def close(self):
+        if self._h:
+            lib().b200_shard_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def nccl_init(self, exchange):
+        idb = (_c.c_ubyte * 128)()
+        if self.rank == 0:
+            _chk(lib().b200_shard_nccl_unique_id(self._h, idb))
+        got = exchange(bytes(idb))[0]
+        buf = (_c.c_ubyte * 128).from_buffer_copy(got)
+        _chk(lib().b200_shard_nccl_init(self._h, buf))
+
+    def broadcast(self, dev_ptr: int, nbytes: int, root: int = 0, stream: int = 0):
+        _chk(lib().b200_shard_broadcast(self._h, _c.c_void_p(dev_ptr), nbytes, root, _c.c_void_p(stream)))
+
+    def gather_setup(self, bytes_per_rank: int, exchange):
+        """Allocate the local gather buffer, swap IPC handles, map every peer's buffer."""
+        h = (_c.c_ubyte * 64)()
+        _chk(lib().b200_shard_gather_export(self._h, bytes_per_rank, h))
+        allh = exchange(bytes(h))
+        flat = (_c.c_ubyte * (64 * self.world)).from_buffer_copy(b"".join(allh))
+        _chk(lib().b200_shard_gather_import(self._h, flat))
+
+    def gather_ptr(self, step: int) -> int:
+        """Device pointer of the local [world][bytes_per_rank] result of `step` (valid once gather_wait(step) has run on the stream)."""
+        p = _c.c_void_p()
+        _chk(lib().b200_shard_gather_ptr(self._h, step, _c.byref(p)))
+        return int(p.value)
+
+    def gather_push(self, dev_src: int, stream: int) -> int:
+        return _chk(lib().b200_shard_gather_push(self._h, _c.c_void_p(dev_src), _c.c_void_p(stream)))
+
+    def gather_wait(self, step: int, stream: int):
+        _chk(lib().b200_shard_gather_wait(self._h, step, _c.c_void_p(stream)))
+
+    def all_gather_nccl(self, dev_src: int, dev_dst: int, bytes_per_rank: int, stream: int):
+        _chk(lib().b200_shard_all_gather_nccl(self._h, _c.c_void_p(dev_src), _c.c_void_p(dev_dst), bytes_per_rank, _c.c_void_p(stream)))
+
+    def launches(self) -> int:
+        return int(lib().b200_shard_launches(self._h))

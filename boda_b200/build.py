@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libboda_b200.so")
-SOURCES = ["b200_compute.cu", "b200_conv_fwd.cu", "caffe_prototxt.cu", "wisdom.cu", "b200_abi.cu"]
+SOURCES = ["b200_compute.cu", "b200_conv_fwd.cu", "caffe_prototxt.cu", "wisdom.cu", "b200_shard.cu", "b200_abi.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden",
          "-ccbin", "g++", "--expt-relaxed-constexpr", "-Xptxas", "-v" if os.environ.get("B200_PTXAS_V") else "-warn-spills"]

@@ -3,12 +3,14 @@
 #include "b200_conv_fwd.h"
 #include "caffe_prototxt.h"
 #include "wisdom.h"
+#include "b200_shard.h"
 #include <cstdio>
 
 using namespace boda;
 
 struct b200_rtc { p_b200_compute_t rtc; string tmp; };
 struct b200_fwd { shared_ptr<b200_conv_fwd_t> fwd; string tmp; };
+struct b200_shard { shared_ptr<b200_shard_t> sh; };
 
 namespace {
 thread_local string g_last_error;
@@ -314,4 +316,32 @@ B200_API int b200_fwd_get_node_raw_native_pointer(b200_fwd *f, const char *node_
 }
 B200_API int b200_rtc_get_kernel_dur(b200_rtc *r, uint32_t id, float *ms_out) { return guarded_dev(r, [&] { *ms_out = r->rtc->get_kernel_dur(id); return 0; }); }
 
+
+/* ---- batch sharding over the GPUs of one box ---- */
+B200_API b200_shard *b200_shard_create(int device, int rank, int world) {
+  b200_shard *s = nullptr;
+  guarded([&] { s = new b200_shard; try { s->sh = std::make_shared<b200_shard_t>(device, rank, world); } catch (...) { delete s; s = nullptr; throw; } return 0; });
+  return s;
+}
+B200_API void b200_shard_destroy(b200_shard *s) { guarded([&] { delete s; return 0; }); }
+B200_API int b200_shard_nccl_unique_id(b200_shard *s, void *id_out_128) { return guarded([&] { s->sh->nccl_unique_id(id_out_128); return 0; }); }
+B200_API int b200_shard_nccl_init(b200_shard *s, const void *id_128) { return guarded([&] { s->sh->nccl_init(id_128); return 0; }); }
+B200_API int b200_shard_broadcast(b200_shard *s, void *dev_buf, uint64_t bytes, int root, void *stream) { return guarded([&] { s->sh->broadcast(dev_buf, bytes, root, stream); return 0; }); }
+B200_API int b200_shard_all_gather_nccl(b200_shard *s, const void *dev_src, void *dev_dst, uint64_t bytes_per_rank, void *stream) {
+  return guarded([&] { s->sh->all_gather_nccl(dev_src, dev_dst, bytes_per_rank, stream); return 0; });
+}
+B200_API int b200_shard_gather_export(b200_shard *s, uint64_t bytes_per_rank, void *ipc_handle_out_64) { return guarded([&] { s->sh->gather_export(bytes_per_rank, ipc_handle_out_64); return 0; }); }
+B200_API int b200_shard_gather_import(b200_shard *s, const void *ipc_handles) { return guarded([&] { s->sh->gather_import(ipc_handles); return 0; }); }
+B200_API int64_t b200_shard_gather_push(b200_shard *s, const void *dev_src, void *stream) {
+  int64_t step = -1;
+  int const rc = guarded([&] { step = s->sh->gather_push(dev_src, stream); return 0; });
+  return rc < 0 ? rc : step;
+}
+B200_API int b200_shard_gather_wait(b200_shard *s, uint32_t step, void *stream) { return guarded([&] { s->sh->gather_wait(step, stream); return 0; }); }
+B200_API int b200_shard_gather_ptr(b200_shard *s, uint32_t step, void **dev_ptr_out) { return guarded([&] { *dev_ptr_out = s->sh->gather_ptr(step); if (!*dev_ptr_out) { rt_err("b200_shard: no gather buffer yet"); } return 0; }); }
+B200_API uint64_t b200_shard_launches(b200_shard *s) { return s->sh->n_launches; }
+/* parameter upload from a DEVICE buffer (the slice of the broadcast flat buffer): no host round trip */
+B200_API int b200_fwd_set_param_device(b200_fwd *f, const char *node_name, const void *dev_src, uint64_t n_elems) {
+  return guarded_dev(f, [&] { f->fwd->set_param_device(node_name, dev_src, n_elems); return 0; });
+}
 }  // extern "C"

@@ -5,6 +5,7 @@
 #include "igemm.cuh"
 #include "igemm2.cuh"
 #include "igemm3.cuh"
+#include "igemm4.cuh"
 #include "pointwise.cuh"
 #include <cudaTypedefs.h>
 #include <cuda_profiler_api.h>
@@ -180,6 +181,84 @@ cluster_choice_t choose_cluster(int p_tiles, int q_tiles, int BN, int planes, bo
   return best;
 }
 
+
+// ---- launch plan of the round-2 kernel (igemm4.cuh) ----------------------------------------------------------------------------------------
+struct sk4_plan_t {
+  bool use = false, halo = false, sk = false;
+  int BN = 0, a_stages = 0, b_stages = 0;
+  int halo_rows = 0, a_loads = 0, a_box_rows = 0, Hp = 0, Wp = 0;
+  long long m_rows = 0;  // halo: virtual pixels that may hold an output
+  int m_pair_tiles = 0, q_tiles = 0, n_tiles = 0, ukb = 0, n_pairs = 0;
+  size_t smem = 0;
+};
+
+sk4_plan_t plan_sk4(conv_plan_t const &cp, int planes, int num_sms, b200_compute_t const &rtc) {
+  sk4_plan_t sp;
+  if (!rtc.use_sk4 || !rtc.use_2cta || num_sms < 2) { return sp; }
+  long long const pixels = (long long)cp.N * cp.OH * cp.OW;
+  // halo mode: stride 1, window > 1x1, padding no larger than the window overhang, an acceptable share of dropped virtual pixels
+  if (rtc.use_halo && cp.im2col && !cp.rowmerge && !cp.swapped && cp.sx == 1 && cp.sy == 1 && cp.KH * cp.KW > 1 && cp.px <= cp.KW - 1 && cp.py <= cp.KH - 1) {
+    int const Hp = cp.H + cp.py, Wp = cp.W + cp.px;
+    double const waste = (double)Hp * Wp / ((double)cp.OH * cp.OW);
+    int halo_rows = (int)round_up(128 + (long long)(cp.KH - 1) * Wp + cp.KW - 1, 8);
+    if (waste <= 1.5 && halo_rows <= 768 && (long long)cp.N * Hp * Wp < (1ll << 31)) {
+      sp.halo = true; sp.Hp = Hp; sp.Wp = Wp;
+      sp.a_loads = ceil_div(halo_rows, 256); sp.a_box_rows = (int)round_up(ceil_div(halo_rows, sp.a_loads), 8);
+      sp.halo_rows = sp.a_loads * sp.a_box_rows;
+      sp.m_rows = (long long)(cp.N - 1) * Hp * Wp + (long long)(cp.OH - 1) * Wp + cp.OW;
+    }
+  }
+  int const kKb = planes == 1 ? 2 : 1;
+  for (int attempt = 0; attempt < 2; ++attempt) {  // second attempt: without the halo mode (its rings did not fit shared memory)
+    long long const p_rows = cp.swapped ? cp.OC : (sp.halo ? sp.m_rows : pixels), q_rows = cp.swapped ? pixels : cp.OC;
+    int const p_tiles = ceil_div(p_rows, b200::IGEMM_BM);
+    if (p_tiles < 2) { return sk4_plan_t(); }
+    if (cp.swapped) { sp.BN = cp.BN; }
+    else {  // tile width over out_chans: least padding, where an MMA narrower than 64 columns costs the issue slot of a 64-wide one; ties -> wider
+      long long best_cost = 0;
+      for (int bn : {128, 96, 64, 32}) {
+        long long const cost = (long long)ceil_div(cp.OC, bn) * std::max(bn, 64);
+        if (!sp.BN || cost < best_cost) { sp.BN = bn; best_cost = cost; }
+      }
+    }
+    long long const avail = 225 * 1024 - 1024 - b200::SK4_BAR_BYTES, b_stage = (long long)sp.BN * 128;
+    if (sp.halo) {
+      long long const a_stage = (long long)planes * sp.halo_rows * 128;
+      sp.a_stages = 0;
+      for (int as : {2, 1}) {
+        long long const bs = std::min<long long>((avail - as * a_stage) / b_stage, b200::SK4_MAX_B_STAGES);
+        if (bs >= (as == 2 ? 4 : 3)) { sp.a_stages = as; sp.b_stages = (int)bs; break; }
+      }
+      if (sp.a_stages == 2 && sp.b_stages == b200::SK4_MAX_B_STAGES && avail - 3 * a_stage >= b200::SK4_MAX_B_STAGES * b_stage) { sp.a_stages = 3; }
+      if (rtc.sk4_max_b_stages > 0) { sp.b_stages = std::min(sp.b_stages, rtc.sk4_max_b_stages); }
+      if (!sp.a_stages) { sp.halo = false; sp.BN = 0; continue; }
+      sp.smem = (size_t)(sp.a_stages * a_stage + sp.b_stages * b_stage + 1024 + b200::SK4_BAR_BYTES);
+    } else {
+      long long const stage = 2ll * b200::IGEMM_BM * 128 + b_stage;
+      sp.b_stages = (int)std::min<long long>(avail / stage, b200::SK4_MAX_A_STAGES);  // modes 0/1: the P slots ride on the Q stages (ring depths are equal)
+      sp.a_stages = sp.b_stages;
+      if (sp.b_stages < 2) { return sk4_plan_t(); }
+      sp.smem = (size_t)(sp.b_stages * stage + 1024 + b200::SK4_BAR_BYTES);
+    }
+    sp.m_pair_tiles = ceil_div(p_tiles, 2); sp.q_tiles = ceil_div(q_rows, sp.BN);
+    sp.n_tiles = sp.m_pair_tiles * sp.q_tiles;
+    int const nkb = sp.halo ? cp.cblks * cp.KH * cp.KW : cp.kblks_total;
+    sp.ukb = ceil_div(nkb, kKb);
+    int const P = num_sms / 2;
+    long long const U = (long long)sp.n_tiles * sp.ukb;
+    // whole tiles cost ceil(tiles / pairs) rounds of ukb stage-units; stream-K costs U / pairs units (>= 2 per pair) plus about two units' worth of
+    // partial-tile hand-off (a 64 KB write + read per split tile). Stream-K when that is at least 8 % faster.
+    int const pairs_sk = (int)std::min<long long>(P, U / 2);
+    double const dp_time = (double)ceil_div(sp.n_tiles, P) * sp.ukb, sk_time = pairs_sk > 0 ? (double)ceil_div(U, pairs_sk) + 2.0 : 1e30;
+    if (U * (P + 1) >= (1ll << 31)) { return sk4_plan_t(); }  // the kernel's range arithmetic is 32-bit
+    sp.sk = rtc.use_streamk && pairs_sk >= 2 && (sk_time < 0.92 * dp_time || rtc.use_streamk == 2) && sp.BN <= 128;  // (use_streamk=2: always, for tests)
+    sp.n_pairs = sp.sk ? pairs_sk : std::min(sp.n_tiles, P);
+    sp.use = true;
+    return sp;
+  }
+  return sk4_plan_t();
+}
+
 }  // namespace
 
 struct b200_impl_t {
@@ -187,7 +266,10 @@ struct b200_impl_t {
   map<string, func_t> funcs;
   // NHWC 16-bit planes of activation vars, shared by every Convolution that reads the same var (the four branches of an inception module, the
   // shortcut + first 1x1 of a ResNet block): the first consumer of a write generation packs, the others reuse. Keyed by the storage pointer.
-  map<void const *, packed_t> act_packs;
+  // (second key: 0 = plain NHWC [pixel][chan]; pad_tag(py, px) = the shared-padding layout a halo-mode convolution reads, igemm4.cuh)
+  map<std::pair<void const *, uint32_t>, packed_t> act_packs;
+  static uint32_t pad_tag(int py, int px) { return 1u + (uint32_t)py * 256u + (uint32_t)px; }
+  p_dev_buf_t sk_ws, sk_flags;  // stream-K partial-tile workspace + hand-off flags of igemm_sk4_kernel (one launch at a time per stream)
   vector<call_ev_t> calls;
   cudaStream_t stream = nullptr;
   bool inited = false, timing = true;
@@ -227,6 +309,10 @@ bool b200_compute_t::set_option(string const &k, string const &v) {
   else if (k == "use_clusters") { use_clusters = std::stoi(v); }
   else if (k == "use_2cta") { use_2cta = std::stoi(v); }
   else if (k == "debug_flags") { debug_flags = std::stoi(v); }
+  else if (k == "use_sk4") { use_sk4 = std::stoi(v); }
+  else if (k == "use_halo") { use_halo = std::stoi(v); }
+  else if (k == "use_streamk") { use_streamk = std::stoi(v); }
+  else if (k == "sk4_max_b_stages") { sk4_max_b_stages = std::stoi(v); }
   else if (k == "device") { device = std::stoi(v); }
   else if (k == "plan_only") { plan_only = std::stoi(v); }
   else if (k == "plan_num_sms") { plan_num_sms = std::stoi(v); }
@@ -297,7 +383,9 @@ void b200_compute_t::create_var_with_dims_as_reshaped_view_of_var(string const &
 }
 void b200_compute_t::release_var(string const &vn) {
   var_info_t &v = impl->must_var(vn);
-  if (v.buf && v.buf.use_count() == 1) { impl->act_packs.erase(v.buf->p); }  // last name of this storage: drop its packed planes too
+  if (v.buf && v.buf.use_count() == 1) {  // last name of this storage: drop its packed planes too (every layout)
+    for (auto i = impl->act_packs.begin(); i != impl->act_packs.end();) { if (i->first.first == v.buf->p) { i = impl->act_packs.erase(i); } else { ++i; } }
+  }
   impl->vars.erase(vn);
 }
 dims_t b200_compute_t::get_var_dims(string const &vn) { return impl->must_var(vn).dims; }
@@ -512,6 +600,12 @@ string b200_compute_t::func_plan_text(string const &fn) const {
   if (fi->second.kind != FK_CONV) { return string(); }
   conv_plan_t const &cp = fi->second.cp;
   long long const pixels = (long long)cp.N * cp.OH * cp.OW;
+  sk4_plan_t const sp = plan_sk4(cp, prec == B200_PREC_FP32_SPLIT ? 2 : 1, impl->num_sms, *this);
+  if (sp.use) {  // the round-2 kernel: what run() launches, without launching it
+    return string("kernel=sk4 mode=") + (sp.halo ? "halo" : cp.im2col ? "im2col" : "2d") + " bn=" + str(sp.BN) + " kblks=" + str(sp.halo ? cp.cblks * cp.KH * cp.KW : cp.kblks_total) +
+           " tiles=" + str(sp.n_tiles) + " streamk=" + str((int)sp.sk) + " a_stages=" + str(sp.a_stages) + " b_stages=" + str(sp.b_stages) + " splits=1 swapped=" + str((int)cp.swapped) +
+           " rowmerge=" + str((int)cp.rowmerge) + " im2col=" + str((int)cp.im2col) + " grid=" + str(2 * sp.n_pairs) + "x1x1";
+  }
   int const p_rows_n = cp.swapped ? cp.OC : (int)pixels, q_rows_n = cp.swapped ? (int)pixels : cp.OC;
   int const p_tiles = ceil_div(p_rows_n, b200::IGEMM_BM), q_tiles = ceil_div(q_rows_n, cp.BN);
   bool const two_cta = use_2cta && !cp.swapped && cp.splits == 1 && p_tiles >= 2;  // the rule of run_conv
@@ -520,6 +614,21 @@ string b200_compute_t::func_plan_text(string const &fn) const {
   else { grid = str(p_tiles) + "x" + str(q_tiles) + "x" + str(cp.splits); }
   return string("kernel=") + (two_cta ? "pair" : "single") + " bn=" + str(cp.BN) + " kblks=" + str(cp.kblks_total) + " splits=" + str(cp.splits) + " swapped=" + str((int)cp.swapped) +
          " rowmerge=" + str((int)cp.rowmerge) + " im2col=" + str((int)cp.im2col) + " grid=" + grid;
+}
+// the shared-padding plane layout (py, px) this convolution's halo mode reads its input in; false = it reads plain NHWC planes
+bool b200_compute_t::conv_halo_pad(op_base_t const &op, int &py, int &px) {
+  conv_plan_t cp;
+  plan_conv(cp, op, impl->num_sms);
+  sk4_plan_t const sp = plan_sk4(cp, prec == B200_PREC_FP32_SPLIT ? 2 : 1, impl->num_sms, *this);
+  if (!sp.use || !sp.halo) { return false; }
+  py = cp.py; px = cp.px;
+  return true;
+}
+// whether this convolution is run by the round-2 kernel (which can write its consumers' planes in the shared-padding layout)
+bool b200_compute_t::conv_uses_sk4(op_base_t const &op) {
+  conv_plan_t cp;
+  plan_conv(cp, op, impl->num_sms);
+  return plan_sk4(cp, prec == B200_PREC_FP32_SPLIT ? 2 : 1, impl->num_sms, *this).use;
 }
 bool b200_compute_t::conv_plane_writable(op_base_t const &op, bool dst_is_concat) {
   conv_plan_t cp;
@@ -627,6 +736,10 @@ struct run_ctx_t {
     if (c_inner <= 0) { c_inner = std::max(Cc, 1); }
     uint64_t const lkey = pack_layout_key({B, R, Cc, Rpad, dst_c_stride, dst_b_stride, c_inner, dst_chi_stride, dst_base, want_lo, bf16, smallc_W, kmajor_rows});
     if (pk.src_gen == *src.gen && pk.src_ptr == src.buf->p && pk.hi && pk.layout_key == lkey && (!want_lo || pk.lo)) { return; }
+    if (pk.hi && pk.layout_key != lkey && pk.hi->bytes >= (uint64_t)total_elems * 2 && (!want_lo || pk.lo)) {  // same storage, other geometry: padding positions must be zero again
+      CU_CHK(cudaMemsetAsync(pk.hi->p, 0, pk.hi->bytes, st));
+      if (pk.lo) { CU_CHK(cudaMemsetAsync(pk.lo->p, 0, pk.lo->bytes, st)); }
+    }
     pk.layout_key = lkey;
     if (!pk.hi || pk.hi->bytes < (uint64_t)total_elems * 2 || (want_lo && !pk.lo)) {
       pk.hi = std::make_shared<dev_buf_t>(total_elems * 2);
@@ -732,6 +845,34 @@ struct run_ctx_t {
     cfg.numAttrs = rtc.use_pdl ? 2 : 1;
     CU_CHK(cudaLaunchKernelEx(&cfg, b200::igemm_umma_2cta_kernel<BN, kPlanes>, ph, pl, qh, ql, prm));
     launched();
+  }
+  template <int BN, int kPlanes>
+  void launch_sk4_t(sk4_plan_t const &sp, CUtensorMap const &ph, CUtensorMap const &pl, CUtensorMap const &qh, CUtensorMap const &ql, b200::Sk4Params const &prm) {
+    static uint64_t attr_set = 0;
+    if (first_use_on_device(attr_set, rtc.device)) {
+      CU_CHK(cudaFuncSetAttribute(b200::igemm_sk4_kernel<BN, kPlanes>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * sp.n_pairs, 1, 1);
+    cfg.blockDim = dim3(b200::IGEMM_THREADS);
+    cfg.dynamicSmemBytes = sp.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = rtc.use_pdl ? 2 : 1;
+    CU_CHK(cudaLaunchKernelEx(&cfg, b200::igemm_sk4_kernel<BN, kPlanes>, ph, pl, qh, ql, prm));
+    launched();
+  }
+  void launch_sk4(int BN, int planes, sk4_plan_t const &sp, CUtensorMap const &ph, CUtensorMap const &pl, CUtensorMap const &qh, CUtensorMap const &ql, b200::Sk4Params const &prm) {
+    if (planes == 2) {
+      if (BN == 128) { launch_sk4_t<128, 2>(sp, ph, pl, qh, ql, prm); } else if (BN == 96) { launch_sk4_t<96, 2>(sp, ph, pl, qh, ql, prm); } else if (BN == 64) { launch_sk4_t<64, 2>(sp, ph, pl, qh, ql, prm); } else { launch_sk4_t<32, 2>(sp, ph, pl, qh, ql, prm); }
+    } else {
+      if (BN == 128) { launch_sk4_t<128, 1>(sp, ph, pl, qh, ql, prm); } else if (BN == 96) { launch_sk4_t<96, 1>(sp, ph, pl, qh, ql, prm); } else if (BN == 64) { launch_sk4_t<64, 1>(sp, ph, pl, qh, ql, prm); } else { launch_sk4_t<32, 1>(sp, ph, pl, qh, ql, prm); }
+    }
   }
   void launch_igemm2(int BN, int planes, dim3 grid, CUtensorMap const &ph, CUtensorMap const &pl, CUtensorMap const &qh, CUtensorMap const &ql, b200::IgemmParams const &prm) {
     if (planes == 2) {
@@ -864,7 +1005,7 @@ struct run_ctx_t {
     CU_CHK(cudaStreamSynchronize(st));
     CU_CHK(cudaMemcpy(ts.data(), ts_dev, ts.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(ts_dev);
-    static char const *names[16] = {"prod_total", "prod_wait_empty", "mma_total", "mma_wait_full", "mma_wait_tmem_empty", "mma_first_full", "mma_stages", "", "epi_total", "epi_wait_tmem_full", "epi_drain", "epi_store", "epi_tiles", "", "", ""};
+    static char const *names[16] = {"prod_total", "prod_wait_empty", "mma_total", "mma_wait_full", "mma_wait_tmem_empty", "mma_first_full", "mma_stages", "mma_wait_afull", "epi_total", "epi_wait_tmem_full", "epi_drain", "epi_store", "epi_tiles", "", "", ""};
     string line = "role stamps '" + rfc.rtc_func_name + "' bn=" + str(BN) + " planes=" + str(planes) + " kblks/tile=" + str(kblks) + " clusters=" + str(n_clusters) + " (median/max cycles):";
     for (int k = 0; k < 13; ++k) {
       if (!names[k][0]) { continue; }
@@ -894,32 +1035,49 @@ struct run_ctx_t {
       if (cp.swapped || cp.splits != 1 || has_arg("out_concat")) { unsup_err("conv: a residual input needs a pixel-major, un-split launch without out_concat (conv_res_fusable)"); }
       res = fptr(vr);
     }
-    if (cp.taps && rtc.use_taps && !res && !has_arg("out_concat") && run_conv_taps(vin, vf, vout, bias, bf16, planes)) { return; }
+    // the round-2 kernel (igemm4.cuh: persistent CTA pairs, halo operand mode, stream-K) takes every layer with at least two 128-row tiles
+    sk4_plan_t const sp = plan_sk4(cp, planes, im.num_sms, rtc);
+    if (!sp.use && cp.taps && rtc.use_taps && !res && !has_arg("out_concat") && run_conv_taps(vin, vf, vout, bias, bf16, planes)) { return; }
+    int const BN = sp.use ? sp.BN : cp.BN;
     // filters: OIHW -> K-major rows (k = tap x chan), stored k-block-major [k / 64][OC padded][64] so that every TMA tile is contiguous
     // (once per weight version; the reference's xpose_filts, src/rtc_fwd.cc:310-313)
     long long const oc_pad = round_up(cp.OC, 128);
-    // activations: NCHW -> NHWC (chan padded to a multiple of 8; row-merged path: chan padded to 4|8 and image rows at pitch Wp with x padding)
+    // activations: NCHW -> NHWC (chan padded to a multiple of 8; row-merged path: chan padded to 4|8 and image rows at pitch Wp with x padding;
+    // halo mode: the shared-padding layout [n][H + py][W + px][chan], pixel (y, x) at (y + py, x + px), see igemm3.cuh / igemm4.cuh)
+    packed_t *a_pack_p = nullptr;
     if (cp.rowmerge) {
       pack(f.w_pack, vf, cp.OC, cp.C, cp.KH * cp.KW, cp.Cpad, cp.Cpad, cp.w_row_stride, oc_pad * cp.w_row_stride, planes == 2, bf16, cp.KW, 64, 0, nullptr, 0, oc_pad);
       long long const img_elems = (long long)cp.H * cp.Wp * cp.Cpad;
       pack(f.a_pack, vin, cp.N, cp.C, cp.H * cp.W, cp.Cpad, cp.Cpad, img_elems, (long long)cp.N * img_elems + 64, planes == 2, bf16, cp.W, (long long)cp.Wp * cp.Cpad, (long long)cp.px * cp.Cpad, absmax_cell("in"), cp.W);
+      a_pack_p = &f.a_pack;  // row-merged planes are private to this function
     } else {
       pack(f.w_pack, vf, cp.OC, cp.C, cp.KH * cp.KW, cp.Cpad, cp.w_tap_stride, cp.w_row_stride, oc_pad * cp.w_row_stride, planes == 2, bf16, 0, 0, 0, nullptr, 0, oc_pad);
-      long long const act_elems = (long long)cp.N * cp.H * cp.W * cp.Cpad;
-      pack(im.act_packs[vin.buf->p], vin, cp.N, cp.C, cp.H * cp.W, cp.Cpad, cp.Cpad, (long long)cp.H * cp.W * cp.Cpad, act_elems, planes == 2, bf16, 0, 0, 0, absmax_cell("in"));
+      if (sp.halo) {
+        long long const img_elems = (long long)sp.Hp * sp.Wp * cp.Cpad;
+        a_pack_p = &im.act_packs[{vin.buf->p, b200_impl_t::pad_tag(cp.py, cp.px)}];
+        pack(*a_pack_p, vin, cp.N, cp.C, cp.H * cp.W, cp.Cpad, cp.Cpad, img_elems, (long long)cp.N * img_elems, planes == 2, bf16, cp.W, (long long)sp.Wp * cp.Cpad,
+             ((long long)cp.py * sp.Wp + cp.px) * cp.Cpad, absmax_cell("in"));
+      } else {
+        long long const act_elems = (long long)cp.N * cp.H * cp.W * cp.Cpad;
+        a_pack_p = &im.act_packs[{vin.buf->p, 0u}];  // plain NHWC planes are shared by every consumer of the node
+        pack(*a_pack_p, vin, cp.N, cp.C, cp.H * cp.W, cp.Cpad, cp.Cpad, (long long)cp.H * cp.W * cp.Cpad, act_elems, planes == 2, bf16, 0, 0, 0, absmax_cell("in"));
+      }
     }
-
-    packed_t &a_pack = cp.rowmerge ? f.a_pack : im.act_packs[vin.buf->p];  // row-merged planes are private to this function; NHWC planes are shared
+    packed_t &a_pack = *a_pack_p;
     long long const pixels = (long long)cp.N * cp.OH * cp.OW;
-    int const p_rows_n = cp.swapped ? cp.OC : (int)pixels, q_rows_n = cp.swapped ? (int)pixels : cp.OC;
-    int const p_tiles = ceil_div(p_rows_n, b200::IGEMM_BM), q_tiles = ceil_div(q_rows_n, cp.BN);
+    int const p_rows_n = cp.swapped ? cp.OC : (sp.halo ? (int)sp.m_rows : (int)pixels), q_rows_n = cp.swapped ? (int)pixels : cp.OC;
+    int const p_tiles = ceil_div(p_rows_n, b200::IGEMM_BM), q_tiles = ceil_div(q_rows_n, BN);
     // CTA pairs (tcgen05 cta_group::2, igemm2.cuh) whenever the layer has >= 2 row tiles and needs no split-K; else one CTA per tile,
     // optionally with TMA-multicast clusters (use_clusters, off by default: measured slower than plain tiles on AlexNet)
-    bool const two_cta = rtc.use_2cta && !cp.swapped && cp.splits == 1 && p_tiles >= 2;
-    cluster_choice_t const cl = choose_cluster(p_tiles, q_tiles, cp.BN, planes, rtc.use_clusters && !two_cta && !cp.swapped && cp.splits == 1);
+    bool const two_cta = !sp.use && rtc.use_2cta && !cp.swapped && cp.splits == 1 && p_tiles >= 2;
+    cluster_choice_t const cl = choose_cluster(p_tiles, q_tiles, BN, planes, rtc.use_clusters && !sp.use && !two_cta && !cp.swapped && cp.splits == 1);
     CUtensorMap act_hi, act_lo, w_hi, w_lo;
-    uint32_t const act_box = cp.swapped ? cp.BN : b200::IGEMM_BM / cl.cn, w_box = cp.swapped ? b200::IGEMM_BM : (two_cta ? cp.BN / 2 : cp.BN / cl.cm);
-    if (cp.im2col) {
+    bool const pairs = sp.use || two_cta;
+    uint32_t const act_box = cp.swapped ? (pairs ? BN / 2 : BN) : b200::IGEMM_BM / cl.cn, w_box = cp.swapped ? b200::IGEMM_BM : (pairs ? BN / 2 : BN / cl.cm);
+    if (sp.halo) {
+      act_hi = make_tiled_map(a_pack.hi->p, bf16, cp.Cpad, (uint64_t)cp.N * sp.Hp * sp.Wp, cp.Cpad, sp.a_box_rows);
+      act_lo = planes == 2 ? make_tiled_map(a_pack.lo->p, bf16, cp.Cpad, (uint64_t)cp.N * sp.Hp * sp.Wp, cp.Cpad, sp.a_box_rows) : act_hi;
+    } else if (cp.im2col) {
       act_hi = make_im2col_map(a_pack.hi->p, bf16, cp, act_box);
       act_lo = planes == 2 ? make_im2col_map(a_pack.lo->p, bf16, cp, act_box) : act_hi;
     } else {
@@ -933,8 +1091,8 @@ struct run_ctx_t {
 
     b200::IgemmParams prm;
     memset(&prm, 0, sizeof(prm));
-    prm.p_rows = cp.swapped ? cp.OC : (int)pixels;
-    prm.q_rows = cp.swapped ? (int)pixels : cp.OC;
+    prm.p_rows = p_rows_n;
+    prm.q_rows = q_rows_n;
     prm.kblks_total = cp.kblks_total;
     prm.kblks_per_split = cp.kblks_per_split;
     prm.chunk_kblks = std::max(1, planes == 2 ? rtc.acc_chunk_kblks : rtc.acc_chunk_kblks_16);
@@ -947,7 +1105,7 @@ struct run_ctx_t {
     prm.relu = cp.relu; prm.has_bias = bias ? 1 : 0; prm.bias = bias;
     prm.p_scale = static_cast<float *>((cp.swapped ? f.w_pack : a_pack).scale2->p);
     prm.q_scale = static_cast<float *>((cp.swapped ? a_pack : f.w_pack).scale2->p);
-    prm.idesc = b200::make_idesc_f16(bf16 ? 1u : 0u, 128, cp.BN);
+    prm.idesc = b200::make_idesc_f16(bf16 ? 1u : 0u, 128, BN);
     prm.cm = cl.cm; prm.cn = cl.cn;
     prm.kb_mod = cp.kb_mod; prm.ksteps_last = cp.ksteps_last;
     prm.p_kb_rows = cp.swapped ? (int)oc_pad : 0; prm.q_kb_rows = cp.swapped ? 0 : (int)oc_pad;
@@ -959,6 +1117,7 @@ struct run_ctx_t {
     // not written (split-K layers: the reduce kernel writes the strided slice).
     float *out_base = fptr(vout);
     var_info_t *vcat = nullptr;
+    bool const splitk_pass = !sp.use && cp.splits > 1;  // two-pass split-K of the one-CTA kernel (the round-2 kernel reduces in place: stream-K)
     if (has_arg("out_concat")) {
       vcat = &var("out_concat");
       check_nchw(vcat->dims, "out_concat");
@@ -967,21 +1126,29 @@ struct run_ctx_t {
         rt_err("conv: out does not fit into out_concat at out_ocix");
       }
       out_base = fptr(*vcat) + (long long)ocix * cp.OH * cp.OW;
-      if (cp.splits == 1) { prm.out_chans = (int)vcat->dims.dsz("chan"); }  // split-K partials keep this layer's own geometry; the reduce kernel strides
+      if (!splitk_pass) { prm.out_chans = (int)vcat->dims.dsz("chan"); }  // split-K partials keep this layer's own geometry; the reduce kernel strides
     }
-    // bf16 storage mode + "out_pack": also write the NHWC bf16 plane the consuming convolutions read (shared act_packs entry of the destination
-    // var), so they find it fresh and skip their pack kernel. Needs 16-byte aligned runs: channel offset and channel count multiples of 8.
+    // "out_pack": also write the NHWC 16-bit plane(s) the consuming convolutions read (shared act_packs entry of the destination var), so
+    // they find it fresh and skip their pack kernel. Needs 16-byte aligned runs: channel offset and channel count multiples of 8. By-value
+    // "out_pack_py" / "out_pack_px" select the shared-padding layout of a halo-mode consumer (0 / absent = plain pixel-major).
     packed_t *out_pk = nullptr;
     var_info_t &vdst = vcat ? *vcat : vout;
+    int o16_py = 0, o16_px = 0;
+    bool o16_padded = false;
     prm.res = res;
     prm.res_absmax = res ? absmax_cell("res") : nullptr;
     // (beside a residual the fp16 planes' bound needs max|res|: without that cell only bf16 planes are written; consumers then pack as usual)
-    if (has_arg("out_pack") && scalar("out_pack") != 0 && !cp.swapped && cp.splits == 1 && (cp.OC % 8) == 0 && (bf16 || !vcat) && (bf16 || !res || prm.res_absmax)) {
+    if (has_arg("out_pack") && scalar("out_pack") != 0 && !cp.swapped && !splitk_pass && (cp.OC % 8) == 0 && (bf16 || !vcat) && (bf16 || !res || prm.res_absmax)) {
       int const ocix = vcat ? (int)scalar("out_ocix") : 0;
       int const cdst = (int)vdst.dims.dsz("chan"), cdst_pad = (int)round_up(cdst, 8);
+      if (sp.use && has_arg("out_pack_py")) { o16_py = (int)scalar("out_pack_py"); o16_px = (int)scalar("out_pack_px"); o16_padded = true; }  // only the round-2 kernel writes padded planes
       if ((ocix % 8) == 0) {
-        out_pk = &im.act_packs[vdst.buf->p];
-        uint64_t const bytes = (uint64_t)cp.N * cp.OH * cp.OW * cdst_pad * 2;
+        out_pk = &im.act_packs[{vdst.buf->p, o16_padded ? b200_impl_t::pad_tag(o16_py, o16_px) : 0u}];
+        uint64_t const bytes = (uint64_t)cp.N * (cp.OH + o16_py) * (cp.OW + o16_px) * cdst_pad * 2;
+        long long const hw = (long long)cp.OH * cp.OW;
+        uint64_t const lkey = o16_padded ? pack_layout_key({cp.N, cdst, hw, cdst_pad, cdst_pad, (long long)(cp.OH + o16_py) * (cp.OW + o16_px) * cdst_pad, cp.OW, (long long)(cp.OW + o16_px) * cdst_pad,
+                                                            ((long long)o16_py * (cp.OW + o16_px) + o16_px) * cdst_pad, planes == 2, bf16, 0, 0})
+                                         : pack_layout_key({cp.N, cdst, hw, cdst_pad, cdst_pad, hw * cdst_pad, std::max<long long>(hw, 1), 0, 0, planes == 2, bf16, 0, 0});
         if (!out_pk->hi || out_pk->hi->bytes < bytes || (planes == 2 && !out_pk->lo)) {
           out_pk->hi = std::make_shared<dev_buf_t>(bytes);
           CU_CHK(cudaMemsetAsync(out_pk->hi->p, 0, bytes, st));
@@ -991,7 +1158,11 @@ struct run_ctx_t {
           CU_CHK(cudaMemsetAsync(out_pk->absmax_bits->p, 0, 8, st));
           static float const ones[2] = {1.0f, 1.0f};
           CU_CHK(cudaMemcpyAsync(out_pk->scale2->p, ones, 8, cudaMemcpyHostToDevice, st));
+        } else if (out_pk->layout_key != lkey) {  // same storage, other geometry: padding positions must be zero again
+          CU_CHK(cudaMemsetAsync(out_pk->hi->p, 0, out_pk->hi->bytes, st));
+          if (out_pk->lo) { CU_CHK(cudaMemsetAsync(out_pk->lo->p, 0, out_pk->lo->bytes, st)); }
         }
+        out_pk->layout_key = lkey;
         prm.out16 = static_cast<uint16_t *>(out_pk->hi->p) + ocix;
         prm.out16_pitch = cdst_pad;
         if (!bf16) {  // fp16 planes: scale from the output bound (IgemmParams::w_l1max); the filter L1 norm is computed once per weight version
@@ -1011,7 +1182,7 @@ struct run_ctx_t {
         }
       }
     }
-    if (cp.splits > 1) {
+    if (splitk_pass) {
       uint64_t const need = (uint64_t)cp.splits * out_elems * 4;
       if (!f.splitk_ws || f.splitk_ws->bytes < need) { f.splitk_ws = std::make_shared<dev_buf_t>(need); }
       prm.out = static_cast<float *>(f.splitk_ws->p);
@@ -1024,28 +1195,54 @@ struct run_ctx_t {
     long long *ts_dev = nullptr;
     int ts_clusters = 0;
     mark_kernel_begin();
-    if (two_cta) {  // persistent: one cluster per SM pair (or per tile, if fewer), each walking its share of the tiles
-      prm.idesc = b200::make_idesc_f16(bf16 ? 1u : 0u, 256, cp.BN);
+    if (sp.use) {
+      b200::Sk4Params sk;
+      memset(&sk, 0, sizeof(sk));
+      prm.idesc = b200::make_idesc_f16(bf16 ? 1u : 0u, 256, BN);
+      prm.m_pair_tiles = sp.m_pair_tiles; prm.q_tiles = sp.q_tiles;
+      prm.kblks_per_split = prm.kblks_total;
+      prm.cm = prm.cn = 1;
+      sk.p_mode = sp.halo ? 2 : (cp.im2col ? 1 : 0);
+      sk.taps = sp.halo ? cp.KH * cp.KW : 1;
+      sk.Wp = sp.Wp; sk.HpWp = sp.Hp * sp.Wp; sk.OH = cp.OH; sk.OW = cp.OW;
+      sk.halo_rows = sp.halo_rows; sk.a_loads = sp.a_loads; sk.a_box_rows = sp.a_box_rows;
+      sk.a_stages = sp.a_stages; sk.b_stages = sp.b_stages;
+      sk.sk = sp.sk ? 1 : 0; sk.n_tiles = sp.n_tiles; sk.ukb = sp.ukb;
+      sk.out_w = cp.OW;
+      if (o16_padded) { sk.o16_Hp = cp.OH + o16_py; sk.o16_Wp = cp.OW + o16_px; sk.o16_py = o16_py; sk.o16_px = o16_px; }
+      if (sp.sk) {
+        uint64_t const ws_bytes = (uint64_t)im.num_sms * 128 * 128 * 4;  // one [BN <= 128][128] fp32 slot per CTA
+        if (!im.sk_ws) {
+          im.sk_ws = std::make_shared<dev_buf_t>(ws_bytes);
+          im.sk_flags = std::make_shared<dev_buf_t>((uint64_t)im.num_sms * 4);
+          CU_CHK(cudaMemsetAsync(im.sk_flags->p, 0, (uint64_t)im.num_sms * 4, st));  // flags are reset by their consumer from here on
+        }
+        sk.sk_ws = static_cast<float *>(im.sk_ws->p);
+        sk.sk_flags = static_cast<unsigned int *>(im.sk_flags->p);
+      }
+      if (rtc.debug_flags & 16) { ts_clusters = sp.n_pairs; CU_CHK(cudaMalloc(&ts_dev, (size_t)sp.n_pairs * 16 * sizeof(long long))); CU_CHK(cudaMemsetAsync(ts_dev, 0, (size_t)sp.n_pairs * 16 * sizeof(long long), st)); prm.ts = ts_dev; }
+      sk.g = prm;
+      if (cp.swapped) { launch_sk4(BN, planes, sp, w_hi, w_lo, act_hi, act_lo, sk); }
+      else { launch_sk4(BN, planes, sp, act_hi, act_lo, w_hi, w_lo, sk); }
+    }
+    else if (two_cta) {  // persistent: one cluster per SM pair (or per tile, if fewer), each walking its share of the tiles
+      prm.idesc = b200::make_idesc_f16(bf16 ? 1u : 0u, 256, BN);
       prm.m_pair_tiles = ceil_div(p_tiles, 2); prm.q_tiles = q_tiles;
       int const n_clusters = std::min(prm.m_pair_tiles * prm.q_tiles, im.num_sms / 2);
       if (rtc.debug_flags & 16) { ts_clusters = n_clusters; CU_CHK(cudaMalloc(&ts_dev, (size_t)n_clusters * 16 * sizeof(long long))); CU_CHK(cudaMemsetAsync(ts_dev, 0, (size_t)n_clusters * 16 * sizeof(long long), st)); prm.ts = ts_dev; }
-      launch_igemm2(cp.BN, planes, dim3(2 * n_clusters, 1, 1), act_hi, act_lo, w_hi, w_lo, prm);
+      launch_igemm2(BN, planes, dim3(2 * n_clusters, 1, 1), act_hi, act_lo, w_hi, w_lo, prm);
     }
-    else if (cp.swapped) { launch_igemm(cp.BN, planes, grid, w_hi, w_lo, act_hi, act_lo, prm); }
-    else { launch_igemm(cp.BN, planes, grid, act_hi, act_lo, w_hi, w_lo, prm); }
+    else if (cp.swapped) { launch_igemm(BN, planes, grid, w_hi, w_lo, act_hi, act_lo, prm); }
+    else { launch_igemm(BN, planes, grid, act_hi, act_lo, w_hi, w_lo, prm); }
     mark_kernel_end();
-    if (ts_dev) { print_role_stamps(ts_dev, ts_clusters, cp.BN, planes, cp.kblks_total); }
-    if (cp.splits > 1) {
+    if (ts_dev) { print_role_stamps(ts_dev, ts_clusters, BN, planes, cp.kblks_total); }
+    if (splitk_pass) {
       B200_CARVEOUT_ONCE(b200::splitk_reduce_kernel); launch_k(b200::splitk_reduce_kernel, dim3(ceil_div(out_elems, 256)), dim3(256), 0, static_cast<float *>(f.splitk_ws->p), out_base, bias, out_elems, cp.splits, cp.OC, cp.OH * cp.OW, cp.relu, prm.out_absmax,
                vcat ? (long long)vcat->dims.dsz("chan") * cp.OH * cp.OW : 0ll);
       launched();
     }
     im.bump(vdst);
-    if (out_pk) {  // the plane is current for this write generation: consumers skip their pack (same key as their pack() call: plain NHWC)
-      out_pk->src_gen = *vdst.gen; out_pk->src_ptr = vdst.buf->p;
-      long long const cd = (long long)vdst.dims.dsz("chan"), cdp = round_up(cd, 8), hw = (long long)cp.OH * cp.OW;
-      out_pk->layout_key = pack_layout_key({cp.N, cd, hw, cdp, cdp, hw * cdp, std::max<long long>(hw, 1), 0, 0, planes == 2, bf16, 0, 0});
-    }
+    if (out_pk) { out_pk->src_gen = *vdst.gen; out_pk->src_ptr = vdst.buf->p; }  // the plane is current for this write generation (layout_key set above): consumers skip their pack
   }
   static constexpr uint32_t IGEMM_BM_host() { return b200::IGEMM_BM; }
 
@@ -1162,10 +1359,18 @@ struct run_ctx_t {
       b200::PoolPlanes pp;
       memset(&pp, 0, sizeof(pp));
       packed_t *out_pk = nullptr;
+      int o16_py = 0, o16_px = 0;
+      bool o16_padded = false;
       if (planes_ok) {
         int const cpad = (int)round_up(C, 8);
-        out_pk = &im.act_packs[vout.buf->p];
-        uint64_t const bytes = (uint64_t)vout.dims.dsz("img") * OH * OW * cpad * 2;
+        long long const nimg = (long long)vout.dims.dsz("img");
+        if (has_arg("out_pack_py")) { o16_py = (int)scalar("out_pack_py"); o16_px = (int)scalar("out_pack_px"); o16_padded = true; }  // the consumer's halo mode (igemm4.cuh)
+        out_pk = &im.act_packs[{vout.buf->p, o16_padded ? b200_impl_t::pad_tag(o16_py, o16_px) : 0u}];
+        uint64_t const bytes = (uint64_t)nimg * (OH + o16_py) * (OW + o16_px) * cpad * 2;
+        long long const ohw2 = (long long)OH * OW;
+        uint64_t const lkey = o16_padded ? pack_layout_key({nimg, C, ohw2, cpad, cpad, (long long)(OH + o16_py) * (OW + o16_px) * cpad, OW, (long long)(OW + o16_px) * cpad,
+                                                            ((long long)o16_py * (OW + o16_px) + o16_px) * cpad, npl == 2, bf16, 0, 0})
+                                         : pack_layout_key({nimg, C, ohw2, cpad, cpad, ohw2 * cpad, std::max<long long>(ohw2, 1), 0, 0, npl == 2, bf16, 0, 0});
         if (!out_pk->hi || out_pk->hi->bytes < bytes || (npl == 2 && !out_pk->lo)) {
           out_pk->hi = std::make_shared<dev_buf_t>(bytes);
           CU_CHK(cudaMemsetAsync(out_pk->hi->p, 0, bytes, st));
@@ -1173,12 +1378,18 @@ struct run_ctx_t {
           out_pk->scale2 = std::make_shared<dev_buf_t>(8);
           out_pk->absmax_bits = std::make_shared<dev_buf_t>(8);
           CU_CHK(cudaMemsetAsync(out_pk->absmax_bits->p, 0, 8, st));
+        } else if (out_pk->layout_key != lkey) {  // same storage, other geometry: padding positions must be zero again
+          CU_CHK(cudaMemsetAsync(out_pk->hi->p, 0, out_pk->hi->bytes, st));
+          if (out_pk->lo) { CU_CHK(cudaMemsetAsync(out_pk->lo->p, 0, out_pk->lo->bytes, st)); }
         }
+        out_pk->layout_key = lkey;
         pp.hi = static_cast<uint16_t *>(out_pk->hi->p);
         pp.lo = npl == 2 ? static_cast<uint16_t *>(out_pk->lo->p) : nullptr;
         pp.scale2 = static_cast<float *>(out_pk->scale2->p);
         pp.in_absmax = in_cell;
         pp.C = C; pp.cpad = cpad; pp.bf16 = bf16 ? 1 : 0;
+        pp.OW = OW;
+        if (o16_padded) { pp.dHp = OH + o16_py; pp.dWp = OW + o16_px; pp.dpy = o16_py; pp.dpx = o16_px; }
       }
       size_t const smem = pipe_ppc ? pipe_smem : (size_t)ppc * (H * W + (pp.hi ? OH * OW : 0)) * 4;
       unsigned int *cell = absmax_cell("out");
@@ -1198,11 +1409,7 @@ struct run_ctx_t {
 #undef B200_POOL_PLANE
       launched();
       im.bump(vout);
-      if (out_pk) {  // the planes are current: the consuming convolution skips its pack (same key as its pack() call: plain NHWC)
-        out_pk->src_gen = *vout.gen; out_pk->src_ptr = vout.buf->p;
-        long long const nimg = (long long)vout.dims.dsz("img"), cdp = round_up(C, 8), ohw2 = (long long)OH * OW;
-        out_pk->layout_key = pack_layout_key({nimg, C, ohw2, cdp, cdp, ohw2 * cdp, std::max<long long>(ohw2, 1), 0, 0, npl == 2, bf16, 0, 0});
-      }
+      if (out_pk) { out_pk->src_gen = *vout.gen; out_pk->src_ptr = vout.buf->p; }  // the planes are current (layout_key set above): the consuming convolution skips its pack
       return;
     }
     if (KH == KW && sy == sx && ((KH == 3 && sy == 2) || (KH == 3 && sy == 1) || (KH == 2 && sy == 2)) && planes <= 65535) {

@@ -73,6 +73,10 @@ struct b200_compute_t {
                             // Off by default: measured slower than the CTA-pair im2col kernel on the AlexNet layers (profiles/), kept for A/B runs
   int taps_max_b_stages = 8, taps_max_a_stages = 3;  // experiments: cap the tap-reuse kernel's ring depths
   int taps_2cta = -1;       // tap-reuse kernel: -1 = cost model picks single CTAs or CTA pairs, 0 / 1 = force
+  int use_sk4 = 1;          // the round-2 contraction kernel (igemm4.cuh: persistent CTA pairs, halo operand mode, stream-K) for every layer with >= 2 row tiles
+  int use_halo = 1;         // igemm4: one activation halo tile per channel block feeds every filter tap of a stride-1 KHxKW convolution
+  int use_streamk = 1;      // igemm4: cut the (tile, k-block) space into equal contiguous ranges per CTA pair when whole tiles would leave > 8 % of a round idle
+  int sk4_max_b_stages = 0; // experiments: cap igemm4's filter ring depth (0 = as many as fit)
   int plan_only = 0;        // host-side planning / inspection only: init() touches no device (plans for plan_num_sms SMs), vars carry dims but no
   int plan_num_sms = 148;   // storage, compile() plans as usual and every call that would compute or copy throws. Never a compute path.
 
@@ -123,6 +127,8 @@ struct b200_compute_t {
   bool conv_plane_writable(op_base_t const &op, bool dst_is_concat);
   // whether this convolution's launch can take a residual input ("res" argument): pixel-major, un-split launches only
   bool conv_res_fusable(op_base_t const &op);
+  bool conv_halo_pad(op_base_t const &op, int &py, int &px);  // halo-mode convolutions read their input planes in the shared-padding layout (py, px)
+  bool conv_uses_sk4(op_base_t const &op);
   bool has_var(string const &vn) const;
   bool has_func(string const &fn) const;
   // host-only: the launch plan compile() made for a convolution function, as "kernel=pair|single bn=<N tile> kblks=<64-wide k-blocks>

@@ -273,6 +273,28 @@ bool b200_conv_fwd_t::dst_plane_by_producers(string const &dst) {
   return true;
 }
 
+// The layout a destination node's producer-written planes take: the shared-padding layout (py, px) of igemm4.cuh's halo mode when EVERY
+// Convolution reading the node runs in that mode with the same padding, else plain pixel-major NHWC (a halo-mode reader then packs for itself).
+bool b200_conv_fwd_t::dst_plane_pad(string const &dst, int &py, int &px) {
+  bool any = false;
+  for (auto const &o : cp->ops) {
+    if (!o->is("Convolution") || o->bots.empty() || o->bots[0] != dst) { continue; }
+    int y = 0, x = 0;
+    if (!rtc->conv_halo_pad(conv_fop(*o), y, x)) { return false; }
+    if (any && (y != py || x != px)) { return false; }
+    py = y; px = x; any = true;
+  }
+  return any;
+}
+void b200_conv_fwd_t::add_out_pack_args(map_str_rtc_arg_t &args, string const &dst) {
+  args["out_pack"] = rtc_arg_t(make_scalar_nda<uint32_t>(1, "uint32_t"));
+  int py = 0, px = 0;
+  if (dst_plane_pad(dst, py, px)) {
+    args["out_pack_py"] = rtc_arg_t(make_scalar_nda<uint32_t>((uint32_t)py, "uint32_t"));
+    args["out_pack_px"] = rtc_arg_t(make_scalar_nda<uint32_t>((uint32_t)px, "uint32_t"));
+  }
+}
+
 void b200_conv_fwd_t::gen_op(p_conv_op_t const &op) {
   if (op->fused) { return; }  // folded into its producer (src/rtc_fwd.cc:266)
   op_base_t fop;              // function signature: op params + the dims of every argument (conv_op_t::set_arg_dims_and_map_from_pipe)
@@ -355,7 +377,7 @@ void b200_conv_fwd_t::gen_op(p_conv_op_t const &op) {
       args["res"] = rtc_arg_t(rf->second.res_node);
       add_absmax_args(args, "out", rf->second.out_node);
       add_absmax_args(args, "res", rf->second.res_node);
-      if (dst_plane_by_producers(rf->second.out_node)) { args["out_pack"] = rtc_arg_t(make_scalar_nda<uint32_t>(1, "uint32_t")); }
+      if (dst_plane_by_producers(rf->second.out_node)) { add_out_pack_args(args, rf->second.out_node); }
       add_call("conv", *op, fop, args);
       return;
     }
@@ -366,7 +388,10 @@ void b200_conv_fwd_t::gen_op(p_conv_op_t const &op) {
       add_absmax_args(args, "out", al->second.cat_node);
     } else { add_absmax_args(args, "out", op->tops[0]); }
     // layout-transform elimination (bf16 storage mode): also write the NHWC plane the consuming convolutions read (they then skip their pack)
-    if (dst_plane_by_producers((al != concat_alias.end()) ? al->second.cat_node : op->tops[0])) { args["out_pack"] = rtc_arg_t(make_scalar_nda<uint32_t>(1, "uint32_t")); }
+    {
+      string const dst = (al != concat_alias.end()) ? al->second.cat_node : op->tops[0];
+      if (dst_plane_by_producers(dst)) { add_out_pack_args(args, dst); }
+    }
     add_call("conv", *op, fop, args);
   } else if (op->is("Pooling")) {
     map_str_rtc_arg_t args{{"in", op->bots[0]}, {"out", op->tops[0]}};
@@ -378,7 +403,7 @@ void b200_conv_fwd_t::gen_op(p_conv_op_t const &op) {
       for (auto const &ip : on->in_place_ops) { if (!ip->is("Dropout")) { clean = false; } }
       if (pack_by_producers && feeds && clean) {
         add_absmax_args(args, "in", op->bots[0]);
-        args["out_pack"] = rtc_arg_t(make_scalar_nda<uint32_t>(1, "uint32_t"));
+        add_out_pack_args(args, op->tops[0]);
       }
     }
     add_call("pool", *op, fop, args);
@@ -562,6 +587,17 @@ void b200_conv_fwd_t::set_param(string const &node_name, float const *src, uint6
   if (n->dims.dims_prod() != n_elems) { rt_err("set_param '" + node_name + "': got " + str(n_elems) + " elements, node holds " + str(n->dims.dims_prod())); }
   rtc->copy_raw_to_var(node_name, src, n_elems * 4);
   // the captured graph skips weight packing (packed once per weight version): new weights need a fresh warm-up + capture
+  if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+  if (graph) { cudaGraphDestroy(graph); graph = nullptr; }
+  warmed = false;
+}
+
+// the same from a device buffer (a slice of the flat buffer the weights were broadcast in, b200_shard.cu): device-to-device on the back-end's stream
+void b200_conv_fwd_t::set_param_device(string const &node_name, void const *dev_src, uint64_t n_elems) {
+  p_conv_node_t n = cp->must_get_node(node_name);
+  if (n->dims.dims_prod() != n_elems) { rt_err("set_param '" + node_name + "': got " + str(n_elems) + " elements, node holds " + str(n->dims.dims_prod())); }
+  rtc->copy_device_to_var_async(node_name, dev_src, n_elems * 4);
+  rtc->finish_and_sync();
   if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
   if (graph) { cudaGraphDestroy(graph); graph = nullptr; }
   warmed = false;

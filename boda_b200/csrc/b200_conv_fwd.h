@@ -69,6 +69,7 @@ struct b200_conv_fwd_t {
 
   // raw-buffer variants used by the C ABI
   void set_param(string const &node_name, float const *src, uint64_t n_elems);
+  void set_param_device(string const &node_name, void const *dev_src, uint64_t n_elems);
   void run_fwd_raw(int n_set, char const *const *set_names, float const *const *set_bufs, uint64_t const *set_elems, int n_get,
                    char const *const *get_names, float *const *get_bufs, uint64_t const *get_elems);
   // Pipelined form of run_fwd for serving loops: submit() enqueues H2D of this batch's inputs (on a copy stream, into one of two staging
@@ -121,7 +122,9 @@ struct b200_conv_fwd_t {
   map<string, concat_alias_t> concat_alias;  // node -> (Concat output that holds its channels, channel offset, name of the read-back function)
   void materialise_aliased(string const &node);
   op_base_t conv_fop(conv_op_t const &op) const;  // function signature of a Convolution op: its params + the dims of in / filts / biases / out
-  bool dst_plane_by_producers(string const &dst);  // bf16 mode: every producer of node `dst` can write its NHWC plane and some conv reads it  // enqueue the slice copy Concat output -> node var (before reading an aliased node)
+  bool dst_plane_by_producers(string const &dst);
+  bool dst_plane_pad(string const &dst, int &py, int &px);
+  void add_out_pack_args(map_str_rtc_arg_t &args, string const &dst);  // bf16 mode: every producer of node `dst` can write its NHWC plane and some conv reads it  // enqueue the slice copy Concat output -> node var (before reading an aliased node)
   void add_absmax_args(map_str_rtc_arg_t &args, string const &which, string const &node);
 };
 

@@ -1,0 +1,34 @@
+// b200_shard.h -- batch sharding of has_conv_fwd_t::run_fwd over the GPUs of one box: the per-process communicator object behind the
+// `b200_shard_*` C ABI (include/boda_b200.h). The reference has no multi-GPU path; see b200_shard.cu.
+#pragma once
+#include "boda_base.h"
+
+namespace boda {
+
+struct b200_shard_impl_t;
+
+struct b200_shard_t {
+  int device, rank, world;
+  uint64_t n_launches = 0;  // kernels of this module launched so far (claimed in bench.py's gpu_launches)
+  b200_shard_t(int device, int rank, int world);
+  ~b200_shard_t();
+  b200_shard_t(b200_shard_t const &) = delete;
+
+  // NCCL (weights): rank 0 makes the 128-byte unique id, the caller hands it to every rank, every rank joins; then one in-place broadcast
+  void nccl_unique_id(void *id_out_128);
+  void nccl_init(void const *id_128);
+  void broadcast(void *dev_buf, uint64_t bytes, int root, void *stream);
+  void all_gather_nccl(void const *dev_src, void *dev_dst, uint64_t bytes_per_rank, void *stream);  // A/B baseline for the peer-memory gather
+
+  // peer-memory gather (logits): export the local buffer's 64-byte IPC handle, import everyone's, then per step push + wait
+  void gather_export(uint64_t bytes_per_rank, void *ipc_handle_out_64);
+  void gather_import(void const *ipc_handles_world_x_64);
+  uint32_t gather_push(void const *dev_src, void *stream);  // returns the step number it published
+  void gather_wait(uint32_t step, void *stream);
+  void *gather_ptr(uint32_t step) const;  // device pointer of the local [world][bytes_per_rank] result of `step` (two halves, by step parity)
+  uint32_t step() const;
+
+  b200_shard_impl_t *impl;
+};
+
+}  // namespace boda

@@ -289,6 +289,8 @@ struct PoolPlanes {
   float *scale2;                  // {scale, 1/scale} of the planes
   unsigned int const *in_absmax;  // max|in| bit pattern (fp16 planes); null = bf16 planes, scale 1
   int C, cpad, bf16;              // channels of the pooled node, its padded NHWC pitch, storage type
+  int OW, dHp, dWp, dpy, dpx;     // dWp != 0: the planes are in the shared-padding layout of a halo-mode consumer (igemm4.cuh): pixel (y, x) of image n at
+                                  // row (n*dHp + y + dpy)*dWp + x + dpx
 };
 
 // Plane-group variant: one CTA stages kPPC consecutive (img,chan) planes -- a CONTIGUOUS run of kPPC*H*W floats -- in shared memory with
@@ -441,7 +443,9 @@ __device__ __forceinline__ void pool_planes_write16(float const *os, PoolPlanes 
           wl[k] = *reinterpret_cast<uint32_t const *>(&l);
         }
       }
-      long long const o16 = (img * ohw + pix) * pp.cpad + chan0 + 8 * g;
+      long long orow = img * ohw + pix;
+      if (pp.dWp) { int const oy = pix / pp.OW, ox = pix - oy * pp.OW; orow = (img * pp.dHp + oy + pp.dpy) * pp.dWp + ox + pp.dpx; }
+      long long const o16 = orow * pp.cpad + chan0 + 8 * g;
       *reinterpret_cast<uint4 *>(pp.hi + o16) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
       if (pp.lo) { *reinterpret_cast<uint4 *>(pp.lo + o16) = make_uint4(wl[0], wl[1], wl[2], wl[3]); }
     }

@@ -147,6 +147,33 @@ int b200_fwd_flush_l2(b200_fwd *f, uint64_t bytes);
 /* device pointer of a node's fp32 NCHW var (e.g. to hand the logits to NCCL) */
 int b200_fwd_get_node_raw_native_pointer(b200_fwd *f, const char *node_name, void **dev_ptr_out);
 
+/* ---- batch sharding of run_fwd over the GPUs of one box (the reference has no multi-GPU path, north_star asks for
+ * "a single NCCL broadcast of weights and gather of logits over NVLink" with a C++ host side). One process per GPU, one b200_shard per
+ * process. Rendezvous bytes (the 128-byte ncclUniqueId, the 64-byte CUDA IPC handles) are plain memory: the caller moves them between the
+ * processes with whatever it has (bench.py: torch.distributed object collectives; a Boda driver: files or MPI). ---- */
+typedef struct b200_shard b200_shard;
+b200_shard *b200_shard_create(int device, int rank, int world);       /* needs a CUDA device (no CPU fallback); NULL + b200_last_error() on failure */
+void b200_shard_destroy(b200_shard *s);
+/* weights: rank 0 makes the id, every rank joins (ncclCommInitRank; the NCCL C API is resolved from libnccl.so.2 at run time), then ONE
+ * in-place ncclBroadcast of a flat device buffer; b200_fwd_set_param_device slices it into the parameter vars device-to-device */
+int b200_shard_nccl_unique_id(b200_shard *s, void *id_out_128);
+int b200_shard_nccl_init(b200_shard *s, const void *id_128);
+int b200_shard_broadcast(b200_shard *s, void *dev_buf, uint64_t bytes, int root, void *stream);
+int b200_fwd_set_param_device(b200_fwd *f, const char *node_name, const void *dev_src, uint64_t n_elems);
+/* logits: every rank owns a gather buffer [2][world][bytes_per_rank] (two halves by step parity: the result of step i stays readable while step
+ * i+1 arrives) that its peers map through CUDA IPC. b200_shard_gather_push queues ONE small
+ * kernel on `stream` (normally the forward's own stream, b200_fwd_get_stream) that writes this rank's output straight into slot [rank] of every
+ * peer's buffer over NVLink and then publishes its step number there; b200_shard_gather_wait queues a one-CTA kernel that returns once every
+ * rank's step number in the LOCAL buffer has reached `step`. No collective kernel occupies SMs beside the forward. push returns the step (>= 1)
+ * or a negative code. b200_shard_all_gather_nccl is the ncclAllGather of the same data, kept for A/B runs. */
+int b200_shard_gather_export(b200_shard *s, uint64_t bytes_per_rank, void *ipc_handle_out_64);
+int b200_shard_gather_import(b200_shard *s, const void *ipc_handles_world_x_64);
+int64_t b200_shard_gather_push(b200_shard *s, const void *dev_src, void *stream);
+int b200_shard_gather_wait(b200_shard *s, uint32_t step, void *stream);
+int b200_shard_gather_ptr(b200_shard *s, uint32_t step, void **dev_ptr_out); /* device pointer of the local [world][bytes_per_rank] result of `step` */
+int b200_shard_all_gather_nccl(b200_shard *s, const void *dev_src, void *dev_dst, uint64_t bytes_per_rank, void *stream);
+uint64_t b200_shard_launches(b200_shard *s);                          /* kernels this module has launched so far */
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,8 +79,10 @@ def test_alexnet_ng_conv_b2_all_nodes(oracle):
 
 def test_alexnet_b32_batch_consistency(oracle):
     """BASELINE config C2 at full size (B=32), through a size-independent property: images are independent units of the
-    path, so a batch whose images repeat with period 2 must give per-image results identical to the B=2 run,
-    which is itself checked against the oracle above."""
+    path, so a batch whose images repeat with period 2 must give per-image results that agree with the B=2 run,
+    which is itself checked against the oracle above. With whole-tile scheduling (use_streamk=0) every repeat of an image is
+    BIT-identical wherever its tile falls; stream-K (the default) cuts the K range of a tile at a pair-dependent place, i.e. the fp32
+    summation GROUPING depends on the tile -- repeats then agree to summation-order noise (and every run is deterministic)."""
     import boda_b200 as bb
     from boda_b200 import nets
     txt2, i, o = nets.alexnet_ng_conv(2)
@@ -88,20 +90,26 @@ def test_alexnet_b32_batch_consistency(oracle):
     params = nets.synth_params(txt32)
     x2 = nets.synth_input((2, 3, 227, 227))
     x32 = np.ascontiguousarray(np.tile(x2, (16, 1, 1, 1)))
-    outs = []
-    for txt, x in ((txt2, x2), (txt32, x32)):
-        f = bb.B200ConvFwd(txt, "")
-        for k, v in params.items():
-            f.set_param(k, v)
-        outs.append(f.run_fwd({i: x}, [o, "conv5", "pool1"]))
-    for n in (o, "conv5", "pool1"):
-        a, b = outs[0][n], outs[1][n]
-        assert b.shape[0] == 32
-        # B=2 picks different tilings (split-K on the small layers), i.e. a different fp32 summation grouping: compare to
-        # summation-order noise; inside the B=32 run every repeat of an image must be BIT-identical wherever its tile falls.
-        assert oracle.mrd(a, b[0:2]) < 5e-4, (n, oracle.mrd(a, b[0:2]))
-        for r in range(1, 16):
-            assert np.array_equal(b[0:2], b[2 * r:2 * r + 2]), (n, r)
+    for opts, exact in (("(use_streamk=0)", True), ("", False)):
+        outs = []
+        for txt, x in ((txt2, x2), (txt32, x32)):
+            f = bb.B200ConvFwd(txt, opts)
+            for k, v in params.items():
+                f.set_param(k, v)
+            outs.append(f.run_fwd({i: x}, [o, "conv5", "pool1"]))
+            if txt is txt32:
+                again = f.run_fwd({i: x}, [o])  # determinism of the stream-K hand-off: same bits on every run
+                assert np.array_equal(again[o], outs[-1][o])
+        for n in (o, "conv5", "pool1"):
+            a, b = outs[0][n], outs[1][n]
+            assert b.shape[0] == 32
+            # B=2 picks different tilings, i.e. a different fp32 summation grouping: compare to summation-order noise
+            assert oracle.mrd(a, b[0:2]) < 5e-4, (n, oracle.mrd(a, b[0:2]))
+            for r in range(1, 16):
+                if exact:
+                    assert np.array_equal(b[0:2], b[2 * r:2 * r + 2]), (n, r)
+                else:
+                    assert oracle.mrd(b[0:2], b[2 * r:2 * r + 2]) < 5e-4, (n, r, oracle.mrd(b[0:2], b[2 * r:2 * r + 2]))  # measured 1.5e-4 on fc8 (8 layers of grouping noise)
 
 
 def test_nin_b2_output(oracle):

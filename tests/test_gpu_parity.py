@@ -380,11 +380,12 @@ def test_conv_cluster_multicast_is_bit_identical(oracle, case):
     ref = oracle.conv_fwd(x, w, b, (sy, sx), (py, px), relu=True, acc64=True)
     outs = []
     import boda_b200 as bb
-    for kw in (dict(use_2cta=1), dict(use_2cta=0, use_clusters=1), dict(use_2cta=0, use_clusters=0)):  # CTA pairs | multicast clusters | plain tiles
+    # CTA pairs | multicast clusters | plain tiles | the round-2 kernel in its per-k-block operand modes, whole tiles (same k order and chunking)
+    for kw in (dict(use_2cta=1, use_sk4=0), dict(use_2cta=0, use_clusters=1), dict(use_2cta=0, use_clusters=0), dict(use_sk4=1, use_halo=0, use_streamk=0)):
         r = OpRunner(use_taps=0, **kw)  # the im2col kernels (the tap-reuse kernel has its own test below)
         outs.append(r.run_conv(conv_op_text(N, C, H, W, OC, KH, KW, sy, sx, py, px, 1), x, w, b, ref.shape))
         r.close()
-    assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[1], outs[2])
+    assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[1], outs[2]) and np.array_equal(outs[3], outs[2])
     assert oracle.mrd(ref, outs[0]) < TOL
 
 
@@ -413,7 +414,7 @@ def test_conv_tap_reuse_kernel(oracle, case):
     ref64 = oracle.conv_fwd(x, w, b, (1, 1), (py, px), relu=True, acc64=True)
     noise = oracle.mrd(ref64, oracle.conv_fwd(x, w, b, (1, 1), (py, px), relu=True))
     outs = {}
-    for name, kw in (("taps_1cta", dict(use_taps=1, taps_2cta=0)), ("taps_2cta", dict(use_taps=1, taps_2cta=1)), ("im2col", dict(use_taps=0))):
+    for name, kw in (("taps_1cta", dict(use_taps=1, taps_2cta=0, use_sk4=0)), ("taps_2cta", dict(use_taps=1, taps_2cta=1, use_sk4=0)), ("im2col", dict(use_taps=0, use_sk4=0))):
         r = OpRunner(**kw)
         try:
             outs[name] = r.run_conv(conv_op_text(N, C, H, W, OC, KH, KW, 1, 1, py, px, 1), x, w, b, ref64.shape)
@@ -422,6 +423,46 @@ def test_conv_tap_reuse_kernel(oracle, case):
         assert oracle.mrd(ref64, outs[name]) < TOL, (name, oracle.mrd(ref64, outs[name]))
     assert np.array_equal(outs["taps_1cta"], outs["taps_2cta"])
     assert oracle.mrd(outs["im2col"], outs["taps_1cta"]) < TOL + noise
+
+
+SK4_CASES = TAPS_CASES + [
+    # N, C, H, W, OC, KH, KW, py, px  -- more shapes for the round-2 kernel (igemm4.cuh): halo mode + stream-K
+    (32, 384, 13, 13, 384, 3, 3, 1, 1),   # AlexNet conv4 at B=32: 75 tiles on 74 pairs -> stream-K by the planner's own rule
+    (8, 192, 14, 14, 208, 3, 3, 1, 1),    # GoogLeNet icp4_out1: 13 pair tiles x 3 ragged N tiles of 96 -> few tiles, stream-K
+    (6, 32, 28, 28, 96, 5, 5, 2, 2),      # 5x5 with half a channel block
+    (3, 72, 10, 31, 40, 2, 4, 1, 2),      # even window, asymmetric padding smaller than the overhang
+]
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", SK4_CASES)
+def test_conv_sk4_halo_and_streamk(oracle, case, prec):
+    """The round-2 kernel on stride-1 window convolutions: halo operand mode (one activation tile per channel block feeds every tap) with
+    whole tiles, with stream-K forced (every pair's range starts / ends inside tiles: partial accumulators through the workspace, finisher adds
+    them), and its im2col mode with stream-K forced -- each within tolerance of the oracle; whole-tile im2col mode is bit-identical to the
+    round-1 pair kernel (same k order and accumulation chunks)."""
+    from b200_harness import OpRunner, conv_op_text
+    import torch
+    N, C, H, W, OC, KH, KW, py, px = case
+    rng = np.random.RandomState(N * 100 + C)
+    x = (rng.rand(N, C, H, W).astype(np.float32) - 0.5) * 10
+    w = (rng.rand(OC, C, KH, KW).astype(np.float32) - 0.5) * 10
+    b = (rng.rand(OC).astype(np.float32) - 0.5) * 10
+    if prec == "bf16":
+        x, w = torch.from_numpy(x).to(torch.bfloat16).float().numpy(), torch.from_numpy(w).to(torch.bfloat16).float().numpy()
+    ref64 = oracle.conv_fwd(x, w, b, (1, 1), (py, px), relu=True, acc64=True)
+    outs = {}
+    for name, kw in (("halo", dict(use_streamk=0)), ("halo_sk", dict(use_streamk=2)), ("planned", dict()), ("im2col_sk", dict(use_halo=0, use_streamk=2)),
+                     ("im2col", dict(use_halo=0, use_streamk=0)), ("pair_r1", dict(use_sk4=0))):
+        r = OpRunner(prec=prec, **kw)
+        try:
+            outs[name] = r.run_conv(conv_op_text(N, C, H, W, OC, KH, KW, 1, 1, py, px, 1), x, w, b, ref64.shape, iters=2)  # twice: the stream-K flags must be reset for the next launch
+        finally:
+            r.close()
+        assert oracle.mrd(ref64, outs[name]) < TOL, (name, oracle.mrd(ref64, outs[name]))
+    n_tiles = -(-(N * (H + 2 * py - KH + 1) * (W + 2 * px - KW + 1)) // 128) * -(-OC // 128)
+    if n_tiles * 2 > 148:  # layers the round-1 planner ran on its pair kernel (fewer tiles: its one-CTA kernel with split-K, another summation grouping)
+        assert np.array_equal(outs["im2col"], outs["pair_r1"])
 
 
 def test_sgemm_cluster_multicast(oracle):

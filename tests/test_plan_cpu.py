@@ -127,17 +127,30 @@ def test_join_rules_on_a_prototxt_block(bb):
 
 
 def test_alexnet_launch_plans_match_the_measured_launch_list(bb):
-    """The per-layer launch plans (tile width from the wave-aware cost model, CTA pairs vs single CTAs, swapped + split-K for the inner-product
-    layers) equal what ncu saw on the B200: profiles/launches_r01_final_ncu_graph_nodes.md -- igemm_umma_2cta_kernel<96|128, 2> with grids
-    148 / 148 / 132 / 132 / 132 for conv1..conv5, igemm_umma_kernel<32, 2> with grids (32,1,4), (32,1,4), (8,1,8) for fc6..fc8."""
+    """The per-layer launch plans. Round-2 kernel (igemm4.cuh, the default): conv1 in its im2col mode (row-merged operand), conv2-5 in halo mode,
+    fc6-8 with the weights as the 128-row operand; stream-K where whole tiles would leave more than 8 % of a round idle (conv3/4: 75 tiles on 74
+    pairs, conv5: 50, the inner-product layers: 16 / 16 / 4 tiles). With use_sk4=0 the round-1 plans, which equal what ncu saw on the B200
+    (profiles/launches_r01_final_ncu_graph_nodes.md): igemm_umma_2cta_kernel<96|128, 2> with grids 148 / 148 / 132 / 132 / 132 for conv1..conv5,
+    igemm_umma_kernel<32, 2> with grids (32,1,4), (32,1,4), (8,1,8) for fc6..fc8."""
     from boda_b200 import nets
     txt, i, o = nets.alexnet_ng_conv(32)
-    plan = bb.fwd_plan(txt, "")
-    got = [(f.split("__")[1], {k[5:]: v for k, v in a.items() if k.startswith("plan:")}) for f, a in plan["calls"] if f.startswith("conv__")]
-    want = [("conv1", "pair", 96, "148x1x1", 11), ("conv2", "pair", 128, "148x1x1", 50), ("conv3", "pair", 128, "132x1x1", 36), ("conv4", "pair", 128, "132x1x1", 54),
-            ("conv5", "pair", 96, "132x1x1", 54), ("fc6-conv", "single", 32, "32x1x4", 144), ("fc7-conv", "single", 32, "32x1x4", 64), ("fc8-conv", "single", 32, "8x1x8", 64)]
-    assert [(t, p["kernel"], int(p["bn"]), p["grid"], int(p["kblks"])) for t, p in got] == want
+
+    def plans(opts):
+        plan = bb.fwd_plan(txt, opts)
+        return plan, [(f.split("__")[1], {k[5:]: v for k, v in a.items() if k.startswith("plan:")}) for f, a in plan["calls"] if f.startswith("conv__")]
+    plan, got = plans("")
+    want = [("conv1", "im2col", 96, 379, 1, 11), ("conv2", "halo", 128, 210, 0, 50), ("conv3", "halo", 128, 75, 1, 36), ("conv4", "halo", 128, 75, 1, 54),
+            ("conv5", "halo", 128, 50, 1, 54), ("fc6-conv", "2d", 32, 16, 1, 144), ("fc7-conv", "2d", 32, 16, 1, 64), ("fc8-conv", "2d", 32, 4, 1, 64)]
+    assert all(p["kernel"] == "sk4" and p["grid"] == "148x1x1" for _, p in got), got
+    assert [(t, p["mode"], int(p["bn"]), int(p["tiles"]), int(p["streamk"]), int(p["kblks"])) for t, p in got] == want
     assert [int(p["swapped"]) for _, p in got] == [0, 0, 0, 0, 0, 1, 1, 1] and [int(p["rowmerge"]) for _, p in got] == [1, 0, 0, 0, 0, 0, 0, 0]
+    # producers write their consumers' planes in the consumer's layout: pool1 -> conv2 (5x5, pad 2), pool2 -> conv3, conv3 -> conv4, conv4 -> conv5 (3x3, pad 1)
+    pads = {f.split("__")[1]: (a.get("out_pack_py"), a.get("out_pack_px")) for f, a in plan["calls"] if "out_pack" in a}
+    assert pads == {"pool1": ("2", "2"), "pool2": ("1", "1"), "conv3": ("1", "1"), "conv4": ("1", "1"), "pool5": (None, None)}, pads
+    _, got1 = plans("(use_sk4=0)")
+    want1 = [("conv1", "pair", 96, "148x1x1", 11), ("conv2", "pair", 128, "148x1x1", 50), ("conv3", "pair", 128, "132x1x1", 36), ("conv4", "pair", 128, "132x1x1", 54),
+             ("conv5", "pair", 96, "132x1x1", 54), ("fc6-conv", "single", 32, "32x1x4", 144), ("fc7-conv", "single", 32, "32x1x4", 64), ("fc8-conv", "single", 32, "8x1x8", 64)]
+    assert [(t, p["kernel"], int(p["bn"]), p["grid"], int(p["kblks"])) for t, p in got1] == want1
     # a smaller chip (plan_num_sms) re-plans: fewer SM pairs -> fewer persistent clusters
     small = bb.fwd_plan(txt, "(plan_num_sms=64)")
     g = dict(next(a for f, a in small["calls"] if f.startswith("conv__conv2__")))
