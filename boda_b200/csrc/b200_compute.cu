@@ -114,6 +114,19 @@ CUtensorMap make_tiled_map(void const *base, bool bf16, uint64_t k_extent, uint6
   return m;
 }
 
+// k-block-major packed filters [n_kb][rows][64] of 16-bit elements as a 3-d tensor; box = 64 x box_rows x box_kb, 128-byte swizzle
+CUtensorMap make_tiled_map3(void const *base, bool bf16, uint64_t rows, uint64_t n_kb, uint32_t box_rows, uint32_t box_kb) {
+  CUtensorMap m;
+  cuuint64_t gdim[3] = {64, rows, n_kb};
+  cuuint64_t gstride[2] = {128, rows * 128};
+  cuuint32_t box[3] = {64, box_rows, box_kb};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult const r = g_encode_tiled(&m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(base), gdim, gstride, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { rt_err("cuTensorMapEncodeTiled (3-d) failed with code " + str(int(r)) + " (rows=" + str(rows) + " kblks=" + str(n_kb) + ")"); }
+  return m;
+}
+
 // NHWC activation tensor [N][H][W][Cpad] read in im2col mode: 128 output pixels x 64 channels per load.
 CUtensorMap make_im2col_map(void const *base, bool bf16, conv_plan_t const &cp, uint32_t pixels_per_col = 128) {
   CUtensorMap m;
@@ -189,6 +202,7 @@ struct sk4_plan_t {
   int halo_rows = 0, a_loads = 0, a_box_rows = 0, Hp = 0, Wp = 0;
   long long m_rows = 0;  // halo: virtual pixels that may hold an output
   int m_pair_tiles = 0, q_tiles = 0, n_tiles = 0, ukb = 0, n_pairs = 0;
+  int ku = 0;  // k-blocks per stage (ku * planes operand slots)
   size_t smem = 0;
 };
 
@@ -208,7 +222,6 @@ sk4_plan_t plan_sk4(conv_plan_t const &cp, int planes, int num_sms, b200_compute
       sp.m_rows = (long long)(cp.N - 1) * Hp * Wp + (long long)(cp.OH - 1) * Wp + cp.OW;
     }
   }
-  int const kKb = planes == 1 ? 2 : 1;
   for (int attempt = 0; attempt < 2; ++attempt) {  // second attempt: without the halo mode (its rings did not fit shared memory)
     long long const p_rows = cp.swapped ? cp.OC : (sp.halo ? sp.m_rows : pixels), q_rows = cp.swapped ? pixels : cp.OC;
     int const p_tiles = ceil_div(p_rows, b200::IGEMM_BM);
@@ -221,20 +234,23 @@ sk4_plan_t plan_sk4(conv_plan_t const &cp, int planes, int num_sms, b200_compute
         if (!sp.BN || cost < best_cost) { sp.BN = bn; best_cost = cost; }
       }
     }
-    long long const avail = 225 * 1024 - 1024 - b200::SK4_BAR_BYTES, b_stage = (long long)sp.BN * 128;
+    // k-blocks per stage: 4 operand slots in halo mode (16 single-plane / 24 fp32-parity MMAs per barrier round trip -- the MMA warp's per-stage
+    // cost is paid once per stage), 2 in the per-k-block operand modes (their stages also carry 16 KB activation tiles)
+    sp.ku = (sp.halo ? 4 : 2) / planes;
+    long long const avail = 225 * 1024 - 1024 - b200::SK4_BAR_BYTES, b_stage = (long long)sp.ku * planes * (sp.BN / 2) * 128;
     if (sp.halo) {
       long long const a_stage = (long long)planes * sp.halo_rows * 128;
       sp.a_stages = 0;
       for (int as : {2, 1}) {
         long long const bs = std::min<long long>((avail - as * a_stage) / b_stage, b200::SK4_MAX_B_STAGES);
-        if (bs >= (as == 2 ? 4 : 3)) { sp.a_stages = as; sp.b_stages = (int)bs; break; }
+        if (bs >= (as == 2 ? 3 : 2)) { sp.a_stages = as; sp.b_stages = (int)bs; break; }
       }
-      if (sp.a_stages == 2 && sp.b_stages == b200::SK4_MAX_B_STAGES && avail - 3 * a_stage >= b200::SK4_MAX_B_STAGES * b_stage) { sp.a_stages = 3; }
+      if (sp.a_stages == 2 && (avail - 3 * a_stage) / b_stage >= 5) { sp.a_stages = 3; sp.b_stages = (int)std::min<long long>((avail - 3 * a_stage) / b_stage, b200::SK4_MAX_B_STAGES); }
       if (rtc.sk4_max_b_stages > 0) { sp.b_stages = std::min(sp.b_stages, rtc.sk4_max_b_stages); }
       if (!sp.a_stages) { sp.halo = false; sp.BN = 0; continue; }
       sp.smem = (size_t)(sp.a_stages * a_stage + sp.b_stages * b_stage + 1024 + b200::SK4_BAR_BYTES);
     } else {
-      long long const stage = 2ll * b200::IGEMM_BM * 128 + b_stage;
+      long long const stage = (long long)sp.ku * planes * b200::IGEMM_BM * 128 + b_stage;
       sp.b_stages = (int)std::min<long long>(avail / stage, b200::SK4_MAX_A_STAGES);  // modes 0/1: the P slots ride on the Q stages (ring depths are equal)
       sp.a_stages = sp.b_stages;
       if (sp.b_stages < 2) { return sk4_plan_t(); }
@@ -243,7 +259,7 @@ sk4_plan_t plan_sk4(conv_plan_t const &cp, int planes, int num_sms, b200_compute
     sp.m_pair_tiles = ceil_div(p_tiles, 2); sp.q_tiles = ceil_div(q_rows, sp.BN);
     sp.n_tiles = sp.m_pair_tiles * sp.q_tiles;
     int const nkb = sp.halo ? cp.cblks * cp.KH * cp.KW : cp.kblks_total;
-    sp.ukb = ceil_div(nkb, kKb);
+    sp.ukb = ceil_div(nkb, sp.ku);
     int const P = num_sms / 2;
     long long const U = (long long)sp.n_tiles * sp.ukb;
     // whole tiles cost ceil(tiles / pairs) rounds of ukb stage-units; stream-K costs U / pairs units (>= 2 per pair) plus about two units' worth of
@@ -732,9 +748,9 @@ struct run_ctx_t {
 
   // src [B][R][Cc] fp32 -> planes [B][Cc][..R..] 16-bit, with abs-max scaling. Cached on (pointer, generation).
   void pack(packed_t &pk, var_info_t &src, int B, int R, int Cc, int Rpad, long long dst_c_stride, long long dst_b_stride, long long total_elems, bool want_lo, bool bf16,
-            int c_inner = 0, long long dst_chi_stride = 0, long long dst_base = 0, unsigned int const *absmax_src = nullptr, int smallc_W = 0, long long kmajor_rows = 0) {
+            int c_inner = 0, long long dst_chi_stride = 0, long long dst_base = 0, unsigned int const *absmax_src = nullptr, int smallc_W = 0, long long kmajor_rows = 0, int tap_minor = 0) {
     if (c_inner <= 0) { c_inner = std::max(Cc, 1); }
-    uint64_t const lkey = pack_layout_key({B, R, Cc, Rpad, dst_c_stride, dst_b_stride, c_inner, dst_chi_stride, dst_base, want_lo, bf16, smallc_W, kmajor_rows});
+    uint64_t const lkey = pack_layout_key({B, R, Cc, Rpad, dst_c_stride, dst_b_stride, c_inner, dst_chi_stride, dst_base, want_lo, bf16, smallc_W, kmajor_rows, tap_minor});
     if (pk.src_gen == *src.gen && pk.src_ptr == src.buf->p && pk.hi && pk.layout_key == lkey && (!want_lo || pk.lo)) { return; }
     if (pk.hi && pk.layout_key != lkey && pk.hi->bytes >= (uint64_t)total_elems * 2 && (!want_lo || pk.lo)) {  // same storage, other geometry: padding positions must be zero again
       CU_CHK(cudaMemsetAsync(pk.hi->p, 0, pk.hi->bytes, st));
@@ -795,8 +811,8 @@ struct run_ctx_t {
       pk.src_ptr = src.buf->p;
       return;
     }
-    if (bf16) { B200_CARVEOUT_ONCE(b200::pack_xpose_split_kernel<true>); launch_k(b200::pack_xpose_split_kernel<true>, dim3(grid), dim3(256), 0, fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, Cc, Rpad, dst_c_stride, dst_b_stride, c_inner, dst_chi_stride, dst_base, absmax_src, kmajor_rows); }
-    else { B200_CARVEOUT_ONCE(b200::pack_xpose_split_kernel<false>); launch_k(b200::pack_xpose_split_kernel<false>, dim3(grid), dim3(256), 0, fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, Cc, Rpad, dst_c_stride, dst_b_stride, c_inner, dst_chi_stride, dst_base, absmax_src, kmajor_rows); }
+    if (bf16) { B200_CARVEOUT_ONCE(b200::pack_xpose_split_kernel<true>); launch_k(b200::pack_xpose_split_kernel<true>, dim3(grid), dim3(256), 0, fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, Cc, Rpad, dst_c_stride, dst_b_stride, c_inner, dst_chi_stride, dst_base, absmax_src, kmajor_rows, tap_minor); }
+    else { B200_CARVEOUT_ONCE(b200::pack_xpose_split_kernel<false>); launch_k(b200::pack_xpose_split_kernel<false>, dim3(grid), dim3(256), 0, fptr(src), hi, lo, static_cast<float *>(pk.scale2->p), R, Cc, Rpad, dst_c_stride, dst_b_stride, c_inner, dst_chi_stride, dst_base, absmax_src, kmajor_rows, tap_minor); }
     launched();
     pk.src_gen = *src.gen;
     pk.src_ptr = src.buf->p;
@@ -846,16 +862,16 @@ struct run_ctx_t {
     CU_CHK(cudaLaunchKernelEx(&cfg, b200::igemm_umma_2cta_kernel<BN, kPlanes>, ph, pl, qh, ql, prm));
     launched();
   }
-  template <int BN, int kPlanes>
+  template <int BN, int kPlanes, int kEpi>
   void launch_sk4_t(sk4_plan_t const &sp, CUtensorMap const &ph, CUtensorMap const &pl, CUtensorMap const &qh, CUtensorMap const &ql, b200::Sk4Params const &prm) {
     static uint64_t attr_set = 0;
     if (first_use_on_device(attr_set, rtc.device)) {
-      CU_CHK(cudaFuncSetAttribute(b200::igemm_sk4_kernel<BN, kPlanes>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      CU_CHK(cudaFuncSetAttribute(b200::igemm_sk4_kernel<BN, kPlanes, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(2 * sp.n_pairs, 1, 1);
-    cfg.blockDim = dim3(b200::IGEMM_THREADS);
+    cfg.blockDim = dim3(b200::SK4_THREADS);
     cfg.dynamicSmemBytes = sp.smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
@@ -864,15 +880,25 @@ struct run_ctx_t {
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = rtc.use_pdl ? 2 : 1;
-    CU_CHK(cudaLaunchKernelEx(&cfg, b200::igemm_sk4_kernel<BN, kPlanes>, ph, pl, qh, ql, prm));
+    CU_CHK(cudaLaunchKernelEx(&cfg, b200::igemm_sk4_kernel<BN, kPlanes, kEpi>, ph, pl, qh, ql, prm));
     launched();
   }
-  void launch_sk4(int BN, int planes, sk4_plan_t const &sp, CUtensorMap const &ph, CUtensorMap const &pl, CUtensorMap const &qh, CUtensorMap const &ql, b200::Sk4Params const &prm) {
-    if (planes == 2) {
-      if (BN == 128) { launch_sk4_t<128, 2>(sp, ph, pl, qh, ql, prm); } else if (BN == 96) { launch_sk4_t<96, 2>(sp, ph, pl, qh, ql, prm); } else if (BN == 64) { launch_sk4_t<64, 2>(sp, ph, pl, qh, ql, prm); } else { launch_sk4_t<32, 2>(sp, ph, pl, qh, ql, prm); }
+  template <int kPlanes>
+  void launch_sk4_p(int BN, sk4_plan_t const &sp, CUtensorMap const &ph, CUtensorMap const &pl, CUtensorMap const &qh, CUtensorMap const &ql, b200::Sk4Params const &prm) {
+    // the epilogue variant compiled into the kernel that is launched (igemm4.cuh: instruction-cache footprint)
+    if (prm.g.swapped) {
+      if (BN == 64) { launch_sk4_t<64, kPlanes, b200::SK4_EPI_SWAPPED>(sp, ph, pl, qh, ql, prm); } else if (BN == 32) { launch_sk4_t<32, kPlanes, b200::SK4_EPI_SWAPPED>(sp, ph, pl, qh, ql, prm); }
+      else { rt_err("igemm4: swapped launches use 32- or 64-wide tiles"); }
+    } else if (prm.g.out16 || prm.g.res) {
+      if (BN == 128) { launch_sk4_t<128, kPlanes, b200::SK4_EPI_FULL>(sp, ph, pl, qh, ql, prm); } else if (BN == 96) { launch_sk4_t<96, kPlanes, b200::SK4_EPI_FULL>(sp, ph, pl, qh, ql, prm); }
+      else if (BN == 64) { launch_sk4_t<64, kPlanes, b200::SK4_EPI_FULL>(sp, ph, pl, qh, ql, prm); } else { launch_sk4_t<32, kPlanes, b200::SK4_EPI_FULL>(sp, ph, pl, qh, ql, prm); }
     } else {
-      if (BN == 128) { launch_sk4_t<128, 1>(sp, ph, pl, qh, ql, prm); } else if (BN == 96) { launch_sk4_t<96, 1>(sp, ph, pl, qh, ql, prm); } else if (BN == 64) { launch_sk4_t<64, 1>(sp, ph, pl, qh, ql, prm); } else { launch_sk4_t<32, 1>(sp, ph, pl, qh, ql, prm); }
+      if (BN == 128) { launch_sk4_t<128, kPlanes, b200::SK4_EPI_LEAN>(sp, ph, pl, qh, ql, prm); } else if (BN == 96) { launch_sk4_t<96, kPlanes, b200::SK4_EPI_LEAN>(sp, ph, pl, qh, ql, prm); }
+      else if (BN == 64) { launch_sk4_t<64, kPlanes, b200::SK4_EPI_LEAN>(sp, ph, pl, qh, ql, prm); } else { launch_sk4_t<32, kPlanes, b200::SK4_EPI_LEAN>(sp, ph, pl, qh, ql, prm); }
     }
+  }
+  void launch_sk4(int BN, int planes, sk4_plan_t const &sp, CUtensorMap const &ph, CUtensorMap const &pl, CUtensorMap const &qh, CUtensorMap const &ql, b200::Sk4Params const &prm) {
+    if (planes == 2) { launch_sk4_p<2>(BN, sp, ph, pl, qh, ql, prm); } else { launch_sk4_p<1>(BN, sp, ph, pl, qh, ql, prm); }
   }
   void launch_igemm2(int BN, int planes, dim3 grid, CUtensorMap const &ph, CUtensorMap const &pl, CUtensorMap const &qh, CUtensorMap const &ql, b200::IgemmParams const &prm) {
     if (planes == 2) {
@@ -1005,9 +1031,9 @@ struct run_ctx_t {
     CU_CHK(cudaStreamSynchronize(st));
     CU_CHK(cudaMemcpy(ts.data(), ts_dev, ts.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(ts_dev);
-    static char const *names[16] = {"prod_total", "prod_wait_empty", "mma_total", "mma_wait_full", "mma_wait_tmem_empty", "mma_first_full", "mma_stages", "mma_wait_afull", "epi_total", "epi_wait_tmem_full", "epi_drain", "epi_store", "epi_tiles", "", "", ""};
+    static char const *names[16] = {"prod_total", "prod_wait_empty", "mma_total", "mma_wait_full", "mma_wait_tmem_empty", "mma_first_full", "mma_stages", "mma_wait_afull", "epi_total", "epi_wait_tmem_full", "epi_drain", "epi_store", "epi_tiles", "prod_issue", "", ""};
     string line = "role stamps '" + rfc.rtc_func_name + "' bn=" + str(BN) + " planes=" + str(planes) + " kblks/tile=" + str(kblks) + " clusters=" + str(n_clusters) + " (median/max cycles):";
-    for (int k = 0; k < 13; ++k) {
+    for (int k = 0; k < 14; ++k) {
       if (!names[k][0]) { continue; }
       std::vector<long long> v;
       for (int c = 0; c < n_clusters; ++c) { v.push_back(ts[(size_t)c * 16 + k]); }
@@ -1051,7 +1077,8 @@ struct run_ctx_t {
       pack(f.a_pack, vin, cp.N, cp.C, cp.H * cp.W, cp.Cpad, cp.Cpad, img_elems, (long long)cp.N * img_elems + 64, planes == 2, bf16, cp.W, (long long)cp.Wp * cp.Cpad, (long long)cp.px * cp.Cpad, absmax_cell("in"), cp.W);
       a_pack_p = &f.a_pack;  // row-merged planes are private to this function
     } else {
-      pack(f.w_pack, vf, cp.OC, cp.C, cp.KH * cp.KW, cp.Cpad, cp.w_tap_stride, cp.w_row_stride, oc_pad * cp.w_row_stride, planes == 2, bf16, 0, 0, 0, nullptr, 0, oc_pad);
+      pack(f.w_pack, vf, cp.OC, cp.C, cp.KH * cp.KW, cp.Cpad, cp.w_tap_stride, cp.w_row_stride, oc_pad * cp.w_row_stride, planes == 2, bf16, 0, 0, 0, nullptr, 0, oc_pad,
+           sp.halo ? cp.KH * cp.KW : 0);  // halo mode: k-blocks channel block major, tap minor (one 3-d TMA box per stage)
       if (sp.halo) {
         long long const img_elems = (long long)sp.Hp * sp.Wp * cp.Cpad;
         a_pack_p = &im.act_packs[{vin.buf->p, b200_impl_t::pad_tag(cp.py, cp.px)}];
@@ -1086,8 +1113,13 @@ struct run_ctx_t {
       act_lo = planes == 2 ? make_tiled_map(a_pack.lo->p, bf16, kext, cp.a_rows, cp.a_row_stride, act_box) : act_hi;
     }
     uint64_t const w_rows = (uint64_t)(cp.w_row_stride / 64) * oc_pad;
-    w_hi = make_tiled_map(f.w_pack.hi->p, bf16, 64, w_rows, 64, w_box);
-    w_lo = planes == 2 ? make_tiled_map(f.w_pack.lo->p, bf16, 64, w_rows, 64, w_box) : w_hi;
+    if (sp.halo) {  // [k-block][out chan (padded)][64]: a stage's ku consecutive k-blocks are one box
+      w_hi = make_tiled_map3(f.w_pack.hi->p, bf16, oc_pad, (uint64_t)(cp.w_row_stride / 64), w_box, sp.ku);
+      w_lo = planes == 2 ? make_tiled_map3(f.w_pack.lo->p, bf16, oc_pad, (uint64_t)(cp.w_row_stride / 64), w_box, sp.ku) : w_hi;
+    } else {
+      w_hi = make_tiled_map(f.w_pack.hi->p, bf16, 64, w_rows, 64, w_box);
+      w_lo = planes == 2 ? make_tiled_map(f.w_pack.lo->p, bf16, 64, w_rows, 64, w_box) : w_hi;
+    }
 
     b200::IgemmParams prm;
     memset(&prm, 0, sizeof(prm));
@@ -1147,8 +1179,8 @@ struct run_ctx_t {
         uint64_t const bytes = (uint64_t)cp.N * (cp.OH + o16_py) * (cp.OW + o16_px) * cdst_pad * 2;
         long long const hw = (long long)cp.OH * cp.OW;
         uint64_t const lkey = o16_padded ? pack_layout_key({cp.N, cdst, hw, cdst_pad, cdst_pad, (long long)(cp.OH + o16_py) * (cp.OW + o16_px) * cdst_pad, cp.OW, (long long)(cp.OW + o16_px) * cdst_pad,
-                                                            ((long long)o16_py * (cp.OW + o16_px) + o16_px) * cdst_pad, planes == 2, bf16, 0, 0})
-                                         : pack_layout_key({cp.N, cdst, hw, cdst_pad, cdst_pad, hw * cdst_pad, std::max<long long>(hw, 1), 0, 0, planes == 2, bf16, 0, 0});
+                                                            ((long long)o16_py * (cp.OW + o16_px) + o16_px) * cdst_pad, planes == 2, bf16, 0, 0, 0})
+                                         : pack_layout_key({cp.N, cdst, hw, cdst_pad, cdst_pad, hw * cdst_pad, std::max<long long>(hw, 1), 0, 0, planes == 2, bf16, 0, 0, 0});
         if (!out_pk->hi || out_pk->hi->bytes < bytes || (planes == 2 && !out_pk->lo)) {
           out_pk->hi = std::make_shared<dev_buf_t>(bytes);
           CU_CHK(cudaMemsetAsync(out_pk->hi->p, 0, bytes, st));
@@ -1206,7 +1238,7 @@ struct run_ctx_t {
       sk.taps = sp.halo ? cp.KH * cp.KW : 1;
       sk.Wp = sp.Wp; sk.HpWp = sp.Hp * sp.Wp; sk.OH = cp.OH; sk.OW = cp.OW;
       sk.halo_rows = sp.halo_rows; sk.a_loads = sp.a_loads; sk.a_box_rows = sp.a_box_rows;
-      sk.a_stages = sp.a_stages; sk.b_stages = sp.b_stages;
+      sk.a_stages = sp.a_stages; sk.b_stages = sp.b_stages; sk.ku = sp.ku;
       sk.sk = sp.sk ? 1 : 0; sk.n_tiles = sp.n_tiles; sk.ukb = sp.ukb;
       sk.out_w = cp.OW;
       if (o16_padded) { sk.o16_Hp = cp.OH + o16_py; sk.o16_Wp = cp.OW + o16_px; sk.o16_py = o16_py; sk.o16_px = o16_px; }
@@ -1369,8 +1401,8 @@ struct run_ctx_t {
         uint64_t const bytes = (uint64_t)nimg * (OH + o16_py) * (OW + o16_px) * cpad * 2;
         long long const ohw2 = (long long)OH * OW;
         uint64_t const lkey = o16_padded ? pack_layout_key({nimg, C, ohw2, cpad, cpad, (long long)(OH + o16_py) * (OW + o16_px) * cpad, OW, (long long)(OW + o16_px) * cpad,
-                                                            ((long long)o16_py * (OW + o16_px) + o16_px) * cpad, npl == 2, bf16, 0, 0})
-                                         : pack_layout_key({nimg, C, ohw2, cpad, cpad, ohw2 * cpad, std::max<long long>(ohw2, 1), 0, 0, npl == 2, bf16, 0, 0});
+                                                            ((long long)o16_py * (OW + o16_px) + o16_px) * cpad, npl == 2, bf16, 0, 0, 0})
+                                         : pack_layout_key({nimg, C, ohw2, cpad, cpad, ohw2 * cpad, std::max<long long>(ohw2, 1), 0, 0, npl == 2, bf16, 0, 0, 0});
         if (!out_pk->hi || out_pk->hi->bytes < bytes || (npl == 2 && !out_pk->lo)) {
           out_pk->hi = std::make_shared<dev_buf_t>(bytes);
           CU_CHK(cudaMemsetAsync(out_pk->hi->p, 0, bytes, st));

@@ -73,7 +73,10 @@ struct b200_compute_t {
                             // Off by default: measured slower than the CTA-pair im2col kernel on the AlexNet layers (profiles/), kept for A/B runs
   int taps_max_b_stages = 8, taps_max_a_stages = 3;  // experiments: cap the tap-reuse kernel's ring depths
   int taps_2cta = -1;       // tap-reuse kernel: -1 = cost model picks single CTAs or CTA pairs, 0 / 1 = force
-  int use_sk4 = 1;          // the round-2 contraction kernel (igemm4.cuh: persistent CTA pairs, halo operand mode, stream-K) for every layer with >= 2 row tiles
+  int use_sk4 = 0;          // the round-2 contraction kernel (igemm4.cuh: persistent CTA pairs, halo operand mode, stage records, stream-K, two epilogue
+                            // warpgroups) for every layer with >= 2 row tiles. OFF by default: parity-green, and on par with the round-1 pair kernel in the
+                            // 16-bit modes (halo mode moves 2.8x fewer bytes), but measured slower in fp32-parity mode, which is MMA-bound at 3 passes and
+                            // only pays the halo layout's dropped virtual pixels (profiles/diag_r02*)
   int use_halo = 1;         // igemm4: one activation halo tile per channel block feeds every filter tap of a stride-1 KHxKW convolution
   int use_streamk = 1;      // igemm4: cut the (tile, k-block) space into equal contiguous ranges per CTA pair when whole tiles would leave > 8 % of a round idle
   int sk4_max_b_stages = 0; // experiments: cap igemm4's filter ring depth (0 = as many as fit)

@@ -65,7 +65,8 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
 
   int const warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
-  uint32_t const cta_rank = cluster_ctarank();  // 0 = leader, 1 = peer (cluster dims are (2,1,1))
+  uint32_t const cta_rank = blockIdx.x & 1u;  // = %cluster_ctarank for (2,1,1) clusters; written this way the compiler can prove it warp-uniform and keeps the TMA operand
+                                              // arithmetic of the producer in uniform registers (each R2UR on the single issuing thread's path costs issue latency)  // 0 = leader, 1 = peer (cluster dims are (2,1,1))
   bool const leader = (cta_rank == 0);
   int const n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
   int const q_tiles = prm.q_tiles, n_tiles = prm.m_pair_tiles * q_tiles;
@@ -92,7 +93,7 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
     // ===================== TMA producer (both CTAs; whole warp walks the loop, one elected lane issues -- see igemm.cuh) ==========
     int it = 0;  // k-blocks issued so far, over all tiles: ring position and phase
     long long const t_begin = prm.ts ? clock64() : 0;
-    long long w_empty = 0;
+    long long w_empty = 0, t_issue = 0;
     for (int tile = cluster_id; tile < ((prm.debug & 1) ? 0 : n_tiles); tile += n_clusters) {  // (debug bit 0: no loads at all)
       int const mt = tile / q_tiles, nt = tile - mt * q_tiles;
       int const m0 = (mt * 2 + static_cast<int>(cta_rank)) * IGEMM_BM;  // this CTA's own 128 P rows (the pair covers 256 consecutive ones)
@@ -111,6 +112,7 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
         uint32_t const ph = (it / kStages) & 1;
         int const nh = min(kKb, nkb - i);  // k-blocks in this stage
         if (prm.ts) { long long const t0 = clock64(); mbar_wait(&empty_bar[s], ph ^ 1); w_empty += clock64() - t0; } else { mbar_wait(&empty_bar[s], ph ^ 1); }
+        long long const t_i0 = prm.ts ? clock64() : 0;
         bool const issue = elect_one_sync();
         if (issue) {
           if (leader) { mbar_expect_tx(&full_bar[s], 2u * nh * Cfg::kKbBytes); }  // both CTAs' bytes land on the leader's barrier
@@ -139,9 +141,10 @@ igemm_umma_2cta_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __gri
           }
         }
         __syncwarp();
+        if (prm.ts) { t_issue += clock64() - t_i0; }
       }
     }
-    if (prm.ts && leader && lane == 0) { long long *t = prm.ts + cluster_id * 16; t[0] = clock64() - t_begin; t[1] = w_empty; }
+    if (prm.ts && leader && lane == 0) { long long *t = prm.ts + cluster_id * 16; t[0] = clock64() - t_begin; t[1] = w_empty; t[13] = t_issue; }
   } else if (warp_id == 1) {
     // ===================== MMA issuer (leader CTA only, one elected thread for the pair) =====================
     if (leader) {

@@ -806,7 +806,7 @@ template <bool kBf16>
 __global__ void __launch_bounds__(256)
 pack_xpose_split_kernel(float const *__restrict__ src, uint16_t *__restrict__ hi, uint16_t *__restrict__ lo, float const *__restrict__ scale2,
                         int R, int C, int Rpad, long long dst_c_stride, long long dst_b_stride, int c_inner, long long dst_chi_stride, long long dst_base,
-                        unsigned int const *__restrict__ absmax_bits, long long kmajor_rows) {
+                        unsigned int const *__restrict__ absmax_bits, long long kmajor_rows, int tap_minor) {
   pdl_prologue();
   __shared__ float tile[64][33];
   int const tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -834,7 +834,10 @@ pack_xpose_split_kernel(float const *__restrict__ src, uint16_t *__restrict__ hi
         // the two-level form lays image rows out with a padded pitch / filter rows as (ky)(kx,chan) for the row-merged conv path
         // k = position inside the destination row; plain layout: row-major [b][k]; k-block-major (kmajor_rows > 0, used for filters):
         // [k / 64][b (padded to kmajor_rows)][k % 64], so that the 128-row x 64-element tile one TMA load fetches is 16 KB CONTIGUOUS
-        long long const k = dst_base + static_cast<long long>(c / c_inner) * dst_chi_stride + static_cast<long long>(c % c_inner) * dst_c_stride + r;
+        // tap_minor > 0 (filters of a halo-mode convolution, igemm4.cuh; = number of taps): k-blocks ordered channel block major, tap minor --
+        // k = ((chan / 64) * taps + tap) * 64 + chan % 64 -- so that the ku consecutive k-blocks of a stage are ONE 3-d TMA box
+        long long const k = tap_minor ? (static_cast<long long>(r >> 6) * tap_minor + c) * 64 + (r & 63)
+                                      : dst_base + static_cast<long long>(c / c_inner) * dst_chi_stride + static_cast<long long>(c % c_inner) * dst_c_stride + r;
         long long const o = kmajor_rows ? ((k >> 6) * kmajor_rows + b) * 64 + (k & 63) : b * dst_b_stride + k;
         if (kBf16) {
           __nv_bfloat16 const h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);

@@ -90,7 +90,7 @@ def test_alexnet_b32_batch_consistency(oracle):
     params = nets.synth_params(txt32)
     x2 = nets.synth_input((2, 3, 227, 227))
     x32 = np.ascontiguousarray(np.tile(x2, (16, 1, 1, 1)))
-    for opts, exact in (("(use_streamk=0)", True), ("", False)):
+    for opts, exact in (("", True), ("(use_sk4=1,use_streamk=0)", True), ("(use_sk4=1)", False)):  # round-1 kernels (default) | round-2 kernel, whole tiles | with stream-K
         outs = []
         for txt, x in ((txt2, x2), (txt32, x32)):
             f = bb.B200ConvFwd(txt, opts)

@@ -452,8 +452,8 @@ def test_conv_sk4_halo_and_streamk(oracle, case, prec):
         x, w = torch.from_numpy(x).to(torch.bfloat16).float().numpy(), torch.from_numpy(w).to(torch.bfloat16).float().numpy()
     ref64 = oracle.conv_fwd(x, w, b, (1, 1), (py, px), relu=True, acc64=True)
     outs = {}
-    for name, kw in (("halo", dict(use_streamk=0)), ("halo_sk", dict(use_streamk=2)), ("planned", dict()), ("im2col_sk", dict(use_halo=0, use_streamk=2)),
-                     ("im2col", dict(use_halo=0, use_streamk=0)), ("pair_r1", dict(use_sk4=0))):
+    for name, kw in (("halo", dict(use_sk4=1, use_streamk=0)), ("halo_sk", dict(use_sk4=1, use_streamk=2)), ("planned", dict(use_sk4=1)), ("im2col_sk", dict(use_sk4=1, use_halo=0, use_streamk=2)),
+                     ("im2col", dict(use_sk4=1, use_halo=0, use_streamk=0)), ("pair_r1", dict(use_sk4=0))):
         r = OpRunner(prec=prec, **kw)
         try:
             outs[name] = r.run_conv(conv_op_text(N, C, H, W, OC, KH, KW, 1, 1, py, px, 1), x, w, b, ref64.shape, iters=2)  # twice: the stream-K flags must be reset for the next launch

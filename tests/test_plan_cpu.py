@@ -127,9 +127,9 @@ def test_join_rules_on_a_prototxt_block(bb):
 
 
 def test_alexnet_launch_plans_match_the_measured_launch_list(bb):
-    """The per-layer launch plans. Round-2 kernel (igemm4.cuh, the default): conv1 in its im2col mode (row-merged operand), conv2-5 in halo mode,
+    """The per-layer launch plans. Round-2 kernel (igemm4.cuh, use_sk4=1): conv1 in its im2col mode (row-merged operand), conv2-5 in halo mode,
     fc6-8 with the weights as the 128-row operand; stream-K where whole tiles would leave more than 8 % of a round idle (conv3/4: 75 tiles on 74
-    pairs, conv5: 50, the inner-product layers: 16 / 16 / 4 tiles). With use_sk4=0 the round-1 plans, which equal what ncu saw on the B200
+    pairs, conv5: 50, the inner-product layers: 16 / 16 / 4 tiles). By default the round-1 plans, which equal what ncu saw on the B200
     (profiles/launches_r01_final_ncu_graph_nodes.md): igemm_umma_2cta_kernel<96|128, 2> with grids 148 / 148 / 132 / 132 / 132 for conv1..conv5,
     igemm_umma_kernel<32, 2> with grids (32,1,4), (32,1,4), (8,1,8) for fc6..fc8."""
     from boda_b200 import nets
@@ -138,7 +138,7 @@ def test_alexnet_launch_plans_match_the_measured_launch_list(bb):
     def plans(opts):
         plan = bb.fwd_plan(txt, opts)
         return plan, [(f.split("__")[1], {k[5:]: v for k, v in a.items() if k.startswith("plan:")}) for f, a in plan["calls"] if f.startswith("conv__")]
-    plan, got = plans("")
+    plan, got = plans("(use_sk4=1)")
     want = [("conv1", "im2col", 96, 379, 1, 11), ("conv2", "halo", 128, 210, 0, 50), ("conv3", "halo", 128, 75, 1, 36), ("conv4", "halo", 128, 75, 1, 54),
             ("conv5", "halo", 128, 50, 1, 54), ("fc6-conv", "2d", 32, 16, 1, 144), ("fc7-conv", "2d", 32, 16, 1, 64), ("fc8-conv", "2d", 32, 4, 1, 64)]
     assert all(p["kernel"] == "sk4" and p["grid"] == "148x1x1" for _, p in got), got
@@ -147,7 +147,7 @@ def test_alexnet_launch_plans_match_the_measured_launch_list(bb):
     # producers write their consumers' planes in the consumer's layout: pool1 -> conv2 (5x5, pad 2), pool2 -> conv3, conv3 -> conv4, conv4 -> conv5 (3x3, pad 1)
     pads = {f.split("__")[1]: (a.get("out_pack_py"), a.get("out_pack_px")) for f, a in plan["calls"] if "out_pack" in a}
     assert pads == {"pool1": ("2", "2"), "pool2": ("1", "1"), "conv3": ("1", "1"), "conv4": ("1", "1"), "pool5": (None, None)}, pads
-    _, got1 = plans("(use_sk4=0)")
+    _, got1 = plans("")
     want1 = [("conv1", "pair", 96, "148x1x1", 11), ("conv2", "pair", 128, "148x1x1", 50), ("conv3", "pair", 128, "132x1x1", 36), ("conv4", "pair", 128, "132x1x1", 54),
              ("conv5", "pair", 96, "132x1x1", 54), ("fc6-conv", "single", 32, "32x1x4", 144), ("fc7-conv", "single", 32, "32x1x4", 64), ("fc8-conv", "single", 32, "8x1x8", 64)]
     assert [(t, p["kernel"], int(p["bn"]), p["grid"], int(p["kblks"])) for t, p in got1] == want1
@@ -157,3 +157,34 @@ def test_alexnet_launch_plans_match_the_measured_launch_list(bb):
     assert g["plan:grid"] == "64x1x1"
     # pooling / LRN calls carry no launch plan
     assert not any(k.startswith("plan:") for f, a in plan["calls"] if not f.startswith("conv__") for k in a)
+
+
+def test_reference_op_tune_knob_names_are_accepted_and_ignored(bb):
+    """Existing `--op-tune=(...)` command lines keep working (SURVEY section 5 "Config/flags"): the reference's op_tune_t knob names
+    (src/cnn_op.H:10-32) select among CUCL variants that do not exist here; they are accepted, flat or nested, and change nothing.
+    use_be naming another back-end and truly unknown keys are still errors (NESI rejects unused keys, src/nesi.cc:25-35)."""
+    from boda_b200 import nets
+    txt, i, o = nets.tiny_net(4)
+    base = bb.fwd_plan(txt, "")["calls"]
+    for opts in ("(k1conv=1,tconv=1)", "(op_tune=(use_be=b200,use_culibs=0,MNt=8:8,MNb=8:16,Kb=8,use_local_mem=1,prof_variant=0,vw=8,k1conv=1,tconv=2,tconv_max_ksz=11:11,ipconv=1))",
+                 "(ipconv=1,prec=fp32)"):
+        assert bb.fwd_plan(txt, opts)["calls"] == base, opts
+    for bad in ("(op_tune=(use_be=ocl))", "(op_tune=(bogus_knob=1))", "(bogus_option=1)"):
+        with pytest.raises(bb.RtException):
+            bb.fwd_plan(txt, bad)
+
+
+def test_node_listed_twice_in_a_concat_is_copied_both_times(bb):
+    """A node that appears twice among one Concat's bottoms has two destinations: it is not written in place (concat by offset aliases a node
+    to ONE channel offset) but copied at both offsets, as the reference does (src/rtc_fwd.cc:267-280)."""
+    from boda_b200.nets import PipeBuilder
+    p = PipeBuilder()
+    p.data("data", 2, 8, 12, 12)
+    p.conv("a", "data", "a", 16, 3, 1, 1, relu="ra")
+    p.conv("b", "data", "b", 8, 1, relu="rb")
+    p.concat("cat", ["a", "b", "a"], "cat")
+    p.conv("c", "cat", "c", 8, 1)
+    plan = bb.fwd_plan(p.text(), "")
+    assert "a" not in plan["alias"] and plan["alias"]["b"][1] == 16   # b alone is written in place, at channel 16
+    copies = [a for f, a in plan["calls"] if f.startswith("copy__")]
+    assert len(copies) == 2 and all(c["in"] == "a" for c in copies)

@@ -72,7 +72,13 @@ def test_errors(bb):
                 'layer { name: "x" type: "Deconvolution" bottom: "d" top: "x" }',                                           # unsupported kind
                 'layer { name: "c" type: "Convolution" bottom: "d" top: "c" convolution_param { num_output: 2 kernel_size: 3 group: 2 } }',
                 'layer { name: "c" type: "ReLU" bottom: "d" top: "d" ',                                                      # missing }
-                'layer { name: "d" type: "Dropout" bottom: "a" top: "b" }'):                                                 # not in place -> clone
+                'layer { name: "d" type: "Dropout" bottom: "a" top: "b" }',                                                  # not in place -> clone
+                # parameters that change the numerics and that this reader does not implement are rejected, never silently dropped:
+                'layer { name: "c" type: "Convolution" bottom: "d" top: "c" convolution_param { num_output: 2 kernel_size: 3 dilation: 2 } }',
+                'layer { name: "r" type: "ReLU" bottom: "d" top: "d" relu_param { negative_slope: 0.1 } }',
+                'layer { name: "k" type: "Concat" bottom: "a" bottom: "b" top: "k" concat_param { axis: 2 } }',
+                'layer { name: "s" type: "Scale" bottom: "d" top: "d" scale_param { bias_term: true axis: 0 } }',
+                'layer { name: "p" type: "Pooling" bottom: "d" top: "p" pooling_param { pool: MAX kernel_size: 2 stride: 2 round_mode: FLOOR } }'):
         with pytest.raises(bb.RtException):
             bb.pipe_from_prototxt(bad)
     with pytest.raises(bb.RtException):

@@ -14,9 +14,8 @@ from b200_harness import conv_op_text
 
 SHAPES = [("conv2_5x5_96-256@27", 32, 96, 27, 27, 256, 5, 5, 1, 2), ("conv4_3x3_384-384@13", 32, 384, 13, 13, 384, 3, 3, 1, 1),
           ("conv5_3x3_384-256@13", 32, 384, 13, 13, 256, 3, 3, 1, 1), ("gn_3x3_128-192@28_b64", 64, 128, 28, 28, 192, 3, 3, 1, 1), ("k1_512-512@28", 32, 512, 28, 28, 512, 1, 1, 1, 0)]
-VARIANTS = [("pair(r1)", dict(use_sk4=0)), ("sk4", dict()), ("sk4 halo dp", dict(use_streamk=0)), ("sk4 halo dp tap0", dict(use_streamk=0, debug_flags=32)), ("sk4 halo dp noTMA", dict(use_streamk=0, debug_flags=1)),
-            ("sk4 halo dp tap0 noTMA", dict(use_streamk=0, debug_flags=33)), ("sk4 im2col dp", dict(use_halo=0, use_streamk=0)), ("sk4 im2col dp noTMA", dict(use_halo=0, use_streamk=0, debug_flags=1)),
-            ("sk4 im2col sk", dict(use_halo=0)), ("sk4 halo dp stamps", dict(use_streamk=0, debug_flags=16)), ("sk4 im2col dp stamps", dict(use_halo=0, use_streamk=0, debug_flags=16))]
+VARIANTS = [("pair(r1)", dict(use_sk4=0)), ("sk4", dict()), ("sk4 im2col dp", dict(use_halo=0, use_streamk=0)), ("sk4 halo dp", dict(use_streamk=0)), ("sk4 halo dp noTMA", dict(use_streamk=0, debug_flags=1)),
+            ("sk4 halo dp noMMA", dict(use_streamk=0, debug_flags=2)), ("sk4 stamps", dict(debug_flags=16)), ("sk4 halo dp stamps", dict(use_streamk=0, debug_flags=16))]
 
 
 def time_conv(rtc, tag, N, C, H, W, OC, KH, KW, s, p, iters=6):

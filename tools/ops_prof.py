@@ -33,8 +33,55 @@ def round_to(a, prec):
     return a
 
 
+def vendor_time_ms(op, prec, iters, warmup):
+    """The vendor-library comparator of the reference's `use_culibs=1` leg (cudnn_conv: src/culibs-wrap.cc:94-212, cublas_sgemm: :214-243, dispatch
+    src/nvrtc_util.cc:369-371) on the same op in the same run, through torch (cuDNN 9 convolution with autotuning / cuBLASLt GEMM). BENCH
+    INFRASTRUCTURE ONLY: nothing in boda_b200/ calls it. Returns {label: median ms} -- for fp32 both the true-fp32 path and the TF32 tensor-core
+    path the libraries would pick by default; for fp16 / bf16 the NHWC (channels_last) tensor-core path. Bias + ReLU are applied as the
+    library would (separate elementwise kernels inside the timed region for conv; none for sgemm), synthetic inputs."""
+    import torch
+    import torch.nn.functional as F
+    dev = torch.device("cuda")
+    out = {}
+    torch.backends.cudnn.benchmark = True
+
+    def timed(fn):
+        for _ in range(max(warmup, 3)):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts))
+
+    modes = [("fp32", torch.float32, False), ("tf32", torch.float32, True)] if prec == "fp32" else [(prec, torch.float16 if prec == "fp16" else torch.bfloat16, False)]
+    for label, dt, tf32 in modes:
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        if op.type == "Convolution":
+            i, f = op.get_dims("in").dims, op.get_dims("filts").dims
+            x = torch.randn(i["img"], i["chan"], i["y"], i["x"], device=dev, dtype=dt)
+            w = torch.randn(f["out_chan"], f["in_chan"], f["y"], f["x"], device=dev, dtype=dt)
+            b = torch.randn(f["out_chan"], device=dev, dtype=dt)
+            if dt != torch.float32:
+                x, w = x.contiguous(memory_format=torch.channels_last), w.contiguous(memory_format=torch.channels_last)
+            st, pd = op.pt("stride", (1, 1)), op.pt("in_pad", (0, 0))
+            out["cudnn_" + label] = timed(lambda: F.relu_(F.conv2d(x, w, b, stride=st, padding=pd)))
+            out["cudnn_" + label + "_conv_only"] = timed(lambda: F.conv2d(x, w, None, stride=st, padding=pd))
+        else:
+            a, bb_ = op.get_dims("a").dims, op.get_dims("b").dims
+            A = torch.randn(a["K"], a["M"], device=dev, dtype=dt)
+            Bm = torch.randn(bb_["K"], bb_["N"], device=dev, dtype=dt)
+            out["cublas_" + label] = timed(lambda: torch.matmul(A.t(), Bm))
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--compare", action="store_true", help="also time the vendor libraries (cuDNN conv / cuBLASLt GEMM through torch) on the same ops in the same run: "
+                    "the reference's use_culibs=1 comparator (src/culibs-wrap.cc). Bench infrastructure only.")
     ap.add_argument("--ops-fn", required=True)
     ap.add_argument("--prec", default="fp32", choices=["fp32", "fp16", "bf16"])
     ap.add_argument("--iters", type=int, default=20)
@@ -127,8 +174,12 @@ def main():
         else:
             a = op.get_dims("a").dims
             desc = "sgemm M=%d N=%d K=%d" % (a["M"], op.get_dims("b").dims["N"], a["K"])
+        vend = vendor_time_ms(op, args.prec, args.iters, args.warmup) if args.compare else {}
         rows.append(dict(op=desc, gflop=flops / 1e9, mbytes=nbytes / 1e6, ai=ai, kernel_ms=kern_ms, call_ms=call_ms, tflops_kernel=tf_k, tflops_call=tf_c,
-                         roof_tflops=roof_tf, frac_roof=tf_k / roof_tf, frac_tc_peak=tf_k / peak_tf, mrd=m))
+                         roof_tflops=roof_tf, frac_roof=tf_k / roof_tf, frac_tc_peak=tf_k / peak_tf, mrd=m, vendor_ms=vend,
+                         vendor_tflops={k: flops / v / 1e9 for k, v in vend.items()}))
+        if vend:
+            print("    vendor: " + "  ".join("%s %.4f ms %.1f TF/s (b200 call / vendor = %.2fx)" % (k, v, flops / v / 1e9, call_ms / v) for k, v in vend.items()), flush=True)
         print("%-44s %7.2f GF  AI %6.0f  kernel %8.4f ms %7.1f TF/s  call %8.4f ms %7.1f TF/s  roof %6.0f  frac %.3f  mrd %.2e" %
               (desc, flops / 1e9, ai, kern_ms, tf_k, call_ms, tf_c, roof_tf, tf_k / roof_tf, m), flush=True)
         for k in names:
@@ -145,6 +196,15 @@ def main():
             for r in rows:
                 f.write("| %s | %.2f | %.1f | %.0f | %.4f | %.1f | %.4f | %.1f | %.0f | %.3f | %.3f | %.1e |\n" %
                         (r["op"], r["gflop"], r["mbytes"], r["ai"], r["kernel_ms"], r["tflops_kernel"], r["call_ms"], r["tflops_call"], r["roof_tflops"], r["frac_roof"], r["frac_tc_peak"], r["mrd"]))
+            if args.compare and rows:
+                keys = list(rows[0]["vendor_ms"].keys())
+                f.write("\nVendor comparator (the reference's `use_culibs=1` leg, src/culibs-wrap.cc:94-243): the same ops in the same run through torch -- cuDNN 9 convolution "
+                        "(autotuned; `_conv_only` = without the bias + ReLU kernels) / cuBLASLt GEMM; for fp32 both true fp32 and the TF32 tensor-core path, for fp16 / bf16 the "
+                        "NHWC tensor-core path on 16-bit tensors (no fp32 NCHW boundary, no operand packing: the library's best case). Bench infrastructure only. "
+                        "ratio = this back-end's CALL time (packing + kernel, fp32 NCHW in and out) / vendor time; < 1 = faster than the library.\n\n")
+                f.write("| op | b200 call ms | " + " | ".join("%s ms | ratio" % k for k in keys) + " |\n|---|---|" + "---|---|" * len(keys) + "\n")
+                for r in rows:
+                    f.write("| %s | %.4f | " % (r["op"], r["call_ms"]) + " | ".join("%.4f | %.2f" % (r["vendor_ms"][k], r["call_ms"] / r["vendor_ms"][k]) for k in keys) + " |\n")
         with open(os.path.splitext(args.out)[0] + ".json", "w") as f:
             json.dump(rows, f, indent=1)
     rtc.close()
