@@ -242,6 +242,34 @@ def run_reference_arm(args, rank, world):
     _emit(line)
 
 
+def bind_to_gpu_numa_node(dev_index):
+    """Run this rank's host threads (and so first-touch its pinned buffers) on the NUMA node its GPU hangs off: the e2e path moves 19.8 MB per
+    step per GPU from host memory, and at 4-8 ranks a remote-socket source halves it. Best effort: silently does nothing without sysfs / NVML."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(dev_index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:  # NVML prints an 8-digit PCI domain, sysfs uses 4
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def _emit(line: dict):
     """Exactly one JSON line on the real stdout (fd 1 is pointed at stderr while libraries such as NCCL are chatty)."""
     os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
@@ -550,6 +578,7 @@ def main():
     if bb.device_count() < 1:
         raise RuntimeError("bench.py needs a CUDA device: the B200 back-end has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None  # before any pinned allocation
     dist = None
     if world > 1:
         import torch.distributed as dist_mod

@@ -79,7 +79,7 @@ struct func_t {
   packed_t w_pack, a_pack;  // conv: filts / in ; sgemm: b / a
   p_dev_buf_t w_l1max;      // conv: max over out chans of sum |w| (bound of the outputs, for producer-written fp16 planes)
   uint64_t w_l1max_gen = ~0ull;
-  p_dev_buf_t splitk_ws;
+  p_dev_buf_t splitk_ws, splitk_tickets;
 };
 
 struct call_ev_t { cudaEvent_t b = nullptr, e = nullptr, kb = nullptr, ke = nullptr; };  // whole call; its main (contraction) kernel
@@ -326,6 +326,7 @@ bool b200_compute_t::set_option(string const &k, string const &v) {
   else if (k == "use_2cta") { use_2cta = std::stoi(v); }
   else if (k == "debug_flags") { debug_flags = std::stoi(v); }
   else if (k == "use_sk4") { use_sk4 = std::stoi(v); }
+  else if (k == "fuse_splitk_reduce") { fuse_splitk_reduce = std::stoi(v); }
   else if (k == "use_halo") { use_halo = std::stoi(v); }
   else if (k == "use_streamk") { use_streamk = std::stoi(v); }
   else if (k == "sk4_max_b_stages") { sk4_max_b_stages = std::stoi(v); }
@@ -1219,6 +1220,15 @@ struct run_ctx_t {
       if (!f.splitk_ws || f.splitk_ws->bytes < need) { f.splitk_ws = std::make_shared<dev_buf_t>(need); }
       prm.out = static_cast<float *>(f.splitk_ws->p);
       prm.split_stride = out_elems;
+      if (!vcat && rtc.fuse_splitk_reduce) {  // the last split CTA of every tile reduces it in the kernel (igemm.cuh): no splitk_reduce_kernel launch
+        uint64_t const n_tix = (uint64_t)round_up(p_tiles, cl.cm) * round_up(q_tiles, cl.cn) * 8;  // {arrived, reduced} per tile
+        if (!f.splitk_tickets || f.splitk_tickets->bytes < n_tix) {
+          f.splitk_tickets = std::make_shared<dev_buf_t>(n_tix);
+          CU_CHK(cudaMemsetAsync(f.splitk_tickets->p, 0, n_tix, st));  // the counters are re-armed by their last CTA from here on
+        }
+        prm.tile_tickets = static_cast<unsigned int *>(f.splitk_tickets->p);
+        prm.out_final = out_base;
+      }
     } else {
       prm.out = out_base;
       prm.split_stride = 0;
@@ -1268,7 +1278,7 @@ struct run_ctx_t {
     else { launch_igemm(BN, planes, grid, act_hi, act_lo, w_hi, w_lo, prm); }
     mark_kernel_end();
     if (ts_dev) { print_role_stamps(ts_dev, ts_clusters, BN, planes, cp.kblks_total); }
-    if (splitk_pass) {
+    if (splitk_pass && !prm.tile_tickets) {
       B200_CARVEOUT_ONCE(b200::splitk_reduce_kernel); launch_k(b200::splitk_reduce_kernel, dim3(ceil_div(out_elems, 256)), dim3(256), 0, static_cast<float *>(f.splitk_ws->p), out_base, bias, out_elems, cp.splits, cp.OC, cp.OH * cp.OW, cp.relu, prm.out_absmax,
                vcat ? (long long)vcat->dims.dsz("chan") * cp.OH * cp.OW : 0ll);
       launched();
@@ -1325,6 +1335,43 @@ struct run_ctx_t {
     im.bump(vc);
   }
 
+  // the consumer's NHWC planes as a second output of a pooling kernel: allocate / re-zero them in the layout the consumer reads (by-value
+  // "out_pack_py" / "out_pack_px": the shared-padding layout of a halo-mode convolution, igemm4.cuh) and fill in the kernel's PoolPlanes argument
+  packed_t *pool_out_planes(b200::PoolPlanes &pp, var_info_t &vout, int C, int OH, int OW, int npl, bool bf16, unsigned int *in_cell) {
+    int o16_py = 0, o16_px = 0;
+    bool o16_padded = false;
+    int const cpad = (int)round_up(C, 8);
+    long long const nimg = (long long)vout.dims.dsz("img");
+    if (has_arg("out_pack_py")) { o16_py = (int)scalar("out_pack_py"); o16_px = (int)scalar("out_pack_px"); o16_padded = true; }
+    packed_t *out_pk = &im.act_packs[{vout.buf->p, o16_padded ? b200_impl_t::pad_tag(o16_py, o16_px) : 0u}];
+    uint64_t const bytes = (uint64_t)nimg * (OH + o16_py) * (OW + o16_px) * cpad * 2;
+    long long const ohw2 = (long long)OH * OW;
+    uint64_t const lkey = o16_padded ? pack_layout_key({nimg, C, ohw2, cpad, cpad, (long long)(OH + o16_py) * (OW + o16_px) * cpad, OW, (long long)(OW + o16_px) * cpad,
+                                                        ((long long)o16_py * (OW + o16_px) + o16_px) * cpad, npl == 2, bf16, 0, 0, 0})
+                                     : pack_layout_key({nimg, C, ohw2, cpad, cpad, ohw2 * cpad, std::max<long long>(ohw2, 1), 0, 0, npl == 2, bf16, 0, 0, 0});
+    if (!out_pk->hi || out_pk->hi->bytes < bytes || (npl == 2 && !out_pk->lo)) {
+      out_pk->hi = std::make_shared<dev_buf_t>(bytes);
+      CU_CHK(cudaMemsetAsync(out_pk->hi->p, 0, bytes, st));
+      if (npl == 2) { out_pk->lo = std::make_shared<dev_buf_t>(bytes); CU_CHK(cudaMemsetAsync(out_pk->lo->p, 0, bytes, st)); }
+      out_pk->scale2 = std::make_shared<dev_buf_t>(8);
+      out_pk->absmax_bits = std::make_shared<dev_buf_t>(8);
+      CU_CHK(cudaMemsetAsync(out_pk->absmax_bits->p, 0, 8, st));
+      if (bf16) { static float const ones[2] = {1.0f, 1.0f}; CU_CHK(cudaMemcpyAsync(out_pk->scale2->p, ones, 8, cudaMemcpyHostToDevice, st)); }
+    } else if (out_pk->layout_key != lkey) {  // same storage, other geometry: padding positions must be zero again
+      CU_CHK(cudaMemsetAsync(out_pk->hi->p, 0, out_pk->hi->bytes, st));
+      if (out_pk->lo) { CU_CHK(cudaMemsetAsync(out_pk->lo->p, 0, out_pk->lo->bytes, st)); }
+    }
+    out_pk->layout_key = lkey;
+    pp.hi = static_cast<uint16_t *>(out_pk->hi->p);
+    pp.lo = npl == 2 ? static_cast<uint16_t *>(out_pk->lo->p) : nullptr;
+    pp.scale2 = static_cast<float *>(out_pk->scale2->p);
+    pp.in_absmax = in_cell;
+    pp.C = C; pp.cpad = cpad; pp.bf16 = bf16 ? 1 : 0;
+    pp.OW = OW;
+    if (o16_padded) { pp.dHp = OH + o16_py; pp.dWp = OW + o16_px; pp.dpy = o16_py; pp.dpx = o16_px; }
+    return out_pk;
+  }
+
   void run_pool() {
     var_info_t &vin = var("in"), &vout = var("out");
     check_nchw(vin.dims, "in"); check_nchw(vout.dims, "out");
@@ -1344,6 +1391,40 @@ struct run_ctx_t {
     long long const n_out = vout.dims.dims_prod();
     long long const planes = (long long)vin.dims.dsz("img") * vin.dims.dsz("chan");
     int const avg = (int)scalar("avg_pool", true, 0);
+    // LRN in front of the pool, fused (by-value "lrn_local_size" + "lrn_alpha" / "lrn_beta" / "lrn_k"; `in` is then the LRN's INPUT):
+    // lrn_maxpool_kernel. The whole-net driver asks for it only for a 3x3 / 2 max pool without padding behind a local_size-5 LRN.
+    if (has_arg("lrn_local_size")) {
+      int const ls = (int)scalar("lrn_local_size");
+      if (ls != 5 || avg || KH != 3 || KW != 3 || sy != 2 || sx != 2 || py != 0 || px != 0) { unsup_err("pool: the fused LRN form handles local_size 5 in front of a 3x3 / 2 max pool without padding"); }
+      int const C = (int)vin.dims.dsz("chan"), N = (int)vin.dims.dsz("img");
+      bool const bf16 = (rtc.prec == B200_PREC_BF16);
+      int const npl = (rtc.prec == B200_PREC_FP32_SPLIT) ? 2 : 1;
+      float const alpha = (float)scalar("lrn_alpha", true, 1.0), beta = (float)scalar("lrn_beta", true, 0.75), kk = (float)scalar("lrn_k", true, 1.0);
+      unsigned int *in_cell = bf16 ? nullptr : absmax_cell("in");
+      bool const want_planes = has_arg("out_pack") && scalar("out_pack") != 0 && (C % 8) == 0 && (bf16 || (in_cell && kk >= 1.0f));  // (k >= 1: the LRN factor is <= 1, max|in| bounds the output)
+      b200::PoolPlanes pp;
+      memset(&pp, 0, sizeof(pp));
+      packed_t *out_pk = nullptr;
+      if (want_planes) { out_pk = pool_out_planes(pp, vout, C, OH, OW, npl, bf16, in_cell); }
+      int const row_groups = ceil_div(OH, b200::kLpRows), chunks = ceil_div(C, b200::kLpCC);
+      long long const n_units = (long long)row_groups * chunks * N;
+      size_t const smem = ((size_t)2 * (b200::kLpCC + 2 * b200::kLpHalo) * b200::lrn_pool_row_stride(W) + (size_t)b200::kLpCC * b200::kLpRows * OW) * 4;
+      if (smem > 200 * 1024 || n_units >= (1ll << 31)) { unsup_err("pool: map too wide for the fused LRN form"); }
+      // (bulk copies of whole 16-byte units: the last channel's run may be rounded up to the end of the tensor, never beyond it)
+      if ((C % 4) != 0 || (reinterpret_cast<uintptr_t>(fptr(vin)) & 15) != 0) { unsup_err("pool: the fused LRN form needs chan % 4 == 0 and a 16-byte aligned input"); }
+      static uint64_t attr_ = 0;
+      if (first_use_on_device(attr_, rtc.device)) {
+        CU_CHK(cudaFuncSetAttribute(b200::lrn_maxpool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); prefer_max_smem(b200::lrn_maxpool_kernel);
+      }
+      int per_sm = 1;
+      CU_CHK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b200::lrn_maxpool_kernel, b200::kLpThreads, smem));
+      int const grid = (int)std::min<long long>(n_units, (long long)im.num_sms * std::max(1, per_sm));
+      launch_k(b200::lrn_maxpool_kernel, dim3(grid), dim3(b200::kLpThreads), smem, fptr(vin), fptr(vout), C, H, W, OH, OW, alpha / 5.0f, -beta, kk, absmax_cell("out"), pp, row_groups, chunks, (int)n_units);
+      launched();
+      im.bump(vout);
+      if (out_pk) { out_pk->src_gen = *vout.gen; out_pk->src_ptr = vout.buf->p; }
+      return;
+    }
     // planes that fit shared memory are staged there (pool_plane_kernel): the 3x3 / 2x2 max pools of AlexNet / NiN / GoogLeNet / ResNet incl.
     // their 112x112 first pools (one 49 KB plane per CTA), GoogLeNet's 5x5 stride-3 average pools, 7x7 (global) average pools
     bool const plane_ks = KH == KW && sy == sx && ((KH == 3 && sy == 2) || (KH == 3 && sy == 1) || (KH == 2 && sy == 2) || (KH == 5 && sy == 3) || (KH == 7 && sy == 1));
@@ -1391,38 +1472,7 @@ struct run_ctx_t {
       b200::PoolPlanes pp;
       memset(&pp, 0, sizeof(pp));
       packed_t *out_pk = nullptr;
-      int o16_py = 0, o16_px = 0;
-      bool o16_padded = false;
-      if (planes_ok) {
-        int const cpad = (int)round_up(C, 8);
-        long long const nimg = (long long)vout.dims.dsz("img");
-        if (has_arg("out_pack_py")) { o16_py = (int)scalar("out_pack_py"); o16_px = (int)scalar("out_pack_px"); o16_padded = true; }  // the consumer's halo mode (igemm4.cuh)
-        out_pk = &im.act_packs[{vout.buf->p, o16_padded ? b200_impl_t::pad_tag(o16_py, o16_px) : 0u}];
-        uint64_t const bytes = (uint64_t)nimg * (OH + o16_py) * (OW + o16_px) * cpad * 2;
-        long long const ohw2 = (long long)OH * OW;
-        uint64_t const lkey = o16_padded ? pack_layout_key({nimg, C, ohw2, cpad, cpad, (long long)(OH + o16_py) * (OW + o16_px) * cpad, OW, (long long)(OW + o16_px) * cpad,
-                                                            ((long long)o16_py * (OW + o16_px) + o16_px) * cpad, npl == 2, bf16, 0, 0, 0})
-                                         : pack_layout_key({nimg, C, ohw2, cpad, cpad, ohw2 * cpad, std::max<long long>(ohw2, 1), 0, 0, npl == 2, bf16, 0, 0, 0});
-        if (!out_pk->hi || out_pk->hi->bytes < bytes || (npl == 2 && !out_pk->lo)) {
-          out_pk->hi = std::make_shared<dev_buf_t>(bytes);
-          CU_CHK(cudaMemsetAsync(out_pk->hi->p, 0, bytes, st));
-          if (npl == 2) { out_pk->lo = std::make_shared<dev_buf_t>(bytes); CU_CHK(cudaMemsetAsync(out_pk->lo->p, 0, bytes, st)); }
-          out_pk->scale2 = std::make_shared<dev_buf_t>(8);
-          out_pk->absmax_bits = std::make_shared<dev_buf_t>(8);
-          CU_CHK(cudaMemsetAsync(out_pk->absmax_bits->p, 0, 8, st));
-        } else if (out_pk->layout_key != lkey) {  // same storage, other geometry: padding positions must be zero again
-          CU_CHK(cudaMemsetAsync(out_pk->hi->p, 0, out_pk->hi->bytes, st));
-          if (out_pk->lo) { CU_CHK(cudaMemsetAsync(out_pk->lo->p, 0, out_pk->lo->bytes, st)); }
-        }
-        out_pk->layout_key = lkey;
-        pp.hi = static_cast<uint16_t *>(out_pk->hi->p);
-        pp.lo = npl == 2 ? static_cast<uint16_t *>(out_pk->lo->p) : nullptr;
-        pp.scale2 = static_cast<float *>(out_pk->scale2->p);
-        pp.in_absmax = in_cell;
-        pp.C = C; pp.cpad = cpad; pp.bf16 = bf16 ? 1 : 0;
-        pp.OW = OW;
-        if (o16_padded) { pp.dHp = OH + o16_py; pp.dWp = OW + o16_px; pp.dpy = o16_py; pp.dpx = o16_px; }
-      }
+      if (planes_ok) { out_pk = pool_out_planes(pp, vout, C, OH, OW, npl, bf16, in_cell); }
       size_t const smem = pipe_ppc ? pipe_smem : (size_t)ppc * (H * W + (pp.hi ? OH * OW : 0)) * 4;
       unsigned int *cell = absmax_cell("out");
       long long const n_groups = ceil_div(planes, ppc);

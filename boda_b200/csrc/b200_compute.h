@@ -77,6 +77,10 @@ struct b200_compute_t {
                             // warpgroups) for every layer with >= 2 row tiles. OFF by default: parity-green, and on par with the round-1 pair kernel in the
                             // 16-bit modes (halo mode moves 2.8x fewer bytes), but measured slower in fp32-parity mode, which is MMA-bound at 3 passes and
                             // only pays the halo layout's dropped virtual pixels (profiles/diag_r02*)
+  int fuse_splitk_reduce = 0;  // split-K layers (inner-product shapes): the last split CTA of a tile sums the partial tiles inside the contraction kernel
+                               // (same order of additions as splitk_reduce_kernel, which then is not launched). Off by default: bit-identical and three
+                               // launches fewer per AlexNet forward, but every split CTA then waits for its slowest sibling inside the kernel --
+                               // measured neutral (0.394 vs 0.389 ms per step), so the two-kernel form stays
   int use_halo = 1;         // igemm4: one activation halo tile per channel block feeds every filter tap of a stride-1 KHxKW convolution
   int use_streamk = 1;      // igemm4: cut the (tile, k-block) space into equal contiguous ranges per CTA pair when whole tiles would leave > 8 % of a round idle
   int sk4_max_b_stages = 0; // experiments: cap igemm4's filter ring depth (0 = as many as fit)

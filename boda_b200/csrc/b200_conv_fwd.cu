@@ -396,13 +396,39 @@ void b200_conv_fwd_t::gen_op(p_conv_op_t const &op) {
   } else if (op->is("Pooling")) {
     map_str_rtc_arg_t args{{"in", op->bots[0]}, {"out", op->tops[0]}};
     add_absmax_args(args, "out", op->tops[0]);
+    string pool_in = op->bots[0];
+    auto lf = lrn_fuse.find(op->tag);
+    if (lf != lrn_fuse.end()) {
+      // the LRN in front runs inside this pool's kernel: the pool reads the LRN's input and takes its parameters by value; a plain lrn call is
+      // kept for readers of the (now bypassed) LRN node
+      p_conv_op_t l;
+      for (auto const &o : cp->ops) { if (o->tag == lf->second.lrn_tag) { l = o; } }
+      op_base_t lop;
+      lop.str_vals = l->str_vals;
+      lop.nda_vals = l->nda_vals;
+      rtc_func_info_t fi;
+      fi.func_name = "lrn__" + l->tag + "__plain";
+      fi.op = lop;
+      fi.op.set_func_name("lrn");
+      rtc->compile({fi}, rtc_compile_opts_t());
+      rtc_func_call_t plain;
+      plain.rtc_func_name = fi.func_name;
+      plain.arg_map = map_str_rtc_arg_t{{"in", lf->second.in_node}, {"out", lf->second.lrn_node}};
+      elided_calls[lf->second.lrn_node] = plain;
+      pool_in = lf->second.in_node;
+      args["in"] = rtc_arg_t(pool_in);
+      args["lrn_local_size"] = rtc_arg_t(make_scalar_nda<uint32_t>(5, "uint32_t"));
+      for (char const *pn : {"alpha", "beta", "k"}) {
+        if (l->has(pn)) { args[string("lrn_") + pn] = rtc_arg_t(make_scalar_nda<float>((float)nda_scalar_as_double(*l->get(pn)), "float")); }
+      }
+    }
     {  // layout-transform elimination: the pool kernel also writes the NHWC planes of a Convolution that reads its output (no in-place ops between)
       p_conv_node_t on = cp->must_get_node(op->tops[0]);
       bool feeds = false, clean = true;
       for (auto const &o : cp->ops) { if (o->is("Convolution") && !o->bots.empty() && o->bots[0] == op->tops[0] && on->dims.dsz("chan") > 8) { feeds = true; } }
       for (auto const &ip : on->in_place_ops) { if (!ip->is("Dropout")) { clean = false; } }
       if (pack_by_producers && feeds && clean) {
-        add_absmax_args(args, "in", op->bots[0]);
+        add_absmax_args(args, "in", pool_in);
         add_out_pack_args(args, op->tops[0]);
       }
     }
@@ -460,6 +486,7 @@ void b200_conv_fwd_t::init(p_conv_pipe_t const &cp_, string const &opts) {
         else if (k == "enable_prof") { enable_prof = (uint32_t)std::stoul(v); }
         else if (k == "concat_by_offset") { concat_by_offset = (uint32_t)std::stoul(v); }
         else if (k == "fuse_eltwise") { fuse_eltwise = (uint32_t)std::stoul(v); }
+        else if (k == "fuse_lrn_pool") { fuse_lrn_pool = (uint32_t)std::stoul(v); }
         else if (k == "pack_by_producers") { pack_by_producers = (uint32_t)std::stoul(v); }
         else if (k == "op_tune" && !kv.second->is_leaf) {  // the reference's nested form, op_tune=(k1conv=1,tconv=1,...) (src/rtc_fwd.cc:36)
           for (auto const &tk : kv.second->kids) { if (!rtc->set_option(tk.first, tk.second->is_leaf ? tk.second->leaf : string())) { rt_err("mode=b200: unused op_tune option '" + tk.first + "'"); } }
@@ -525,6 +552,28 @@ void b200_conv_fwd_t::init(p_conv_pipe_t const &cp_, string const &opts) {
       }
     }
   }
+  // LRN in front of a max pool (AlexNet norm1 -> pool1, norm2 -> pool2; GoogLeNet norm2 -> pool2): when the LRN output is read by nothing but
+  // one 3x3 / 2 max pool without padding and carries no in-place op, the pool's kernel normalises the values it stages (lrn_maxpool_kernel).
+  if (fuse_lrn_pool) {
+    for (auto const &l : cp->ops) {
+      if (!l->is("LRN") || l->in_place || l->bots.size() != 1 || l->tops.size() != 1) { continue; }
+      uint32_t const ls = l->has("local_size") ? (uint32_t)nda_scalar_as_double(*l->get("local_size")) : 5;
+      p_conv_node_t ln = cp->must_get_node(l->tops[0]);
+      if (ls != 5 || !ln->in_place_ops.empty() || ln->top_for.size() != 1 || ln->bot_for.size() != 1) { continue; }
+      p_conv_op_t pool;
+      for (auto const &o : cp->ops) { if (o->tag == ln->bot_for[0]) { pool = o; } }
+      if (!pool || !pool->is("Pooling") || pool->in_place || !pool->has("kern_sz")) { continue; }
+      bool const avg = pool->has("avg_pool") && nda_scalar_as_double(*pool->get("avg_pool")) != 0;
+      if (avg || pool->yx("kern_sz", "y", 0) != 3 || pool->yx("kern_sz", "x", 0) != 3 || pool->yx("stride", "y", 1) != 2 || pool->yx("stride", "x", 1) != 2 ||
+          pool->yx("in_pad", "y", 0) != 0 || pool->yx("in_pad", "x", 0) != 0) { continue; }
+      if (pool->has("emit_out_in_yx") && nda_scalar_as_double(*pool->get("emit_out_in_yx")) != 0) { continue; }
+      dims_t const &d = ln->dims;
+      if ((d.dsz("chan") % 4) != 0) { continue; }
+      if ((uint64_t)2 * (16 + 4) * (9 * d.dsz("x") + 8) * 4 + (uint64_t)16 * 4 * cp->must_get_node(pool->tops[0])->dims.dsz("x") * 4 > 200 * 1024) { continue; }  // the kernel's staging must fit shared memory
+      lrn_fuse[pool->tag] = lrn_fuse_t{l->tag, l->bots[0], l->tops[0]};
+      l->fused = true;
+    }
+  }
   // abs-max side channel: a node gets a cell when its (single) writer can publish max|x| and some Convolution reads it.
   // In-place ReLU/Dropout on the node only shrink max|x|, so the published value stays a valid bound.
   for (auto const &kv : cp->nodes) {
@@ -542,6 +591,13 @@ void b200_conv_fwd_t::init(p_conv_pipe_t const &cp_, string const &opts) {
       }
     }
     for (auto const &rf : res_fuse) { if (rf.second.res_node == n.name) { feeds_conv = true; } }  // a residual input: its max bounds the join's output
+    for (auto const &lf : lrn_fuse) {  // the input of an LRN that runs inside a pool kernel: that kernel scales the planes it writes by max|in| (the LRN factor is <= 1)
+      if (lf.second.in_node != n.name) { continue; }
+      for (auto const &o : cp->ops) {
+        if (o->tag != lf.first) { continue; }
+        for (auto const &o2 : cp->ops) { if (o2->is("Convolution") && !o2->bots.empty() && o2->bots[0] == o->tops[0]) { feeds_conv = true; } }
+      }
+    }
     if (feeds_conv) { uint32_t const ix = (uint32_t)absmax_ix.size(); absmax_ix[n.name] = ix; }
   }
   rtc->create_var_with_dims(absmax_cells_vn, dims_t({(uint32_t)std::max<size_t>(absmax_ix.size(), 1)}, {"cell"}, "uint32_t"));
@@ -578,6 +634,7 @@ string b200_conv_fwd_t::plan_text() const {
   for (auto const &c : fwd_calls) { put_call("call", c); }
   for (auto const &kv : concat_alias) { out += "alias " + kv.first + " " + kv.second.cat_node + " " + str(kv.second.ocix) + "\n"; }
   for (auto const &kv : res_fuse) { out += "join " + kv.first + " " + kv.second.out_node + " " + kv.second.res_node + "\n"; }
+  for (auto const &kv : lrn_fuse) { out += "lrnpool " + kv.first + " " + kv.second.lrn_tag + " " + kv.second.in_node + "\n"; }
   for (auto const &kv : absmax_ix) { out += "absmax " + kv.first + " " + str(kv.second) + "\n"; }
   return out;
 }

@@ -59,6 +59,11 @@ struct IgemmParams {
   unsigned int const *res_absmax;  // max|res| published by its producer (bit pattern): the residual's term of the fp16 planes' output bound
   float const *p_scale;    // {scale, inv_scale} of the P tensor
   float const *q_scale;
+  // split-K launches of the one-CTA kernel: with `tile_tickets` (one zeroed counter per output tile) the LAST of a tile's split CTAs to finish adds
+  // the partial tiles in split order (+ bias, ReLU) and writes `out_final` -- the same arithmetic in the same order as splitk_reduce_kernel, without
+  // the second launch. The counter is re-armed by that CTA. null = partials only (the reduce kernel follows).
+  unsigned int *tile_tickets;
+  float *out_final;
   long long *ts;  // experiments (debug_flags bit 4): per-cluster role stall counters of the CTA-pair kernel, [cluster][16] SM cycles (null = off)
   int debug;   // bit 0: skip TMA (MMA runs on whatever is in smem), bit 1: skip MMA issue (loads + barriers only), bit 2: skip the final global stores,
                // bit 3: skip the TMEM drains -- timing experiments only (results are garbage)
@@ -481,6 +486,82 @@ igemm_umma_kernel(const __grid_constant__ CUtensorMap p_hi_map, const __grid_con
           }
           if (++pix == prm.out_hw) { pix = 0; off += img_step; } else { off += 1; }
         }
+      }
+    }
+    if (!final_out && prm.tile_tickets) {
+      // ---- fused split-K reduction, spread over the tile's split CTAs: once all `splits` partial tiles are written, CTA z sums columns
+      // [z*BN/splits, ...) of the tile over the splits in split order (+ bias, ReLU) -- the arithmetic of splitk_reduce_kernel without its launch.
+      // (A first version let the LAST CTA reduce the whole tile: 8 dependent L2 round trips per column group on 8 CTAs made fc8 20 us slower.)
+      // All CTAs of a split-K launch are co-resident (tiles * splits <= #SMs by plan), so the bounded spin below cannot deadlock.
+      unsigned int *ticket = prm.tile_tickets + 2 * (blockIdx.y * gridDim.x + blockIdx.x);  // {arrived, reduced}
+      unsigned int const splits = gridDim.z;
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (row == 0) {
+        atomicAdd(ticket, 1u);
+        unsigned int v = 0, spins = 0;
+        while (true) {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ticket) : "memory");
+          if (v >= splits) { break; }
+          __nanosleep(64);
+          if (++spins > (1u << 22)) { printf("b200: split-K partial tiles never completed (block %d,%d,%d)\n", blockIdx.x, blockIdx.y, blockIdx.z); __trap(); }
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      __threadfence();
+      float const floor_f = prm.relu ? 0.0f : -INFINITY;
+      int const nvalid = min(BN, prm.q_rows - n0);
+      int const per = (BN + static_cast<int>(splits) - 1) / static_cast<int>(splits);
+      int const j_begin = static_cast<int>(blockIdx.z) * per, j_end = min(nvalid, j_begin + per);
+      amax = 0.0f;
+      if (prow < prm.p_rows && !(prm.debug & 4)) {
+        float b_row = 0.0f;
+        long long off0 = 0, img_step = 0;
+        int pix0 = 0;
+        if (!prm.swapped) {  // row = pixel, columns = channels: column j at off0 + j * out_hw
+          int const img = prow / prm.out_hw, pix = prow - img * prm.out_hw;
+          off0 = (static_cast<long long>(img) * prm.out_chans + n0) * prm.out_hw + pix;
+        } else {             // row = channel, columns = pixels
+          b_row = prm.has_bias ? __ldg(prm.bias + prow) : 0.0f;
+          int const p0 = n0 + j_begin, img0 = p0 / prm.out_hw;
+          pix0 = p0 - img0 * prm.out_hw;
+          off0 = (static_cast<long long>(img0) * prm.out_chans + prow) * prm.out_hw + pix0;
+          img_step = static_cast<long long>(prm.out_chans) * prm.out_hw - (prm.out_hw - 1);
+        }
+        for (int j0 = j_begin; j0 < j_end; j0 += 4) {  // 4 columns x all splits in flight per thread, then the adds in split order
+          long long offs[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (!prm.swapped) { offs[j] = off0 + static_cast<long long>(j0 + j) * prm.out_hw; }
+            else { offs[j] = off0; if (++pix0 == prm.out_hw) { pix0 = 0; off0 += img_step; } else { off0 += 1; } }
+          }
+          float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 4
+          for (unsigned int sp = 0; sp < splits; ++sp) {
+            float const *w = prm.out + static_cast<long long>(sp) * prm.split_stride;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { if (j0 + j < j_end) { v[j] += __ldcg(w + offs[j]); } }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (j0 + j < j_end) {
+              float r = v[j];
+              if (!prm.swapped) { if (prm.has_bias) { r += __ldg(prm.bias + n0 + j0 + j); } } else { r += b_row; }
+              r = fmaxf(r, floor_f);
+              amax = fmaxf(amax, fabsf(r));
+              prm.out_final[offs[j]] = r;
+            }
+          }
+        }
+      }
+      if (prm.out_absmax) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o)); }
+        if (lane == 0 && amax > 0.0f) { atomicMax(prm.out_absmax, __float_as_uint(amax)); }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (row == 0) {  // the last CTA to finish its share re-arms both counters for the next launch
+        if (atomicAdd(ticket + 1, 1u) == splits - 1) { ticket[1] = 0u; __threadfence(); ticket[0] = 0u; }
       }
     }
     if (prm.out_absmax && prm.split_stride == 0) {  // warp-uniform branch; all 32 lanes take part in the shuffle reduce

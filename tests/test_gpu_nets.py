@@ -331,3 +331,34 @@ def test_planes_written_by_producers(oracle, net, batch, in_sz, prec):
         ma, mb = oracle.mrd(ref[o], a[o]), oracle.mrd(ref[o], b[o])
         print("nin b=8 fp32 output mrd vs acc64 oracle: producer-written planes %.2e, pack kernels %.2e" % (ma, mb))
         assert ma < TOL and mb < TOL
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "fp16"])
+@pytest.mark.parametrize("net,batch,in_sz,nodes", [("alexnet_ng_conv", 3, 227, ["norm1", "pool1", "norm2", "pool2", "conv3", "fc8"]),
+                                                   ("googlenet_conv", 2, 224, ["norm2", "pool2", "icp1_out1", "cls3_fc"])])
+def test_lrn_inside_the_pool_kernel_matches_separate_kernels(oracle, net, batch, in_sz, nodes, prec):
+    """LRN -> 3x3/2 max pool as one kernel (lrn_maxpool_kernel) against the two-kernel path (fuse_lrn_pool=0): the LRN node (computed on
+    demand by the plain lrn kernel) and the pool output of the first fused pair are BIT-IDENTICAL -- same arithmetic on the same values. bf16: so
+    is everything behind them. fp32-parity / fp16: the planes the pool writes for the next convolution take their power-of-two scale from max|LRN input| instead of
+    max|LRN output| -> later nodes agree to the lo plane's rounding (mrd < 5e-4). At least two launches fewer (AlexNet) / one (GoogLeNet)."""
+    import boda_b200 as bb
+    from boda_b200 import nets
+    txt, i, o = nets.NETS[net](batch)
+    params = nets.synth_params(txt)
+    x = nets.synth_input((batch, 3, in_sz, in_sz))
+    res = []
+    for on in (1, 0):
+        fwd = bb.B200ConvFwd(txt, "(prec=%s,fuse_lrn_pool=%d)" % (prec, on))
+        for k, v in params.items():
+            fwd.set_param(k, v)
+        out = fwd.run_fwd({i: x}, nodes)
+        l0 = fwd.launches()
+        fwd.run_fwd({i: x}, [o])
+        res.append((out, fwd.launches() - l0))
+    (a, la), (b, lb) = res
+    assert la <= lb - (2 if net == "alexnet_ng_conv" else 1), (la, lb)
+    for n in nodes:
+        if prec == "bf16" or n == nodes[0] or n == nodes[1]:  # (the first fused pair sees identical inputs in every mode)
+            assert np.array_equal(a[n], b[n]), (n, oracle.mrd(a[n], b[n]))
+        else:
+            assert np.isfinite(a[n]).all() and oracle.mrd(a[n], b[n]) < 5e-4, (n, oracle.mrd(a[n], b[n]))

@@ -465,6 +465,33 @@ def test_conv_sk4_halo_and_streamk(oracle, case, prec):
         assert np.array_equal(outs["im2col"], outs["pair_r1"])
 
 
+@pytest.mark.parametrize("case", [(32, 256, 6, 6, 4096, 6, 6, 1, 1, 0, 0),    # fc6 shape: weights as the 128-row operand, split-K
+                                  (32, 4096, 1, 1, 1000, 1, 1, 1, 1, 0, 0),  # fc8 shape: ragged last row tile
+                                  (2, 96, 14, 14, 40, 3, 3, 1, 1, 1, 1),     # few pixels, pixel-major split-K, ragged N tile
+                                  (4, 32, 6, 6, 200, 6, 6, 1, 1, 0, 0)])
+@pytest.mark.parametrize("relu", [1, 0])
+def test_conv_splitk_reduce_in_kernel_is_bit_identical(oracle, case, relu):
+    """Split-K layers: the last split CTA of a tile sums the partial tiles inside the contraction kernel, in split order with the bias added last --
+    the arithmetic of splitk_reduce_kernel, which is then not launched. Bit-identical to the two-kernel form, one launch fewer, and the counters
+    re-arm themselves (second call)."""
+    from b200_harness import OpRunner, conv_op_text
+    N, C, H, W, OC, KH, KW, sy, sx, py, px = case
+    x, w, b = oracle.gen_conv_in(N, C, H, W), oracle.gen_conv_filts(OC, C, KH, KW), oracle.gen_conv_biases(OC)
+    ref = oracle.conv_fwd(x, w, b, (sy, sx), (py, px), relu=bool(relu), acc64=True)
+    outs, launches = [], []
+    for fuse in (1, 0):
+        r = OpRunner(fuse_splitk_reduce=fuse)
+        try:
+            l0 = r.rtc.launches()
+            outs.append(r.run_conv(conv_op_text(N, C, H, W, OC, KH, KW, sy, sx, py, px, relu), x, w, b, ref.shape, iters=2))
+            launches.append(r.rtc.launches() - l0)
+        finally:
+            r.close()
+    assert np.array_equal(outs[0], outs[1])
+    assert launches[0] == launches[1] - 2, launches  # two calls, one reduce launch fewer each
+    assert oracle.mrd(ref, outs[0]) < TOL
+
+
 def test_sgemm_cluster_multicast(oracle):
     from b200_harness import OpRunner
     import boda_b200 as bb

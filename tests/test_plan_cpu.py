@@ -47,7 +47,7 @@ def test_googlenet_concat_inputs_are_written_in_place(bb):
     txt, i, o = nets.googlenet_conv(64)
     desc = bb.pipe_describe(txt)["nodes"]
     plan = bb.fwd_plan(txt, "(prec=bf16)")
-    assert _kinds(plan) == {"conv": 64, "pool": 16, "lrn": 2} and len(plan["alias"]) == 36   # 9 inception Concats x 4 inputs, no copy kernels
+    assert _kinds(plan) == {"conv": 64, "pool": 16, "lrn": 1} and len(plan["alias"]) == 36   # 9 inception Concats x 4 inputs, no copy kernels
     chans = lambda n: dict(desc[n])["chan"]
     per_cat = {}
     for node, (cat, ocix) in plan["alias"].items():
@@ -65,7 +65,7 @@ def test_googlenet_concat_inputs_are_written_in_place(bb):
     assert n_pack(plan) > n_pack(bb.fwd_plan(txt, "")) > 0 and n_pack(bb.fwd_plan(txt, "(pack_by_producers=0)")) == 0
 
 
-@pytest.mark.parametrize("net,batch,n_calls", [("alexnet_ng_conv", 32, 13), ("nin_imagenet", 32, 16)])
+@pytest.mark.parametrize("net,batch,n_calls", [("alexnet_ng_conv", 32, 11), ("nin_imagenet", 32, 16)])
 def test_plain_chains_plan_one_call_per_layer(bb, net, batch, n_calls):
     from boda_b200 import nets
     txt, i, o = nets.NETS[net](batch)
@@ -188,3 +188,23 @@ def test_node_listed_twice_in_a_concat_is_copied_both_times(bb):
     assert "a" not in plan["alias"] and plan["alias"]["b"][1] == 16   # b alone is written in place, at channel 16
     copies = [a for f, a in plan["calls"] if f.startswith("copy__")]
     assert len(copies) == 2 and all(c["in"] == "a" for c in copies)
+
+
+def test_lrn_in_front_of_a_max_pool_is_planned_into_the_pool(bb):
+    """AlexNet's norm1 -> pool1 and norm2 -> pool2 (and GoogLeNet's norm2 -> pool2) run as ONE kernel: the pool call reads the LRN's input and
+    carries the LRN parameters by value, the lrn call is gone. GoogLeNet's norm1 sits BEHIND pool1 and feeds a convolution: not fused.
+    fuse_lrn_pool=0 restores one call per layer."""
+    from boda_b200 import nets
+    txt, i, o = nets.alexnet_ng_conv(32)
+    plan = bb.fwd_plan(txt, "")
+    assert plan["lrnpool"] == {"pool1": ("norm1", "conv1"), "pool2": ("norm2", "conv2")}
+    assert not [f for f, _ in plan["calls"] if f.startswith("lrn__")]
+    pools = {a["out"]: a for f, a in plan["calls"] if f.startswith("pool__")}
+    assert pools["pool1"]["in"] == "conv1" and pools["pool1"]["lrn_local_size"] == "5" and "lrn_local_size" not in pools["pool5"]
+    assert "in_absmax_cells" in pools["pool1"]  # the planes pool1 writes for conv2 are scaled by max|conv1|, published by conv1
+    off = bb.fwd_plan(txt, "(fuse_lrn_pool=0)")
+    assert not off["lrnpool"] and len(off["calls"]) == len(plan["calls"]) + 2 and len([f for f, _ in off["calls"] if f.startswith("lrn__")]) == 2
+    txt, i, o = nets.googlenet_conv(8)
+    plan = bb.fwd_plan(txt, "")
+    assert plan["lrnpool"] == {"pool2": ("norm2", "conv2")}
+    assert [a["out"] for f, a in plan["calls"] if f.startswith("lrn__")] == ["norm1"]
