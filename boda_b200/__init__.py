@@ -208,7 +208,7 @@ def fwd_plan(pipe_text: str, opts: str = "") -> Dict[str, object]:
     need = _chk(lib().b200_fwd_plan(_b(pipe_text), _b(opts), None, 0))
     buf = ctypes.create_string_buffer(need + 1)
     _chk(lib().b200_fwd_plan(_b(pipe_text), _b(opts), buf, need + 1))
-    res: Dict[str, object] = {"calls": [], "prep": [], "alias": {}, "join": {}, "absmax": {}, "lrnpool": {}}
+    res: Dict[str, object] = {"calls": [], "prep": [], "alias": {}, "join": {}, "absmax": {}, "lrnpool": {}, "fcchain": []}
     for line in buf.value.decode().splitlines():
         parts = line.split(" ")
         if parts[0] in ("call", "prep"):
@@ -219,6 +219,8 @@ def fwd_plan(pipe_text: str, opts: str = "") -> Dict[str, object]:
             res["join"][parts[1]] = (parts[2], parts[3])
         elif parts[0] == "absmax":
             res["absmax"][parts[1]] = int(parts[2])
+        elif parts[0] == "fcchain":  # the convolutions one fc_chain call runs, first to last
+            res["fcchain"].append(parts[1:])
         elif parts[0] == "lrnpool":  # pool tag -> (the LRN that runs inside its kernel, the node that kernel reads)
             res["lrnpool"][parts[1]] = (parts[2], parts[3])
     return res

@@ -2,11 +2,13 @@
 // Replaces nvrtc_compute_t (src/nvrtc_util.cc:174-395) and the culibs escape hatch (src/culibs-wrap.cc) for the
 // rtc_fwd path. There is deliberately NO CPU fallback: every function either launches sm_100a kernels or throws.
 #include "b200_compute.h"
+#include <climits>
 #include "igemm.cuh"
 #include "igemm2.cuh"
 #include "igemm3.cuh"
 #include "igemm4.cuh"
 #include "pointwise.cuh"
+#include "fcchain.cuh"
 #include <cudaTypedefs.h>
 #include <cuda_profiler_api.h>
 #include <algorithm>
@@ -54,7 +56,7 @@ uint64_t pack_layout_key(std::initializer_list<long long> v) {
   return h ? h : 1;
 }
 
-enum func_kind_t { FK_CONV, FK_SGEMM, FK_POOL, FK_LRN, FK_RELU, FK_SOFTMAX, FK_COPY, FK_REDUCE, FK_GEN_DATA, FK_BN_FOLD };
+enum func_kind_t { FK_CONV, FK_SGEMM, FK_POOL, FK_LRN, FK_RELU, FK_SOFTMAX, FK_COPY, FK_REDUCE, FK_GEN_DATA, FK_BN_FOLD, FK_FC_CHAIN };
 
 struct conv_plan_t {
   int N, C, H, W, OC, KH, KW, sy, sx, py, px, OH, OW;
@@ -80,6 +82,10 @@ struct func_t {
   p_dev_buf_t w_l1max;      // conv: max over out chans of sum |w| (bound of the outputs, for producer-written fp16 planes)
   uint64_t w_l1max_gen = ~0ull;
   p_dev_buf_t splitk_ws, splitk_tickets;
+  // fc_chain: the compiled conv functions it runs as one kernel (their plans and filter packs are used), the planes between the layers, the barrier counters
+  vector<string> chain_funcs;
+  vector<packed_t> chain_planes;
+  p_dev_buf_t chain_sync;
 };
 
 struct call_ev_t { cudaEvent_t b = nullptr, e = nullptr, kb = nullptr, ke = nullptr; };  // whole call; its main (contraction) kernel
@@ -325,6 +331,8 @@ bool b200_compute_t::set_option(string const &k, string const &v) {
   else if (k == "use_clusters") { use_clusters = std::stoi(v); }
   else if (k == "use_2cta") { use_2cta = std::stoi(v); }
   else if (k == "debug_flags") { debug_flags = std::stoi(v); }
+  else if (k == "fc_l2_ahead") { fc_l2_ahead = std::stoi(v); }
+  else if (k == "fc_l2_next") { fc_l2_next = std::stoi(v); }
   else if (k == "use_sk4") { use_sk4 = std::stoi(v); }
   else if (k == "fuse_splitk_reduce") { fuse_splitk_reduce = std::stoi(v); }
   else if (k == "use_halo") { use_halo = std::stoi(v); }
@@ -489,6 +497,7 @@ func_kind_t resolve_kind(op_base_t const &op, string &gen_arg) {
   if (fn == "copy") { return FK_COPY; }
   if (fn == "reduce") { return FK_REDUCE; }
   if (fn == "bn_fold") { return FK_BN_FOLD; }
+  if (fn == "fc_chain") { return FK_FC_CHAIN; }
   unsup_err("be=b200: unknown function '" + fn + "'");
 }
 
@@ -598,6 +607,15 @@ void plan_conv(conv_plan_t &cp, op_base_t const &op, int num_sms) {
   }
 }
 
+// a layer fc_chain_kernel can run: weights as the 128-row operand, all images in one 32-wide tile, plain 2-d K-major operands, one CTA per
+// (tile, split) unit with all units resident at once
+bool fc_chainable_plan(conv_plan_t const &cp, int num_sms) {
+  long long const pixels = (long long)cp.N * cp.OH * cp.OW;
+  long long const tiles = ceil_div(cp.OC, b200::IGEMM_BM);
+  return cp.swapped && !cp.im2col && !cp.rowmerge && cp.BN == b200::FC_BN && pixels <= b200::FC_BN && cp.OH == 1 && cp.OW == 1 && tiles * cp.splits <= num_sms &&
+         (cp.OC % 4) == 0 && cp.splits <= 16;
+}
+
 }  // namespace
 
 void b200_compute_t::compile(vect_rtc_func_info_t const &func_infos, rtc_compile_opts_t const &) {
@@ -608,6 +626,21 @@ void b200_compute_t::compile(vect_rtc_func_info_t const &func_infos, rtc_compile
     f.op = fi.op;
     f.kind = resolve_kind(fi.op, f.gen_arg);
     if (f.kind == FK_CONV) { plan_conv(f.cp, fi.op, impl->num_sms); }
+    if (f.kind == FK_FC_CHAIN) {  // "layers" = the names of already compiled conv functions, first to last, separated by ':'
+      string const &ls = fi.op.get_str("layers");
+      for (size_t b = 0; b <= ls.size();) {
+        size_t e = ls.find(':', b);
+        if (e == string::npos) { e = ls.size(); }
+        string const n = ls.substr(b, e - b);
+        auto li = impl->funcs.find(n);
+        if (li == impl->funcs.end() || li->second.kind != FK_CONV) { rt_err("fc_chain '" + fi.func_name + "': layer '" + n + "' is not a compiled conv function"); }
+        if (!fc_chainable_plan(li->second.cp, impl->num_sms)) { unsup_err("fc_chain '" + fi.func_name + "': layer '" + n + "' is not inner-product shaped at batch <= 32 (conv_fc_chainable)"); }
+        f.chain_funcs.push_back(n);
+        b = e + 1;
+      }
+      if (f.chain_funcs.size() < 2 || f.chain_funcs.size() > (size_t)b200::FC_MAX_LAYERS) { unsup_err("fc_chain '" + fi.func_name + "': 2.." + str(b200::FC_MAX_LAYERS) + " layers"); }
+      f.chain_planes.resize(f.chain_funcs.size());
+    }
     impl->funcs[fi.func_name] = f;
   }
 }
@@ -654,6 +687,10 @@ bool b200_compute_t::conv_plane_writable(op_base_t const &op, bool dst_is_concat
   // producers of one Concat output would not agree on it, so those modes write planes for a convolution's own output node only
   if (prec != B200_PREC_BF16 && dst_is_concat) { return false; }
   return !cp.swapped && cp.splits == 1 && (cp.OC % 8) == 0;
+}
+bool b200_compute_t::func_fc_chainable(string const &fn) const {
+  auto fi = impl->funcs.find(fn);
+  return fi != impl->funcs.end() && fi->second.kind == FK_CONV && use_sk4 == 0 && fc_chainable_plan(fi->second.cp, impl->num_sms);
 }
 bool b200_compute_t::conv_res_fusable(op_base_t const &op) {
   conv_plan_t cp;
@@ -1288,6 +1325,144 @@ struct run_ctx_t {
   }
   static constexpr uint32_t IGEMM_BM_host() { return b200::IGEMM_BM; }
 
+  // A chain of inner-product-shaped convolutions as one persistent kernel (fcchain.cuh). Arguments: "in" (+ its abs-max cell), and per layer
+  // i = 0.. : "filts<i>", "biases<i>", "out<i>" (+ "out<i>_absmax_cells" / "out<i>_absmax_ix"). The layers' plans and filter packs are those of
+  // the conv functions named by the chain function's "layers" parameter, so each node is bit-identical to running them one by one.
+  template <int kPlanes>
+  void launch_fc_chain_t(int grid, b200::FcChainMaps const &maps, b200::FcChainParams const &prm) {
+    using Cfg = b200::IgemmCfg<b200::FC_BN, kPlanes>;
+    static uint64_t attr_set = 0;
+    if (first_use_on_device(attr_set, rtc.device)) {
+      CU_CHK(cudaFuncSetAttribute(b200::fc_chain_kernel<kPlanes>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(b200::IGEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = rtc.use_pdl ? 1 : 0;
+    CU_CHK(cudaLaunchKernelEx(&cfg, b200::fc_chain_kernel<kPlanes>, maps, prm));
+    launched();
+  }
+  void run_fc_chain() {
+    bool const bf16 = (rtc.prec == B200_PREC_BF16);
+    int const planes = (rtc.prec == B200_PREC_FP32_SPLIT) ? 2 : 1;
+    int const nl = (int)f.chain_funcs.size();
+    b200::FcChainMaps maps;
+    b200::FcChainParams prm;
+    memset(&maps, 0, sizeof(maps));
+    memset(&prm, 0, sizeof(prm));
+    prm.n_layers = nl;
+    prm.bf16 = bf16 ? 1 : 0;
+    prm.chunk_kblks = std::max(1, planes == 2 ? rtc.acc_chunk_kblks : rtc.acc_chunk_kblks_16);
+    prm.idesc = b200::make_idesc_f16(bf16 ? 1u : 0u, 128, b200::FC_BN);
+    prm.l2_ahead = rtc.fc_l2_ahead; prm.l2_next = rtc.fc_l2_next;
+    if (!f.chain_sync) {
+      f.chain_sync = std::make_shared<dev_buf_t>(b200::FC_SYNC_WORDS * 4);
+      CU_CHK(cudaMemsetAsync(f.chain_sync->p, 0, b200::FC_SYNC_WORDS * 4, st));  // re-armed by the kernel's last CTA from here on
+    }
+    prm.sync = static_cast<unsigned int *>(f.chain_sync->p);
+    var_info_t *vprev = &var("in");
+    uint64_t ws_need = 0;
+    int grid = 1;
+    vector<var_info_t *> outs;
+    for (int i = 0; i < nl; ++i) {
+      func_t &lf = im.funcs.at(f.chain_funcs[i]);
+      conv_plan_t const &cp = lf.cp;
+      string const si = str(i);
+      var_info_t &vf = var("filts" + si), &vout = var("out" + si);
+      if (!(vprev->dims == lf.op.get_dims("in")) || !(vf.dims == lf.op.get_dims("filts")) || !(vout.dims == lf.op.get_dims("out"))) {
+        rt_err("fc_chain call '" + rfc.rtc_func_name + "': layer " + si + " var dims differ from the dims '" + f.chain_funcs[i] + "' was compiled for");
+      }
+      long long const K = (long long)cp.KH * cp.KW * cp.Cpad;
+      if ((cp.OC % 4) != 0 || cp.splits > 16) { unsup_err("fc_chain: layer " + si + " needs out chans % 4 == 0 and at most 16 splits"); }
+      if (i > 0 && (cp.C != (int)outs.back()->dims.dsz("chan") || cp.C != cp.Cpad || cp.KH * cp.KW != 1 || (K % 64) != 0)) { unsup_err("fc_chain: layer " + si + " does not read the previous layer's output as a 64-multiple K"); }
+      b200::FcLayer &L = prm.L[i];
+      long long const oc_pad = round_up(cp.OC, 128);
+      // filters: as run_conv packs them (once per weight version)
+      pack(lf.w_pack, vf, cp.OC, cp.C, cp.KH * cp.KW, cp.Cpad, cp.w_tap_stride, cp.w_row_stride, oc_pad * cp.w_row_stride, planes == 2, bf16, 0, 0, 0, nullptr, 0, oc_pad, 0);
+      uint64_t const w_rows = (uint64_t)(cp.w_row_stride / 64) * oc_pad;
+      maps.w_hi[i] = make_tiled_map(lf.w_pack.hi->p, bf16, 64, w_rows, 64, b200::IGEMM_BM);
+      maps.w_lo[i] = planes == 2 ? make_tiled_map(lf.w_pack.lo->p, bf16, 64, w_rows, 64, b200::IGEMM_BM) : maps.w_hi[i];
+      if (i == 0) {  // the first layer's activation planes: the node's shared NHWC planes (written by its producer, or packed here)
+        long long const act_elems = (long long)cp.N * cp.H * cp.W * cp.Cpad;
+        packed_t &a_pack = im.act_packs[{vprev->buf->p, 0u}];
+        pack(a_pack, *vprev, cp.N, cp.C, cp.H * cp.W, cp.Cpad, cp.Cpad, (long long)cp.H * cp.W * cp.Cpad, act_elems, planes == 2, bf16, 0, 0, 0, absmax_cell("in"));
+        uint64_t const kext = cp.full_kernel ? (uint64_t)cp.a_row_stride : (uint64_t)cp.Cpad;
+        maps.a_hi[0] = make_tiled_map(a_pack.hi->p, bf16, kext, cp.a_rows, cp.a_row_stride, b200::FC_BN);
+        maps.a_lo[0] = planes == 2 ? make_tiled_map(a_pack.lo->p, bf16, kext, cp.a_rows, cp.a_row_stride, b200::FC_BN) : maps.a_hi[0];
+        prm.a0_scale2 = static_cast<float *>(a_pack.scale2->p);
+        prm.batch = cp.N;
+      } else {  // planes between the layers belong to the chain: [32][K], rows beyond the batch stay zero
+        packed_t &pk = f.chain_planes[i];
+        uint64_t const bytes = (uint64_t)b200::FC_BN * K * 2;
+        if (!pk.hi || pk.hi->bytes < bytes || (planes == 2 && !pk.lo)) {
+          pk.hi = std::make_shared<dev_buf_t>(bytes);
+          CU_CHK(cudaMemsetAsync(pk.hi->p, 0, bytes, st));
+          if (planes == 2) { pk.lo = std::make_shared<dev_buf_t>(bytes); CU_CHK(cudaMemsetAsync(pk.lo->p, 0, bytes, st)); }
+          pk.scale2 = std::make_shared<dev_buf_t>(8);
+        }
+        maps.a_hi[i] = make_tiled_map(pk.hi->p, bf16, (uint64_t)K, b200::FC_BN, (uint64_t)K, b200::FC_BN);
+        maps.a_lo[i] = planes == 2 ? make_tiled_map(pk.lo->p, bf16, (uint64_t)K, b200::FC_BN, (uint64_t)K, b200::FC_BN) : maps.a_hi[i];
+        b200::FcLayer &P = prm.L[i - 1];
+        P.nxt_hi = static_cast<uint16_t *>(pk.hi->p);
+        P.nxt_lo = planes == 2 ? static_cast<uint16_t *>(pk.lo->p) : nullptr;
+        P.nxt_scale2 = static_cast<float *>(pk.scale2->p);
+        if (cp.N != prm.batch) { rt_err("fc_chain: batch changes along the chain"); }
+      }
+      L.n_out = cp.OC; L.oc_pad = (int)oc_pad;
+      L.tiles = ceil_div(cp.OC, b200::IGEMM_BM); L.splits = cp.splits; L.kblks_total = cp.kblks_total; L.kblks_per_split = cp.kblks_per_split;
+      L.kb_mod = cp.kb_mod; L.ksteps_last = cp.ksteps_last;
+      L.relu = cp.relu;
+      L.has_bias = has_arg("biases" + si) ? 1 : 0;
+      if (L.has_bias) { var_info_t &vb = var("biases" + si); if ((int)vb.dims.dims_prod() != cp.OC) { rt_err("fc_chain: biases size mismatch"); } L.bias = fptr(vb); }
+      L.out = fptr(vout);
+      L.w_scale2 = static_cast<float *>(lf.w_pack.scale2->p);
+      unsigned int *cell = absmax_cell("out" + si);
+      L.out_absmax = cell ? cell : prm.sync + 16 + i;
+      ws_need = std::max<uint64_t>(ws_need, (uint64_t)cp.splits * cp.N * cp.OC * 4);
+      grid = std::max(grid, L.tiles * L.splits);
+      outs.push_back(&vout);
+      vprev = &vout;
+    }
+    if (grid > im.num_sms) { unsup_err("fc_chain: more units than SMs"); }
+    if (!f.splitk_ws || f.splitk_ws->bytes < ws_need) { f.splitk_ws = std::make_shared<dev_buf_t>(ws_need); }
+    prm.ws = static_cast<float *>(f.splitk_ws->p);
+    long long *ts_dev = nullptr;
+    if (rtc.debug_flags & 16) { CU_CHK(cudaMalloc(&ts_dev, (size_t)grid * 32 * sizeof(long long))); CU_CHK(cudaMemsetAsync(ts_dev, 0, (size_t)grid * 32 * sizeof(long long), st)); prm.ts = ts_dev; }
+    mark_kernel_begin();
+    if (planes == 2) { launch_fc_chain_t<2>(grid, maps, prm); } else { launch_fc_chain_t<1>(grid, maps, prm); }
+    mark_kernel_end();
+    if (ts_dev) {  // per event: min / median / max over the CTAs, in us since the first CTA started
+      std::vector<long long> ts((size_t)grid * 32);
+      CU_CHK(cudaStreamSynchronize(st));
+      CU_CHK(cudaMemcpy(ts.data(), ts_dev, ts.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      cudaFree(ts_dev);
+      long long t0 = LLONG_MAX;
+      for (int c = 0; c < grid; ++c) { if (ts[(size_t)c * 32 + 31]) { t0 = std::min(t0, ts[(size_t)c * 32 + 31]); } }
+      static char const *names[8] = {"w_issued", "planes_ready", "drained", "barA", "reduced", "barB", "packed", ""};
+      string line = "fc_chain stamps '" + rfc.rtc_func_name + "' grid=" + str(grid) + " (us since start, min/median/max over CTAs):";
+      for (int l = 0; l < nl; ++l) {
+        line += "\n  layer " + str(l) + ":";
+        for (int k = 0; k < 7; ++k) {
+          std::vector<long long> v;
+          for (int c = 0; c < grid; ++c) { long long const t = ts[(size_t)c * 32 + 8 * l + k]; if (t) { v.push_back(t - t0); } }
+          if (v.empty()) { continue; }
+          std::sort(v.begin(), v.end());
+          char buf[96];
+          snprintf(buf, sizeof(buf), " %s=%.1f/%.1f/%.1f", names[k], v.front() * 1e-3, v[v.size() / 2] * 1e-3, v.back() * 1e-3);
+          line += buf;
+        }
+      }
+      fprintf(stderr, "%s\n", line.c_str());
+    }
+    for (auto *v : outs) { im.bump(*v); }
+  }
+
   // c[M,N] = a[K,M]^T b[K,N]  (test/rtc/sgemm.cucl:1-3). P = a^T rows (M), Q = b^T rows (N), both packed K-major.
   void run_sgemm() {
     var_info_t &va = var("a"), &vb = var("b"), &vc = var("c");
@@ -1652,6 +1827,7 @@ uint32_t b200_compute_t::run(rtc_func_call_t const &rfc) {
     case FK_REDUCE: ctx.run_reduce(); break;
     case FK_GEN_DATA: ctx.run_gen_data(); break;
     case FK_BN_FOLD: ctx.run_bn_fold(); break;
+    case FK_FC_CHAIN: ctx.run_fc_chain(); break;
   }
   if (impl->timing) { CU_CHK(cudaEventRecord(ev.e, impl->stream)); }
   impl->calls.push_back(ev);

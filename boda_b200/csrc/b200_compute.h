@@ -63,6 +63,8 @@ struct b200_compute_t {
   string be = "b200";
   int device = 0;
   b200_prec_t prec = B200_PREC_FP32_SPLIT;
+  int fc_l2_ahead = 0;      // fc_chain kernel: the first layer's filter tiles are requested into L2 this many k-blocks ahead of the shared-memory ring (0 = off; measured: slower, r02)
+  int fc_l2_next = 0;       // fc_chain kernel: request the next layer's filter tiles into L2 while the current layer drains and reduces (measured: no net gain, r02)
   int debug_flags = 0;      // timing experiments on the 1-CTA kernel: 1 = skip TMA loads, 2 = skip MMA issue (results are garbage)
   int use_2cta = 1;         // CTA pairs: one tcgen05.mma.cta_group::2 per 256 x BN tile (igemm2.cuh)
   int use_clusters = 0;     // 1-CTA tiles only: let CTAs that share an operand tile form a cluster and TMA-multicast it (choose_cluster)
@@ -136,6 +138,10 @@ struct b200_compute_t {
   bool conv_res_fusable(op_base_t const &op);
   bool conv_halo_pad(op_base_t const &op, int &py, int &px);  // halo-mode convolutions read their input planes in the shared-padding layout (py, px)
   bool conv_uses_sk4(op_base_t const &op);
+  // inner-product shaped at batch <= 32 (weights as the 128-row operand, one 32-image tile, all (tile, split) units resident): a run of such
+  // conv functions, each reading the previous one's output, can be one "fc_chain" function (fcchain.cuh): str parameter "layers" = their names
+  // joined by ':'; call arguments "in", and per layer i "filts<i>", "biases<i>", "out<i>" (+ the abs-max cell arguments of "in" / "out<i>")
+  bool func_fc_chainable(string const &fn) const;  // (of a compiled conv function)
   bool has_var(string const &vn) const;
   bool has_func(string const &fn) const;
   // host-only: the launch plan compile() made for a convolution function, as "kernel=pair|single bn=<N tile> kblks=<64-wide k-blocks>

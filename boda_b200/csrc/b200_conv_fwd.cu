@@ -487,6 +487,7 @@ void b200_conv_fwd_t::init(p_conv_pipe_t const &cp_, string const &opts) {
         else if (k == "concat_by_offset") { concat_by_offset = (uint32_t)std::stoul(v); }
         else if (k == "fuse_eltwise") { fuse_eltwise = (uint32_t)std::stoul(v); }
         else if (k == "fuse_lrn_pool") { fuse_lrn_pool = (uint32_t)std::stoul(v); }
+        else if (k == "fuse_fc_chain") { fuse_fc_chain = (uint32_t)std::stoul(v); }
         else if (k == "pack_by_producers") { pack_by_producers = (uint32_t)std::stoul(v); }
         else if (k == "op_tune" && !kv.second->is_leaf) {  // the reference's nested form, op_tune=(k1conv=1,tconv=1,...) (src/rtc_fwd.cc:36)
           for (auto const &tk : kv.second->kids) { if (!rtc->set_option(tk.first, tk.second->is_leaf ? tk.second->leaf : string())) { rt_err("mode=b200: unused op_tune option '" + tk.first + "'"); } }
@@ -602,6 +603,7 @@ void b200_conv_fwd_t::init(p_conv_pipe_t const &cp_, string const &opts) {
   }
   rtc->create_var_with_dims(absmax_cells_vn, dims_t({(uint32_t)std::max<size_t>(absmax_ix.size(), 1)}, {"cell"}, "uint32_t"));
   for (auto const &op : cp->ops) { gen_op(op); }
+  if (fuse_fc_chain) { fuse_fc_chains(); }
   for (auto &kv : concat_alias) {  // read-back functions: node = Concat output[:, ocix : ocix + chan]
     op_base_t cop;
     cop.set_type("Concat");
@@ -615,6 +617,68 @@ void b200_conv_fwd_t::init(p_conv_pipe_t const &cp_, string const &opts) {
   }
   info_log = "mode=b200 plat=" + rtc->get_plat_tag() + " nodes=" + str(cp->nodes.size()) + " ops=" + str(cp->ops.size()) + " fwd_calls=" + str(fwd_calls.size()) +
              " conv_flops=" + str(cp->total_conv_flops());
+}
+
+// Runs of consecutive conv calls that are inner-product shaped at this batch (b200_compute_t::func_fc_chainable), each reading the previous
+// one's output, become one "fc_chain" call (fcchain.cuh). The conv functions stay compiled: the chain uses their plans and filter packs, and
+// every layer's fp32 node is still written, so other readers of those nodes are unaffected.
+void b200_conv_fwd_t::fuse_fc_chains() {
+  auto arg_var = [](fwd_call_t const &c, char const *an) -> string {
+    auto i = c.rfc.arg_map.find(an);
+    return (i != c.rfc.arg_map.end() && i->second.is_var()) ? i->second.get_var() : string();
+  };
+  auto plain = [&](fwd_call_t const &c) {  // a conv call with nothing but in / filts / biases / out and abs-max cells
+    if (c.func_name.compare(0, 6, "conv__") != 0 || !rtc->func_fc_chainable(c.func_name)) { return false; }
+    for (auto const &kv : c.rfc.arg_map) {
+      string const &k = kv.first;
+      if (k != "in" && k != "filts" && k != "biases" && k != "out" && k != "in_absmax_cells" && k != "in_absmax_ix" && k != "out_absmax_cells" && k != "out_absmax_ix") { return false; }
+    }
+    return true;
+  };
+  vector<fwd_call_t> calls;
+  vector<double> flops;
+  for (size_t i = 0; i < fwd_calls.size();) {
+    size_t j = i;
+    if (plain(fwd_calls[i])) {
+      j = i + 1;
+      while (j < fwd_calls.size() && j - i < 4 && plain(fwd_calls[j]) && arg_var(fwd_calls[j], "in") == arg_var(fwd_calls[j - 1], "out")) { ++j; }
+    }
+    if (j - i < 2) { calls.push_back(fwd_calls[i]); flops.push_back(call_flops[i]); ++i; continue; }
+    fwd_call_t c;
+    c.tag = fwd_calls[i].tag;
+    c.func_name = "fc_chain__" + c.tag + "__" + str(calls.size());
+    op_base_t cop;
+    string layers;
+    vector<string> tags;
+    double fl = 0.0;
+    for (size_t k = i; k < j; ++k) {
+      fwd_call_t const &l = fwd_calls[k];
+      string const si = str(k - i);
+      layers += (k == i ? "" : ":") + l.func_name;
+      tags.push_back(l.tag);
+      fl += call_flops[k];
+      for (auto const &kv : l.rfc.arg_map) {
+        if (kv.first == "in" || kv.first == "in_absmax_cells" || kv.first == "in_absmax_ix") { if (k == i) { c.rfc.arg_map[kv.first] = kv.second; } continue; }
+        string an = kv.first;  // filts -> filts<i>, out_absmax_ix -> out<i>_absmax_ix
+        size_t const us = an.find('_');
+        an = (us == string::npos) ? an + si : an.substr(0, us) + si + an.substr(us);
+        c.rfc.arg_map[an] = kv.second;
+      }
+    }
+    cop.str_vals["layers"] = layers;
+    rtc_func_info_t fi;
+    fi.func_name = c.func_name;
+    fi.op = cop;
+    fi.op.set_func_name("fc_chain");
+    rtc->compile({fi}, rtc_compile_opts_t());
+    c.rfc.rtc_func_name = c.func_name;
+    calls.push_back(c);
+    flops.push_back(fl);
+    fc_chains.push_back(tags);
+    i = j;
+  }
+  fwd_calls.swap(calls);
+  call_flops.swap(flops);
 }
 
 string b200_conv_fwd_t::plan_text() const {
@@ -634,6 +698,7 @@ string b200_conv_fwd_t::plan_text() const {
   for (auto const &c : fwd_calls) { put_call("call", c); }
   for (auto const &kv : concat_alias) { out += "alias " + kv.first + " " + kv.second.cat_node + " " + str(kv.second.ocix) + "\n"; }
   for (auto const &kv : res_fuse) { out += "join " + kv.first + " " + kv.second.out_node + " " + kv.second.res_node + "\n"; }
+  for (auto const &ch : fc_chains) { out += "fcchain"; for (auto const &t : ch) { out += " " + t; } out += "\n"; }
   for (auto const &kv : lrn_fuse) { out += "lrnpool " + kv.first + " " + kv.second.lrn_tag + " " + kv.second.in_node + "\n"; }
   for (auto const &kv : absmax_ix) { out += "absmax " + kv.first + " " + str(kv.second) + "\n"; }
   return out;

@@ -52,6 +52,8 @@ struct b200_conv_fwd_t {
   uint32_t pack_by_producers = 1; // bf16 storage mode: convolutions also write the NHWC bf16 plane their consumers read (no activation pack kernel)
   uint32_t fuse_lrn_pool = 1;     // an LRN (local_size 5) read only by a 3x3 / 2 max pool runs inside that pool's kernel: no round trip of the normalised map, one
                                   // launch fewer; the LRN node is computed on demand (plain lrn call) when run_fwd is asked for it
+  uint32_t fuse_fc_chain = 1;     // consecutive inner-product-shaped convolutions at batch <= 32 (AlexNet fc6 -> fc7 -> fc8), each reading the previous one's
+                                  // output, run as ONE persistent kernel (fcchain.cuh): the weight stream does not stop between the layers
   uint32_t fuse_eltwise = 1;      // residual joins: a two-input Eltwise SUM (+ReLU) whose one input is written by a Convolution and read by nothing else is
                                   // folded into that convolution's epilogue; the bypassed node is recomputed on demand when read
   uint32_t concat_by_offset = 1;  // Convolutions that only feed a Concat write straight into its output at their channel offset (no copy kernel);
@@ -122,6 +124,8 @@ struct b200_conv_fwd_t {
   map<string, res_fuse_t> res_fuse;          // Convolution tag -> (Eltwise output it writes, the join's other input)
   struct lrn_fuse_t { string lrn_tag, in_node, lrn_node; };
   map<string, lrn_fuse_t> lrn_fuse;          // Pooling tag -> the LRN in front of it that runs inside the pool kernel (lrn_maxpool_kernel)
+  vector<vector<string>> fc_chains;          // per fc_chain call: the tags of the convolutions it runs
+  void fuse_fc_chains();
   map<string, rtc_func_call_t> elided_calls; // bypassed node -> the plain convolution call that materialises it when somebody reads it
   map<string, concat_alias_t> concat_alias;  // node -> (Concat output that holds its channels, channel offset, name of the read-back function)
   void materialise_aliased(string const &node);

@@ -83,6 +83,10 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, CUtensorMap const *m
 // im2col 4-d on an NHWC tensor: coordinates {c, w, h, n} of the first pixel's filter-footprint corner, plus the
 // filter-tap offsets {w_off, h_off}; the hardware walks pixelsPerColumn output pixels (row-major over w,h,n with the
 // traversal strides baked into the map) and zero-fills taps that fall outside the image.
+// the same tile into L2 only (no shared-memory destination, no completion): a later tma_load_2d of it hits L2
+__device__ __forceinline__ void tma_prefetch_l2_2d(CUtensorMap const *m, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_load_im2col_4d(void *smem_dst, CUtensorMap const *m, uint64_t *bar, int32_t c, int32_t w,
                                                    int32_t h, int32_t n, uint16_t w_off, uint16_t h_off) {
   asm volatile(

@@ -362,3 +362,33 @@ def test_lrn_inside_the_pool_kernel_matches_separate_kernels(oracle, net, batch,
             assert np.array_equal(a[n], b[n]), (n, oracle.mrd(a[n], b[n]))
         else:
             assert np.isfinite(a[n]).all() and oracle.mrd(a[n], b[n]) < 5e-4, (n, oracle.mrd(a[n], b[n]))
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "fp16"])
+@pytest.mark.parametrize("net,batch,in_sz,nodes", [("alexnet_ng_conv", 32, 227, ["fc6", "fc7", "fc8"]), ("alexnet_ng_conv", 3, 227, ["fc6", "fc7", "fc8"]),
+                                                   ("googlenet_conv", 8, 224, ["cls1_fc1", "cls1_fc2", "cls2_fc2", "cls3_fc"])])
+def test_fc_chain_kernel_is_bit_identical_to_separate_layers(oracle, net, batch, in_sz, nodes, prec):
+    """Inner-product chains (AlexNet fc6 -> fc7 -> fc8, GoogLeNet's auxiliary classifiers) as ONE persistent kernel (fcchain.cuh) against the
+    per-layer path (fuse_fc_chain=0: contraction + split-K reduce + activation pack per layer): same tiles, splits, drain chunks, reduce order
+    and plane arithmetic -> every node BIT-IDENTICAL, in every precision mode; several forwards in a row (the kernel re-arms its own barrier
+    counters), fewer launches."""
+    import boda_b200 as bb
+    from boda_b200 import nets
+    txt, i, o = nets.NETS[net](batch)
+    params = nets.synth_params(txt)
+    x = nets.synth_input((batch, 3, in_sz, in_sz))
+    res = []
+    for on in (1, 0):
+        fwd = bb.B200ConvFwd(txt, "(prec=%s,fuse_fc_chain=%d)" % (prec, on))
+        for k, v in params.items():
+            fwd.set_param(k, v)
+        out = fwd.run_fwd({i: x}, nodes)
+        l0 = fwd.launches()
+        for _ in range(3):
+            again = fwd.run_fwd({i: x}, [nodes[-1]])
+        res.append((out, again, (fwd.launches() - l0) // 3))
+    (a, a2, la), (b, b2, lb) = res
+    assert la < lb, (la, lb)
+    for n in nodes:
+        assert np.isfinite(a[n]).all() and np.array_equal(a[n], b[n]), (n, oracle.mrd(a[n], b[n]))
+    assert np.array_equal(a2[nodes[-1]], a[nodes[-1]])

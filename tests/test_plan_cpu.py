@@ -65,7 +65,7 @@ def test_googlenet_concat_inputs_are_written_in_place(bb):
     assert n_pack(plan) > n_pack(bb.fwd_plan(txt, "")) > 0 and n_pack(bb.fwd_plan(txt, "(pack_by_producers=0)")) == 0
 
 
-@pytest.mark.parametrize("net,batch,n_calls", [("alexnet_ng_conv", 32, 11), ("nin_imagenet", 32, 16)])
+@pytest.mark.parametrize("net,batch,n_calls", [("alexnet_ng_conv", 32, 9), ("nin_imagenet", 32, 16)])
 def test_plain_chains_plan_one_call_per_layer(bb, net, batch, n_calls):
     from boda_b200 import nets
     txt, i, o = nets.NETS[net](batch)
@@ -131,7 +131,7 @@ def test_alexnet_launch_plans_match_the_measured_launch_list(bb):
     fc6-8 with the weights as the 128-row operand; stream-K where whole tiles would leave more than 8 % of a round idle (conv3/4: 75 tiles on 74
     pairs, conv5: 50, the inner-product layers: 16 / 16 / 4 tiles). By default the round-1 plans, which equal what ncu saw on the B200
     (profiles/launches_r01_final_ncu_graph_nodes.md): igemm_umma_2cta_kernel<96|128, 2> with grids 148 / 148 / 132 / 132 / 132 for conv1..conv5,
-    igemm_umma_kernel<32, 2> with grids (32,1,4), (32,1,4), (8,1,8) for fc6..fc8."""
+    igemm_umma_kernel<32, 2> with grids (32,1,4), (32,1,4), (8,1,8) for fc6..fc8 (fuse_fc_chain=0; by default those three are one fc_chain call)."""
     from boda_b200 import nets
     txt, i, o = nets.alexnet_ng_conv(32)
 
@@ -147,7 +147,7 @@ def test_alexnet_launch_plans_match_the_measured_launch_list(bb):
     # producers write their consumers' planes in the consumer's layout: pool1 -> conv2 (5x5, pad 2), pool2 -> conv3, conv3 -> conv4, conv4 -> conv5 (3x3, pad 1)
     pads = {f.split("__")[1]: (a.get("out_pack_py"), a.get("out_pack_px")) for f, a in plan["calls"] if "out_pack" in a}
     assert pads == {"pool1": ("2", "2"), "pool2": ("1", "1"), "conv3": ("1", "1"), "conv4": ("1", "1"), "pool5": (None, None)}, pads
-    _, got1 = plans("")
+    _, got1 = plans("(fuse_fc_chain=0)")
     want1 = [("conv1", "pair", 96, "148x1x1", 11), ("conv2", "pair", 128, "148x1x1", 50), ("conv3", "pair", 128, "132x1x1", 36), ("conv4", "pair", 128, "132x1x1", 54),
              ("conv5", "pair", 96, "132x1x1", 54), ("fc6-conv", "single", 32, "32x1x4", 144), ("fc7-conv", "single", 32, "32x1x4", 64), ("fc8-conv", "single", 32, "8x1x8", 64)]
     assert [(t, p["kernel"], int(p["bn"]), p["grid"], int(p["kblks"])) for t, p in got1] == want1
@@ -208,3 +208,24 @@ def test_lrn_in_front_of_a_max_pool_is_planned_into_the_pool(bb):
     plan = bb.fwd_plan(txt, "")
     assert plan["lrnpool"] == {"pool2": ("norm2", "conv2")}
     assert [a["out"] for f, a in plan["calls"] if f.startswith("lrn__")] == ["norm1"]
+
+
+def test_inner_product_chains_are_planned_as_one_call(bb):
+    """AlexNet fc6 -> fc7 -> fc8 at batch <= 32 is ONE fc_chain call (fcchain.cuh) carrying every layer's filts / biases / out and abs-max
+    cells; GoogLeNet's auxiliary classifier pairs too; at batch 64 (two image tiles) and for ResNet-50's single fc1000 nothing is chained.
+    fuse_fc_chain=0 and the round-2 contraction kernel (use_sk4=1, which runs these layers itself) restore one call per layer."""
+    from boda_b200 import nets
+    txt, i, o = nets.alexnet_ng_conv(32)
+    plan = bb.fwd_plan(txt, "")
+    assert plan["fcchain"] == [["fc6-conv", "fc7-conv", "fc8-conv"]]
+    (f, a), = [(f, a) for f, a in plan["calls"] if f.startswith("fc_chain__")]
+    assert plan["calls"][-1][0] == f and a["in"] == "pool5" and [a["out%d" % k] for k in range(3)] == ["fc6", "fc7", "fc8"]
+    assert [a["filts%d" % k] for k in range(3)] == ["fc6-conv_filts", "fc7-conv_filts", "fc8-conv_filts"] and "biases2" in a
+    assert "in_absmax_ix" in a and "out0_absmax_ix" in a and "out1_absmax_ix" in a and "out2_absmax_ix" not in a  # nobody reads max|fc8|
+    for opts in ("(fuse_fc_chain=0)", "(use_sk4=1)"):
+        off = bb.fwd_plan(txt, opts)
+        assert not off["fcchain"] and len(off["calls"]) == len(plan["calls"]) + 2
+    assert bb.fwd_plan(nets.googlenet_conv(8)[0], "")["fcchain"] == [["cls1_fc1-conv", "cls1_fc2-conv"], ["cls2_fc1-conv", "cls2_fc2-conv"]]
+    assert bb.fwd_plan(nets.googlenet_conv(64)[0], "(prec=bf16)")["fcchain"] == []
+    assert bb.fwd_plan(nets.resnet50(32)[0], "")["fcchain"] == []
+    assert bb.fwd_plan(nets.alexnet_ng_conv(64)[0], "")["fcchain"] == []
