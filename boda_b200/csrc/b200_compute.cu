@@ -331,6 +331,7 @@ bool b200_compute_t::set_option(string const &k, string const &v) {
   else if (k == "use_clusters") { use_clusters = std::stoi(v); }
   else if (k == "use_2cta") { use_2cta = std::stoi(v); }
   else if (k == "debug_flags") { debug_flags = std::stoi(v); }
+  else if (k == "fuse_input_pack") { fuse_input_pack = std::stoi(v); }
   else if (k == "fc_l2_ahead") { fc_l2_ahead = std::stoi(v); }
   else if (k == "fc_l2_next") { fc_l2_next = std::stoi(v); }
   else if (k == "use_sk4") { use_sk4 = std::stoi(v); }
@@ -582,6 +583,8 @@ void plan_conv(conv_plan_t &cp, op_base_t const &op, int num_sms) {
     int best = 0;
     long long best_cost = 0, best_cols = 0;
     long long const m_pairs = ceil_div(ceil_div(pixels, b200::IGEMM_BM), 2), slots = std::max(num_sms / 2, 1);
+    // (measured, r02: counting the fp32-parity mode's three MMAs per k-step here -- which moves AlexNet conv2 from 184 tiles of 128 = 3 rounds
+    // to 368 tiles of 64 = 5 half rounds -- made the step 8 % SLOWER: the tensor pipe does not run 64-wide MMAs at twice the rate of 128-wide ones)
     for (int bn : {128, 96, 64, 32}) {
       long long const tiles_n = ceil_div(cp.OC, bn), cols = tiles_n * bn;
       long long const cost = ceil_div(m_pairs * tiles_n, slots) * (std::max(4 * bn, 300) + 64);
@@ -800,14 +803,39 @@ struct run_ctx_t {
       CU_CHK(cudaMemsetAsync(pk.hi->p, 0, total_elems * 2, st));
       if (want_lo) { pk.lo = std::make_shared<dev_buf_t>(total_elems * 2); CU_CHK(cudaMemsetAsync(pk.lo->p, 0, total_elems * 2, st)); }
       pk.scale2 = std::make_shared<dev_buf_t>(8);
-      pk.absmax_bits = std::make_shared<dev_buf_t>(8);  // {max bits, blocks-done counter}
-      CU_CHK(cudaMemsetAsync(pk.absmax_bits->p, 0, 8, st));
+      pk.absmax_bits = std::make_shared<dev_buf_t>(16);  // {max bits, blocks-done counter, blocks-left counter (absmax_pack_smallc_kernel)}
+      CU_CHK(cudaMemsetAsync(pk.absmax_bits->p, 0, 16, st));
       if (bf16) { static float const ones[2] = {1.0f, 1.0f}; CU_CHK(cudaMemcpyAsync(pk.scale2->p, ones, 8, cudaMemcpyHostToDevice, st)); }  // bf16 has fp32's exponent range: no scaling, ever
     }
     long long const n = (long long)B * R * Cc;
     int const blocks = (int)std::min<long long>((n + 4095) / 4096, 148 * 8);
     bool const use_scale = !bf16;  // bf16 has fp32's exponent range: no scaling needed
     if (!use_scale) { absmax_src = nullptr; }
+    uint16_t *hi0 = static_cast<uint16_t *>(pk.hi->p), *lo0 = want_lo ? static_cast<uint16_t *>(pk.lo->p) : nullptr;
+    if (!absmax_src && use_scale && rtc.fuse_input_pack && smallc_W > 0 && (Rpad == 4 || Rpad == 8) && dst_base % Rpad == 0 &&
+        (reinterpret_cast<uintptr_t>(fptr(src)) & 15) == 0) {
+      // network input (few channels, row-merged layout): max|x|, the scale and the planes in ONE kernel -- every CTA keeps its rows in shared
+      // memory across a grid-wide barrier, so the input is read once and the step has a launch fewer (absmax_pack_smallc_kernel)
+      int const H = Cc / smallc_W, Wp = (int)(dst_chi_stride / Rpad), px_off = (int)(dst_base / Rpad);
+      for (int upi = std::min(H, 64); upi >= 1; --upi) {  // row groups per image: as many as can be resident at once
+        int const rows = ceil_div(H, upi);
+        if (ceil_div(H, rows) != upi) { continue; }
+        size_t const smem = (size_t)R * b200::smallc_row_stride(rows, smallc_W) * 4;
+        if (smem > 200 * 1024) { break; }
+        auto kern = Rpad == 4 ? b200::absmax_pack_smallc_kernel<4> : b200::absmax_pack_smallc_kernel<8>;
+        static uint64_t attr4_ = 0, attr8_ = 0;
+        if (first_use_on_device(Rpad == 4 ? attr4_ : attr8_, rtc.device)) { CU_CHK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); prefer_max_smem(kern); }
+        int per_sm = 0;
+        CU_CHK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+        if ((long long)B * upi > (long long)im.num_sms * per_sm) { continue; }
+        launch_k(kern, dim3(B * upi), dim3(256), smem, fptr(src), hi0, lo0, static_cast<float *>(pk.scale2->p), static_cast<unsigned int *>(pk.absmax_bits->p), R, H, smallc_W, Wp, px_off, rows, upi,
+                 (long long)B * R * Cc);
+        launched();
+        pk.src_gen = *src.gen;
+        pk.src_ptr = src.buf->p;
+        return;
+      }
+    }
     if (!absmax_src) {  // nobody published max|x| for this tensor: reduce it here
       if (use_scale) {  // max|x| and the scale in one launch (the last block finalises)
         B200_CARVEOUT_ONCE(b200::absmax_kernel); launch_k(b200::absmax_kernel, dim3(std::max(blocks, 1)), dim3(256), 0, fptr(src), n, static_cast<unsigned int *>(pk.absmax_bits->p), static_cast<float *>(pk.scale2->p));
@@ -1224,8 +1252,8 @@ struct run_ctx_t {
           CU_CHK(cudaMemsetAsync(out_pk->hi->p, 0, bytes, st));
           if (planes == 2) { out_pk->lo = std::make_shared<dev_buf_t>(bytes); CU_CHK(cudaMemsetAsync(out_pk->lo->p, 0, bytes, st)); }
           out_pk->scale2 = std::make_shared<dev_buf_t>(8);
-          out_pk->absmax_bits = std::make_shared<dev_buf_t>(8);
-          CU_CHK(cudaMemsetAsync(out_pk->absmax_bits->p, 0, 8, st));
+          out_pk->absmax_bits = std::make_shared<dev_buf_t>(16);
+          CU_CHK(cudaMemsetAsync(out_pk->absmax_bits->p, 0, 16, st));
           static float const ones[2] = {1.0f, 1.0f};
           CU_CHK(cudaMemcpyAsync(out_pk->scale2->p, ones, 8, cudaMemcpyHostToDevice, st));
         } else if (out_pk->layout_key != lkey) {  // same storage, other geometry: padding positions must be zero again
@@ -1529,8 +1557,8 @@ struct run_ctx_t {
       CU_CHK(cudaMemsetAsync(out_pk->hi->p, 0, bytes, st));
       if (npl == 2) { out_pk->lo = std::make_shared<dev_buf_t>(bytes); CU_CHK(cudaMemsetAsync(out_pk->lo->p, 0, bytes, st)); }
       out_pk->scale2 = std::make_shared<dev_buf_t>(8);
-      out_pk->absmax_bits = std::make_shared<dev_buf_t>(8);
-      CU_CHK(cudaMemsetAsync(out_pk->absmax_bits->p, 0, 8, st));
+      out_pk->absmax_bits = std::make_shared<dev_buf_t>(16);
+      CU_CHK(cudaMemsetAsync(out_pk->absmax_bits->p, 0, 16, st));
       if (bf16) { static float const ones[2] = {1.0f, 1.0f}; CU_CHK(cudaMemcpyAsync(out_pk->scale2->p, ones, 8, cudaMemcpyHostToDevice, st)); }
     } else if (out_pk->layout_key != lkey) {  // same storage, other geometry: padding positions must be zero again
       CU_CHK(cudaMemsetAsync(out_pk->hi->p, 0, out_pk->hi->bytes, st));

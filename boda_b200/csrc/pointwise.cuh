@@ -964,6 +964,102 @@ pack_smallc_kernel(float const *__restrict__ src, uint16_t *__restrict__ hi, uin
   }
 }
 
+// absmax_kernel + pack_smallc_kernel in one launch (fp16 planes need max|x| of the WHOLE tensor before the first element can be written):
+// a CTA owns `rows` image rows of one image, all C channels; it fetches them into shared memory with one bulk copy per channel (runs start at
+// any float offset of a 16-byte unit: the enclosing units are fetched), folds its max|x| into cells[0], waits at a grid-wide barrier
+// (cells[1]; every CTA is resident -- the host sizes the grid by occupancy), derives the scale and writes its pixels' planes from shared
+// memory. The input is read from memory once; cells[2] counts the CTAs out, the last one re-arms the cells.
+__host__ __device__ constexpr int smallc_row_stride(int rows, int W) { return (rows * W + 3 + 3) & ~3; }
+
+template <int kCp>
+__global__ void __launch_bounds__(256)
+absmax_pack_smallc_kernel(float const *__restrict__ src, uint16_t *__restrict__ hi, uint16_t *__restrict__ lo, float *__restrict__ scale2, unsigned int *cells,
+                          int C, int H, int W, int Wp, int px_off, int rows, int upi, long long n_total) {
+  extern __shared__ __align__(128) float ap_s[];
+  __shared__ __align__(8) uint64_t full_bar;
+  __shared__ float warp_m[8];
+  __shared__ float s_bcast;
+  int const img = blockIdx.x / upi, y0 = (blockIdx.x - img * upi) * rows;
+  int const nrows = min(rows, H - y0), npix = nrows * W;
+  int const rs = smallc_row_stride(rows, W);
+  long long const hw = static_cast<long long>(H) * W;
+  long long const g0 = (static_cast<long long>(img) * C * H + y0) * W;  // float index of channel 0's run; channel c: + c * hw
+  if (threadIdx.x == 0) { mbar_init(&full_bar, 1); fence_barrier_init(); }
+  __syncthreads();
+  pdl_prologue();
+  if (threadIdx.x < 32) {  // lane c fetches channel c
+    int const c = threadIdx.x;
+    bool const mine = c < C;
+    long long const g = g0 + c * hw;
+    int const off = static_cast<int>(g & 3);
+    // whole 16-byte units, but never past the end of the tensor (its last floats, if any, are read one by one below)
+    long long const units_end = min((g - off) + ((off + npix + 3) & ~3), n_total & ~3ll);
+    uint32_t const bytes = mine ? static_cast<uint32_t>(max(0ll, units_end - (g - off))) * 4u : 0u;
+    uint32_t const total = __reduce_add_sync(0xffffffffu, bytes);
+    if (c == 0) { mbar_expect_tx(&full_bar, total); }
+    __syncwarp();
+    if (mine && bytes) {
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(ap_s + c * rs)), "l"(src + (g - off)),
+                   "r"(bytes), "r"(smem_u32(&full_bar))
+                   : "memory");
+    }
+    if (mine) { for (long long i = max(units_end, g); i < g + npix; ++i) { ap_s[c * rs + off + static_cast<int>(i - g)] = __ldg(src + i); } }
+  }
+  mbar_wait(&full_bar, 0);
+  __syncthreads();
+  float m = 0.0f;
+  for (int c = 0; c < C; ++c) {
+    float const *row = ap_s + c * rs + static_cast<int>((g0 + c * hw) & 3);
+    for (int i = threadIdx.x; i < npix; i += 256) { m = fmaxf(m, fabsf(row[i])); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o)); }
+  if ((threadIdx.x & 31) == 0) { warp_m[threadIdx.x >> 5] = m; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float bm = 0.0f;
+    for (int w = 0; w < 8; ++w) { bm = fmaxf(bm, warp_m[w]); }
+    if (bm > 0.0f) { atomicMax(cells, __float_as_uint(bm)); }
+    __threadfence();
+    atomicAdd(cells + 1, 1u);
+    unsigned int v = 0, spins = 0;
+    while (true) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cells + 1) : "memory");
+      if (v >= gridDim.x) { break; }
+      if (++spins > (1u << 22)) { printf("b200: input pack barrier never completed (block %d: %u of %u)\n", blockIdx.x, v, gridDim.x); __trap(); }
+    }
+    float const s = scale_from_absmax_bits(*reinterpret_cast<volatile unsigned int *>(cells));
+    s_bcast = s;
+    if (blockIdx.x == 0) { scale2[0] = s; scale2[1] = 1.0f / s; }
+    __threadfence();
+    if (atomicAdd(cells + 2, 1u) == gridDim.x - 1) { cells[0] = 0u; cells[1] = 0u; cells[2] = 0u; }  // everybody has read the maximum: re-arm for the next launch
+  }
+  __syncthreads();
+  float const s = s_bcast;
+  int offc[kCp];
+#pragma unroll
+  for (int c = 0; c < kCp; ++c) { offc[c] = c * rs + static_cast<int>((g0 + c * hw) & 3); }
+  for (int pix = threadIdx.x; pix < npix; pix += 256) {
+    int const y = pix / W, x = pix - y * W;
+    __align__(16) uint16_t h[kCp], l[kCp];
+#pragma unroll
+    for (int c = 0; c < kCp; ++c) {
+      float const v = (c < C) ? ap_s[offc[c] + pix] * s : 0.0f;
+      __half const hv = __float2half_rn(v);
+      h[c] = __half_as_ushort(hv);
+      l[c] = __half_as_ushort(__float2half_rn(v - __half2float(hv)));
+    }
+    long long const o = ((static_cast<long long>(img) * H + y0 + y) * Wp + x + px_off) * kCp;
+    if (kCp == 4) {
+      *reinterpret_cast<uint2 *>(hi + o) = *reinterpret_cast<uint2 *>(h);
+      if (lo) { *reinterpret_cast<uint2 *>(lo + o) = *reinterpret_cast<uint2 *>(l); }
+    } else {
+      *reinterpret_cast<uint4 *>(hi + o) = *reinterpret_cast<uint4 *>(h);
+      if (lo) { *reinterpret_cast<uint4 *>(lo + o) = *reinterpret_cast<uint4 *>(l); }
+    }
+  }
+}
+
 // src [B][R][C] fp32 (C contiguous)  ->  dst planes [B][C][Rpad] 16-bit (R contiguous, zero padded to Rpad):
 //   NCHW activations  (B=img, R=chan, C=y*x)        -> NHWC  [img][y*x][chan_pad]
 //   OIHW filters      (B=out_chan, R=in_chan, C=ky*kx) -> [out_chan][ky*kx][chan_pad]  (K-major rows for the Q operand)

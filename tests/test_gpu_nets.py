@@ -392,3 +392,31 @@ def test_fc_chain_kernel_is_bit_identical_to_separate_layers(oracle, net, batch,
     for n in nodes:
         assert np.isfinite(a[n]).all() and np.array_equal(a[n], b[n]), (n, oracle.mrd(a[n], b[n]))
     assert np.array_equal(a2[nodes[-1]], a[nodes[-1]])
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp16"])
+@pytest.mark.parametrize("net,batch,in_sz,node", [("alexnet_ng_conv", 32, 227, "conv1"), ("alexnet_ng_conv", 3, 227, "conv1"), ("googlenet_conv", 5, 224, "conv1")])
+def test_input_planes_in_one_kernel_are_bit_identical(oracle, net, batch, in_sz, node, prec):
+    """The network input's max|x|, scale and row-merged fp16 planes from ONE kernel (absmax_pack_smallc_kernel: rows held in shared memory
+    across a grid-wide barrier) against the two-kernel path (fuse_input_pack=0): conv1 and the net's output bit-identical; one launch fewer;
+    repeated forwards with a different input (the kernel re-arms its cells; a stale maximum would change the scale)."""
+    import boda_b200 as bb
+    from boda_b200 import nets
+    txt, i, o = nets.NETS[net](batch)
+    params = nets.synth_params(txt)
+    x = nets.synth_input((batch, 3, in_sz, in_sz))
+    x2 = (0.25 * x[::-1]).copy()
+    res = []
+    for on in (1, 0):
+        fwd = bb.B200ConvFwd(txt, "(prec=%s,fuse_input_pack=%d)" % (prec, on))
+        for k, v in params.items():
+            fwd.set_param(k, v)
+        out = fwd.run_fwd({i: x}, [node, o])
+        l0 = fwd.launches()
+        out2 = fwd.run_fwd({i: x2}, [o])
+        l1 = fwd.launches()
+        out3 = fwd.run_fwd({i: x}, [o])
+        res.append((out, out2, out3, l1 - l0))
+    (a, a2, a3, la), (b, b2, b3, lb) = res
+    assert la == lb - 1, (la, lb)
+    assert np.array_equal(a[node], b[node]) and np.array_equal(a[o], b[o]) and np.array_equal(a2[o], b2[o]) and np.array_equal(a3[o], a[o])
