@@ -1610,19 +1610,14 @@ struct run_ctx_t {
       packed_t *out_pk = nullptr;
       if (want_planes) { out_pk = pool_out_planes(pp, vout, C, OH, OW, npl, bf16, in_cell); }
       int const row_groups = ceil_div(OH, b200::kLpRows), chunks = ceil_div(C, b200::kLpCC);
-      long long const n_units = (long long)row_groups * chunks * N;
-      size_t const smem = ((size_t)2 * (b200::kLpCC + 2 * b200::kLpHalo) * b200::lrn_pool_row_stride(W) + (size_t)b200::kLpCC * b200::kLpRows * OW) * 4;
-      if (smem > 200 * 1024 || n_units >= (1ll << 31)) { unsup_err("pool: map too wide for the fused LRN form"); }
-      // (bulk copies of whole 16-byte units: the last channel's run may be rounded up to the end of the tensor, never beyond it)
-      if ((C % 4) != 0 || (reinterpret_cast<uintptr_t>(fptr(vin)) & 15) != 0) { unsup_err("pool: the fused LRN form needs chan % 4 == 0 and a 16-byte aligned input"); }
+      size_t const smem = ((size_t)b200::kLpCC * (2 * b200::kLpRows + 1) * W + (size_t)b200::kLpCC * b200::kLpRows * OW) * 4;
+      if (smem > 200 * 1024 || N > 65535 || chunks > 65535) { unsup_err("pool: map too wide for the fused LRN form"); }
+      // (128 threads, 4 CTAs per SM: measured best of {512x2, 512x1, 256x4, 256x2, 128x4} on AlexNet's two maps, r02)
       static uint64_t attr_ = 0;
       if (first_use_on_device(attr_, rtc.device)) {
-        CU_CHK(cudaFuncSetAttribute(b200::lrn_maxpool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); prefer_max_smem(b200::lrn_maxpool_kernel);
+        CU_CHK(cudaFuncSetAttribute(b200::lrn_maxpool_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); prefer_max_smem(b200::lrn_maxpool_kernel<128, 4>);
       }
-      int per_sm = 1;
-      CU_CHK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b200::lrn_maxpool_kernel, b200::kLpThreads, smem));
-      int const grid = (int)std::min<long long>(n_units, (long long)im.num_sms * std::max(1, per_sm));
-      launch_k(b200::lrn_maxpool_kernel, dim3(grid), dim3(b200::kLpThreads), smem, fptr(vin), fptr(vout), C, H, W, OH, OW, alpha / 5.0f, -beta, kk, absmax_cell("out"), pp, row_groups, chunks, (int)n_units);
+      launch_k(b200::lrn_maxpool_kernel<128, 4>, dim3(row_groups, chunks, N), dim3(128), smem, fptr(vin), fptr(vout), C, H, W, OH, OW, alpha / 5.0f, -beta, kk, absmax_cell("out"), pp);
       launched();
       im.bump(vout);
       if (out_pk) { out_pk->src_gen = *vout.gen; out_pk->src_ptr = vout.buf->p; }

@@ -643,91 +643,53 @@ __global__ void lrn_kernel_generic(float const *__restrict__ in, float *__restri
 
 // ---- lrn + max-pool(3x3, stride 2) in one kernel (test/rtc/lrn.cucl:35-50 followed by test/rtc/pool.cucl:1-41) ---------------------------
 // AlexNet-ng norm1 -> pool1 and norm2 -> pool2 (GoogLeNet: norm2 -> pool2): the LRN output is read by nothing but the pool, and both kernels
-// are bandwidth kernels -- apart, the normalised map makes a 37 MB round trip through memory (write, then read) and costs a launch. Here a CTA owns
-// kLpRows pooled rows x all columns x kLpCC channels of one image: it stages the 2*kLpRows+1 input rows of kLpCC+4 channels (the LRN window
-// reaches two channels to either side) in shared memory, normalises them IN PLACE -- one thread per staged pixel, the window sum built from the
-// chunk's first channel on: exactly the arithmetic of lrn_kernel<5,16> (lrn_chunk), so the values are bit-identical -- pools them,
-// writes the pooled node and (optionally) the consumer convolution's NHWC 16-bit planes, in the consumer's layout. The LRN node itself is not
-// written (the whole-net driver recomputes it on demand with the plain lrn function when somebody asks for it).
-constexpr int kLpThreads = 256;
+// are bandwidth kernels -- apart, the normalised map makes a round trip through memory (37 MB written, then read, for norm1) and costs a launch.
+// A CTA owns kLpRows pooled rows x all columns x kLpCC channels of one image. Phase 1 is lrn_kernel's: one thread per pixel of the
+// 2*kLpRows+1 input rows loads its kLpCC+4 channel values straight from memory (consecutive threads = consecutive x: coalesced rows; the
+// window reaches two channels to either side), runs lrn_chunk<5, 16>'s arithmetic in registers -- so the values are bit-identical to the plain
+// kernel's -- and leaves the normalised values in shared memory. Phase 2 pools them and writes the pooled node and (optionally) the consumer
+// convolution's NHWC 16-bit planes, in the consumer's layout. The LRN node itself is not written (the whole-net driver recomputes it on demand
+// with the plain lrn function when somebody asks for it).
+// (Two earlier forms staged the inputs in shared memory -- per-element copies, then one bulk copy per channel into a persistent double-buffered
+// ring: 87 KB per CTA left two CTAs = 16 warps per SM for code that is a chain of dependent FMAs and exp2/log2, 1.3 TB/s on 37 MB and SLOWER
+// than the two separate kernels on GoogLeNet's 154 MB map, r02 ncu. This form needs 39 KB; small CTAs (128 threads, four per SM) measured best.
+// It is still bound by its instruction stream (LRN's FMA / exp2 / log2 chain plus the pooling loads), not by memory: on AlexNet's 37 / 24 MB maps
+// it saves the launch and the round trip (42 -> 31 us, 35 -> 25 us); on a 154 MB map it only equals the two kernels, so the whole-net driver
+// fuses maps up to 64 MB.)
 constexpr int kLpCC = 16, kLpRows = 4, kLpHalo = 2;  // channels per CTA (= the chunk of lrn_kernel<5, 16>), pooled rows per CTA, LRN half window (local_size 5)
-// staged floats per channel for a W-wide map: the run of 2*kLpRows+1 rows starts at any float offset of a 16-byte unit (55 x 55 planes), the bulk
-// copy fetches the enclosing 16-byte units
-__host__ __device__ constexpr int lrn_pool_row_stride(int W) { return (((2 * kLpRows + 1) * W + 3 + 3) & ~3); }
 
-// Persistent: a CTA walks units (row group, channel chunk, image) u = blockIdx.x, blockIdx.x + gridDim.x, ... with two staging buffers: one
-// thread issues the bulk copies of unit u + gridDim.x while everybody normalises and pools unit u (with one unit per CTA the co-resident CTAs
-// loaded together, then computed together: 1.3 TB/s, r02). Consecutive units are vertically adjacent row groups, then adjacent chunks: their
-// shared halo row / halo channels come from L2.
-__global__ void __launch_bounds__(kLpThreads, 2)
+template <int kT, int kB>
+__global__ void __launch_bounds__(kT, kB)
 lrn_maxpool_kernel(float const *__restrict__ in, float *__restrict__ out, int C, int H, int W, int OH, int OW, float alpha_over_ls, float neg_beta, float k,
-                   unsigned int *out_absmax, PoolPlanes pp, int n_rg, int n_chunks, int n_units) {
-  extern __shared__ __align__(128) float lp_smem[];
-  __shared__ __align__(8) uint64_t full_bar[2];
-  constexpr int kCh = kLpCC + 2 * kLpHalo;  // staged channels
-  int const rs = lrn_pool_row_stride(W);
-  float *stage = lp_smem + 2 * kCh * rs;  // pooled outputs [kLpCC][n_orows * OW] for the plane write
+                   unsigned int *out_absmax, PoolPlanes pp) {
+  extern __shared__ __align__(16) float lp_s[];
+  constexpr int kCh = kLpCC + 2 * kLpHalo;
+  int const oy0 = blockIdx.x * kLpRows, c0 = blockIdx.y * kLpCC;
+  long long const img = blockIdx.z;
+  int const n_orows = min(kLpRows, OH - oy0);
+  int const iy0 = oy0 * 2, n_irows = min(H - iy0, 2 * n_orows + 1);
+  int const npix = n_irows * W;        // rows iy0 .. iy0 + n_irows - 1 are one contiguous run of a channel plane
+  int const nstride = (2 * kLpRows + 1) * W;  // floats per normalised channel in shared memory
+  float *stage = lp_s + kLpCC * nstride;      // pooled outputs [kLpCC][n_orows * OW] for the plane write
   long long const HW = static_cast<long long>(H) * W;
-  int const hwm = static_cast<int>(HW & 3);
-  struct unit_t { int oy0, c0, n_orows, iy0, n_irows, npix, off0; long long img, g0; };
-  auto unit_of = [&](int u) {
-    unit_t q;
-    int const rg = u % n_rg, t = u / n_rg;
-    q.oy0 = rg * kLpRows;
-    q.c0 = (t % n_chunks) * kLpCC;
-    q.img = t / n_chunks;
-    q.n_orows = min(kLpRows, OH - q.oy0);
-    q.iy0 = q.oy0 * 2;
-    q.n_irows = min(H - q.iy0, 2 * q.n_orows + 1);
-    q.npix = q.n_irows * W;  // staged pixels per channel: rows iy0 .. iy0 + n_irows - 1 are one contiguous run of a channel plane
-    q.g0 = ((q.img * C + (q.c0 - kLpHalo)) * H + q.iy0) * static_cast<long long>(W);  // float index of staged channel 0's run (may lie outside [0, C))
-    q.off0 = static_cast<int>(q.g0 & 3);  // channel s's run starts off_s = (off0 + s * hwm) & 3 floats into its 16-byte aligned row
-    return q;
-  };
-  // one bulk copy per channel inside [0, C), issued by lane s of warp 0 (per-element copies left the first versions of this kernel
-  // instruction-issue bound: 115, then 64 SASS instructions per normalised value; one thread issuing all 20 put ~1.5k cycles of serial address
-  // arithmetic on every unit's critical path, ncu r02); channels outside read as zero below
-  auto fetch = [&](unit_t const &q, int b) {  // all of warp 0
-    int const s = threadIdx.x;
-    bool const mine = s < kCh && static_cast<unsigned>(q.c0 - kLpHalo + s) < static_cast<unsigned>(C);
-    int const off = (q.off0 + s * hwm) & 3;
-    uint32_t const bytes = mine ? static_cast<uint32_t>((off + q.npix + 3) & ~3) * 4u : 0u;
-    uint32_t const total = __reduce_add_sync(0xffffffffu, bytes);
-    if (s == 0) { mbar_expect_tx(&full_bar[b], total); }
-    __syncwarp();
-    if (mine) {
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(lp_smem + (b * kCh + s) * rs)),
-                   "l"(in + (q.g0 + s * HW - off)), "r"(bytes), "r"(smem_u32(&full_bar[b]))
-                   : "memory");
-    }
-  };
-  if (threadIdx.x == 0) { mbar_init(&full_bar[0], 1); mbar_init(&full_bar[1], 1); fence_barrier_init(); }
-  __syncthreads();
+  constexpr int nthreads = kT;
   pdl_prologue();
-  float amax = 0.0f;
-  float const sc = (pp.hi && pp.in_absmax) ? scale_from_absmax_bits(*pp.in_absmax) : 1.0f;
-  if (pp.hi && blockIdx.x == 0 && threadIdx.x == 0) { pp.scale2[0] = sc; pp.scale2[1] = 1.0f / sc; }
-  int u = blockIdx.x;
-  static_assert(kCh <= 32, "one lane per staged channel");
-  if (threadIdx.x < 32 && u < n_units) { fetch(unit_of(u), 0); }
-  for (int it = 0; u < n_units; u += gridDim.x, ++it) {
-  int const b = it & 1;
-  if (threadIdx.x < 32 && u + static_cast<int>(gridDim.x) < n_units) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // buffer b^1 was written in place (generic proxy) two units ago; everybody passed the barrier since
-    fetch(unit_of(u + gridDim.x), b ^ 1);
+  // ---- phase 1: normalise. lrn_chunk<5, 16>'s arithmetic: the window sum rebuilt at the chunk start, then the running update ----
+  // (a thread's next pixel is loaded while the current one is normalised: the loads are the long pole and a 128-thread CTA walks ~4 pixels per thread)
+  float const *src0 = in + ((img * C + (c0 - kLpHalo)) * H + iy0) * static_cast<long long>(W);  // only dereferenced for channels inside [0, C)
+  float nxt[kCh];
+#pragma unroll
+  for (int t = 0; t < kCh; ++t) {
+    nxt[t] = (static_cast<int>(threadIdx.x) < npix && static_cast<unsigned>(c0 - kLpHalo + t) < static_cast<unsigned>(C)) ? __ldg(src0 + threadIdx.x + t * HW) : 0.0f;
   }
-  unit_t const q = unit_of(u);
-  int const oy0 = q.oy0, c0 = q.c0, n_orows = q.n_orows, n_irows = q.n_irows, npix = q.npix, off0 = q.off0;
-  long long const img = q.img;
-  float *lp_s = lp_smem + b * kCh * rs;
-  mbar_wait(&full_bar[b], (it >> 1) & 1);
-  // ---- normalise in place: one thread per pixel, all of its kCh values in registers before the first store (the outputs land on staged channels
-  // 2 .. kLpCC + 1, inputs of the same thread only). lrn_chunk<5, 16>'s arithmetic: the window sum rebuilt at the start, then the running update ----
-  // (two pixels per thread interleaved, for ILP on the 40-FMA window-sum chain, and 16 warps per CTA were both tried: no gain, r02)
-  for (int p = threadIdx.x; p < npix; p += kLpThreads) {
+  for (int p = threadIdx.x; p < npix; p += nthreads) {
     float v[kCh];
 #pragma unroll
-    for (int t = 0; t < kCh; ++t) { v[t] = (static_cast<unsigned>(c0 - kLpHalo + t) < static_cast<unsigned>(C)) ? lp_s[t * rs + ((off0 + t * hwm) & 3) + p] : 0.0f; }
+    for (int t = 0; t < kCh; ++t) { v[t] = nxt[t]; }
+    if (p + nthreads < npix) {
+#pragma unroll
+      for (int t = 0; t < kCh; ++t) { nxt[t] = (static_cast<unsigned>(c0 - kLpHalo + t) < static_cast<unsigned>(C)) ? __ldg(src0 + p + nthreads + t * HW) : 0.0f; }
+    }
     float ls_sum = 0.0f;
 #pragma unroll
     for (int t = 0; t < kCh; ++t) {
@@ -735,51 +697,54 @@ lrn_maxpool_kernel(float const *__restrict__ in, float *__restrict__ out, int C,
       if (t >= 5) { ls_sum = __fmaf_rn(-v[t - 5], v[t - 5], ls_sum); }
       if (t >= 2 * kLpHalo) {
         float const scale_base = __fmaf_rn(ls_sum, alpha_over_ls, k);
-        lp_s[(t - kLpHalo) * rs + ((off0 + (t - kLpHalo) * hwm) & 3) + p] = v[t - kLpHalo] * lrn_pow_neg(scale_base, neg_beta);
+        lp_s[(t - 2 * kLpHalo) * nstride + p] = v[t - kLpHalo] * lrn_pow_neg(scale_base, neg_beta);
       }
     }
   }
   __syncthreads();
-  // ---- 3x3 / 2 max pooling (windows clipped at the map's edge, Caffe ceil rule) of the normalised channels c0 .. c0 + kLpCC - 1. A thread keeps
-  // ONE output pixel and walks the channels (the pixel's index arithmetic and edge tests happen once); kLpThreads / n_out thread groups share the channels ----
+  // ---- phase 2: 3x3 / 2 max pooling (windows clipped at the map's edge, Caffe ceil rule) of channels c0 .. c0 + kLpCC - 1. A thread keeps ONE
+  // output pixel and walks the channels (the pixel's index arithmetic and edge tests happen once); nthreads / n_out thread groups share the channels ----
+  float amax = 0.0f;
   int const n_out = n_orows * OW;
   int const n_ch = min(kLpCC, C - c0);
   {
-    int const n_grp = n_out <= kLpThreads ? kLpThreads / n_out : 1;
-    int const grp = n_out <= kLpThreads ? static_cast<int>(threadIdx.x) / n_out : 0;
+    int const n_grp = n_out <= nthreads ? nthreads / n_out : 1;
+    int const grp = n_out <= nthreads ? static_cast<int>(threadIdx.x) / n_out : 0;
     long long const ohw = static_cast<long long>(OH) * OW;
-    for (int rem = static_cast<int>(threadIdx.x) - grp * n_out; rem < n_out && grp < n_grp; rem += kLpThreads) {
+    for (int rem = static_cast<int>(threadIdx.x) - grp * n_out; rem < n_out && grp < n_grp; rem += nthreads) {
       int const oyl = (rem >= OW) + (rem >= 2 * OW) + (rem >= 3 * OW), ox = rem - oyl * OW;  // (kLpRows == 4)
-      int const pofs = (oyl * 2) * W + ox * 2;
       int const ny = min(3, n_irows - oyl * 2), nx = min(3, W - ox * 2);
-      float *op = out + ((img * C + c0) * OH + oy0) * static_cast<long long>(OW) + rem;
+      float *op = out + ((img * C + c0) * OH + oy0) * static_cast<long long>(OW) + rem + grp * ohw;
+      float const *pl = lp_s + grp * nstride + (oyl * 2) * W + ox * 2;
+      float *sp = stage + grp * n_out + rem;
       if (ny == 3 && nx == 3) {
+        float const *r1 = pl + W, *r2 = r1 + W;
 #pragma unroll 2
-        for (int ch = grp; ch < n_ch; ch += n_grp) {
-          float const *pl = lp_s + (kLpHalo + ch) * rs + ((off0 + (kLpHalo + ch) * hwm) & 3) + pofs;
-          float const *r1 = pl + W, *r2 = r1 + W;
+        for (int ch = grp; ch < n_ch; ch += n_grp, pl += n_grp * nstride, r1 += n_grp * nstride, r2 += n_grp * nstride, op += n_grp * ohw, sp += n_grp * n_out) {
           float const m = fmaxf(fmaxf(fmaxf(pl[0], pl[1]), fmaxf(pl[2], r1[0])), fmaxf(fmaxf(r1[1], r1[2]), fmaxf(r2[0], fmaxf(r2[1], r2[2]))));
-          op[ch * ohw] = m;
-          if (pp.hi) { stage[ch * n_out + rem] = m; }
+          *op = m;
+          if (pp.hi) { *sp = m; }
           amax = fmaxf(amax, fabsf(m));
         }
       } else {
-        for (int ch = grp; ch < n_ch; ch += n_grp) {
-          float const *pl = lp_s + (kLpHalo + ch) * rs + ((off0 + (kLpHalo + ch) * hwm) & 3) + pofs;
+        for (int ch = grp; ch < n_ch; ch += n_grp, pl += n_grp * nstride, op += n_grp * ohw, sp += n_grp * n_out) {
           float m = -FLT_MAX;
           for (int y = 0; y < ny; ++y) { for (int x = 0; x < nx; ++x) { m = fmaxf(m, pl[y * W + x]); } }
-          op[ch * ohw] = m;
-          if (pp.hi) { stage[ch * n_out + rem] = m; }
+          *op = m;
+          if (pp.hi) { *sp = m; }
           amax = fmaxf(amax, fabsf(m));
         }
       }
     }
   }
-  __syncthreads();  // everybody is done with buffer b; the staged outputs are complete
+  if (out_absmax) { publish_absmax_warp(amax, out_absmax); }
   if (pp.hi) {  // the consumer's planes: 16-byte runs of 8 channels per pixel (host: C a multiple of 8; fp16 planes: the scale from max|in|, the LRN scale factor is <= 1 for k >= 1)
+    float const sc = pp.in_absmax ? scale_from_absmax_bits(*pp.in_absmax) : 1.0f;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) { pp.scale2[0] = sc; pp.scale2[1] = 1.0f / sc; }
+    __syncthreads();
     int const groups = n_ch >> 3;
     static_assert(kLpCC == 16 && kLpRows == 4, "index arithmetic below");
-    for (int idx = threadIdx.x; idx < n_out * 2; idx += kLpThreads) {
+    for (int idx = threadIdx.x; idx < n_out * 2; idx += nthreads) {
       int const pix = idx >> 1, g = idx & 1;
       if (g >= groups) { continue; }
       uint32_t wh[4], wl[4];
@@ -804,10 +769,7 @@ lrn_maxpool_kernel(float const *__restrict__ in, float *__restrict__ out, int C,
       *reinterpret_cast<uint4 *>(pp.hi + o16) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
       if (pp.lo) { *reinterpret_cast<uint4 *>(pp.lo + o16) = make_uint4(wl[0], wl[1], wl[2], wl[3]); }
     }
-    __syncthreads();  // ... before the next unit overwrites the stage
   }
-  }  // units
-  if (out_absmax) { publish_absmax_warp(amax, out_absmax); }
 }
 
 // ---- softmax over chan (test/rtc/softmax.cucl:6-21; running max starts at 0.0f) -------------------------------

@@ -47,7 +47,7 @@ def test_googlenet_concat_inputs_are_written_in_place(bb):
     txt, i, o = nets.googlenet_conv(64)
     desc = bb.pipe_describe(txt)["nodes"]
     plan = bb.fwd_plan(txt, "(prec=bf16)")
-    assert _kinds(plan) == {"conv": 64, "pool": 16, "lrn": 1} and len(plan["alias"]) == 36   # 9 inception Concats x 4 inputs, no copy kernels
+    assert _kinds(plan) == {"conv": 64, "pool": 16, "lrn": 2} and len(plan["alias"]) == 36   # 9 inception Concats x 4 inputs, no copy kernels
     chans = lambda n: dict(desc[n])["chan"]
     per_cat = {}
     for node, (cat, ocix) in plan["alias"].items():
@@ -208,6 +208,7 @@ def test_lrn_in_front_of_a_max_pool_is_planned_into_the_pool(bb):
     plan = bb.fwd_plan(txt, "")
     assert plan["lrnpool"] == {"pool2": ("norm2", "conv2")}
     assert [a["out"] for f, a in plan["calls"] if f.startswith("lrn__")] == ["norm1"]
+    assert bb.fwd_plan(nets.googlenet_conv(64)[0], "(prec=bf16)")["lrnpool"] == {}
 
 
 def test_inner_product_chains_are_planned_as_one_call(bb):
