@@ -483,7 +483,12 @@ def bench_one(args, rank, local_rank, world, dist, sh_nccl, is_main):
     peaks = measured_peaks()
     achieved_tf = conv_flops / (conv_kernel_ms * 1e-3) / 1e12 if conv_kernel_ms > 0 else 0.0
     peak_tf = peaks["bf16_tflops"]
-    fc_bytes = 4.0 * sum(per_op.get(_tag(r[0]), (0, 0))[0] for r in fc_rows)
+    # (an fc_chain call runs several inner-product layers: its bytes are those of every layer in the chain)
+    chains = {c[0]: c for c in bb.fwd_plan(txt, "(prec=%s%s)" % (args.prec, ("," + extra) if extra else "")).get("fcchain", [])}
+    def _fc_tags(func):
+        return chains.get(_tag(func), [_tag(func)]) if func.startswith("fc_chain__") else [_tag(func)]
+    fc_bytes = 4.0 * sum(per_op.get(t, (0, 0))[0] for r in fc_rows for t in _fc_tags(r[0]))
+    fc_chained = any(r[0].startswith("fc_chain__") for r in fc_rows)
     fc_ms = sum(r[2] for r in fc_rows)
     all_flops, all_ms = sum(r[3] for r in conv_rows), sum(r[2] for r in conv_rows)
 
@@ -514,7 +519,9 @@ def bench_one(args, rank, local_rank, world, dist, sh_nccl, is_main):
                          "note": "achieved = algorithmic conv FLOPs / summed CUDA-event launch durations of the dominant kernel's launches; the fp32-parity mode issues "
                                  "3 fp16 MMAs per product (mma_passes), so tensor_work_frac = achieved x mma_passes / peak is the share of the tensor pipe's peak actually kept busy",
                          "all_contraction_launches": {"launches": len(conv_rows), "achieved": all_flops / (all_ms * 1e-3) / 1e12 if all_ms > 0 else None, "unit": "TFLOP/s"},
-                         "fc_shaped_layers": {"bound": "hbm", "launches": len(fc_rows), "kernel": "b200::igemm_umma_kernel (weights as the 128-row operand, split-K)",
+                         "fc_shaped_layers": {"bound": "hbm", "launches": len(fc_rows),
+                                              "kernel": ("b200::fc_chain_kernel (all inner-product layers of a chain in one persistent launch; weights as the 128-row operand, split-K, "
+                                                         "grid barriers between the layers)" if fc_chained else "b200::igemm_umma_kernel (weights as the 128-row operand, split-K)"),
                                               "achieved": fc_bytes / (fc_ms * 1e-3) / 1e9 if fc_ms > 0 else None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                               "frac": (fc_bytes / (fc_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if fc_ms > 0 else None}},
             "clocks": sampler.summary(),
