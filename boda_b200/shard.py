@@ -17,12 +17,22 @@ import numpy as np
 
 
 def shard_range(global_batch: int, world: int, rank: int) -> Tuple[int, int]:
-    """Contiguous split of the `img` dim: [begin, end) for `rank`; trailing ranks may get fewer (or zero) images."""
+    """Contiguous split of the `img` dim: [begin, end) for `rank`; trailing ranks may get fewer (or zero) images.
+    The gathers below (`gather_logits`, `GatherPipeline`, `b200_shard_gather_*`) need EQUAL shards: use `equal_shard_size` to check a global
+    batch before building the per-rank forwards (bench.py is weak-scaling: every rank runs the same per-GPU batch)."""
     if world < 1 or not (0 <= rank < world) or global_batch < 0:
         raise ValueError("shard_range: bad world/rank/batch %r/%r/%r" % (world, rank, global_batch))
     per = -(-global_batch // world)
     b = min(global_batch, rank * per)
     return b, min(global_batch, b + per)
+
+
+def equal_shard_size(global_batch: int, world: int) -> int:
+    """Images per rank when `global_batch` splits evenly over `world` ranks; raises otherwise (an uneven split would make the fixed-size
+    all-gather hang or mis-order images -- pad the batch to a multiple of `world` and slice the gathered result with `shard_range`)."""
+    if world < 1 or global_batch < 0 or global_batch % world:
+        raise ValueError("global batch %d does not split evenly over %d ranks: pad it to %d" % (global_batch, world, -(-global_batch // max(world, 1)) * max(world, 1)))
+    return global_batch // world
 
 
 def param_layout(shapes: Dict[str, Tuple[int, ...]]) -> List[Tuple[str, int, int, Tuple[int, ...]]]:
@@ -64,6 +74,8 @@ def gather_logits(dist, local, out=None):
     world = dist.get_world_size()
     if out is None:
         out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    if out.shape[0] != world * local.shape[0]:
+        raise ValueError("gather_logits: output holds %d rows, %d ranks x %d local rows expected (unequal shards? see equal_shard_size)" % (out.shape[0], world, local.shape[0]))
     dist.all_gather_into_tensor(out, local.contiguous())
     return out
 

@@ -102,3 +102,12 @@ def test_two_rank_broadcast_shard_gather_matches_unsharded_forward(oracle):
     assert res[0]["match_full"]
     assert all(r["ok_t"] for r in res)
     assert all(r["pipe_ok"] for r in res)
+
+
+def test_equal_shard_size_rejects_uneven_batches():
+    """The fixed-size gathers need equal shards on every rank: the check that guards them names the padded batch."""
+    from boda_b200 import shard
+    assert shard.equal_shard_size(256, 8) == 32 and shard.equal_shard_size(0, 4) == 0
+    with pytest.raises(ValueError, match="pad it to 36"):
+        shard.equal_shard_size(33, 4)
+    assert [shard.shard_range(33, 4, r) for r in range(4)] == [(0, 9), (9, 18), (18, 27), (27, 33)]
