@@ -331,6 +331,7 @@ bool b200_compute_t::set_option(string const &k, string const &v) {
   else if (k == "use_clusters") { use_clusters = std::stoi(v); }
   else if (k == "use_2cta") { use_2cta = std::stoi(v); }
   else if (k == "debug_flags") { debug_flags = std::stoi(v); }
+  else if (k == "input_pack_ctas_per_sm") { input_pack_ctas_per_sm = std::max(1, std::stoi(v)); }
   else if (k == "fuse_input_pack") { fuse_input_pack = std::stoi(v); }
   else if (k == "fc_l2_ahead") { fc_l2_ahead = std::stoi(v); }
   else if (k == "fc_l2_next") { fc_l2_next = std::stoi(v); }
@@ -817,17 +818,21 @@ struct run_ctx_t {
       // network input (few channels, row-merged layout): max|x|, the scale and the planes in ONE kernel -- every CTA keeps its rows in shared
       // memory across a grid-wide barrier, so the input is read once and the step has a launch fewer (absmax_pack_smallc_kernel)
       int const H = Cc / smallc_W, Wp = (int)(dst_chi_stride / Rpad), px_off = (int)(dst_base / Rpad);
-      for (int upi = std::min(H, 64); upi >= 1; --upi) {  // row groups per image: as many as can be resident at once
+      // row groups per image: the fewest that put input_pack_ctas_per_sm CTAs on every SM (every CTA arrives on ONE counter: with 1056 CTAs the
+      // barrier's serialised atomics were a quarter of the kernel), more only when the rows would not fit shared memory
+      int upi_first = 1;
+      while (upi_first < H && (long long)B * upi_first < (long long)im.num_sms * rtc.input_pack_ctas_per_sm) { ++upi_first; }
+      for (int upi = upi_first; upi <= H; ++upi) {
         int const rows = ceil_div(H, upi);
         if (ceil_div(H, rows) != upi) { continue; }
         size_t const smem = (size_t)R * b200::smallc_row_stride(rows, smallc_W) * 4;
-        if (smem > 200 * 1024) { break; }
+        if (smem > 200 * 1024) { continue; }
         auto kern = Rpad == 4 ? b200::absmax_pack_smallc_kernel<4> : b200::absmax_pack_smallc_kernel<8>;
         static uint64_t attr4_ = 0, attr8_ = 0;
         if (first_use_on_device(Rpad == 4 ? attr4_ : attr8_, rtc.device)) { CU_CHK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); prefer_max_smem(kern); }
         int per_sm = 0;
         CU_CHK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
-        if ((long long)B * upi > (long long)im.num_sms * per_sm) { continue; }
+        if ((long long)B * upi > (long long)im.num_sms * per_sm) { break; }  // (more groups only shrink per_sm's slack further)
         launch_k(kern, dim3(B * upi), dim3(256), smem, fptr(src), hi0, lo0, static_cast<float *>(pk.scale2->p), static_cast<unsigned int *>(pk.absmax_bits->p), R, H, smallc_W, Wp, px_off, rows, upi,
                  (long long)B * R * Cc);
         launched();

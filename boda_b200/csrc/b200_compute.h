@@ -65,6 +65,7 @@ struct b200_compute_t {
   b200_prec_t prec = B200_PREC_FP32_SPLIT;
   int fc_l2_ahead = 0;      // fc_chain kernel: the first layer's filter tiles are requested into L2 this many k-blocks ahead of the shared-memory ring (0 = off; measured: slower, r02)
   int fc_l2_next = 0;       // fc_chain kernel: request the next layer's filter tiles into L2 while the current layer drains and reduces (measured: no net gain, r02)
+  int input_pack_ctas_per_sm = 2;  // absmax_pack_smallc_kernel: CTAs per SM the grid is sized for
   int fuse_input_pack = 1;  // fp32-parity / fp16 modes, few-channel network inputs: max|x|, scale and the row-merged planes in one kernel (absmax_pack_smallc_kernel)
   int debug_flags = 0;      // timing experiments on the 1-CTA kernel: 1 = skip TMA loads, 2 = skip MMA issue (results are garbage)
   int use_2cta = 1;         // CTA pairs: one tcgen05.mma.cta_group::2 per 256 x BN tile (igemm2.cuh)
