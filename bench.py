@@ -585,7 +585,7 @@ def main():
     if bb.device_count() < 1:
         raise RuntimeError("bench.py needs a CUDA device: the B200 back-end has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None  # before any pinned allocation
+    numa_node = None if os.environ.get("B200_BENCH_NO_NUMA_BIND") else bind_to_gpu_numa_node(local_rank)  # before any pinned allocation
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
