@@ -1617,12 +1617,12 @@ struct run_ctx_t {
       int const row_groups = ceil_div(OH, b200::kLpRows), chunks = ceil_div(C, b200::kLpCC);
       size_t const smem = ((size_t)b200::kLpCC * (2 * b200::kLpRows + 1) * W + (size_t)b200::kLpCC * b200::kLpRows * OW) * 4;
       if (smem > 200 * 1024 || N > 65535 || chunks > 65535) { unsup_err("pool: map too wide for the fused LRN form"); }
-      // (128 threads, 4 CTAs per SM: measured best of {512x2, 512x1, 256x4, 256x2, 128x4} on AlexNet's two maps, r02)
+      // (128 threads at 64 registers, up to six CTAs per SM: measured best of {512x2, 512x1, 256x4, 256x2, 128x4, 128x6, 128x8, 64x8, 64x12}, r02)
       static uint64_t attr_ = 0;
       if (first_use_on_device(attr_, rtc.device)) {
-        CU_CHK(cudaFuncSetAttribute(b200::lrn_maxpool_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); prefer_max_smem(b200::lrn_maxpool_kernel<128, 4>);
+        CU_CHK(cudaFuncSetAttribute(b200::lrn_maxpool_kernel<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); prefer_max_smem(b200::lrn_maxpool_kernel<128, 6>);
       }
-      launch_k(b200::lrn_maxpool_kernel<128, 4>, dim3(row_groups, chunks, N), dim3(128), smem, fptr(vin), fptr(vout), C, H, W, OH, OW, alpha / 5.0f, -beta, kk, absmax_cell("out"), pp);
+      launch_k(b200::lrn_maxpool_kernel<128, 6>, dim3(row_groups, chunks, N), dim3(128), smem, fptr(vin), fptr(vout), C, H, W, OH, OW, alpha / 5.0f, -beta, kk, absmax_cell("out"), pp);
       launched();
       im.bump(vout);
       if (out_pk) { out_pk->src_gen = *vout.gen; out_pk->src_ptr = vout.buf->p; }
