@@ -382,6 +382,14 @@ def bench_one(args, rank, local_rank, world, dist, sh_nccl, is_main):
         gathered = torch.as_tensor(_DevView(sh.gather_ptr(step), (world * B, n_logits)), device="cuda")
         if not torch.equal(ref, gathered):
             raise RuntimeError("peer-memory logits gather disagrees with the NCCL all-gather of the same data")
+        # the per-step form of the timed loop (push step i + wait for step i-1 in one launch), checked the same way
+        fwd.enqueue()
+        step2 = sh.gather_push_wait(fwd.node_device_ptr(out_node), step, st_ptr)
+        sh.gather_wait(step2, st_ptr)
+        torch.cuda.synchronize()
+        gathered2 = torch.as_tensor(_DevView(sh.gather_ptr(step2), (world * B, n_logits)), device="cuda")
+        if not torch.equal(ref, gathered2):
+            raise RuntimeError("peer-memory logits gather (push + wait in one launch) disagrees with the NCCL all-gather of the same data")
     barrier()
 
     sampler.start()
@@ -421,8 +429,8 @@ def bench_one(args, rank, local_rank, world, dist, sh_nccl, is_main):
                 step = None
                 if i < args.steps:
                     fwd.enqueue()
-                    step = sh.gather_push(out_ptr, st_ptr)
-                if prev_step is not None:
+                    step = sh.gather_push_wait(out_ptr, prev_step or 0, st_ptr)  # one launch: push step i, wait for step i-1
+                elif prev_step is not None:
                     sh.gather_wait(prev_step, st_ptr)
                 prev_step = step
                 ev1.record()

@@ -96,6 +96,7 @@ _SIGS = {
     "b200_shard_gather_import": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
     "b200_shard_gather_push": (_c.c_int64, [_c.c_void_p, _c.c_void_p, _c.c_void_p]),
     "b200_shard_gather_wait": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_void_p]),
+    "b200_shard_gather_push_wait": (_c.c_int64, [_c.c_void_p, _c.c_void_p, _c.c_uint32, _c.c_void_p]),
     "b200_shard_gather_ptr": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.POINTER(_c.c_void_p)]),
     "b200_shard_all_gather_nccl": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_uint64, _c.c_void_p]),
     "b200_shard_launches": (_c.c_uint64, [_c.c_void_p]),
@@ -551,6 +552,10 @@ class B200Shard:
 
     def gather_push(self, dev_src: int, stream: int) -> int:
         return _chk(lib().b200_shard_gather_push(self._h, _c.c_void_p(dev_src), _c.c_void_p(stream)))
+
+    def gather_push_wait(self, dev_src: int, wait_step: int, stream: int) -> int:
+        """Push this step's logits and wait for `wait_step` (0 = none) in ONE kernel launch; returns the step it published."""
+        return _chk(lib().b200_shard_gather_push_wait(self._h, _c.c_void_p(dev_src), int(wait_step), _c.c_void_p(stream)))
 
     def gather_wait(self, step: int, stream: int):
         _chk(lib().b200_shard_gather_wait(self._h, step, _c.c_void_p(stream)))

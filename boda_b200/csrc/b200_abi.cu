@@ -337,6 +337,11 @@ B200_API int64_t b200_shard_gather_push(b200_shard *s, const void *dev_src, void
   int const rc = guarded([&] { step = s->sh->gather_push(dev_src, stream); return 0; });
   return rc < 0 ? rc : step;
 }
+B200_API int64_t b200_shard_gather_push_wait(b200_shard *s, const void *dev_src, uint32_t wait_step, void *stream) {
+  int64_t step = 0;
+  int const rc = guarded([&] { step = s->sh->gather_push_wait(dev_src, wait_step, stream); return 0; });
+  return rc < 0 ? rc : step;
+}
 B200_API int b200_shard_gather_wait(b200_shard *s, uint32_t step, void *stream) { return guarded([&] { s->sh->gather_wait(step, stream); return 0; }); }
 B200_API int b200_shard_gather_ptr(b200_shard *s, uint32_t step, void **dev_ptr_out) { return guarded([&] { *dev_ptr_out = s->sh->gather_ptr(step); if (!*dev_ptr_out) { rt_err("b200_shard: no gather buffer yet"); } return 0; }); }
 B200_API uint64_t b200_shard_launches(b200_shard *s) { return s->sh->n_launches; }

@@ -96,6 +96,44 @@ __global__ void shard_wait_kernel(unsigned char *local_base, int world, unsigned
   }
 }
 
+// Both in one launch (the per-step form): CTAs 0 .. world-1 push this step's logits as shard_push_kernel does, CTA `world` waits for
+// `wait_step` as shard_wait_kernel does (wait_step == 0: nothing to wait for). Launched with programmatic stream serialization: the launch
+// and the wait overlap the tail of the forward; the pushing CTAs execute griddepcontrol.wait before they read the logits.
+__global__ void __launch_bounds__(1024) shard_push_wait_kernel(peer_ptrs_t peers, unsigned char const *__restrict__ src, uint64_t bytes, int rank, int world, unsigned int step,
+                                                              unsigned char *local_base, unsigned int wait_step) {
+  if (static_cast<int>(blockIdx.x) == world) {
+    if (wait_step != 0u && static_cast<int>(threadIdx.x) < world) {
+      unsigned int const *flag = reinterpret_cast<unsigned int const *>(local_base) + threadIdx.x;
+      unsigned int v = 0, spins = 0;
+      while (true) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (static_cast<int>(v - wait_step) >= 0) { break; }
+        __nanosleep(100);
+        if (++spins > (1u << 25)) { printf("b200_shard: rank %d never published step %u (have %u)\n", (int)threadIdx.x, wait_step, v); __trap(); }
+      }
+    }
+    return;
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // the forward that wrote `src` is complete and visible
+  unsigned char *dst_base = peers.base[blockIdx.x];
+  uint4 const *s = reinterpret_cast<uint4 const *>(src);
+  uint4 *d = reinterpret_cast<uint4 *>(dst_base + kFlagBytes + (static_cast<uint64_t>(step & 1u) * world + static_cast<uint64_t>(rank)) * bytes);
+  uint64_t const n = bytes >> 4;
+  for (uint64_t i = threadIdx.x; i < n; i += 8 * 1024) {  // 1024 threads x eight 128-bit loads in flight: 128 KB of logits in one round trip
+    uint4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { if (i + k * 1024 < n) { v[k] = s[i + k * 1024]; } }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { if (i + k * 1024 < n) { d[i + k * 1024] = v[k]; } }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int *flag = reinterpret_cast<unsigned int *>(dst_base) + rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(step) : "memory");
+  }
+}
+
 }  // namespace
 
 struct b200_shard_impl_t {
@@ -190,6 +228,23 @@ void b200_shard_t::gather_wait(uint32_t step, void *stream) {
   shard_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(impl->local, world, step);
   SH_CHK(cudaGetLastError());
   ++n_launches;
+}
+uint32_t b200_shard_t::gather_push_wait(void const *dev_src, uint32_t wait_step, void *stream) {
+  if (!impl->imported) { rt_err("b200_shard: gather_push_wait before gather_import"); }
+  SH_CHK(cudaSetDevice(device));
+  ++impl->step;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(world + 1);
+  cfg.blockDim = dim3(1024);
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SH_CHK(cudaLaunchKernelEx(&cfg, shard_push_wait_kernel, impl->peers, static_cast<unsigned char const *>(dev_src), impl->bytes_per_rank, rank, world, impl->step, impl->local, wait_step));
+  ++n_launches;
+  return impl->step;
 }
 void *b200_shard_t::gather_ptr(uint32_t step) const { return impl->local ? impl->local + kFlagBytes + static_cast<uint64_t>(step & 1u) * world * impl->bytes_per_rank : nullptr; }
 uint32_t b200_shard_t::step() const { return impl->step; }

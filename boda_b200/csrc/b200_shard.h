@@ -25,6 +25,7 @@ struct b200_shard_t {
   void gather_import(void const *ipc_handles_world_x_64);
   uint32_t gather_push(void const *dev_src, void *stream);  // returns the step number it published
   void gather_wait(uint32_t step, void *stream);
+  uint32_t gather_push_wait(void const *dev_src, uint32_t wait_step, void *stream);  // both in ONE launch (wait_step 0: push only); returns the step it published
   void *gather_ptr(uint32_t step) const;  // device pointer of the local [world][bytes_per_rank] result of `step` (two halves, by step parity)
   uint32_t step() const;
 

@@ -170,6 +170,9 @@ int b200_shard_gather_export(b200_shard *s, uint64_t bytes_per_rank, void *ipc_h
 int b200_shard_gather_import(b200_shard *s, const void *ipc_handles_world_x_64);
 int64_t b200_shard_gather_push(b200_shard *s, const void *dev_src, void *stream);
 int b200_shard_gather_wait(b200_shard *s, uint32_t step, void *stream);
+/* the per-step form: push this step's logits AND wait for `wait_step` (0 = none) in one launch (programmatic dependent launch: the launch and the
+ * wait overlap the forward's tail); returns the published step */
+int64_t b200_shard_gather_push_wait(b200_shard *s, const void *dev_src, uint32_t wait_step, void *stream);
 int b200_shard_gather_ptr(b200_shard *s, uint32_t step, void **dev_ptr_out); /* device pointer of the local [world][bytes_per_rank] result of `step` */
 int b200_shard_all_gather_nccl(b200_shard *s, const void *dev_src, void *dev_dst, uint64_t bytes_per_rank, void *stream);
 uint64_t b200_shard_launches(b200_shard *s);                          /* kernels this module has launched so far */
