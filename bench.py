@@ -34,6 +34,7 @@ import numpy as np  # noqa: E402
 METRIC = "alexnet_ng_conv_fwd_images_per_sec"
 UNIT = "images/s"
 PER_GPU_BATCH = 32
+GATHER_FORM = ["b200_shard_gather_push_wait: one launch per step"]  # how the multi-GPU timed loop gathered the logits (set by bench_one)
 L2_FLUSH_BYTES = 256 << 20
 
 
@@ -417,6 +418,31 @@ def bench_one(args, rank, local_rank, world, dist, sh_nccl, is_main):
         s_fwd = torch.cuda.ExternalStream(fwd.stream_ptr(), device=torch.device("cuda", local_rank))
         st_ptr = fwd.stream_ptr()
         out_ptr = fwd.node_device_ptr(out_node)
+        # Nets that end in an inner-product chain (AlexNet: fc8) gather INSIDE the chain's kernel: its last layer's CTAs store the logits into every
+        # rank's buffer, the last CTA publishes the step and waits for the previous one (b200_fwd_attach_gather) -- no gather launch, and part of
+        # the captured graph. Checked against the NCCL all-gather before it is timed. B200_BENCH_GATHER=peer_launch keeps the separate launch.
+        fused = os.environ.get("B200_BENCH_GATHER", "peer") == "peer" and fwd.attach_gather(sh, out_node)
+        fused_all = shard.max_over_ranks(dist, 0.0 if fused else 1.0, device="cuda") == 0.0  # every rank or none
+        if fused and not fused_all:
+            fwd.attach_gather(None, out_node)
+        fused = fused and fused_all
+        GATHER_FORM[0] = ("inside the fc_chain kernel of the forward: b200_fwd_attach_gather, no gather launch" if fused
+                          else "b200_shard_gather_push_wait: one launch per step")
+        if fused:
+            with torch.cuda.stream(s_fwd):
+                for _ in range(3):  # warm-up forward, capture, one replay: all ranks the same count
+                    fwd.enqueue()
+                s_fwd.synchronize()
+            step_f = sh.step_from_device()
+            sh.gather_wait(step_f, st_ptr)
+            torch.cuda.synchronize()
+            barrier()
+            dist.all_gather_into_tensor(ref, logits_dev.contiguous())
+            torch.cuda.synchronize()
+            gathered_f = torch.as_tensor(_DevView(sh.gather_ptr(step_f), (world * B, n_logits)), device="cuda")
+            if not torch.equal(ref, gathered_f):
+                raise RuntimeError("in-kernel logits gather (fc_chain) disagrees with the NCCL all-gather of the same data")
+            barrier()
         windows = []
         sh_launches0 = sh.launches()
         torch.cuda.synchronize()
@@ -427,17 +453,33 @@ def bench_one(args, rank, local_rank, world, dist, sh_nccl, is_main):
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
                 step = None
-                if i < args.steps:
+                if fused:
+                    if i < args.steps:
+                        fwd.enqueue()  # forward i + push of its logits + wait for step i-1, one graph
+                elif i < args.steps:
                     fwd.enqueue()
-                    step = sh.gather_push_wait(out_ptr, prev_step or 0, st_ptr)  # one launch: push step i, wait for step i-1
+                    if os.environ.get("B200_BENCH_GATHER") != "none":  # ("none": experiment -- the same loop without any gather)
+                        step = sh.gather_push_wait(out_ptr, prev_step or 0, st_ptr)  # one launch: push step i, wait for step i-1
                 elif prev_step is not None:
                     sh.gather_wait(prev_step, st_ptr)
                 prev_step = step
                 ev1.record()
                 windows.append((ev0, ev1))
             s_fwd.synchronize()
+            if fused:  # the last step's gather completes with an explicit wait (outside the windows' forwards, inside the timed sum)
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                last = sh.step_from_device()
+                ev0.record()
+                sh.gather_wait(last, st_ptr)
+                ev1.record()
+                windows.append((ev0, ev1))
+                s_fwd.synchronize()
         dev_ms = float(sum(a.elapsed_time(b) for a, b in windows))
         shard_launches = sh.launches() - sh_launches0
+        if fused:
+            fwd.attach_gather(None, out_node)  # the e2e and profile passes below run the plain forward ...
+            fwd.run_timed(3, 0)                # ... whose graph is captured again here, outside every timed region
+            torch.cuda.synchronize()
     barrier()
     launches = fwd.launches() - launches0 + (shard_launches if world > 1 and os.environ.get("B200_BENCH_GATHER", "peer") != "nccl" else 0)
     if dist:
@@ -510,7 +552,7 @@ def bench_one(args, rank, local_rank, world, dist, sh_nccl, is_main):
             "dtype": {"fp32": "f32 (fp16 hi/lo split, 3 tcgen05.mma per k-step, fp32 accumulate)", "fp16": "f16", "bf16": "bf16"}[args.prec], "data": "synthetic",
             "config": {"workload": "nets/%s fwd, batch=%d per GPU, %s, %dx%d%s" % (args.net, B, args.prec, NET_IN_SZ, NET_IN_SZ, " (BASELINE configs[1])" if (args.net, B, args.prec) == ("alexnet_ng_conv", 32, "fp32") else ""), "global_batch": global_batch,
                        "parallelism": ("batch-shard x%d, one NCCL broadcast of the weights at init (device-resident) + per-step logits gather into every rank's peer-mapped buffer "
-                                       "over NVLink (b200_shard_gather_push / _wait, awaited one step late)" % world) if world > 1 else "single GPU",
+                                       "over NVLink (%s, awaited one step late)" % (world, GATHER_FORM[0])) if world > 1 else "single GPU",
                        "l2": "256 MiB scratch buffer overwritten before every timed step (outside the events)", "cuda_graph": True},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": in_elems * 4, "d2h_bytes_per_step": out_elems * 4, "ms_per_step": 1e3 * e2e_s / args.steps,
                     "api": "b200_fwd_submit / b200_fwd_wait (pipelined run_fwd, depth 2: H2D of batch i+1 overlaps the forward of batch i)",

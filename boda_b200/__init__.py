@@ -97,6 +97,8 @@ _SIGS = {
     "b200_shard_gather_push": (_c.c_int64, [_c.c_void_p, _c.c_void_p, _c.c_void_p]),
     "b200_shard_gather_wait": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_void_p]),
     "b200_shard_gather_push_wait": (_c.c_int64, [_c.c_void_p, _c.c_void_p, _c.c_uint32, _c.c_void_p]),
+    "b200_fwd_attach_gather": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_char_p]),
+    "b200_shard_step_from_device": (_c.c_int64, [_c.c_void_p]),
     "b200_shard_gather_ptr": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.POINTER(_c.c_void_p)]),
     "b200_shard_all_gather_nccl": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_uint64, _c.c_void_p]),
     "b200_shard_launches": (_c.c_uint64, [_c.c_void_p]),
@@ -417,6 +419,11 @@ class B200ConvFwd:
         """Parameter upload from a device buffer (a slice of the flat buffer the weights were broadcast in): no host round trip."""
         _chk(lib().b200_fwd_set_param_device(self._h, _b(name), _c.c_void_p(dev_ptr), n_elems))
 
+    def attach_gather(self, shard, node: str) -> bool:
+        """Multi-GPU: let the forward's last kernel (an fc_chain ending in `node`) gather the logits into every rank's buffer itself
+        (b200_fwd_attach_gather). False: this net does not end that way -- keep calling B200Shard.gather_push_wait. shard=None detaches."""
+        return bool(_chk(lib().b200_fwd_attach_gather(self._h, shard._h if shard is not None else None, _b(node))))
+
     def run_fwd(self, to_set: Dict[str, np.ndarray], to_get: Sequence[str], out_bufs: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
         """has_conv_fwd_t::run_fwd(to_set_vns, fwd, to_get_vns): host fp32 NCHW in, host out, synchronous."""
         sn = list(to_set)
@@ -552,6 +559,10 @@ class B200Shard:
 
     def gather_push(self, dev_src: int, stream: int) -> int:
         return _chk(lib().b200_shard_gather_push(self._h, _c.c_void_p(dev_src), _c.c_void_p(stream)))
+
+    def step_from_device(self) -> int:
+        """The step the last fused forward (B200ConvFwd.attach_gather) published; re-synchronises the host-side counter."""
+        return _chk(lib().b200_shard_step_from_device(self._h))
 
     def gather_push_wait(self, dev_src: int, wait_step: int, stream: int) -> int:
         """Push this step's logits and wait for `wait_step` (0 = none) in ONE kernel launch; returns the step it published."""

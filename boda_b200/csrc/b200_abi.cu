@@ -308,6 +308,19 @@ B200_API int b200_fwd_run_timed(b200_fwd *f, int iters, uint64_t l2_flush_bytes,
     return 0;
   });
 }
+B200_API int b200_fwd_attach_gather(b200_fwd *f, b200_shard *s, const char *node_name) {
+  return guarded_dev(f, [&] {
+    if (!s) { f->fwd->attach_gather(string(), nullptr); return 0; }
+    b200_gather_desc_t d;
+    s->sh->gather_desc(d);
+    return f->fwd->attach_gather(node_name, &d) ? 1 : 0;
+  });
+}
+B200_API int64_t b200_shard_step_from_device(b200_shard *s) {
+  int64_t step = 0;
+  int const rc = guarded([&] { step = s->sh->step_from_device(); return 0; });
+  return rc < 0 ? rc : step;
+}
 B200_API int b200_fwd_enqueue(b200_fwd *f) { return guarded_dev(f, [&] { f->fwd->enqueue_fwd(); return 0; }); }
 B200_API int b200_fwd_flush_l2(b200_fwd *f, uint64_t bytes) { return guarded_dev(f, [&] { f->fwd->flush_l2(bytes); return 0; }); }
 B200_API int b200_fwd_get_stream(b200_fwd *f, void **stream_out) { return guarded_dev(f, [&] { *stream_out = f->fwd->stream(); return 0; }); }

@@ -286,6 +286,9 @@ sk4_plan_t plan_sk4(conv_plan_t const &cp, int planes, int num_sms, b200_compute
 struct b200_impl_t {
   map<string, var_info_t> vars;
   map<string, func_t> funcs;
+  bool tail_gather_on = false;  // set_tail_gather
+  string tail_gather_vn;
+  b200_gather_desc_t tail_gather;
   // NHWC 16-bit planes of activation vars, shared by every Convolution that reads the same var (the four branches of an inception module, the
   // shortcut + first 1x1 of a ResNet block): the first consumer of a write generation packs, the others reuse. Keyed by the storage pointer.
   // (second key: 0 = plain NHWC [pixel][chan]; pad_tag(py, px) = the shared-padding layout a halo-mode convolution reads, igemm4.cuh)
@@ -691,6 +694,15 @@ bool b200_compute_t::conv_plane_writable(op_base_t const &op, bool dst_is_concat
   // producers of one Concat output would not agree on it, so those modes write planes for a convolution's own output node only
   if (prec != B200_PREC_BF16 && dst_is_concat) { return false; }
   return !cp.swapped && cp.splits == 1 && (cp.OC % 8) == 0;
+}
+bool b200_compute_t::set_tail_gather(string const &out_vn, b200_gather_desc_t const *d) {
+  impl->tail_gather_on = false;
+  if (!d) { return true; }
+  if (d->world < 1 || d->world > 8) { return false; }
+  impl->tail_gather = *d;
+  impl->tail_gather_vn = out_vn;
+  impl->tail_gather_on = true;
+  return true;
 }
 bool b200_compute_t::func_fc_chainable(string const &fn) const {
   auto fi = impl->funcs.find(fn);
@@ -1463,6 +1475,12 @@ struct run_ctx_t {
       vprev = &vout;
     }
     if (grid > im.num_sms) { unsup_err("fc_chain: more units than SMs"); }
+    if (im.tail_gather_on && rfc.arg_map.at("out" + str(nl - 1)).is_var() && rfc.arg_map.at("out" + str(nl - 1)).get_var() == im.tail_gather_vn) {
+      b200_gather_desc_t const &d = im.tail_gather;
+      if (d.bytes_per_rank != (uint64_t)prm.batch * prm.L[nl - 1].n_out * 4) { rt_err("fc_chain: the gather buffer's bytes per rank differ from the size of '" + im.tail_gather_vn + "'"); }
+      for (int r = 0; r < d.world; ++r) { prm.g.peer_base[r] = d.peer_base[r]; }
+      prm.g.local_base = d.local_base; prm.g.bytes_per_rank = d.bytes_per_rank; prm.g.flag_bytes = d.flag_bytes; prm.g.rank = d.rank; prm.g.world = d.world;
+    }
     if (!f.splitk_ws || f.splitk_ws->bytes < ws_need) { f.splitk_ws = std::make_shared<dev_buf_t>(ws_need); }
     prm.ws = static_cast<float *>(f.splitk_ws->p);
     long long *ts_dev = nullptr;

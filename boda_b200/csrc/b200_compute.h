@@ -12,6 +12,7 @@
 // B200 kernels pick their own geometry (as the culibs escape hatch does, src/nvrtc_util.cc:369-373).
 #pragma once
 #include "boda_base.h"
+#include "b200_shard.h"
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -144,6 +145,9 @@ struct b200_compute_t {
   // conv functions, each reading the previous one's output, can be one "fc_chain" function (fcchain.cuh): str parameter "layers" = their names
   // joined by ':'; call arguments "in", and per layer i "filts<i>", "biases<i>", "out<i>" (+ the abs-max cell arguments of "in" / "out<i>")
   bool func_fc_chainable(string const &fn) const;  // (of a compiled conv function)
+  // multi-GPU: an fc_chain call whose last layer writes the var `out_vn` also stores those values into every rank's gather buffer and publishes
+  // the step from inside its kernel (fcchain.cuh: FcGather). nullptr = off. Returns false when the descriptor does not fit (world > 8).
+  bool set_tail_gather(string const &out_vn, b200_gather_desc_t const *d);
   bool has_var(string const &vn) const;
   bool has_func(string const &fn) const;
   // host-only: the launch plan compile() made for a convolution function, as "kernel=pair|single bn=<N tile> kblks=<64-wide k-blocks>

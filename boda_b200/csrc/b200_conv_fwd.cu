@@ -725,6 +725,25 @@ void b200_conv_fwd_t::set_param_device(string const &node_name, void const *dev_
   warmed = false;
 }
 
+bool b200_conv_fwd_t::attach_gather(string const &node, b200_gather_desc_t const *d) {
+  bool ok = false;
+  if (d && !fwd_calls.empty() && fwd_calls.back().func_name.compare(0, 10, "fc_chain__") == 0) {
+    string last_out;
+    for (auto const &kv : fwd_calls.back().rfc.arg_map) {  // out<i> with the largest i
+      if (kv.first.compare(0, 3, "out") == 0 && kv.first.find('_') == string::npos && kv.second.is_var() && kv.first >= "out0") { last_out = kv.second.get_var(); }
+    }
+    if (last_out == node) { ok = rtc->set_tail_gather(node, d); }
+  }
+  if (!ok) { rtc->set_tail_gather(string(), nullptr); }
+  if (ok || gather_attached) {  // the last call's launch changes: capture again
+    if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+    if (graph) { cudaGraphDestroy(graph); graph = nullptr; }
+    warmed = false;
+  }
+  gather_attached = ok;
+  return ok;
+}
+
 void b200_conv_fwd_t::run_calls() {
   rtc->set_var_to_zero(absmax_cells_vn);  // one memset re-arms every abs-max cell for this forward
   for (auto const &c : fwd_calls) { rtc->run(c.rfc); }

@@ -93,6 +93,10 @@ struct b200_conv_fwd_t {
   // sync; flush_l2() queues an overwrite of a scratch buffer of `bytes`.
   void *stream() const { return (void *)rtc->stream(); }
   void enqueue_fwd();
+  // multi-GPU: let the forward's last call (an fc_chain ending in `node`) do the logits gather inside its kernel; false = not that shape (the caller
+  // keeps launching b200_shard_gather_push_wait). nullptr detaches. Either way the captured graph is dropped.
+  bool attach_gather(string const &node, b200_gather_desc_t const *d);
+  bool gather_attached = false;
   void flush_l2(uint64_t bytes);
   uint64_t launches() const { return rtc->launches() + graph_launches; }
   // The forward as planned at init, one line per item, for inspection and host-only tests (also on a plan_only=1 instance, which needs no

@@ -189,7 +189,7 @@ void b200_shard_t::gather_export(uint64_t bytes_per_rank, void *ipc_handle_out) 
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
   if (impl->local) { rt_err("b200_shard: gather buffer already allocated"); }
   if (bytes_per_rank == 0 || (bytes_per_rank & 15)) { rt_err("b200_shard: bytes_per_rank must be a positive multiple of 16"); }
-  if (static_cast<uint64_t>(world) * 4 > kFlagBytes) { rt_err("b200_shard: world too large for the flag block"); }
+  if (static_cast<uint64_t>(world) * 4 > 32 * 4) { rt_err("b200_shard: world too large for the flag block"); }  // (uint32 index 32 is the device-side step counter)
   SH_CHK(cudaSetDevice(device));
   uint64_t const total = kFlagBytes + 2 * static_cast<uint64_t>(world) * bytes_per_rank;
   SH_CHK(cudaMalloc(&impl->local, total));
@@ -248,5 +248,23 @@ uint32_t b200_shard_t::gather_push_wait(void const *dev_src, uint32_t wait_step,
 }
 void *b200_shard_t::gather_ptr(uint32_t step) const { return impl->local ? impl->local + kFlagBytes + static_cast<uint64_t>(step & 1u) * world * impl->bytes_per_rank : nullptr; }
 uint32_t b200_shard_t::step() const { return impl->step; }
+void b200_shard_t::gather_desc(b200_gather_desc_t &d) {
+  if (!impl->imported) { rt_err("b200_shard: gather_desc before gather_import"); }
+  SH_CHK(cudaSetDevice(device));
+  memset(&d, 0, sizeof(d));
+  for (int r = 0; r < world; ++r) { d.peer_base[r] = impl->peers.base[r]; }
+  d.local_base = impl->local;
+  d.bytes_per_rank = impl->bytes_per_rank;
+  d.flag_bytes = kFlagBytes;
+  d.rank = rank; d.world = world;
+  SH_CHK(cudaDeviceSynchronize());
+  SH_CHK(cudaMemcpy(impl->local + 32 * 4, &impl->step, 4, cudaMemcpyHostToDevice));  // device-side step counter := the host's
+}
+uint32_t b200_shard_t::step_from_device() {
+  SH_CHK(cudaSetDevice(device));
+  SH_CHK(cudaDeviceSynchronize());
+  SH_CHK(cudaMemcpy(&impl->step, impl->local + 32 * 4, 4, cudaMemcpyDeviceToHost));
+  return impl->step;
+}
 
 }  // namespace boda

@@ -7,6 +7,16 @@ namespace boda {
 
 struct b200_shard_impl_t;
 
+// What a kernel needs to do the gather itself (fcchain.cuh: the last layer's CTAs store the logits into every rank's buffer and the last CTA
+// publishes the step): the peer-mapped buffers, the local one, and where the counters live. `step_ctr` (device) holds the last step published
+// from this rank; a kernel that gathers reads it, publishes step_ctr + 1 and stores that back, so a CUDA graph can replay it.
+struct b200_gather_desc_t {
+  unsigned char *peer_base[16];
+  unsigned char *local_base;
+  uint64_t bytes_per_rank, flag_bytes;  // a buffer: [flag_bytes: uint32 step counters, one per rank; step_ctr at uint32 index 32][2 (step parity)][world][bytes_per_rank]
+  int rank, world;
+};
+
 struct b200_shard_t {
   int device, rank, world;
   uint64_t n_launches = 0;  // kernels of this module launched so far (claimed in bench.py's gpu_launches)
@@ -28,6 +38,9 @@ struct b200_shard_t {
   uint32_t gather_push_wait(void const *dev_src, uint32_t wait_step, void *stream);  // both in ONE launch (wait_step 0: push only); returns the step it published
   void *gather_ptr(uint32_t step) const;  // device pointer of the local [world][bytes_per_rank] result of `step` (two halves, by step parity)
   uint32_t step() const;
+  // in-kernel gather: the descriptor (also writes the host's step counter to the device-side one), and the way back (device -> host counter)
+  void gather_desc(b200_gather_desc_t &d);
+  uint32_t step_from_device();
 
   b200_shard_impl_t *impl;
 };

@@ -49,6 +49,16 @@ struct FcLayer {
   float *nxt_scale2;
 };
 
+// Multi-GPU: the last layer's logits go straight into every rank's gather buffer over NVLink (b200_shard.h: b200_gather_desc_t), from the CTAs
+// that reduce them; the last CTA to leave publishes the step to every peer and waits (bounded) until the previous step of every rank has
+// landed locally -- the compute and the collective are one kernel, and a CUDA graph can replay it (the step lives in device memory).
+struct FcGather {
+  unsigned char *peer_base[8];
+  unsigned char *local_base;
+  unsigned long long bytes_per_rank, flag_bytes;
+  int rank, world;  // world == 0: off
+};
+
 struct FcChainParams {
   int n_layers, batch, chunk_kblks, bf16;
   uint32_t idesc;
@@ -56,6 +66,7 @@ struct FcChainParams {
   float *ws;               // split-K partials, max over layers of splits * batch * n_out floats
   unsigned int *sync;      // FC_SYNC_WORDS counters, zero at kernel start (re-armed by the last CTA)
   int l2_ahead, l2_next;   // L2 prefetch of filter tiles: layer 0, this many k-blocks ahead of the ring (0 = off); next layer's tiles at the end of a layer
+  FcGather g;
   long long *ts;           // experiments (debug_flags bit 4): [CTA][32] globaltimer stamps (ns), see the FC_TS_* slots; null = off
   FcLayer L[FC_MAX_LAYERS];
 };
@@ -253,6 +264,19 @@ fc_chain_kernel(const __grid_constant__ FcChainMaps maps, const __grid_constant_
     int const row = q * 32 + lane;
     int cg = 0;
     float a_inv = 0.0f;  // 1 / scale of the current layer's activation planes
+    if (prm.g.world > 0 && u == 0 && row < prm.g.world) {
+      // one step late: the PREVIOUS step's logits of every rank have landed in the local gather buffer before this forward ends -- polled here,
+      // while these warps would only wait for the first accumulators (thread `row` watches rank `row`; bounded)
+      unsigned int const prev = *reinterpret_cast<volatile unsigned int const *>(prm.g.local_base + 32 * 4);  // = this launch's step - 1
+      unsigned int const *flag = reinterpret_cast<unsigned int const *>(prm.g.local_base) + row;
+      unsigned int v = 0, spins = 0;
+      while (prev > 0u) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (static_cast<int>(v - prev) >= 0) { break; }
+        __nanosleep(100);
+        if (++spins > (1u << 25)) { printf("b200: fc chain gather: rank %d never published step %u (have %u)\n", row, prev, v); __trap(); }
+      }
+    }
     int const gtid = u * 128 + row, gstride = static_cast<int>(gridDim.x) * 128;
     for (int l = 0; l < prm.n_layers; ++l) {
       int tile, split, kb_begin;
@@ -309,6 +333,12 @@ fc_chain_kernel(const __grid_constant__ FcChainMaps maps, const __grid_constant_
       // ---- reduce this CTA's slice over the splits, in split order (splitk_reduce_kernel's arithmetic) ----
       float amax = 0.0f;
       float const floor_v = L.relu ? 0.0f : -INFINITY;
+      bool const gather_here = prm.g.world > 0 && l + 1 == prm.n_layers;
+      unsigned long long g_off = 0;
+      if (gather_here) {  // slot [step parity][this rank] of a gather buffer; step = the device-side counter + 1 (same value in every CTA: only the last CTA to leave advances it)
+        unsigned int const step = *reinterpret_cast<volatile unsigned int const *>(prm.g.local_base + 32 * 4) + 1u;
+        g_off = prm.g.flag_bytes + (static_cast<unsigned long long>(step & 1u) * prm.g.world + prm.g.rank) * prm.g.bytes_per_rank;
+      }
       // (four consecutive outputs per thread, the loads of all splits in flight together: with one output per iteration the 8 iterations of a
       // thread were 8 dependent L2 round trips, 6.5 us per layer, r02 stamps. Host: n_out % 4 == 0.)
       for (int i4 = gtid; i4 * 4 < total; i4 += gstride) {
@@ -325,7 +355,16 @@ fc_chain_kernel(const __grid_constant__ FcChainMaps maps, const __grid_constant_
         }
         v.x = fmaxf(v.x, floor_v); v.y = fmaxf(v.y, floor_v); v.z = fmaxf(v.z, floor_v); v.w = fmaxf(v.w, floor_v);
         *reinterpret_cast<float4 *>(L.out + idx) = v;
+        if (gather_here) {
+#pragma unroll 1
+          for (int pr = 0; pr < prm.g.world; ++pr) { *reinterpret_cast<float4 *>(prm.g.peer_base[pr] + g_off + static_cast<unsigned long long>(idx) * 4ull) = v; }
+        }
         amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+      }
+      if (gather_here) {  // the CTA's stores into the peers' buffers are ordered (system scope, cumulative over the CTA barrier) before it counts itself out below
+        // (one fence per CTA: a system-scope fence in every one of the 16k epilogue threads cost ~10 us per step, r02)
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (row == 0) { __threadfence_system(); }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) { amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o)); }
@@ -379,6 +418,17 @@ fc_chain_kernel(const __grid_constant__ FcChainMaps maps, const __grid_constant_
     if (atomicAdd(prm.sync + 15, 1u) == gridDim.x - 1) {
       for (int i = 0; i < FC_SYNC_WORDS; ++i) { prm.sync[i] = 0u; }
       __threadfence();
+      if (prm.g.world > 0) {  // every CTA's logits are in every peer's buffer (each CTA fenced at system scope before it counted itself out): publish the step
+        unsigned int *ctr = reinterpret_cast<unsigned int *>(prm.g.local_base + 32 * 4);
+        unsigned int const step = *reinterpret_cast<volatile unsigned int *>(ctr) + 1u;
+        __threadfence_system();
+        for (int pr = 0; pr < prm.g.world; ++pr) {  // (one fence, then plain system-scope stores: a release per peer would repeat the fence)
+          unsigned int *flag = reinterpret_cast<unsigned int *>(prm.g.peer_base[pr]) + prm.g.rank;
+          asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(step) : "memory");
+        }
+        *ctr = step;
+        __threadfence();
+      }
     }
   }
 }

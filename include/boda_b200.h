@@ -173,6 +173,13 @@ int b200_shard_gather_wait(b200_shard *s, uint32_t step, void *stream);
 /* the per-step form: push this step's logits AND wait for `wait_step` (0 = none) in one launch (programmatic dependent launch: the launch and the
  * wait overlap the forward's tail); returns the published step */
 int64_t b200_shard_gather_push_wait(b200_shard *s, const void *dev_src, uint32_t wait_step, void *stream);
+/* Fused form: when the forward ends in an fc_chain call that writes `node_name` (AlexNet: fc8), that kernel stores the logits into every rank's
+ * gather buffer itself, publishes the step and waits for the previous one -- no gather launch at all, and the captured CUDA graph replays it
+ * (the step counter lives in device memory). Returns 1 when attached, 0 when this net does not end that way (keep calling
+ * b200_shard_gather_push_wait), negative on error; s == NULL detaches. After the last fused forward, b200_shard_step_from_device() returns the
+ * step it published (and re-synchronises the host-side counter that the separate push / wait calls use). */
+int b200_fwd_attach_gather(b200_fwd *f, b200_shard *s, const char *node_name);
+int64_t b200_shard_step_from_device(b200_shard *s);
 int b200_shard_gather_ptr(b200_shard *s, uint32_t step, void **dev_ptr_out); /* device pointer of the local [world][bytes_per_rank] result of `step` */
 int b200_shard_all_gather_nccl(b200_shard *s, const void *dev_src, void *dev_dst, uint64_t bytes_per_rank, void *stream);
 uint64_t b200_shard_launches(b200_shard *s);                          /* kernels this module has launched so far */
