@@ -15,7 +15,13 @@ A step = one whole-net forward of one batch (32 images per GPU) of synthetic NCH
             here: boost/protobuf/python2/Caffe missing) on all host cores, on a bounded sample of the same workload (>= 10 s of CPU
             work). `cpu_baseline.torch_cpu` adds SURVEY 8(d)'s second figure, torch's CPU operators (oneDNN), from a child process.
 Multi-GPU: images are independent units of the path, so ranks shard the batch dimension (weak scaling, 32 images per
-GPU); weights are broadcast once from rank 0 over NCCL at init and the logits are all-gathered over NCCL every step.
+GPU); weights are broadcast once from rank 0 over NCCL at init (b200_shard_broadcast) and every step's logits are gathered
+into every rank's peer-mapped buffer over NVLink, awaited one step late: inside the forward's last kernel when the net ends
+in an inner-product chain (b200_fwd_attach_gather), else with one gather launch per step (b200_shard_gather_push_wait).
+Each form is checked against the NCCL all-gather of the same data before it is timed. B200_BENCH_GATHER=peer_launch forces
+the one-launch form, =nccl the host-synchronised NCCL all-gather of round 1, =none times the loop without any gather (A/B only).
+Also run by default: `other_configs` (BASELINE C4 GoogLeNet B=64 bf16, C5 ResNet-50 B=32/GPU fp32) and a >= 2 s `sustained` run
+(N=1); --no-other-configs / --no-cpu-baseline skip them.
 """
 import argparse
 import ctypes
